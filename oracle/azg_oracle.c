@@ -1,0 +1,767 @@
+/*
+ * azg_oracle.c -- CPU restatement of the reference's self-play hot path (TEST INFRASTRUCTURE).
+ *
+ * This file is the parity checker and the CPU baseline. It is NOT on the product path:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load it. The product (alpha-zero-general_b200/csrc) never links or calls it.
+ *
+ * Pinned against the reference itself: tests/golden/*.npz are produced by
+ * oracle/gen_golden.py, which imports and runs the unmodified Python reference in the
+ * build container; tests/test_oracle_*.py check every function below against them.
+ *
+ * Each function cites the reference code it follows (paths relative to the reference root).
+ * Floating-point operation ORDER follows the machine code numba 0.65 / LLVM emits for the
+ * reference's @njit(fastmath=True) helpers on the build host (x86-64 AVX2+FMA), which is
+ * what produced the golden vectors:
+ *   pick_highest_UCB (MCTS.py:210-230):  c1 = cpuct*sqrt(Ns) hoisted;  visited  u = Q + (c1*P)/(1+N)
+ *                                        c0 = cpuct*sqrt(Ns+1e-8);     unvisited u = fma(c0, P, fpu_init)
+ *   normalise (MCTS.py:250-253):         float32 sum in 4x8-lane AVX2 order, then x *= (1/sum)
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef int8_t i8;
+typedef uint8_t u8;
+
+#define COLS 7
+#define NA 81            /* action_size(), splendor/SplendorLogicNumba.py:94-96 */
+#define MAXP 4
+#define MAXROWS 88       /* observation_size(4) = 32+40+16 rows */
+#define MAXS (MAXROWS * COLS)
+
+/* ---------------------------------------------------------------- game data ------------- */
+/* Card/noble data of the board game, restated from splendor/SplendorLogic.py:127-280 in a
+ * packed form: cost of colour k in nibble k (bits 4k..4k+3), points in bits 20..23.
+ * Index [deck colour][card index]; the deck colour index c yields a bonus of colour GAIN_COL[c]. */
+static const int GAIN_COL[5] = {1, 3, 4, 0, 2};
+static const uint32_t CARDS_T0[5][8] = {
+    {0x030000, 0x020001, 0x020200, 0x002201, 0x001310, 0x011101, 0x012101, 0x104000},
+    {0x000003, 0x000120, 0x002002, 0x020102, 0x031001, 0x010111, 0x010112, 0x100004},
+    {0x000300, 0x001200, 0x000202, 0x001022, 0x013100, 0x001111, 0x001121, 0x100040},
+    {0x000030, 0x012000, 0x020020, 0x010220, 0x010013, 0x011110, 0x011210, 0x100400},
+    {0x003000, 0x000012, 0x002020, 0x022010, 0x000131, 0x011011, 0x021011, 0x140000}};
+static const uint32_t CARDS_T1[5][6] = {
+    {0x103220, 0x130320, 0x200050, 0x200035, 0x241002, 0x300060},
+    {0x132002, 0x132030, 0x250000, 0x250003, 0x200241, 0x306000},
+    {0x100223, 0x120303, 0x200005, 0x203500, 0x202410, 0x360000},
+    {0x122300, 0x103032, 0x205000, 0x235000, 0x224100, 0x300006},
+    {0x120032, 0x103203, 0x200500, 0x200350, 0x210024, 0x300600}};
+static const uint32_t CARDS_T2[5][4] = {
+    {0x353303, 0x400007, 0x430036, 0x500037},
+    {0x330353, 0x400700, 0x403630, 0x503700},
+    {0x303533, 0x407000, 0x436300, 0x537000},
+    {0x335330, 0x470000, 0x463003, 0x570003},
+    {0x333035, 0x400070, 0x400363, 0x500370}};
+static const uint32_t NOBLES[10] = {0x304400, 0x344000, 0x300440, 0x340004, 0x300044,
+                                    0x333003, 0x300333, 0x333300, 0x303330, 0x330033};
+static const int DECK_SIZE[3] = {8, 6, 4};
+/* colour subsets in itertools.combinations order, sizes 1,2,3 (SplendorLogic.py:76-87); bit k = colour k */
+static const u8 GEMS3[25] = {1, 2, 4, 8, 16, 3, 5, 9, 17, 6, 10, 18, 12, 20, 24, 7, 11, 19, 13, 21, 25, 14, 22, 26, 28};
+static const u8 GEMS2[15] = {1, 2, 4, 8, 16, 3, 5, 9, 17, 6, 10, 18, 12, 20, 24};
+
+static uint32_t card_code(int tier, int colour, int idx) {
+    return tier == 0 ? CARDS_T0[colour][idx] : tier == 1 ? CARDS_T1[colour][idx] : CARDS_T2[colour][idx];
+}
+
+/* ---------------------------------------------------------------- RNG (oracle-own) ------ */
+typedef struct { uint64_t s[4]; } azo_rng;
+static uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static uint64_t splitmix64(uint64_t* x) {
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static void rng_seed(azo_rng* r, uint64_t seed) { for (int i = 0; i < 4; i++) r->s[i] = splitmix64(&seed); }
+static uint64_t rng_next(azo_rng* r) {
+    uint64_t* s = r->s; uint64_t res = rotl64(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl64(s[3], 45);
+    return res;
+}
+static double rng_uniform(azo_rng* r) { return (double)(rng_next(r) >> 11) * (1.0 / 9007199254740992.0); }
+static double rng_normal(azo_rng* r) {
+    double u1 = rng_uniform(r), u2 = rng_uniform(r);
+    if (u1 < 1e-300) u1 = 1e-300;
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
+static double rng_gamma(azo_rng* r, double a) { /* Marsaglia-Tsang */
+    if (a < 1.0) { double u = rng_uniform(r); if (u < 1e-300) u = 1e-300; return rng_gamma(r, a + 1.0) * pow(u, 1.0 / a); }
+    double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+        double x = rng_normal(r), v = 1.0 + c * x;
+        if (v <= 0) continue;
+        v = v * v * v;
+        double u = rng_uniform(r);
+        if (u < 1.0 - 0.0331 * x * x * x * x) return d * v;
+        if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return d * v;
+    }
+}
+
+/* ---------------------------------------------------------------- board layout ---------- */
+/* Row map: SplendorLogicNumba.py:207-219 (copy_state). */
+typedef struct { int n, nn, rows, r_nobles, r_pgems, r_pnobles, r_pcards, r_pres; } layout_t;
+static layout_t layout(int n) {
+    layout_t L; L.n = n; L.nn = n + 1; L.rows = 32 + 10 * n + n * n;
+    L.r_nobles = 31; L.r_pgems = 32 + n; L.r_pnobles = 32 + 2 * n; L.r_pcards = 32 + 3 * n + n * n; L.r_pres = 32 + 4 * n + n * n;
+    return L;
+}
+#define R_BANK 0
+#define R_CARDS 1
+#define R_DECK 25
+#define ROW(b, r) ((b) + (r) * COLS)
+
+int azo_state_rows(int n) { return 32 + 10 * n + n * n; }
+
+static int sum5(const i8* row) { return row[0] + row[1] + row[2] + row[3] + row[4]; }
+static int sum7(const i8* row) { return sum5(row) + row[5] + row[6]; }
+static void write_card(i8* rows2, int tier, int colour, int idx) {
+    uint32_t code = card_code(tier, colour, idx);
+    memset(rows2, 0, 2 * COLS);
+    for (int k = 0; k < 5; k++) rows2[k] = (i8)((code >> (4 * k)) & 15);
+    rows2[COLS + GAIN_COL[colour]] = 1;
+    rows2[COLS + 6] = (i8)((code >> 20) & 15);
+}
+
+/* SplendorLogicNumba.py:306-342 (_get_deck_card). Returns 0 if the deck is empty, else writes the
+ * 2-row card to `out`. seed==0: true random (colour ~ remaining count, then uniform among that
+ * colour's cards) drawn from `rng`; else the deterministic index (4594591*(seed+sum bits*32^c)) mod n. */
+static int get_deck_card(i8* b, int tier, int64_t seed, azo_rng* rng, i8* out) {
+    i8* cnt = ROW(b, R_DECK + 2 * tier);
+    i8* bits = ROW(b, R_DECK + 2 * tier + 1);
+    int total = sum5(cnt);
+    if (total == 0) return 0;
+    int colour = -1, idx = -1;
+    if (seed == 0) {
+        double r = rng_uniform(rng), acc = 0;
+        for (int c = 0; c < 5; c++) { acc += (double)cnt[c] / (double)total; if (acc > r) { colour = c; break; } }
+        if (colour < 0) for (int c = 4; c >= 0; c--) if (cnt[c] > 0) { colour = c; break; }
+        u8 f = (u8)bits[colour]; int nrem = __builtin_popcount(f);
+        double r2 = rng_uniform(rng); acc = 0;
+        for (int i = 0; i < 8; i++) if (f & (128 >> i)) { acc += 1.0 / nrem; idx = i; if (acc > r2) break; }
+    } else {
+        int lc[40], li[40], m = 0; int64_t s = 0, mul = 1;
+        for (int c = 0; c < 5; c++) {
+            u8 f = (u8)bits[c];
+            for (int i = 0; i < 8; i++) if (f & (128 >> i)) { lc[m] = c; li[m] = i; m++; }
+            s += (int64_t)f * mul; mul *= 32;
+        }
+        int64_t x = 4594591LL * (seed + s);
+        int64_t k = x % m; if (k < 0) k += m;          /* Python modulo */
+        colour = lc[k]; idx = li[k];
+    }
+    bits[colour] = (i8)((u8)bits[colour] & ~(128 >> idx));
+    cnt[colour] -= 1;
+    write_card(out, tier, colour, idx);
+    return 1;
+}
+
+/* SplendorLogicNumba.py:325-329 */
+static void fill_new_card(i8* b, int tier, int index, int64_t seed, azo_rng* rng) {
+    i8* slot = ROW(b, R_CARDS + 8 * tier + 2 * index);
+    i8 card[2 * COLS];
+    memset(slot, 0, 2 * COLS);
+    if (get_deck_card(b, tier, seed, rng, card)) memcpy(slot, card, 2 * COLS);
+}
+
+/* SplendorLogicNumba.py:151-178 (init_game); randomness from the oracle's own RNG (numba's MT19937
+ * stream is not reproducible outside numba -- parity tests use golden initial boards instead). */
+void azo_init_game(i8* b, int n, uint64_t seed) {
+    layout_t L = layout(n); azo_rng rng; rng_seed(&rng, seed);
+    memset(b, 0, L.rows * COLS);
+    int gems = n == 2 ? 4 : n == 3 ? 5 : 7;
+    for (int c = 0; c < 5; c++) ROW(b, R_BANK)[c] = (i8)gems;
+    ROW(b, R_BANK)[5] = 5;
+    for (int t = 0; t < 3; t++)
+        for (int c = 0; c < 5; c++) {
+            ROW(b, R_DECK + 2 * t)[c] = (i8)DECK_SIZE[t];
+            ROW(b, R_DECK + 2 * t + 1)[c] = (i8)(u8)(0xFF << (8 - DECK_SIZE[t]));
+        }
+    for (int t = 0; t < 3; t++) for (int i = 0; i < 4; i++) fill_new_card(b, t, i, 0, &rng);
+    int perm[10]; for (int i = 0; i < 10; i++) perm[i] = i;
+    for (int i = 0; i < L.nn; i++) {
+        int j = i + (int)(rng_uniform(&rng) * (10 - i)); if (j > 9) j = 9;
+        int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+        uint32_t code = NOBLES[perm[i]]; i8* row = ROW(b, L.r_nobles + i);
+        for (int k = 0; k < 5; k++) row[k] = (i8)((code >> (4 * k)) & 15);
+        row[6] = (i8)((code >> 20) & 15);
+    }
+}
+
+/* SplendorLogicNumba.py:303-304 */
+int azo_get_round(const i8* b) { return (u8)ROW(b, R_BANK)[6]; }
+
+/* SplendorLogicNumba.py:151-154 */
+int azo_get_score(const i8* b, int n, int player) {
+    layout_t L = layout(n); int s = ROW(b, L.r_pcards + player)[6];
+    for (int i = 0; i < L.nn; i++) s += ROW(b, L.r_pnobles + L.nn * player + i)[6];
+    return s;
+}
+
+static int can_buy(const i8* cost, const i8* pg, const i8* pc) {
+    int missing = 0;
+    for (int c = 0; c < 5; c++) { int d = (i8)(cost[c] - pg[c] - pc[c]); if (d > 0) missing += d; }
+    return missing <= pg[5] && sum5(cost) != 0;
+}
+
+/* SplendorLogicNumba.py:180-188 with _valid_buy :359-368, _valid_reserve :375-380, _valid_buy_reserve
+ * :402-412, _valid_get_gems(_identical) :422-434, _valid_give_gems(_identical) :443-453 */
+void azo_valid_moves(const i8* b, int n, int player, u8* out) {
+    layout_t L = layout(n);
+    const i8* bank = ROW(b, R_BANK); const i8* pg = ROW(b, L.r_pgems + player); const i8* pc = ROW(b, L.r_pcards + player);
+    const i8* res = ROW(b, L.r_pres + 6 * player);
+    for (int i = 0; i < 12; i++) out[i] = (u8)can_buy(ROW(b, R_CARDS + 2 * i), pg, pc);
+    int empty_slot = sum5(res + 5 * COLS) == 0;      /* gain row of the 3rd reserve slot */
+    for (int i = 0; i < 12; i++) out[12 + i] = (u8)(sum5(ROW(b, R_CARDS + 2 * i)) != 0 && empty_slot);
+    for (int t = 0; t < 3; t++) out[24 + t] = (u8)(sum5(ROW(b, R_DECK + 2 * t)) != 0 && empty_slot);
+    for (int i = 0; i < 3; i++) out[27 + i] = (u8)can_buy(res + 2 * i * COLS, pg, pc);
+    int have = sum7(pg);
+    for (int i = 0; i < 25; i++) {
+        int ok = 1, k = 0;
+        for (int c = 0; c < 5; c++) if (GEMS3[i] >> c & 1) { k++; if (bank[c] - 1 < 0) ok = 0; }
+        out[30 + i] = (u8)(ok && have + k <= 10);
+    }
+    for (int c = 0; c < 5; c++) out[55 + c] = (u8)(bank[c] >= 4 && have + 2 <= 10);
+    for (int i = 0; i < 15; i++) {
+        int ok = 1;
+        for (int c = 0; c < 5; c++) if ((GEMS2[i] >> c & 1) && pg[c] - 1 < 0) ok = 0;
+        out[60 + i] = (u8)ok;
+    }
+    for (int c = 0; c < 5; c++) out[75 + c] = (u8)(pg[c] >= 2);
+    out[80] = 1;
+}
+
+/* SplendorLogicNumba.py:465-470 */
+static void give_nobles(i8* b, const layout_t* L, int player) {
+    i8* pc = ROW(b, L->r_pcards + player);
+    for (int i = 0; i < L->nn; i++) {
+        i8* noble = ROW(b, L->r_nobles + i);
+        if (sum5(noble) <= 0) continue;
+        int ok = 1; for (int c = 0; c < 5; c++) if (pc[c] < noble[c]) ok = 0;
+        if (ok) { memcpy(ROW(b, L->r_pnobles + L->nn * player + i), noble, COLS); memset(noble, 0, COLS); }
+    }
+}
+
+/* SplendorLogicNumba.py:331-357 (_buy_card) */
+static void buy_card(i8* b, const layout_t* L, const i8* card0, const i8* card1, int player) {
+    i8* bank = ROW(b, R_BANK); i8* pg = ROW(b, L->r_pgems + player); i8* pc = ROW(b, L->r_pcards + player);
+    int missing = 0; i8 paid[5];
+    for (int c = 0; c < 5; c++) {
+        int d = (i8)(card0[c] - pg[c] - pc[c]); if (d > 0) missing += d;
+        int need = (i8)(card0[c] - pc[c]); if (need < 0) need = 0;
+        paid[c] = (i8)(need < pg[c] ? need : pg[c]);
+    }
+    for (int c = 0; c < 5; c++) { pg[c] -= paid[c]; bank[c] += paid[c]; }
+    pg[5] = (i8)(pg[5] - missing); bank[5] = (i8)(bank[5] + missing);
+    for (int c = 0; c < COLS; c++) pc[c] += card1[c];
+    give_nobles(b, L, player);
+}
+
+/* SplendorLogicNumba.py:190-205 (make_move) and the helpers it dispatches to:
+ * _buy :370-373, _reserve :382-400, _buy_reserve :414-420, _get_gems :436-441 area, _give_gems :455-463 */
+int azo_make_move(i8* b, int n, int move, int player, int64_t seed, azo_rng* rng) {
+    layout_t L = layout(n);
+    i8* bank = ROW(b, R_BANK); i8* pg = ROW(b, L.r_pgems + player);
+    i8 c0[COLS], c1[COLS];
+    if (move < 12) {
+        i8* card = ROW(b, R_CARDS + 2 * move);
+        memcpy(c0, card, COLS); memcpy(c1, card + COLS, COLS);
+        buy_card(b, &L, c0, c1, player);
+        fill_new_card(b, move / 4, move % 4, seed, rng);
+    } else if (move < 27) {
+        int i = move - 12; i8* res = ROW(b, L.r_pres + 6 * player); int slot = -1;
+        for (int k = 0; k < 3; k++) if (sum5(res + 2 * k * COLS) == 0) { slot = k; break; }
+        if (slot >= 0) {
+            if (i < 12) {
+                memcpy(res + 2 * slot * COLS, ROW(b, R_CARDS + 2 * i), 2 * COLS);
+                fill_new_card(b, i / 4, i % 4, seed, rng);
+            } else {
+                i8 card[2 * COLS];
+                if (get_deck_card(b, i - 12, seed, rng, card)) memcpy(res + 2 * slot * COLS, card, 2 * COLS);
+            }
+        }
+        if (bank[5] > 0 && sum7(pg) <= 9) { pg[5] += 1; bank[5] -= 1; }
+    } else if (move < 30) {
+        int i = move - 27; i8* res = ROW(b, L.r_pres + 6 * player); i8* card = res + 2 * i * COLS;
+        memcpy(c0, card, COLS); memcpy(c1, card + COLS, COLS);
+        buy_card(b, &L, c0, c1, player);
+        if (i < 2) memmove(card, card + 2 * COLS, (size_t)(2 - i) * 2 * COLS);
+        memset(res + 4 * COLS, 0, 2 * COLS);
+    } else if (move < 60) {
+        int i = move - 30;
+        if (i < 25) { for (int c = 0; c < 5; c++) if (GEMS3[i] >> c & 1) { bank[c] -= 1; pg[c] += 1; } }
+        else { bank[i - 25] -= 2; pg[i - 25] += 2; }
+    } else if (move < 80) {
+        int i = move - 60;
+        if (i < 15) { for (int c = 0; c < 5; c++) if (GEMS2[i] >> c & 1) { bank[c] += 1; pg[c] -= 1; } }
+        else { bank[i - 15] += 2; pg[i - 15] -= 2; }
+    }
+    bank[6] += 1;
+    return (player + 1) % n;
+}
+
+/* C-callable wrapper with an explicit RNG seed for the seed==0 (true random) case. */
+int azo_next_state(i8* b, int n, int move, int player, int64_t seed, uint64_t rng_seed_) {
+    azo_rng r; rng_seed(&r, rng_seed_);
+    return azo_make_move(b, n, move, player, seed, &r);
+}
+
+/* SplendorLogicNumba.py:221-240 (check_end_game) */
+void azo_check_end_game(const i8* b, int n, float* out) {
+    layout_t L = layout(n);
+    for (int p = 0; p < n; p++) out[p] = 0.f;
+    int round = azo_get_round(b);
+    if (round % n != 0) return;
+    float scores[MAXP], mx = -1e30f;
+    for (int p = 0; p < n; p++) { scores[p] = (float)azo_get_score(b, n, p); if (scores[p] > mx) mx = scores[p]; }
+    if (!(mx >= 15.f || round >= 62 * n)) return;
+    int winners = 0; for (int p = 0; p < n; p++) winners += scores[p] == mx;
+    int several = winners > 1;
+    if (several) {
+        for (int p = 0; p < n; p++) {
+            int cards = sum5(ROW(b, L.r_pcards + p));
+            scores[p] = (float)((double)scores[p] - (double)cards / 100.);
+        }
+        mx = -1e30f; for (int p = 0; p < n; p++) if (scores[p] > mx) mx = scores[p];
+        winners = 0; for (int p = 0; p < n; p++) winners += scores[p] == mx;
+        several = winners > 1;
+    }
+    for (int p = 0; p < n; p++) out[p] = scores[p] == mx ? (several ? 0.01f : 1.f) : -1.f;
+}
+
+/* SplendorLogicNumba.py:244-253 (swap_players): new[i] = old[(i+shift) % size] on 4 row groups */
+static void roll_rows(i8* base, int size, int shift) {
+    i8 tmp[MAXROWS * COLS];
+    memcpy(tmp, base, (size_t)size * COLS);
+    for (int i = 0; i < size; i++) memcpy(base + i * COLS, tmp + ((i + shift) % size) * COLS, COLS);
+}
+void azo_swap_players(i8* b, int n, int nb_swaps) {
+    layout_t L = layout(n);
+    roll_rows(ROW(b, L.r_pgems), n, nb_swaps);
+    roll_rows(ROW(b, L.r_pnobles), n * L.nn, L.nn * nb_swaps);
+    roll_rows(ROW(b, L.r_pcards), n, nb_swaps);
+    roll_rows(ROW(b, L.r_pres), 6 * n, 6 * nb_swaps);
+}
+
+/* SplendorLogicNumba.py:255-301 (get_symmetries). Writes up to 1+9+2n triples, returns the count. */
+static const int CARD_PERM[3][4] = {{1, 3, 0, 2}, {2, 0, 3, 1}, {3, 2, 1, 0}};
+static const int RES_PERM[4][2][3] = {{{-1, -1, -1}, {-1, -1, -1}}, {{-1, -1, -1}, {-1, -1, -1}},
+                                      {{1, 0, 2}, {-1, -1, -1}}, {{1, 2, 0}, {2, 0, 1}}};
+int azo_symmetries(const i8* b, int n, const float* pi, const u8* valids, i8* ob, float* opi, u8* ov) {
+    layout_t L = layout(n); int S = L.rows * COLS, k = 0;
+    memcpy(ob, b, S); memcpy(opi, pi, NA * sizeof(float)); memcpy(ov, valids, NA); k++;
+    for (int t = 0; t < 3; t++)
+        for (int q = 0; q < 3; q++) {
+            i8* o = ob + (size_t)k * S; float* p = opi + (size_t)k * NA; u8* v = ov + (size_t)k * NA;
+            memcpy(o, b, S); memcpy(p, pi, NA * sizeof(float)); memcpy(v, valids, NA);
+            for (int i = 0; i < 4; i++) {
+                int src = CARD_PERM[q][i];
+                memcpy(ROW(o, R_CARDS + 8 * t + 2 * i), ROW(b, R_CARDS + 8 * t + 2 * src), 2 * COLS);
+                p[4 * t + i] = pi[4 * t + src]; p[12 + 4 * t + i] = pi[12 + 4 * t + src];
+                v[4 * t + i] = valids[4 * t + src]; v[12 + 4 * t + i] = valids[12 + 4 * t + src];
+            }
+            k++;
+        }
+    for (int pl = 0; pl < n; pl++) {
+        const i8* res = ROW(b, L.r_pres + 6 * pl);
+        int nres = 3; for (int c = 0; c < 3; c++) if (sum5(res + 2 * c * COLS) == 0) { nres = c; break; }
+        for (int q = 0; q < 2; q++) {
+            if (RES_PERM[nres][q][0] < 0) continue;
+            i8* o = ob + (size_t)k * S; float* p = opi + (size_t)k * NA; u8* v = ov + (size_t)k * NA;
+            memcpy(o, b, S); memcpy(p, pi, NA * sizeof(float)); memcpy(v, valids, NA);
+            for (int i = 0; i < 3; i++) {
+                int src = RES_PERM[nres][q][i];
+                memcpy(ROW(o, L.r_pres + 6 * pl + 2 * i), res + 2 * src * COLS, 2 * COLS);
+                if (pl == 0) { p[27 + i] = pi[27 + src]; v[27 + i] = valids[27 + src]; }
+            }
+            k++;
+        }
+    }
+    return k;
+}
+
+/* ---------------------------------------------------------------- nets ------------------ */
+/* (1) hash-net: see oracle/hashnet.py (test-only deterministic prior/value). */
+static uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
+void azo_hashnet(const i8* b, int S, const u8* valids, int n, float* pi, float* v) {
+    uint32_t h = 0x811C9DC5u;
+    for (int i = 0; i < S; i++) h = (h ^ (u8)b[i]) * 16777619u;
+    int64_t w[NA], W = 0, ksum = 0, k[NA]; int best = -1; int64_t bw = -1;
+    for (int a = 0; a < NA; a++) {
+        w[a] = valids[a] ? 256 + (fmix32(h + (uint32_t)a * 0x9E3779B1u) & 1023) : 0;
+        W += w[a]; if (w[a] > bw) { bw = w[a]; best = a; }
+    }
+    for (int a = 0; a < NA; a++) { k[a] = (w[a] * 4096) / W; ksum += k[a]; }
+    k[best] += 4096 - ksum;
+    for (int a = 0; a < NA; a++) pi[a] = (float)k[a] / 4096.0f;
+    int j = (int)(fmix32(h ^ 0xABCDEF01u) % 129u) - 64;
+    float v0 = (float)j / 64.0f;
+    v[0] = v0; for (int p = 1; p < n; p++) v[p] = -v0 / (float)(n - 1);
+}
+
+/* (2) SplendorNNet version 80, eval mode (splendor/SplendorNNet.py:149-204,259-280,397-404,440).
+ * Weights arrive as one flat float32 blob in the tensor order listed in oracle/oracle.py:V80_ORDER. */
+typedef struct { const float *w, *g, *b, *m, *v; } lin_bn;
+typedef struct { lin_bn expand, dw, project; const float *fc1w, *fc1b, *fc2w, *fc2b; } irblock;
+typedef struct {
+    int nv;                 /* number of board rows (56 for 2 players) */
+    lin_bn first; irblock blk[3];
+    const float *pi2w, *pi2b, *pi4w, *pi4b, *v2w, *v2b, *v4w, *v4b;
+    int np;
+} v80_net;
+
+static const float* take(const float** p, size_t n) { const float* r = *p; *p += n; return r; }
+static lin_bn take_lin_bn(const float** p, int out, int in, int ch) {
+    lin_bn l; l.w = take(p, (size_t)out * in); l.g = take(p, ch); l.b = take(p, ch); l.m = take(p, ch); l.v = take(p, ch); return l;
+}
+static void v80_bind(v80_net* N, const float* blob, int nv, int np) {
+    const float* p = blob; int E = 3 * nv, Q = 40 * nv / 56; /* _make_divisible(168//4, 8) = 40 for nv=56 */
+    N->nv = nv; N->np = np;
+    N->first = take_lin_bn(&p, nv, nv, nv);
+    for (int k = 0; k < 3; k++) {
+        irblock* B = &N->blk[k];
+        B->expand = take_lin_bn(&p, E, nv, E);
+        B->dw = take_lin_bn(&p, 7, 7, E);
+        B->fc1w = take(&p, (size_t)Q * E); B->fc1b = take(&p, Q); B->fc2w = take(&p, (size_t)E * Q); B->fc2b = take(&p, E);
+        B->project = take_lin_bn(&p, nv, E, nv);
+    }
+    N->pi2w = take(&p, (size_t)NA * nv * 7); N->pi2b = take(&p, NA); N->pi4w = take(&p, NA * NA); N->pi4b = take(&p, NA);
+    N->v2w = take(&p, (size_t)np * nv * 7); N->v2b = take(&p, np); N->v4w = take(&p, (size_t)np * np); N->v4b = take(&p, np);
+}
+static float bn_apply(const lin_bn* l, int ch, float x) { return (x - l->m[ch]) / sqrtf(l->v[ch] + 1e-5f) * l->g[ch] + l->b[ch]; }
+static float relu6f(float x) { return x < 0 ? 0 : x > 6 ? 6 : x; }
+static float act(float x, int hs) { return hs ? x * relu6f(x + 3.f) / 6.f : (x > 0 ? x : 0); }
+
+/* token-axis linear + BN (+act): y[o][f] = act(bn_o(sum_i W[o][i] x[i][f]))  (LinearNormActivation, non-depthwise) */
+static void token_linear(const lin_bn* l, int out, int in, const float* x, float* y, int activation /*0 none,1 relu,2 hs*/) {
+    for (int o = 0; o < out; o++)
+        for (int f = 0; f < 7; f++) {
+            float s = 0; for (int i = 0; i < in; i++) s += l->w[o * in + i] * x[i * 7 + f];
+            s = bn_apply(l, o, s);
+            y[o * 7 + f] = activation == 0 ? s : act(s, activation == 2);
+        }
+}
+static void ir_block(const irblock* B, int nv, const float* x, float* y, int hs, int se_max) {
+    int E = 3 * nv, Q = 40 * nv / 56;
+    float e[3 * MAXROWS * 7], d[3 * MAXROWS * 7], sq[3 * MAXROWS], hid[64], sc[3 * MAXROWS], pr[MAXROWS * 7];
+    token_linear(&B->expand, E, nv, x, e, hs ? 2 : 1);
+    for (int c = 0; c < E; c++)                                  /* "depthwise": shared Linear(7->7) on the feature axis, BN per channel */
+        for (int g = 0; g < 7; g++) {
+            float s = 0; for (int f = 0; f < 7; f++) s += B->dw.w[g * 7 + f] * e[c * 7 + f];
+            d[c * 7 + g] = act(bn_apply(&B->dw, c, s), hs);
+        }
+    for (int c = 0; c < E; c++) {                                /* squeeze: avg (trunk) or max (heads) over the 7 features */
+        float s = se_max ? -1e30f : 0.f;
+        for (int f = 0; f < 7; f++) s = se_max ? (d[c * 7 + f] > s ? d[c * 7 + f] : s) : s + d[c * 7 + f];
+        sq[c] = se_max ? s : s / 7.f;
+    }
+    for (int q = 0; q < Q; q++) { float s = B->fc1b[q]; for (int c = 0; c < E; c++) s += B->fc1w[q * E + c] * sq[c]; hid[q] = s > 0 ? s : 0; }
+    for (int c = 0; c < E; c++) { float s = B->fc2b[c]; for (int q = 0; q < Q; q++) s += B->fc2w[c * Q + q] * hid[q]; sc[c] = relu6f(s + 3.f) / 6.f; }
+    for (int c = 0; c < E; c++) for (int f = 0; f < 7; f++) d[c * 7 + f] *= sc[c];
+    token_linear(&B->project, nv, E, d, pr, 0);
+    for (int i = 0; i < nv * 7; i++) y[i] = pr[i] + x[i];
+}
+static void v80_forward(const v80_net* N, const i8* board, const u8* valids, float* pi, float* v) {
+    int nv = N->nv, F = nv * 7;
+    float x[MAXROWS * 7], x0[MAXROWS * 7], t[MAXROWS * 7], hp[MAXROWS * 7], hv[MAXROWS * 7], h1[NA], logit[NA], hv1[MAXP];
+    for (int i = 0; i < F; i++) x[i] = (float)board[i];
+    token_linear(&N->first, nv, nv, x, x0, 0);
+    ir_block(&N->blk[0], nv, x0, t, 0, 0);
+    ir_block(&N->blk[1], nv, t, hp, 1, 1);
+    ir_block(&N->blk[2], nv, t, hv, 1, 1);
+    for (int o = 0; o < NA; o++) { float s = N->pi2b[o]; for (int i = 0; i < F; i++) s += N->pi2w[o * F + i] * hp[i]; h1[o] = s > 0 ? s : 0; }
+    float mx = -INFINITY;
+    for (int o = 0; o < NA; o++) {
+        float s = N->pi4b[o]; for (int i = 0; i < NA; i++) s += N->pi4w[o * NA + i] * h1[i];
+        logit[o] = valids[o] ? s : -1e8f; if (logit[o] > mx) mx = logit[o];
+    }
+    float se = 0; for (int o = 0; o < NA; o++) se += expf(logit[o] - mx);
+    float lse = logf(se);
+    for (int o = 0; o < NA; o++) pi[o] = expf(logit[o] - mx - lse);   /* exp(log_softmax), GenericNNetWrapper.py:119 */
+    for (int p = 0; p < N->np; p++) { float s = N->v2b[p]; for (int i = 0; i < F; i++) s += N->v2w[p * F + i] * hv[i]; hv1[p] = s > 0 ? s : 0; }
+    for (int p = 0; p < N->np; p++) { float s = N->v4b[p]; for (int q = 0; q < N->np; q++) s += N->v4w[p * N->np + q] * hv1[q]; v[p] = tanhf(s); }
+}
+void azo_v80_forward(const float* blob, int n_players, int batch, const i8* boards, const u8* valids, float* pi, float* v) {
+    v80_net N; int nv = azo_state_rows(n_players); v80_bind(&N, blob, nv, n_players);
+    for (int b = 0; b < batch; b++) v80_forward(&N, boards + (size_t)b * nv * 7, valids + (size_t)b * NA, pi + (size_t)b * NA, v + (size_t)b * n_players);
+}
+
+/* ---------------------------------------------------------------- MCTS ------------------ */
+#define NAN_Q (-42.0)
+static const int64_t MAGIC_SEEDS[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   /* MCTS.py:14 */
+
+typedef struct {
+    int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80*/;
+    double cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2;
+} azo_cfg;
+
+typedef struct node {
+    i8 key[MAXS];
+    int has_es, expanded, r; float Es[MAXP];
+    u8 Vs[NA]; float Ps[NA]; int64_t Ns; double Qsa[NA]; int64_t Nsa[NA]; float Qs;
+    int used;
+} node_t;
+
+typedef struct {
+    azo_cfg cfg; int S; v80_net net; const float* blob;
+    node_t* nodes; int* table; int cap, tcap, count;
+    int dirichlet_noise, step, last_cleaning; int64_t random_seed;
+    azo_rng rng;
+    /* counters */
+    int64_t n_sims, n_expansions, n_node_visits, n_nn_evals;
+} azo_mcts;
+
+static uint64_t key_hash(const i8* k, int S) { uint64_t h = 1469598103934665603ULL; for (int i = 0; i < S; i++) h = (h ^ (u8)k[i]) * 1099511628211ULL; return h; }
+static void table_rebuild(azo_mcts* m) {
+    for (int i = 0; i < m->tcap; i++) m->table[i] = -1;
+    for (int i = 0; i < m->count; i++) { uint64_t h = key_hash(m->nodes[i].key, m->S) & (uint64_t)(m->tcap - 1); while (m->table[h] >= 0) h = (h + 1) & (uint64_t)(m->tcap - 1); m->table[h] = i; }
+}
+static void grow(azo_mcts* m) {
+    m->cap *= 2; m->tcap *= 2;
+    m->nodes = (node_t*)realloc(m->nodes, sizeof(node_t) * (size_t)m->cap);
+    m->table = (int*)realloc(m->table, sizeof(int) * (size_t)m->tcap);
+    table_rebuild(m);
+}
+static node_t* lookup(azo_mcts* m, const i8* key) {
+    uint64_t h = key_hash(key, m->S) & (uint64_t)(m->tcap - 1);
+    while (m->table[h] >= 0) { node_t* nd = &m->nodes[m->table[h]]; if (memcmp(nd->key, key, (size_t)m->S) == 0) return nd; h = (h + 1) & (uint64_t)(m->tcap - 1); }
+    return NULL;
+}
+static node_t* insert(azo_mcts* m, const i8* key) {
+    if (m->count + 1 > m->cap) grow(m);
+    node_t* nd = &m->nodes[m->count]; memset(nd, 0, sizeof(*nd)); memcpy(nd->key, key, (size_t)m->S);
+    uint64_t h = key_hash(key, m->S) & (uint64_t)(m->tcap - 1); while (m->table[h] >= 0) h = (h + 1) & (uint64_t)(m->tcap - 1);
+    m->table[h] = m->count++; return nd;
+}
+
+azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_noise, uint64_t seed) {
+    azo_mcts* m = (azo_mcts*)calloc(1, sizeof(azo_mcts));
+    m->cfg = *cfg; m->S = azo_state_rows(cfg->num_players) * COLS; m->blob = blob;
+    if (cfg->net_kind == 1) v80_bind(&m->net, blob, azo_state_rows(cfg->num_players), cfg->num_players);
+    m->cap = 4096; m->tcap = 16384; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
+    m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed);
+    return m;
+}
+void azo_mcts_free(azo_mcts* m) { if (m) { free(m->nodes); free(m->table); free(m); } }
+void azo_mcts_reset(azo_mcts* m) { m->count = 0; m->last_cleaning = 0; table_rebuild(m); }
+void azo_mcts_stats(const azo_mcts* m, int64_t* out) {
+    int64_t nt = 0, sns = 0;
+    for (int i = 0; i < m->count; i++) { if (!m->nodes[i].expanded) nt++; else sns += m->nodes[i].Ns; }
+    out[0] = m->count; out[1] = nt; out[2] = sns; out[3] = m->n_sims; out[4] = m->n_expansions; out[5] = m->n_node_visits; out[6] = m->n_nn_evals;
+}
+
+/* float32 sum in the order numba's vectorised np.sum uses on the build host (see file header) */
+static float sum_f32_avx2(const float* x, int n) {
+    float s = 0.f; int i = 0;
+    if (n >= 32) {
+        float acc[32]; for (int j = 0; j < 32; j++) acc[j] = 0.f;
+        int nb = n / 32;
+        for (int b = 0; b < nb; b++) for (int j = 0; j < 32; j++) acc[j] = acc[j] + x[32 * b + j];
+        float t[8], u[4];
+        for (int j = 0; j < 8; j++) t[j] = (acc[8 + j] + acc[j]) + (acc[16 + j] + acc[24 + j]);
+        for (int j = 0; j < 4; j++) u[j] = t[j + 4] + t[j];
+        s = (u[0] + u[2]) + (u[1] + u[3]);
+        i = 32 * nb;
+    }
+    if ((n & 28) != 0 && (n & ~3) > i) {
+        float q0 = s, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        for (; i < (n & ~3); i += 4) { q0 += x[i]; q1 += x[i + 1]; q2 += x[i + 2]; q3 += x[i + 3]; }
+        s = (q0 + q2) + (q1 + q3);
+    }
+    for (; i < n; i++) s += x[i];
+    return s;
+}
+/* MCTS.py:250-253 */
+static void normalise_f32(float* x, int n) { float inv = 1.0f / sum_f32_avx2(x, n); for (int i = 0; i < n; i++) x[i] = x[i] * inv; }
+/* MCTS.py:255-261 */
+static void softmax_temp(float* P, int n, double T) {
+    if (T == 1.0) return;
+    double r[NA], s = 0; for (int i = 0; i < n; i++) { r[i] = pow((double)P[i], 1.0 / T); s += r[i]; }
+    double inv = 1.0 / s; for (int i = 0; i < n; i++) P[i] = (float)(r[i] * inv);
+}
+/* MCTS.py:187-197; `noise` (length = number of legal actions) is either injected by the caller
+ * (parity tests replay the reference's draws) or sampled here. */
+static void apply_dir_noise(azo_mcts* m, float* P, const u8* Vs, const double* noise) {
+    int L = 0; for (int a = 0; a < NA; a++) L += Vs[a] != 0;
+    double tmp[NA];
+    if (!noise) {
+        double alpha = m->cfg.dirichletAlpha > 0 ? m->cfg.dirichletAlpha : 10.0 / L, s = 0;
+        for (int i = 0; i < L; i++) { tmp[i] = rng_gamma(&m->rng, alpha); s += tmp[i]; }
+        for (int i = 0; i < L; i++) tmp[i] /= s;
+        noise = tmp;
+    }
+    int k = 0;
+    for (int a = 0; a < NA; a++) if (Vs[a]) { float t1 = 0.75f * P[a]; P[a] = (float)((double)t1 + 0.25 * noise[k]); k++; }
+}
+
+/* MCTS.py:210-230 */
+static int pick_highest_ucb(const node_t* nd, double cpuct, int forced, int64_t n_iter, double fpu) {
+    double best = -INFINITY; int best_a = -1;
+    double fpu_init = fpu > 0 ? (double)nd->Qs - fpu : fpu;
+    double c0 = cpuct * sqrt((double)nd->Ns + 1e-8), c1 = cpuct * sqrt((double)nd->Ns), kn = (double)n_iter * 0.5;
+    for (int a = 0; a < NA; a++) {
+        if (!nd->Vs[a]) continue;
+        if (forced && nd->Nsa[a] < (int64_t)sqrt(kn * (double)nd->Ps[a])) return a;
+        double u;
+        if (nd->Qsa[a] != NAN_Q) u = nd->Qsa[a] + (c1 * (double)nd->Ps[a]) / (double)(nd->Nsa[a] + 1);
+        else u = fma(c0, (double)nd->Ps[a], fpu_init);
+        if (u > best) { best = u; best_a = a; }
+    }
+    return best_a;
+}
+
+/* MCTS.py:105-184 (search), unrolled from recursion into select / leaf / backup. */
+static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const double* noise) {
+    int n = m->cfg.num_players, S = m->S, depth = 0;
+    static __thread node_t* path_node[256]; static __thread int path_a[256], path_np[256];
+    i8 cur[MAXS]; memcpy(cur, root, (size_t)S);
+    float v[MAXP];
+    azo_rng dummy; rng_seed(&dummy, 1);
+    m->n_sims++;
+    for (;;) {
+        node_t* nd = lookup(m, cur);
+        if (!nd || !nd->has_es) {
+            float Es[MAXP]; azo_check_end_game(cur, n, Es);
+            int any = 0; for (int p = 0; p < n; p++) any |= Es[p] != 0.f;
+            if (!nd) { nd = insert(m, cur); nd->r = azo_get_round(cur); }
+            nd->has_es = 1; memcpy(nd->Es, Es, sizeof(float) * (size_t)n);
+            if (any) { memcpy(v, Es, sizeof(float) * (size_t)n); break; }
+        } else {
+            int any = 0; for (int p = 0; p < n; p++) any |= nd->Es[p] != 0.f;
+            if (any) { memcpy(v, nd->Es, sizeof(float) * (size_t)n); break; }
+        }
+        if (!nd->expanded) {
+            azo_valid_moves(cur, n, 0, nd->Vs);
+            if (m->cfg.net_kind == 0) azo_hashnet(cur, S, nd->Vs, n, nd->Ps, v); else v80_forward(&m->net, cur, nd->Vs, nd->Ps, v);
+            m->n_nn_evals++; m->n_expansions++;
+            if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, NA, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); }
+            normalise_f32(nd->Ps, NA);
+            nd->Ns = 0; for (int a = 0; a < NA; a++) { nd->Qsa[a] = NAN_Q; nd->Nsa[a] = 0; }
+            nd->Qs = v[0]; nd->expanded = 1;
+            break;
+        }
+        if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, NA, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); normalise_f32(nd->Ps, NA); }
+        int a = pick_highest_ucb(nd, m->cfg.cpuct, depth == 0 && forced, m->step, m->cfg.fpu);
+        m->n_node_visits++;
+        int np_ = azo_make_move(cur, n, a, 0, m->random_seed, &dummy);     /* MCTS.py:233-248 */
+        if (np_ != 0) azo_swap_players(cur, n, np_);
+        path_node[depth] = nd; path_a[depth] = a; path_np[depth] = np_; depth++;
+    }
+    for (int d = depth - 1; d >= 0; d--) {
+        float t[MAXP]; for (int p = 0; p < n; p++) t[(p + path_np[d]) % n] = v[p];       /* np.roll(v, next_player) */
+        memcpy(v, t, sizeof(float) * (size_t)n);
+        node_t* nd = path_node[d]; int a = path_a[d];
+        nd->Qsa[a] = ((double)nd->Nsa[a] * nd->Qsa[a] + (double)v[0]) / (double)(nd->Nsa[a] + 1);
+        nd->Qs = ((float)(nd->Ns + 1) * nd->Qs + v[0]) / (float)(nd->Ns + 2);
+        nd->Nsa[a] += 1; nd->Ns += 1;
+    }
+}
+
+/* MCTS.py:49-103 (getActionProb). noise: injected Dirichlet vector or NULL. Outputs: probs f64[A], q f32[np],
+ * raw_counts i64[A] (root Nsa before policy-target pruning). Returns is_full_search. */
+int azo_mcts_get_action_prob(azo_mcts* m, const i8* cb, double temp, int force_full, const double* noise,
+                             double* probs, float* q, int64_t* raw_counts) {
+    const azo_cfg* c = &m->cfg; int n = c->num_players;
+    int full = force_full || (rng_uniform(&m->rng) < c->prob_fullMCTS);
+    int nsims = full ? c->numMCTSSims : c->numMCTSSims / c->ratio_fullMCTS;
+    int forced = full && c->forced_playouts;
+    for (m->step = 0; m->step < nsims; m->step++) {
+        m->random_seed = c->universes > 0 ? MAGIC_SEEDS[m->step % c->universes] : -1;
+        search(m, cb, m->step == 0 && full && m->dirichlet_noise, forced, noise);
+    }
+    if (nsims > 0) m->step = nsims - 1;
+    node_t* root = lookup(m, cb);
+    double counts[NA];
+    for (int a = 0; a < NA; a++) { counts[a] = (double)root->Nsa[a]; if (raw_counts) raw_counts[a] = root->Nsa[a]; }
+    q[0] = root->Qs; for (int p = 1; p < n; p++) q[p] = -root->Qs / (float)(n - 1);
+    if (forced) {
+        double best = 0; for (int a = 0; a < NA; a++) if (counts[a] > best) best = counts[a];
+        for (int a = 0; a < NA; a++) {
+            double cnt = counts[a];
+            if (cnt != best) { float t = 0.5f * root->Ps[a]; t = t * (float)nsims; cnt = cnt - (double)(int64_t)sqrt((double)t); }
+            counts[a] = cnt > 1 ? cnt : 0;
+        }
+    }
+    if (!c->no_mem_optim) {                                                /* MCTS.py:86-91 */
+        int r = azo_get_round(cb);
+        if (r > m->last_cleaning + 20) {
+            int w = 0;
+            for (int i = 0; i < m->count; i++) if (!(m->nodes[i].r < r - 5)) { if (w != i) m->nodes[w] = m->nodes[i]; w++; }
+            m->count = w; table_rebuild(m); m->last_cleaning = r;
+        }
+    }
+    if (temp <= 0.02) {
+        double best = -1; int nb = 0; for (int a = 0; a < NA; a++) { if (counts[a] > best) { best = counts[a]; nb = 1; } else if (counts[a] == best) nb++; }
+        int pick = (int)(rng_uniform(&m->rng) * nb), k = 0; if (pick >= nb) pick = nb - 1;
+        for (int a = 0; a < NA; a++) { probs[a] = 0; if (counts[a] == best) { if (k == pick) probs[a] = 1; k++; } }
+        return full;
+    }
+    double s = 0; for (int a = 0; a < NA; a++) { counts[a] = pow(counts[a], 1.0 / temp); s += counts[a]; }
+    for (int a = 0; a < NA; a++) probs[a] = counts[a] / s;
+    return full;
+}
+
+/* ---------------------------------------------------------------- episode (Coach.py:37-84) */
+typedef struct { int64_t sims, expansions, node_visits, nn_evals, plies, examples, games; double seconds; } azo_run_stats;
+
+static double temp_for_selfplay(double t_begin, double t_end, double half_life, int n) {   /* Coach.py:266-271 */
+    if (half_life < 0) return n > -half_life ? t_end : t_begin;
+    return t_end + (t_begin - t_end) * pow(0.5, n / half_life);
+}
+
+/* One self-play game. Example boards/policies are only counted (the CPU baseline measures search
+ * throughput); `max_plies` > 0 truncates the game (bounded sample for bench.py). */
+static void execute_episode(azo_mcts* m, uint64_t seed, double t0, double t1, double half, int max_plies, azo_run_stats* st) {
+    int n = m->cfg.num_players, S = m->S; azo_rng rng; rng_seed(&rng, seed ^ 0xA5A5A5A5ULL);
+    i8 board[MAXS], cb[MAXS]; azo_init_game(board, n, seed);
+    int player = 0, step = 0; azo_mcts_reset(m);
+    double probs[NA]; float q[MAXP], r[MAXP];
+    for (;;) {
+        step++;
+        memcpy(cb, board, (size_t)S); if (player) azo_swap_players(cb, n, player);
+        int64_t before = m->n_sims;
+        int full = azo_mcts_get_action_prob(m, cb, 1.0, 0, NULL, probs, q, NULL);
+        (void)before;
+        double T = temp_for_selfplay(t0, t1, half, step), w[NA], s = 0;
+        int action = 80;
+        if (T == 0) { double b = -1; for (int a = 0; a < NA; a++) if (probs[a] > b) { b = probs[a]; action = a; } }
+        else {
+            for (int a = 0; a < NA; a++) { w[a] = pow(probs[a], 1.0 / T); s += w[a]; }
+            double u = rng_uniform(&rng) * s, acc = 0;
+            for (int a = 0; a < NA; a++) { acc += w[a]; if (w[a] > 0 && acc > u) { action = a; break; } }
+        }
+        if (full) { u8 V[NA]; azo_valid_moves(cb, n, 0, V); st->examples += 1; }
+        player = azo_make_move(board, n, action, player, 0, &rng);
+        st->plies++;
+        azo_check_end_game(board, n, r);
+        int any = 0; for (int p = 0; p < n; p++) any |= r[p] != 0.f;
+        if (any || (max_plies > 0 && step >= max_plies)) break;
+    }
+    st->games++;
+}
+
+typedef struct { azo_cfg cfg; const float* blob; int games, max_plies; uint64_t seed; double t0, t1, half; azo_run_stats st; } worker_t;
+static void* worker(void* arg) {
+    worker_t* w = (worker_t*)arg;
+    azo_mcts* m = azo_mcts_new(&w->cfg, w->blob, w->cfg.dirichletAlpha != 0, w->seed);
+    for (int g = 0; g < w->games; g++) execute_episode(m, w->seed * 1000003ULL + (uint64_t)g, w->t0, w->t1, w->half, w->max_plies, &w->st);
+    w->st.sims = m->n_sims; w->st.expansions = m->n_expansions; w->st.node_visits = m->n_node_visits; w->st.nn_evals = m->n_nn_evals;
+    azo_mcts_free(m); return NULL;
+}
+/* CPU baseline: `threads` independent workers (the author's own scaling method is independent
+ * processes, README.md:175-176), each playing `games_per_thread` self-play games. out[8]. */
+void azo_selfplay_bench(const azo_cfg* cfg, const float* blob, int threads, int games_per_thread, int max_plies,
+                        double t_begin, double t_end, double half_life, uint64_t seed, double* out) {
+    worker_t* ws = (worker_t*)calloc((size_t)threads, sizeof(worker_t)); pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    struct timespec a, b; clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int i = 0; i < threads; i++) { ws[i].cfg = *cfg; ws[i].blob = blob; ws[i].games = games_per_thread; ws[i].max_plies = max_plies; ws[i].seed = seed + (uint64_t)i; ws[i].t0 = t_begin; ws[i].t1 = t_end; ws[i].half = half_life; pthread_create(&th[i], NULL, worker, &ws[i]); }
+    for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    double secs = (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+    for (int k = 0; k < 8; k++) out[k] = 0;
+    for (int i = 0; i < threads; i++) { out[0] += (double)ws[i].st.sims; out[1] += (double)ws[i].st.expansions; out[2] += (double)ws[i].st.node_visits; out[3] += (double)ws[i].st.nn_evals; out[4] += (double)ws[i].st.plies; out[5] += (double)ws[i].st.examples; out[6] += (double)ws[i].st.games; }
+    out[7] = secs; free(ws); free(th);
+}

@@ -1,0 +1,192 @@
+"""ctypes front-end of the CPU oracle (oracle/azg_oracle.c). TEST INFRASTRUCTURE ONLY.
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+NA = 81
+
+# state_dict tensor order expected by azg_oracle.c:v80_bind (names as in splendor/SplendorNNet.py V80)
+def _lin_bn(prefix):
+    return [f'{prefix}.linear.weight', f'{prefix}.norm.weight', f'{prefix}.norm.bias',
+            f'{prefix}.norm.running_mean', f'{prefix}.norm.running_var']
+
+
+def v80_order():
+    names = _lin_bn('first_layer')
+    for blk in ('trunk.0', 'output_layers_PI.0', 'output_layers_V.0'):
+        names += _lin_bn(f'{blk}.expand') + _lin_bn(f'{blk}.depthwise')
+        names += [f'{blk}.se.fc1.weight', f'{blk}.se.fc1.bias', f'{blk}.se.fc2.weight', f'{blk}.se.fc2.bias']
+        names += _lin_bn(f'{blk}.project')
+    names += ['output_layers_PI.2.weight', 'output_layers_PI.2.bias', 'output_layers_PI.4.weight', 'output_layers_PI.4.bias',
+              'output_layers_V.2.weight', 'output_layers_V.2.bias', 'output_layers_V.4.weight', 'output_layers_V.4.bias']
+    return names
+
+
+def v80_blob(state_dict):
+    """Flatten a V80 state_dict (name -> ndarray) into the oracle's float32 blob."""
+    return np.concatenate([np.asarray(state_dict[n], dtype=np.float32).ravel() for n in v80_order()]).astype(np.float32)
+
+
+def build(force=False):
+    so = os.path.join(HERE, 'libazg_oracle.so')
+    src = os.path.join(HERE, 'azg_oracle.c')
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(['make', '-C', HERE, '-s', '-B', 'libazg_oracle.so'])
+    return so
+
+
+class Cfg(C.Structure):
+    _fields_ = [('num_players', C.c_int), ('numMCTSSims', C.c_int), ('ratio_fullMCTS', C.c_int), ('universes', C.c_int),
+                ('forced_playouts', C.c_int), ('no_mem_optim', C.c_int), ('net_kind', C.c_int),
+                ('cpuct', C.c_double), ('fpu', C.c_double), ('dirichletAlpha', C.c_double), ('prob_fullMCTS', C.c_double),
+                ('temperature2', C.c_double)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        p8, pu8, pf, pd, pi64 = (C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int64))
+        L.azo_init_game.argtypes = [p8, C.c_int, C.c_uint64]
+        L.azo_get_round.argtypes = [p8]; L.azo_get_round.restype = C.c_int
+        L.azo_get_score.argtypes = [p8, C.c_int, C.c_int]; L.azo_get_score.restype = C.c_int
+        L.azo_valid_moves.argtypes = [p8, C.c_int, C.c_int, pu8]
+        L.azo_next_state.argtypes = [p8, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64]; L.azo_next_state.restype = C.c_int
+        L.azo_check_end_game.argtypes = [p8, C.c_int, pf]
+        L.azo_swap_players.argtypes = [p8, C.c_int, C.c_int]
+        L.azo_symmetries.argtypes = [p8, C.c_int, pf, pu8, p8, pf, pu8]; L.azo_symmetries.restype = C.c_int
+        L.azo_hashnet.argtypes = [p8, C.c_int, pu8, C.c_int, pf, pf]
+        L.azo_v80_forward.argtypes = [pf, C.c_int, C.c_int, p8, pu8, pf, pf]
+        L.azo_mcts_new.argtypes = [C.POINTER(Cfg), pf, C.c_int, C.c_uint64]; L.azo_mcts_new.restype = C.c_void_p
+        L.azo_mcts_free.argtypes = [C.c_void_p]
+        L.azo_mcts_reset.argtypes = [C.c_void_p]
+        L.azo_mcts_stats.argtypes = [C.c_void_p, pi64]
+        L.azo_mcts_get_action_prob.argtypes = [C.c_void_p, p8, C.c_double, C.c_int, pd, pd, pf, pi64]; L.azo_mcts_get_action_prob.restype = C.c_int
+        L.azo_selfplay_bench.argtypes = [C.POINTER(Cfg), pf, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, pd]
+        _LIB = L
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _board(b):
+    return np.ascontiguousarray(b, dtype=np.int8).copy()
+
+
+def init_game(seed, n=2):
+    b = np.zeros((32 + 10 * n + n * n, 7), np.int8)
+    lib().azo_init_game(_p(b, C.c_int8), n, seed)
+    return b
+
+
+def valid_moves(board, player=0, n=2):
+    b = _board(board); out = np.zeros(NA, np.uint8)
+    lib().azo_valid_moves(_p(b, C.c_int8), n, player, _p(out, C.c_uint8))
+    return out.astype(np.bool_)
+
+
+def next_state(board, player, action, seed, n=2, rng_seed=0):
+    b = _board(board)
+    np_ = lib().azo_next_state(_p(b, C.c_int8), n, int(action), int(player), int(seed), int(rng_seed))
+    return b, np_
+
+
+def game_ended(board, n=2):
+    b = _board(board); out = np.zeros(n, np.float32)
+    lib().azo_check_end_game(_p(b, C.c_int8), n, _p(out, C.c_float))
+    return out
+
+
+def canonical(board, player, n=2):
+    b = _board(board)
+    if player:
+        lib().azo_swap_players(_p(b, C.c_int8), n, int(player))
+    return b
+
+
+def get_round(board):
+    b = _board(board)
+    return lib().azo_get_round(_p(b, C.c_int8))
+
+
+def get_score(board, player, n=2):
+    b = _board(board)
+    return lib().azo_get_score(_p(b, C.c_int8), n, player)
+
+
+def symmetries(board, pi, valids, n=2):
+    b = _board(board); pi = np.ascontiguousarray(pi, np.float32); v = np.ascontiguousarray(valids).astype(np.uint8)
+    kmax = 1 + 9 + 2 * n
+    ob = np.zeros((kmax,) + b.shape, np.int8); op = np.zeros((kmax, NA), np.float32); ov = np.zeros((kmax, NA), np.uint8)
+    k = lib().azo_symmetries(_p(b, C.c_int8), n, _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
+    return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]
+
+
+def hashnet(board, valids, n=2):
+    b = _board(board); v = np.ascontiguousarray(valids).astype(np.uint8)
+    pi = np.zeros(NA, np.float32); val = np.zeros(n, np.float32)
+    lib().azo_hashnet(_p(b, C.c_int8), b.size, _p(v, C.c_uint8), n, _p(pi, C.c_float), _p(val, C.c_float))
+    return pi, val
+
+
+def v80_forward(blob, boards, valids, n=2):
+    boards = np.ascontiguousarray(boards, np.int8); B = boards.shape[0]
+    v = np.ascontiguousarray(valids).astype(np.uint8)
+    blob = np.ascontiguousarray(blob, np.float32)
+    pi = np.zeros((B, NA), np.float32); val = np.zeros((B, n), np.float32)
+    lib().azo_v80_forward(_p(blob, C.c_float), n, B, _p(boards, C.c_int8), _p(v, C.c_uint8), _p(pi, C.c_float), _p(val, C.c_float))
+    return pi, val
+
+
+def make_cfg(num_players=2, numMCTSSims=800, ratio_fullMCTS=5, universes=1, forced_playouts=False, no_mem_optim=False,
+             net_kind=0, cpuct=1.25, fpu=0.0, dirichletAlpha=-1.0, prob_fullMCTS=1.0, temperature2=1.1):
+    return Cfg(num_players, numMCTSSims, ratio_fullMCTS, universes, int(forced_playouts), int(no_mem_optim), net_kind,
+               cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2)
+
+
+class MCTS:
+    """Oracle counterpart of the reference's MCTS class (MCTS.py:19-203)."""
+
+    def __init__(self, cfg, blob=None, dirichlet_noise=False, seed=0):
+        self.cfg = cfg
+        self.blob = None if blob is None else np.ascontiguousarray(blob, np.float32)
+        bp = _p(self.blob, C.c_float) if self.blob is not None else None
+        self.h = lib().azo_mcts_new(C.byref(cfg), bp, int(dirichlet_noise), seed)
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            lib().azo_mcts_free(self.h); self.h = None
+
+    def reset(self):
+        lib().azo_mcts_reset(self.h)
+
+    def stats(self):
+        out = np.zeros(7, np.int64); lib().azo_mcts_stats(self.h, _p(out, C.c_int64)); return out
+
+    def getActionProb(self, cb, temp=1.0, force_full_search=False, noise=None):
+        b = _board(cb); probs = np.zeros(NA, np.float64); q = np.zeros(self.cfg.num_players, np.float32); raw = np.zeros(NA, np.int64)
+        nz = None
+        if noise is not None and len(noise):
+            nz = np.ascontiguousarray(noise, np.float64)
+        full = lib().azo_mcts_get_action_prob(self.h, _p(b, C.c_int8), float(temp), int(force_full_search),
+                                              _p(nz, C.c_double) if nz is not None else None,
+                                              _p(probs, C.c_double), _p(q, C.c_float), _p(raw, C.c_int64))
+        return probs, q, bool(full), raw
+
+
+def selfplay_bench(cfg, blob, threads, games_per_thread, max_plies=0, temperature=(1.0, 0.1), tempThreshold=10, seed=1):
+    blob = np.ascontiguousarray(blob, np.float32); out = np.zeros(8, np.float64)
+    lib().azo_selfplay_bench(C.byref(cfg), _p(blob, C.c_float), threads, games_per_thread, max_plies,
+                             float(temperature[0]), float(temperature[1]), float(tempThreshold), seed, _p(out, C.c_double))
+    keys = ('sims', 'expansions', 'node_visits', 'nn_evals', 'plies', 'examples', 'games', 'seconds')
+    return dict(zip(keys, out.tolist()))

@@ -1,0 +1,55 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def kat():
+    return np.load(os.path.join(GOLDEN, 'splendor_kat.npz'))
+
+
+@pytest.fixture(scope='session')
+def mcts_cases():
+    z = np.load(os.path.join(GOLDEN, 'splendor_mcts.npz'))
+    n = int(z['n_cases'])
+    keys = ('cfg', 'root', 'n_sims', 'probs', 'q', 'raw_counts', 'root_P', 'root_Qsa', 'noise', 'summary')
+    return [{k: z[f'c{i}_{k}'] for k in keys} for i in range(n)]
+
+
+@pytest.fixture(scope='session')
+def episodes():
+    return {t: np.load(os.path.join(GOLDEN, f'splendor_episode_{t}.npz')) for t in ('A', 'B')}
+
+
+@pytest.fixture(scope='session')
+def v80_golden():
+    out = {}
+    for tag in ('rand', 'shipped'):
+        z = np.load(os.path.join(GOLDEN, f'splendor_v80_{tag}.npz'))
+        sd = {k[4:]: z[k] for k in z.files if k.startswith('sd__')}
+        out[tag] = dict(sd=sd, boards=z['boards'], valids=z['valids'], pi=z['pi'], v=z['v'])
+    return out
+
+
+# MCTS argument sets used to produce the goldens (mirrors oracle/gen_golden.py:MCTS_CONFIGS)
+MCTS_CONFIGS = {
+    'default': dict(cpuct=1.25, fpu=0.0, universes=1, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1],
+                    forced_playouts=False, noise=False),
+    'shipped': dict(cpuct=0.8, fpu=0.0593, universes=3, dirichletAlpha=0.3, temperature=[1.25, 0.8, 1.1],
+                    forced_playouts=True, noise=True),
+    'auto_noise': dict(cpuct=1.25, fpu=0.2, universes=0, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1],
+                       forced_playouts=False, noise=True),
+    'universes8': dict(cpuct=2.0, fpu=0.0, universes=8, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.0],
+                       forced_playouts=True, noise=False),
+}

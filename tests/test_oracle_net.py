@@ -1,0 +1,15 @@
+"""Pins the oracle's V80 forward to the reference's SplendorNNet (torch CPU fp32) outputs
+(tests/golden/splendor_v80_{rand,shipped}.npz). Tolerance 1e-5 absolute on pi and v (BASELINE.json)."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+def test_v80_forward_matches_reference(v80_golden):
+    for tag, g in v80_golden.items():
+        blob = O.v80_blob(g['sd'])
+        assert blob.size == 142406 + 5 * 0 + sum(g['sd'][k].size for k in g['sd'] if 'running' in k)
+        pi, v = O.v80_forward(blob, g['boards'], g['valids'])
+        np.testing.assert_allclose(pi, g['pi'], rtol=0, atol=1e-5, err_msg=tag)
+        np.testing.assert_allclose(v, g['v'], rtol=0, atol=1e-5, err_msg=tag)
+        assert (pi[~g['valids']] == 0).all()
