@@ -1,0 +1,49 @@
+"""Self-play half of Coach (reference: Coach.py:37-148) on the device engine.
+
+`Coach(game, nnet, args).executeEpisodes()` returns the same example tuples as the reference
+`(board int8[56,7], pi float32[81], z float32[np], valids bool[81], q float32[np])`, symmetry-augmented like
+Coach.py:67, for `args.numEps` finished games played by `args.parallel_inferences` (= n_games) concurrent slots.
+"""
+from collections import deque
+
+import numpy as np
+
+from .mcts import Engine
+from .utils import with_defaults
+
+
+class Coach:
+    def __init__(self, game, nnet, args, n_games=None, seed=0, node_cap=0, edge_cap=0):
+        self.game = game; self.nnet = nnet; self.args = a = with_defaults(args)
+        self.n_games = int(n_games if n_games is not None else a.parallel_inferences)
+        self.engine = Engine(game, nnet, a, self.n_games, dirichlet_noise=(a.dirichletAlpha != 0), seed=seed,
+                             node_cap=node_cap, edge_cap=edge_cap)
+        self.trainExamplesHistory = []
+
+    def raw_examples(self, min_episodes, max_moves=0):
+        """Plays until `min_episodes` games finished; returns un-augmented example arrays (one per full-search ply)."""
+        self.engine.selfplay(min_episodes=min_episodes, max_moves=max_moves)
+        cap = self.n_games * self.game.info.max_game_len
+        return self.engine.examples(cap)
+
+    def augment(self, boards, pis, zs, valids, qs):
+        """getSymmetries for every example (Coach.py:67-69) through the batched symmetry kernel."""
+        out = []
+        if len(boards) == 0:
+            return out
+        ob, op, ov, ok = self.game.symmetries_batch(boards, pis, valids)
+        for i in range(len(boards)):
+            for k in range(int(ok[i])):
+                out.append((ob[i, k], op[i, k], zs[i], ov[i, k], [qs[i, p] for p in range(qs.shape[1])]))
+        return out
+
+    def executeEpisode(self):
+        """One finished game's examples (Coach.py:37-84); uses slot-parallel play and returns the first game that ends."""
+        return self.executeEpisodes(num_eps=1)
+
+    def executeEpisodes(self, num_eps=None):
+        num_eps = int(self.args.numEps if num_eps is None else num_eps)
+        ex = self.augment(*self.raw_examples(num_eps))
+        q = deque([], maxlen=self.args.maxlenOfQueue)
+        q += ex
+        return q

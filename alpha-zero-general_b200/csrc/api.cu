@@ -1,0 +1,478 @@
+// api.cu -- the C ABI declared in include/azg.h: batched game-step kernels, the net handle and the
+// search / self-play engine. Host side is plain C++ (no torch types); device memory is owned by the
+// handles, caller buffers may be host or device memory.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/azg.h"
+#include "common.cuh"
+#include "net_v80.cuh"
+#include "selfplay.cuh"
+#include "splendor.cuh"
+#include "tree.cuh"
+
+using namespace azg;
+
+// ------------------------------------------------------------------ errors -----------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+
+extern "C" int azg_abi_version(void) { return AZG_ABI_VERSION; }
+extern "C" const char* azg_last_error(void) { return g_err.c_str(); }
+extern "C" int azg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+static int require_device() {
+    if (azg_device_count() <= 0) return fail("no CUDA device: the B200 engine has no CPU fallback");
+    return 0;
+}
+
+// ------------------------------------------------------------------ host/device staging ----------------
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+struct Scratch {                       // grow-only device buffer
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) return fail("cudaMalloc scratch failed");
+        cap = n; return 0;
+    }
+    ~Scratch() { if (p) cudaFree(p); }
+};
+// An argument that may live on the host: in() gives a device pointer (copying if needed), out() copies back.
+struct Arg {
+    Scratch s; const void* src = nullptr; void* dst = nullptr; void* dev = nullptr; size_t bytes = 0; bool staged = false;
+    int in(const void* p, size_t n, cudaStream_t st) {
+        src = p; bytes = n; staged = false; dev = const_cast<void*>(p);
+        if (!p || n == 0) { dev = nullptr; return 0; }
+        if (is_device_ptr(p)) return 0;
+        if (s.ensure(n)) return 1;
+        CK(cudaMemcpyAsync(s.p, p, n, cudaMemcpyHostToDevice, st));
+        dev = s.p; staged = true; return 0;
+    }
+    int outbuf(void* p, size_t n) {
+        dst = p; bytes = n; staged = false; dev = p;
+        if (!p || n == 0) { dev = nullptr; return 0; }
+        if (is_device_ptr(p)) return 0;
+        if (s.ensure(n)) return 1;
+        dev = s.p; staged = true; return 0;
+    }
+    int flush(cudaStream_t st) {
+        if (staged && dst) CK(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(dev); }
+};
+static thread_local Arg tl_arg[12];
+static bool any_staged(int n) { for (int i = 0; i < n; i++) if (tl_arg[i].staged) return true; return false; }
+
+// ------------------------------------------------------------------ game info ---------------------------
+typedef Splendor<2> SP2;
+
+extern "C" int azg_game_info(int game_id, int num_players, azg_game_info_t* out) {
+    if (!out) return fail("out is NULL");
+    if (game_id != AZG_GAME_SPLENDOR) return fail("unknown game_id (built: 1=splendor)");
+    if (num_players != 2) return fail("splendor: only num_players=2 is built in this version");
+    out->game_id = game_id; out->num_players = 2; out->state_rows = SP2::ROWS; out->state_cols = SP2::COLS; out->state_bytes = SP2::S;
+    out->action_size = SP2::A; out->max_symmetries = SP2::MAX_SYM; out->max_game_len = SP2::MAX_MOVES;
+    return 0;
+}
+static int check_game(int game_id, int np) { azg_game_info_t t; return azg_game_info(game_id, np, &t); }
+
+// ------------------------------------------------------------------ batched game-step kernels ----------
+// One warp per board; the board is staged in shared memory exactly as in the search kernels.
+constexpr int GK_WARPS = 4;
+template <class G> __device__ __forceinline__ void load_board(int8_t* sb, const int8_t* src, int lane) {
+    for (int i = lane; i < G::SP; i += 32) sb[i] = i < G::S ? src[i] : (int8_t)0;
+    __syncwarp();
+}
+template <class G> __device__ __forceinline__ void store_board(int8_t* dst, const int8_t* sb, int lane) {
+    __syncwarp();
+    for (int i = lane; i < G::S; i += 32) dst[i] = sb[i];
+}
+
+template <class G>
+__global__ void k_game_init(int n, const uint64_t* seeds, int8_t* boards) {
+    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    if (i >= n) return;
+    if (lane == 0) { Philox rng(seeds[i], 0x1717, 0); G::init_game(sm[w], &rng); }
+    store_board<G>(boards + (size_t)i * G::S, sm[w], lane);
+}
+template <class G>
+__global__ void k_game_valid(int n, const int8_t* boards, const int* players, uint8_t* mask) {
+    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    if (i >= n) return;
+    load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
+    uint32_t m[G::MASK_WORDS];
+    G::valid_mask(sm[w], players ? players[i] : 0, lane, m);
+#pragma unroll
+    for (int k = 0; k < G::MASK_WORDS; k++) { int a = lane + 32 * k; if (a < G::A) mask[(size_t)i * G::A + a] = (m[k] >> lane) & 1; }
+}
+template <class G>
+__global__ void k_game_next(int n, const int8_t* boards, const int* players, const int* actions, const long long* seeds,
+                            const uint64_t* keys, int8_t* out, int* out_np) {
+    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    if (i >= n) return;
+    load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
+    if (lane == 0) {
+        Philox rng(keys ? keys[i] : (uint64_t)i, 0x2323, 0);
+        int np = G::make_move(sm[w], actions[i], players ? players[i] : 0, seeds ? seeds[i] : 0, &rng);
+        if (out_np) out_np[i] = np;
+    }
+    store_board<G>(out + (size_t)i * G::S, sm[w], lane);
+}
+template <class G>
+__global__ void k_game_ended(int n, const int8_t* boards, float* out) {
+    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    if (i >= n) return;
+    load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
+    float es[G::NP]; G::ended(sm[w], es);
+    if (lane == 0) for (int p = 0; p < G::NP; p++) out[(size_t)i * G::NP + p] = es[p];
+}
+template <class G>
+__global__ void k_game_canonical(int n, const int8_t* boards, const int* players, int8_t* out) {
+    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    if (i >= n) return;
+    load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
+    const int p = players ? players[i] : 0;
+    if (p != 0) G::swap_players(sm[w], p, lane);
+    store_board<G>(out + (size_t)i * G::S, sm[w], lane);
+}
+template <class G>
+__global__ void k_game_round_score(int n, const int8_t* boards, int* rounds, int* scores) {
+    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    if (i >= n) return;
+    load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
+    if (lane == 0 && rounds) rounds[i] = G::round(sm[w]);
+    if (scores && lane < G::NP) scores[(size_t)i * G::NP + lane] = G::score(sm[w], lane);
+}
+template <class G>
+__global__ void k_game_symmetries(int n, const int8_t* boards, const float* pi, const uint8_t* mask, int8_t* ob, float* opi,
+                                  uint8_t* om, int* ok) {
+    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
+    __shared__ float spi[GK_WARPS][G::A];
+    __shared__ uint8_t smask[GK_WARPS][G::A];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    if (i >= n) return;
+    load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
+    for (int a = lane; a < G::A; a += 32) { spi[w][a] = pi[(size_t)i * G::A + a]; smask[w][a] = mask[(size_t)i * G::A + a]; }
+    __syncwarp();
+    const int K = G::num_symmetries(sm[w]);
+    if (lane == 0) ok[i] = K;
+    for (int k = 0; k < G::MAX_SYM; k++) {
+        const size_t o = (size_t)i * G::MAX_SYM + k;
+        if (k < K) G::symmetry(sm[w], spi[w], smask[w], k, lane, ob + o * G::S, opi + o * G::A, om + o * G::A);
+        else {
+            for (int j = lane; j < G::S; j += 32) ob[o * G::S + j] = 0;
+            for (int a = lane; a < G::A; a += 32) { opi[o * G::A + a] = 0.f; om[o * G::A + a] = 0; }
+        }
+    }
+}
+
+static dim3 gk_grid(int n) { return dim3((unsigned)((n + GK_WARPS - 1) / GK_WARPS)); }
+#define GK_BLOCK (GK_WARPS * 32)
+#define FINISH(nargs)                                                          \
+    do {                                                                       \
+        CKL();                                                                 \
+        for (int i_ = 0; i_ < (nargs); i_++) if (tl_arg[i_].flush(st)) return 1; \
+        if (any_staged(nargs)) CK(cudaStreamSynchronize(st));                  \
+        return 0;                                                              \
+    } while (0)
+
+extern "C" int azg_game_init(int game_id, int np, int n, const uint64_t* seeds, int8_t* boards, void* stream) {
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
+    if (a[0].in(seeds, sizeof(uint64_t) * n, st) || a[1].outbuf(boards, (size_t)n * SP2::S)) return 1;
+    k_game_init<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<uint64_t>(), a[1].as<int8_t>());
+    FINISH(2);
+}
+extern "C" int azg_game_valid(int game_id, int np, int n, const int8_t* boards, const int32_t* players, uint8_t* mask, void* stream) {
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].outbuf(mask, (size_t)n * SP2::A)) return 1;
+    k_game_valid<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<uint8_t>());
+    FINISH(3);
+}
+extern "C" int azg_game_next(int game_id, int np, int n, const int8_t* boards, const int32_t* players, const int32_t* actions,
+                             const int64_t* seeds, const uint64_t* rng_keys, int8_t* out_boards, int32_t* out_next_player, void* stream) {
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (n <= 0) return 0;
+    if (!actions) return fail("actions is NULL");
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].in(actions, sizeof(int) * n, st) ||
+        a[3].in(seeds, sizeof(int64_t) * n, st) || a[4].in(rng_keys, sizeof(uint64_t) * n, st) ||
+        a[5].outbuf(out_boards, (size_t)n * SP2::S) || a[6].outbuf(out_next_player, sizeof(int) * n)) return 1;
+    k_game_next<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int>(), a[3].as<long long>(),
+                                                      a[4].as<uint64_t>(), a[5].as<int8_t>(), a[6].as<int>());
+    FINISH(7);
+}
+extern "C" int azg_game_ended(int game_id, int np, int n, const int8_t* boards, float* out, void* stream) {
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].outbuf(out, sizeof(float) * n * SP2::NP)) return 1;
+    k_game_ended<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<float>());
+    FINISH(2);
+}
+extern "C" int azg_game_canonical(int game_id, int np, int n, const int8_t* boards, const int32_t* players, int8_t* out_boards, void* stream) {
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].outbuf(out_boards, (size_t)n * SP2::S)) return 1;
+    k_game_canonical<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int8_t>());
+    FINISH(3);
+}
+extern "C" int azg_game_round_score(int game_id, int np, int n, const int8_t* boards, int32_t* rounds, int32_t* scores, void* stream) {
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].outbuf(rounds, sizeof(int) * n) || a[2].outbuf(scores, sizeof(int) * n * SP2::NP)) return 1;
+    k_game_round_score<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int>());
+    FINISH(3);
+}
+extern "C" int azg_game_symmetries(int game_id, int np, int n, const int8_t* boards, const float* pi, const uint8_t* mask,
+                                   int8_t* out_boards, float* out_pi, uint8_t* out_mask, int32_t* out_k, void* stream) {
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg; const size_t K = SP2::MAX_SYM;
+    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(pi, sizeof(float) * n * SP2::A, st) || a[2].in(mask, (size_t)n * SP2::A, st) ||
+        a[3].outbuf(out_boards, n * K * SP2::S) || a[4].outbuf(out_pi, sizeof(float) * n * K * SP2::A) ||
+        a[5].outbuf(out_mask, n * K * SP2::A) || a[6].outbuf(out_k, sizeof(int) * n)) return 1;
+    k_game_symmetries<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<float>(), a[2].as<uint8_t>(), a[3].as<int8_t>(),
+                                                            a[4].as<float>(), a[5].as<uint8_t>(), a[6].as<int>());
+    FINISH(7);
+}
+
+// ------------------------------------------------------------------ net handle --------------------------
+constexpr int V80_TB = 16;
+struct azg_net {
+    int kind, game_id, np;
+    V80Layout L; float* blob = nullptr;
+    Scratch masks;                        // packed masks for the standalone forward
+    unsigned long long launches = 0;
+};
+__global__ void k_pack_masks(int n, int A, int MW, const uint8_t* mask, uint32_t* words) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= n) return;
+    for (int k = 0; k < MW; k++) {
+        const int a = lane + 32 * k;
+        const unsigned w = __ballot_sync(FULL, a < A && mask[(size_t)j * A + a] != 0);
+        if (lane == 0) words[(size_t)j * MW + k] = w;
+    }
+}
+// Evaluate slots: list/count on device (engine) or identity (standalone). boards stride `bstride` bytes.
+static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, const int8_t* boards, int bstride,
+                           const uint32_t* masks, float* pi, float* v, int n_max, cudaStream_t st) {
+    if (n_max <= 0) return 0;
+    if (net->kind == AZG_NET_HASH) {
+        const int warps_per_block = 4;
+        k_hashnet_forward<SP2::S, SP2::A, SP2::NP, SP2::MASK_WORDS><<<(n_max + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+            count_ptr, list, boards, bstride, masks, pi, v, n_max);
+    } else {
+        static bool attr_set = false;
+        constexpr size_t smem = v80_smem_bytes<SP2::ROWS, V80_TB>();
+        if (!attr_set) { CK(cudaFuncSetAttribute(k_v80_forward<SP2::ROWS, SP2::NP, V80_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+        k_v80_forward<SP2::ROWS, SP2::NP, V80_TB><<<(n_max + V80_TB - 1) / V80_TB, V80_THREADS, smem, st>>>(
+            net->blob, net->L, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+    }
+    net->launches++;
+    CKL();
+    return 0;
+}
+extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights) {
+    if (!net) return fail("net is NULL");
+    if (net->kind == AZG_NET_HASH) return 0;
+    const size_t need = v80_src_floats(SP2::ROWS, net->np);
+    if (!weights || n_weights != need) return fail("V80 weights: expected " + std::to_string(need) + " floats, got " + std::to_string(n_weights));
+    std::vector<float> src(n_weights), dst((size_t)net->L.total);
+    CK(cudaMemcpy(src.data(), weights, n_weights * sizeof(float), cudaMemcpyDefault));
+    v80_prepare(src.data(), SP2::ROWS, net->np, net->L, dst.data());
+    CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* weights, size_t n_weights, azg_net** out) {
+    if (!out) return fail("out is NULL");
+    if (require_device() || check_game(game_id, np)) return 1;
+    if (net_kind != AZG_NET_HASH && net_kind != AZG_NET_SPLENDOR_V80) return fail("unknown net kind (built: 0=hash test net, 80=Splendor V80)");
+    azg_net* net = new azg_net(); net->kind = net_kind; net->game_id = game_id; net->np = np;
+    if (net_kind == AZG_NET_SPLENDOR_V80) {
+        net->L = v80_layout(SP2::ROWS, np);
+        if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
+        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
+    }
+    *out = net; return 0;
+}
+extern "C" int azg_net_destroy(azg_net* net) { if (net) { if (net->blob) cudaFree(net->blob); delete net; } return 0; }
+extern "C" int azg_net_forward(azg_net* net, int n, const int8_t* boards, const uint8_t* mask, float* pi, float* v, void* stream) {
+    if (!net) return fail("net is NULL");
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(mask, (size_t)n * SP2::A, st) || a[2].outbuf(pi, sizeof(float) * n * SP2::A) ||
+        a[3].outbuf(v, sizeof(float) * n * SP2::NP)) return 1;
+    if (net->masks.ensure(sizeof(uint32_t) * (size_t)n * SP2::MASK_WORDS)) return 1;
+    k_pack_masks<<<(n + 3) / 4, 128, 0, st>>>(n, SP2::A, SP2::MASK_WORDS, a[1].as<uint8_t>(), (uint32_t*)net->masks.p);
+    if (net_forward_dev(net, nullptr, nullptr, a[0].as<int8_t>(), SP2::S, (const uint32_t*)net->masks.p, a[2].as<float>(), a[3].as<float>(), n, st)) return 1;
+    FINISH(4);
+}
+
+// ------------------------------------------------------------------ engine ------------------------------
+struct azg_engine {
+    azg_engine_cfg cfg; azg_net* net = nullptr;
+    Dev<SP2> d; SelfPlay<SP2> sp;
+    std::vector<void*> allocs;
+    Scratch in_roots, in_full, in_noise, out_counts, out_raw, out_q;
+    unsigned long long launches = 0;
+    int sims_full = 0, sims_fast = 0;
+    bool sp_ready = false;
+    template <class T> int alloc(T** p, size_t n, bool zero = true) {
+        void* q = nullptr;
+        if (cudaMalloc(&q, sizeof(T) * n) != cudaSuccess) return fail("cudaMalloc failed for " + std::to_string(sizeof(T) * n) + " bytes (reduce n_games / node_cap / edge_cap)");
+        if (zero && cudaMemset(q, 0, sizeof(T) * n) != cudaSuccess) return fail("cudaMemset failed");
+        allocs.push_back(q); *p = (T*)q; return 0;
+    }
+};
+
+__global__ void k_load_roots(Dev<SP2> d, int n, const int8_t* roots, const uint8_t* full, int sims_full, int sims_fast) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= d.n_games) return;
+    if (g < n) {
+        for (int i = lane; i < SP2::SP; i += 32) d.root[(size_t)g * SP2::SP + i] = i < SP2::S ? roots[(size_t)g * SP2::S + i] : (int8_t)0;
+        if (lane == 0) { const bool f = full ? full[g] != 0 : true; d.full[g] = f; d.n_sims[g] = f ? sims_full : sims_fast; }
+    } else if (lane == 0) d.n_sims[g] = 0;
+}
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_engine** out) {
+    if (!cfg || !net || !out) return fail("NULL argument");
+    if (require_device() || check_game(cfg->game_id, cfg->num_players)) return 1;
+    if (cfg->n_games <= 0 || cfg->numMCTSSims <= 0) return fail("n_games and numMCTSSims must be positive");
+    azg_engine* e = new azg_engine(); e->cfg = *cfg; e->net = net;
+    const int G = cfg->n_games;
+    int node_cap = cfg->node_cap, edge_cap = cfg->edge_cap;
+    if (node_cap <= 0) {
+        // default: room for the nodes that survive tree reuse (measured <= ~10x sims/move with a random-init net)
+        // bounded by 60 % of free HBM
+        size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+        const double per_node = 32.0 + 36.0 * 17.0 + 2 * 8.0;
+        double fit = 0.6 * (double)free_b / (double)G / per_node;
+        node_cap = (int)std::min<double>(fit, 16.0 * cfg->numMCTSSims + 1024);
+        node_cap = std::max(node_cap, cfg->numMCTSSims + 64);
+    }
+    if (edge_cap <= 0) edge_cap = node_cap * 36;
+    if (edge_cap >= (1 << 24)) return fail("edge_cap must be < 2^24");
+    e->cfg.node_cap = node_cap; e->cfg.edge_cap = edge_cap;
+    Dev<SP2>& d = e->d;
+    d.n_games = G; d.node_cap = node_cap; d.edge_cap = edge_cap; d.ht_cap = next_pow2(2 * node_cap);
+    d.universes = cfg->universes; d.forced_playouts = cfg->forced_playouts; d.dirichlet_noise = cfg->dirichlet_noise;
+    d.cpuct = cfg->cpuct; d.fpu = cfg->fpu; d.dir_alpha = cfg->dirichletAlpha; d.temp2 = cfg->temperature[2]; d.seed = cfg->seed;
+    d.noise = nullptr;
+    e->sims_full = cfg->numMCTSSims; e->sims_fast = cfg->ratio_fullMCTS > 0 ? cfg->numMCTSSims / cfg->ratio_fullMCTS : cfg->numMCTSSims;
+    int bad = 0;
+    bad |= e->alloc(&d.nodes, (size_t)G * node_cap, false); bad |= e->alloc(&d.edges, (size_t)G * edge_cap, false);
+    bad |= e->alloc(&d.acts, (size_t)G * edge_cap, false); bad |= e->alloc(&d.ht, (size_t)G * d.ht_cap);
+    bad |= e->alloc(&d.n_nodes, G); bad |= e->alloc(&d.n_edges, G);
+    bad |= e->alloc(&d.root, (size_t)G * SP2::SP); bad |= e->alloc(&d.n_sims, G); bad |= e->alloc(&d.full, G); bad |= e->alloc(&d.move_ctr, G);
+    bad |= e->alloc(&d.path, (size_t)G * SP2::MAX_DEPTH); bad |= e->alloc(&d.path_len, G); bad |= e->alloc(&d.leaf_kind, G);
+    bad |= e->alloc(&d.leaf_key, (size_t)2 * G); bad |= e->alloc(&d.leaf_v, (size_t)G * SP2::NP); bad |= e->alloc(&d.leaf_mask, (size_t)G * SP2::MASK_WORDS);
+    bad |= e->alloc(&d.leaf_round, G);
+    bad |= e->alloc(&d.nn_in, (size_t)G * SP2::SP); bad |= e->alloc(&d.nn_pi, (size_t)G * SP2::A); bad |= e->alloc(&d.nn_v, (size_t)G * SP2::NP);
+    bad |= e->alloc(&d.nn_list, G); bad |= e->alloc(&d.nn_count, 1); bad |= e->alloc(&d.stats, (size_t)G * ST_N);
+    if (bad) { azg_engine_destroy(e); return 1; }
+    *out = e; return 0;
+}
+extern "C" int azg_engine_destroy(azg_engine* e) {
+    if (!e) return 0;
+    for (void* p : e->allocs) cudaFree(p);
+    delete e; return 0;
+}
+extern "C" int azg_engine_reset(azg_engine* e, int game) {
+    if (!e) return fail("engine is NULL");
+    if (game >= e->d.n_games) return fail("game index out of range");
+    k_reset<SP2><<<game >= 0 ? 8 : 592, 256>>>(e->d, game);
+    e->launches++;
+    CKL(); return 0;
+}
+
+// One lock-step simulation for every game: select -> batched leaf evaluation -> expand + backup.
+static int engine_step(azg_engine* e, int step, cudaStream_t st) {
+    const int G = e->d.n_games; const dim3 grid((unsigned)((G + SEL_WARPS - 1) / SEL_WARPS));
+    k_select<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, step);
+    if (net_forward_dev(e->net, e->d.nn_count, e->d.nn_list, e->d.nn_in, SP2::SP, e->d.leaf_mask, e->d.nn_pi, e->d.nn_v, G, st)) return 1;
+    k_backup<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, step);
+    e->launches += 3;
+    return 0;
+}
+static int engine_gc(azg_engine* e, int sims, cudaStream_t st) {
+    const int G = e->d.n_games; const dim3 grid((unsigned)((G + SEL_WARPS - 1) / SEL_WARPS));
+    k_gc<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, sims + 2, (sims + 2) * 48, 0);
+    e->launches++;
+    return 0;
+}
+
+extern "C" int azg_engine_search(azg_engine* e, int n, const int8_t* roots, const uint8_t* full_search, const double* noise,
+                                 int32_t* out_counts, int32_t* out_raw, float* out_q, void* stream) {
+    if (!e) return fail("engine is NULL");
+    if (n <= 0 || n > e->d.n_games) return fail("n must be in [1, n_games]");
+    if (!roots || !out_counts) return fail("roots / out_counts is NULL");
+    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg; const int G = e->d.n_games;
+    if (a[0].in(roots, (size_t)n * SP2::S, st) || a[1].in(full_search, (size_t)n, st) || a[2].in(noise, sizeof(double) * n * SP2::A, st) ||
+        a[3].outbuf(out_counts, sizeof(int) * n * SP2::A) || a[4].outbuf(out_raw, sizeof(int) * n * SP2::A) || a[5].outbuf(out_q, sizeof(float) * n * SP2::NP)) return 1;
+    CK(cudaMemsetAsync(e->d.nn_count, 0, sizeof(int), st));
+    k_load_roots<<<(G + 3) / 4, 128, 0, st>>>(e->d, n, a[0].as<int8_t>(), a[1].as<uint8_t>(), e->sims_full, e->sims_fast);
+    e->launches++;
+    e->d.noise = a[2].as<double>();
+    // without host knowledge of the flags run the longer budget; finished games idle (k_select early-out)
+    int steps = e->sims_full;
+    if (full_search && !is_device_ptr(full_search)) { bool any = false; for (int i = 0; i < n; i++) any |= full_search[i] != 0; if (!any) steps = e->sims_fast; }
+    engine_gc(e, steps, st);
+    for (int s = 0; s < steps; s++) if (engine_step(e, s, st)) return 1;
+    k_finish<SP2><<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(e->d, n, a[3].as<int>(), a[4].as<int>(), a[5].as<float>());
+    e->launches++;
+    e->d.noise = nullptr;
+    FINISH(6);
+}
+
+extern "C" int azg_engine_stats(azg_engine* e, int64_t* out16) {
+    if (!e || !out16) return fail("NULL argument");
+    const int G = e->d.n_games;
+    std::vector<unsigned long long> h((size_t)G * ST_N);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), e->d.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 16; k++) out16[k] = 0;
+    for (int g = 0; g < G; g++)
+        for (int k = 0; k < ST_N; k++) {
+            if (k == ST_MAXNODES) out16[k] = std::max<int64_t>(out16[k], (int64_t)h[(size_t)g * ST_N + k]);
+            else out16[k] += (int64_t)h[(size_t)g * ST_N + k];
+        }
+    out16[12] = (int64_t)(e->launches + (e->net ? e->net->launches : 0));
+    out16[13] = e->d.node_cap; out16[14] = e->d.edge_cap;
+    return 0;
+}
+
+#include "selfplay_api.inl"

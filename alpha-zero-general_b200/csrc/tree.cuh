@@ -1,0 +1,519 @@
+// tree.cuh -- per-game search trees in HBM and the MCTS kernels (select / expand+backup / finish / gc).
+//
+// Replaces MCTS.search and its njit helpers (MCTS.py:105-261) for n_games independent trees advanced in
+// lock-step, one simulation per game per step, ONE WARP PER GAME:
+//   k_select  : root -> leaf walk. Per level: 128-bit board hash -> warp-wide probe of the game's open-
+//               addressing table -> 32 B node header -> coalesced read of the node's legal-edge array
+//               (16 B/edge) -> PUCT argmax by warp shuffle (first index wins ties, MCTS.py:227-228) ->
+//               make_move + swap_players on the board held in shared memory (children are recomputed,
+//               never cached: MCTS.py:233-248).
+//   (net)     : batched leaf evaluation of the compacted leaf list (GenericNNetWrapper.predict_server).
+//   k_backup  : writes the new node (normalised priors, Q=-42 sentinel, N=0), inserts it in the table,
+//               then backs the value up the recorded path, lanes parallel over levels (MCTS.py:176-181).
+// Arithmetic follows the reference operation by operation (see oracle/azg_oracle.c header): f64 Q and
+// PUCT with explicit round-to-nearest intrinsics so nvcc cannot contract or reassociate them.
+//
+// HBM layout per game g (arena sizes are engine parameters):
+//   nodes [node_cap] NodeHdr 32 B : 128-bit key, Ns, Qs, edge_off, n_legal, round, kind
+//   edges [edge_cap] Edge    16 B : {Q f64, P f32, N i32} for LEGAL actions only, ascending action index
+//   acts  [edge_cap] act_t        : action id of each edge
+//   ht    [ht_cap]   u64          : (tag32 << 32) | (node index + 1), 0 = empty, linear probing
+#pragma once
+#include "common.cuh"
+
+namespace azg {
+
+struct __align__(16) Edge { double q; float p; int n; };
+struct __align__(16) NodeHdr {
+    uint64_t klo, khi;
+    int ns; float qs;
+    uint32_t edge_off; uint16_t n_legal; uint8_t round; uint8_t kind;
+};
+static_assert(sizeof(Edge) == 16 && sizeof(NodeHdr) == 32, "layout");
+struct PathEnt { uint32_t node; uint32_t edge_np; };          // edge index (24 bits) | next_player << 24
+
+enum { NODE_EXPANDED = 0, NODE_TERMINAL = 1 };
+enum { LEAF_NONE = 0, LEAF_EXPAND = 1, LEAF_NEW_TERMINAL = 2, LEAF_OLD_TERMINAL = 3 };
+enum { ST_SIMS = 0, ST_VISITS, ST_EXPANSIONS, ST_NNEVALS, ST_TERMINAL, ST_OVERFLOW, ST_GC, ST_MAXNODES, ST_SUMLEGAL,
+       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_N = 16 };
+
+constexpr double kNanQ = -42.0;                                // MCTS.py:11
+__constant__ long long kMagicSeeds[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   // MCTS.py:14
+
+template <class G>
+struct Dev {
+    // configuration
+    int n_games, node_cap, edge_cap, ht_cap;
+    int universes, forced_playouts, dirichlet_noise;
+    double cpuct, fpu, dir_alpha, temp2;
+    uint64_t seed;
+    // trees
+    NodeHdr* nodes; Edge* edges; typename G::act_t* acts; uint64_t* ht; int* n_nodes; int* n_edges;
+    // search control (per game)
+    int8_t* root;              // [G][SP] canonical root boards
+    int* n_sims;               // sims requested for the current search
+    uint8_t* full;             // full-search flag (MCTS.py:58)
+    const double* noise;       // injected Dirichlet draws [G][A] or nullptr
+    unsigned* move_ctr;        // searches done in this slot (RNG counter)
+    // per-simulation scratch
+    PathEnt* path; int* path_len; int* leaf_kind; uint64_t* leaf_key; float* leaf_v; uint32_t* leaf_mask; int* leaf_round;
+    int8_t* nn_in; float* nn_pi; float* nn_v; int* nn_list; int* nn_count;
+    unsigned long long* stats; // [G][ST_N]
+
+    __device__ __forceinline__ NodeHdr* g_nodes(int g) const { return nodes + (size_t)g * node_cap; }
+    __device__ __forceinline__ Edge* g_edges(int g) const { return edges + (size_t)g * edge_cap; }
+    __device__ __forceinline__ typename G::act_t* g_acts(int g) const { return acts + (size_t)g * edge_cap; }
+    __device__ __forceinline__ uint64_t* g_ht(int g) const { return ht + (size_t)g * ht_cap; }
+};
+
+// ---- board hash (WARP): sum over words of two independent 64-bit mixes of (position, word) ----------
+template <class G>
+__device__ __forceinline__ void board_hash(const int8_t* b, int lane, uint64_t& lo, uint64_t& hi) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(b);
+    uint64_t a = 0, c = 0;
+#pragma unroll
+    for (int i = lane; i < G::SP / 4; i += 32) {
+        uint64_t x = ((uint64_t)(i + 1) << 32) | w[i];
+        a += mix64(x ^ 0x2545F4914F6CDD1DULL);
+        c += mix64(x * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL);
+    }
+    lo = warp_sum_u64(a); hi = warp_sum_u64(c);
+}
+
+// ---- hash table (WARP): 32 slots probed per round trip ---------------------------------------------------
+__device__ __forceinline__ int ht_find(const uint64_t* ht, int cap, const NodeHdr* nodes, uint64_t klo, uint64_t khi, int lane) {
+    const uint32_t tag = (uint32_t)(khi >> 32);
+    const uint32_t start = (uint32_t)klo & (uint32_t)(cap - 1);
+    for (int probe = 0; probe < cap; probe += 32) {
+        uint64_t e = ht[(start + probe + lane) & (uint32_t)(cap - 1)];
+        unsigned em = __ballot_sync(FULL, e == 0);
+        unsigned mm = __ballot_sync(FULL, e != 0 && (uint32_t)(e >> 32) == tag);
+        if (em) mm &= (1u << (__ffs(em) - 1)) - 1u;            // only entries before the first empty slot
+        while (mm) {
+            int l = __ffs(mm) - 1; mm &= mm - 1;
+            int idx = (int)(uint32_t)__shfl_sync(FULL, e, l) - 1;
+            const NodeHdr* h = nodes + idx;
+            if (h->klo == klo && h->khi == khi) return idx;
+        }
+        if (em) return -1;
+    }
+    return -1;
+}
+__device__ __forceinline__ void ht_insert(uint64_t* ht, int cap, uint64_t klo, uint64_t khi, int idx, int lane) {
+    const uint32_t start = (uint32_t)klo & (uint32_t)(cap - 1);
+    const uint64_t ent = ((uint64_t)(uint32_t)(khi >> 32) << 32) | (uint32_t)(idx + 1);
+    for (int probe = 0; probe < cap; probe += 32) {
+        uint32_t slot = (start + probe + lane) & (uint32_t)(cap - 1);
+        unsigned em = __ballot_sync(FULL, ht[slot] == 0);
+        if (em) { if (lane == __ffs(em) - 1) ht[slot] = ent; __syncwarp(); return; }
+    }
+}
+
+// ---- float32 sum in the order of the reference's vectorised np.sum (oracle/azg_oracle.c:sum_f32_avx2) -----
+__device__ __forceinline__ float warp_sum_avx2order(const float* x, int n, int lane) {
+    float s = 0.f; int i = 0;
+    if (n >= 32) {
+        int nb = n / 32; float acc = 0.f;
+        for (int b = 0; b < nb; b++) acc = __fadd_rn(acc, x[32 * b + lane]);
+        float p = __fadd_rn(__shfl_down_sync(FULL, acc, 8), acc);
+        float t = __fadd_rn(p, __shfl_down_sync(FULL, p, 16));
+        float u = __fadd_rn(__shfl_down_sync(FULL, t, 4), t);
+        float w = __fadd_rn(u, __shfl_down_sync(FULL, u, 2));
+        s = __shfl_sync(FULL, __fadd_rn(w, __shfl_down_sync(FULL, w, 1)), 0);
+        i = 32 * nb;
+    }
+    if ((n & 28) != 0 && (n & ~3) > i) {
+        float q = lane == 0 ? s : 0.f;
+        for (int k = i; k < (n & ~3); k += 4) if (lane < 4) q = __fadd_rn(q, x[k + lane]);
+        float w = __fadd_rn(q, __shfl_down_sync(FULL, q, 2));
+        s = __shfl_sync(FULL, __fadd_rn(w, __shfl_down_sync(FULL, w, 1)), 0);
+        i = n & ~3;
+    }
+    for (; i < n; i++) s = __fadd_rn(s, x[i]);
+    return s;
+}
+
+// ---- root prior noise (WARP): softmax(Ps, T) -> 0.75 P + 0.25 Dir -> (caller normalises) ----------------
+// MCTS.py:147-149,156-160,187-197,255-261. `p` is the dense prior (0 at illegal actions) in shared memory,
+// `dscr` an A-sized f64 scratch. Injected noise if d.noise, else drawn from the Philox stream.
+template <class G>
+__device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const uint32_t (&mask)[G::MASK_WORDS], int lane) {
+    constexpr int A = G::A;
+    if (d.temp2 != 1.0) {
+        double inv_t = 1.0 / d.temp2;
+        for (int a = lane; a < A; a += 32) dscr[a] = pow((double)p[a], inv_t);
+        __syncwarp();
+        double s = 0;
+        if (lane == 0) { for (int a = 0; a < A; a++) s = __dadd_rn(s, dscr[a]); s = __ddiv_rn(1.0, s); }
+        s = __shfl_sync(FULL, s, 0);
+        for (int a = lane; a < A; a += 32) p[a] = (float)__dmul_rn(dscr[a], s);
+        __syncwarp();
+    }
+    int L = 0;
+#pragma unroll
+    for (int k = 0; k < G::MASK_WORDS; k++) L += __popc(mask[k]);
+    // dscr[k] <- k-th Dirichlet component
+    if (d.noise) {
+        for (int k = lane; k < L; k += 32) dscr[k] = d.noise[(size_t)g * A + k];
+    } else {
+        double alpha = d.dir_alpha > 0 ? d.dir_alpha : 10.0 / (double)L, part = 0;
+        for (int k = lane; k < L; k += 32) {
+            Philox r(d.seed, ((uint64_t)g << 8) | 1u, ((uint64_t)d.move_ctr[g] << 16) | (unsigned)k);
+            double x = r.gamma(alpha); dscr[k] = x; part += x;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+        for (int k = lane; k < L; k += 32) dscr[k] = dscr[k] / part;
+    }
+    __syncwarp();
+    int before = 0;
+#pragma unroll
+    for (int k = 0; k < G::MASK_WORDS; k++) {
+        int a = lane + 32 * k;
+        if (a < A && (mask[k] >> lane & 1)) {
+            int rank = before + __popc(mask[k] & ((1u << lane) - 1u));
+            float t1 = __fmul_rn(0.75f, p[a]);
+            p[a] = (float)__dadd_rn((double)t1, __dmul_rn(0.25, dscr[rank]));
+        }
+        before += __popc(mask[k]);
+    }
+    __syncwarp();
+}
+
+// ---- PUCT (WARP): pick_highest_UCB, MCTS.py:210-230; returns the edge index -----------------------------
+__device__ __forceinline__ int puct_select(const Edge* e, int L, int ns, float qs, double cpuct, double fpu,
+                                           bool forced, int n_iter, int lane) {
+    const double fpu_init = fpu > 0 ? __dsub_rn((double)qs, fpu) : fpu;
+    const double c0 = __dmul_rn(cpuct, __dsqrt_rn(__dadd_rn((double)ns, 1e-8)));
+    const double c1 = __dmul_rn(cpuct, __dsqrt_rn((double)ns));
+    const double kn = __dmul_rn((double)n_iter, 0.5);
+    double best = -INFINITY; int best_i = 0x7FFFFFFF, forced_i = 0x7FFFFFFF;
+    for (int i = lane; i < L; i += 32) {
+        Edge ed = e[i];
+        double pd = (double)ed.p;
+        if (forced) {
+            long long th = __double2ll_rz(__dsqrt_rn(__dmul_rn(kn, pd)));
+            if ((long long)ed.n < th && i < forced_i) forced_i = i;
+        }
+        double u = ed.q != kNanQ ? __dadd_rn(ed.q, __ddiv_rn(__dmul_rn(c1, pd), (double)(ed.n + 1)))
+                                 : __fma_rn(c0, pd, fpu_init);
+        if (u > best) { best = u; best_i = i; }
+    }
+    if (forced) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) forced_i = min(forced_i, __shfl_xor_sync(FULL, forced_i, o));
+        if (forced_i != 0x7FFFFFFF) return forced_i;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(FULL, best, o); int oi = __shfl_xor_sync(FULL, best_i, o);
+        if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    return best_i;
+}
+
+constexpr int SEL_WARPS = 4;
+template <class G> struct WarpSmem {
+    __align__(16) int8_t board[G::SP];
+    __align__(16) float f[(G::A + 31) / 32 * 32];
+    __align__(16) double d[(G::A + 31) / 32 * 32];
+};
+
+// ============================================================ select ==================================
+template <class G>
+__global__ void __launch_bounds__(SEL_WARPS * 32) k_select(Dev<G> d, int step) {
+    __shared__ WarpSmem<G> sm[SEL_WARPS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+    if (g >= d.n_games) return;
+    if (step >= d.n_sims[g]) { if (lane == 0) d.leaf_kind[g] = LEAF_NONE; return; }
+    int8_t* sb = sm[w].board;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(d.root + (size_t)g * G::SP);
+        if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = src[lane];
+        __syncwarp();
+    }
+    const bool full = d.full ? d.full[g] != 0 : true;
+    const bool forced_root = full && d.forced_playouts;
+    const bool noise_now = step == 0 && full && d.dirichlet_noise;
+    const long long seed = d.universes > 0 ? kMagicSeeds[step % d.universes] : -1;
+    NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
+    const uint64_t* ht = d.g_ht(g);
+    PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
+    int depth = 0, kind = LEAF_NONE;
+    for (;;) {
+        uint64_t klo, khi;
+        board_hash<G>(sb, lane, klo, khi);
+        int idx = ht_find(ht, d.ht_cap, nodes, klo, khi, lane);
+        if (idx < 0) {                                           // state never seen: MCTS.py:130-154
+            float es[G::NP];
+            bool over = G::ended(sb, es);
+            if (over) {
+                kind = LEAF_NEW_TERMINAL;
+                if (lane == 0) for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p];
+            } else {
+                kind = LEAF_EXPAND;
+                uint32_t m[G::MASK_WORDS];
+                G::valid_mask(sb, 0, lane, m);
+                if (lane < G::MASK_WORDS) d.leaf_mask[(size_t)g * G::MASK_WORDS + lane] = m[lane];
+                if (lane < G::SP / 16) reinterpret_cast<uint4*>(d.nn_in + (size_t)g * G::SP)[lane] = reinterpret_cast<const uint4*>(sb)[lane];
+                if (lane == 0) { int pos = atomicAdd(d.nn_count, 1); d.nn_list[pos] = g; }
+            }
+            if (lane == 0) { d.leaf_key[2 * (size_t)g] = klo; d.leaf_key[2 * (size_t)g + 1] = khi; d.leaf_round[g] = G::round(sb); }
+            break;
+        }
+        const NodeHdr h = nodes[idx];
+        if (h.kind == NODE_TERMINAL) {                           // MCTS.py:136-138
+            kind = LEAF_OLD_TERMINAL;
+            if (lane == 0) { const float* es = reinterpret_cast<const float*>(edges + h.edge_off); for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p]; }
+            break;
+        }
+        if (depth == 0 && noise_now) {                           // re-noise an already expanded root, MCTS.py:156-160
+            float* pf = sm[w].f; uint32_t m[G::MASK_WORDS];
+#pragma unroll
+            for (int k = 0; k < G::MASK_WORDS; k++) m[k] = 0;
+            for (int a = lane; a < G::A; a += 32) pf[a] = 0.f;
+            __syncwarp();
+            for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; pf[a] = edges[h.edge_off + i].p; }
+            for (int i = 0; i < h.n_legal; i++) { int a = acts[h.edge_off + i]; m[a >> 5] |= 1u << (a & 31); }
+            __syncwarp();
+            root_noise<G>(d, g, pf, sm[w].d, m, lane);
+            float s = warp_sum_avx2order(pf, G::A, lane);
+            float inv = __fdiv_rn(1.0f, s);
+            for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; edges[h.edge_off + i].p = __fmul_rn(pf[a], inv); }
+            __syncwarp();
+        }
+        const int e = puct_select(edges + h.edge_off, h.n_legal, h.ns, h.qs, d.cpuct, d.fpu, depth == 0 && forced_root, step, lane);
+        const int a = acts[h.edge_off + e];
+        int np = 0;
+        if (lane == 0) {
+            np = G::make_move(sb, a, 0, seed, nullptr);          // seed != 0 in search: deterministic chance
+            path[depth].node = (uint32_t)idx; path[depth].edge_np = (h.edge_off + (uint32_t)e) | ((uint32_t)np << 24);
+        }
+        __syncwarp();
+        np = __shfl_sync(FULL, np, 0);
+        if (np != 0) G::swap_players(sb, np, lane);
+        depth++;
+        if (depth >= G::MAX_DEPTH) break;
+    }
+    if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; }
+}
+
+// ============================================================ expand + backup =========================
+template <class G>
+__global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(Dev<G> d, int step) {
+    __shared__ WarpSmem<G> sm[SEL_WARPS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;    // leaf list consumed by the net; reset for the next step
+    if (g >= d.n_games) return;
+    const int kind = d.leaf_kind[g];
+    if (kind == LEAF_NONE) return;
+    constexpr int NP = G::NP, A = G::A, MW = G::MASK_WORDS;
+    const int depth = d.path_len[g];
+    NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
+    unsigned long long* st = d.stats + (size_t)g * ST_N;
+    float v[NP];
+    if (kind == LEAF_EXPAND) {
+        float* pf = sm[w].f;
+        for (int a = lane; a < A; a += 32) pf[a] = d.nn_pi[(size_t)g * A + a];
+        uint32_t m[MW]; int L = 0;
+#pragma unroll
+        for (int k = 0; k < MW; k++) { m[k] = d.leaf_mask[(size_t)g * MW + k]; L += __popc(m[k]); }
+#pragma unroll
+        for (int p = 0; p < NP; p++) v[p] = d.nn_v[(size_t)g * NP + p];
+        __syncwarp();
+        const bool full = d.full ? d.full[g] != 0 : true;
+        if (depth == 0 && step == 0 && full && d.dirichlet_noise) root_noise<G>(d, g, pf, sm[w].d, m, lane);   // MCTS.py:147-149
+        const float s = warp_sum_avx2order(pf, A, lane);                                                    // normalise, MCTS.py:150
+        const float inv = __fdiv_rn(1.0f, s);
+        const int ni = d.n_nodes[g], eo = d.n_edges[g];
+        if (ni >= d.node_cap || eo + L > d.edge_cap) {
+            if (lane == 0) st[ST_OVERFLOW]++;                    // arena full: value is still backed up, node not stored
+        } else {
+            int before = 0;
+#pragma unroll
+            for (int k = 0; k < MW; k++) {
+                int a = lane + 32 * k;
+                if (a < A && (m[k] >> lane & 1)) {
+                    int rank = before + __popc(m[k] & ((1u << lane) - 1u));
+                    Edge ed; ed.q = kNanQ; ed.p = __fmul_rn(pf[a], inv); ed.n = 0;
+                    edges[eo + rank] = ed; acts[eo + rank] = (typename G::act_t)a;
+                }
+                before += __popc(m[k]);
+            }
+            const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
+            if (lane == 0) {
+                NodeHdr h; h.klo = klo; h.khi = khi; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
+                h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_EXPANDED;
+                nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + L;
+                st[ST_EXPANSIONS]++; st[ST_NNEVALS]++; st[ST_SUMLEGAL] += (unsigned)L;
+                if ((unsigned long long)(ni + 1) > st[ST_MAXNODES]) st[ST_MAXNODES] = (unsigned long long)(ni + 1);
+            }
+            ht_insert(d.g_ht(g), d.ht_cap, klo, khi, ni, lane);
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < NP; p++) v[p] = d.leaf_v[(size_t)g * NP + p];
+        if (kind == LEAF_NEW_TERMINAL) {                         // MCTS.py:130-135: terminal states are stored too
+            const int ni = d.n_nodes[g], eo = d.n_edges[g];
+            if (ni >= d.node_cap || eo + 1 > d.edge_cap) { if (lane == 0) st[ST_OVERFLOW]++; }
+            else {
+                const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
+                if (lane == 0) {
+                    float* es = reinterpret_cast<float*>(edges + eo);
+                    for (int p = 0; p < 4; p++) es[p] = p < NP ? v[p] : 0.f;
+                    NodeHdr h; h.klo = klo; h.khi = khi; h.ns = 0; h.qs = 0.f; h.edge_off = (uint32_t)eo; h.n_legal = 0;
+                    h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_TERMINAL;
+                    nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + 1;
+                }
+                ht_insert(d.g_ht(g), d.ht_cap, klo, khi, ni, lane);
+            }
+        }
+        if (lane == 0) st[ST_TERMINAL]++;
+    }
+    // ---- backup (MCTS.py:176-181), lanes parallel over levels; a path never visits a node twice (the round
+    //      counter in the key increases with every move) so the updates are independent.
+    const PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
+    int carry = 0;                                               // rotation accumulated from deeper chunks
+    for (int base = ((depth - 1) / 32) * 32; base >= 0 && depth > 0; base -= 32) {
+        const int lvl = base + lane;
+        PathEnt pe; pe.node = 0; pe.edge_np = 0;
+        if (lvl < depth) pe = path[lvl];
+        int npv = lvl < depth ? (int)(pe.edge_np >> 24) : 0;
+        int suf = npv;                                           // inclusive suffix sum over lanes (levels >= lvl in this chunk)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_down_sync(FULL, suf, o); if (lane + o < 32) suf += t; }
+        const int rot = (suf + carry) % NP;                      // v_lvl = roll(v_leaf, rot)
+        if (lvl < depth) {
+            const float v0 = v[(NP - rot) % NP];
+            Edge* ed = edges + (pe.edge_np & 0xFFFFFFu);
+            NodeHdr* nh = nodes + pe.node;
+            Edge x = *ed; int ns = nh->ns; float qs = nh->qs;
+            x.q = __ddiv_rn(__dadd_rn(__dmul_rn((double)x.n, x.q), (double)v0), (double)(x.n + 1));
+            x.n += 1;
+            qs = __fdiv_rn(__fadd_rn(__fmul_rn((float)(ns + 1), qs), v0), (float)(ns + 2));
+            *ed = x; nh->ns = ns + 1; nh->qs = qs;
+        }
+        carry = (carry + __shfl_sync(FULL, suf, 0)) % NP;
+    }
+    if (lane == 0) { st[ST_SIMS]++; st[ST_VISITS] += (unsigned)depth; }
+}
+
+// ============================================================ finish (getActionProb tail) ==============
+// MCTS.py:67-80: root counts, q vector, forced-playout policy-target pruning.
+template <class G>
+__global__ void __launch_bounds__(SEL_WARPS * 32) k_finish(Dev<G> d, int n, int* out_counts, int* out_raw, float* out_q) {
+    __shared__ WarpSmem<G> sm[SEL_WARPS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+    if (g >= n) return;
+    constexpr int A = G::A, NP = G::NP;
+    int8_t* sb = sm[w].board;
+    if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(d.root + (size_t)g * G::SP)[lane];
+    __syncwarp();
+    uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
+    const NodeHdr* nodes = d.g_nodes(g); const Edge* edges = d.g_edges(g); const typename G::act_t* acts = d.g_acts(g);
+    const int idx = ht_find(d.g_ht(g), d.ht_cap, nodes, klo, khi, lane);
+    int* cnt = reinterpret_cast<int*>(sm[w].f);
+    for (int a = lane; a < A; a += 32) { cnt[a] = 0; if (out_raw) out_raw[(size_t)g * A + a] = 0; }
+    __syncwarp();
+    if (idx < 0 || nodes[idx].kind == NODE_TERMINAL) {            // no search ran / terminal root: all-zero counts
+        for (int a = lane; a < A; a += 32) out_counts[(size_t)g * A + a] = 0;
+        if (out_q && lane < NP) out_q[(size_t)g * NP + lane] = 0.f;
+        if (lane == 0) d.move_ctr[g]++;
+        return;
+    }
+    const NodeHdr h = nodes[idx];
+    const bool full = d.full ? d.full[g] != 0 : true;
+    const bool forced = full && d.forced_playouts;
+    const int nsims = d.n_sims[g];
+    int best = 0;
+    for (int i = lane; i < h.n_legal; i += 32) best = max(best, edges[h.edge_off + i].n);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+    for (int i = lane; i < h.n_legal; i += 32) {
+        const Edge ed = edges[h.edge_off + i]; const int a = acts[h.edge_off + i];
+        int c = ed.n;
+        if (out_raw) out_raw[(size_t)g * A + a] = c;
+        if (forced) {
+            if (c != best) { float t = __fmul_rn(__fmul_rn(0.5f, ed.p), (float)nsims); c -= (int)__double2ll_rz(__dsqrt_rn((double)t)); }
+            c = c > 1 ? c : 0;
+        }
+        cnt[a] = c;
+    }
+    __syncwarp();
+    for (int a = lane; a < A; a += 32) out_counts[(size_t)g * A + a] = cnt[a];
+    if (out_q && lane < NP) out_q[(size_t)g * NP + lane] = lane == 0 ? h.qs : -h.qs / (float)(NP - 1);
+    if (lane == 0) d.move_ctr[g]++;
+}
+
+// ============================================================ tree GC ==================================
+// Drops every node that can no longer be reached: its round is <= the new root's round and it is not the
+// root itself (the round counter is part of the key and grows with every move). This is the reference's
+// cleaning (MCTS.py:86-91, nodes with round < r-5) made exact; both are semantic no-ops. Runs only when
+// the arena could not hold another `need_nodes` / `need_edges`. Compacts nodes+edges in place, rebuilds ht.
+template <class G>
+__global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes, int need_edges, int force) {
+    __shared__ WarpSmem<G> sm[SEL_WARPS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+    if (g >= d.n_games) return;
+    const int nn = d.n_nodes[g], ne = d.n_edges[g];
+    if (!force && nn + need_nodes <= d.node_cap && ne + need_edges <= d.edge_cap) return;
+    int8_t* sb = sm[w].board;
+    if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(d.root + (size_t)g * G::SP)[lane];
+    __syncwarp();
+    uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
+    const int r = G::round(sb);
+    NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g); uint64_t* ht = d.g_ht(g);
+    int wn = 0, we = 0;                                          // write cursors
+    for (int base = 0; base < nn; base += 32) {
+        const int i = base + lane;
+        NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.klo = h.khi = 0; h.ns = 0; h.qs = 0;
+        bool keep = false;
+        if (i < nn) { h = nodes[i]; keep = (int)h.round > r || (h.klo == klo && h.khi == khi); }
+        const int len = keep ? (h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal) : 0;
+        const unsigned km = __ballot_sync(FULL, keep);
+        int pre = len;                                           // inclusive prefix sum of edge counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
+        const int new_off = we + pre - len, old_off = (int)h.edge_off;
+        const int new_idx = wn + __popc(km & ((1u << lane) - 1u));
+        __syncwarp();
+        if (keep) { h.edge_off = (uint32_t)new_off; nodes[new_idx] = h; }
+        // move the edge blocks of this chunk, node by node in ascending order (dest <= src)
+        for (unsigned mm = km; mm; mm &= mm - 1) {
+            const int l = __ffs(mm) - 1;
+            const int so = __shfl_sync(FULL, old_off, l), dn = __shfl_sync(FULL, new_off, l), ln = __shfl_sync(FULL, len, l);
+            if (so != dn)
+                for (int k = 0; k < ln; k += 32) {
+                    Edge tmp; typename G::act_t ta = 0; const bool in = k + lane < ln;
+                    if (in) { tmp = edges[so + k + lane]; ta = acts[so + k + lane]; }
+                    __syncwarp();
+                    if (in) { edges[dn + k + lane] = tmp; acts[dn + k + lane] = ta; }
+                    __syncwarp();
+                }
+        }
+        wn += __popc(km); we += __shfl_sync(FULL, pre, 31);
+    }
+    __syncwarp();
+    for (int s = lane; s < d.ht_cap; s += 32) ht[s] = 0;
+    __threadfence_block(); __syncwarp();
+    for (int i = lane; i < wn; i += 32) {                         // lane-parallel re-insert
+        const NodeHdr h = nodes[i];
+        const uint64_t ent = ((uint64_t)(uint32_t)(h.khi >> 32) << 32) | (uint32_t)(i + 1);
+        uint32_t slot = (uint32_t)h.klo & (uint32_t)(d.ht_cap - 1);
+        while (atomicCAS(reinterpret_cast<unsigned long long*>(ht + slot), 0ULL, (unsigned long long)ent) != 0ULL)
+            slot = (slot + 1) & (uint32_t)(d.ht_cap - 1);
+    }
+    if (lane == 0) { d.n_nodes[g] = wn; d.n_edges[g] = we; d.stats[(size_t)g * ST_N + ST_GC]++; }
+}
+
+// Reset trees (MCTS.reset_all_search_trees, MCTS.py:199-203): one slot (game >= 0) or all.
+template <class G>
+__global__ void k_reset(Dev<G> d, int game) {
+    const int g0 = game >= 0 ? game : 0, g1 = game >= 0 ? game + 1 : d.n_games;
+    const size_t per = (size_t)d.ht_cap, total = (size_t)(g1 - g0) * per;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        d.ht[(size_t)g0 * per + i] = 0;
+    for (int g = g0 + blockIdx.x * blockDim.x + threadIdx.x; g < g1; g += gridDim.x * blockDim.x) { d.n_nodes[g] = 0; d.n_edges[g] = 0; }
+}
+
+}  // namespace azg

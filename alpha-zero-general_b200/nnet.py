@@ -1,0 +1,162 @@
+"""Inference half of GenericNNetWrapper (GenericNNetWrapper.py:94-157) on the CUDA forward kernels.
+
+`NNetWrapper(game, nn_args)` mirrors splendor/NNet.py:NNetWrapper for nn_version 80. Weights come from a
+reference checkpoint / state_dict; torch (if present) is used only to read them.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+
+
+def _lin_bn(prefix):
+    return [f'{prefix}.linear.weight', f'{prefix}.norm.weight', f'{prefix}.norm.bias',
+            f'{prefix}.norm.running_mean', f'{prefix}.norm.running_var']
+
+
+def _v80_order():
+    names = _lin_bn('first_layer')
+    for blk in ('trunk.0', 'output_layers_PI.0', 'output_layers_V.0'):
+        names += _lin_bn(f'{blk}.expand') + _lin_bn(f'{blk}.depthwise')
+        names += [f'{blk}.se.fc1.weight', f'{blk}.se.fc1.bias', f'{blk}.se.fc2.weight', f'{blk}.se.fc2.bias']
+        names += _lin_bn(f'{blk}.project')
+    names += ['output_layers_PI.2.weight', 'output_layers_PI.2.bias', 'output_layers_PI.4.weight', 'output_layers_PI.4.bias',
+              'output_layers_V.2.weight', 'output_layers_V.2.bias', 'output_layers_V.4.weight', 'output_layers_V.4.bias']
+    return names
+
+
+# Order in which azg_net_create expects the SplendorNNet V80 state_dict tensors (splendor/SplendorNNet.py:259-280),
+# each flattened row-major and concatenated as float32.
+V80_TENSOR_ORDER = _v80_order()
+
+
+def v80_blob(state_dict):
+    parts = []
+    for n in V80_TENSOR_ORDER:
+        t = state_dict[n]
+        if hasattr(t, 'detach'):
+            t = t.detach().cpu().numpy()
+        parts.append(np.asarray(t, dtype=np.float32).ravel())
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+def random_v80_state_dict(seed=0, num_players=2):
+    """Random-init V80 weights with the reference's initialisers (kaiming_uniform_ weights, zero biases, default BN;
+    SplendorNNet.py:385-395) drawn from numpy so no torch is needed. Used by bench.py and smoke()."""
+    rng = np.random.default_rng(seed)
+    nv = 32 + 10 * num_players + num_players * num_players
+    E, Q, A = 3 * nv, 40 * nv // 56, 81
+    shapes = {}
+    def lin_bn(prefix, out, inn, ch):
+        shapes[f'{prefix}.linear.weight'] = (out, inn)
+        for k, val in (('weight', 1.0), ('bias', 0.0), ('running_mean', 0.0), ('running_var', 1.0)):
+            shapes[f'{prefix}.norm.{k}'] = ((ch,), val)
+    lin_bn('first_layer', nv, nv, nv)
+    for blk in ('trunk.0', 'output_layers_PI.0', 'output_layers_V.0'):
+        lin_bn(f'{blk}.expand', E, nv, E); lin_bn(f'{blk}.depthwise', 7, 7, E)
+        shapes[f'{blk}.se.fc1.weight'] = (Q, E); shapes[f'{blk}.se.fc1.bias'] = ((Q,), 0.0)
+        shapes[f'{blk}.se.fc2.weight'] = (E, Q); shapes[f'{blk}.se.fc2.bias'] = ((E,), 0.0)
+        lin_bn(f'{blk}.project', nv, E, nv)
+    shapes['output_layers_PI.2.weight'] = (A, nv * 7); shapes['output_layers_PI.2.bias'] = ((A,), 0.0)
+    shapes['output_layers_PI.4.weight'] = (A, A); shapes['output_layers_PI.4.bias'] = ((A,), 0.0)
+    shapes['output_layers_V.2.weight'] = (num_players, nv * 7); shapes['output_layers_V.2.bias'] = ((num_players,), 0.0)
+    shapes['output_layers_V.4.weight'] = (num_players, num_players); shapes['output_layers_V.4.bias'] = ((num_players,), 0.0)
+    sd = {}
+    for name, shp in shapes.items():
+        if isinstance(shp[0], tuple):
+            sd[name] = np.full(shp[0], shp[1], np.float32)
+        else:
+            bound = np.sqrt(6.0 / shp[1])                       # kaiming_uniform_(a=0): gain sqrt(2) * sqrt(3/fan_in)
+            sd[name] = rng.uniform(-bound, bound, size=shp).astype(np.float32)
+    return sd
+
+
+class CudaNet:
+    """Owns an azg_net handle."""
+
+    def __init__(self, kind, game, weights=None):
+        self._L = _lib.load()
+        self.kind = kind
+        self.game = game
+        self.h = C.c_void_p()
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        _lib.check(self._L.azg_net_create(kind, game.game_id, game.num_players, _lib.ptr(w), 0 if w is None else w.size, C.byref(self.h)))
+
+    def load(self, weights):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        _lib.check(self._L.azg_net_load(self.h, _lib.ptr(w), w.size))
+
+    def forward(self, boards, valids):
+        """boards int8 [n,...], valids bool/uint8 [n,A] (numpy, or torch CUDA tensors) -> (pi, v) numpy float32."""
+        info = self.game.info
+        b = np.ascontiguousarray(boards, dtype=np.int8).reshape(-1, info.state_bytes); n = len(b)
+        va = np.ascontiguousarray(np.asarray(valids).astype(np.uint8)).reshape(n, info.action_size)
+        pi = np.empty((n, info.action_size), np.float32); v = np.empty((n, self.game.num_players), np.float32)
+        _lib.check(self._L.azg_net_forward(self.h, n, _lib.ptr(b), _lib.ptr(va), _lib.ptr(pi), _lib.ptr(v), None))
+        return pi, v
+
+    def close(self):
+        if self.h:
+            self._L.azg_net_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NNetWrapper:
+    """splendor/NNet.py:NNetWrapper (inference surface). nn_args['nn_version'] must be 80."""
+
+    def __init__(self, game, nn_args=None, state_dict=None, seed=0):
+        nn_args = dict(nn_args or {'nn_version': 80})
+        if nn_args.get('nn_version', 80) != 80:
+            raise NotImplementedError('only SplendorNNet version 80 is built (the shipped 2-player checkpoint)')
+        self.args = nn_args
+        self.game = game
+        self.board_size = game.getBoardSize(); self.action_size = game.getActionSize(); self.num_players = game.num_players
+        self.requestKnowledgeTransfer = False
+        self.state_dict = state_dict if state_dict is not None else random_v80_state_dict(seed, game.num_players)
+        self.net = CudaNet(_lib.AZG_NET_SPLENDOR_V80, game, v80_blob(self.state_dict))
+
+    # NeuralNet.predict (NeuralNet.py:27, GenericNNetWrapper.py:94-120): single board
+    def predict(self, board, valid_actions):
+        pi, v = self.net.forward(np.asarray(board)[None], np.asarray(valid_actions)[None])
+        return pi[0], v[0]
+
+    # batched form of predict_server (GenericNNetWrapper.py:139-157)
+    def predict_batch(self, boards, valid_actions):
+        return self.net.forward(boards, valid_actions)
+
+    def load_state_dict(self, state_dict):
+        self.state_dict = state_dict
+        self.net.load(v80_blob(state_dict))
+
+    def load_checkpoint(self, folder, filename):
+        """Reads a reference checkpoint (torch.save dict with 'state_dict', GenericNNetWrapper.py:192-205)."""
+        import os
+        import torch
+        ck = torch.load(os.path.join(folder, filename), map_location='cpu', weights_only=False)
+        self.load_state_dict(ck['state_dict'])
+        return ck
+
+    def train(self, examples):
+        raise NotImplementedError('training is outside the self-play hot path (SURVEY.md section 8f-1)')
+
+
+class HashNetWrapper:
+    """Deterministic test net (tests only): prior/value are a hash of the board, see oracle/hashnet.py."""
+
+    def __init__(self, game):
+        self.game = game
+        self.num_players = game.num_players
+        self.net = CudaNet(_lib.AZG_NET_HASH, game, None)
+
+    def predict(self, board, valid_actions):
+        pi, v = self.net.forward(np.asarray(board)[None], np.asarray(valid_actions)[None])
+        return pi[0], v[0]
+
+    def predict_batch(self, boards, valid_actions):
+        return self.net.forward(boards, valid_actions)

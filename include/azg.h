@@ -1,0 +1,139 @@
+/*
+ * azg.h -- C ABI of the B200-native AlphaZero self-play engine (libazg_b200.so).
+ *
+ * The reference (cestpasphoto/alpha-zero-general) is pure Python: its "FFI" for the hot path is
+ * the duck-typed plugin surface Game.py / NeuralNet.py / MCTS.py / Coach.py. Each entry point below
+ * names the reference interface it replaces (file:line relative to the reference root). A ctypes
+ * binding of exactly these symbols is what alpha-zero-general_b200/lib.py loads, and what a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; azg_last_error() gives the message
+ *    (thread-local).
+ *  - all buffers are caller-owned. A pointer may be HOST memory (numpy) or DEVICE memory
+ *    (torch.Tensor.data_ptr()): the library detects which (cudaPointerGetAttributes) and stages host
+ *    buffers through its own device scratch, synchronising before it returns. With device pointers the
+ *    work is only enqueued on `stream` (a cudaStream_t passed as void*, NULL = default stream).
+ *  - boards are int8, row-major, `state_bytes` bytes per board, tightly packed [n][state_bytes].
+ *  - masks are uint8 0/1 [n][action_size]; policies float32 [n][action_size]; values float32 [n][num_players].
+ *  - handles are not thread-safe; one engine per GPU / process.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef AZG_H
+#define AZG_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZG_ABI_VERSION 1
+
+enum { AZG_GAME_SPLENDOR = 1 };                          /* GameSwitcher.py:3-13 ('splendor') */
+enum { AZG_NET_HASH = 0, AZG_NET_SPLENDOR_V80 = 80 };    /* HASH: deterministic test net (tests only) */
+
+typedef struct {
+    int32_t game_id, num_players;
+    int32_t state_rows, state_cols, state_bytes;         /* Game.getBoardSize   Game.py:22  */
+    int32_t action_size;                                 /* Game.getActionSize  Game.py:29  */
+    int32_t max_symmetries;                              /* upper bound of len(getSymmetries()) */
+    int32_t max_game_len;                                /* upper bound on plies per game */
+} azg_game_info_t;
+
+int azg_abi_version(void);
+const char* azg_last_error(void);
+int azg_device_count(void);                               /* 0 when no CUDA device is usable */
+int azg_game_info(int game_id, int num_players, azg_game_info_t* out);
+
+/* ---- batched game step: the *LogicNumba.Board methods behind the Game facade ------------------- */
+/* Game.getInitBoard (Game.py:14; splendor/SplendorLogicNumba.py:151-178). One board per seed; the draws
+ * come from a counter-based device RNG keyed by the seed (the reference uses numba's MT19937 stream). */
+int azg_game_init(int game_id, int num_players, int n, const uint64_t* seeds, int8_t* boards, void* stream);
+/* Game.getValidMoves (Game.py:51; SplendorLogicNumba.py:180-188). players may be NULL (= all 0). */
+int azg_game_valid(int game_id, int num_players, int n, const int8_t* boards, const int32_t* players,
+                   uint8_t* mask, void* stream);
+/* Game.getNextState (Game.py:36-49; SplendorLogicNumba.py:190-205,306-357). seeds[i]==0 means a true
+ * random chance draw taken from the device RNG keyed by rng_keys[i] (may be NULL => key i). */
+int azg_game_next(int game_id, int num_players, int n, const int8_t* boards, const int32_t* players,
+                  const int32_t* actions, const int64_t* seeds, const uint64_t* rng_keys,
+                  int8_t* out_boards, int32_t* out_next_player, void* stream);
+/* Game.getGameEnded (Game.py:64; SplendorLogicNumba.py:221-240): float32[n][num_players]. */
+int azg_game_ended(int game_id, int num_players, int n, const int8_t* boards, float* out, void* stream);
+/* Game.getCanonicalForm (Game.py:97; SplendorLogicNumba.py:244-253). */
+int azg_game_canonical(int game_id, int num_players, int n, const int8_t* boards, const int32_t* players,
+                       int8_t* out_boards, void* stream);
+/* Game.getRound / Game.getScore (Game.py:76,87; SplendorLogicNumba.py:151-154,303-304).
+ * rounds int32[n]; scores int32[n][num_players]; either output may be NULL. */
+int azg_game_round_score(int game_id, int num_players, int n, const int8_t* boards, int32_t* rounds,
+                         int32_t* scores, void* stream);
+/* Game.getSymmetries (Game.py:113; SplendorLogicNumba.py:255-301). Outputs are [n][max_symmetries][..];
+ * out_k[i] = number of valid entries for board i. */
+int azg_game_symmetries(int game_id, int num_players, int n, const int8_t* boards, const float* pi,
+                        const uint8_t* mask, int8_t* out_boards, float* out_pi, uint8_t* out_mask,
+                        int32_t* out_k, void* stream);
+
+/* ---- policy/value net: GenericNNetWrapper.predict / predict_server (GenericNNetWrapper.py:94-157) ---- */
+typedef struct azg_net azg_net;
+/* weights: float32 blob = the net's state_dict tensors concatenated in the order documented in
+ * alpha-zero-general_b200/nnet.py (V80_TENSOR_ORDER); host or device pointer. NULL for AZG_NET_HASH. */
+int azg_net_create(int net_kind, int game_id, int num_players, const float* weights, size_t n_weights, azg_net** out);
+int azg_net_load(azg_net* net, const float* weights, size_t n_weights);      /* new weights, same architecture */
+/* pi = softmax over legal actions (what predict returns after np.exp), v = tanh value vector. */
+int azg_net_forward(azg_net* net, int n, const int8_t* boards, const uint8_t* mask, float* pi, float* v, void* stream);
+int azg_net_destroy(azg_net* net);
+
+/* ---- search engine: MCTS.py:19-261 for n_games concurrent, independent trees ---------------------- */
+typedef struct {
+    int32_t game_id, num_players;
+    int32_t n_games;                 /* concurrent trees (= threads of Coach.executeEpisodes_batch, Coach.py:86) */
+    int32_t numMCTSSims;             /* main.py:125 */
+    int32_t ratio_fullMCTS;          /* main.py:131 */
+    int32_t universes;               /* main.py:133; 0 => seed -1 */
+    int32_t forced_playouts;         /* main.py:132 */
+    int32_t no_mem_optim;            /* main.py:153 (tree GC is a semantic no-op; kept for flag parity) */
+    int32_t dirichlet_noise;         /* MCTS(..., dirichlet_noise=) MCTS.py:24; Coach passes dirichletAlpha!=0 */
+    int32_t node_cap, edge_cap;      /* per-game arena sizes; 0 => defaults derived from numMCTSSims */
+    double cpuct, fpu, dirichletAlpha, prob_fullMCTS;      /* main.py:126-130 */
+    double temperature[3];           /* main.py:135 ; [2] is the root-prior softmax temperature */
+    double tempThreshold;            /* main.py:136 */
+    uint64_t seed;                   /* device RNG seed (Dirichlet, PCR coin flips, move sampling, chance) */
+} azg_engine_cfg;
+
+typedef struct azg_engine azg_engine;
+int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_engine** out);
+int azg_engine_destroy(azg_engine* e);
+/* MCTS.reset_all_search_trees (MCTS.py:199-203) for all games, or one game slot if game >= 0. */
+int azg_engine_reset(azg_engine* e, int game);
+
+/* MCTS.getActionProb (MCTS.py:49-103) for games [0,n): n_sims simulations each from roots[i] (canonical
+ * boards). Trees persist across calls (tree reuse) until azg_engine_reset.
+ *   full_search  uint8[n] or NULL (=all full): selects numMCTSSims vs numMCTSSims/ratio, Dirichlet at sim 0,
+ *                forced playouts and policy-target pruning exactly as MCTS.py:58-65,75-80.
+ *   noise        float64[n][action_size] or NULL: injected Dirichlet draws (first L entries used, L = number
+ *                of legal actions); NULL => drawn on device.
+ *   out_counts   int32[n][action_size]  root Nsa after policy-target pruning (MCTS.py:75-80)
+ *   out_raw      int32[n][action_size]  root Nsa before pruning (may be NULL)
+ *   out_q        float32[n][num_players] (MCTS.py:71-72) (may be NULL)
+ * Policies are counts/sum(counts) (temp=1); other temperatures are a host-side power of the counts. */
+int azg_engine_search(azg_engine* e, int n, const int8_t* roots, const uint8_t* full_search, const double* noise,
+                      int32_t* out_counts, int32_t* out_raw, float* out_q, void* stream);
+
+/* Coach.executeEpisodes (Coach.py:86-148): keeps all n_games slots playing (refilling finished games)
+ * until at least `min_episodes` games have finished or `max_moves` lock-step plies were played.
+ * Training examples (un-augmented: one per full-search ply) are appended to the engine's example ring
+ * and fetched with azg_engine_examples. Returns counters in out_stats (see azg_engine_stats). */
+int azg_engine_selfplay(azg_engine* e, int min_episodes, int max_moves, void* stream);
+/* Drains up to `cap` finished-game examples: boards int8[cap][S], pi f32[cap][A], z f32[cap][np],
+ * valids u8[cap][A], q f32[cap][np]; *out_n = number written. (tuple layout of Coach.py:76-82) */
+int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n);
+
+/* Counters since creation: [0] sims [1] node_visits (select steps) [2] expansions (nodes with priors)
+ * [3] nn_evals [4] terminal_hits [5] arena_overflows [6] gc_runs [7] max_nodes_in_a_tree
+ * [8] sum_legal (over expansions) [9] moves_played [10] episodes_finished [11] examples_recorded
+ * [12] kernels_launched [13..15] reserved */
+int azg_engine_stats(azg_engine* e, int64_t* out16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
