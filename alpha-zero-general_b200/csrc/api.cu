@@ -60,7 +60,7 @@ struct Scratch {                       // grow-only device buffer
 struct Arg {
     Scratch s; const void* src = nullptr; void* dst = nullptr; void* dev = nullptr; size_t bytes = 0; bool staged = false;
     int in(const void* p, size_t n, cudaStream_t st) {
-        src = p; bytes = n; staged = false; dev = const_cast<void*>(p);
+        src = p; dst = nullptr; bytes = n; staged = false; dev = const_cast<void*>(p);
         if (!p || n == 0) { dev = nullptr; return 0; }
         if (is_device_ptr(p)) return 0;
         if (s.ensure(n)) return 1;
@@ -68,7 +68,7 @@ struct Arg {
         dev = s.p; staged = true; return 0;
     }
     int outbuf(void* p, size_t n) {
-        dst = p; bytes = n; staged = false; dev = p;
+        dst = p; src = nullptr; bytes = n; staged = false; dev = p;
         if (!p || n == 0) { dev = nullptr; return 0; }
         if (is_device_ptr(p)) return 0;
         if (s.ensure(n)) return 1;
