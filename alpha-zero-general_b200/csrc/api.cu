@@ -33,6 +33,8 @@ extern "C" int azg_abi_version(void) { return AZG_ABI_VERSION; }
 extern "C" const char* azg_last_error(void) { return g_err.c_str(); }
 extern "C" int azg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
+extern "C" int azg_set_device(int device) { CK(cudaSetDevice(device)); return 0; }
+
 static int require_device() {
     if (azg_device_count() <= 0) return fail("no CUDA device: the B200 engine has no CPU fallback");
     return 0;
@@ -349,6 +351,7 @@ struct azg_engine {
     unsigned long long launches = 0;
     int sims_full = 0, sims_fast = 0;
     bool sp_ready = false;
+    bool profiling = false; std::vector<cudaEvent_t> ev; size_t ev_used = 0; std::vector<int> ev_kind; double prof_ms[4] = {0, 0, 0, 0}; long long prof_n[4] = {0, 0, 0, 0};
     template <class T> int alloc(T** p, size_t n, bool zero = true) {
         void* q = nullptr;
         if (cudaMalloc(&q, sizeof(T) * n) != cudaSuccess) return fail("cudaMalloc failed for " + std::to_string(sizeof(T) * n) + " bytes (reduce n_games / node_cap / edge_cap)");
@@ -409,6 +412,7 @@ extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_en
 extern "C" int azg_engine_destroy(azg_engine* e) {
     if (!e) return 0;
     for (void* p : e->allocs) cudaFree(p);
+    for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
     delete e; return 0;
 }
 extern "C" int azg_engine_reset(azg_engine* e, int game) {
@@ -419,19 +423,59 @@ extern "C" int azg_engine_reset(azg_engine* e, int game) {
     CKL(); return 0;
 }
 
+// ---- optional per-kernel timing: an event before and after each launch, drained by prof_drain() ----
+enum { PK_SELECT = 0, PK_NET = 1, PK_BACKUP = 2, PK_OTHER = 3 };
+static void prof_mark(azg_engine* e, int kind, cudaStream_t st) {      // kind >= 0: start of a launch of that kind; -1: end
+    if (!e->profiling) return;
+    if (e->ev_used == e->ev.size()) { cudaEvent_t x; cudaEventCreate(&x); e->ev.push_back(x); e->ev_kind.push_back(0); }
+    e->ev_kind[e->ev_used] = kind;
+    cudaEventRecord(e->ev[e->ev_used++], st);
+}
+static int prof_drain(azg_engine* e) {
+    if (e->ev_used == 0) return 0;
+    CK(cudaEventSynchronize(e->ev[e->ev_used - 1]));
+    for (size_t i = 0; i + 1 < e->ev_used; i++) {
+        const int k = e->ev_kind[i];
+        if (k < 0) continue;
+        float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+        e->prof_ms[k] += ms; e->prof_n[k]++;
+    }
+    e->ev_used = 0; return 0;
+}
+
 // One lock-step simulation for every game: select -> batched leaf evaluation -> expand + backup.
 static int engine_step(azg_engine* e, int step, cudaStream_t st) {
     const int G = e->d.n_games; const dim3 grid((unsigned)((G + SEL_WARPS - 1) / SEL_WARPS));
+    prof_mark(e, PK_SELECT, st);
     k_select<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, step);
+    prof_mark(e, PK_NET, st);
     if (net_forward_dev(e->net, e->d.nn_count, e->d.nn_list, e->d.nn_in, SP2::SP, e->d.leaf_mask, e->d.nn_pi, e->d.nn_v, G, st)) return 1;
+    prof_mark(e, PK_BACKUP, st);
     k_backup<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, step);
+    prof_mark(e, -1, st);
     e->launches += 3;
     return 0;
 }
 static int engine_gc(azg_engine* e, int sims, cudaStream_t st) {
     const int G = e->d.n_games; const dim3 grid((unsigned)((G + SEL_WARPS - 1) / SEL_WARPS));
+    prof_mark(e, PK_OTHER, st);
     k_gc<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, sims + 2, (sims + 2) * 48, 0);
+    prof_mark(e, -1, st);
     e->launches++;
+    return 0;
+}
+extern "C" int azg_engine_profile(azg_engine* e, int enable) {
+    if (!e) return fail("engine is NULL");
+    if (prof_drain(e)) return 1;
+    e->profiling = enable != 0;
+    if (enable) for (int k = 0; k < 4; k++) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
+    return 0;
+}
+extern "C" int azg_engine_kernel_times(azg_engine* e, double* out8) {
+    if (!e || !out8) return fail("NULL argument");
+    if (prof_drain(e)) return 1;
+    out8[0] = e->prof_ms[PK_SELECT]; out8[1] = e->prof_ms[PK_NET]; out8[2] = e->prof_ms[PK_BACKUP]; out8[3] = e->prof_ms[PK_OTHER];
+    out8[4] = (double)e->prof_n[PK_SELECT]; out8[5] = (double)e->prof_n[PK_SELECT]; out8[6] = (double)e->prof_n[PK_NET]; out8[7] = (double)e->prof_n[PK_BACKUP];
     return 0;
 }
 
@@ -455,6 +499,7 @@ extern "C" int azg_engine_search(azg_engine* e, int n, const int8_t* roots, cons
     k_finish<SP2><<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(e->d, n, a[3].as<int>(), a[4].as<int>(), a[5].as<float>());
     e->launches++;
     e->d.noise = nullptr;
+    if (e->profiling) { CKL(); if (prof_drain(e)) return 1; }
     FINISH(6);
 }
 

@@ -25,14 +25,19 @@ extern "C" int azg_engine_selfplay(azg_engine* e, int min_episodes, int max_move
     CK(cudaMemcpyAsync(start, e->sp.counters, sizeof(start), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
     const bool pcr = e->cfg.prob_fullMCTS < 1.0;
     for (int mv = 0; max_moves <= 0 || mv < max_moves; mv++) {
+        prof_mark(e, PK_OTHER, st);
         k_sp_begin<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, e->sp, e->sims_full, e->sims_fast);
+        prof_mark(e, -1, st);
         e->launches++;
         const int steps = (e->cfg.prob_fullMCTS > 0.0) ? e->sims_full : e->sims_fast; (void)pcr;
         engine_gc(e, steps, st);
         for (int s = 0; s < steps; s++) if (engine_step(e, s, st)) return 1;
+        prof_mark(e, PK_OTHER, st);
         k_sp_end<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, e->sp);
+        prof_mark(e, -1, st);
         e->launches++;
         CKL();
+        if (e->profiling && prof_drain(e)) return 1;
         if (min_episodes > 0) {
             CK(cudaMemcpyAsync(now, e->sp.counters, sizeof(now), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
             if ((long long)(now[0] - start[0]) >= min_episodes) break;

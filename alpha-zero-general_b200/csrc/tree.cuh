@@ -35,7 +35,7 @@ struct PathEnt { uint32_t node; uint32_t edge_np; };          // edge index (24 
 enum { NODE_EXPANDED = 0, NODE_TERMINAL = 1 };
 enum { LEAF_NONE = 0, LEAF_EXPAND = 1, LEAF_NEW_TERMINAL = 2, LEAF_OLD_TERMINAL = 3 };
 enum { ST_SIMS = 0, ST_VISITS, ST_EXPANSIONS, ST_NNEVALS, ST_TERMINAL, ST_OVERFLOW, ST_GC, ST_MAXNODES, ST_SUMLEGAL,
-       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_N = 16 };
+       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_SELLEGAL = 15, ST_N = 16 };
 
 constexpr double kNanQ = -42.0;                                // MCTS.py:11
 __constant__ long long kMagicSeeds[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   // MCTS.py:14
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_select(Dev<G> d, int step) {
     NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
     const uint64_t* ht = d.g_ht(g);
     PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
-    int depth = 0, kind = LEAF_NONE;
+    int depth = 0, kind = LEAF_NONE, sum_legal = 0;
     for (;;) {
         uint64_t klo, khi;
         board_hash<G>(sb, lane, klo, khi);
@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_select(Dev<G> d, int step) {
         }
         const int e = puct_select(edges + h.edge_off, h.n_legal, h.ns, h.qs, d.cpuct, d.fpu, depth == 0 && forced_root, step, lane);
         const int a = acts[h.edge_off + e];
+        sum_legal += h.n_legal;
         int np = 0;
         if (lane == 0) {
             np = G::make_move(sb, a, 0, seed, nullptr);          // seed != 0 in search: deterministic chance
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_select(Dev<G> d, int step) {
         depth++;
         if (depth >= G::MAX_DEPTH) break;
     }
-    if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; }
+    if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; }
 }
 
 // ============================================================ expand + backup =========================

@@ -14,7 +14,7 @@ AZG_NET_HASH = 0
 AZG_NET_SPLENDOR_V80 = 80
 
 # every symbol include/azg.h declares (checked by tests/test_abi.py)
-SYMBOLS = ['azg_abi_version', 'azg_last_error', 'azg_device_count', 'azg_game_info', 'azg_game_init', 'azg_game_valid',
+SYMBOLS = ['azg_abi_version', 'azg_last_error', 'azg_device_count', 'azg_set_device', 'azg_engine_profile', 'azg_engine_kernel_times', 'azg_game_info', 'azg_game_init', 'azg_game_valid',
            'azg_game_next', 'azg_game_ended', 'azg_game_canonical', 'azg_game_round_score', 'azg_game_symmetries',
            'azg_net_create', 'azg_net_load', 'azg_net_forward', 'azg_net_destroy', 'azg_engine_create', 'azg_engine_destroy',
            'azg_engine_reset', 'azg_engine_search', 'azg_engine_selfplay', 'azg_engine_examples', 'azg_engine_stats']
@@ -76,6 +76,9 @@ def load():
     L.azg_engine_selfplay.argtypes = [vp, i32, i32, vp]
     L.azg_engine_examples.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(i32)]
     L.azg_engine_stats.argtypes = [vp, vp]
+    L.azg_set_device.argtypes = [i32]
+    L.azg_engine_profile.argtypes = [vp, i32]
+    L.azg_engine_kernel_times.argtypes = [vp, vp]
     for name in SYMBOLS:
         if name not in ('azg_last_error',):
             getattr(L, name).restype = i32
@@ -113,4 +116,4 @@ def game_info(game_id=AZG_GAME_SPLENDOR, num_players=2):
 
 STAT_NAMES = ['sims', 'node_visits', 'expansions', 'nn_evals', 'terminal_hits', 'arena_overflows', 'gc_runs', 'max_nodes',
               'sum_legal', 'moves_played', 'episodes_finished', 'examples_recorded', 'kernels_launched', 'node_cap', 'edge_cap',
-              'reserved']
+              'sum_legal_visited']

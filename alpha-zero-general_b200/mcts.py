@@ -36,14 +36,17 @@ class Engine:
     def reset(self, game=-1):
         _lib.check(self._L.azg_engine_reset(self.h, game))
 
-    def search(self, roots, full_search=None, noise=None, out=None):
+    def search(self, roots, full_search=None, noise=None, out=None, stream=None):
         """getActionProb for games [0,n). Host (numpy) or device (torch CUDA) buffers.
         Returns (counts int32[n,A], raw_counts int32[n,A], q float32[n,np])."""
         A, S, NPL = self.info.action_size, self.info.state_bytes, self.game.num_players
         if isinstance(roots, np.ndarray):
             roots = np.ascontiguousarray(roots, dtype=np.int8).reshape(-1, S)
             n = len(roots)
-            counts = np.empty((n, A), np.int32); raw = np.empty((n, A), np.int32); q = np.empty((n, NPL), np.float32)
+            if out is not None:
+                counts, raw, q = out
+            else:
+                counts = np.empty((n, A), np.int32); raw = np.empty((n, A), np.int32); q = np.empty((n, NPL), np.float32)
             fs = None if full_search is None else np.ascontiguousarray(np.asarray(full_search).astype(np.uint8))
             nz = None
             if noise is not None:
@@ -55,11 +58,20 @@ class Engine:
             counts, raw, q = out
             fs, nz = full_search, noise
         _lib.check(self._L.azg_engine_search(self.h, n, _lib.ptr(roots), _lib.ptr(fs), _lib.ptr(nz), _lib.ptr(counts), _lib.ptr(raw),
-                                             _lib.ptr(q), None))
+                                             _lib.ptr(q), stream))
         return counts, raw, q
 
-    def selfplay(self, min_episodes=0, max_moves=0):
-        _lib.check(self._L.azg_engine_selfplay(self.h, int(min_episodes), int(max_moves), None))
+    def selfplay(self, min_episodes=0, max_moves=0, stream=None):
+        _lib.check(self._L.azg_engine_selfplay(self.h, int(min_episodes), int(max_moves), stream))
+
+    def profile(self, enable):
+        _lib.check(self._L.azg_engine_profile(self.h, int(bool(enable))))
+
+    def kernel_times(self):
+        out = np.zeros(8, np.float64)
+        _lib.check(self._L.azg_engine_kernel_times(self.h, _lib.ptr(out)))
+        keys = ('select_ms', 'net_ms', 'backup_ms', 'other_ms', 'steps', 'select_launches', 'net_launches', 'backup_launches')
+        return dict(zip(keys, out.tolist()))
 
     def examples(self, cap):
         A, S, NPL = self.info.action_size, self.info.state_bytes, self.game.num_players

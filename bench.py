@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- self-play MCTS sims/sec of the B200 engine (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's engine
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm: the oracle port of the reference path
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU)
+
+Workload (config.workload): BASELINE.json configs[2] -- Splendor 2-player with chance-node card draws
+(universes=3), 16384 concurrent self-play games per GPU, numMCTSSims=800, every move a full search, SplendorNNet
+V80 random-init (seed 0), root Dirichlet noise on.  One STEP = one self-play ply of every game = 800 lock-step
+simulations x n_games trees (select -> batched V80 forward -> expand+backup), plus the move itself.
+
+  value  : device-resident arm. azg_engine_selfplay plays W warm-up plies then K timed plies entirely on the GPU
+           (Coach.executeEpisodes equivalent); sims counted by the engine's own counters; CUDA events on the
+           launching stream; max over ranks.
+  e2e    : the same K plies driven through the reference-facing plugin calls with HOST buffers
+           (MCTS.getActionProb-> azg_engine_search, Game.getNextState/getGameEnded/getCanonicalForm ->
+           azg_game_*), pinned host memory, every host<->device copy inside the timed region.
+  roofline : dominant kernel by device time (CUDA events around every launch inside the timed region).
+  cpu_baseline : oracle port (oracle/azg_oracle.c) of the same path on all host threads, bounded sample.
+
+The working set (trees: tens of GB) is far larger than L2 (126 MB), so no explicit L2 flush is needed (config.l2).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'selfplay_mcts_sims_per_sec'
+UNIT = 'sims/s'
+V80_FLOPS = 2 * 521205            # multiply-adds of one V80 leaf evaluation (1.04 MFLOP)
+S_BYTES, N_ACT, N_PL = 392, 81, 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--games', type=int, default=16384, help='concurrent games per GPU')
+    ap.add_argument('--sims', type=int, default=800)
+    ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 5 x sims + 96)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-plies', type=int, default=12, help='plies per thread of the cpu_baseline sample')
+    return ap.parse_args()
+
+
+def mcts_args(sims):
+    # main.py defaults + config C3: universes=3, every move a full search
+    return dict(numMCTSSims=sims, cpuct=1.25, fpu=0.0, universes=3, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1],
+                tempThreshold=10, prob_fullMCTS=1.0, ratio_fullMCTS=5, forced_playouts=False, no_mem_optim=False)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d['hbm_gbs']), bf16=float(d['bf16_tflops']), bf16_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                    src='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+# --------------------------------------------------------------------------- clocks --------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i', str(index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ''
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm), reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------- reference (CPU) arm -------
+def cpu_sample(sims, plies, threads, seed=1):
+    """Oracle port of Coach.executeEpisode / MCTS.search / Splendor Board / V80 forward on `threads` host threads,
+    each playing one self-play game truncated after `plies` plies. Returns the oracle's counters."""
+    from oracle import oracle as O
+    from azg_b200.nnet import random_v80_state_dict
+    a = mcts_args(sims)
+    cfg = O.make_cfg(numMCTSSims=sims, net_kind=1, universes=a['universes'], prob_fullMCTS=1.0, cpuct=a['cpuct'], fpu=a['fpu'],
+                     dirichletAlpha=a['dirichletAlpha'], temperature2=a['temperature'][2])
+    blob = O.v80_blob(random_v80_state_dict(0))
+    return O.selfplay_bench(cfg, blob, threads, 1, max_plies=plies, temperature=a['temperature'][:2], tempThreshold=a['tempThreshold'], seed=seed)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    plies = 2                                               # one step = every host thread plays 2 plies (2 x sims sims)
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(args.sims, 1, threads)
+    t0 = time.perf_counter(); sims = 0
+    for k in range(args.steps):
+        r = cpu_sample(args.sims, plies, threads, seed=100 + k); sims += r['sims']
+    dt = time.perf_counter() - t0
+    val = sims / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32/f64',
+            'data': 'synthetic', 'config': workload_cfg(args, threads),
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': f'{threads} host threads x 1 Splendor self-play game x {plies} plies x {args.sims} sims per step, {args.steps} steps; '
+                                       'oracle/azg_oracle.c (C port of the reference path; the Python/numba reference cannot travel to the GPU box)'},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_cfg(args, cpu_threads=None):
+    c = {'workload': f'splendor2p_chance_universes3_{args.games}games_per_gpu_{args.sims}sims_V80_randinit', 'game': 'splendor', 'num_players': 2,
+         'games_per_gpu': args.games, 'numMCTSSims': args.sims, 'net': 'SplendorNNet V80 (142406 params, random init seed 0)',
+         'universes': 3, 'prob_fullMCTS': 1.0, 'dirichlet_noise': True, 'step': 'one self-play ply of every game (numMCTSSims lock-step simulations per tree)',
+         'parallelism': f'games sharded over {args.gpus} GPU(s), no data-path collective', 'l2': 'working set >> L2 (tree arenas of tens of GB); no flush needed'}
+    if cpu_threads:
+        c['cpu_threads'] = cpu_threads
+    return c
+
+
+# --------------------------------------------------------------------------- e2e (host-buffer) arm -----
+class HostLoop:
+    """Coach.executeEpisode written against the plugin calls, batched over all games, with pinned HOST buffers."""
+
+    def __init__(self, torch, game, eng, n, seed):
+        import azg_b200.lib as lib
+        self.lib = lib; self.L = lib.load(); self.game = game; self.eng = eng; self.n = n
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+        self.board = pin((n, S_BYTES), torch.int8); self.board2 = pin((n, S_BYTES), torch.int8); self.roots = pin((n, S_BYTES), torch.int8)
+        self.player = pin((n,), torch.int32); self.player2 = pin((n,), torch.int32); self.action = pin((n,), torch.int32)
+        self.seeds = pin((n,), torch.int64); self.keys = pin((n,), torch.int64).view(np.uint64); self.ended = pin((n, N_PL), torch.float32)
+        self.counts = pin((n, N_ACT), torch.int32); self.raw = pin((n, N_ACT), torch.int32); self.q = pin((n, N_PL), torch.float32)
+        self.rng = np.random.default_rng(seed); self.key_ctr = 1 << 20
+        self.board[:] = game.init_batch(np.arange(1, n + 1, dtype=np.uint64) + (seed << 32)).reshape(n, S_BYTES)
+        self.player[:] = 0; self.seeds[:] = 0
+        self.roots[:] = self.board
+        self.h2d = 0; self.d2h = 0
+
+    def step(self):
+        lib, L, g, n = self.lib, self.L, self.game, self.n
+        p = lib.ptr
+        # MCTS.getActionProb for every game (host roots in, host counts out)
+        lib.check(L.azg_engine_search(self.eng.h, n, p(self.roots), None, None, p(self.counts), p(self.raw), p(self.q), None))
+        self.h2d += self.roots.nbytes; self.d2h += self.counts.nbytes + self.raw.nbytes + self.q.nbytes
+        # Coach.py:63 random_pick with temp_for_selfplay ~ 1 (early plies): sample from the visit counts
+        c = self.counts.astype(np.float64); cs = np.cumsum(c, axis=1); u = self.rng.random(n) * cs[:, -1]
+        self.action[:] = np.minimum((cs <= u[:, None]).sum(axis=1), N_ACT - 1)
+        # Game.getNextState with a true random chance draw (random_seed=0), Coach.py:71
+        self.keys[:] = np.arange(self.key_ctr, self.key_ctr + n, dtype=np.uint64); self.key_ctr += n
+        lib.check(L.azg_game_next(g.game_id, N_PL, n, p(self.board), p(self.player), p(self.action), p(self.seeds), p(self.keys),
+                                  p(self.board2), p(self.player2), None))
+        self.h2d += self.board.nbytes + self.player.nbytes + self.action.nbytes + self.seeds.nbytes + self.keys.nbytes
+        self.d2h += self.board2.nbytes + self.player2.nbytes
+        self.board, self.board2 = self.board2, self.board; self.player, self.player2 = self.player2, self.player
+        # Game.getGameEnded, Coach.py:73
+        lib.check(L.azg_game_ended(g.game_id, N_PL, n, p(self.board), p(self.ended), None))
+        self.h2d += self.board.nbytes; self.d2h += self.ended.nbytes
+        done = np.flatnonzero(self.ended.any(axis=1))
+        for i in done:                                              # finished game: new game + fresh tree in that slot (Coach.py:93-98)
+            self.board[i] = g.init_batch(np.array([self.key_ctr + int(i)], dtype=np.uint64)).reshape(-1); self.player[i] = 0
+            self.eng.reset(int(i))
+        # Game.getCanonicalForm, Coach.py:61
+        lib.check(L.azg_game_canonical(g.game_id, N_PL, n, p(self.board), p(self.player), p(self.roots), None))
+        self.h2d += self.board.nbytes + self.player.nbytes; self.d2h += self.roots.nbytes
+
+
+# --------------------------------------------------------------------------- main (B200 arm) -----------
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return 0
+    import torch
+    import torch.distributed as dist
+    import azg_b200
+    from azg_b200 import lib
+    from azg_b200.mcts import Engine
+    if not torch.cuda.is_available() or lib.device_count() <= 0:
+        raise SystemExit('bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    lib.check(lib.load().azg_set_device(local))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    game = azg_b200.SplendorGame()
+    net = azg_b200.NNetWrapper(game, {'nn_version': 80}, seed=0)             # identical weights on every rank
+    a = mcts_args(args.sims)
+    node_cap = args.node_cap or (5 * args.sims + 96)
+    eng = Engine(game, net, a, n_games=args.games, dirichlet_noise=True, seed=1000 + rank, node_cap=node_cap)
+    K, W = args.steps, args.warmup
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident arm ------------------------------------------------------------------------
+    eng.selfplay(max_moves=W)                                                  # warm-up plies (untimed)
+    s0 = eng.stats()
+    eng.profile(True)
+    clocks = ClockSampler(local)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    eng.selfplay(max_moves=K)
+    e1.record(stream)
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    kt = eng.kernel_times(); eng.profile(False)
+    s1 = eng.stats()
+    d = {k: s1[k] - s0[k] for k in s1 if k not in ('max_nodes', 'node_cap', 'edge_cap')}
+    ms = max_over_ranks(ms_local)
+    sims_total = sum_over_ranks(d['sims'])
+    value = sims_total / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0's launches; all ranks run the same kernels) --------------
+    pk = peaks()
+    visits, exps, evals = d['node_visits'], d['expansions'], d['nn_evals']
+    Lbar_vis = d['sum_legal_visited'] / max(visits, 1); Lbar_exp = d['sum_legal'] / max(exps, 1); Dbar = visits / max(d['sims'], 1)
+    n_launch = max(int(kt['select_launches']), 1)
+    sel_bytes = 16.0 * visits + 14.0 * d['sum_legal_visited']                    # B_sel = 16 + 14 L per select step
+    bak_bytes = 32.0 * visits + (2.0 * S_BYTES + 32.0) * exps + 14.0 * d['sum_legal'] + (S_BYTES + 11 + 4 * N_ACT + 4 * N_PL) * evals  # B_bak, B_exp, B_nn
+    net_flops = float(V80_FLOPS) * evals
+    kern = {
+        'select': {'ms': kt['select_ms'], 'bound': 'hbm', 'achieved': sel_bytes / max(kt['select_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
+                   'per_launch_bytes': sel_bytes / n_launch},
+        'net_v80': {'ms': kt['net_ms'], 'bound': 'tensor', 'achieved': net_flops / max(kt['net_ms'], 1e-9) / 1e9, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+                    'per_launch_flops': net_flops / n_launch},
+        'expand_backup': {'ms': kt['backup_ms'], 'bound': 'hbm', 'achieved': bak_bytes / max(kt['backup_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
+                          'per_launch_bytes': bak_bytes / n_launch},
+    }
+    tot_ms = kt['select_ms'] + kt['net_ms'] + kt['backup_ms'] + kt['other_ms']
+    for v in kern.values():
+        v['frac'] = v['achieved'] / v['peak']; v['share'] = v['ms'] / max(tot_ms, 1e-9); v['avg_launch_us'] = 1e3 * v['ms'] / n_launch
+    dom = max(kern, key=lambda k: kern[k]['ms'])
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')                          # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom)
+    roofline = {'kernel': dom, 'bound': kern[dom]['bound'], 'achieved': kern[dom]['achieved'], 'peak': kern[dom]['peak'], 'unit': kern[dom]['unit'],
+                'frac': kern[dom]['frac'], 'traffic': traffic, 'peak_source': pk['src'] + (' sustained bf16' if kern[dom]['bound'] == 'tensor' else ''),
+                'avg_launch_us': kern[dom]['avg_launch_us'], 'share_of_step': kern[dom]['share']}
+
+    # ---- e2e arm: same plies through the plugin calls with host buffers ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        eng.reset()
+        hl = HostLoop(torch, game, eng, args.games, seed=7 + rank)
+        for _ in range(W):
+            hl.step()
+        hl.h2d = hl.d2h = 0
+        t0 = eng.stats()
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(K):
+            hl.step()
+        f1.record(stream)
+        barrier()
+        ms2 = max_over_ranks(f0.elapsed_time(f1))
+        t1 = eng.stats()
+        sims2 = sum_over_ranks(t1['sims'] - t0['sims'])
+        e2e = {'value': sims2 / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': hl.h2d // K, 'd2h_bytes_per_step': hl.d2h // K,
+               'ms_per_step': ms2 / K, 'api': 'azg_engine_search + azg_game_next/ended/canonical with pinned host buffers'}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        r = cpu_sample(args.sims, args.cpu_plies, threads)
+        cpu = {'value': r['sims'] / r['seconds'], 'unit': UNIT, 'cores': threads, 'kind': 'port', 'seconds': r['seconds'],
+               'sample': f'{threads} host threads x 1 Splendor self-play game x {args.cpu_plies} plies x {args.sims} sims (oracle/azg_oracle.c, same MCTS args and V80 weights)'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 net / f64 PUCT / i8 boards', 'data': 'synthetic',
+                'config': workload_cfg(args), 'e2e': e2e, 'gpu_launches': int(d['kernels_launched']), 'roofline': roofline, 'cpu_baseline': cpu,
+                'clocks': clk, 'kernels': kern,
+                'counters': {'sims': d['sims'], 'node_visits': visits, 'expansions': exps, 'nn_evals': evals, 'terminal_hits': d['terminal_hits'],
+                             'arena_overflows': d['arena_overflows'], 'gc_runs': d['gc_runs'], 'moves_played': d['moves_played'],
+                             'episodes_finished': d['episodes_finished'], 'mean_depth': Dbar, 'mean_legal_visited': Lbar_vis, 'mean_legal_expanded': Lbar_exp,
+                             'expansions_per_sec': sum_over_ranks(exps) / (ms * 1e-3) if world == 1 else None, 'node_visits_per_sec': visits / (ms * 1e-3) if world == 1 else None,
+                             'node_cap': s1['node_cap'], 'max_nodes': s1['max_nodes']}}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

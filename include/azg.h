@@ -43,6 +43,7 @@ typedef struct {
 int azg_abi_version(void);
 const char* azg_last_error(void);
 int azg_device_count(void);                               /* 0 when no CUDA device is usable */
+int azg_set_device(int device);                           /* device used by handles created afterwards on this thread */
 int azg_game_info(int game_id, int num_players, azg_game_info_t* out);
 
 /* ---- batched game step: the *LogicNumba.Board methods behind the Game facade ------------------- */
@@ -130,8 +131,16 @@ int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float
 /* Counters since creation: [0] sims [1] node_visits (select steps) [2] expansions (nodes with priors)
  * [3] nn_evals [4] terminal_hits [5] arena_overflows [6] gc_runs [7] max_nodes_in_a_tree
  * [8] sum_legal (over expansions) [9] moves_played [10] episodes_finished [11] examples_recorded
- * [12] kernels_launched [13..15] reserved */
+ * [12] kernels_launched [13] node_cap [14] edge_cap [15] sum_legal_visited (sum of n_legal over select steps) */
 int azg_engine_stats(azg_engine* e, int64_t* out16);
+
+/* Per-kernel device timing (CUDA events on the launching stream around every launch of the search loop).
+ * enable=1 starts collecting (slows the loop down slightly: use a separate measuring pass), enable=0 stops.
+ * azg_engine_kernel_times drains the events: out8 = [0] select ms [1] leaf-eval (net) ms [2] expand+backup ms
+ * [3] other (gc, move begin/end, finish) ms [4] profiled lock-step simulations [5] select launches
+ * [6] net launches [7] backup launches. */
+int azg_engine_profile(azg_engine* e, int enable);
+int azg_engine_kernel_times(azg_engine* e, double* out8);
 
 #ifdef __cplusplus
 }
