@@ -365,7 +365,7 @@ __global__ void k_load_roots(Dev<SP2> d, int n, const int8_t* roots, const uint8
     if (g >= d.n_games) return;
     if (g < n) {
         for (int i = lane; i < SP2::SP; i += 32) d.root[(size_t)g * SP2::SP + i] = i < SP2::S ? roots[(size_t)g * SP2::S + i] : (int8_t)0;
-        if (lane == 0) { const bool f = full ? full[g] != 0 : true; d.full[g] = f; d.n_sims[g] = f ? sims_full : sims_fast; }
+        if (lane == 0) { const bool f = full ? full[g] != 0 : true; d.full[g] = f; d.n_sims[g] = f ? sims_full : sims_fast; d.root_node[g] = 0; }
     } else if (lane == 0) d.n_sims[g] = 0;
 }
 
@@ -382,17 +382,19 @@ extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_en
         // default: room for the nodes that survive tree reuse (measured <= ~10x sims/move with a random-init net)
         // bounded by 60 % of free HBM
         size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-        const double per_node = 32.0 + 36.0 * 17.0 + 2 * 8.0;
+        const int U0 = std::max(cfg->universes, 1);
+        const double per_node = 32.0 + SP2::SP + 4.0 + 44.0 * (17.0 + 4.0 * U0) + 2 * 8.0;
         double fit = 0.6 * (double)free_b / (double)G / per_node;
         node_cap = (int)std::min<double>(fit, 16.0 * cfg->numMCTSSims + 1024);
         node_cap = std::max(node_cap, cfg->numMCTSSims + 64);
     }
-    if (edge_cap <= 0) edge_cap = node_cap * 36;
+    if (edge_cap <= 0) edge_cap = node_cap * 44;             // mean legal moves per expanded node ~38-42 (measured)
     if (edge_cap >= (1 << 24)) return fail("edge_cap must be < 2^24");
     e->cfg.node_cap = node_cap; e->cfg.edge_cap = edge_cap;
     Dev<SP2>& d = e->d;
     d.n_games = G; d.node_cap = node_cap; d.edge_cap = edge_cap; d.ht_cap = next_pow2(2 * node_cap);
-    d.universes = cfg->universes; d.forced_playouts = cfg->forced_playouts; d.dirichlet_noise = cfg->dirichlet_noise;
+    if (cfg->universes < 0 || cfg->universes > 8) { delete e; return fail("universes must be in [0, 8]"); }
+    d.universes = cfg->universes; d.U = std::max(cfg->universes, 1); d.forced_playouts = cfg->forced_playouts; d.dirichlet_noise = cfg->dirichlet_noise;
     d.cpuct = cfg->cpuct; d.fpu = cfg->fpu; d.dir_alpha = cfg->dirichletAlpha; d.temp2 = cfg->temperature[2]; d.seed = cfg->seed;
     d.noise = nullptr;
     e->sims_full = cfg->numMCTSSims; e->sims_fast = cfg->ratio_fullMCTS > 0 ? cfg->numMCTSSims / cfg->ratio_fullMCTS : cfg->numMCTSSims;
@@ -400,6 +402,8 @@ extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_en
     bad |= e->alloc(&d.nodes, (size_t)G * node_cap, false); bad |= e->alloc(&d.edges, (size_t)G * edge_cap, false);
     bad |= e->alloc(&d.acts, (size_t)G * edge_cap, false); bad |= e->alloc(&d.ht, (size_t)G * d.ht_cap);
     bad |= e->alloc(&d.n_nodes, G); bad |= e->alloc(&d.n_edges, G);
+    bad |= e->alloc(&d.child, (size_t)G * edge_cap * d.U, false); bad |= e->alloc(&d.boards, (size_t)G * node_cap * SP2::SP, false);
+    bad |= e->alloc(&d.remap, (size_t)G * node_cap, false); bad |= e->alloc(&d.gcq, (size_t)G * node_cap, false); bad |= e->alloc(&d.root_node, G); bad |= e->alloc(&d.leaf_link, G);
     bad |= e->alloc(&d.root, (size_t)G * SP2::SP); bad |= e->alloc(&d.n_sims, G); bad |= e->alloc(&d.full, G); bad |= e->alloc(&d.move_ctr, G);
     bad |= e->alloc(&d.path, (size_t)G * SP2::MAX_DEPTH); bad |= e->alloc(&d.path_len, G); bad |= e->alloc(&d.leaf_kind, G);
     bad |= e->alloc(&d.leaf_key, (size_t)2 * G); bad |= e->alloc(&d.leaf_v, (size_t)G * SP2::NP); bad |= e->alloc(&d.leaf_mask, (size_t)G * SP2::MASK_WORDS);
@@ -516,7 +520,7 @@ extern "C" int azg_engine_stats(azg_engine* e, int64_t* out16) {
             else out16[k] += (int64_t)h[(size_t)g * ST_N + k];
         }
     out16[12] = (int64_t)(e->launches + (e->net ? e->net->launches : 0));
-    out16[13] = e->d.node_cap; out16[14] = e->d.edge_cap;
+    out16[14] = e->d.node_cap;
     return 0;
 }
 

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_sp_begin(Dev<G> d, SelfPlay<
         const int ply = sp.ply[g] + 1; sp.ply[g] = ply;
         Philox rng(d.seed, ((uint64_t)g << 8) | 3u, ((uint64_t)sp.games_started[g] << 16) | (unsigned)ply);
         const bool full = rng.uniform() < sp.prob_full;           // MCTS.py:58
-        d.full[g] = full; d.n_sims[g] = full ? sims_full : sims_fast;
+        d.full[g] = full; d.n_sims[g] = full ? sims_full : sims_fast; d.root_node[g] = 0;
     }
 }
 

@@ -2,11 +2,15 @@
 //
 // Replaces MCTS.search and its njit helpers (MCTS.py:105-261) for n_games independent trees advanced in
 // lock-step, one simulation per game per step, ONE WARP PER GAME:
-//   k_select  : root -> leaf walk. Per level: 128-bit board hash -> warp-wide probe of the game's open-
-//               addressing table -> 32 B node header -> coalesced read of the node's legal-edge array
-//               (16 B/edge) -> PUCT argmax by warp shuffle (first index wins ties, MCTS.py:227-228) ->
-//               make_move + swap_players on the board held in shared memory (children are recomputed,
-//               never cached: MCTS.py:233-248).
+//   k_select  : root -> leaf walk. Per level: 32 B node header -> coalesced read of the node's legal-edge
+//               array (16 B/edge) together with the per-(edge, universe) child links -> PUCT argmax by warp
+//               shuffle (first index wins ties, MCTS.py:227-228) -> follow the child link. The reference
+//               recomputes every child state on every traversal and finds it again through a dict of board
+//               bytes (MCTS.py:125,233-248); here the FIRST traversal of an (edge, universe) does exactly
+//               that (parent board from the node's board slot -> make_move + swap_players in shared memory
+//               -> 128-bit board hash -> warp-wide probe of the game's open-addressing table, so
+//               transpositions resolve to the same node as in the reference) and stores the resulting node
+//               index in the link; later traversals are a pure pointer walk.
 //   (net)     : batched leaf evaluation of the compacted leaf list (GenericNNetWrapper.predict_server).
 //   k_backup  : writes the new node (normalised priors, Q=-42 sentinel, N=0), inserts it in the table,
 //               then backs the value up the recorded path, lanes parallel over levels (MCTS.py:176-181).
@@ -17,6 +21,8 @@
 //   nodes [node_cap] NodeHdr 32 B : 128-bit key, Ns, Qs, edge_off, n_legal, round, kind
 //   edges [edge_cap] Edge    16 B : {Q f64, P f32, N i32} for LEGAL actions only, ascending action index
 //   acts  [edge_cap] act_t        : action id of each edge
+//   child [edge_cap][U] u32       : (next_player << 28) | (child node index + 1), 0 = not resolved yet; U = universes
+//   boards[node_cap][SP] i8       : canonical board of every expanded node (source of first-traversal make_move)
 //   ht    [ht_cap]   u64          : (tag32 << 32) | (node index + 1), 0 = empty, linear probing
 #pragma once
 #include "common.cuh"
@@ -35,7 +41,7 @@ struct PathEnt { uint32_t node; uint32_t edge_np; };          // edge index (24 
 enum { NODE_EXPANDED = 0, NODE_TERMINAL = 1 };
 enum { LEAF_NONE = 0, LEAF_EXPAND = 1, LEAF_NEW_TERMINAL = 2, LEAF_OLD_TERMINAL = 3 };
 enum { ST_SIMS = 0, ST_VISITS, ST_EXPANSIONS, ST_NNEVALS, ST_TERMINAL, ST_OVERFLOW, ST_GC, ST_MAXNODES, ST_SUMLEGAL,
-       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_SELLEGAL = 15, ST_N = 16 };
+       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_GC_SWEEP = 13, ST_SELLEGAL = 15, ST_N = 16 };
 
 constexpr double kNanQ = -42.0;                                // MCTS.py:11
 __constant__ long long kMagicSeeds[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   // MCTS.py:14
@@ -44,11 +50,14 @@ template <class G>
 struct Dev {
     // configuration
     int n_games, node_cap, edge_cap, ht_cap;
-    int universes, forced_playouts, dirichlet_noise;
+    int universes, U, forced_playouts, dirichlet_noise;         // U = max(universes, 1): child links per edge
     double cpuct, fpu, dir_alpha, temp2;
     uint64_t seed;
     // trees
     NodeHdr* nodes; Edge* edges; typename G::act_t* acts; uint64_t* ht; int* n_nodes; int* n_edges;
+    uint32_t* child; int8_t* boards; int* remap; int* gcq;     // remap, gcq: [G][node_cap] scratch of the tree GC
+    int* root_node;                                            // [G] root node index + 1 once known for this search, else 0
+    uint32_t* leaf_link;                                       // [G] child-link slot (index into child, +1) the new leaf hangs on; 0 = root
     // search control (per game)
     int8_t* root;              // [G][SP] canonical root boards
     int* n_sims;               // sims requested for the current search
@@ -64,7 +73,10 @@ struct Dev {
     __device__ __forceinline__ Edge* g_edges(int g) const { return edges + (size_t)g * edge_cap; }
     __device__ __forceinline__ typename G::act_t* g_acts(int g) const { return acts + (size_t)g * edge_cap; }
     __device__ __forceinline__ uint64_t* g_ht(int g) const { return ht + (size_t)g * ht_cap; }
+    __device__ __forceinline__ uint32_t* g_child(int g) const { return child + (size_t)g * edge_cap * U; }
+    __device__ __forceinline__ int8_t* g_boards(int g) const { return boards + (size_t)g * node_cap * G::SP; }
 };
+constexpr uint32_t LINK_IDX = 0x0FFFFFFFu;                      // child link: low 28 bits = node index + 1, high 4 = next player
 
 // ---- board hash (WARP): sum over words of two independent 64-bit mixes of (position, word) ----------
 template <class G>
@@ -180,128 +192,192 @@ __device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const
     __syncwarp();
 }
 
-// ---- PUCT (WARP): pick_highest_UCB, MCTS.py:210-230; returns the edge index -----------------------------
-__device__ __forceinline__ int puct_select(const Edge* e, int L, int ns, float qs, double cpuct, double fpu,
-                                           bool forced, int n_iter, int lane) {
+// ---- PUCT (WARP): pick_highest_UCB, MCTS.py:210-230; returns the edge index and, in `link`, the child link
+// of that edge for universe `uni` (fetched together with the edges so that following it costs no extra round trip).
+__device__ __forceinline__ int puct_select(const Edge* e, const uint32_t* child, int U, int uni, int L, int ns, float qs,
+                                           double cpuct, double fpu, bool forced, int n_iter, int lane, uint32_t& link) {
     const double fpu_init = fpu > 0 ? __dsub_rn((double)qs, fpu) : fpu;
     const double c0 = __dmul_rn(cpuct, __dsqrt_rn(__dadd_rn((double)ns, 1e-8)));
     const double c1 = __dmul_rn(cpuct, __dsqrt_rn((double)ns));
     const double kn = __dmul_rn((double)n_iter, 0.5);
-    double best = -INFINITY; int best_i = 0x7FFFFFFF, forced_i = 0x7FFFFFFF;
+    double best = -INFINITY; int best_i = 0x7FFFFFFF, forced_i = 0x7FFFFFFF; uint32_t best_c = 0;
     for (int i = lane; i < L; i += 32) {
-        Edge ed = e[i];
-        double pd = (double)ed.p;
+        const Edge ed = e[i];
+        const uint32_t c = child[(size_t)i * U + uni];
+        const double pd = (double)ed.p;
         if (forced) {
             long long th = __double2ll_rz(__dsqrt_rn(__dmul_rn(kn, pd)));
             if ((long long)ed.n < th && i < forced_i) forced_i = i;
         }
-        double u = ed.q != kNanQ ? __dadd_rn(ed.q, __ddiv_rn(__dmul_rn(c1, pd), (double)(ed.n + 1)))
-                                 : __fma_rn(c0, pd, fpu_init);
-        if (u > best) { best = u; best_i = i; }
+        const double ucb = ed.q != kNanQ ? __dadd_rn(ed.q, __ddiv_rn(__dmul_rn(c1, pd), (double)(ed.n + 1)))
+                                         : __fma_rn(c0, pd, fpu_init);
+        if (ucb > best) { best = ucb; best_i = i; best_c = c; }
     }
     if (forced) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) forced_i = min(forced_i, __shfl_xor_sync(FULL, forced_i, o));
-        if (forced_i != 0x7FFFFFFF) return forced_i;
+        if (forced_i != 0x7FFFFFFF) { link = child[(size_t)forced_i * U + uni]; return forced_i; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         double ob = __shfl_xor_sync(FULL, best, o); int oi = __shfl_xor_sync(FULL, best_i, o);
         if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
     }
+    link = __shfl_sync(FULL, best_c, best_i & 31);               // the winner is the local best of lane (best_i % 32)
     return best_i;
 }
 
 constexpr int SEL_WARPS = 4;
+#ifndef AZG_SEL_MIN_BLOCKS
+#define AZG_SEL_MIN_BLOCKS 8                                  // 64 registers/thread -> 32 resident warps (games) per SM
+#endif
 template <class G> struct WarpSmem {
     __align__(16) int8_t board[G::SP];
     __align__(16) float f[(G::A + 31) / 32 * 32];
     __align__(16) double d[(G::A + 31) / 32 * 32];
+    uint64_t key[2]; int np;                                     // key / next player of the state in `board` (select kernel)
 };
+
+template <class G> __device__ __forceinline__ void warp_load_board(int8_t* sb, const int8_t* src, int lane) {
+    if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(src)[lane];
+    if (G::SP / 16 > 32) for (int i = lane + 32; i < G::SP / 16; i += 32) reinterpret_cast<uint4*>(sb)[i] = reinterpret_cast<const uint4*>(src)[i];
+    __syncwarp();
+}
+template <class G> __device__ __forceinline__ void warp_store_board(int8_t* dst, const int8_t* sb, int lane) {
+    for (int i = lane; i < G::SP / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(sb)[i];
+}
+
+// Re-noise an already expanded root (MCTS.py:156-160): the stored P of the root's edges gets a fresh Dirichlet mix.
+template <class G>
+__device__ __noinline__ void renoise_root(const Dev<G>& d, int g, uint32_t edge_off, int n_legal, Edge* edges, const typename G::act_t* acts,
+                                          WarpSmem<G>& ws, int lane) {
+    struct { uint32_t edge_off; int n_legal; } h = {edge_off, n_legal};
+    float* pf = ws.f; uint32_t m[G::MASK_WORDS];
+#pragma unroll
+    for (int k = 0; k < G::MASK_WORDS; k++) m[k] = 0;
+    for (int a = lane; a < G::A; a += 32) pf[a] = 0.f;
+    __syncwarp();
+    for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; pf[a] = edges[h.edge_off + i].p; }
+    for (int i = 0; i < h.n_legal; i++) { int a = acts[h.edge_off + i]; m[a >> 5] |= 1u << (a & 31); }
+    __syncwarp();
+    root_noise<G>(d, g, pf, ws.d, m, lane);
+    float s = warp_sum_avx2order(pf, G::A, lane);
+    float inv = __fdiv_rn(1.0f, s);
+    for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; edges[h.edge_off + i].p = __fmul_rn(pf[a], inv); }
+    __syncwarp();
+}
+
+// First traversal of an (edge, universe): child state = make_move(parent board) + swap_players (MCTS.py:233-248),
+// then the reference's dict lookup (MCTS.py:125-126) as a hash-table probe. The board stays in shared memory, its
+// key in ws.key; returns (found node index, or -1) and the next player in ws.np. Kept out of line: once per simulation.
+template <class G>
+__device__ __noinline__ int materialise_child(const Dev<G>& d, int g, WarpSmem<G>& ws, int parent, int action, long long seed, int lane) {
+    int8_t* sb = ws.board;
+    warp_load_board<G>(sb, d.g_boards(g) + (size_t)parent * G::SP, lane);
+    int np = 0;
+    if (lane == 0) { np = G::make_move(sb, action, 0, seed, nullptr); ws.np = np; }   // seed != 0 in search: deterministic chance
+    __syncwarp();
+    np = ws.np;
+    if (np != 0) G::swap_players(sb, np, lane);
+    uint64_t klo, khi;
+    board_hash<G>(sb, lane, klo, khi);
+    if (lane == 0) { ws.key[0] = klo; ws.key[1] = khi; }
+    __syncwarp();
+    return ht_find(d.g_ht(g), d.ht_cap, d.g_nodes(g), klo, khi, lane);
+}
+
+// Root of this search (MCTS.py:125-126 for the top-level call): board from d.root, key in ws.key; returns its node or -1.
+template <class G>
+__device__ __noinline__ int locate_root(const Dev<G>& d, int g, WarpSmem<G>& ws, int lane) {
+    warp_load_board<G>(ws.board, d.root + (size_t)g * G::SP, lane);
+    uint64_t klo, khi;
+    board_hash<G>(ws.board, lane, klo, khi);
+    if (lane == 0) { ws.key[0] = klo; ws.key[1] = khi; }
+    __syncwarp();
+    const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_nodes(g), klo, khi, lane);
+    if (idx >= 0 && lane == 0) d.root_node[g] = idx + 1;
+    return idx;
+}
+
+// The state in ws.board has never been seen (MCTS.py:130-154): terminal test, else legal mask + hand-over to the net.
+template <class G>
+__device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, uint32_t link_slot, int lane) {
+    const int8_t* sb = ws.board;
+    float es[G::NP];
+    int kind;
+    if (G::ended(sb, es)) {
+        kind = LEAF_NEW_TERMINAL;
+        if (lane == 0) for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p];
+    } else {
+        kind = LEAF_EXPAND;
+        uint32_t m[G::MASK_WORDS];
+        G::valid_mask(sb, 0, lane, m);
+        if (lane < G::MASK_WORDS) d.leaf_mask[(size_t)g * G::MASK_WORDS + lane] = m[lane];
+        warp_store_board<G>(d.nn_in + (size_t)g * G::SP, sb, lane);
+        if (lane == 0) { int pos = atomicAdd(d.nn_count, 1); d.nn_list[pos] = g; }
+    }
+    if (lane == 0) { d.leaf_key[2 * (size_t)g] = ws.key[0]; d.leaf_key[2 * (size_t)g + 1] = ws.key[1]; d.leaf_round[g] = G::round(sb); d.leaf_link[g] = link_slot; }
+    return kind;
+}
 
 // ============================================================ select ==================================
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_select(Dev<G> d, int step) {
+__global__ void __launch_bounds__(SEL_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
     __shared__ WarpSmem<G> sm[SEL_WARPS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
     if (g >= d.n_games) return;
     if (step >= d.n_sims[g]) { if (lane == 0) d.leaf_kind[g] = LEAF_NONE; return; }
-    int8_t* sb = sm[w].board;
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(d.root + (size_t)g * G::SP);
-        if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = src[lane];
-        __syncwarp();
-    }
     const bool full = d.full ? d.full[g] != 0 : true;
     const bool forced_root = full && d.forced_playouts;
     const bool noise_now = step == 0 && full && d.dirichlet_noise;
-    const long long seed = d.universes > 0 ? kMagicSeeds[step % d.universes] : -1;
-    NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
-    const uint64_t* ht = d.g_ht(g);
+    const int uni = d.universes > 0 ? step % d.universes : 0;
+    const NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); uint32_t* child = d.g_child(g);
     PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
     int depth = 0, kind = LEAF_NONE, sum_legal = 0;
-    for (;;) {
-        uint64_t klo, khi;
-        board_hash<G>(sb, lane, klo, khi);
-        int idx = ht_find(ht, d.ht_cap, nodes, klo, khi, lane);
-        if (idx < 0) {                                           // state never seen: MCTS.py:130-154
-            float es[G::NP];
-            bool over = G::ended(sb, es);
-            if (over) {
-                kind = LEAF_NEW_TERMINAL;
-                if (lane == 0) for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p];
-            } else {
-                kind = LEAF_EXPAND;
-                uint32_t m[G::MASK_WORDS];
-                G::valid_mask(sb, 0, lane, m);
-                if (lane < G::MASK_WORDS) d.leaf_mask[(size_t)g * G::MASK_WORDS + lane] = m[lane];
-                if (lane < G::SP / 16) reinterpret_cast<uint4*>(d.nn_in + (size_t)g * G::SP)[lane] = reinterpret_cast<const uint4*>(sb)[lane];
-                if (lane == 0) { int pos = atomicAdd(d.nn_count, 1); d.nn_list[pos] = g; }
-            }
-            if (lane == 0) { d.leaf_key[2 * (size_t)g] = klo; d.leaf_key[2 * (size_t)g + 1] = khi; d.leaf_round[g] = G::round(sb); }
-            break;
-        }
+    uint32_t link_slot = 0;                                      // child-link slot (+1) a new leaf hangs on; 0 = it is the root
+    bool at_new = false;                                         // ws.board holds a state that is not in the tree yet
+    int idx = d.root_node[g] - 1;
+    if (idx < 0) { idx = locate_root<G>(d, g, sm[w], lane); at_new = idx < 0; }
+    while (!at_new) {
         const NodeHdr h = nodes[idx];
         if (h.kind == NODE_TERMINAL) {                           // MCTS.py:136-138
             kind = LEAF_OLD_TERMINAL;
             if (lane == 0) { const float* es = reinterpret_cast<const float*>(edges + h.edge_off); for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p]; }
             break;
         }
-        if (depth == 0 && noise_now) {                           // re-noise an already expanded root, MCTS.py:156-160
-            float* pf = sm[w].f; uint32_t m[G::MASK_WORDS];
-#pragma unroll
-            for (int k = 0; k < G::MASK_WORDS; k++) m[k] = 0;
-            for (int a = lane; a < G::A; a += 32) pf[a] = 0.f;
-            __syncwarp();
-            for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; pf[a] = edges[h.edge_off + i].p; }
-            for (int i = 0; i < h.n_legal; i++) { int a = acts[h.edge_off + i]; m[a >> 5] |= 1u << (a & 31); }
-            __syncwarp();
-            root_noise<G>(d, g, pf, sm[w].d, m, lane);
-            float s = warp_sum_avx2order(pf, G::A, lane);
-            float inv = __fdiv_rn(1.0f, s);
-            for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; edges[h.edge_off + i].p = __fmul_rn(pf[a], inv); }
-            __syncwarp();
-        }
-        const int e = puct_select(edges + h.edge_off, h.n_legal, h.ns, h.qs, d.cpuct, d.fpu, depth == 0 && forced_root, step, lane);
-        const int a = acts[h.edge_off + e];
+        if (depth == 0 && noise_now) renoise_root<G>(d, g, h.edge_off, (int)h.n_legal, edges, d.g_acts(g), sm[w], lane);
+        uint32_t link;
+        const int e = puct_select(edges + h.edge_off, child + (size_t)h.edge_off * d.U, d.U, uni, h.n_legal, h.ns, h.qs, d.cpuct, d.fpu,
+                                  depth == 0 && forced_root, step, lane, link);
         sum_legal += h.n_legal;
-        int np = 0;
-        if (lane == 0) {
-            np = G::make_move(sb, a, 0, seed, nullptr);          // seed != 0 in search: deterministic chance
-            path[depth].node = (uint32_t)idx; path[depth].edge_np = (h.edge_off + (uint32_t)e) | ((uint32_t)np << 24);
+        const uint32_t eidx = h.edge_off + (uint32_t)e;
+        if (link != 0) {                                         // resolved before: pure pointer walk
+            if (lane == 0) { path[depth].node = (uint32_t)idx; path[depth].edge_np = eidx | ((link >> 28) << 24); }
+            idx = (int)(link & LINK_IDX) - 1;
+            if (++depth >= G::MAX_DEPTH) break;
+            continue;
         }
-        __syncwarp();
-        np = __shfl_sync(FULL, np, 0);
-        if (np != 0) G::swap_players(sb, np, lane);
+        const long long seed = d.universes > 0 ? kMagicSeeds[uni] : -1;
+        const int found = materialise_child<G>(d, g, sm[w], idx, d.g_acts(g)[eidx], seed, lane);
+        const uint32_t np = (uint32_t)sm[w].np;
+        if (lane == 0) { path[depth].node = (uint32_t)idx; path[depth].edge_np = eidx | (np << 24); }
         depth++;
-        if (depth >= G::MAX_DEPTH) break;
+        const size_t slot = (size_t)eidx * d.U + uni;
+        if (found >= 0) {                                        // transposition, or the same child under another universe
+            if (lane == 0) child[slot] = (uint32_t)(found + 1) | (np << 28);
+            idx = found;
+            if (depth >= G::MAX_DEPTH) break;
+            continue;
+        }
+        link_slot = (uint32_t)slot + 1u; at_new = true;
     }
+    if (at_new) kind = new_leaf<G>(d, g, sm[w], link_slot, lane);
     if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; }
 }
 
 // ============================================================ expand + backup =========================
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(Dev<G> d, int step) {
+__global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant__ Dev<G> d, int step) {
     __shared__ WarpSmem<G> sm[SEL_WARPS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;    // leaf list consumed by the net; reset for the next step
@@ -341,8 +417,18 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(Dev<G> d, int step) {
                 }
                 before += __popc(m[k]);
             }
+            uint32_t* child = d.g_child(g);
+            for (int k = lane; k < L * d.U; k += 32) child[(size_t)eo * d.U + k] = 0;                          // links unresolved
+            {                                                        // board slot of the node (source of its children's states)
+                const uint4* src = reinterpret_cast<const uint4*>(d.nn_in + (size_t)g * G::SP);
+                uint4* dst = reinterpret_cast<uint4*>(d.g_boards(g) + (size_t)ni * G::SP);
+                for (int i = lane; i < G::SP / 16; i += 32) dst[i] = src[i];
+            }
             const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
+            const uint32_t ls = d.leaf_link[g];
             if (lane == 0) {
+                if (ls) child[ls - 1] = (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28);
+                else d.root_node[g] = ni + 1;
                 NodeHdr h; h.klo = klo; h.khi = khi; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
                 h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_EXPANDED;
                 nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + L;
@@ -359,7 +445,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(Dev<G> d, int step) {
             if (ni >= d.node_cap || eo + 1 > d.edge_cap) { if (lane == 0) st[ST_OVERFLOW]++; }
             else {
                 const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
+                const uint32_t ls = d.leaf_link[g];
                 if (lane == 0) {
+                    if (ls) d.g_child(g)[ls - 1] = (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28);
+                    else d.root_node[g] = ni + 1;
                     float* es = reinterpret_cast<float*>(edges + eo);
                     for (int p = 0; p < 4; p++) es[p] = p < NP ? v[p] : 0.f;
                     NodeHdr h; h.klo = klo; h.khi = khi; h.ns = 0; h.qs = 0.f; h.edge_off = (uint32_t)eo; h.n_legal = 0;
@@ -447,10 +536,18 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_finish(Dev<G> d, int n, int*
 }
 
 // ============================================================ tree GC ==================================
-// Drops every node that can no longer be reached: its round is <= the new root's round and it is not the
-// root itself (the round counter is part of the key and grows with every move). This is the reference's
-// cleaning (MCTS.py:86-91, nodes with round < r-5) made exact; both are semantic no-ops. Runs only when
-// the arena could not hold another `need_nodes` / `need_edges`. Compacts nodes+edges in place, rebuilds ht.
+// Runs only when the arena could not hold another `need_nodes` / `need_edges`. Two tiers:
+//   tier 1 (exact): drop every node whose round is <= the new root's round and that is not the root itself (the
+//          round counter is part of the key and grows with every move, so such a node can never be looked up
+//          again). This is the reference's cleaning (MCTS.py:86-91, nodes with round < r-5) made tight; both are
+//          semantic no-ops.
+//   tier 2 (memory pressure only, counted in ST_GC_SWEEP): if tier 1 would not free enough, keep only what is
+//          reachable from the new root through resolved child links (breadth-first mark). The reference has
+//          unbounded memory and would keep the sub-trees of the moves that were not played; a later transposition
+//          into one of them finds fresh statistics here instead of the old ones. Parity tests size the arena so
+//          that tier 2 never runs.
+// Compacts nodes + boards + edges + actions + child links in place (ascending, destination <= source), rewrites
+// the links through an old->new index map and rebuilds the hash table.
 template <class G>
 __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes, int need_edges, int force) {
     __shared__ WarpSmem<G> sm[SEL_WARPS];
@@ -459,17 +556,52 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
     const int nn = d.n_nodes[g], ne = d.n_edges[g];
     if (!force && nn + need_nodes <= d.node_cap && ne + need_edges <= d.edge_cap) return;
     int8_t* sb = sm[w].board;
-    if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(d.root + (size_t)g * G::SP)[lane];
-    __syncwarp();
+    warp_load_board<G>(sb, d.root + (size_t)g * G::SP, lane);
     uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
-    const int r = G::round(sb);
+    const int r = G::round(sb), U = d.U;
     NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g); uint64_t* ht = d.g_ht(g);
+    uint32_t* child = d.g_child(g); int8_t* boards = d.g_boards(g); int* remap = d.remap + (size_t)g * d.node_cap;
+    // ---- would tier 1 free enough?
+    int kn1 = 0, ke1 = 0;
+    for (int i = lane; i < nn; i += 32) {
+        const NodeHdr h = nodes[i];
+        if ((int)h.round > r || (h.klo == klo && h.khi == khi)) { kn1++; ke1 += h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal; }
+    }
+    kn1 = warp_sum_i32(kn1); ke1 = warp_sum_i32(ke1);
+    const bool sweep = force != 1 && (force == 2 || kn1 + need_nodes > d.node_cap || ke1 + need_edges > d.edge_cap);
+    if (sweep) {                                                 // ---- tier 2: mark what the new root reaches
+        int* q = d.gcq + (size_t)g * d.node_cap;
+        for (int i = lane; i < nn; i += 32) remap[i] = 0;
+        const int root = ht_find(ht, d.ht_cap, nodes, klo, khi, lane);
+        __syncwarp();
+        int head = 0, tail = 0;
+        if (root >= 0) { if (lane == 0) { remap[root] = -1; q[0] = root; } tail = 1; }
+        __syncwarp();
+        while (head < tail) {
+            const int cnt = min(32, tail - head);
+            int off = 0, len = 0;
+            if (lane < cnt) { const NodeHdr h = nodes[q[head + lane]]; off = (int)h.edge_off; len = h.kind == NODE_TERMINAL ? 0 : (int)h.n_legal; }
+            for (int j = 0; j < cnt; j++) {
+                const int oj = __shfl_sync(FULL, off, j), lj = __shfl_sync(FULL, len, j) * U;
+                for (int k = 0; k < lj; k += 32) {
+                    int ci = -1;
+                    if (k + lane < lj) { const uint32_t c = child[(size_t)oj * U + k + lane]; if (c) ci = (int)(c & LINK_IDX) - 1; }
+                    const bool won = ci >= 0 && atomicCAS(&remap[ci], 0, -1) == 0;
+                    const unsigned wm = __ballot_sync(FULL, won);
+                    if (won) q[tail + __popc(wm & ((1u << lane) - 1u))] = ci;
+                    tail += __popc(wm);
+                }
+            }
+            head += cnt;
+            __syncwarp();
+        }
+    }
     int wn = 0, we = 0;                                          // write cursors
     for (int base = 0; base < nn; base += 32) {
         const int i = base + lane;
         NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.klo = h.khi = 0; h.ns = 0; h.qs = 0;
         bool keep = false;
-        if (i < nn) { h = nodes[i]; keep = (int)h.round > r || (h.klo == klo && h.khi == khi); }
+        if (i < nn) { h = nodes[i]; keep = sweep ? remap[i] == -1 : ((int)h.round > r || (h.klo == klo && h.khi == khi)); }
         const int len = keep ? (h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal) : 0;
         const unsigned km = __ballot_sync(FULL, keep);
         int pre = len;                                           // inclusive prefix sum of edge counts
@@ -478,12 +610,26 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
         const int new_off = we + pre - len, old_off = (int)h.edge_off;
         const int new_idx = wn + __popc(km & ((1u << lane) - 1u));
         __syncwarp();
+        if (i < nn) remap[i] = keep ? new_idx + 1 : 0;
         if (keep) { h.edge_off = (uint32_t)new_off; nodes[new_idx] = h; }
-        // move the edge blocks of this chunk, node by node in ascending order (dest <= src)
+        // move board, edge, action and link blocks of this chunk, node by node in ascending order (dest <= src)
         for (unsigned mm = km; mm; mm &= mm - 1) {
             const int l = __ffs(mm) - 1;
             const int so = __shfl_sync(FULL, old_off, l), dn = __shfl_sync(FULL, new_off, l), ln = __shfl_sync(FULL, len, l);
-            if (so != dn)
+            const int si = base + l, di = __shfl_sync(FULL, new_idx, l);
+            if (si != di) {
+                uint4 t = make_uint4(0, 0, 0, 0);
+                const uint4* src = reinterpret_cast<const uint4*>(boards + (size_t)si * G::SP);
+                uint4* dst = reinterpret_cast<uint4*>(boards + (size_t)di * G::SP);
+                for (int k = 0; k < G::SP / 16; k += 32) {
+                    const bool in = k + lane < G::SP / 16;
+                    if (in) t = src[k + lane];
+                    __syncwarp();
+                    if (in) dst[k + lane] = t;
+                    __syncwarp();
+                }
+            }
+            if (so != dn) {
                 for (int k = 0; k < ln; k += 32) {
                     Edge tmp; typename G::act_t ta = 0; const bool in = k + lane < ln;
                     if (in) { tmp = edges[so + k + lane]; ta = acts[so + k + lane]; }
@@ -491,10 +637,23 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
                     if (in) { edges[dn + k + lane] = tmp; acts[dn + k + lane] = ta; }
                     __syncwarp();
                 }
+                for (int k = 0; k < ln * U; k += 32) {
+                    uint32_t c = 0; const bool in = k + lane < ln * U;
+                    if (in) c = child[(size_t)so * U + k + lane];
+                    __syncwarp();
+                    if (in) child[(size_t)dn * U + k + lane] = c;
+                    __syncwarp();
+                }
+            }
         }
         wn += __popc(km); we += __shfl_sync(FULL, pre, 31);
     }
-    __syncwarp();
+    __threadfence_block(); __syncwarp();
+    // links: old node index -> new node index (children of kept nodes are kept: their round is larger still)
+    for (size_t k = lane; k < (size_t)we * U; k += 32) {
+        const uint32_t c = child[k];
+        if (c) { const int m = remap[(int)(c & LINK_IDX) - 1]; child[k] = m ? ((uint32_t)m | (c & ~LINK_IDX)) : 0u; }
+    }
     for (int s = lane; s < d.ht_cap; s += 32) ht[s] = 0;
     __threadfence_block(); __syncwarp();
     for (int i = lane; i < wn; i += 32) {                         // lane-parallel re-insert
@@ -504,7 +663,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
         while (atomicCAS(reinterpret_cast<unsigned long long*>(ht + slot), 0ULL, (unsigned long long)ent) != 0ULL)
             slot = (slot + 1) & (uint32_t)(d.ht_cap - 1);
     }
-    if (lane == 0) { d.n_nodes[g] = wn; d.n_edges[g] = we; d.stats[(size_t)g * ST_N + ST_GC]++; }
+    if (lane == 0) { d.n_nodes[g] = wn; d.n_edges[g] = we; d.root_node[g] = 0; d.stats[(size_t)g * ST_N + ST_GC]++; if (sweep) d.stats[(size_t)g * ST_N + ST_GC_SWEEP]++; }
 }
 
 // Reset trees (MCTS.reset_all_search_trees, MCTS.py:199-203): one slot (game >= 0) or all.
@@ -514,7 +673,7 @@ __global__ void k_reset(Dev<G> d, int game) {
     const size_t per = (size_t)d.ht_cap, total = (size_t)(g1 - g0) * per;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
         d.ht[(size_t)g0 * per + i] = 0;
-    for (int g = g0 + blockIdx.x * blockDim.x + threadIdx.x; g < g1; g += gridDim.x * blockDim.x) { d.n_nodes[g] = 0; d.n_edges[g] = 0; }
+    for (int g = g0 + blockIdx.x * blockDim.x + threadIdx.x; g < g1; g += gridDim.x * blockDim.x) { d.n_nodes[g] = 0; d.n_edges[g] = 0; d.root_node[g] = 0; }
 }
 
 }  // namespace azg

@@ -49,7 +49,7 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--games', type=int, default=16384, help='concurrent games per GPU')
     ap.add_argument('--sims', type=int, default=800)
-    ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 5 x sims + 96)')
+    ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 6 x sims + 320)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-plies', type=int, default=12, help='plies per thread of the cpu_baseline sample')
@@ -240,7 +240,7 @@ def main():
     game = azg_b200.SplendorGame()
     net = azg_b200.NNetWrapper(game, {'nn_version': 80}, seed=0)             # identical weights on every rank
     a = mcts_args(args.sims)
-    node_cap = args.node_cap or (5 * args.sims + 96)
+    node_cap = args.node_cap or (6 * args.sims + 320)
     eng = Engine(game, net, a, n_games=args.games, dirichlet_noise=True, seed=1000 + rank, node_cap=node_cap)
     K, W = args.steps, args.warmup
     stream = torch.cuda.current_stream()

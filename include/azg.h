@@ -131,7 +131,7 @@ int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float
 /* Counters since creation: [0] sims [1] node_visits (select steps) [2] expansions (nodes with priors)
  * [3] nn_evals [4] terminal_hits [5] arena_overflows [6] gc_runs [7] max_nodes_in_a_tree
  * [8] sum_legal (over expansions) [9] moves_played [10] episodes_finished [11] examples_recorded
- * [12] kernels_launched [13] node_cap [14] edge_cap [15] sum_legal_visited (sum of n_legal over select steps) */
+ * [12] kernels_launched [13] gc_sweeps (tier-2 reachability GCs, see tree.cuh) [14] node_cap [15] sum_legal_visited (sum of n_legal over select steps) */
 int azg_engine_stats(azg_engine* e, int64_t* out16);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch of the search loop).

@@ -616,7 +616,7 @@ static int pick_highest_ucb(const node_t* nd, double cpuct, int forced, int64_t 
 /* MCTS.py:105-184 (search), unrolled from recursion into select / leaf / backup. */
 static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const double* noise) {
     int n = m->cfg.num_players, S = m->S, depth = 0;
-    static __thread node_t* path_node[256]; static __thread int path_a[256], path_np[256];
+    static __thread int path_node[256], path_a[256], path_np[256];   /* node INDICES: insert() may realloc m->nodes */
     i8 cur[MAXS]; memcpy(cur, root, (size_t)S);
     float v[MAXP];
     azo_rng dummy; rng_seed(&dummy, 1);
@@ -648,12 +648,12 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
         m->n_node_visits++;
         int np_ = azo_make_move(cur, n, a, 0, m->random_seed, &dummy);     /* MCTS.py:233-248 */
         if (np_ != 0) azo_swap_players(cur, n, np_);
-        path_node[depth] = nd; path_a[depth] = a; path_np[depth] = np_; depth++;
+        path_node[depth] = (int)(nd - m->nodes); path_a[depth] = a; path_np[depth] = np_; depth++;
     }
     for (int d = depth - 1; d >= 0; d--) {
         float t[MAXP]; for (int p = 0; p < n; p++) t[(p + path_np[d]) % n] = v[p];       /* np.roll(v, next_player) */
         memcpy(v, t, sizeof(float) * (size_t)n);
-        node_t* nd = path_node[d]; int a = path_a[d];
+        node_t* nd = &m->nodes[path_node[d]]; int a = path_a[d];
         nd->Qsa[a] = ((double)nd->Nsa[a] * nd->Qsa[a] + (double)v[0]) / (double)(nd->Nsa[a] + 1);
         nd->Qs = ((float)(nd->Ns + 1) * nd->Qs + v[0]) / (float)(nd->Ns + 2);
         nd->Nsa[a] += 1; nd->Ns += 1;

@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --games 2048 --sims 200 --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err; echo "rc=$?" >> gpurun_out/bench_small.err
+timeout 1500 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "rc=$?" >> gpurun_out/bench_full.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_select -s 1200 -c 2 -o gpurun_out/prof_select2 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_select.log 2>&1
+ls -la gpurun_out
