@@ -271,10 +271,9 @@ extern "C" int azg_game_symmetries(int game_id, int np, int n, const int8_t* boa
 }
 
 // ------------------------------------------------------------------ net handle --------------------------
-constexpr int V80_TB = 16;
 struct azg_net {
     int kind, game_id, np;
-    V80Layout L; float* blob = nullptr;
+    V80Layout L; V80Chunks CK; V80DW DW; float* blob = nullptr;
     Scratch masks;                        // packed masks for the standalone forward
     unsigned long long launches = 0;
 };
@@ -300,7 +299,7 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
         constexpr size_t smem = v80_smem_bytes<SP2::ROWS, V80_TB>();
         if (!attr_set) { CK(cudaFuncSetAttribute(k_v80_forward<SP2::ROWS, SP2::NP, V80_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
         k_v80_forward<SP2::ROWS, SP2::NP, V80_TB><<<(n_max + V80_TB - 1) / V80_TB, V80_THREADS, smem, st>>>(
-            net->blob, net->L, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+            net->blob, net->L, net->CK, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max);
     }
     net->launches++;
     CKL();
@@ -314,6 +313,7 @@ extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights
     std::vector<float> src(n_weights), dst((size_t)net->L.total);
     CK(cudaMemcpy(src.data(), weights, n_weights * sizeof(float), cudaMemcpyDefault));
     v80_prepare(src.data(), SP2::ROWS, net->np, net->L, dst.data());
+    for (int k = 0; k < 3; k++) for (int i = 0; i < 49; i++) net->DW.w[k][i] = dst[(size_t)net->L.blk[k].wd + i];
     CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -323,7 +323,7 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     if (net_kind != AZG_NET_HASH && net_kind != AZG_NET_SPLENDOR_V80) return fail("unknown net kind (built: 0=hash test net, 80=Splendor V80)");
     azg_net* net = new azg_net(); net->kind = net_kind; net->game_id = game_id; net->np = np;
     if (net_kind == AZG_NET_SPLENDOR_V80) {
-        net->L = v80_layout(SP2::ROWS, np);
+        net->L = v80_layout(SP2::ROWS, np); net->CK = v80_chunks(net->L); memset(&net->DW, 0, sizeof(net->DW));
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
         if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
     }
@@ -383,7 +383,7 @@ extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_en
         // bounded by 60 % of free HBM
         size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
         const int U0 = std::max(cfg->universes, 1);
-        const double per_node = 32.0 + SP2::SP + 4.0 + 44.0 * (17.0 + 4.0 * U0) + 2 * 8.0;
+        const double per_node = 48.0 + SP2::SP + 8.0 + 44.0 * (17.0 + 4.0 * U0) + 2 * 8.0;
         double fit = 0.6 * (double)free_b / (double)G / per_node;
         node_cap = (int)std::min<double>(fit, 16.0 * cfg->numMCTSSims + 1024);
         node_cap = std::max(node_cap, cfg->numMCTSSims + 64);
@@ -399,7 +399,7 @@ extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_en
     d.noise = nullptr;
     e->sims_full = cfg->numMCTSSims; e->sims_fast = cfg->ratio_fullMCTS > 0 ? cfg->numMCTSSims / cfg->ratio_fullMCTS : cfg->numMCTSSims;
     int bad = 0;
-    bad |= e->alloc(&d.nodes, (size_t)G * node_cap, false); bad |= e->alloc(&d.edges, (size_t)G * edge_cap, false);
+    bad |= e->alloc(&d.nodes, (size_t)G * node_cap, false); bad |= e->alloc(&d.keys, (size_t)G * node_cap, false); bad |= e->alloc(&d.edges, (size_t)G * edge_cap, false);
     bad |= e->alloc(&d.acts, (size_t)G * edge_cap, false); bad |= e->alloc(&d.ht, (size_t)G * d.ht_cap);
     bad |= e->alloc(&d.n_nodes, G); bad |= e->alloc(&d.n_edges, G);
     bad |= e->alloc(&d.child, (size_t)G * edge_cap * d.U, false); bad |= e->alloc(&d.boards, (size_t)G * node_cap * SP2::SP, false);
@@ -451,7 +451,7 @@ static int prof_drain(azg_engine* e) {
 static int engine_step(azg_engine* e, int step, cudaStream_t st) {
     const int G = e->d.n_games; const dim3 grid((unsigned)((G + SEL_WARPS - 1) / SEL_WARPS));
     prof_mark(e, PK_SELECT, st);
-    k_select<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, step);
+    k_select<SP2><<<(unsigned)((G + SELK_WARPS - 1) / SELK_WARPS), SELK_WARPS * 32, 0, st>>>(e->d, step);
     prof_mark(e, PK_NET, st);
     if (net_forward_dev(e->net, e->d.nn_count, e->d.nn_list, e->d.nn_in, SP2::SP, e->d.leaf_mask, e->d.nn_pi, e->d.nn_v, G, st)) return 1;
     prof_mark(e, PK_BACKUP, st);

@@ -39,7 +39,7 @@ __device__ bool root_policy(const Dev<G>& d, int g, const int8_t* sb, int lane, 
     constexpr int A = G::A;
     uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
     const NodeHdr* nodes = d.g_nodes(g); const Edge* edges = d.g_edges(g); const typename G::act_t* acts = d.g_acts(g);
-    const int idx = ht_find(d.g_ht(g), d.ht_cap, nodes, klo, khi, lane);
+    const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_keys(g), klo, khi, lane);
     for (int a = lane; a < A; a += 32) cnt[a] = 0;
 #pragma unroll
     for (int k = 0; k < G::MASK_WORDS; k++) mask[k] = 0;

@@ -18,7 +18,8 @@
 // PUCT with explicit round-to-nearest intrinsics so nvcc cannot contract or reassociate them.
 //
 // HBM layout per game g (arena sizes are engine parameters):
-//   nodes [node_cap] NodeHdr 32 B : 128-bit key, Ns, Qs, edge_off, n_legal, round, kind
+//   nodes [node_cap] NodeHdr 32 B : cpuct*sqrt(Ns), cpuct*sqrt(Ns+1e-8), Ns, Qs, edge_off, n_legal, round, kind
+//   keys  [node_cap] NodeKey 16 B : 128-bit board hash
 //   edges [edge_cap] Edge    16 B : {Q f64, P f32, N i32} for LEGAL actions only, ascending action index
 //   acts  [edge_cap] act_t        : action id of each edge
 //   child [edge_cap][U] u32       : (next_player << 28) | (child node index + 1), 0 = not resolved yet; U = universes
@@ -31,11 +32,12 @@ namespace azg {
 
 struct __align__(16) Edge { double q; float p; int n; };
 struct __align__(16) NodeHdr {
-    uint64_t klo, khi;
+    double c1, c0;                                             // cpuct*sqrt(Ns), cpuct*sqrt(Ns+1e-8): PUCT constants, refreshed by the backup
     int ns; float qs;
     uint32_t edge_off; uint16_t n_legal; uint8_t round; uint8_t kind;
 };
-static_assert(sizeof(Edge) == 16 && sizeof(NodeHdr) == 32, "layout");
+struct __align__(16) NodeKey { uint64_t lo, hi; };             // 128-bit board hash of the node (hash-table verification, GC)
+static_assert(sizeof(Edge) == 16 && sizeof(NodeHdr) == 32 && sizeof(NodeKey) == 16, "layout");
 struct PathEnt { uint32_t node; uint32_t edge_np; };          // edge index (24 bits) | next_player << 24
 
 enum { NODE_EXPANDED = 0, NODE_TERMINAL = 1 };
@@ -54,7 +56,7 @@ struct Dev {
     double cpuct, fpu, dir_alpha, temp2;
     uint64_t seed;
     // trees
-    NodeHdr* nodes; Edge* edges; typename G::act_t* acts; uint64_t* ht; int* n_nodes; int* n_edges;
+    NodeHdr* nodes; NodeKey* keys; Edge* edges; typename G::act_t* acts; uint64_t* ht; int* n_nodes; int* n_edges;
     uint32_t* child; int8_t* boards; int* remap; int* gcq;     // remap, gcq: [G][node_cap] scratch of the tree GC
     int* root_node;                                            // [G] root node index + 1 once known for this search, else 0
     uint32_t* leaf_link;                                       // [G] child-link slot (index into child, +1) the new leaf hangs on; 0 = root
@@ -70,6 +72,7 @@ struct Dev {
     unsigned long long* stats; // [G][ST_N]
 
     __device__ __forceinline__ NodeHdr* g_nodes(int g) const { return nodes + (size_t)g * node_cap; }
+    __device__ __forceinline__ NodeKey* g_keys(int g) const { return keys + (size_t)g * node_cap; }
     __device__ __forceinline__ Edge* g_edges(int g) const { return edges + (size_t)g * edge_cap; }
     __device__ __forceinline__ typename G::act_t* g_acts(int g) const { return acts + (size_t)g * edge_cap; }
     __device__ __forceinline__ uint64_t* g_ht(int g) const { return ht + (size_t)g * ht_cap; }
@@ -93,7 +96,7 @@ __device__ __forceinline__ void board_hash(const int8_t* b, int lane, uint64_t& 
 }
 
 // ---- hash table (WARP): 32 slots probed per round trip ---------------------------------------------------
-__device__ __forceinline__ int ht_find(const uint64_t* ht, int cap, const NodeHdr* nodes, uint64_t klo, uint64_t khi, int lane) {
+__device__ __forceinline__ int ht_find(const uint64_t* ht, int cap, const NodeKey* keys, uint64_t klo, uint64_t khi, int lane) {
     const uint32_t tag = (uint32_t)(khi >> 32);
     const uint32_t start = (uint32_t)klo & (uint32_t)(cap - 1);
     for (int probe = 0; probe < cap; probe += 32) {
@@ -104,8 +107,8 @@ __device__ __forceinline__ int ht_find(const uint64_t* ht, int cap, const NodeHd
         while (mm) {
             int l = __ffs(mm) - 1; mm &= mm - 1;
             int idx = (int)(uint32_t)__shfl_sync(FULL, e, l) - 1;
-            const NodeHdr* h = nodes + idx;
-            if (h->klo == klo && h->khi == khi) return idx;
+            const NodeKey k = keys[idx];
+            if (k.lo == klo && k.hi == khi) return idx;
         }
         if (em) return -1;
     }
@@ -194,11 +197,14 @@ __device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const
 
 // ---- PUCT (WARP): pick_highest_UCB, MCTS.py:210-230; returns the edge index and, in `link`, the child link
 // of that edge for universe `uni` (fetched together with the edges so that following it costs no extra round trip).
-__device__ __forceinline__ int puct_select(const Edge* e, const uint32_t* child, int U, int uni, int L, int ns, float qs,
-                                           double cpuct, double fpu, bool forced, int n_iter, int lane, uint32_t& link) {
+// c1 = cpuct*sqrt(Ns) and c0 = cpuct*sqrt(Ns+1e-8) come from the node header (the backup refreshes them).
+__device__ __forceinline__ uint64_t f64_order_key(double x) {   // unsigned order == double order (no NaNs here)
+    const long long b = __double_as_longlong(x);
+    return (uint64_t)b ^ ((uint64_t)(b >> 63) | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ int puct_select(const Edge* e, const uint32_t* child, int U, int uni, int L, double c1, double c0, float qs,
+                                           double fpu, bool forced, int n_iter, int lane, uint32_t& link) {
     const double fpu_init = fpu > 0 ? __dsub_rn((double)qs, fpu) : fpu;
-    const double c0 = __dmul_rn(cpuct, __dsqrt_rn(__dadd_rn((double)ns, 1e-8)));
-    const double c1 = __dmul_rn(cpuct, __dsqrt_rn((double)ns));
     const double kn = __dmul_rn((double)n_iter, 0.5);
     double best = -INFINITY; int best_i = 0x7FFFFFFF, forced_i = 0x7FFFFFFF; uint32_t best_c = 0;
     for (int i = lane; i < L; i += 32) {
@@ -214,23 +220,30 @@ __device__ __forceinline__ int puct_select(const Edge* e, const uint32_t* child,
         if (ucb > best) { best = ucb; best_i = i; best_c = c; }
     }
     if (forced) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) forced_i = min(forced_i, __shfl_xor_sync(FULL, forced_i, o));
+        forced_i = __reduce_min_sync(FULL, forced_i);
         if (forced_i != 0x7FFFFFFF) { link = child[(size_t)forced_i * U + uni]; return forced_i; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(FULL, best, o); int oi = __shfl_xor_sync(FULL, best_i, o);
-        if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
-    }
-    link = __shfl_sync(FULL, best_c, best_i & 31);               // the winner is the local best of lane (best_i % 32)
-    return best_i;
+    // warp argmax with first-index tie-break (MCTS.py:227-228): three REDUX steps on the order-preserving key
+    const uint64_t key = f64_order_key(best);
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mh = __reduce_max_sync(FULL, hi);
+    const bool ch = hi == mh && best_i != 0x7FFFFFFF;
+    const uint32_t ml = __reduce_max_sync(FULL, ch ? lo : 0u);
+    const int win = __reduce_min_sync(FULL, (ch && lo == ml) ? best_i : 0x7FFFFFFF);
+    link = __shfl_sync(FULL, best_c, win & 31);                  // the winner is the local best of lane (win % 32)
+    return win;
 }
 
 constexpr int SEL_WARPS = 4;
-#ifndef AZG_SEL_MIN_BLOCKS
-#define AZG_SEL_MIN_BLOCKS 8                                  // 64 registers/thread -> 32 resident warps (games) per SM
+// k_select runs ONE warp (= one game) per CTA so that an SM slot is recycled as soon as its game's walk ends
+// (walk lengths differ a lot between games); 64 registers/thread -> 32 resident CTAs = 32 games per SM.
+#ifndef AZG_SELK_WARPS
+#define AZG_SELK_WARPS 1
 #endif
+#ifndef AZG_SEL_MIN_BLOCKS
+#define AZG_SEL_MIN_BLOCKS (32 / AZG_SELK_WARPS)
+#endif
+constexpr int SELK_WARPS = AZG_SELK_WARPS;
 template <class G> struct WarpSmem {
     __align__(16) int8_t board[G::SP];
     __align__(16) float f[(G::A + 31) / 32 * 32];
@@ -283,7 +296,7 @@ __device__ __noinline__ int materialise_child(const Dev<G>& d, int g, WarpSmem<G
     board_hash<G>(sb, lane, klo, khi);
     if (lane == 0) { ws.key[0] = klo; ws.key[1] = khi; }
     __syncwarp();
-    return ht_find(d.g_ht(g), d.ht_cap, d.g_nodes(g), klo, khi, lane);
+    return ht_find(d.g_ht(g), d.ht_cap, d.g_keys(g), klo, khi, lane);
 }
 
 // Root of this search (MCTS.py:125-126 for the top-level call): board from d.root, key in ws.key; returns its node or -1.
@@ -294,7 +307,7 @@ __device__ __noinline__ int locate_root(const Dev<G>& d, int g, WarpSmem<G>& ws,
     board_hash<G>(ws.board, lane, klo, khi);
     if (lane == 0) { ws.key[0] = klo; ws.key[1] = khi; }
     __syncwarp();
-    const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_nodes(g), klo, khi, lane);
+    const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_keys(g), klo, khi, lane);
     if (idx >= 0 && lane == 0) d.root_node[g] = idx + 1;
     return idx;
 }
@@ -322,9 +335,9 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, ui
 
 // ============================================================ select ==================================
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
-    __shared__ WarpSmem<G> sm[SEL_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+__global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
+    __shared__ WarpSmem<G> sm[SELK_WARPS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SELK_WARPS + w;
     if (g >= d.n_games) return;
     if (step >= d.n_sims[g]) { if (lane == 0) d.leaf_kind[g] = LEAF_NONE; return; }
     const bool full = d.full ? d.full[g] != 0 : true;
@@ -347,7 +360,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(c
         }
         if (depth == 0 && noise_now) renoise_root<G>(d, g, h.edge_off, (int)h.n_legal, edges, d.g_acts(g), sm[w], lane);
         uint32_t link;
-        const int e = puct_select(edges + h.edge_off, child + (size_t)h.edge_off * d.U, d.U, uni, h.n_legal, h.ns, h.qs, d.cpuct, d.fpu,
+        const int e = puct_select(edges + h.edge_off, child + (size_t)h.edge_off * d.U, d.U, uni, h.n_legal, h.c1, h.c0, h.qs, d.fpu,
                                   depth == 0 && forced_root, step, lane, link);
         sum_legal += h.n_legal;
         const uint32_t eidx = h.edge_off + (uint32_t)e;
@@ -429,7 +442,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant
             if (lane == 0) {
                 if (ls) child[ls - 1] = (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28);
                 else d.root_node[g] = ni + 1;
-                NodeHdr h; h.klo = klo; h.khi = khi; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
+                NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
+                NodeHdr h; h.c1 = 0.0; h.c0 = __dmul_rn(d.cpuct, __dsqrt_rn(1e-8)); h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
                 h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_EXPANDED;
                 nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + L;
                 st[ST_EXPANSIONS]++; st[ST_NNEVALS]++; st[ST_SUMLEGAL] += (unsigned)L;
@@ -451,7 +465,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant
                     else d.root_node[g] = ni + 1;
                     float* es = reinterpret_cast<float*>(edges + eo);
                     for (int p = 0; p < 4; p++) es[p] = p < NP ? v[p] : 0.f;
-                    NodeHdr h; h.klo = klo; h.khi = khi; h.ns = 0; h.qs = 0.f; h.edge_off = (uint32_t)eo; h.n_legal = 0;
+                    NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
+                    NodeHdr h; h.c1 = 0.0; h.c0 = 0.0; h.ns = 0; h.qs = 0.f; h.edge_off = (uint32_t)eo; h.n_legal = 0;
                     h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_TERMINAL;
                     nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + 1;
                 }
@@ -482,6 +497,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant
             x.n += 1;
             qs = __fdiv_rn(__fadd_rn(__fmul_rn((float)(ns + 1), qs), v0), (float)(ns + 2));
             *ed = x; nh->ns = ns + 1; nh->qs = qs;
+            nh->c1 = __dmul_rn(d.cpuct, __dsqrt_rn((double)(ns + 1)));              // pick_highest_UCB's sqrt(Ns) terms, MCTS.py:224-226
+            nh->c0 = __dmul_rn(d.cpuct, __dsqrt_rn(__dadd_rn((double)(ns + 1), 1e-8)));
         }
         carry = (carry + __shfl_sync(FULL, suf, 0)) % NP;
     }
@@ -501,7 +518,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_finish(Dev<G> d, int n, int*
     __syncwarp();
     uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
     const NodeHdr* nodes = d.g_nodes(g); const Edge* edges = d.g_edges(g); const typename G::act_t* acts = d.g_acts(g);
-    const int idx = ht_find(d.g_ht(g), d.ht_cap, nodes, klo, khi, lane);
+    const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_keys(g), klo, khi, lane);
     int* cnt = reinterpret_cast<int*>(sm[w].f);
     for (int a = lane; a < A; a += 32) { cnt[a] = 0; if (out_raw) out_raw[(size_t)g * A + a] = 0; }
     __syncwarp();
@@ -563,16 +580,17 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
     uint32_t* child = d.g_child(g); int8_t* boards = d.g_boards(g); int* remap = d.remap + (size_t)g * d.node_cap;
     // ---- would tier 1 free enough?
     int kn1 = 0, ke1 = 0;
+    NodeKey* keys = d.g_keys(g);
     for (int i = lane; i < nn; i += 32) {
-        const NodeHdr h = nodes[i];
-        if ((int)h.round > r || (h.klo == klo && h.khi == khi)) { kn1++; ke1 += h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal; }
+        const NodeHdr h = nodes[i]; const NodeKey k = keys[i];
+        if ((int)h.round > r || (k.lo == klo && k.hi == khi)) { kn1++; ke1 += h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal; }
     }
     kn1 = warp_sum_i32(kn1); ke1 = warp_sum_i32(ke1);
     const bool sweep = force != 1 && (force == 2 || kn1 + need_nodes > d.node_cap || ke1 + need_edges > d.edge_cap);
     if (sweep) {                                                 // ---- tier 2: mark what the new root reaches
         int* q = d.gcq + (size_t)g * d.node_cap;
         for (int i = lane; i < nn; i += 32) remap[i] = 0;
-        const int root = ht_find(ht, d.ht_cap, nodes, klo, khi, lane);
+        const int root = ht_find(ht, d.ht_cap, keys, klo, khi, lane);
         __syncwarp();
         int head = 0, tail = 0;
         if (root >= 0) { if (lane == 0) { remap[root] = -1; q[0] = root; } tail = 1; }
@@ -599,9 +617,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
     int wn = 0, we = 0;                                          // write cursors
     for (int base = 0; base < nn; base += 32) {
         const int i = base + lane;
-        NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.klo = h.khi = 0; h.ns = 0; h.qs = 0;
+        NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.c0 = h.c1 = 0; h.ns = 0; h.qs = 0;
+        NodeKey nk; nk.lo = nk.hi = 0;
         bool keep = false;
-        if (i < nn) { h = nodes[i]; keep = sweep ? remap[i] == -1 : ((int)h.round > r || (h.klo == klo && h.khi == khi)); }
+        if (i < nn) { h = nodes[i]; nk = keys[i]; keep = sweep ? remap[i] == -1 : ((int)h.round > r || (nk.lo == klo && nk.hi == khi)); }
         const int len = keep ? (h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal) : 0;
         const unsigned km = __ballot_sync(FULL, keep);
         int pre = len;                                           // inclusive prefix sum of edge counts
@@ -611,7 +630,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
         const int new_idx = wn + __popc(km & ((1u << lane) - 1u));
         __syncwarp();
         if (i < nn) remap[i] = keep ? new_idx + 1 : 0;
-        if (keep) { h.edge_off = (uint32_t)new_off; nodes[new_idx] = h; }
+        if (keep) { h.edge_off = (uint32_t)new_off; nodes[new_idx] = h; keys[new_idx] = nk; }
         // move board, edge, action and link blocks of this chunk, node by node in ascending order (dest <= src)
         for (unsigned mm = km; mm; mm &= mm - 1) {
             const int l = __ffs(mm) - 1;
@@ -657,9 +676,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes,
     for (int s = lane; s < d.ht_cap; s += 32) ht[s] = 0;
     __threadfence_block(); __syncwarp();
     for (int i = lane; i < wn; i += 32) {                         // lane-parallel re-insert
-        const NodeHdr h = nodes[i];
-        const uint64_t ent = ((uint64_t)(uint32_t)(h.khi >> 32) << 32) | (uint32_t)(i + 1);
-        uint32_t slot = (uint32_t)h.klo & (uint32_t)(d.ht_cap - 1);
+        const NodeKey k = keys[i];
+        const uint64_t ent = ((uint64_t)(uint32_t)(k.hi >> 32) << 32) | (uint32_t)(i + 1);
+        uint32_t slot = (uint32_t)k.lo & (uint32_t)(d.ht_cap - 1);
         while (atomicCAS(reinterpret_cast<unsigned long long*>(ht + slot), 0ULL, (unsigned long long)ent) != 0ULL)
             slot = (slot + 1) & (uint32_t)(d.ht_cap - 1);
     }
