@@ -13,6 +13,7 @@
 #include "../../include/azg.h"
 #include "common.cuh"
 #include "net_v80.cuh"
+#include "santorini.cuh"
 #include "selfplay.cuh"
 #include "splendor.cuh"
 #include "tree.cuh"
@@ -85,18 +86,26 @@ struct Arg {
 static thread_local Arg tl_arg[12];
 static bool any_staged(int n) { for (int i = 0; i < n; i++) if (tl_arg[i].staged) return true; return false; }
 
-// ------------------------------------------------------------------ game info ---------------------------
+// ------------------------------------------------------------------ game registry ------------------------
+// GameSwitcher.py:3-35 of the reference maps a game name to its module; here a game id selects the template
+// instance. Every host entry point below is a template over the game type G and is reached through DISPATCH.
 typedef Splendor<2> SP2;
+#define DISPATCH(game_id, np, CALL)                                                                       \
+    do {                                                                                                  \
+        if ((game_id) == AZG_GAME_SPLENDOR && (np) == 2) { typedef Splendor<2> G; return CALL; }           \
+        if ((game_id) == AZG_GAME_SANTORINI && (np) == 2) { typedef Santorini G; return CALL; }            \
+        return fail("unknown game (built: 1 = splendor with 2 players, 2 = santorini without gods)");      \
+    } while (0)
 
-extern "C" int azg_game_info(int game_id, int num_players, azg_game_info_t* out) {
-    if (!out) return fail("out is NULL");
-    if (game_id != AZG_GAME_SPLENDOR) return fail("unknown game_id (built: 1=splendor)");
-    if (num_players != 2) return fail("splendor: only num_players=2 is built in this version");
-    out->game_id = game_id; out->num_players = 2; out->state_rows = SP2::ROWS; out->state_cols = SP2::COLS; out->state_bytes = SP2::S;
-    out->action_size = SP2::A; out->max_symmetries = SP2::MAX_SYM; out->max_game_len = SP2::MAX_MOVES;
+template <class G> static int game_info_t(azg_game_info_t* out) {
+    out->game_id = G::GAME_ID; out->num_players = G::NP; out->state_rows = G::D0; out->state_cols = G::D1; out->state_depth = G::D2;
+    out->state_bytes = G::S; out->action_size = G::A; out->max_symmetries = G::MAX_SYM; out->max_game_len = G::MAX_MOVES;
     return 0;
 }
-static int check_game(int game_id, int np) { azg_game_info_t t; return azg_game_info(game_id, np, &t); }
+extern "C" int azg_game_info(int game_id, int num_players, azg_game_info_t* out) {
+    if (!out) return fail("out is NULL");
+    DISPATCH(game_id, num_players, game_info_t<G>(out));
+}
 
 // ------------------------------------------------------------------ batched game-step kernels ----------
 // One warp per board; the board is staged in shared memory exactly as in the search kernels.
@@ -144,12 +153,12 @@ __global__ void k_game_next(int n, const int8_t* boards, const int* players, con
     store_board<G>(out + (size_t)i * G::S, sm[w], lane);
 }
 template <class G>
-__global__ void k_game_ended(int n, const int8_t* boards, float* out) {
+__global__ void k_game_ended(int n, const int8_t* boards, const int* next_players, float* out) {
     __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
     if (i >= n) return;
     load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
-    float es[G::NP]; G::ended(sm[w], es);
+    float es[G::NP]; G::ended(sm[w], next_players ? next_players[i] : 0, es, lane);
     if (lane == 0) for (int p = 0; p < G::NP; p++) out[(size_t)i * G::NP + p] = es[p];
 }
 template <class G>
@@ -204,70 +213,94 @@ static dim3 gk_grid(int n) { return dim3((unsigned)((n + GK_WARPS - 1) / GK_WARP
         return 0;                                                              \
     } while (0)
 
-extern "C" int azg_game_init(int game_id, int np, int n, const uint64_t* seeds, int8_t* boards, void* stream) {
-    if (require_device() || check_game(game_id, np)) return 1;
-    if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
-    if (a[0].in(seeds, sizeof(uint64_t) * n, st) || a[1].outbuf(boards, (size_t)n * SP2::S)) return 1;
-    k_game_init<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<uint64_t>(), a[1].as<int8_t>());
+template <class G> static int game_init_t(int n, const uint64_t* seeds, int8_t* boards, cudaStream_t st) {
+    Arg* a = tl_arg;
+    if (a[0].in(seeds, sizeof(uint64_t) * n, st) || a[1].outbuf(boards, (size_t)n * G::S)) return 1;
+    k_game_init<G><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<uint64_t>(), a[1].as<int8_t>());
     FINISH(2);
 }
-extern "C" int azg_game_valid(int game_id, int np, int n, const int8_t* boards, const int32_t* players, uint8_t* mask, void* stream) {
-    if (require_device() || check_game(game_id, np)) return 1;
-    if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
-    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].outbuf(mask, (size_t)n * SP2::A)) return 1;
-    k_game_valid<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<uint8_t>());
+template <class G> static int game_valid_t(int n, const int8_t* boards, const int32_t* players, uint8_t* mask, cudaStream_t st) {
+    Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].outbuf(mask, (size_t)n * G::A)) return 1;
+    k_game_valid<G><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<uint8_t>());
     FINISH(3);
+}
+template <class G> static int game_next_t(int n, const int8_t* boards, const int32_t* players, const int32_t* actions, const int64_t* seeds,
+                                          const uint64_t* rng_keys, int8_t* out_boards, int32_t* out_next_player, cudaStream_t st) {
+    Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].in(actions, sizeof(int) * n, st) ||
+        a[3].in(seeds, sizeof(int64_t) * n, st) || a[4].in(rng_keys, sizeof(uint64_t) * n, st) ||
+        a[5].outbuf(out_boards, (size_t)n * G::S) || a[6].outbuf(out_next_player, sizeof(int) * n)) return 1;
+    k_game_next<G><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int>(), a[3].as<long long>(),
+                                                    a[4].as<uint64_t>(), a[5].as<int8_t>(), a[6].as<int>());
+    FINISH(7);
+}
+template <class G> static int game_ended_t(int n, const int8_t* boards, const int32_t* next_players, float* out, cudaStream_t st) {
+    Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(next_players, sizeof(int) * n, st) || a[2].outbuf(out, sizeof(float) * n * G::NP)) return 1;
+    k_game_ended<G><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<float>());
+    FINISH(3);
+}
+template <class G> static int game_canonical_t(int n, const int8_t* boards, const int32_t* players, int8_t* out_boards, cudaStream_t st) {
+    Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].outbuf(out_boards, (size_t)n * G::S)) return 1;
+    k_game_canonical<G><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int8_t>());
+    FINISH(3);
+}
+template <class G> static int game_round_score_t(int n, const int8_t* boards, int32_t* rounds, int32_t* scores, cudaStream_t st) {
+    Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * G::S, st) || a[1].outbuf(rounds, sizeof(int) * n) || a[2].outbuf(scores, sizeof(int) * n * G::NP)) return 1;
+    k_game_round_score<G><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int>());
+    FINISH(3);
+}
+template <class G> static int game_symmetries_t(int n, const int8_t* boards, const float* pi, const uint8_t* mask, int8_t* out_boards,
+                                                float* out_pi, uint8_t* out_mask, int32_t* out_k, cudaStream_t st) {
+    Arg* a = tl_arg; const size_t K = G::MAX_SYM;
+    if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(pi, sizeof(float) * n * G::A, st) || a[2].in(mask, (size_t)n * G::A, st) ||
+        a[3].outbuf(out_boards, n * K * G::S) || a[4].outbuf(out_pi, sizeof(float) * n * K * G::A) ||
+        a[5].outbuf(out_mask, n * K * G::A) || a[6].outbuf(out_k, sizeof(int) * n)) return 1;
+    k_game_symmetries<G><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<float>(), a[2].as<uint8_t>(), a[3].as<int8_t>(),
+                                                          a[4].as<float>(), a[5].as<uint8_t>(), a[6].as<int>());
+    FINISH(7);
+}
+
+extern "C" int azg_game_init(int game_id, int np, int n, const uint64_t* seeds, int8_t* boards, void* stream) {
+    if (require_device()) return 1;
+    if (n <= 0) return 0;
+    DISPATCH(game_id, np, game_init_t<G>(n, seeds, boards, (cudaStream_t)stream));
+}
+extern "C" int azg_game_valid(int game_id, int np, int n, const int8_t* boards, const int32_t* players, uint8_t* mask, void* stream) {
+    if (require_device()) return 1;
+    if (n <= 0) return 0;
+    DISPATCH(game_id, np, game_valid_t<G>(n, boards, players, mask, (cudaStream_t)stream));
 }
 extern "C" int azg_game_next(int game_id, int np, int n, const int8_t* boards, const int32_t* players, const int32_t* actions,
                              const int64_t* seeds, const uint64_t* rng_keys, int8_t* out_boards, int32_t* out_next_player, void* stream) {
-    if (require_device() || check_game(game_id, np)) return 1;
+    if (require_device()) return 1;
     if (n <= 0) return 0;
     if (!actions) return fail("actions is NULL");
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
-    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].in(actions, sizeof(int) * n, st) ||
-        a[3].in(seeds, sizeof(int64_t) * n, st) || a[4].in(rng_keys, sizeof(uint64_t) * n, st) ||
-        a[5].outbuf(out_boards, (size_t)n * SP2::S) || a[6].outbuf(out_next_player, sizeof(int) * n)) return 1;
-    k_game_next<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int>(), a[3].as<long long>(),
-                                                      a[4].as<uint64_t>(), a[5].as<int8_t>(), a[6].as<int>());
-    FINISH(7);
+    DISPATCH(game_id, np, game_next_t<G>(n, boards, players, actions, seeds, rng_keys, out_boards, out_next_player, (cudaStream_t)stream));
 }
-extern "C" int azg_game_ended(int game_id, int np, int n, const int8_t* boards, float* out, void* stream) {
-    if (require_device() || check_game(game_id, np)) return 1;
+extern "C" int azg_game_ended(int game_id, int np, int n, const int8_t* boards, const int32_t* next_players, float* out, void* stream) {
+    if (require_device()) return 1;
     if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
-    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].outbuf(out, sizeof(float) * n * SP2::NP)) return 1;
-    k_game_ended<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<float>());
-    FINISH(2);
+    DISPATCH(game_id, np, game_ended_t<G>(n, boards, next_players, out, (cudaStream_t)stream));
 }
 extern "C" int azg_game_canonical(int game_id, int np, int n, const int8_t* boards, const int32_t* players, int8_t* out_boards, void* stream) {
-    if (require_device() || check_game(game_id, np)) return 1;
+    if (require_device()) return 1;
     if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
-    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(players, sizeof(int) * n, st) || a[2].outbuf(out_boards, (size_t)n * SP2::S)) return 1;
-    k_game_canonical<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int8_t>());
-    FINISH(3);
+    DISPATCH(game_id, np, game_canonical_t<G>(n, boards, players, out_boards, (cudaStream_t)stream));
 }
 extern "C" int azg_game_round_score(int game_id, int np, int n, const int8_t* boards, int32_t* rounds, int32_t* scores, void* stream) {
-    if (require_device() || check_game(game_id, np)) return 1;
+    if (require_device()) return 1;
     if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
-    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].outbuf(rounds, sizeof(int) * n) || a[2].outbuf(scores, sizeof(int) * n * SP2::NP)) return 1;
-    k_game_round_score<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<int>(), a[2].as<int>());
-    FINISH(3);
+    DISPATCH(game_id, np, game_round_score_t<G>(n, boards, rounds, scores, (cudaStream_t)stream));
 }
 extern "C" int azg_game_symmetries(int game_id, int np, int n, const int8_t* boards, const float* pi, const uint8_t* mask,
                                    int8_t* out_boards, float* out_pi, uint8_t* out_mask, int32_t* out_k, void* stream) {
-    if (require_device() || check_game(game_id, np)) return 1;
+    if (require_device()) return 1;
     if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg; const size_t K = SP2::MAX_SYM;
-    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(pi, sizeof(float) * n * SP2::A, st) || a[2].in(mask, (size_t)n * SP2::A, st) ||
-        a[3].outbuf(out_boards, n * K * SP2::S) || a[4].outbuf(out_pi, sizeof(float) * n * K * SP2::A) ||
-        a[5].outbuf(out_mask, n * K * SP2::A) || a[6].outbuf(out_k, sizeof(int) * n)) return 1;
-    k_game_symmetries<SP2><<<gk_grid(n), GK_BLOCK, 0, st>>>(n, a[0].as<int8_t>(), a[1].as<float>(), a[2].as<uint8_t>(), a[3].as<int8_t>(),
-                                                            a[4].as<float>(), a[5].as<uint8_t>(), a[6].as<int>());
-    FINISH(7);
+    DISPATCH(game_id, np, game_symmetries_t<G>(n, boards, pi, mask, out_boards, out_pi, out_mask, out_k, (cudaStream_t)stream));
 }
 
 // ------------------------------------------------------------------ net handle --------------------------
@@ -287,20 +320,24 @@ __global__ void k_pack_masks(int n, int A, int MW, const uint8_t* mask, uint32_t
     }
 }
 // Evaluate slots: list/count on device (engine) or identity (standalone). boards stride `bstride` bytes.
+template <class G>
 static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, const int8_t* boards, int bstride,
                            const uint32_t* masks, float* pi, float* v, int n_max, cudaStream_t st) {
     if (n_max <= 0) return 0;
+    if (net->game_id != G::GAME_ID || net->np != G::NP) return fail("net was created for another game");
     if (net->kind == AZG_NET_HASH) {
         const int warps_per_block = 4;
-        k_hashnet_forward<SP2::S, SP2::A, SP2::NP, SP2::MASK_WORDS><<<(n_max + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        k_hashnet_forward<G::S, G::A, G::NP, G::MASK_WORDS><<<(n_max + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
             count_ptr, list, boards, bstride, masks, pi, v, n_max);
-    } else {
-        static bool attr_set = false;
-        constexpr size_t smem = v80_smem_bytes<SP2::ROWS, V80_TB>();
-        if (!attr_set) { CK(cudaFuncSetAttribute(k_v80_forward<SP2::ROWS, SP2::NP, V80_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-        k_v80_forward<SP2::ROWS, SP2::NP, V80_TB><<<(n_max + V80_TB - 1) / V80_TB, V80_THREADS, smem, st>>>(
-            net->blob, net->L, net->CK, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max);
-    }
+    } else if (net->kind == AZG_NET_SPLENDOR_V80) {
+        if constexpr (G::GAME_ID == AZG_GAME_SPLENDOR) {
+            static bool attr_set = false;
+            constexpr size_t smem = v80_smem_bytes<G::ROWS, V80_TB>();
+            if (!attr_set) { CK(cudaFuncSetAttribute(k_v80_forward<G::ROWS, G::NP, V80_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            k_v80_forward<G::ROWS, G::NP, V80_TB><<<(n_max + V80_TB - 1) / V80_TB, V80_THREADS, smem, st>>>(
+                net->blob, net->L, net->CK, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+        } else return fail("SplendorNNet V80 only evaluates Splendor boards");
+    } else return fail("net kind not built");
     net->launches++;
     CKL();
     return 0;
@@ -319,8 +356,10 @@ extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights
 }
 extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* weights, size_t n_weights, azg_net** out) {
     if (!out) return fail("out is NULL");
-    if (require_device() || check_game(game_id, np)) return 1;
+    azg_game_info_t gi;
+    if (require_device() || azg_game_info(game_id, np, &gi)) return 1;
     if (net_kind != AZG_NET_HASH && net_kind != AZG_NET_SPLENDOR_V80) return fail("unknown net kind (built: 0=hash test net, 80=Splendor V80)");
+    if (net_kind == AZG_NET_SPLENDOR_V80 && game_id != AZG_GAME_SPLENDOR) return fail("SplendorNNet V80 only evaluates Splendor boards");
     azg_net* net = new azg_net(); net->kind = net_kind; net->game_id = game_id; net->np = np;
     if (net_kind == AZG_NET_SPLENDOR_V80) {
         net->L = v80_layout(SP2::ROWS, np); net->CK = v80_chunks(net->L); memset(&net->DW, 0, sizeof(net->DW));
@@ -330,198 +369,306 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     *out = net; return 0;
 }
 extern "C" int azg_net_destroy(azg_net* net) { if (net) { if (net->blob) cudaFree(net->blob); delete net; } return 0; }
+template <class G> static int net_forward_t(azg_net* net, int n, const int8_t* boards, const uint8_t* mask, float* pi, float* v, cudaStream_t st) {
+    Arg* a = tl_arg;
+    if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(mask, (size_t)n * G::A, st) || a[2].outbuf(pi, sizeof(float) * n * G::A) ||
+        a[3].outbuf(v, sizeof(float) * n * G::NP)) return 1;
+    if (net->masks.ensure(sizeof(uint32_t) * (size_t)n * G::MASK_WORDS)) return 1;
+    k_pack_masks<<<(n + 3) / 4, 128, 0, st>>>(n, G::A, G::MASK_WORDS, a[1].as<uint8_t>(), (uint32_t*)net->masks.p);
+    if (net_forward_dev<G>(net, nullptr, nullptr, a[0].as<int8_t>(), G::S, (const uint32_t*)net->masks.p, a[2].as<float>(), a[3].as<float>(), n, st)) return 1;
+    FINISH(4);
+}
 extern "C" int azg_net_forward(azg_net* net, int n, const int8_t* boards, const uint8_t* mask, float* pi, float* v, void* stream) {
     if (!net) return fail("net is NULL");
     if (n <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg;
-    if (a[0].in(boards, (size_t)n * SP2::S, st) || a[1].in(mask, (size_t)n * SP2::A, st) || a[2].outbuf(pi, sizeof(float) * n * SP2::A) ||
-        a[3].outbuf(v, sizeof(float) * n * SP2::NP)) return 1;
-    if (net->masks.ensure(sizeof(uint32_t) * (size_t)n * SP2::MASK_WORDS)) return 1;
-    k_pack_masks<<<(n + 3) / 4, 128, 0, st>>>(n, SP2::A, SP2::MASK_WORDS, a[1].as<uint8_t>(), (uint32_t*)net->masks.p);
-    if (net_forward_dev(net, nullptr, nullptr, a[0].as<int8_t>(), SP2::S, (const uint32_t*)net->masks.p, a[2].as<float>(), a[3].as<float>(), n, st)) return 1;
-    FINISH(4);
+    DISPATCH(net->game_id, net->np, net_forward_t<G>(net, n, boards, mask, pi, v, (cudaStream_t)stream));
 }
 
 // ------------------------------------------------------------------ engine ------------------------------
-struct azg_engine {
+template <class G>
+__global__ void k_load_roots(Dev<G> d, int n, const int8_t* roots, const uint8_t* full, int sims_full, int sims_fast) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= d.n_games) return;
+    if (g < n) {
+        for (int i = lane; i < G::SP; i += 32) d.root[(size_t)g * G::SP + i] = i < G::S ? roots[(size_t)g * G::S + i] : (int8_t)0;
+        if (lane == 0) { const bool f = full ? full[g] != 0 : true; d.full[g] = f; d.n_sims[g] = f ? sims_full : sims_fast; d.root_node[g] = 0; }
+    } else if (lane == 0) d.n_sims[g] = 0;
+}
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+enum { PK_SELECT = 0, PK_NET = 1, PK_BACKUP = 2, PK_OTHER = 3 };
+
+struct azg_engine {                      // game-independent face of the engine (the C ABI holds this)
+    virtual ~azg_engine() {}
+    virtual int reset(int game) = 0;
+    virtual int search(int n, const int8_t* roots, const uint8_t* full_search, const double* noise, int32_t* out_counts, int32_t* out_raw,
+                       float* out_q, cudaStream_t st) = 0;
+    virtual int selfplay(int min_episodes, int max_moves, cudaStream_t st) = 0;
+    virtual int examples(int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) = 0;
+    virtual int stats(int64_t* out16) = 0;
+    virtual int profile(int enable) = 0;
+    virtual int kernel_times(double* out8) = 0;
+};
+
+template <class G>
+struct EngineT : azg_engine {
     azg_engine_cfg cfg; azg_net* net = nullptr;
-    Dev<SP2> d; SelfPlay<SP2> sp;
+    Dev<G> d; SelfPlay<G> sp;
     std::vector<void*> allocs;
-    Scratch in_roots, in_full, in_noise, out_counts, out_raw, out_q;
     unsigned long long launches = 0;
     int sims_full = 0, sims_fast = 0;
     bool sp_ready = false;
     bool profiling = false; std::vector<cudaEvent_t> ev; size_t ev_used = 0; std::vector<int> ev_kind; double prof_ms[4] = {0, 0, 0, 0}; long long prof_n[4] = {0, 0, 0, 0};
+
     template <class T> int alloc(T** p, size_t n, bool zero = true) {
         void* q = nullptr;
         if (cudaMalloc(&q, sizeof(T) * n) != cudaSuccess) return fail("cudaMalloc failed for " + std::to_string(sizeof(T) * n) + " bytes (reduce n_games / node_cap / edge_cap)");
         if (zero && cudaMemset(q, 0, sizeof(T) * n) != cudaSuccess) return fail("cudaMemset failed");
         allocs.push_back(q); *p = (T*)q; return 0;
     }
+    ~EngineT() override {
+        for (void* p : allocs) cudaFree(p);
+        for (cudaEvent_t x : ev) cudaEventDestroy(x);
+    }
+    dim3 grid() const { return dim3((unsigned)((d.n_games + SEL_WARPS - 1) / SEL_WARPS)); }
+
+    int create(const azg_engine_cfg* c, azg_net* n_) {
+        cfg = *c; net = n_;
+        const int NG = c->n_games;
+        if (c->universes < 0 || c->universes > 8) return fail("universes must be in [0, 8]");
+        int node_cap = c->node_cap, edge_cap = c->edge_cap;
+        const int U0 = std::max(c->universes, 1);
+        constexpr int EDGE_FACTOR = G::A < 48 ? G::A : (G::GAME_ID == AZG_GAME_SPLENDOR ? 44 : 56);   // mean legal moves per expanded node (measured) + margin
+        if (node_cap <= 0) {
+            // default: room for the nodes that survive tree reuse, bounded by 60 % of free HBM
+            size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+            const double per_node = 48.0 + G::SP + 8.0 + EDGE_FACTOR * (17.0 + 4.0 * U0) + 2 * 8.0;
+            double fit = 0.6 * (double)free_b / (double)NG / per_node;
+            node_cap = (int)std::min<double>(fit, 16.0 * c->numMCTSSims + 1024);
+            node_cap = std::max(node_cap, c->numMCTSSims + 64);
+        }
+        if (edge_cap <= 0) edge_cap = node_cap * EDGE_FACTOR;
+        if (edge_cap >= (1 << 24)) return fail("edge_cap must be < 2^24");
+        cfg.node_cap = node_cap; cfg.edge_cap = edge_cap;
+        d.n_games = NG; d.node_cap = node_cap; d.edge_cap = edge_cap; d.ht_cap = next_pow2(2 * node_cap);
+        d.universes = c->universes; d.U = U0; d.forced_playouts = c->forced_playouts; d.dirichlet_noise = c->dirichlet_noise;
+        d.cpuct = c->cpuct; d.fpu = c->fpu; d.dir_alpha = c->dirichletAlpha; d.temp2 = c->temperature[2]; d.seed = c->seed;
+        d.noise = nullptr;
+        sims_full = c->numMCTSSims; sims_fast = c->ratio_fullMCTS > 0 ? c->numMCTSSims / c->ratio_fullMCTS : c->numMCTSSims;
+        int bad = 0;
+        bad |= alloc(&d.nodes, (size_t)NG * node_cap, false); bad |= alloc(&d.keys, (size_t)NG * node_cap, false); bad |= alloc(&d.edges, (size_t)NG * edge_cap, false);
+        bad |= alloc(&d.acts, (size_t)NG * edge_cap, false); bad |= alloc(&d.ht, (size_t)NG * d.ht_cap);
+        bad |= alloc(&d.n_nodes, NG); bad |= alloc(&d.n_edges, NG);
+        bad |= alloc(&d.child, (size_t)NG * edge_cap * d.U, false); bad |= alloc(&d.boards, (size_t)NG * node_cap * G::SP, false);
+        bad |= alloc(&d.remap, (size_t)NG * node_cap, false); bad |= alloc(&d.gcq, (size_t)NG * node_cap, false); bad |= alloc(&d.root_node, NG); bad |= alloc(&d.leaf_link, NG);
+        bad |= alloc(&d.root, (size_t)NG * G::SP); bad |= alloc(&d.n_sims, NG); bad |= alloc(&d.full, NG); bad |= alloc(&d.move_ctr, NG);
+        bad |= alloc(&d.path, (size_t)NG * G::MAX_DEPTH); bad |= alloc(&d.path_len, NG); bad |= alloc(&d.leaf_kind, NG);
+        bad |= alloc(&d.leaf_key, (size_t)2 * NG); bad |= alloc(&d.leaf_v, (size_t)NG * G::NP); bad |= alloc(&d.leaf_mask, (size_t)NG * G::MASK_WORDS);
+        bad |= alloc(&d.leaf_round, NG);
+        bad |= alloc(&d.nn_in, (size_t)NG * G::SP); bad |= alloc(&d.nn_pi, (size_t)NG * G::A); bad |= alloc(&d.nn_v, (size_t)NG * G::NP);
+        bad |= alloc(&d.nn_list, NG); bad |= alloc(&d.nn_count, 1); bad |= alloc(&d.stats, (size_t)NG * ST_N);
+        return bad;
+    }
+    int reset(int game) override {
+        if (game >= d.n_games) return fail("game index out of range");
+        k_reset<G><<<game >= 0 ? 8 : 592, 256>>>(d, game);
+        launches++;
+        CKL(); return 0;
+    }
+
+    // ---- optional per-kernel timing: an event before and after each launch, drained by prof_drain() ----
+    void prof_mark(int kind, cudaStream_t st) {              // kind >= 0: start of a launch of that kind; -1: end
+        if (!profiling) return;
+        if (ev_used == ev.size()) { cudaEvent_t x; cudaEventCreate(&x); ev.push_back(x); ev_kind.push_back(0); }
+        ev_kind[ev_used] = kind;
+        cudaEventRecord(ev[ev_used++], st);
+    }
+    int prof_drain() {
+        if (ev_used == 0) return 0;
+        CK(cudaEventSynchronize(ev[ev_used - 1]));
+        for (size_t i = 0; i + 1 < ev_used; i++) {
+            const int k = ev_kind[i];
+            if (k < 0) continue;
+            float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            prof_ms[k] += ms; prof_n[k]++;
+        }
+        ev_used = 0; return 0;
+    }
+    int profile(int enable) override {
+        if (prof_drain()) return 1;
+        profiling = enable != 0;
+        if (enable) for (int k = 0; k < 4; k++) { prof_ms[k] = 0; prof_n[k] = 0; }
+        return 0;
+    }
+    int kernel_times(double* out8) override {
+        if (prof_drain()) return 1;
+        out8[0] = prof_ms[PK_SELECT]; out8[1] = prof_ms[PK_NET]; out8[2] = prof_ms[PK_BACKUP]; out8[3] = prof_ms[PK_OTHER];
+        out8[4] = (double)prof_n[PK_SELECT]; out8[5] = (double)prof_n[PK_SELECT]; out8[6] = (double)prof_n[PK_NET]; out8[7] = (double)prof_n[PK_BACKUP];
+        return 0;
+    }
+
+    // One lock-step simulation for every game: select -> batched leaf evaluation -> expand + backup.
+    int step(int s, cudaStream_t st) {
+        const int NG = d.n_games;
+        prof_mark(PK_SELECT, st);
+        k_select<G><<<(unsigned)((NG + SELK_WARPS - 1) / SELK_WARPS), SELK_WARPS * 32, 0, st>>>(d, s);
+        prof_mark(PK_NET, st);
+        if (net_forward_dev<G>(net, d.nn_count, d.nn_list, d.nn_in, G::SP, d.leaf_mask, d.nn_pi, d.nn_v, NG, st)) return 1;
+        prof_mark(PK_BACKUP, st);
+        k_backup<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, s);
+        prof_mark(-1, st);
+        launches += 3;
+        return 0;
+    }
+    int gc(int sims, cudaStream_t st) {
+        prof_mark(PK_OTHER, st);
+        k_gc<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, sims + 2, (sims + 2) * G::MAX_LEGAL, 0);
+        prof_mark(-1, st);
+        launches++;
+        return 0;
+    }
+
+    int search(int n, const int8_t* roots, const uint8_t* full_search, const double* noise, int32_t* out_counts, int32_t* out_raw,
+               float* out_q, cudaStream_t st) override {
+        if (n <= 0 || n > d.n_games) return fail("n must be in [1, n_games]");
+        if (!roots || !out_counts) return fail("roots / out_counts is NULL");
+        Arg* a = tl_arg; const int NG = d.n_games;
+        if (a[0].in(roots, (size_t)n * G::S, st) || a[1].in(full_search, (size_t)n, st) || a[2].in(noise, sizeof(double) * n * G::A, st) ||
+            a[3].outbuf(out_counts, sizeof(int) * n * G::A) || a[4].outbuf(out_raw, sizeof(int) * n * G::A) || a[5].outbuf(out_q, sizeof(float) * n * G::NP)) return 1;
+        CK(cudaMemsetAsync(d.nn_count, 0, sizeof(int), st));
+        k_load_roots<G><<<(NG + 3) / 4, 128, 0, st>>>(d, n, a[0].as<int8_t>(), a[1].as<uint8_t>(), sims_full, sims_fast);
+        launches++;
+        d.noise = a[2].as<double>();
+        // without host knowledge of the flags run the longer budget; finished games idle (k_select early-out)
+        int steps = sims_full;
+        if (full_search && !is_device_ptr(full_search)) { bool any = false; for (int i = 0; i < n; i++) any |= full_search[i] != 0; if (!any) steps = sims_fast; }
+        gc(steps, st);
+        for (int s = 0; s < steps; s++) if (step(s, st)) return 1;
+        k_finish<G><<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(d, n, a[3].as<int>(), a[4].as<int>(), a[5].as<float>());
+        launches++;
+        d.noise = nullptr;
+        if (profiling) { CKL(); if (prof_drain()) return 1; }
+        FINISH(6);
+    }
+
+    int stats(int64_t* out16) override {
+        const int NG = d.n_games;
+        std::vector<unsigned long long> h((size_t)NG * ST_N);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h.data(), d.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 16; k++) out16[k] = 0;
+        for (int g = 0; g < NG; g++)
+            for (int k = 0; k < ST_N; k++) {
+                if (k == ST_MAXNODES) out16[k] = std::max<int64_t>(out16[k], (int64_t)h[(size_t)g * ST_N + k]);
+                else out16[k] += (int64_t)h[(size_t)g * ST_N + k];
+            }
+        out16[12] = (int64_t)(launches + (net ? net->launches : 0));
+        out16[14] = d.node_cap;
+        return 0;
+    }
+
+    // ---- Coach.executeEpisodes (Coach.py:86-148) ----
+    int selfplay_setup() {
+        if (sp_ready) return 0;
+        const int NG = d.n_games; const azg_engine_cfg& c = cfg;
+        sp.max_ply = G::MAX_MOVES; sp.ex_cap = NG * G::MAX_MOVES;
+        sp.prob_full = c.prob_fullMCTS; sp.t_begin = c.temperature[0]; sp.t_end = c.temperature[1]; sp.half_life = c.tempThreshold;
+        int bad = 0; const size_t M = (size_t)NG * sp.max_ply;
+        bad |= alloc(&sp.board, (size_t)NG * G::SP); bad |= alloc(&sp.player, NG); bad |= alloc(&sp.ply, NG); bad |= alloc(&sp.active, NG);
+        bad |= alloc(&sp.games_started, NG);
+        bad |= alloc(&sp.st_board, M * G::S, false); bad |= alloc(&sp.st_pi, M * G::A, false); bad |= alloc(&sp.st_mask, M * G::MASK_WORDS, false);
+        bad |= alloc(&sp.st_q, M * G::NP, false); bad |= alloc(&sp.st_player, M, false); bad |= alloc(&sp.st_count, NG);
+        bad |= alloc(&sp.ex_board, (size_t)sp.ex_cap * G::S, false); bad |= alloc(&sp.ex_pi, (size_t)sp.ex_cap * G::A, false);
+        bad |= alloc(&sp.ex_z, (size_t)sp.ex_cap * G::NP, false); bad |= alloc(&sp.ex_valid, (size_t)sp.ex_cap * G::A, false);
+        bad |= alloc(&sp.ex_q, (size_t)sp.ex_cap * G::NP, false); bad |= alloc(&sp.ex_count, 1); bad |= alloc(&sp.counters, 8);
+        if (bad) return 1;
+        sp_ready = true; return 0;
+    }
+    int selfplay(int min_episodes, int max_moves, cudaStream_t st) override {
+        if (selfplay_setup()) return 1;
+        unsigned long long start[8], now[8];
+        CK(cudaMemcpyAsync(start, sp.counters, sizeof(start), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        for (int mv = 0; max_moves <= 0 || mv < max_moves; mv++) {
+            prof_mark(PK_OTHER, st);
+            k_sp_begin<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, sp, sims_full, sims_fast);
+            prof_mark(-1, st);
+            launches++;
+            const int steps = (cfg.prob_fullMCTS > 0.0) ? sims_full : sims_fast;
+            gc(steps, st);
+            for (int s = 0; s < steps; s++) if (step(s, st)) return 1;
+            prof_mark(PK_OTHER, st);
+            k_sp_end<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, sp);
+            prof_mark(-1, st);
+            launches++;
+            CKL();
+            if (profiling && prof_drain()) return 1;
+            if (min_episodes > 0) {
+                CK(cudaMemcpyAsync(now, sp.counters, sizeof(now), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+                if ((long long)(now[0] - start[0]) >= min_episodes) break;
+            }
+            if (max_moves <= 0 && min_episodes <= 0) break;
+        }
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    int examples(int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) override {
+        *out_n = 0;
+        if (!sp_ready) return 0;
+        CK(cudaDeviceSynchronize());
+        int count = 0; CK(cudaMemcpy(&count, sp.ex_count, sizeof(int), cudaMemcpyDeviceToHost));
+        count = std::min(count, sp.ex_cap);
+        const int m = std::min(count, cap);
+        if (m > 0) {
+            if (!boards || !pi || !z || !valids || !q) return fail("NULL output buffer");
+            CK(cudaMemcpy(boards, sp.ex_board, (size_t)m * G::S, cudaMemcpyDefault));
+            CK(cudaMemcpy(pi, sp.ex_pi, sizeof(float) * (size_t)m * G::A, cudaMemcpyDefault));
+            CK(cudaMemcpy(z, sp.ex_z, sizeof(float) * (size_t)m * G::NP, cudaMemcpyDefault));
+            CK(cudaMemcpy(valids, sp.ex_valid, (size_t)m * G::A, cudaMemcpyDefault));
+            CK(cudaMemcpy(q, sp.ex_q, sizeof(float) * (size_t)m * G::NP, cudaMemcpyDefault));
+        }
+        const int rest = count - m;
+        if (rest > 0) {                                   // keep what did not fit: slide it to the front through a temporary
+            Scratch tmp;
+            auto slide = [&](void* base, size_t elt) -> int {
+                if (tmp.ensure((size_t)rest * elt)) return 1;
+                if (cudaMemcpy(tmp.p, (char*)base + (size_t)m * elt, (size_t)rest * elt, cudaMemcpyDeviceToDevice) != cudaSuccess) return fail("slide copy failed");
+                if (cudaMemcpy(base, tmp.p, (size_t)rest * elt, cudaMemcpyDeviceToDevice) != cudaSuccess) return fail("slide copy failed");
+                return 0;
+            };
+            if (slide(sp.ex_board, G::S) || slide(sp.ex_pi, sizeof(float) * G::A) || slide(sp.ex_z, sizeof(float) * G::NP) ||
+                slide(sp.ex_valid, G::A) || slide(sp.ex_q, sizeof(float) * G::NP)) return 1;
+        }
+        CK(cudaMemcpy(sp.ex_count, &rest, sizeof(int), cudaMemcpyHostToDevice));
+        *out_n = m; return 0;
+    }
 };
 
-__global__ void k_load_roots(Dev<SP2> d, int n, const int8_t* roots, const uint8_t* full, int sims_full, int sims_fast) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (g >= d.n_games) return;
-    if (g < n) {
-        for (int i = lane; i < SP2::SP; i += 32) d.root[(size_t)g * SP2::SP + i] = i < SP2::S ? roots[(size_t)g * SP2::S + i] : (int8_t)0;
-        if (lane == 0) { const bool f = full ? full[g] != 0 : true; d.full[g] = f; d.n_sims[g] = f ? sims_full : sims_fast; d.root_node[g] = 0; }
-    } else if (lane == 0) d.n_sims[g] = 0;
-}
-
-static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
-
-extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_engine** out) {
-    if (!cfg || !net || !out) return fail("NULL argument");
-    if (require_device() || check_game(cfg->game_id, cfg->num_players)) return 1;
-    if (cfg->n_games <= 0 || cfg->numMCTSSims <= 0) return fail("n_games and numMCTSSims must be positive");
-    azg_engine* e = new azg_engine(); e->cfg = *cfg; e->net = net;
-    const int G = cfg->n_games;
-    int node_cap = cfg->node_cap, edge_cap = cfg->edge_cap;
-    if (node_cap <= 0) {
-        // default: room for the nodes that survive tree reuse (measured <= ~10x sims/move with a random-init net)
-        // bounded by 60 % of free HBM
-        size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-        const int U0 = std::max(cfg->universes, 1);
-        const double per_node = 48.0 + SP2::SP + 8.0 + 44.0 * (17.0 + 4.0 * U0) + 2 * 8.0;
-        double fit = 0.6 * (double)free_b / (double)G / per_node;
-        node_cap = (int)std::min<double>(fit, 16.0 * cfg->numMCTSSims + 1024);
-        node_cap = std::max(node_cap, cfg->numMCTSSims + 64);
-    }
-    if (edge_cap <= 0) edge_cap = node_cap * 44;             // mean legal moves per expanded node ~38-42 (measured)
-    if (edge_cap >= (1 << 24)) return fail("edge_cap must be < 2^24");
-    e->cfg.node_cap = node_cap; e->cfg.edge_cap = edge_cap;
-    Dev<SP2>& d = e->d;
-    d.n_games = G; d.node_cap = node_cap; d.edge_cap = edge_cap; d.ht_cap = next_pow2(2 * node_cap);
-    if (cfg->universes < 0 || cfg->universes > 8) { delete e; return fail("universes must be in [0, 8]"); }
-    d.universes = cfg->universes; d.U = std::max(cfg->universes, 1); d.forced_playouts = cfg->forced_playouts; d.dirichlet_noise = cfg->dirichlet_noise;
-    d.cpuct = cfg->cpuct; d.fpu = cfg->fpu; d.dir_alpha = cfg->dirichletAlpha; d.temp2 = cfg->temperature[2]; d.seed = cfg->seed;
-    d.noise = nullptr;
-    e->sims_full = cfg->numMCTSSims; e->sims_fast = cfg->ratio_fullMCTS > 0 ? cfg->numMCTSSims / cfg->ratio_fullMCTS : cfg->numMCTSSims;
-    int bad = 0;
-    bad |= e->alloc(&d.nodes, (size_t)G * node_cap, false); bad |= e->alloc(&d.keys, (size_t)G * node_cap, false); bad |= e->alloc(&d.edges, (size_t)G * edge_cap, false);
-    bad |= e->alloc(&d.acts, (size_t)G * edge_cap, false); bad |= e->alloc(&d.ht, (size_t)G * d.ht_cap);
-    bad |= e->alloc(&d.n_nodes, G); bad |= e->alloc(&d.n_edges, G);
-    bad |= e->alloc(&d.child, (size_t)G * edge_cap * d.U, false); bad |= e->alloc(&d.boards, (size_t)G * node_cap * SP2::SP, false);
-    bad |= e->alloc(&d.remap, (size_t)G * node_cap, false); bad |= e->alloc(&d.gcq, (size_t)G * node_cap, false); bad |= e->alloc(&d.root_node, G); bad |= e->alloc(&d.leaf_link, G);
-    bad |= e->alloc(&d.root, (size_t)G * SP2::SP); bad |= e->alloc(&d.n_sims, G); bad |= e->alloc(&d.full, G); bad |= e->alloc(&d.move_ctr, G);
-    bad |= e->alloc(&d.path, (size_t)G * SP2::MAX_DEPTH); bad |= e->alloc(&d.path_len, G); bad |= e->alloc(&d.leaf_kind, G);
-    bad |= e->alloc(&d.leaf_key, (size_t)2 * G); bad |= e->alloc(&d.leaf_v, (size_t)G * SP2::NP); bad |= e->alloc(&d.leaf_mask, (size_t)G * SP2::MASK_WORDS);
-    bad |= e->alloc(&d.leaf_round, G);
-    bad |= e->alloc(&d.nn_in, (size_t)G * SP2::SP); bad |= e->alloc(&d.nn_pi, (size_t)G * SP2::A); bad |= e->alloc(&d.nn_v, (size_t)G * SP2::NP);
-    bad |= e->alloc(&d.nn_list, G); bad |= e->alloc(&d.nn_count, 1); bad |= e->alloc(&d.stats, (size_t)G * ST_N);
-    if (bad) { azg_engine_destroy(e); return 1; }
+template <class G> static int engine_create_t(const azg_engine_cfg* cfg, azg_net* net, azg_engine** out) {
+    EngineT<G>* e = new EngineT<G>();
+    if (e->create(cfg, net)) { delete e; return 1; }
     *out = e; return 0;
 }
-extern "C" int azg_engine_destroy(azg_engine* e) {
-    if (!e) return 0;
-    for (void* p : e->allocs) cudaFree(p);
-    for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
-    delete e; return 0;
+extern "C" int azg_engine_create(const azg_engine_cfg* cfg, azg_net* net, azg_engine** out) {
+    if (!cfg || !net || !out) return fail("NULL argument");
+    if (require_device()) return 1;
+    if (cfg->n_games <= 0 || cfg->numMCTSSims <= 0) return fail("n_games and numMCTSSims must be positive");
+    if (net->game_id != cfg->game_id || net->np != cfg->num_players) return fail("net was created for another game");
+    DISPATCH(cfg->game_id, cfg->num_players, engine_create_t<G>(cfg, net, out));
 }
-extern "C" int azg_engine_reset(azg_engine* e, int game) {
-    if (!e) return fail("engine is NULL");
-    if (game >= e->d.n_games) return fail("game index out of range");
-    k_reset<SP2><<<game >= 0 ? 8 : 592, 256>>>(e->d, game);
-    e->launches++;
-    CKL(); return 0;
-}
-
-// ---- optional per-kernel timing: an event before and after each launch, drained by prof_drain() ----
-enum { PK_SELECT = 0, PK_NET = 1, PK_BACKUP = 2, PK_OTHER = 3 };
-static void prof_mark(azg_engine* e, int kind, cudaStream_t st) {      // kind >= 0: start of a launch of that kind; -1: end
-    if (!e->profiling) return;
-    if (e->ev_used == e->ev.size()) { cudaEvent_t x; cudaEventCreate(&x); e->ev.push_back(x); e->ev_kind.push_back(0); }
-    e->ev_kind[e->ev_used] = kind;
-    cudaEventRecord(e->ev[e->ev_used++], st);
-}
-static int prof_drain(azg_engine* e) {
-    if (e->ev_used == 0) return 0;
-    CK(cudaEventSynchronize(e->ev[e->ev_used - 1]));
-    for (size_t i = 0; i + 1 < e->ev_used; i++) {
-        const int k = e->ev_kind[i];
-        if (k < 0) continue;
-        float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
-        e->prof_ms[k] += ms; e->prof_n[k]++;
-    }
-    e->ev_used = 0; return 0;
-}
-
-// One lock-step simulation for every game: select -> batched leaf evaluation -> expand + backup.
-static int engine_step(azg_engine* e, int step, cudaStream_t st) {
-    const int G = e->d.n_games; const dim3 grid((unsigned)((G + SEL_WARPS - 1) / SEL_WARPS));
-    prof_mark(e, PK_SELECT, st);
-    k_select<SP2><<<(unsigned)((G + SELK_WARPS - 1) / SELK_WARPS), SELK_WARPS * 32, 0, st>>>(e->d, step);
-    prof_mark(e, PK_NET, st);
-    if (net_forward_dev(e->net, e->d.nn_count, e->d.nn_list, e->d.nn_in, SP2::SP, e->d.leaf_mask, e->d.nn_pi, e->d.nn_v, G, st)) return 1;
-    prof_mark(e, PK_BACKUP, st);
-    k_backup<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, step);
-    prof_mark(e, -1, st);
-    e->launches += 3;
-    return 0;
-}
-static int engine_gc(azg_engine* e, int sims, cudaStream_t st) {
-    const int G = e->d.n_games; const dim3 grid((unsigned)((G + SEL_WARPS - 1) / SEL_WARPS));
-    prof_mark(e, PK_OTHER, st);
-    k_gc<SP2><<<grid, SEL_WARPS * 32, 0, st>>>(e->d, sims + 2, (sims + 2) * 48, 0);
-    prof_mark(e, -1, st);
-    e->launches++;
-    return 0;
-}
-extern "C" int azg_engine_profile(azg_engine* e, int enable) {
-    if (!e) return fail("engine is NULL");
-    if (prof_drain(e)) return 1;
-    e->profiling = enable != 0;
-    if (enable) for (int k = 0; k < 4; k++) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
-    return 0;
-}
-extern "C" int azg_engine_kernel_times(azg_engine* e, double* out8) {
-    if (!e || !out8) return fail("NULL argument");
-    if (prof_drain(e)) return 1;
-    out8[0] = e->prof_ms[PK_SELECT]; out8[1] = e->prof_ms[PK_NET]; out8[2] = e->prof_ms[PK_BACKUP]; out8[3] = e->prof_ms[PK_OTHER];
-    out8[4] = (double)e->prof_n[PK_SELECT]; out8[5] = (double)e->prof_n[PK_SELECT]; out8[6] = (double)e->prof_n[PK_NET]; out8[7] = (double)e->prof_n[PK_BACKUP];
-    return 0;
-}
-
+extern "C" int azg_engine_destroy(azg_engine* e) { delete e; return 0; }
+extern "C" int azg_engine_reset(azg_engine* e, int game) { if (!e) return fail("engine is NULL"); return e->reset(game); }
+extern "C" int azg_engine_profile(azg_engine* e, int enable) { if (!e) return fail("engine is NULL"); return e->profile(enable); }
+extern "C" int azg_engine_kernel_times(azg_engine* e, double* out8) { if (!e || !out8) return fail("NULL argument"); return e->kernel_times(out8); }
 extern "C" int azg_engine_search(azg_engine* e, int n, const int8_t* roots, const uint8_t* full_search, const double* noise,
                                  int32_t* out_counts, int32_t* out_raw, float* out_q, void* stream) {
     if (!e) return fail("engine is NULL");
-    if (n <= 0 || n > e->d.n_games) return fail("n must be in [1, n_games]");
-    if (!roots || !out_counts) return fail("roots / out_counts is NULL");
-    cudaStream_t st = (cudaStream_t)stream; Arg* a = tl_arg; const int G = e->d.n_games;
-    if (a[0].in(roots, (size_t)n * SP2::S, st) || a[1].in(full_search, (size_t)n, st) || a[2].in(noise, sizeof(double) * n * SP2::A, st) ||
-        a[3].outbuf(out_counts, sizeof(int) * n * SP2::A) || a[4].outbuf(out_raw, sizeof(int) * n * SP2::A) || a[5].outbuf(out_q, sizeof(float) * n * SP2::NP)) return 1;
-    CK(cudaMemsetAsync(e->d.nn_count, 0, sizeof(int), st));
-    k_load_roots<<<(G + 3) / 4, 128, 0, st>>>(e->d, n, a[0].as<int8_t>(), a[1].as<uint8_t>(), e->sims_full, e->sims_fast);
-    e->launches++;
-    e->d.noise = a[2].as<double>();
-    // without host knowledge of the flags run the longer budget; finished games idle (k_select early-out)
-    int steps = e->sims_full;
-    if (full_search && !is_device_ptr(full_search)) { bool any = false; for (int i = 0; i < n; i++) any |= full_search[i] != 0; if (!any) steps = e->sims_fast; }
-    engine_gc(e, steps, st);
-    for (int s = 0; s < steps; s++) if (engine_step(e, s, st)) return 1;
-    k_finish<SP2><<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(e->d, n, a[3].as<int>(), a[4].as<int>(), a[5].as<float>());
-    e->launches++;
-    e->d.noise = nullptr;
-    if (e->profiling) { CKL(); if (prof_drain(e)) return 1; }
-    FINISH(6);
+    return e->search(n, roots, full_search, noise, out_counts, out_raw, out_q, (cudaStream_t)stream);
 }
-
-extern "C" int azg_engine_stats(azg_engine* e, int64_t* out16) {
-    if (!e || !out16) return fail("NULL argument");
-    const int G = e->d.n_games;
-    std::vector<unsigned long long> h((size_t)G * ST_N);
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(h.data(), e->d.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 16; k++) out16[k] = 0;
-    for (int g = 0; g < G; g++)
-        for (int k = 0; k < ST_N; k++) {
-            if (k == ST_MAXNODES) out16[k] = std::max<int64_t>(out16[k], (int64_t)h[(size_t)g * ST_N + k]);
-            else out16[k] += (int64_t)h[(size_t)g * ST_N + k];
-        }
-    out16[12] = (int64_t)(e->launches + (e->net ? e->net->launches : 0));
-    out16[14] = e->d.node_cap;
-    return 0;
+extern "C" int azg_engine_stats(azg_engine* e, int64_t* out16) { if (!e || !out16) return fail("NULL argument"); return e->stats(out16); }
+extern "C" int azg_engine_selfplay(azg_engine* e, int min_episodes, int max_moves, void* stream) {
+    if (!e) return fail("engine is NULL");
+    return e->selfplay(min_episodes, max_moves, (cudaStream_t)stream);
 }
-
-#include "selfplay_api.inl"
+extern "C" int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) {
+    if (!e || !out_n) return fail("NULL argument");
+    return e->examples(cap, boards, pi, z, valids, q, out_n);
+}

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_sp_end(Dev<G> d, SelfPlay<G>
     np = __shfl_sync(FULL, np, 0);
     for (int i = lane; i < G::SP; i += 32) board[i] = sb[i];
     float r[NP];
-    const bool over = G::ended(sb, r);                            // Coach.py:73
+    const bool over = G::ended(sb, np, r, lane);                  // Coach.py:73: getGameEnded(board, curPlayer)
     if (lane == 0) { sp.player[g] = np; atomicAdd(&sp.counters[3], 1ULL); d.stats[(size_t)g * ST_N + ST_MOVES]++; }
     if (over) {
         const int n_ex = sp.st_count[g];

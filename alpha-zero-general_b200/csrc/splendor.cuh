@@ -45,10 +45,12 @@ struct Splendor {
     static constexpr int NN = NP + 1;                         // nobles in play
     static constexpr int COLS = 7;
     static constexpr int ROWS = 32 + 10 * NP + NP * NP;      // observation_size(), SplendorLogicNumba.py:90-92
+    static constexpr int D0 = ROWS, D1 = COLS, D2 = 1;
     static constexpr int S = ROWS * COLS;                     // 392 bytes for 2 players
     static constexpr int SP = (S + 15) / 16 * 16;             // padded to 16 B for 128-bit loads (400)
     static constexpr int A = 81;
     static constexpr int MASK_WORDS = 3;
+    static constexpr int MAX_LEGAL = 64;                      // upper bound used to reserve edge space (largest seen: 62)
     static constexpr int MAX_MOVES = 62 * NP;                 // SplendorLogicNumba.py:146
     static constexpr int MAX_DEPTH = MAX_MOVES + 4;
     static constexpr int MAX_SYM = 1 + 9 + 2 * NP;
@@ -263,8 +265,9 @@ struct Splendor {
         return (player + 1) % NP;
     }
 
-    // check_end_game (SplendorLogicNumba.py:221-240). Any lane; returns true if the game is over.
-    static __device__ bool ended(const int8_t* b, float (&out)[NP]) {
+    // check_end_game (SplendorLogicNumba.py:221-240). Every lane computes the same result; returns true if the game is over.
+    // (`next_player` is part of the Game.getGameEnded signature, Game.py:64; Splendor does not use it.)
+    static __device__ bool ended(const int8_t* b, int next_player, float (&out)[NP], int lane) {
 #pragma unroll
         for (int p = 0; p < NP; p++) out[p] = 0.f;
         int rnd = round(b);

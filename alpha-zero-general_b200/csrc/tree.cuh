@@ -318,7 +318,7 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, ui
     const int8_t* sb = ws.board;
     float es[G::NP];
     int kind;
-    if (G::ended(sb, es)) {
+    if (G::ended(sb, 0, es, lane)) {                            // MCTS.py:131: getGameEnded(canonicalBoard, 0)
         kind = LEAF_NEW_TERMINAL;
         if (lane == 0) for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p];
     } else {

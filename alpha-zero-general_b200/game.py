@@ -14,6 +14,7 @@ class CudaGame:
     """Same 15-method surface as the reference's Game (Game.py). Batched variants carry a `_batch` suffix."""
 
     game_id = _lib.AZG_GAME_SPLENDOR
+    max_score_diff = 15
 
     def __init__(self, num_players=NUMBER_PLAYERS):
         self.num_players = num_players
@@ -24,6 +25,8 @@ class CudaGame:
 
     # ---- sizes
     def getBoardSize(self):
+        if self.info.state_depth > 1:
+            return (self.info.state_rows, self.info.state_cols, self.info.state_depth)
         return (self.info.state_rows, self.info.state_cols)
 
     def getActionSize(self):
@@ -33,7 +36,7 @@ class CudaGame:
         return self.num_players
 
     def getMaxScoreDiff(self):
-        return 15
+        return self.max_score_diff
 
     # ---- batched primitives
     def _boards(self, boards):
@@ -63,10 +66,11 @@ class CudaGame:
                                          _lib.ptr(rk), _lib.ptr(out), _lib.ptr(onp), None))
         return out.reshape((-1,) + self.getBoardSize()), onp
 
-    def ended_batch(self, boards):
+    def ended_batch(self, boards, next_players=None):
         b = self._boards(boards); n = len(b)
+        npl = None if next_players is None else np.ascontiguousarray(next_players, dtype=np.int32)
         out = np.empty((n, self.num_players), np.float32)
-        _lib.check(self._L.azg_game_ended(self.game_id, self.num_players, n, _lib.ptr(b), _lib.ptr(out), None))
+        _lib.check(self._L.azg_game_ended(self.game_id, self.num_players, n, _lib.ptr(b), _lib.ptr(npl), _lib.ptr(out), None))
         return out
 
     def canonical_batch(self, boards, players):
@@ -106,7 +110,7 @@ class CudaGame:
         return self.valid_batch(board[None], [player])[0]
 
     def getGameEnded(self, board, next_player):
-        return self.ended_batch(board[None])[0]
+        return self.ended_batch(board[None], [next_player])[0]
 
     def getScore(self, board, player):
         return int(self.round_score_batch(board[None])[1][0, player])
@@ -127,7 +131,7 @@ class CudaGame:
         return board.tobytes()
 
     def moveToString(self, move, current_player):
-        return splendor_move_to_str(move)
+        return f'action {move}'
 
     def printBoard(self, numpy_board):
         print(np.asarray(numpy_board))
@@ -159,3 +163,21 @@ class SplendorGame(CudaGame):
 
     def __init__(self):
         super().__init__(NUMBER_PLAYERS)
+
+    def moveToString(self, move, current_player):
+        return splendor_move_to_str(move)
+
+
+class SantoriniGame(CudaGame):
+    """Drop-in for santorini/SantoriniGame.py:SantoriniGame built without god powers (NB_GODS = 1,
+    santorini/SantoriniConstants.py:19): int8[5,5,3] boards, 162 actions = 81*worker + 9*move_direction + build_direction."""
+
+    game_id = _lib.AZG_GAME_SANTORINI
+    max_score_diff = 3
+
+    def __init__(self):
+        super().__init__(2)
+
+    def moveToString(self, move, current_player):
+        dirs = ('NW', 'N', 'NE', 'W', '-', 'E', 'SW', 'S', 'SE')
+        return f'worker {move // 81 + 1} moves {dirs[(move % 81) // 9]} and builds {dirs[move % 9]}'

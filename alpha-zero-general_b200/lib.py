@@ -10,6 +10,8 @@ CSRC = os.path.join(HERE, 'csrc')
 SO_PATH = os.path.join(CSRC, 'libazg_b200.so')
 
 AZG_GAME_SPLENDOR = 1
+AZG_GAME_SANTORINI = 2
+AZG_ABI_VERSION = 2
 AZG_NET_HASH = 0
 AZG_NET_SPLENDOR_V80 = 80
 
@@ -21,7 +23,7 @@ SYMBOLS = ['azg_abi_version', 'azg_last_error', 'azg_device_count', 'azg_set_dev
 
 
 class GameInfo(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ('game_id', 'num_players', 'state_rows', 'state_cols', 'state_bytes', 'action_size',
+    _fields_ = [(n, C.c_int32) for n in ('game_id', 'num_players', 'state_rows', 'state_cols', 'state_depth', 'state_bytes', 'action_size',
                                          'max_symmetries', 'max_game_len')]
 
 
@@ -61,7 +63,7 @@ def load():
     L.azg_game_init.argtypes = [i32, i32, i32, vp, vp, vp]
     L.azg_game_valid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     L.azg_game_next.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
-    L.azg_game_ended.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.azg_game_ended.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     L.azg_game_canonical.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     L.azg_game_round_score.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     L.azg_game_symmetries.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -82,6 +84,8 @@ def load():
     for name in SYMBOLS:
         if name not in ('azg_last_error',):
             getattr(L, name).restype = i32
+    if L.azg_abi_version() != AZG_ABI_VERSION:
+        raise AzgError(f'{SO_PATH}: ABI version {L.azg_abi_version()} != {AZG_ABI_VERSION}; rebuild (make -C alpha-zero-general_b200/csrc)')
     _lib = L
     return L
 

@@ -189,8 +189,8 @@ class HostLoop:
         self.d2h += self.board2.nbytes + self.player2.nbytes
         self.board, self.board2 = self.board2, self.board; self.player, self.player2 = self.player2, self.player
         # Game.getGameEnded, Coach.py:73
-        lib.check(L.azg_game_ended(g.game_id, N_PL, n, p(self.board), p(self.ended), None))
-        self.h2d += self.board.nbytes; self.d2h += self.ended.nbytes
+        lib.check(L.azg_game_ended(g.game_id, N_PL, n, p(self.board), p(self.player), p(self.ended), None))
+        self.h2d += self.board.nbytes + self.player.nbytes; self.d2h += self.ended.nbytes
         done = np.flatnonzero(self.ended.any(axis=1))
         for i in done:                                              # finished game: new game + fresh tree in that slot (Coach.py:93-98)
             self.board[i] = g.init_batch(np.array([self.key_ctr + int(i)], dtype=np.uint64)).reshape(-1); self.player[i] = 0

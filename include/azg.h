@@ -27,14 +27,16 @@
 extern "C" {
 #endif
 
-#define AZG_ABI_VERSION 1
+#define AZG_ABI_VERSION 2
 
-enum { AZG_GAME_SPLENDOR = 1 };                          /* GameSwitcher.py:3-13 ('splendor') */
+enum { AZG_GAME_SPLENDOR = 1,                            /* GameSwitcher.py:3-13 ('splendor'), 2 players            */
+       AZG_GAME_SANTORINI = 2 };                         /* 'santorini' built with NB_GODS = 1 (SantoriniConstants.py:19) */
 enum { AZG_NET_HASH = 0, AZG_NET_SPLENDOR_V80 = 80 };    /* HASH: deterministic test net (tests only) */
 
 typedef struct {
     int32_t game_id, num_players;
-    int32_t state_rows, state_cols, state_bytes;         /* Game.getBoardSize   Game.py:22  */
+    int32_t state_rows, state_cols, state_depth;         /* Game.getBoardSize   Game.py:22 (depth 1 = 2-D board) */
+    int32_t state_bytes;
     int32_t action_size;                                 /* Game.getActionSize  Game.py:29  */
     int32_t max_symmetries;                              /* upper bound of len(getSymmetries()) */
     int32_t max_game_len;                                /* upper bound on plies per game */
@@ -58,8 +60,9 @@ int azg_game_valid(int game_id, int num_players, int n, const int8_t* boards, co
 int azg_game_next(int game_id, int num_players, int n, const int8_t* boards, const int32_t* players,
                   const int32_t* actions, const int64_t* seeds, const uint64_t* rng_keys,
                   int8_t* out_boards, int32_t* out_next_player, void* stream);
-/* Game.getGameEnded (Game.py:64; SplendorLogicNumba.py:221-240): float32[n][num_players]. */
-int azg_game_ended(int game_id, int num_players, int n, const int8_t* boards, float* out, void* stream);
+/* Game.getGameEnded(board, next_player) (Game.py:64; SplendorLogicNumba.py:221-240; SantoriniLogicNumba.py:552-565):
+ * float32[n][num_players]. next_players = the player to move on each board (NULL = all 0; Splendor ignores it). */
+int azg_game_ended(int game_id, int num_players, int n, const int8_t* boards, const int32_t* next_players, float* out, void* stream);
 /* Game.getCanonicalForm (Game.py:97; SplendorLogicNumba.py:244-253). */
 int azg_game_canonical(int game_id, int num_players, int n, const int8_t* boards, const int32_t* players,
                        int8_t* out_boards, void* stream);

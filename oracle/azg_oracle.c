@@ -29,6 +29,7 @@ typedef uint8_t u8;
 
 #define COLS 7
 #define NA 81            /* action_size(), splendor/SplendorLogicNumba.py:94-96 */
+#define MAXA 162         /* largest action space the MCTS port handles (Santorini without gods) */
 #define MAXP 4
 #define MAXROWS 88       /* observation_size(4) = 32+40+16 rows */
 #define MAXS (MAXROWS * COLS)
@@ -383,24 +384,155 @@ int azo_symmetries(const i8* b, int n, const float* pi, const u8* valids, i8* ob
     return k;
 }
 
+/* ================================================================ Santorini, no gods ====================
+ * santorini/SantoriniLogicNumba.py built with NB_GODS = 1 (santorini/SantoriniConstants.py:19): state int8[5][5][3]
+ * (cell c = 5y+x at bytes 3c..3c+2: worker, level, gods_power), gods_power.flat[i] = byte 3i+2; flat[0], flat[1] = 64
+ * (NO_GOD owned), flat[2] = round counter; flat[8..10] are the Pan / Athena slots the no-god code still reads.
+ * Action = 81*worker + 9*move_direction + build_direction (SantoriniConstants.py:23-34). */
+#define SAN_S 75
+#define SAN_A 162
+#define SAN_PAN 8
+#define SAN_ATHENA 9
+static int san_wk(const i8* b, int c) { return b[3 * c]; }
+static int san_lv(const i8* b, int c) { return b[3 * c + 1]; }
+static int san_gp(const i8* b, int i) { return b[3 * i + 2]; }
+int azo_sant_get_round(const i8* b) { return san_gp(b, 2); }                                  /* :655-656 */
+int azo_sant_get_score(const i8* b, int player) {                                             /* :87-101 */
+    int best = 0;
+    for (int c = 0; c < 25; c++) { int w = san_wk(b, c); if ((player == 0 ? w > 0 : w < 0) && san_lv(b, c) > best) best = san_lv(b, c); }
+    return best;
+}
+static int san_find(const i8* b, int id) { for (int c = 0; c < 25; c++) if (san_wk(b, c) == id) return c; return -1; }   /* :667-672 */
+/* _able_to_move_worker_to :675-701 (no swap / push without gods) */
+static int san_can_move(const i8* b, int old, int ny, int nx, int no_climb) {
+    if (ny < 0 || ny >= 5 || nx < 0 || nx >= 5) return 0;
+    int nc = 5 * ny + nx;
+    if (san_wk(b, nc) != 0) return 0;
+    if (san_lv(b, nc) > 3) return 0;
+    if (san_lv(b, nc) > san_lv(b, old) + (no_climb ? 0 : 1)) return 0;
+    return 1;
+}
+/* _able_to_build :719-729 */
+static int san_can_build(const i8* b, int y, int x, int ignore) {
+    if (y < 0 || y >= 5 || x < 0 || x >= 5) return 0;
+    int w = san_wk(b, 5 * y + x);
+    if (!(w == 0 || w == ignore)) return 0;
+    return san_lv(b, 5 * y + x) < 4;
+}
+/* valid_moves, NO_GOD branch :135-151 */
+void azo_sant_valid_moves(const i8* b, int player, u8* out) {
+    memset(out, 0, SAN_A);
+    if (san_gp(b, player) <= 0) return;
+    int no_climb = san_gp(b, SAN_ATHENA + (1 - player)) > 64;
+    for (int worker = 0; worker < 2; worker++) {
+        int wid = (worker + 1) * (player == 0 ? 1 : -1), old = san_find(b, wid);
+        if (old < 0) continue;
+        for (int md = 0; md < 9; md++) {
+            if (md == 4) continue;
+            int ny = old / 5 + md / 3 - 1, nx = old % 5 + md % 3 - 1;
+            if (!san_can_move(b, old, ny, nx, no_climb)) continue;
+            for (int bd = 0; bd < 9; bd++) {
+                if (bd == 4) continue;
+                if (!san_can_build(b, ny + bd / 3 - 1, nx + bd % 3 - 1, wid)) continue;
+                out[81 * worker + 9 * md + bd] = 1;
+            }
+        }
+    }
+}
+/* make_move :434-550, power == NO_GOD; returns the next player */
+int azo_sant_make_move(i8* b, int move, int player) {
+    int worker = move / 81, md = (move % 81) / 9, bd = move % 9;
+    int wid = (worker + 1) * (player == 0 ? 1 : -1), old = san_find(b, wid);
+    if (old >= 0) {
+        int old_level = san_lv(b, old);
+        int nc = 5 * (old / 5 + md / 3 - 1) + (old % 5 + md % 3 - 1);
+        b[3 * old] = 0; b[3 * nc] = (i8)wid;
+        if (bd != 4) { int bc = 5 * (nc / 5 + bd / 3 - 1) + (nc % 5 + bd % 3 - 1); b[3 * bc + 1] = (i8)(b[3 * bc + 1] + 1); }
+        int new_level = san_lv(b, nc);
+        if (san_gp(b, SAN_PAN + player) > 0) { if (new_level <= old_level - 2) b[3 * (SAN_PAN + player) + 2] = 65; }
+        else if (san_gp(b, SAN_ATHENA + player) > 0) b[3 * (SAN_ATHENA + player) + 2] = (i8)(64 + (new_level > old_level ? 1 : 0));
+        else { int v = san_gp(b, player); b[3 * player + 2] = (i8)(v < 64 ? v : 64); }
+    }
+    if (san_gp(b, 2) < 127) b[3 * 2 + 2] = (i8)(san_gp(b, 2) + 1);
+    return 1 - player;
+}
+/* check_end_game :552-565 */
+void azo_sant_check_end_game(const i8* b, int next_player, float* out) {
+    out[0] = out[1] = 0.f;
+    if (azo_sant_get_score(b, 0) == 3 || san_gp(b, SAN_PAN) > 64) { out[0] = 1.f; out[1] = -1.f; return; }
+    if (azo_sant_get_score(b, 1) == 3 || san_gp(b, SAN_PAN + 1) > 64) { out[0] = -1.f; out[1] = 1.f; return; }
+    u8 v[SAN_A]; azo_sant_valid_moves(b, next_player, v);
+    int any = 0; for (int a = 0; a < SAN_A; a++) any |= v[a];
+    if (!any) { out[next_player] = -1.f; out[1 - next_player] = 1.f; }
+}
+/* swap_players :567-576 */
+void azo_sant_swap_players(i8* b, int nb_swaps) {
+    if (nb_swaps != 1) return;
+    for (int c = 0; c < 25; c++) b[3 * c] = (i8)(-b[3 * c]);
+    i8 t = b[2]; b[2] = b[5]; b[5] = t;
+}
+/* init_game :103-120, INIT_METHOD = 1 (random worker squares; oracle-own RNG, the reference uses numba's MT19937) */
+void azo_sant_init_game(i8* b, uint64_t seed) {
+    azo_rng r; rng_seed(&r, seed);
+    memset(b, 0, SAN_S);
+    const int ids[4] = {1, -1, 2, -2}; uint32_t used = 0;
+    for (int i = 0; i < 4; i++) {
+        int k = (int)(rng_uniform(&r) * (25 - i)), c = 0;
+        for (int j = 0; j < 25; j++) if (!(used >> j & 1)) { if (k == 0) { c = j; break; } k--; }
+        used |= 1u << c; b[3 * c] = (i8)ids[i];
+    }
+    b[2] = 64; b[5] = 64;
+}
+/* get_symmetries :578-653: identity, rot90 x1..3, flipLR, flipUD, swap own workers, swap opponent workers */
+static const int SAN_ROT[9] = {6, 3, 0, 7, 4, 1, 8, 5, 2}, SAN_FLR[9] = {2, 1, 0, 5, 4, 3, 8, 7, 6}, SAN_FUD[9] = {6, 7, 8, 3, 4, 5, 0, 1, 2};
+int azo_sant_symmetries(const i8* b, const float* pi, const u8* valids, i8* ob, float* opi, u8* ov) {
+    for (int k = 0; k < 8; k++) {
+        i8* o = ob + k * SAN_S; float* op = opi + k * SAN_A; u8* om = ov + k * SAN_A;
+        for (int c = 0; c < 25; c++) {
+            int y = c / 5, x = c % 5, sy = y, sx = x;
+            if (k >= 1 && k <= 3) for (int i = 0; i < k; i++) { int ty = sx, tx = 4 - sy; sy = ty; sx = tx; }      /* np.rot90 */
+            else if (k == 4) sx = 4 - x;
+            else if (k == 5) sy = 4 - y;
+            int sc = 5 * sy + sx, w = b[3 * sc];
+            if (k == 6 && w > 0) w = 3 - w;
+            if (k == 7 && w < 0) w = -3 - w;
+            o[3 * c] = (i8)w; o[3 * c + 1] = b[3 * sc + 1]; o[3 * c + 2] = b[3 * c + 2];
+        }
+        for (int a = 0; a < SAN_A; a++) {
+            int worker = a / 81, md = (a % 81) / 9, bd = a % 9, dst;
+            if (k == 6) dst = (1 - worker) * 81 + md * 9 + bd;
+            else {
+                int m2 = md, b2 = bd;
+                if (k >= 1 && k <= 3) for (int i = 0; i < k; i++) { m2 = SAN_ROT[m2]; b2 = SAN_ROT[b2]; }
+                else if (k == 4) { m2 = SAN_FLR[md]; b2 = SAN_FLR[bd]; }
+                else if (k == 5) { m2 = SAN_FUD[md]; b2 = SAN_FUD[bd]; }
+                dst = worker * 81 + m2 * 9 + b2;
+            }
+            op[dst] = pi[a]; om[dst] = valids[a];
+        }
+    }
+    return 8;
+}
+
 /* ---------------------------------------------------------------- nets ------------------ */
 /* (1) hash-net: see oracle/hashnet.py (test-only deterministic prior/value). */
 static uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
-void azo_hashnet(const i8* b, int S, const u8* valids, int n, float* pi, float* v) {
+void azo_hashnet_a(const i8* b, int S, const u8* valids, int A, int n, float* pi, float* v) {
     uint32_t h = 0x811C9DC5u;
     for (int i = 0; i < S; i++) h = (h ^ (u8)b[i]) * 16777619u;
-    int64_t w[NA], W = 0, ksum = 0, k[NA]; int best = -1; int64_t bw = -1;
-    for (int a = 0; a < NA; a++) {
+    int64_t w[MAXA], W = 0, ksum = 0, k[MAXA]; int best = -1; int64_t bw = -1;
+    for (int a = 0; a < A; a++) {
         w[a] = valids[a] ? 256 + (fmix32(h + (uint32_t)a * 0x9E3779B1u) & 1023) : 0;
         W += w[a]; if (w[a] > bw) { bw = w[a]; best = a; }
     }
-    for (int a = 0; a < NA; a++) { k[a] = (w[a] * 4096) / W; ksum += k[a]; }
+    for (int a = 0; a < A; a++) { k[a] = (w[a] * 4096) / W; ksum += k[a]; }
     k[best] += 4096 - ksum;
-    for (int a = 0; a < NA; a++) pi[a] = (float)k[a] / 4096.0f;
+    for (int a = 0; a < A; a++) pi[a] = (float)k[a] / 4096.0f;
     int j = (int)(fmix32(h ^ 0xABCDEF01u) % 129u) - 64;
     float v0 = (float)j / 64.0f;
     v[0] = v0; for (int p = 1; p < n; p++) v[p] = -v0 / (float)(n - 1);
 }
+void azo_hashnet(const i8* b, int S, const u8* valids, int n, float* pi, float* v) { azo_hashnet_a(b, S, valids, NA, n, pi, v); }
 
 /* (2) SplendorNNet version 80, eval mode (splendor/SplendorNNet.py:149-204,259-280,397-404,440).
  * Weights arrive as one flat float32 blob in the tensor order listed in oracle/oracle.py:V80_ORDER. */
@@ -496,17 +628,18 @@ static const int64_t MAGIC_SEEDS[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};
 typedef struct {
     int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80*/;
     double cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2;
+    int game /*0 splendor, 1 santorini without gods*/;
 } azo_cfg;
 
 typedef struct node {
     i8 key[MAXS];
     int has_es, expanded, r; float Es[MAXP];
-    u8 Vs[NA]; float Ps[NA]; int64_t Ns; double Qsa[NA]; int64_t Nsa[NA]; float Qs;
+    u8 Vs[MAXA]; float Ps[MAXA]; int64_t Ns; double Qsa[MAXA]; int64_t Nsa[MAXA]; float Qs;
     int used;
 } node_t;
 
 typedef struct {
-    azo_cfg cfg; int S; v80_net net; const float* blob;
+    azo_cfg cfg; int S, A; v80_net net; const float* blob;
     node_t* nodes; int* table; int cap, tcap, count;
     int dirichlet_noise, step, last_cleaning; int64_t random_seed;
     azo_rng rng;
@@ -539,7 +672,8 @@ static node_t* insert(azo_mcts* m, const i8* key) {
 
 azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_noise, uint64_t seed) {
     azo_mcts* m = (azo_mcts*)calloc(1, sizeof(azo_mcts));
-    m->cfg = *cfg; m->S = azo_state_rows(cfg->num_players) * COLS; m->blob = blob;
+    m->cfg = *cfg; m->blob = blob;
+    if (cfg->game == 1) { m->S = SAN_S; m->A = SAN_A; } else { m->S = azo_state_rows(cfg->num_players) * COLS; m->A = NA; }
     if (cfg->net_kind == 1) v80_bind(&m->net, blob, azo_state_rows(cfg->num_players), cfg->num_players);
     m->cap = 4096; m->tcap = 16384; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
     m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed);
@@ -579,14 +713,30 @@ static void normalise_f32(float* x, int n) { float inv = 1.0f / sum_f32_avx2(x, 
 /* MCTS.py:255-261 */
 static void softmax_temp(float* P, int n, double T) {
     if (T == 1.0) return;
-    double r[NA], s = 0; for (int i = 0; i < n; i++) { r[i] = pow((double)P[i], 1.0 / T); s += r[i]; }
+    double r[MAXA], s = 0; for (int i = 0; i < n; i++) { r[i] = pow((double)P[i], 1.0 / T); s += r[i]; }
     double inv = 1.0 / s; for (int i = 0; i < n; i++) P[i] = (float)(r[i] * inv);
 }
+/* ---- game dispatch of the Game.py methods the search calls (MCTS.py:125-173) ---- */
+static void g_ended(const azo_mcts* m, const i8* b, int next_player, float* out) {
+    if (m->cfg.game == 1) azo_sant_check_end_game(b, next_player, out); else azo_check_end_game(b, m->cfg.num_players, out);
+}
+static void g_valid(const azo_mcts* m, const i8* b, u8* out) {
+    if (m->cfg.game == 1) azo_sant_valid_moves(b, 0, out); else azo_valid_moves(b, m->cfg.num_players, 0, out);
+}
+static int g_move(const azo_mcts* m, i8* b, int a, int player, int64_t seed, azo_rng* rng) {
+    return m->cfg.game == 1 ? azo_sant_make_move(b, a, player) : azo_make_move(b, m->cfg.num_players, a, player, seed, rng);
+}
+static void g_swap(const azo_mcts* m, i8* b, int nb) {
+    if (m->cfg.game == 1) azo_sant_swap_players(b, nb); else azo_swap_players(b, m->cfg.num_players, nb);
+}
+static int g_round(const azo_mcts* m, const i8* b) { return m->cfg.game == 1 ? azo_sant_get_round(b) : azo_get_round(b); }
+
 /* MCTS.py:187-197; `noise` (length = number of legal actions) is either injected by the caller
  * (parity tests replay the reference's draws) or sampled here. */
 static void apply_dir_noise(azo_mcts* m, float* P, const u8* Vs, const double* noise) {
-    int L = 0; for (int a = 0; a < NA; a++) L += Vs[a] != 0;
-    double tmp[NA];
+    const int A = m->A;
+    int L = 0; for (int a = 0; a < A; a++) L += Vs[a] != 0;
+    double tmp[MAXA];
     if (!noise) {
         double alpha = m->cfg.dirichletAlpha > 0 ? m->cfg.dirichletAlpha : 10.0 / L, s = 0;
         for (int i = 0; i < L; i++) { tmp[i] = rng_gamma(&m->rng, alpha); s += tmp[i]; }
@@ -594,15 +744,15 @@ static void apply_dir_noise(azo_mcts* m, float* P, const u8* Vs, const double* n
         noise = tmp;
     }
     int k = 0;
-    for (int a = 0; a < NA; a++) if (Vs[a]) { float t1 = 0.75f * P[a]; P[a] = (float)((double)t1 + 0.25 * noise[k]); k++; }
+    for (int a = 0; a < A; a++) if (Vs[a]) { float t1 = 0.75f * P[a]; P[a] = (float)((double)t1 + 0.25 * noise[k]); k++; }
 }
 
 /* MCTS.py:210-230 */
-static int pick_highest_ucb(const node_t* nd, double cpuct, int forced, int64_t n_iter, double fpu) {
+static int pick_highest_ucb(const node_t* nd, int A, double cpuct, int forced, int64_t n_iter, double fpu) {
     double best = -INFINITY; int best_a = -1;
     double fpu_init = fpu > 0 ? (double)nd->Qs - fpu : fpu;
     double c0 = cpuct * sqrt((double)nd->Ns + 1e-8), c1 = cpuct * sqrt((double)nd->Ns), kn = (double)n_iter * 0.5;
-    for (int a = 0; a < NA; a++) {
+    for (int a = 0; a < A; a++) {
         if (!nd->Vs[a]) continue;
         if (forced && nd->Nsa[a] < (int64_t)sqrt(kn * (double)nd->Ps[a])) return a;
         double u;
@@ -615,7 +765,7 @@ static int pick_highest_ucb(const node_t* nd, double cpuct, int forced, int64_t 
 
 /* MCTS.py:105-184 (search), unrolled from recursion into select / leaf / backup. */
 static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const double* noise) {
-    int n = m->cfg.num_players, S = m->S, depth = 0;
+    int n = m->cfg.num_players, S = m->S, depth = 0; const int A = m->A;
     static __thread int path_node[256], path_a[256], path_np[256];   /* node INDICES: insert() may realloc m->nodes */
     i8 cur[MAXS]; memcpy(cur, root, (size_t)S);
     float v[MAXP];
@@ -624,9 +774,9 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
     for (;;) {
         node_t* nd = lookup(m, cur);
         if (!nd || !nd->has_es) {
-            float Es[MAXP]; azo_check_end_game(cur, n, Es);
+            float Es[MAXP]; g_ended(m, cur, 0, Es);                       /* MCTS.py:131 getGameEnded(canonicalBoard, 0) */
             int any = 0; for (int p = 0; p < n; p++) any |= Es[p] != 0.f;
-            if (!nd) { nd = insert(m, cur); nd->r = azo_get_round(cur); }
+            if (!nd) { nd = insert(m, cur); nd->r = g_round(m, cur); }
             nd->has_es = 1; memcpy(nd->Es, Es, sizeof(float) * (size_t)n);
             if (any) { memcpy(v, Es, sizeof(float) * (size_t)n); break; }
         } else {
@@ -634,20 +784,20 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
             if (any) { memcpy(v, nd->Es, sizeof(float) * (size_t)n); break; }
         }
         if (!nd->expanded) {
-            azo_valid_moves(cur, n, 0, nd->Vs);
-            if (m->cfg.net_kind == 0) azo_hashnet(cur, S, nd->Vs, n, nd->Ps, v); else v80_forward(&m->net, cur, nd->Vs, nd->Ps, v);
+            g_valid(m, cur, nd->Vs);
+            if (m->cfg.net_kind == 0) azo_hashnet_a(cur, S, nd->Vs, A, n, nd->Ps, v); else v80_forward(&m->net, cur, nd->Vs, nd->Ps, v);
             m->n_nn_evals++; m->n_expansions++;
-            if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, NA, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); }
-            normalise_f32(nd->Ps, NA);
-            nd->Ns = 0; for (int a = 0; a < NA; a++) { nd->Qsa[a] = NAN_Q; nd->Nsa[a] = 0; }
+            if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, A, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); }
+            normalise_f32(nd->Ps, A);
+            nd->Ns = 0; for (int a = 0; a < A; a++) { nd->Qsa[a] = NAN_Q; nd->Nsa[a] = 0; }
             nd->Qs = v[0]; nd->expanded = 1;
             break;
         }
-        if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, NA, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); normalise_f32(nd->Ps, NA); }
-        int a = pick_highest_ucb(nd, m->cfg.cpuct, depth == 0 && forced, m->step, m->cfg.fpu);
+        if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, A, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); normalise_f32(nd->Ps, A); }
+        int a = pick_highest_ucb(nd, m->A, m->cfg.cpuct, depth == 0 && forced, m->step, m->cfg.fpu);
         m->n_node_visits++;
-        int np_ = azo_make_move(cur, n, a, 0, m->random_seed, &dummy);     /* MCTS.py:233-248 */
-        if (np_ != 0) azo_swap_players(cur, n, np_);
+        int np_ = g_move(m, cur, a, 0, m->random_seed, &dummy);           /* MCTS.py:233-248 */
+        if (np_ != 0) g_swap(m, cur, np_);
         path_node[depth] = (int)(nd - m->nodes); path_a[depth] = a; path_np[depth] = np_; depth++;
     }
     for (int d = depth - 1; d >= 0; d--) {
@@ -664,7 +814,7 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
  * raw_counts i64[A] (root Nsa before policy-target pruning). Returns is_full_search. */
 int azo_mcts_get_action_prob(azo_mcts* m, const i8* cb, double temp, int force_full, const double* noise,
                              double* probs, float* q, int64_t* raw_counts) {
-    const azo_cfg* c = &m->cfg; int n = c->num_players;
+    const azo_cfg* c = &m->cfg; int n = c->num_players; const int A = m->A;
     int full = force_full || (rng_uniform(&m->rng) < c->prob_fullMCTS);
     int nsims = full ? c->numMCTSSims : c->numMCTSSims / c->ratio_fullMCTS;
     int forced = full && c->forced_playouts;
@@ -674,19 +824,19 @@ int azo_mcts_get_action_prob(azo_mcts* m, const i8* cb, double temp, int force_f
     }
     if (nsims > 0) m->step = nsims - 1;
     node_t* root = lookup(m, cb);
-    double counts[NA];
-    for (int a = 0; a < NA; a++) { counts[a] = (double)root->Nsa[a]; if (raw_counts) raw_counts[a] = root->Nsa[a]; }
+    double counts[MAXA];
+    for (int a = 0; a < A; a++) { counts[a] = (double)root->Nsa[a]; if (raw_counts) raw_counts[a] = root->Nsa[a]; }
     q[0] = root->Qs; for (int p = 1; p < n; p++) q[p] = -root->Qs / (float)(n - 1);
     if (forced) {
-        double best = 0; for (int a = 0; a < NA; a++) if (counts[a] > best) best = counts[a];
-        for (int a = 0; a < NA; a++) {
+        double best = 0; for (int a = 0; a < A; a++) if (counts[a] > best) best = counts[a];
+        for (int a = 0; a < A; a++) {
             double cnt = counts[a];
             if (cnt != best) { float t = 0.5f * root->Ps[a]; t = t * (float)nsims; cnt = cnt - (double)(int64_t)sqrt((double)t); }
             counts[a] = cnt > 1 ? cnt : 0;
         }
     }
     if (!c->no_mem_optim) {                                                /* MCTS.py:86-91 */
-        int r = azo_get_round(cb);
+        int r = g_round(m, cb);
         if (r > m->last_cleaning + 20) {
             int w = 0;
             for (int i = 0; i < m->count; i++) if (!(m->nodes[i].r < r - 5)) { if (w != i) m->nodes[w] = m->nodes[i]; w++; }
@@ -694,13 +844,13 @@ int azo_mcts_get_action_prob(azo_mcts* m, const i8* cb, double temp, int force_f
         }
     }
     if (temp <= 0.02) {
-        double best = -1; int nb = 0; for (int a = 0; a < NA; a++) { if (counts[a] > best) { best = counts[a]; nb = 1; } else if (counts[a] == best) nb++; }
+        double best = -1; int nb = 0; for (int a = 0; a < A; a++) { if (counts[a] > best) { best = counts[a]; nb = 1; } else if (counts[a] == best) nb++; }
         int pick = (int)(rng_uniform(&m->rng) * nb), k = 0; if (pick >= nb) pick = nb - 1;
-        for (int a = 0; a < NA; a++) { probs[a] = 0; if (counts[a] == best) { if (k == pick) probs[a] = 1; k++; } }
+        for (int a = 0; a < A; a++) { probs[a] = 0; if (counts[a] == best) { if (k == pick) probs[a] = 1; k++; } }
         return full;
     }
-    double s = 0; for (int a = 0; a < NA; a++) { counts[a] = pow(counts[a], 1.0 / temp); s += counts[a]; }
-    for (int a = 0; a < NA; a++) probs[a] = counts[a] / s;
+    double s = 0; for (int a = 0; a < A; a++) { counts[a] = pow(counts[a], 1.0 / temp); s += counts[a]; }
+    for (int a = 0; a < A; a++) probs[a] = counts[a] / s;
     return full;
 }
 
@@ -715,28 +865,29 @@ static double temp_for_selfplay(double t_begin, double t_end, double half_life, 
 /* One self-play game. Example boards/policies are only counted (the CPU baseline measures search
  * throughput); `max_plies` > 0 truncates the game (bounded sample for bench.py). */
 static void execute_episode(azo_mcts* m, uint64_t seed, double t0, double t1, double half, int max_plies, azo_run_stats* st) {
-    int n = m->cfg.num_players, S = m->S; azo_rng rng; rng_seed(&rng, seed ^ 0xA5A5A5A5ULL);
-    i8 board[MAXS], cb[MAXS]; azo_init_game(board, n, seed);
+    int n = m->cfg.num_players, S = m->S; const int A = m->A; azo_rng rng; rng_seed(&rng, seed ^ 0xA5A5A5A5ULL);
+    i8 board[MAXS], cb[MAXS];
+    if (m->cfg.game == 1) azo_sant_init_game(board, seed); else azo_init_game(board, n, seed);
     int player = 0, step = 0; azo_mcts_reset(m);
-    double probs[NA]; float q[MAXP], r[MAXP];
+    double probs[MAXA]; float q[MAXP], r[MAXP];
     for (;;) {
         step++;
-        memcpy(cb, board, (size_t)S); if (player) azo_swap_players(cb, n, player);
+        memcpy(cb, board, (size_t)S); if (player) g_swap(m, cb, player);
         int64_t before = m->n_sims;
         int full = azo_mcts_get_action_prob(m, cb, 1.0, 0, NULL, probs, q, NULL);
         (void)before;
-        double T = temp_for_selfplay(t0, t1, half, step), w[NA], s = 0;
-        int action = 80;
-        if (T == 0) { double b = -1; for (int a = 0; a < NA; a++) if (probs[a] > b) { b = probs[a]; action = a; } }
+        double T = temp_for_selfplay(t0, t1, half, step), w[MAXA], s = 0;
+        int action = -1;
+        if (T == 0) { double b = -1; for (int a = 0; a < A; a++) if (probs[a] > b) { b = probs[a]; action = a; } }
         else {
-            for (int a = 0; a < NA; a++) { w[a] = pow(probs[a], 1.0 / T); s += w[a]; }
+            for (int a = 0; a < A; a++) { w[a] = pow(probs[a], 1.0 / T); s += w[a]; }
             double u = rng_uniform(&rng) * s, acc = 0;
-            for (int a = 0; a < NA; a++) { acc += w[a]; if (w[a] > 0 && acc > u) { action = a; break; } }
+            for (int a = 0; a < A; a++) { if (w[a] > 0) { action = a; acc += w[a]; if (acc > u) break; } }
         }
-        if (full) { u8 V[NA]; azo_valid_moves(cb, n, 0, V); st->examples += 1; }
-        player = azo_make_move(board, n, action, player, 0, &rng);
+        if (full) { u8 V[MAXA]; g_valid(m, cb, V); st->examples += 1; }
+        player = g_move(m, board, action, player, 0, &rng);
         st->plies++;
-        azo_check_end_game(board, n, r);
+        g_ended(m, board, player, r);                             /* Coach.py:73 getGameEnded(board, curPlayer) */
         int any = 0; for (int p = 0; p < n; p++) any |= r[p] != 0.f;
         if (any || (max_plies > 0 && step >= max_plies)) break;
     }

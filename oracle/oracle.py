@@ -47,7 +47,7 @@ class Cfg(C.Structure):
     _fields_ = [('num_players', C.c_int), ('numMCTSSims', C.c_int), ('ratio_fullMCTS', C.c_int), ('universes', C.c_int),
                 ('forced_playouts', C.c_int), ('no_mem_optim', C.c_int), ('net_kind', C.c_int),
                 ('cpuct', C.c_double), ('fpu', C.c_double), ('dirichletAlpha', C.c_double), ('prob_fullMCTS', C.c_double),
-                ('temperature2', C.c_double)]
+                ('temperature2', C.c_double), ('game', C.c_int)]
 
 
 def lib():
@@ -64,6 +64,15 @@ def lib():
         L.azo_swap_players.argtypes = [p8, C.c_int, C.c_int]
         L.azo_symmetries.argtypes = [p8, C.c_int, pf, pu8, p8, pf, pu8]; L.azo_symmetries.restype = C.c_int
         L.azo_hashnet.argtypes = [p8, C.c_int, pu8, C.c_int, pf, pf]
+        L.azo_hashnet_a.argtypes = [p8, C.c_int, pu8, C.c_int, C.c_int, pf, pf]
+        L.azo_sant_get_round.argtypes = [p8]; L.azo_sant_get_round.restype = C.c_int
+        L.azo_sant_get_score.argtypes = [p8, C.c_int]; L.azo_sant_get_score.restype = C.c_int
+        L.azo_sant_valid_moves.argtypes = [p8, C.c_int, pu8]
+        L.azo_sant_make_move.argtypes = [p8, C.c_int, C.c_int]; L.azo_sant_make_move.restype = C.c_int
+        L.azo_sant_check_end_game.argtypes = [p8, C.c_int, pf]
+        L.azo_sant_swap_players.argtypes = [p8, C.c_int]
+        L.azo_sant_init_game.argtypes = [p8, C.c_uint64]
+        L.azo_sant_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_sant_symmetries.restype = C.c_int
         L.azo_v80_forward.argtypes = [pf, C.c_int, C.c_int, p8, pu8, pf, pf]
         L.azo_mcts_new.argtypes = [C.POINTER(Cfg), pf, C.c_int, C.c_uint64]; L.azo_mcts_new.restype = C.c_void_p
         L.azo_mcts_free.argtypes = [C.c_void_p]
@@ -134,8 +143,8 @@ def symmetries(board, pi, valids, n=2):
 
 def hashnet(board, valids, n=2):
     b = _board(board); v = np.ascontiguousarray(valids).astype(np.uint8)
-    pi = np.zeros(NA, np.float32); val = np.zeros(n, np.float32)
-    lib().azo_hashnet(_p(b, C.c_int8), b.size, _p(v, C.c_uint8), n, _p(pi, C.c_float), _p(val, C.c_float))
+    pi = np.zeros(v.size, np.float32); val = np.zeros(n, np.float32)
+    lib().azo_hashnet_a(_p(b, C.c_int8), b.size, _p(v, C.c_uint8), v.size, n, _p(pi, C.c_float), _p(val, C.c_float))
     return pi, val
 
 
@@ -148,10 +157,14 @@ def v80_forward(blob, boards, valids, n=2):
     return pi, val
 
 
+GAME_SPLENDOR, GAME_SANTORINI = 0, 1
+GAME_ACTIONS = {GAME_SPLENDOR: 81, GAME_SANTORINI: 162}
+
+
 def make_cfg(num_players=2, numMCTSSims=800, ratio_fullMCTS=5, universes=1, forced_playouts=False, no_mem_optim=False,
-             net_kind=0, cpuct=1.25, fpu=0.0, dirichletAlpha=-1.0, prob_fullMCTS=1.0, temperature2=1.1):
+             net_kind=0, cpuct=1.25, fpu=0.0, dirichletAlpha=-1.0, prob_fullMCTS=1.0, temperature2=1.1, game=GAME_SPLENDOR):
     return Cfg(num_players, numMCTSSims, ratio_fullMCTS, universes, int(forced_playouts), int(no_mem_optim), net_kind,
-               cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2)
+               cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2, game)
 
 
 class MCTS:
@@ -174,7 +187,8 @@ class MCTS:
         out = np.zeros(7, np.int64); lib().azo_mcts_stats(self.h, _p(out, C.c_int64)); return out
 
     def getActionProb(self, cb, temp=1.0, force_full_search=False, noise=None):
-        b = _board(cb); probs = np.zeros(NA, np.float64); q = np.zeros(self.cfg.num_players, np.float32); raw = np.zeros(NA, np.int64)
+        A = GAME_ACTIONS[self.cfg.game]
+        b = _board(cb); probs = np.zeros(A, np.float64); q = np.zeros(self.cfg.num_players, np.float32); raw = np.zeros(A, np.int64)
         nz = None
         if noise is not None and len(noise):
             nz = np.ascontiguousarray(noise, np.float64)
@@ -190,3 +204,50 @@ def selfplay_bench(cfg, blob, threads, games_per_thread, max_plies=0, temperatur
                              float(temperature[0]), float(temperature[1]), float(tempThreshold), seed, _p(out, C.c_double))
     keys = ('sims', 'expansions', 'node_visits', 'nn_evals', 'plies', 'examples', 'games', 'seconds')
     return dict(zip(keys, out.tolist()))
+
+
+# ---- Santorini without gods (santorini/SantoriniLogicNumba.py with NB_GODS = 1) ----
+SAN_A = 162
+
+
+def sant_init_game(seed):
+    b = np.zeros((5, 5, 3), np.int8); lib().azo_sant_init_game(_p(b, C.c_int8), seed); return b
+
+
+def sant_valid_moves(board, player=0):
+    b = _board(board); out = np.zeros(SAN_A, np.uint8)
+    lib().azo_sant_valid_moves(_p(b, C.c_int8), int(player), _p(out, C.c_uint8))
+    return out.astype(np.bool_)
+
+
+def sant_next_state(board, player, action):
+    b = _board(board)
+    return b, lib().azo_sant_make_move(_p(b, C.c_int8), int(action), int(player))
+
+
+def sant_game_ended(board, next_player):
+    b = _board(board); out = np.zeros(2, np.float32)
+    lib().azo_sant_check_end_game(_p(b, C.c_int8), int(next_player), _p(out, C.c_float))
+    return out
+
+
+def sant_canonical(board, player):
+    b = _board(board)
+    if player:
+        lib().azo_sant_swap_players(_p(b, C.c_int8), int(player))
+    return b
+
+
+def sant_get_round(board):
+    b = _board(board); return lib().azo_sant_get_round(_p(b, C.c_int8))
+
+
+def sant_get_score(board, player):
+    b = _board(board); return lib().azo_sant_get_score(_p(b, C.c_int8), int(player))
+
+
+def sant_symmetries(board, pi, valids):
+    b = _board(board); pi = np.ascontiguousarray(pi, np.float32); v = np.ascontiguousarray(valids).astype(np.uint8)
+    ob = np.zeros((8, 5, 5, 3), np.int8); op = np.zeros((8, SAN_A), np.float32); ov = np.zeros((8, SAN_A), np.uint8)
+    k = lib().azo_sant_symmetries(_p(b, C.c_int8), _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
+    return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]

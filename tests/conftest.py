@@ -53,3 +53,21 @@ MCTS_CONFIGS = {
     'universes8': dict(cpuct=2.0, fpu=0.0, universes=8, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.0],
                        forced_playouts=True, noise=False),
 }
+
+
+@pytest.fixture(scope='session')
+def san_kat():
+    return np.load(os.path.join(GOLDEN, 'santorini_kat.npz'))
+
+
+@pytest.fixture(scope='session')
+def san_mcts_cases():
+    z = np.load(os.path.join(GOLDEN, 'santorini_mcts.npz'))
+    n = int(z['n_cases'])
+    keys = ('cfg', 'root', 'n_sims', 'probs', 'q', 'raw_counts', 'root_P', 'root_Qsa', 'noise', 'summary')
+    return [{k: z[f'c{i}_{k}'] for k in keys} for i in range(n)]
+
+
+@pytest.fixture(scope='session')
+def san_episode():
+    return np.load(os.path.join(GOLDEN, 'santorini_episode.npz'))

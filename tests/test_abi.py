@@ -19,7 +19,7 @@ def test_header_symbols_all_exported():
     assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.azg_abi_version() == 1
+    assert L.azg_abi_version() == lib.AZG_ABI_VERSION
 
 
 def test_game_info_matches_reference_sizes():
@@ -27,6 +27,9 @@ def test_game_info_matches_reference_sizes():
     # splendor/SplendorLogicNumba.py:90-96: observation_size(2) = (56, 7), action_size() = 81
     assert (gi.state_rows, gi.state_cols, gi.state_bytes, gi.action_size) == (56, 7, 392, 81)
     assert gi.max_symmetries == 14 and gi.max_game_len == 124
+    gs = lib.game_info(lib.AZG_GAME_SANTORINI, 2)
+    # santorini/SantoriniLogicNumba.py:13-19 with NB_GODS = 1: observation_size() = (5, 5, 3), action_size() = 162
+    assert (gs.state_rows, gs.state_cols, gs.state_depth, gs.state_bytes, gs.action_size, gs.max_symmetries) == (5, 5, 3, 75, 162, 8)
     with pytest.raises(lib.AzgError):
         lib.game_info(99, 2)
     with pytest.raises(lib.AzgError):
