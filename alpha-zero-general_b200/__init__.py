@@ -2,7 +2,7 @@
 
 Host-side mirror of the reference's interfaces for the self-play hot path:
   game.SplendorGame   <->  splendor/SplendorGame.py (Game.py)
-  nnet.NNetWrapper    <->  splendor/NNet.py / GenericNNetWrapper.py (predict half)
+  nnet.NNetWrapper    <->  splendor/NNet.py / GenericNNetWrapper.py (predict half); nnet.SantoriniNNetWrapper <-> santorini/NNet.py
   mcts.MCTS           <->  MCTS.py
   coach.Coach         <->  Coach.py (executeEpisode / executeEpisodes)
 All compute goes through the C ABI in include/azg.h (csrc/libazg_b200.so, hand-written sm_100a CUDA).
@@ -10,9 +10,9 @@ There is no CPU fallback: importing works anywhere, computing needs the built li
 """
 from . import lib  # noqa: F401
 from .game import SplendorGame, SantoriniGame, CudaGame  # noqa: F401
-from .nnet import NNetWrapper, V80_TENSOR_ORDER  # noqa: F401
+from .nnet import NNetWrapper, SantoriniNNetWrapper, V80_TENSOR_ORDER, V89_TENSOR_ORDER  # noqa: F401
 from .mcts import MCTS  # noqa: F401
 from .coach import Coach  # noqa: F401
 from .utils import dotdict  # noqa: F401
 
-__all__ = ['lib', 'SplendorGame', 'SantoriniGame', 'CudaGame', 'NNetWrapper', 'MCTS', 'Coach', 'dotdict', 'V80_TENSOR_ORDER']
+__all__ = ['lib', 'SplendorGame', 'SantoriniGame', 'CudaGame', 'NNetWrapper', 'SantoriniNNetWrapper', 'MCTS', 'Coach', 'dotdict', 'V80_TENSOR_ORDER', 'V89_TENSOR_ORDER']

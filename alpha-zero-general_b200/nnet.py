@@ -72,6 +72,61 @@ def random_v80_state_dict(seed=0, num_players=2):
     return sd
 
 
+def _bn(prefix):
+    return [f'{prefix}.weight', f'{prefix}.bias', f'{prefix}.running_mean', f'{prefix}.running_var']
+
+
+def _v89_order():
+    names = ['first_layer.0.weight'] + _bn('first_layer.1')
+    for b in range(5):
+        names += [f'trunk.{b}.conv1.weight'] + _bn(f'trunk.{b}.bn1') + [f'trunk.{b}.conv2.weight'] + _bn(f'trunk.{b}.bn2')
+    names += ['head_PI.conv1x1.weight'] + _bn('head_PI.bn') + ['head_PI.fc.weight', 'head_PI.fc.bias']
+    names += ['head_V.conv1x1.weight'] + _bn('head_V.bn') + ['head_V.fc1.weight', 'head_V.fc1.bias', 'head_V.fc2.weight', 'head_V.fc2.bias']
+    return names
+
+
+# Order in which azg_net_create expects the SantoriniNNet V89 state_dict tensors (santorini/SantoriniNNet.py:194-217).
+V89_TENSOR_ORDER = _v89_order()
+
+
+def v89_blob(state_dict):
+    parts = []
+    for n in V89_TENSOR_ORDER:
+        t = state_dict[n]
+        if hasattr(t, 'detach'):
+            t = t.detach().cpu().numpy()
+        parts.append(np.asarray(t, dtype=np.float32).ravel())
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+def random_v89_state_dict(seed=0):
+    """Random-init V89 weights drawn from numpy with the reference's initialisers: PyTorch-default convolutions
+    (kaiming_uniform_(a=sqrt(5)) => U(+-1/sqrt(fan_in))), kaiming_uniform_ Linear weights with zero biases
+    (SantoriniNNet.py:222-232), default BatchNorm. Used by bench.py and smoke()."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv(name, out, cin, k):
+        b = 1.0 / np.sqrt(cin * k * k)
+        sd[name] = rng.uniform(-b, b, size=(out, cin, k, k)).astype(np.float32)
+
+    def bn(prefix, ch):
+        sd[f'{prefix}.weight'] = np.ones(ch, np.float32); sd[f'{prefix}.bias'] = np.zeros(ch, np.float32)
+        sd[f'{prefix}.running_mean'] = np.zeros(ch, np.float32); sd[f'{prefix}.running_var'] = np.ones(ch, np.float32)
+
+    def lin(name, out, inn):
+        b = np.sqrt(6.0 / inn)
+        sd[f'{name}.weight'] = rng.uniform(-b, b, size=(out, inn)).astype(np.float32); sd[f'{name}.bias'] = np.zeros(out, np.float32)
+
+    conv('first_layer.0.weight', 64, 2, 3); bn('first_layer.1', 64)
+    for blk in range(5):
+        conv(f'trunk.{blk}.conv1.weight', 64, 64, 3); bn(f'trunk.{blk}.bn1', 64)
+        conv(f'trunk.{blk}.conv2.weight', 64, 64, 3); bn(f'trunk.{blk}.bn2', 64)
+    conv('head_PI.conv1x1.weight', 2, 64, 1); bn('head_PI.bn', 2); lin('head_PI.fc', 162, 50)
+    conv('head_V.conv1x1.weight', 1, 64, 1); bn('head_V.bn', 1); lin('head_V.fc1', 64, 25); lin('head_V.fc2', 2, 64)
+    return sd
+
+
 class CudaNet:
     """Owns an azg_net handle."""
 
@@ -144,6 +199,25 @@ class NNetWrapper:
 
     def train(self, examples):
         raise NotImplementedError('training is outside the self-play hot path (SURVEY.md section 8f-1)')
+
+
+class SantoriniNNetWrapper(NNetWrapper):
+    """santorini/NNet.py:NNetWrapper (inference surface) for the no-god game. nn_args['nn_version'] must be 89."""
+
+    def __init__(self, game, nn_args=None, state_dict=None, seed=0):
+        nn_args = dict(nn_args or {'nn_version': 89})
+        if nn_args.get('nn_version', 89) != 89:
+            raise NotImplementedError('only SantoriniNNet version 89 is built (the shipped no-god checkpoint)')
+        self.args = nn_args
+        self.game = game
+        self.board_size = game.getBoardSize(); self.action_size = game.getActionSize(); self.num_players = game.num_players
+        self.requestKnowledgeTransfer = False
+        self.state_dict = state_dict if state_dict is not None else random_v89_state_dict(seed)
+        self.net = CudaNet(_lib.AZG_NET_SANTORINI_V89, game, v89_blob(self.state_dict))
+
+    def load_state_dict(self, state_dict):
+        self.state_dict = state_dict
+        self.net.load(v89_blob(state_dict))
 
 
 class HashNetWrapper:

@@ -37,8 +37,15 @@ if ROOT not in sys.path:
 
 METRIC = 'selfplay_mcts_sims_per_sec'
 UNIT = 'sims/s'
-V80_FLOPS = 2 * 521205            # multiply-adds of one V80 leaf evaluation (1.04 MFLOP)
-S_BYTES, N_ACT, N_PL = 392, 81, 2
+N_PL = 2
+# per-game workload constants: board bytes, actions, multiply-adds of one leaf evaluation (SURVEY.md section 8a row a17:
+# V80 1.04 MFLOP, V89 18.52 MFLOP), default concurrent games (BASELINE.json configs[2] / configs[1]), universes
+GAMES = {
+    'splendor': dict(S=392, A=81, flops=2 * 521205, games=16384, universes=3, net='SplendorNNet V80 (142406 params, random init seed 0)',
+                     tag='splendor2p_chance_universes3'),
+    'santorini': dict(S=75, A=162, flops=2 * 9259428, games=4096, universes=1, net='SantoriniNNet V89 (381454 params, random init seed 0)',
+                      tag='santorini_nogods'),
+}
 
 
 def parse():
@@ -47,18 +54,22 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--games', type=int, default=16384, help='concurrent games per GPU')
+    ap.add_argument('--game', default='splendor', choices=sorted(GAMES), help='splendor = BASELINE.json configs[2] (headline metric), santorini = configs[1]')
+    ap.add_argument('--games', type=int, default=0, help='concurrent games per GPU (0 = the config default: 16384 splendor / 4096 santorini)')
     ap.add_argument('--sims', type=int, default=800)
     ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 6 x sims + 320)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--cpu-plies', type=int, default=12, help='plies per thread of the cpu_baseline sample')
-    return ap.parse_args()
+    ap.add_argument('--cpu-plies', type=int, default=0, help='plies per thread of the cpu_baseline sample (0 = 12 splendor / 1 santorini: ~10-30 s)')
+    a = ap.parse_args()
+    a.games = a.games or GAMES[a.game]['games']
+    a.cpu_plies = a.cpu_plies or (12 if a.game == 'splendor' else 1)
+    return a
 
 
-def mcts_args(sims):
-    # main.py defaults + config C3: universes=3, every move a full search
-    return dict(numMCTSSims=sims, cpuct=1.25, fpu=0.0, universes=3, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1],
+def mcts_args(sims, game='splendor'):
+    # main.py defaults; config C3 (splendor): universes=3; every move a full search
+    return dict(numMCTSSims=sims, cpuct=1.25, fpu=0.0, universes=GAMES[game]['universes'], dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1],
                 tempThreshold=10, prob_fullMCTS=1.0, ratio_fullMCTS=5, forced_playouts=False, no_mem_optim=False)
 
 
@@ -110,15 +121,15 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- reference (CPU) arm -------
-def cpu_sample(sims, plies, threads, seed=1):
-    """Oracle port of Coach.executeEpisode / MCTS.search / Splendor Board / V80 forward on `threads` host threads,
+def cpu_sample(sims, plies, threads, seed=1, game='splendor'):
+    """Oracle port of Coach.executeEpisode / MCTS.search / the game's Board / the net forward on `threads` host threads,
     each playing one self-play game truncated after `plies` plies. Returns the oracle's counters."""
     from oracle import oracle as O
-    from azg_b200.nnet import random_v80_state_dict
-    a = mcts_args(sims)
-    cfg = O.make_cfg(numMCTSSims=sims, net_kind=1, universes=a['universes'], prob_fullMCTS=1.0, cpuct=a['cpuct'], fpu=a['fpu'],
-                     dirichletAlpha=a['dirichletAlpha'], temperature2=a['temperature'][2])
-    blob = O.v80_blob(random_v80_state_dict(0))
+    from azg_b200.nnet import random_v80_state_dict, random_v89_state_dict
+    a = mcts_args(sims, game)
+    cfg = O.make_cfg(numMCTSSims=sims, net_kind=1 if game == 'splendor' else 2, universes=a['universes'], prob_fullMCTS=1.0, cpuct=a['cpuct'], fpu=a['fpu'],
+                     dirichletAlpha=a['dirichletAlpha'], temperature2=a['temperature'][2], game=O.GAME_SPLENDOR if game == 'splendor' else O.GAME_SANTORINI)
+    blob = O.v80_blob(random_v80_state_dict(0)) if game == 'splendor' else O.v89_blob(random_v89_state_dict(0))
     return O.selfplay_bench(cfg, blob, threads, 1, max_plies=plies, temperature=a['temperature'][:2], tempThreshold=a['tempThreshold'], seed=seed)
 
 
@@ -128,26 +139,27 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     plies = 2                                               # one step = every host thread plays 2 plies (2 x sims sims)
     for _ in range(min(args.warmup, 1)):
-        cpu_sample(args.sims, 1, threads)
+        cpu_sample(args.sims, 1, threads, game=args.game)
     t0 = time.perf_counter(); sims = 0
     for k in range(args.steps):
-        r = cpu_sample(args.sims, plies, threads, seed=100 + k); sims += r['sims']
+        r = cpu_sample(args.sims, plies, threads, seed=100 + k, game=args.game); sims += r['sims']
     dt = time.perf_counter() - t0
     val = sims / dt
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32/f64',
             'data': 'synthetic', 'config': workload_cfg(args, threads),
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                             'sample': f'{threads} host threads x 1 Splendor self-play game x {plies} plies x {args.sims} sims per step, {args.steps} steps; '
+                             'sample': f'{threads} host threads x 1 {args.game} self-play game x {plies} plies x {args.sims} sims per step, {args.steps} steps; '
                                        'oracle/azg_oracle.c (C port of the reference path; the Python/numba reference cannot travel to the GPU box)'},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
 def workload_cfg(args, cpu_threads=None):
-    c = {'workload': f'splendor2p_chance_universes3_{args.games}games_per_gpu_{args.sims}sims_V80_randinit', 'game': 'splendor', 'num_players': 2,
-         'games_per_gpu': args.games, 'numMCTSSims': args.sims, 'net': 'SplendorNNet V80 (142406 params, random init seed 0)',
-         'universes': 3, 'prob_fullMCTS': 1.0, 'dirichlet_noise': True, 'step': 'one self-play ply of every game (numMCTSSims lock-step simulations per tree)',
+    gm = GAMES[args.game]
+    c = {'workload': f'{gm["tag"]}_{args.games}games_per_gpu_{args.sims}sims_randinit', 'game': args.game, 'num_players': 2,
+         'games_per_gpu': args.games, 'numMCTSSims': args.sims, 'net': gm['net'],
+         'universes': gm['universes'], 'prob_fullMCTS': 1.0, 'dirichlet_noise': True, 'step': 'one self-play ply of every game (numMCTSSims lock-step simulations per tree)',
          'parallelism': f'games sharded over {args.gpus} GPU(s), no data-path collective', 'l2': 'working set >> L2 (tree arenas of tens of GB); no flush needed'}
     if cpu_threads:
         c['cpu_threads'] = cpu_threads
@@ -161,6 +173,8 @@ class HostLoop:
     def __init__(self, torch, game, eng, n, seed):
         import azg_b200.lib as lib
         self.lib = lib; self.L = lib.load(); self.game = game; self.eng = eng; self.n = n
+        S_BYTES, N_ACT = game.info.state_bytes, game.info.action_size
+        self.N_ACT = N_ACT
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
         self.board = pin((n, S_BYTES), torch.int8); self.board2 = pin((n, S_BYTES), torch.int8); self.roots = pin((n, S_BYTES), torch.int8)
         self.player = pin((n,), torch.int32); self.player2 = pin((n,), torch.int32); self.action = pin((n,), torch.int32)
@@ -174,7 +188,7 @@ class HostLoop:
 
     def step(self):
         lib, L, g, n = self.lib, self.L, self.game, self.n
-        p = lib.ptr
+        p = lib.ptr; N_ACT = self.N_ACT
         # MCTS.getActionProb for every game (host roots in, host counts out)
         lib.check(L.azg_engine_search(self.eng.h, n, p(self.roots), None, None, p(self.counts), p(self.raw), p(self.q), None))
         self.h2d += self.roots.nbytes; self.d2h += self.counts.nbytes + self.raw.nbytes + self.q.nbytes
@@ -237,9 +251,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    game = azg_b200.SplendorGame()
-    net = azg_b200.NNetWrapper(game, {'nn_version': 80}, seed=0)             # identical weights on every rank
-    a = mcts_args(args.sims)
+    gm = GAMES[args.game]
+    if args.game == 'splendor':
+        game = azg_b200.SplendorGame(); net = azg_b200.NNetWrapper(game, {'nn_version': 80}, seed=0)      # identical weights on every rank
+    else:
+        game = azg_b200.SantoriniGame(); net = azg_b200.SantoriniNNetWrapper(game, {'nn_version': 89}, seed=0)
+    S_BYTES, N_ACT = gm['S'], gm['A']
+    a = mcts_args(args.sims, args.game)
     node_cap = args.node_cap or (6 * args.sims + 320)
     eng = Engine(game, net, a, n_games=args.games, dirichlet_noise=True, seed=1000 + rank, node_cap=node_cap)
     K, W = args.steps, args.warmup
@@ -272,11 +290,11 @@ def main():
     n_launch = max(int(kt['select_launches']), 1)
     sel_bytes = 16.0 * visits + 14.0 * d['sum_legal_visited']                    # B_sel = 16 + 14 L per select step
     bak_bytes = 32.0 * visits + (2.0 * S_BYTES + 32.0) * exps + 14.0 * d['sum_legal'] + (S_BYTES + 11 + 4 * N_ACT + 4 * N_PL) * evals  # B_bak, B_exp, B_nn
-    net_flops = float(V80_FLOPS) * evals
+    net_flops = float(gm['flops']) * evals
     kern = {
         'select': {'ms': kt['select_ms'], 'bound': 'hbm', 'achieved': sel_bytes / max(kt['select_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
                    'per_launch_bytes': sel_bytes / n_launch},
-        'net_v80': {'ms': kt['net_ms'], 'bound': 'tensor', 'achieved': net_flops / max(kt['net_ms'], 1e-9) / 1e9, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+        'net': {'ms': kt['net_ms'], 'bound': 'tensor', 'achieved': net_flops / max(kt['net_ms'], 1e-9) / 1e9, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
                     'per_launch_flops': net_flops / n_launch},
         'expand_backup': {'ms': kt['backup_ms'], 'bound': 'hbm', 'achieved': bak_bytes / max(kt['backup_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
                           'per_launch_bytes': bak_bytes / n_launch},
@@ -319,9 +337,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        r = cpu_sample(args.sims, args.cpu_plies, threads)
+        r = cpu_sample(args.sims, args.cpu_plies, threads, game=args.game)
         cpu = {'value': r['sims'] / r['seconds'], 'unit': UNIT, 'cores': threads, 'kind': 'port', 'seconds': r['seconds'],
-               'sample': f'{threads} host threads x 1 Splendor self-play game x {args.cpu_plies} plies x {args.sims} sims (oracle/azg_oracle.c, same MCTS args and V80 weights)'}
+               'sample': f'{threads} host threads x 1 {args.game} self-play game x {args.cpu_plies} plies x {args.sims} sims (oracle/azg_oracle.c, same MCTS args and net weights)'}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,

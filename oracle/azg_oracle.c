@@ -621,12 +621,76 @@ void azo_v80_forward(const float* blob, int n_players, int batch, const i8* boar
     for (int b = 0; b < batch; b++) v80_forward(&N, boards + (size_t)b * nv * 7, valids + (size_t)b * NA, pi + (size_t)b * NA, v + (size_t)b * n_players);
 }
 
+/* ---------------------------------------------------------------- SantoriniNNet V89 ------ */
+/* santorini/SantoriniNNet.py:70-84 (SimpleResBlock), :16-40 (SimpleHead), :194-217 (layers), :273-279 (forward), eval mode.
+ * blob = state_dict tensors in the order of oracle.py:v89_order() (conv weight, then BN weight/bias/mean/var; heads). */
+typedef struct { const float *w, *g, *b, *m, *v; } conv_bn;
+typedef struct { conv_bn first, c1[5], c2[5], pi, vv; const float *pifc, *pifcb, *vfc1, *vfc1b, *vfc2, *vfc2b; } v89_net;
+static conv_bn take_conv_bn(const float** p, int out, int cin, int k) {
+    conv_bn c; c.w = take(p, (size_t)out * cin * k * k); c.g = take(p, out); c.b = take(p, out); c.m = take(p, out); c.v = take(p, out); return c;
+}
+static void v89_bind(v89_net* N, const float* blob) {
+    const float* p = blob;
+    N->first = take_conv_bn(&p, 64, 2, 3);
+    for (int i = 0; i < 5; i++) { N->c1[i] = take_conv_bn(&p, 64, 64, 3); N->c2[i] = take_conv_bn(&p, 64, 64, 3); }
+    N->pi = take_conv_bn(&p, 2, 64, 1); N->pifc = take(&p, 162 * 50); N->pifcb = take(&p, 162);
+    N->vv = take_conv_bn(&p, 1, 64, 1); N->vfc1 = take(&p, 64 * 25); N->vfc1b = take(&p, 64); N->vfc2 = take(&p, 2 * 64); N->vfc2b = take(&p, 2);
+}
+/* Conv2d(cin->cout, k x k, padding k/2, no bias) + BatchNorm2d (eval) on a 5x5 plane stack x[cin][25] -> y[cout][25] */
+static void conv_bn_apply(const conv_bn* c, int cout, int cin, int k, const float* x, float* y) {
+    int r = k / 2;
+    for (int o = 0; o < cout; o++)
+        for (int py = 0; py < 5; py++)
+            for (int px = 0; px < 5; px++) {
+                float s = 0;
+                for (int ci = 0; ci < cin; ci++)
+                    for (int ky = 0; ky < k; ky++)
+                        for (int kx = 0; kx < k; kx++) {
+                            int yy = py + ky - r, xx = px + kx - r;
+                            if (yy < 0 || yy >= 5 || xx < 0 || xx >= 5) continue;
+                            s += c->w[((o * cin + ci) * k + ky) * k + kx] * x[ci * 25 + yy * 5 + xx];
+                        }
+                y[o * 25 + py * 5 + px] = (s - c->m[o]) / sqrtf(c->v[o] + 1e-5f) * c->g[o] + c->b[o];
+            }
+}
+static void v89_forward(const v89_net* N, const i8* board, const u8* valids, float* pi, float* v) {
+    float x[2 * 25], a[64 * 25], h[64 * 25], t[64 * 25];
+    for (int c = 0; c < 2; c++) for (int pos = 0; pos < 25; pos++) x[c * 25 + pos] = (float)board[pos * 3 + c];   /* permute(0,3,1,2), channels 0-1 */
+    conv_bn_apply(&N->first, 64, 2, 3, x, a);
+    for (int i = 0; i < 64 * 25; i++) a[i] = a[i] > 0 ? a[i] : 0;
+    for (int blk = 0; blk < 5; blk++) {
+        conv_bn_apply(&N->c1[blk], 64, 64, 3, a, h);
+        for (int i = 0; i < 64 * 25; i++) h[i] = h[i] > 0 ? h[i] : 0;
+        conv_bn_apply(&N->c2[blk], 64, 64, 3, h, t);
+        for (int i = 0; i < 64 * 25; i++) { float s = t[i] + a[i]; a[i] = s > 0 ? s : 0; }
+    }
+    float pf[50], vf[25], logit[SAN_A], hv[64];
+    conv_bn_apply(&N->pi, 2, 64, 1, a, pf);
+    for (int i = 0; i < 50; i++) pf[i] = pf[i] > 0 ? pf[i] : 0;
+    float mx = -INFINITY;
+    for (int o = 0; o < SAN_A; o++) {
+        float s = N->pifcb[o]; for (int k = 0; k < 50; k++) s += N->pifc[o * 50 + k] * pf[k];
+        logit[o] = valids[o] ? s : -1e8f; if (logit[o] > mx) mx = logit[o];
+    }
+    float se = 0; for (int o = 0; o < SAN_A; o++) se += expf(logit[o] - mx);
+    float lse = logf(se);
+    for (int o = 0; o < SAN_A; o++) pi[o] = expf(logit[o] - mx - lse);
+    conv_bn_apply(&N->vv, 1, 64, 1, a, vf);
+    for (int i = 0; i < 25; i++) vf[i] = vf[i] > 0 ? vf[i] : 0;
+    for (int j = 0; j < 64; j++) { float s = N->vfc1b[j]; for (int k = 0; k < 25; k++) s += N->vfc1[j * 25 + k] * vf[k]; hv[j] = s > 0 ? s : 0; }
+    for (int o = 0; o < 2; o++) { float s = N->vfc2b[o]; for (int j = 0; j < 64; j++) s += N->vfc2[o * 64 + j] * hv[j]; v[o] = tanhf(s); }
+}
+void azo_v89_forward(const float* blob, int batch, const i8* boards, const u8* valids, float* pi, float* v) {
+    v89_net N; v89_bind(&N, blob);
+    for (int b = 0; b < batch; b++) v89_forward(&N, boards + (size_t)b * SAN_S, valids + (size_t)b * SAN_A, pi + (size_t)b * SAN_A, v + (size_t)b * 2);
+}
+
 /* ---------------------------------------------------------------- MCTS ------------------ */
 #define NAN_Q (-42.0)
 static const int64_t MAGIC_SEEDS[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   /* MCTS.py:14 */
 
 typedef struct {
-    int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80*/;
+    int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80,2 v89*/;
     double cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2;
     int game /*0 splendor, 1 santorini without gods*/;
 } azo_cfg;
@@ -639,7 +703,7 @@ typedef struct node {
 } node_t;
 
 typedef struct {
-    azo_cfg cfg; int S, A; v80_net net; const float* blob;
+    azo_cfg cfg; int S, A; v80_net net; v89_net net89; const float* blob;
     node_t* nodes; int* table; int cap, tcap, count;
     int dirichlet_noise, step, last_cleaning; int64_t random_seed;
     azo_rng rng;
@@ -675,6 +739,7 @@ azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_nois
     m->cfg = *cfg; m->blob = blob;
     if (cfg->game == 1) { m->S = SAN_S; m->A = SAN_A; } else { m->S = azo_state_rows(cfg->num_players) * COLS; m->A = NA; }
     if (cfg->net_kind == 1) v80_bind(&m->net, blob, azo_state_rows(cfg->num_players), cfg->num_players);
+    if (cfg->net_kind == 2) v89_bind(&m->net89, blob);
     m->cap = 4096; m->tcap = 16384; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
     m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed);
     return m;
@@ -785,7 +850,9 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
         }
         if (!nd->expanded) {
             g_valid(m, cur, nd->Vs);
-            if (m->cfg.net_kind == 0) azo_hashnet_a(cur, S, nd->Vs, A, n, nd->Ps, v); else v80_forward(&m->net, cur, nd->Vs, nd->Ps, v);
+            if (m->cfg.net_kind == 0) azo_hashnet_a(cur, S, nd->Vs, A, n, nd->Ps, v);
+            else if (m->cfg.net_kind == 2) v89_forward(&m->net89, cur, nd->Vs, nd->Ps, v);
+            else v80_forward(&m->net, cur, nd->Vs, nd->Ps, v);
             m->n_nn_evals++; m->n_expansions++;
             if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, A, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); }
             normalise_f32(nd->Ps, A);

@@ -74,6 +74,7 @@ def lib():
         L.azo_sant_init_game.argtypes = [p8, C.c_uint64]
         L.azo_sant_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_sant_symmetries.restype = C.c_int
         L.azo_v80_forward.argtypes = [pf, C.c_int, C.c_int, p8, pu8, pf, pf]
+        L.azo_v89_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
         L.azo_mcts_new.argtypes = [C.POINTER(Cfg), pf, C.c_int, C.c_uint64]; L.azo_mcts_new.restype = C.c_void_p
         L.azo_mcts_free.argtypes = [C.c_void_p]
         L.azo_mcts_reset.argtypes = [C.c_void_p]
@@ -251,3 +252,29 @@ def sant_symmetries(board, pi, valids):
     ob = np.zeros((8, 5, 5, 3), np.int8); op = np.zeros((8, SAN_A), np.float32); ov = np.zeros((8, SAN_A), np.uint8)
     k = lib().azo_sant_symmetries(_p(b, C.c_int8), _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
     return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]
+
+
+def _bn(prefix):
+    return [f'{prefix}.weight', f'{prefix}.bias', f'{prefix}.running_mean', f'{prefix}.running_var']
+
+
+def v89_order():
+    """state_dict tensor order expected by azg_oracle.c:v89_bind (names as in santorini/SantoriniNNet.py V89)."""
+    names = ['first_layer.0.weight'] + _bn('first_layer.1')
+    for b in range(5):
+        names += [f'trunk.{b}.conv1.weight'] + _bn(f'trunk.{b}.bn1') + [f'trunk.{b}.conv2.weight'] + _bn(f'trunk.{b}.bn2')
+    names += ['head_PI.conv1x1.weight'] + _bn('head_PI.bn') + ['head_PI.fc.weight', 'head_PI.fc.bias']
+    names += ['head_V.conv1x1.weight'] + _bn('head_V.bn') + ['head_V.fc1.weight', 'head_V.fc1.bias', 'head_V.fc2.weight', 'head_V.fc2.bias']
+    return names
+
+
+def v89_blob(state_dict):
+    return np.concatenate([np.asarray(state_dict[n], dtype=np.float32).ravel() for n in v89_order()]).astype(np.float32)
+
+
+def v89_forward(blob, boards, valids):
+    boards = np.ascontiguousarray(boards, np.int8); B = boards.shape[0]
+    v = np.ascontiguousarray(valids).astype(np.uint8); blob = np.ascontiguousarray(blob, np.float32)
+    pi = np.zeros((B, SAN_A), np.float32); val = np.zeros((B, 2), np.float32)
+    lib().azo_v89_forward(_p(blob, C.c_float), B, _p(boards, C.c_int8), _p(v, C.c_uint8), _p(pi, C.c_float), _p(val, C.c_float))
+    return pi, val

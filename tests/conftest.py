@@ -71,3 +71,13 @@ def san_mcts_cases():
 @pytest.fixture(scope='session')
 def san_episode():
     return np.load(os.path.join(GOLDEN, 'santorini_episode.npz'))
+
+
+@pytest.fixture(scope='session')
+def v89_golden():
+    out = {}
+    for tag in ('rand', 'shipped'):
+        z = np.load(os.path.join(GOLDEN, f'santorini_v89_{tag}.npz'))
+        sd = {k[4:]: z[k] for k in z.files if k.startswith('sd__')}
+        out[tag] = dict(sd=sd, boards=z['boards'], valids=z['valids'], pi=z['pi'], v=z['v'])
+    return out

@@ -146,3 +146,50 @@ def test_selfplay_finishes_games(game, hashnet):
     assert len(ex) == 32 and ex[0][0].shape == (5, 5, 3)
     st = c.engine.stats()
     assert st['episodes_finished'] >= 16 and st['arena_overflows'] == 0
+
+
+@pytest.mark.parametrize('tag', ['rand', 'shipped'])
+def test_v89_forward_golden(game, v89_golden, tag):
+    """SantoriniNNet V89 kernel vs the reference's torch CPU fp32 outputs; tolerance 1e-5 absolute on pi and v."""
+    from azg_b200.nnet import SantoriniNNetWrapper
+    g = v89_golden[tag]
+    net = SantoriniNNetWrapper(game, {'nn_version': 89}, state_dict=g['sd'])
+    pi, v = net.predict_batch(g['boards'], g['valids'])
+    np.testing.assert_allclose(pi, g['pi'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(v, g['v'], rtol=0, atol=1e-5)
+    assert (pi[~g['valids']] == 0).all()
+    p0, v0 = net.predict(g['boards'][5], g['valids'][5])
+    assert p0.shape == (162,) and v0.shape == (2,)
+    np.testing.assert_allclose(p0, g['pi'][5], rtol=0, atol=1e-5)
+
+
+def test_v89_forward_vs_oracle_ragged_batches(game, v89_golden, san_kat):
+    from azg_b200.nnet import SantoriniNNetWrapper
+    sd = v89_golden['rand']['sd']
+    net = SantoriniNNetWrapper(game, {'nn_version': 89}, state_dict=sd)
+    blob = O.v89_blob(sd)
+    for n in (1, 5, 6, 7, 100):                              # partial tiles of the 6-leaf CTA tile
+        b = san_kat['canonical'][:n]; va = san_kat['valids'][:n]
+        pi, v = net.predict_batch(b, va)
+        opi, ov = O.v89_forward(blob, b, va)
+        np.testing.assert_allclose(pi, opi, rtol=0, atol=1e-5)
+        np.testing.assert_allclose(v, ov, rtol=0, atol=1e-5)
+
+
+def test_v89_in_the_search_loop(game, v89_golden, san_kat):
+    """Real net in the loop: engine vs CPU oracle; nets agree to ~1e-6 so visit counts agree exactly on most roots."""
+    from azg_b200.nnet import SantoriniNNetWrapper
+    sd = v89_golden['shipped']['sd']
+    net = SantoriniNNetWrapper(game, {'nn_version': 89}, state_dict=sd)
+    roots = san_kat['canonical'][[0, 50, 120, 300]]
+    args, _ = _args('default', 100)
+    eng = Engine(game, net, args, n_games=len(roots), node_cap=1024)
+    counts, raw, q = eng.search(roots)
+    cfg = O.make_cfg(numMCTSSims=100, net_kind=2, game=O.GAME_SANTORINI)
+    exact = 0
+    for i, r in enumerate(roots):
+        probs, oq, full, oraw = O.MCTS(cfg, blob=O.v89_blob(sd)).getActionProb(r, temp=1, force_full_search=True)
+        assert np.abs(raw[i] / raw[i].sum() - probs).max() < 0.06
+        exact += int((raw[i] == oraw).all())
+    assert exact >= len(roots) - 1
+    eng.close()
