@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "net_v80.cuh"
 #include "net_v89.cuh"
+#include "abalone.cuh"
 #include "santorini.cuh"
 #include "selfplay.cuh"
 #include "splendor.cuh"
@@ -95,7 +96,8 @@ typedef Splendor<2> SP2;
     do {                                                                                                  \
         if ((game_id) == AZG_GAME_SPLENDOR && (np) == 2) { typedef Splendor<2> G; return CALL; }           \
         if ((game_id) == AZG_GAME_SANTORINI && (np) == 2) { typedef Santorini G; return CALL; }            \
-        return fail("unknown game (built: 1 = splendor with 2 players, 2 = santorini without gods)");      \
+        if ((game_id) == AZG_GAME_ABALONE && (np) == 2) { typedef Abalone G; return CALL; }                \
+        return fail("unknown game (built: 1 = splendor with 2 players, 2 = santorini without gods, 3 = abalone)"); \
     } while (0)
 
 template <class G> static int game_info_t(azg_game_info_t* out) {
@@ -110,7 +112,7 @@ extern "C" int azg_game_info(int game_id, int num_players, azg_game_info_t* out)
 
 // ------------------------------------------------------------------ batched game-step kernels ----------
 // One warp per board; the board is staged in shared memory exactly as in the search kernels.
-constexpr int GK_WARPS = 4;
+template <class G> __host__ __device__ constexpr int gk_warps() { return G::A > 1024 ? 1 : 4; }     // warps (= boards) per CTA of the game-step kernels
 template <class G> __device__ __forceinline__ void load_board(int8_t* sb, const int8_t* src, int lane) {
     for (int i = lane; i < G::SP; i += 32) sb[i] = i < G::S ? src[i] : (int8_t)0;
     __syncwarp();
@@ -122,28 +124,27 @@ template <class G> __device__ __forceinline__ void store_board(int8_t* dst, cons
 
 template <class G>
 __global__ void k_game_init(int n, const uint64_t* seeds, int8_t* boards) {
-    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    __shared__ __align__(16) int8_t sm[gk_warps<G>()][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * gk_warps<G>() + w;
     if (i >= n) return;
     if (lane == 0) { Philox rng(seeds[i], 0x1717, 0); G::init_game(sm[w], &rng); }
     store_board<G>(boards + (size_t)i * G::S, sm[w], lane);
 }
 template <class G>
 __global__ void k_game_valid(int n, const int8_t* boards, const int* players, uint8_t* mask) {
-    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    __shared__ __align__(16) int8_t sm[gk_warps<G>()][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * gk_warps<G>() + w;
     if (i >= n) return;
     load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
-    uint32_t m[G::MASK_WORDS];
-    G::valid_mask(sm[w], players ? players[i] : 0, lane, m);
-#pragma unroll
-    for (int k = 0; k < G::MASK_WORDS; k++) { int a = lane + 32 * k; if (a < G::A) mask[(size_t)i * G::A + a] = (m[k] >> lane) & 1; }
+    __shared__ uint32_t smw[gk_warps<G>()][G::MASK_WORDS];
+    G::valid_mask(sm[w], players ? players[i] : 0, lane, smw[w]);
+    for (int a = lane; a < G::A; a += 32) mask[(size_t)i * G::A + a] = (smw[w][a >> 5] >> (a & 31)) & 1;
 }
 template <class G>
 __global__ void k_game_next(int n, const int8_t* boards, const int* players, const int* actions, const long long* seeds,
                             const uint64_t* keys, int8_t* out, int* out_np) {
-    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    __shared__ __align__(16) int8_t sm[gk_warps<G>()][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * gk_warps<G>() + w;
     if (i >= n) return;
     load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
     if (lane == 0) {
@@ -155,8 +156,8 @@ __global__ void k_game_next(int n, const int8_t* boards, const int* players, con
 }
 template <class G>
 __global__ void k_game_ended(int n, const int8_t* boards, const int* next_players, float* out) {
-    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    __shared__ __align__(16) int8_t sm[gk_warps<G>()][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * gk_warps<G>() + w;
     if (i >= n) return;
     load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
     float es[G::NP]; G::ended(sm[w], next_players ? next_players[i] : 0, es, lane);
@@ -164,8 +165,8 @@ __global__ void k_game_ended(int n, const int8_t* boards, const int* next_player
 }
 template <class G>
 __global__ void k_game_canonical(int n, const int8_t* boards, const int* players, int8_t* out) {
-    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    __shared__ __align__(16) int8_t sm[gk_warps<G>()][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * gk_warps<G>() + w;
     if (i >= n) return;
     load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
     const int p = players ? players[i] : 0;
@@ -174,8 +175,8 @@ __global__ void k_game_canonical(int n, const int8_t* boards, const int* players
 }
 template <class G>
 __global__ void k_game_round_score(int n, const int8_t* boards, int* rounds, int* scores) {
-    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    __shared__ __align__(16) int8_t sm[gk_warps<G>()][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * gk_warps<G>() + w;
     if (i >= n) return;
     load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
     if (lane == 0 && rounds) rounds[i] = G::round(sm[w]);
@@ -184,10 +185,10 @@ __global__ void k_game_round_score(int n, const int8_t* boards, int* rounds, int
 template <class G>
 __global__ void k_game_symmetries(int n, const int8_t* boards, const float* pi, const uint8_t* mask, int8_t* ob, float* opi,
                                   uint8_t* om, int* ok) {
-    __shared__ __align__(16) int8_t sm[GK_WARPS][G::SP];
-    __shared__ float spi[GK_WARPS][G::A];
-    __shared__ uint8_t smask[GK_WARPS][G::A];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * GK_WARPS + w;
+    __shared__ __align__(16) int8_t sm[gk_warps<G>()][G::SP];
+    __shared__ float spi[gk_warps<G>()][G::A];
+    __shared__ uint8_t smask[gk_warps<G>()][G::A];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * gk_warps<G>() + w;
     if (i >= n) return;
     load_board<G>(sm[w], boards + (size_t)i * G::S, lane);
     for (int a = lane; a < G::A; a += 32) { spi[w][a] = pi[(size_t)i * G::A + a]; smask[w][a] = mask[(size_t)i * G::A + a]; }
@@ -204,8 +205,9 @@ __global__ void k_game_symmetries(int n, const int8_t* boards, const float* pi, 
     }
 }
 
-static dim3 gk_grid(int n) { return dim3((unsigned)((n + GK_WARPS - 1) / GK_WARPS)); }
-#define GK_BLOCK (GK_WARPS * 32)
+template <class G> static dim3 gk_grid_t(int n) { return dim3((unsigned)((n + gk_warps<G>() - 1) / gk_warps<G>())); }
+#define gk_grid(n) gk_grid_t<G>(n)
+#define GK_BLOCK (gk_warps<G>() * 32)
 #define FINISH(nargs)                                                          \
     do {                                                                       \
         CKL();                                                                 \
@@ -453,7 +455,7 @@ struct EngineT : azg_engine {
         for (void* p : allocs) cudaFree(p);
         for (cudaEvent_t x : ev) cudaEventDestroy(x);
     }
-    dim3 grid() const { return dim3((unsigned)((d.n_games + SEL_WARPS - 1) / SEL_WARPS)); }
+    dim3 grid() const { return dim3((unsigned)((d.n_games + sel_warps<G>() - 1) / sel_warps<G>())); }
 
     int create(const azg_engine_cfg* c, azg_net* n_) {
         cfg = *c; net = n_;
@@ -461,7 +463,7 @@ struct EngineT : azg_engine {
         if (c->universes < 0 || c->universes > 8) return fail("universes must be in [0, 8]");
         int node_cap = c->node_cap, edge_cap = c->edge_cap;
         const int U0 = std::max(c->universes, 1);
-        constexpr int EDGE_FACTOR = G::A < 48 ? G::A : (G::GAME_ID == AZG_GAME_SPLENDOR ? 44 : 56);   // mean legal moves per expanded node (measured) + margin
+        constexpr int EDGE_FACTOR = G::EDGE_FACTOR;
         if (node_cap <= 0) {
             // default: room for the nodes that survive tree reuse, bounded by 60 % of free HBM
             size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
@@ -538,14 +540,14 @@ struct EngineT : azg_engine {
         prof_mark(PK_NET, st);
         if (net_forward_dev<G>(net, d.nn_count, d.nn_list, d.nn_in, G::SP, d.leaf_mask, d.nn_pi, d.nn_v, NG, st)) return 1;
         prof_mark(PK_BACKUP, st);
-        k_backup<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, s);
+        k_backup<G><<<grid(), sel_warps<G>() * 32, 0, st>>>(d, s);
         prof_mark(-1, st);
         launches += 3;
         return 0;
     }
     int gc(int sims, cudaStream_t st) {
         prof_mark(PK_OTHER, st);
-        k_gc<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, sims + 2, (sims + 2) * G::MAX_LEGAL, 0);
+        k_gc<G><<<grid(), sel_warps<G>() * 32, 0, st>>>(d, sims + 2, (sims + 2) * G::MAX_LEGAL, 0);
         prof_mark(-1, st);
         launches++;
         return 0;
@@ -567,7 +569,7 @@ struct EngineT : azg_engine {
         if (full_search && !is_device_ptr(full_search)) { bool any = false; for (int i = 0; i < n; i++) any |= full_search[i] != 0; if (!any) steps = sims_fast; }
         gc(steps, st);
         for (int s = 0; s < steps; s++) if (step(s, st)) return 1;
-        k_finish<G><<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(d, n, a[3].as<int>(), a[4].as<int>(), a[5].as<float>());
+        k_finish<G><<<(n + sel_warps<G>() - 1) / sel_warps<G>(), sel_warps<G>() * 32, 0, st>>>(d, n, a[3].as<int>(), a[4].as<int>(), a[5].as<float>());
         launches++;
         d.noise = nullptr;
         if (profiling) { CKL(); if (prof_drain()) return 1; }
@@ -613,14 +615,14 @@ struct EngineT : azg_engine {
         CK(cudaMemcpyAsync(start, sp.counters, sizeof(start), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
         for (int mv = 0; max_moves <= 0 || mv < max_moves; mv++) {
             prof_mark(PK_OTHER, st);
-            k_sp_begin<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, sp, sims_full, sims_fast);
+            k_sp_begin<G><<<grid(), sel_warps<G>() * 32, 0, st>>>(d, sp, sims_full, sims_fast);
             prof_mark(-1, st);
             launches++;
             const int steps = (cfg.prob_fullMCTS > 0.0) ? sims_full : sims_fast;
             gc(steps, st);
             for (int s = 0; s < steps; s++) if (step(s, st)) return 1;
             prof_mark(PK_OTHER, st);
-            k_sp_end<G><<<grid(), SEL_WARPS * 32, 0, st>>>(d, sp);
+            k_sp_end<G><<<grid(), sel_warps<G>() * 32, 0, st>>>(d, sp);
             prof_mark(-1, st);
             launches++;
             CKL();

@@ -26,6 +26,7 @@ struct Santorini {
     static constexpr int A = 162;                              // action_size() = NB_GODS*2*9*9
     static constexpr int MASK_WORDS = 6;
     static constexpr int MAX_LEGAL = 128;                      // 2 workers x 8 moves x 8 builds
+    static constexpr int EDGE_FACTOR = 56;                     // edge arena = node arena x this (mean legal moves ~45-57)
     static constexpr int MAX_MOVES = 104;                      // every move builds one level: at most 100 builds fit on the board
     static constexpr int MAX_DEPTH = MAX_MOVES + 4;
     static constexpr int MAX_SYM = 8;
@@ -70,13 +71,22 @@ struct Santorini {
         if (!(bw == 0 || bw == wid)) return false;             // the moving worker has left its old cell
         return lv(b, bc) < 4;
     }
-    // WARP: legal-action bitmask, identical in every lane on return.
-    static __device__ __forceinline__ void valid_mask(const int8_t* b, int player, int lane, uint32_t (&w)[MASK_WORDS]) {
+    // WARP: legal-action bitmask into `w` (MASK_WORDS words of warp-private shared memory), visible to all lanes on return.
+    static __device__ __forceinline__ void valid_mask(const int8_t* b, int player, int lane, uint32_t* w) {
 #pragma unroll
         for (int k = 0; k < MASK_WORDS; k++) {
             const int a = lane + 32 * k;
-            w[k] = __ballot_sync(FULL, a < A && action_valid(b, a, player));
+            const uint32_t m = __ballot_sync(FULL, a < A && action_valid(b, a, player));
+            if (lane == 0) w[k] = m;
         }
+        __syncwarp();
+    }
+    // WARP: does `player` have any legal move?
+    static __device__ __forceinline__ bool any_valid(const int8_t* b, int player, int lane) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < MASK_WORDS; k++) { const int a = lane + 32 * k; any |= __ballot_sync(FULL, a < A && action_valid(b, a, player)); }
+        return any != 0;
     }
     // LANE: make_move :434-550 (power == NO_GOD). Deterministic: `seed` / `rng` are unused. Returns the next player.
     static __device__ int make_move(int8_t* b, int move, int player, long long seed, Philox* rng) {
@@ -101,11 +111,7 @@ struct Santorini {
         out[0] = out[1] = 0.f;
         if (score(b, 0) == 3 || gp(b, PAN) > 64) { out[0] = 1.f; out[1] = -1.f; return true; }
         if (score(b, 1) == 3 || gp(b, PAN + 1) > 64) { out[0] = -1.f; out[1] = 1.f; return true; }
-        uint32_t m[MASK_WORDS]; valid_mask(b, next_player, lane, m);
-        uint32_t any = 0;
-#pragma unroll
-        for (int k = 0; k < MASK_WORDS; k++) any |= m[k];
-        if (any == 0) { out[next_player] = -1.f; out[1 - next_player] = 1.f; return true; }
+        if (!any_valid(b, next_player, lane)) { out[next_player] = -1.f; out[1 - next_player] = 1.f; return true; }
         return false;
     }
     // WARP: swap_players :567-576.

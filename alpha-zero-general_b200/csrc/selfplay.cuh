@@ -35,14 +35,13 @@ struct SelfPlay {
 
 // visit-count policy at the root of slot g (shared by k_finish-style read-out and self-play)
 template <class G>
-__device__ bool root_policy(const Dev<G>& d, int g, const int8_t* sb, int lane, int* cnt, uint32_t (&mask)[G::MASK_WORDS], float& qs) {
+__device__ bool root_policy(const Dev<G>& d, int g, const int8_t* sb, int lane, int* cnt, uint32_t* mask /*shared, MASK_WORDS*/, float& qs) {
     constexpr int A = G::A;
     uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
     const NodeHdr* nodes = d.g_nodes(g); const Edge* edges = d.g_edges(g); const typename G::act_t* acts = d.g_acts(g);
     const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_keys(g), klo, khi, lane);
     for (int a = lane; a < A; a += 32) cnt[a] = 0;
-#pragma unroll
-    for (int k = 0; k < G::MASK_WORDS; k++) mask[k] = 0;
+    for (int k = lane; k < G::MASK_WORDS; k += 32) mask[k] = 0;
     __syncwarp();
     if (idx < 0 || nodes[idx].kind == NODE_TERMINAL) return false;
     const NodeHdr h = nodes[idx];
@@ -52,9 +51,6 @@ __device__ bool root_policy(const Dev<G>& d, int g, const int8_t* sb, int lane, 
     for (int i = lane; i < h.n_legal; i += 32) best = max(best, edges[h.edge_off + i].n);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
-    uint32_t mine[G::MASK_WORDS];
-#pragma unroll
-    for (int k = 0; k < G::MASK_WORDS; k++) mine[k] = 0;
     for (int i = lane; i < h.n_legal; i += 32) {
         const Edge ed = edges[h.edge_off + i]; const int a = acts[h.edge_off + i];
         int c = ed.n;
@@ -63,15 +59,7 @@ __device__ bool root_policy(const Dev<G>& d, int g, const int8_t* sb, int lane, 
             c = c > 1 ? c : 0;
         }
         cnt[a] = c;
-#pragma unroll
-        for (int k = 0; k < G::MASK_WORDS; k++) if ((a >> 5) == k) mine[k] |= 1u << (a & 31);
-    }
-#pragma unroll
-    for (int k = 0; k < G::MASK_WORDS; k++) {
-        uint32_t m = mine[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(FULL, m, o);
-        mask[k] = m;
+        atomicOr(&mask[a >> 5], 1u << (a & 31));
     }
     qs = h.qs;
     __syncwarp();
@@ -79,9 +67,9 @@ __device__ bool root_policy(const Dev<G>& d, int g, const int8_t* sb, int lane, 
 }
 
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_sp_begin(Dev<G> d, SelfPlay<G> sp, int sims_full, int sims_fast) {
-    __shared__ WarpSmem<G> sm[SEL_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_begin(Dev<G> d, SelfPlay<G> sp, int sims_full, int sims_fast) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;
     if (g >= d.n_games) return;
     int8_t* sb = sm[w].board;
@@ -110,16 +98,16 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_sp_begin(Dev<G> d, SelfPlay<
 }
 
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_sp_end(Dev<G> d, SelfPlay<G> sp) {
-    __shared__ WarpSmem<G> sm[SEL_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPlay<G> sp) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (g >= d.n_games) return;
     constexpr int A = G::A, NP = G::NP, MW = G::MASK_WORDS;
     int8_t* sb = sm[w].board;
     for (int i = lane; i < G::SP; i += 32) sb[i] = d.root[(size_t)g * G::SP + i];
     __syncwarp();
     int* cnt = reinterpret_cast<int*>(sm[w].f); double* pw = sm[w].d;
-    uint32_t mask[MW]; float qs = 0.f;
+    uint32_t* mask = sm[w].mask; float qs = 0.f;
     const bool found = root_policy<G>(d, g, sb, lane, cnt, mask, qs);
     const int ply = sp.ply[g], player = sp.player[g];
     long long total = 0;
@@ -135,7 +123,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_sp_end(Dev<G> d, SelfPlay<G>
             const size_t o = (size_t)g * sp.max_ply + sc;
             for (int i = lane; i < G::S; i += 32) sp.st_board[o * G::S + i] = sb[i];
             for (int a = lane; a < A; a += 32) sp.st_pi[o * A + a] = (float)((double)cnt[a] / (double)total);
-            if (lane < MW) sp.st_mask[o * MW + lane] = mask[lane];
+            for (int k = lane; k < MW; k += 32) sp.st_mask[o * MW + k] = mask[k];
             if (lane < NP) sp.st_q[o * NP + lane] = lane == 0 ? qs : -qs / (float)(NP - 1);
             if (lane == 0) { sp.st_player[o] = (uint8_t)player; sp.st_count[g] = sc + 1; }
         }
@@ -160,8 +148,6 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_sp_end(Dev<G> d, SelfPlay<G>
             action = last;
         }
     } else if (lane == 0) {                                       // arena overflow kept the root out of the tree: uniform legal move
-        uint32_t m[MW] = {0};
-        (void)m;
         int nlegal = 0; for (int a = 0; a < A; a++) nlegal += G::action_valid(sb, a, 0);
         int k = (int)(rng.uniformf() * (float)nlegal); if (k >= nlegal) k = nlegal - 1;
         for (int a = 0; a < A; a++) if (G::action_valid(sb, a, 0)) { if (k == 0) { action = a; break; } k--; }

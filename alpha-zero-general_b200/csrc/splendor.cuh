@@ -51,6 +51,7 @@ struct Splendor {
     static constexpr int A = 81;
     static constexpr int MASK_WORDS = 3;
     static constexpr int MAX_LEGAL = 64;                      // upper bound used to reserve edge space (largest seen: 62)
+    static constexpr int EDGE_FACTOR = 44;                    // edge arena = node arena x this (mean legal moves per expanded node ~34-42)
     static constexpr int MAX_MOVES = 62 * NP;                 // SplendorLogicNumba.py:146
     static constexpr int MAX_DEPTH = MAX_MOVES + 4;
     static constexpr int MAX_SYM = 1 + 9 + 2 * NP;
@@ -113,14 +114,16 @@ struct Splendor {
         return true;                                               // 80: pass is always legal
     }
 
-    // WARP: legal-action bitmask, identical in every lane on return.
-    static __device__ __forceinline__ void valid_mask(const int8_t* b, int player, int lane, uint32_t (&w)[MASK_WORDS]) {
+    // WARP: legal-action bitmask into `w` (MASK_WORDS words of warp-private shared memory), visible to all lanes on return.
+    static __device__ __forceinline__ void valid_mask(const int8_t* b, int player, int lane, uint32_t* w) {
 #pragma unroll
         for (int k = 0; k < MASK_WORDS; k++) {
             int a = lane + 32 * k;
             bool v = a < A && action_valid(b, a, player);
-            w[k] = __ballot_sync(FULL, v);
+            const uint32_t m = __ballot_sync(FULL, v);
+            if (lane == 0) w[k] = m;
         }
+        __syncwarp();
     }
 
     static __device__ __forceinline__ void write_card(int8_t* rows2, int tier, int colour, int idx) {

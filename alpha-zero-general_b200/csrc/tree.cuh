@@ -152,7 +152,7 @@ __device__ __forceinline__ float warp_sum_avx2order(const float* x, int n, int l
 // MCTS.py:147-149,156-160,187-197,255-261. `p` is the dense prior (0 at illegal actions) in shared memory,
 // `dscr` an A-sized f64 scratch. Injected noise if d.noise, else drawn from the Philox stream.
 template <class G>
-__device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const uint32_t (&mask)[G::MASK_WORDS], int lane) {
+__device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const uint32_t* mask /*shared, MASK_WORDS*/, int lane) {
     constexpr int A = G::A;
     if (d.temp2 != 1.0) {
         double inv_t = 1.0 / d.temp2;
@@ -165,7 +165,6 @@ __device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const
         __syncwarp();
     }
     int L = 0;
-#pragma unroll
     for (int k = 0; k < G::MASK_WORDS; k++) L += __popc(mask[k]);
     // dscr[k] <- k-th Dirichlet component
     if (d.noise) {
@@ -182,7 +181,6 @@ __device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const
     }
     __syncwarp();
     int before = 0;
-#pragma unroll
     for (int k = 0; k < G::MASK_WORDS; k++) {
         int a = lane + 32 * k;
         if (a < A && (mask[k] >> lane & 1)) {
@@ -234,7 +232,6 @@ __device__ __forceinline__ int puct_select(const Edge* e, const uint32_t* child,
     return win;
 }
 
-constexpr int SEL_WARPS = 4;
 // k_select runs ONE warp (= one game) per CTA so that an SM slot is recycled as soon as its game's walk ends
 // (walk lengths differ a lot between games); 64 registers/thread -> 32 resident CTAs = 32 games per SM.
 #ifndef AZG_SELK_WARPS
@@ -248,8 +245,11 @@ template <class G> struct WarpSmem {
     __align__(16) int8_t board[G::SP];
     __align__(16) float f[(G::A + 31) / 32 * 32];
     __align__(16) double d[(G::A + 31) / 32 * 32];
+    uint32_t mask[G::MASK_WORDS];                                // legal-action bitmask of the state being expanded / re-noised
     uint64_t key[2]; int np;                                     // key / next player of the state in `board` (select kernel)
 };
+// Warps per CTA of the one-warp-per-game kernels: 4, or 1 when the per-warp scratch is large (Abalone: 3402 actions).
+template <class G> __host__ __device__ constexpr int sel_warps() { return sizeof(WarpSmem<G>) * 4 <= 40 * 1024 ? 4 : 1; }
 
 template <class G> __device__ __forceinline__ void warp_load_board(int8_t* sb, const int8_t* src, int lane) {
     if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(src)[lane];
@@ -265,13 +265,11 @@ template <class G>
 __device__ __noinline__ void renoise_root(const Dev<G>& d, int g, uint32_t edge_off, int n_legal, Edge* edges, const typename G::act_t* acts,
                                           WarpSmem<G>& ws, int lane) {
     struct { uint32_t edge_off; int n_legal; } h = {edge_off, n_legal};
-    float* pf = ws.f; uint32_t m[G::MASK_WORDS];
-#pragma unroll
-    for (int k = 0; k < G::MASK_WORDS; k++) m[k] = 0;
+    float* pf = ws.f; uint32_t* m = ws.mask;
+    for (int k = lane; k < G::MASK_WORDS; k += 32) m[k] = 0;
     for (int a = lane; a < G::A; a += 32) pf[a] = 0.f;
     __syncwarp();
-    for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; pf[a] = edges[h.edge_off + i].p; }
-    for (int i = 0; i < h.n_legal; i++) { int a = acts[h.edge_off + i]; m[a >> 5] |= 1u << (a & 31); }
+    for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; pf[a] = edges[h.edge_off + i].p; atomicOr(&m[a >> 5], 1u << (a & 31)); }
     __syncwarp();
     root_noise<G>(d, g, pf, ws.d, m, lane);
     float s = warp_sum_avx2order(pf, G::A, lane);
@@ -323,9 +321,8 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, ui
         if (lane == 0) for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p];
     } else {
         kind = LEAF_EXPAND;
-        uint32_t m[G::MASK_WORDS];
-        G::valid_mask(sb, 0, lane, m);
-        if (lane < G::MASK_WORDS) d.leaf_mask[(size_t)g * G::MASK_WORDS + lane] = m[lane];
+        G::valid_mask(sb, 0, lane, ws.mask);
+        for (int k = lane; k < G::MASK_WORDS; k += 32) d.leaf_mask[(size_t)g * G::MASK_WORDS + k] = ws.mask[k];
         warp_store_board<G>(d.nn_in + (size_t)g * G::SP, sb, lane);
         if (lane == 0) { int pos = atomicAdd(d.nn_count, 1); d.nn_list[pos] = g; }
     }
@@ -390,9 +387,9 @@ __global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(
 
 // ============================================================ expand + backup =========================
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant__ Dev<G> d, int step) {
-    __shared__ WarpSmem<G> sm[SEL_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_backup(const __grid_constant__ Dev<G> d, int step) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;    // leaf list consumed by the net; reset for the next step
     if (g >= d.n_games) return;
     const int kind = d.leaf_kind[g];
@@ -405,9 +402,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant
     if (kind == LEAF_EXPAND) {
         float* pf = sm[w].f;
         for (int a = lane; a < A; a += 32) pf[a] = d.nn_pi[(size_t)g * A + a];
-        uint32_t m[MW]; int L = 0;
-#pragma unroll
-        for (int k = 0; k < MW; k++) { m[k] = d.leaf_mask[(size_t)g * MW + k]; L += __popc(m[k]); }
+        uint32_t* m = sm[w].mask; int L = 0;
+        for (int k = lane; k < MW; k += 32) { const uint32_t x = d.leaf_mask[(size_t)g * MW + k]; m[k] = x; L += __popc(x); }
+        L = warp_sum_i32(L);
 #pragma unroll
         for (int p = 0; p < NP; p++) v[p] = d.nn_v[(size_t)g * NP + p];
         __syncwarp();
@@ -420,7 +417,6 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant
             if (lane == 0) st[ST_OVERFLOW]++;                    // arena full: value is still backed up, node not stored
         } else {
             int before = 0;
-#pragma unroll
             for (int k = 0; k < MW; k++) {
                 int a = lane + 32 * k;
                 if (a < A && (m[k] >> lane & 1)) {
@@ -508,9 +504,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_backup(const __grid_constant
 // ============================================================ finish (getActionProb tail) ==============
 // MCTS.py:67-80: root counts, q vector, forced-playout policy-target pruning.
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_finish(Dev<G> d, int n, int* out_counts, int* out_raw, float* out_q) {
-    __shared__ WarpSmem<G> sm[SEL_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_finish(Dev<G> d, int n, int* out_counts, int* out_raw, float* out_q) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (g >= n) return;
     constexpr int A = G::A, NP = G::NP;
     int8_t* sb = sm[w].board;
@@ -566,9 +562,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) k_finish(Dev<G> d, int n, int*
 // Compacts nodes + boards + edges + actions + child links in place (ascending, destination <= source), rewrites
 // the links through an old->new index map and rebuilds the hash table.
 template <class G>
-__global__ void __launch_bounds__(SEL_WARPS * 32) k_gc(Dev<G> d, int need_nodes, int need_edges, int force) {
-    __shared__ WarpSmem<G> sm[SEL_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SEL_WARPS + w;
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_nodes, int need_edges, int force) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (g >= d.n_games) return;
     const int nn = d.n_nodes[g], ne = d.n_edges[g];
     if (!force && nn + need_nodes <= d.node_cap && ne + need_edges <= d.edge_cap) return;

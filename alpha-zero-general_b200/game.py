@@ -181,3 +181,22 @@ class SantoriniGame(CudaGame):
     def moveToString(self, move, current_player):
         dirs = ('NW', 'N', 'NE', 'W', '-', 'E', 'SW', 'S', 'SE')
         return f'worker {move // 81 + 1} moves {dirs[(move % 81) // 9]} and builds {dirs[move % 9]}'
+
+
+class AbaloneGame(CudaGame):
+    """Drop-in for abalone/AbaloneGame.py:AbaloneGame (Belgian daisy start, no dynamic komi: the shipped constants of
+    abalone/AbaloneLogicNumba.py:5-6): int8[9,9,4] axial-hex boards, 3402 actions = 378 r + 42 q + plane."""
+
+    game_id = _lib.AZG_GAME_ABALONE
+    max_score_diff = 6
+
+    def __init__(self):
+        super().__init__(2)
+
+    def moveToString(self, move, current_player):
+        plane = move % 42; q = (move // 42) % 9; r = move // 378
+        dirs = ('E', 'SE', 'SW', 'W', 'NW', 'NE')
+        if plane < 6:
+            return f'marble ({r},{q}) moves {dirs[plane]}'
+        size, axis = (2, (plane - 6) // 6) if plane < 24 else (3, (plane - 24) // 6)
+        return f'{size} marbles from ({r},{q}) along {dirs[axis]} move {dirs[plane % 6]}'

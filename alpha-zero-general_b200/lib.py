@@ -11,6 +11,7 @@ SO_PATH = os.path.join(CSRC, 'libazg_b200.so')
 
 AZG_GAME_SPLENDOR = 1
 AZG_GAME_SANTORINI = 2
+AZG_GAME_ABALONE = 3
 AZG_ABI_VERSION = 2
 AZG_NET_HASH = 0
 AZG_NET_SPLENDOR_V80 = 80

@@ -30,7 +30,8 @@ extern "C" {
 #define AZG_ABI_VERSION 2
 
 enum { AZG_GAME_SPLENDOR = 1,                            /* GameSwitcher.py:3-13 ('splendor'), 2 players            */
-       AZG_GAME_SANTORINI = 2 };                         /* 'santorini' built with NB_GODS = 1 (SantoriniConstants.py:19) */
+       AZG_GAME_SANTORINI = 2,                           /* 'santorini' built with NB_GODS = 1 (SantoriniConstants.py:19) */
+       AZG_GAME_ABALONE = 3 };                           /* 'abalone', Belgian daisy start (AbaloneLogicNumba.py:5-6)      */
 enum { AZG_NET_HASH = 0,                                 /* deterministic test net (tests only)                       */
        AZG_NET_SPLENDOR_V80 = 80,                        /* splendor/SplendorNNet.py version 80 (shipped 2-player net) */
        AZG_NET_SANTORINI_V89 = 89 };                     /* santorini/SantoriniNNet.py version 89 (shipped no-god net) */

@@ -29,7 +29,7 @@ typedef uint8_t u8;
 
 #define COLS 7
 #define NA 81            /* action_size(), splendor/SplendorLogicNumba.py:94-96 */
-#define MAXA 162         /* largest action space the MCTS port handles (Santorini without gods) */
+#define MAXA 3402        /* largest action space the MCTS port handles (Abalone) */
 #define MAXP 4
 #define MAXROWS 88       /* observation_size(4) = 32+40+16 rows */
 #define MAXS (MAXROWS * COLS)
@@ -384,6 +384,146 @@ int azo_symmetries(const i8* b, int n, const float* pi, const u8* valids, i8* ob
     return k;
 }
 
+/* ================================================================ Abalone (Belgian daisy) ===============
+ * abalone/AbaloneLogicNumba.py with the shipped constants INITIAL_LAYOUT = 1, ENABLE_DYNAMIC_KOMI = False (:5-6).
+ * State int8[9][9][4] (cell (r,q) at bytes 4(9r+q)..+3: mover's marble, opponent's marble, board mask, misc);
+ * misc[0,0] = byte 3 mover's score, misc[0,1] = byte 7 opponent's score, misc[0,2] = byte 11 round.
+ * Action = 378 r + 42 q + plane (:62-84). */
+#define ABA_S 324
+#define ABA_A 3402
+static const int ABA_DR[6] = {0, 1, 1, 0, -1, -1}, ABA_DQ[6] = {1, 0, -1, -1, 0, 1};          /* DIRECTIONS :53-60 */
+static int aba_at(const i8* b, int r, int q, int ch) { return b[4 * (9 * r + q) + ch]; }
+static int aba_on(const i8* b, int r, int q) { return r >= 0 && r < 9 && q >= 0 && q < 9 && aba_at(b, r, q, 2) == 1; }   /* :86-90 */
+static int aba_enc(int r, int q, int size, int axis, int d) { int plane = size == 1 ? d : (size == 2 ? 6 + axis * 6 + d : 24 + axis * 6 + d); return r * 378 + q * 42 + plane; }
+static void aba_dec(int a, int* r, int* q, int* size, int* axis, int* d) {
+    int plane = a % 42; *q = (a / 42) % 9; *r = a / 378; *d = plane % 6;
+    if (plane < 6) { *size = 1; *axis = 0; } else if (plane < 24) { *size = 2; *axis = (plane - 6) / 6; } else { *size = 3; *axis = (plane - 24) / 6; }
+}
+int azo_aba_get_round(const i8* b) { return b[11]; }
+int azo_aba_get_score(const i8* b, int player) { return player == 0 ? b[3] : b[7]; }
+/* valid_moves :254-331 */
+void azo_aba_valid_moves(const i8* b, int player, u8* out) {
+    memset(out, 0, ABA_A);
+    int opp = 1 - player;
+    for (int r = 0; r < 9; r++) for (int q = 0; q < 9; q++) {
+        if (aba_at(b, r, q, player) == 0) continue;
+        for (int d = 0; d < 6; d++) {
+            int nr = r + ABA_DR[d], nq = q + ABA_DQ[d];
+            if (aba_on(b, nr, nq) && aba_at(b, nr, nq, player) == 0 && aba_at(b, nr, nq, opp) == 0) out[aba_enc(r, q, 1, 0, d)] = 1;
+        }
+        for (int axis = 0; axis < 3; axis++) {
+            int r1 = r + ABA_DR[axis], q1 = q + ABA_DQ[axis];
+            if (!aba_on(b, r1, q1) || aba_at(b, r1, q1, player) == 0) continue;
+            int r2 = r1 + ABA_DR[axis], q2 = q1 + ABA_DQ[axis];
+            int max_size = (aba_on(b, r2, q2) && aba_at(b, r2, q2, player) == 1) ? 3 : 2;
+            for (int size = 2; size <= max_size; size++)
+                for (int d = 0; d < 6; d++) {
+                    int inl = d == axis || d == (axis + 3) % 6;
+                    if (!inl) {
+                        int ok = 1;
+                        for (int i = 0; i < size; i++) {
+                            int tr = r + i * ABA_DR[axis] + ABA_DR[d], tq = q + i * ABA_DQ[axis] + ABA_DQ[d];
+                            if (!aba_on(b, tr, tq) || aba_at(b, tr, tq, player) == 1 || aba_at(b, tr, tq, opp) == 1) { ok = 0; break; }
+                        }
+                        if (ok) out[aba_enc(r, q, size, axis, d)] = 1;
+                    } else {
+                        int fr = d == axis ? r + (size - 1) * ABA_DR[axis] : r, fq = d == axis ? q + (size - 1) * ABA_DQ[axis] : q;
+                        int tr = fr + ABA_DR[d], tq = fq + ABA_DQ[d];
+                        if (!aba_on(b, tr, tq)) continue;
+                        if (aba_at(b, tr, tq, player) == 1) continue;
+                        if (aba_at(b, tr, tq, opp) == 0) { out[aba_enc(r, q, size, axis, d)] = 1; continue; }
+                        int cnt = 0, cr = tr, cq = tq, ok = 0;
+                        for (;;) {
+                            if (!aba_on(b, cr, cq)) { if (cnt > 0) ok = 1; break; }
+                            if (aba_at(b, cr, cq, opp) == 1) { cnt++; if (cnt >= size) break; cr += ABA_DR[d]; cq += ABA_DQ[d]; }
+                            else if (aba_at(b, cr, cq, player) == 1) break;
+                            else { ok = 1; break; }
+                        }
+                        if (ok) out[aba_enc(r, q, size, axis, d)] = 1;
+                    }
+                }
+        }
+    }
+}
+/* make_move :333-374 */
+int azo_aba_make_move(i8* b, int move, int player) {
+    int r, q, size, axis, d; aba_dec(move, &r, &q, &size, &axis, &d);
+    int inl = d == axis || d == (axis + 3) % 6, opp = 1 - player;
+    if (size == 1 || !inl) {
+        for (int i = 0; i < size; i++) {
+            int cr = size > 1 ? r + i * ABA_DR[axis] : r, cq = size > 1 ? q + i * ABA_DQ[axis] : q;
+            b[4 * (9 * cr + cq) + player] = 0; b[4 * (9 * (cr + ABA_DR[d]) + cq + ABA_DQ[d]) + player] = 1;
+        }
+    } else {
+        int fr, fq, br, bq;
+        if (d == axis) { fr = r + (size - 1) * ABA_DR[axis]; fq = q + (size - 1) * ABA_DQ[axis]; br = r; bq = q; }
+        else { fr = r; fq = q; br = r + (size - 1) * ABA_DR[axis]; bq = q + (size - 1) * ABA_DQ[axis]; }
+        int tr = fr + ABA_DR[d], tq = fq + ABA_DQ[d];
+        if (aba_on(b, tr, tq) && aba_at(b, tr, tq, opp) == 1) {
+            int cr = tr, cq = tq;
+            while (aba_on(b, cr, cq) && aba_at(b, cr, cq, opp) == 1) { cr += ABA_DR[d]; cq += ABA_DQ[d]; }
+            b[4 * (9 * tr + tq) + opp] = 0;
+            if (aba_on(b, cr, cq)) b[4 * (9 * cr + cq) + opp] = 1; else b[4 * player + 3] = (i8)(b[4 * player + 3] + 1);
+        }
+        b[4 * (9 * br + bq) + player] = 0; b[4 * (9 * tr + tq) + player] = 1;
+    }
+    b[11] = (i8)(b[11] + 1);
+    return 1 - player;
+}
+/* check_end_game :376-392 */
+void azo_aba_check_end_game(const i8* b, float* out) {
+    out[0] = out[1] = 0.f;
+    if (b[3] >= 6) { out[0] = 1.f; out[1] = -1.f; return; }
+    if (b[7] >= 6) { out[0] = -1.f; out[1] = 1.f; return; }
+    if (b[11] >= 127) {
+        if (b[3] > b[7]) { out[0] = 1.f; out[1] = -1.f; } else if (b[7] > b[3]) { out[0] = -1.f; out[1] = 1.f; } else { out[0] = out[1] = 0.001f; }
+    }
+}
+/* swap_players :394-406 */
+void azo_aba_swap_players(i8* b, int nb_swaps) {
+    if (nb_swaps % 2 != 1) return;
+    for (int c = 0; c < 81; c++) { i8 t = b[4 * c]; b[4 * c] = b[4 * c + 1]; b[4 * c + 1] = t; }
+    i8 t = b[3]; b[3] = b[7]; b[7] = t;
+}
+/* init_game :167-252, Belgian daisy */
+void azo_aba_init_game(i8* b) {
+    memset(b, 0, ABA_S);
+    for (int r = 0; r < 9; r++) for (int q = 0; q < 9; q++) if (r + q >= 4 && r + q <= 12) b[4 * (9 * r + q) + 2] = 1;
+    static const int OPP[6][3] = {{0, 4, 6}, {1, 3, 6}, {2, 3, 5}, {6, 4, 6}, {7, 3, 6}, {8, 3, 5}}, ME[6][3] = {{0, 7, 9}, {1, 6, 9}, {2, 6, 8}, {6, 1, 3}, {7, 0, 3}, {8, 0, 2}};
+    for (int i = 0; i < 6; i++) { for (int q = OPP[i][1]; q < OPP[i][2]; q++) b[4 * (9 * OPP[i][0] + q) + 1] = 1; for (int q = ME[i][1]; q < ME[i][2]; q++) b[4 * (9 * ME[i][0] + q)] = 1; }
+}
+static void aba_xform(int* r, int* q, int rot, int flip) {
+    if (flip) *q = 12 - *r - *q;
+    for (int i = 0; i < rot; i++) { int nr = *q + *r - 4, nq = 8 - *r; *r = nr; *q = nq; }
+}
+/* _build_action_symmetries :95-148, one entry */
+static int aba_map_action(int a, int rot, int flip) {
+    static const int FLIPD[6] = {3, 2, 1, 0, 5, 4};
+    int r, q, size, axis, d; aba_dec(a, &r, &q, &size, &axis, &d);
+    int mr[3], mq[3];
+    for (int i = 0; i < size; i++) { mr[i] = r + i * ABA_DR[axis]; mq[i] = q + i * ABA_DQ[axis]; aba_xform(&mr[i], &mq[i], rot, flip); }
+    int mi = 0; for (int i = 1; i < size; i++) if (mr[i] < mr[mi] || (mr[i] == mr[mi] && mq[i] < mq[mi])) mi = i;
+    int na = 0;
+    if (size > 1) { int oi = mi == 0 ? 1 : 0, dr = mr[oi] - mr[mi], dq = mq[oi] - mq[mi]; if (dr == 0 && dq > 0) na = 0; else if (dr > 0 && dq == 0) na = 1; else if (dr > 0 && dq < 0) na = 2; }
+    int nd = d; if (flip) nd = FLIPD[nd]; nd = (nd + rot) % 6;
+    return aba_enc(mr[mi], mq[mi], size, na, nd);
+}
+/* get_symmetries :408-441: 12 = 6 rotations x 2 reflections, k = 2*rot + flip */
+int azo_aba_symmetries(const i8* b, const float* pi, const u8* valids, i8* ob, float* opi, u8* ov) {
+    for (int k = 0; k < 12; k++) {
+        int rot = k / 2, flip = k % 2;
+        i8* o = ob + k * ABA_S; float* op = opi + (size_t)k * ABA_A; u8* om = ov + (size_t)k * ABA_A;
+        memset(o, 0, ABA_S); memset(op, 0, sizeof(float) * ABA_A); memset(om, 0, ABA_A);
+        for (int r = 0; r < 9; r++) for (int q = 0; q < 9; q++) if (aba_at(b, r, q, 2) == 1) {
+            int nr = r, nq = q; aba_xform(&nr, &nq, rot, flip);
+            for (int ch = 0; ch < 3; ch++) o[4 * (9 * nr + nq) + ch] = b[4 * (9 * r + q) + ch];
+        }
+        for (int c = 0; c < 81; c++) o[4 * c + 3] = b[4 * c + 3];
+        for (int a = 0; a < ABA_A; a++) if (valids[a]) { int m = aba_map_action(a, rot, flip); op[m] = pi[a]; om[m] = valids[a]; }
+    }
+    return 12;
+}
+
 /* ================================================================ Santorini, no gods ====================
  * santorini/SantoriniLogicNumba.py built with NB_GODS = 1 (santorini/SantoriniConstants.py:19): state int8[5][5][3]
  * (cell c = 5y+x at bytes 3c..3c+2: worker, level, gods_power), gods_power.flat[i] = byte 3i+2; flat[0], flat[1] = 64
@@ -692,19 +832,20 @@ static const int64_t MAGIC_SEEDS[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};
 typedef struct {
     int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80,2 v89*/;
     double cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2;
-    int game /*0 splendor, 1 santorini without gods*/;
+    int game /*0 splendor, 1 santorini without gods, 2 abalone*/;
 } azo_cfg;
 
 typedef struct node {
     i8 key[MAXS];
     int has_es, expanded, r; float Es[MAXP];
-    u8 Vs[MAXA]; float Ps[MAXA]; int64_t Ns; double Qsa[MAXA]; int64_t Nsa[MAXA]; float Qs;
+    int64_t Ns; float Qs;            /* per-action arrays Vs/Ps/Qsa/Nsa live in the tree's slabs (row = node index, A entries) */
     int used;
 } node_t;
 
 typedef struct {
     azo_cfg cfg; int S, A; v80_net net; v89_net net89; const float* blob;
     node_t* nodes; int* table; int cap, tcap, count;
+    u8* sVs; float* sPs; double* sQsa; int64_t* sNsa;        /* [cap][A] slabs */
     int dirichlet_noise, step, last_cleaning; int64_t random_seed;
     azo_rng rng;
     /* counters */
@@ -716,10 +857,20 @@ static void table_rebuild(azo_mcts* m) {
     for (int i = 0; i < m->tcap; i++) m->table[i] = -1;
     for (int i = 0; i < m->count; i++) { uint64_t h = key_hash(m->nodes[i].key, m->S) & (uint64_t)(m->tcap - 1); while (m->table[h] >= 0) h = (h + 1) & (uint64_t)(m->tcap - 1); m->table[h] = i; }
 }
+#define N_VS(m, nd) ((m)->sVs + (size_t)((nd) - (m)->nodes) * (size_t)(m)->A)
+#define N_PS(m, nd) ((m)->sPs + (size_t)((nd) - (m)->nodes) * (size_t)(m)->A)
+#define N_QSA(m, nd) ((m)->sQsa + (size_t)((nd) - (m)->nodes) * (size_t)(m)->A)
+#define N_NSA(m, nd) ((m)->sNsa + (size_t)((nd) - (m)->nodes) * (size_t)(m)->A)
+static void slabs_alloc(azo_mcts* m) {
+    size_t n = (size_t)m->cap * (size_t)m->A;
+    m->sVs = (u8*)realloc(m->sVs, n); m->sPs = (float*)realloc(m->sPs, n * sizeof(float));
+    m->sQsa = (double*)realloc(m->sQsa, n * sizeof(double)); m->sNsa = (int64_t*)realloc(m->sNsa, n * sizeof(int64_t));
+}
 static void grow(azo_mcts* m) {
     m->cap *= 2; m->tcap *= 2;
     m->nodes = (node_t*)realloc(m->nodes, sizeof(node_t) * (size_t)m->cap);
     m->table = (int*)realloc(m->table, sizeof(int) * (size_t)m->tcap);
+    slabs_alloc(m);
     table_rebuild(m);
 }
 static node_t* lookup(azo_mcts* m, const i8* key) {
@@ -737,14 +888,15 @@ static node_t* insert(azo_mcts* m, const i8* key) {
 azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_noise, uint64_t seed) {
     azo_mcts* m = (azo_mcts*)calloc(1, sizeof(azo_mcts));
     m->cfg = *cfg; m->blob = blob;
-    if (cfg->game == 1) { m->S = SAN_S; m->A = SAN_A; } else { m->S = azo_state_rows(cfg->num_players) * COLS; m->A = NA; }
+    if (cfg->game == 1) { m->S = SAN_S; m->A = SAN_A; } else if (cfg->game == 2) { m->S = ABA_S; m->A = ABA_A; } else { m->S = azo_state_rows(cfg->num_players) * COLS; m->A = NA; }
     if (cfg->net_kind == 1) v80_bind(&m->net, blob, azo_state_rows(cfg->num_players), cfg->num_players);
     if (cfg->net_kind == 2) v89_bind(&m->net89, blob);
-    m->cap = 4096; m->tcap = 16384; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
+    m->cap = m->A > 1000 ? 512 : 4096; m->tcap = 4 * m->cap; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
+    slabs_alloc(m);
     m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed);
     return m;
 }
-void azo_mcts_free(azo_mcts* m) { if (m) { free(m->nodes); free(m->table); free(m); } }
+void azo_mcts_free(azo_mcts* m) { if (m) { free(m->nodes); free(m->table); free(m->sVs); free(m->sPs); free(m->sQsa); free(m->sNsa); free(m); } }
 void azo_mcts_reset(azo_mcts* m) { m->count = 0; m->last_cleaning = 0; table_rebuild(m); }
 void azo_mcts_stats(const azo_mcts* m, int64_t* out) {
     int64_t nt = 0, sns = 0;
@@ -783,18 +935,18 @@ static void softmax_temp(float* P, int n, double T) {
 }
 /* ---- game dispatch of the Game.py methods the search calls (MCTS.py:125-173) ---- */
 static void g_ended(const azo_mcts* m, const i8* b, int next_player, float* out) {
-    if (m->cfg.game == 1) azo_sant_check_end_game(b, next_player, out); else azo_check_end_game(b, m->cfg.num_players, out);
+    if (m->cfg.game == 1) azo_sant_check_end_game(b, next_player, out); else if (m->cfg.game == 2) azo_aba_check_end_game(b, out); else azo_check_end_game(b, m->cfg.num_players, out);
 }
 static void g_valid(const azo_mcts* m, const i8* b, u8* out) {
-    if (m->cfg.game == 1) azo_sant_valid_moves(b, 0, out); else azo_valid_moves(b, m->cfg.num_players, 0, out);
+    if (m->cfg.game == 1) azo_sant_valid_moves(b, 0, out); else if (m->cfg.game == 2) azo_aba_valid_moves(b, 0, out); else azo_valid_moves(b, m->cfg.num_players, 0, out);
 }
 static int g_move(const azo_mcts* m, i8* b, int a, int player, int64_t seed, azo_rng* rng) {
-    return m->cfg.game == 1 ? azo_sant_make_move(b, a, player) : azo_make_move(b, m->cfg.num_players, a, player, seed, rng);
+    return m->cfg.game == 1 ? azo_sant_make_move(b, a, player) : m->cfg.game == 2 ? azo_aba_make_move(b, a, player) : azo_make_move(b, m->cfg.num_players, a, player, seed, rng);
 }
 static void g_swap(const azo_mcts* m, i8* b, int nb) {
-    if (m->cfg.game == 1) azo_sant_swap_players(b, nb); else azo_swap_players(b, m->cfg.num_players, nb);
+    if (m->cfg.game == 1) azo_sant_swap_players(b, nb); else if (m->cfg.game == 2) azo_aba_swap_players(b, nb); else azo_swap_players(b, m->cfg.num_players, nb);
 }
-static int g_round(const azo_mcts* m, const i8* b) { return m->cfg.game == 1 ? azo_sant_get_round(b) : azo_get_round(b); }
+static int g_round(const azo_mcts* m, const i8* b) { return m->cfg.game == 1 ? azo_sant_get_round(b) : m->cfg.game == 2 ? azo_aba_get_round(b) : azo_get_round(b); }
 
 /* MCTS.py:187-197; `noise` (length = number of legal actions) is either injected by the caller
  * (parity tests replay the reference's draws) or sampled here. */
@@ -813,16 +965,16 @@ static void apply_dir_noise(azo_mcts* m, float* P, const u8* Vs, const double* n
 }
 
 /* MCTS.py:210-230 */
-static int pick_highest_ucb(const node_t* nd, int A, double cpuct, int forced, int64_t n_iter, double fpu) {
+static int pick_highest_ucb(const node_t* nd, const u8* Vs, const float* Ps, const double* Qsa, const int64_t* Nsa, int A, double cpuct, int forced, int64_t n_iter, double fpu) {
     double best = -INFINITY; int best_a = -1;
     double fpu_init = fpu > 0 ? (double)nd->Qs - fpu : fpu;
     double c0 = cpuct * sqrt((double)nd->Ns + 1e-8), c1 = cpuct * sqrt((double)nd->Ns), kn = (double)n_iter * 0.5;
     for (int a = 0; a < A; a++) {
-        if (!nd->Vs[a]) continue;
-        if (forced && nd->Nsa[a] < (int64_t)sqrt(kn * (double)nd->Ps[a])) return a;
+        if (!Vs[a]) continue;
+        if (forced && Nsa[a] < (int64_t)sqrt(kn * (double)Ps[a])) return a;
         double u;
-        if (nd->Qsa[a] != NAN_Q) u = nd->Qsa[a] + (c1 * (double)nd->Ps[a]) / (double)(nd->Nsa[a] + 1);
-        else u = fma(c0, (double)nd->Ps[a], fpu_init);
+        if (Qsa[a] != NAN_Q) u = Qsa[a] + (c1 * (double)Ps[a]) / (double)(Nsa[a] + 1);
+        else u = fma(c0, (double)Ps[a], fpu_init);
         if (u > best) { best = u; best_a = a; }
     }
     return best_a;
@@ -849,19 +1001,20 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
             if (any) { memcpy(v, nd->Es, sizeof(float) * (size_t)n); break; }
         }
         if (!nd->expanded) {
-            g_valid(m, cur, nd->Vs);
-            if (m->cfg.net_kind == 0) azo_hashnet_a(cur, S, nd->Vs, A, n, nd->Ps, v);
-            else if (m->cfg.net_kind == 2) v89_forward(&m->net89, cur, nd->Vs, nd->Ps, v);
-            else v80_forward(&m->net, cur, nd->Vs, nd->Ps, v);
+            u8* Vs = N_VS(m, nd); float* Ps = N_PS(m, nd); double* Qsa = N_QSA(m, nd); int64_t* Nsa = N_NSA(m, nd);
+            g_valid(m, cur, Vs);
+            if (m->cfg.net_kind == 0) azo_hashnet_a(cur, S, Vs, A, n, Ps, v);
+            else if (m->cfg.net_kind == 2) v89_forward(&m->net89, cur, Vs, Ps, v);
+            else v80_forward(&m->net, cur, Vs, Ps, v);
             m->n_nn_evals++; m->n_expansions++;
-            if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, A, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); }
-            normalise_f32(nd->Ps, A);
-            nd->Ns = 0; for (int a = 0; a < A; a++) { nd->Qsa[a] = NAN_Q; nd->Nsa[a] = 0; }
+            if (depth == 0 && dir_noise) { softmax_temp(Ps, A, m->cfg.temperature2); apply_dir_noise(m, Ps, Vs, noise); }
+            normalise_f32(Ps, A);
+            nd->Ns = 0; for (int a = 0; a < A; a++) { Qsa[a] = NAN_Q; Nsa[a] = 0; }
             nd->Qs = v[0]; nd->expanded = 1;
             break;
         }
-        if (depth == 0 && dir_noise) { softmax_temp(nd->Ps, A, m->cfg.temperature2); apply_dir_noise(m, nd->Ps, nd->Vs, noise); normalise_f32(nd->Ps, A); }
-        int a = pick_highest_ucb(nd, m->A, m->cfg.cpuct, depth == 0 && forced, m->step, m->cfg.fpu);
+        if (depth == 0 && dir_noise) { softmax_temp(N_PS(m, nd), A, m->cfg.temperature2); apply_dir_noise(m, N_PS(m, nd), N_VS(m, nd), noise); normalise_f32(N_PS(m, nd), A); }
+        int a = pick_highest_ucb(nd, N_VS(m, nd), N_PS(m, nd), N_QSA(m, nd), N_NSA(m, nd), m->A, m->cfg.cpuct, depth == 0 && forced, m->step, m->cfg.fpu);
         m->n_node_visits++;
         int np_ = g_move(m, cur, a, 0, m->random_seed, &dummy);           /* MCTS.py:233-248 */
         if (np_ != 0) g_swap(m, cur, np_);
@@ -871,9 +1024,10 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
         float t[MAXP]; for (int p = 0; p < n; p++) t[(p + path_np[d]) % n] = v[p];       /* np.roll(v, next_player) */
         memcpy(v, t, sizeof(float) * (size_t)n);
         node_t* nd = &m->nodes[path_node[d]]; int a = path_a[d];
-        nd->Qsa[a] = ((double)nd->Nsa[a] * nd->Qsa[a] + (double)v[0]) / (double)(nd->Nsa[a] + 1);
+        double* Qsa = N_QSA(m, nd); int64_t* Nsa = N_NSA(m, nd);
+        Qsa[a] = ((double)Nsa[a] * Qsa[a] + (double)v[0]) / (double)(Nsa[a] + 1);
         nd->Qs = ((float)(nd->Ns + 1) * nd->Qs + v[0]) / (float)(nd->Ns + 2);
-        nd->Nsa[a] += 1; nd->Ns += 1;
+        Nsa[a] += 1; nd->Ns += 1;
     }
 }
 
@@ -892,13 +1046,14 @@ int azo_mcts_get_action_prob(azo_mcts* m, const i8* cb, double temp, int force_f
     if (nsims > 0) m->step = nsims - 1;
     node_t* root = lookup(m, cb);
     double counts[MAXA];
-    for (int a = 0; a < A; a++) { counts[a] = (double)root->Nsa[a]; if (raw_counts) raw_counts[a] = root->Nsa[a]; }
+    const int64_t* rNsa = N_NSA(m, root); const float* rPs = N_PS(m, root);
+    for (int a = 0; a < A; a++) { counts[a] = (double)rNsa[a]; if (raw_counts) raw_counts[a] = rNsa[a]; }
     q[0] = root->Qs; for (int p = 1; p < n; p++) q[p] = -root->Qs / (float)(n - 1);
     if (forced) {
         double best = 0; for (int a = 0; a < A; a++) if (counts[a] > best) best = counts[a];
         for (int a = 0; a < A; a++) {
             double cnt = counts[a];
-            if (cnt != best) { float t = 0.5f * root->Ps[a]; t = t * (float)nsims; cnt = cnt - (double)(int64_t)sqrt((double)t); }
+            if (cnt != best) { float t = 0.5f * rPs[a]; t = t * (float)nsims; cnt = cnt - (double)(int64_t)sqrt((double)t); }
             counts[a] = cnt > 1 ? cnt : 0;
         }
     }
@@ -906,7 +1061,15 @@ int azo_mcts_get_action_prob(azo_mcts* m, const i8* cb, double temp, int force_f
         int r = g_round(m, cb);
         if (r > m->last_cleaning + 20) {
             int w = 0;
-            for (int i = 0; i < m->count; i++) if (!(m->nodes[i].r < r - 5)) { if (w != i) m->nodes[w] = m->nodes[i]; w++; }
+            for (int i = 0; i < m->count; i++) if (!(m->nodes[i].r < r - 5)) {
+                if (w != i) {
+                    size_t Az = (size_t)m->A;
+                    m->nodes[w] = m->nodes[i];
+                    memcpy(m->sVs + w * Az, m->sVs + i * Az, Az); memcpy(m->sPs + w * Az, m->sPs + i * Az, Az * sizeof(float));
+                    memcpy(m->sQsa + w * Az, m->sQsa + i * Az, Az * sizeof(double)); memcpy(m->sNsa + w * Az, m->sNsa + i * Az, Az * sizeof(int64_t));
+                }
+                w++;
+            }
             m->count = w; table_rebuild(m); m->last_cleaning = r;
         }
     }
@@ -934,7 +1097,7 @@ static double temp_for_selfplay(double t_begin, double t_end, double half_life, 
 static void execute_episode(azo_mcts* m, uint64_t seed, double t0, double t1, double half, int max_plies, azo_run_stats* st) {
     int n = m->cfg.num_players, S = m->S; const int A = m->A; azo_rng rng; rng_seed(&rng, seed ^ 0xA5A5A5A5ULL);
     i8 board[MAXS], cb[MAXS];
-    if (m->cfg.game == 1) azo_sant_init_game(board, seed); else azo_init_game(board, n, seed);
+    if (m->cfg.game == 1) azo_sant_init_game(board, seed); else if (m->cfg.game == 2) azo_aba_init_game(board); else azo_init_game(board, n, seed);
     int player = 0, step = 0; azo_mcts_reset(m);
     double probs[MAXA]; float q[MAXP], r[MAXP];
     for (;;) {

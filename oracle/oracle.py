@@ -73,6 +73,14 @@ def lib():
         L.azo_sant_swap_players.argtypes = [p8, C.c_int]
         L.azo_sant_init_game.argtypes = [p8, C.c_uint64]
         L.azo_sant_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_sant_symmetries.restype = C.c_int
+        L.azo_aba_get_round.argtypes = [p8]; L.azo_aba_get_round.restype = C.c_int
+        L.azo_aba_get_score.argtypes = [p8, C.c_int]; L.azo_aba_get_score.restype = C.c_int
+        L.azo_aba_valid_moves.argtypes = [p8, C.c_int, pu8]
+        L.azo_aba_make_move.argtypes = [p8, C.c_int, C.c_int]; L.azo_aba_make_move.restype = C.c_int
+        L.azo_aba_check_end_game.argtypes = [p8, pf]
+        L.azo_aba_swap_players.argtypes = [p8, C.c_int]
+        L.azo_aba_init_game.argtypes = [p8]
+        L.azo_aba_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_aba_symmetries.restype = C.c_int
         L.azo_v80_forward.argtypes = [pf, C.c_int, C.c_int, p8, pu8, pf, pf]
         L.azo_v89_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
         L.azo_mcts_new.argtypes = [C.POINTER(Cfg), pf, C.c_int, C.c_uint64]; L.azo_mcts_new.restype = C.c_void_p
@@ -158,8 +166,8 @@ def v80_forward(blob, boards, valids, n=2):
     return pi, val
 
 
-GAME_SPLENDOR, GAME_SANTORINI = 0, 1
-GAME_ACTIONS = {GAME_SPLENDOR: 81, GAME_SANTORINI: 162}
+GAME_SPLENDOR, GAME_SANTORINI, GAME_ABALONE = 0, 1, 2
+GAME_ACTIONS = {GAME_SPLENDOR: 81, GAME_SANTORINI: 162, GAME_ABALONE: 3402}
 
 
 def make_cfg(num_players=2, numMCTSSims=800, ratio_fullMCTS=5, universes=1, forced_playouts=False, no_mem_optim=False,
@@ -278,3 +286,50 @@ def v89_forward(blob, boards, valids):
     pi = np.zeros((B, SAN_A), np.float32); val = np.zeros((B, 2), np.float32)
     lib().azo_v89_forward(_p(blob, C.c_float), B, _p(boards, C.c_int8), _p(v, C.c_uint8), _p(pi, C.c_float), _p(val, C.c_float))
     return pi, val
+
+
+# ---- Abalone, Belgian daisy (abalone/AbaloneLogicNumba.py, shipped constants) ----
+ABA_A = 3402
+
+
+def aba_init_game():
+    b = np.zeros((9, 9, 4), np.int8); lib().azo_aba_init_game(_p(b, C.c_int8)); return b
+
+
+def aba_valid_moves(board, player=0):
+    b = _board(board); out = np.zeros(ABA_A, np.uint8)
+    lib().azo_aba_valid_moves(_p(b, C.c_int8), int(player), _p(out, C.c_uint8))
+    return out.astype(np.bool_)
+
+
+def aba_next_state(board, player, action):
+    b = _board(board)
+    return b, lib().azo_aba_make_move(_p(b, C.c_int8), int(action), int(player))
+
+
+def aba_game_ended(board):
+    b = _board(board); out = np.zeros(2, np.float32)
+    lib().azo_aba_check_end_game(_p(b, C.c_int8), _p(out, C.c_float))
+    return out
+
+
+def aba_canonical(board, player):
+    b = _board(board)
+    if player:
+        lib().azo_aba_swap_players(_p(b, C.c_int8), int(player))
+    return b
+
+
+def aba_get_round(board):
+    b = _board(board); return lib().azo_aba_get_round(_p(b, C.c_int8))
+
+
+def aba_get_score(board, player):
+    b = _board(board); return lib().azo_aba_get_score(_p(b, C.c_int8), int(player))
+
+
+def aba_symmetries(board, pi, valids):
+    b = _board(board); pi = np.ascontiguousarray(pi, np.float32); v = np.ascontiguousarray(valids).astype(np.uint8)
+    ob = np.zeros((12, 9, 9, 4), np.int8); op = np.zeros((12, ABA_A), np.float32); ov = np.zeros((12, ABA_A), np.uint8)
+    k = lib().azo_aba_symmetries(_p(b, C.c_int8), _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
+    return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]

@@ -81,3 +81,41 @@ def v89_golden():
         sd = {k[4:]: z[k] for k in z.files if k.startswith('sd__')}
         out[tag] = dict(sd=sd, boards=z['boards'], valids=z['valids'], pi=z['pi'], v=z['v'])
     return out
+
+
+def _unpack(bits, n=3402):
+    return np.unpackbits(bits, axis=-1)[..., :n].astype(np.bool_)
+
+
+@pytest.fixture(scope='session')
+def aba_kat():
+    z = np.load(os.path.join(GOLDEN, 'abalone_kat.npz'))
+    d = {k: z[k] for k in z.files}
+    d['valids'] = _unpack(d['valids']); d['sym_valids'] = _unpack(d['sym_valids']); d['sym_out_valids'] = _unpack(d['sym_out_valids'])
+    return d
+
+
+@pytest.fixture(scope='session')
+def aba_mcts_cases():
+    z = np.load(os.path.join(GOLDEN, 'abalone_mcts.npz'))
+    n = int(z['n_cases'])
+    keys = ('cfg', 'root', 'n_sims', 'q', 'raw_idx', 'raw_cnt', 'probs_nz', 'probs_idx', 'noise', 'summary')
+    out = []
+    for i in range(n):
+        c = {k: z[f'c{i}_{k}'] for k in keys}
+        raw = np.zeros(3402, np.int64); raw[c['raw_idx']] = c['raw_cnt']; c['raw_counts'] = raw
+        probs = np.zeros(3402, np.float64); probs[c['probs_idx']] = c['probs_nz']; c['probs'] = probs
+        out.append(c)
+    return out
+
+
+@pytest.fixture(scope='session')
+def aba_episode():
+    z = np.load(os.path.join(GOLDEN, 'abalone_episode.npz'))
+    d = {k: z[k] for k in z.files}
+    raw = np.zeros((len(d['roots']), 3402), np.int64)
+    for i in range(len(raw)):
+        m = d['raw_idx'][i] >= 0
+        raw[i, d['raw_idx'][i][m]] = d['raw_cnt'][i][m]
+    d['raw_counts'] = raw
+    return d

@@ -30,6 +30,9 @@ def test_game_info_matches_reference_sizes():
     gs = lib.game_info(lib.AZG_GAME_SANTORINI, 2)
     # santorini/SantoriniLogicNumba.py:13-19 with NB_GODS = 1: observation_size() = (5, 5, 3), action_size() = 162
     assert (gs.state_rows, gs.state_cols, gs.state_depth, gs.state_bytes, gs.action_size, gs.max_symmetries) == (5, 5, 3, 75, 162, 8)
+    ga = lib.game_info(lib.AZG_GAME_ABALONE, 2)
+    # abalone/AbaloneLogicNumba.py:44-50: observation_size() = (9, 9, 4), action_size() = 3402; 12 symmetries
+    assert (ga.state_rows, ga.state_cols, ga.state_depth, ga.state_bytes, ga.action_size, ga.max_symmetries) == (9, 9, 4, 324, 3402, 12)
     with pytest.raises(lib.AzgError):
         lib.game_info(99, 2)
     with pytest.raises(lib.AzgError):
