@@ -13,6 +13,7 @@
 #include "../../include/azg.h"
 #include "common.cuh"
 #include "net_v80.cuh"
+#include "net_v21.cuh"
 #include "net_v89.cuh"
 #include "abalone.cuh"
 #include "santorini.cuh"
@@ -310,7 +311,7 @@ extern "C" int azg_game_symmetries(int game_id, int np, int n, const int8_t* boa
 struct azg_net {
     int kind, game_id, np;
     V80Layout L; V80Chunks CK; V80DW DW; float* blob = nullptr;
-    V89Layout L89; V89Chunks CK89;
+    V89Layout L89; V89Chunks CK89; V21Layout L21;
     Scratch masks;                        // packed masks for the standalone forward
     unsigned long long launches = 0;
 };
@@ -348,6 +349,13 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
             if (!attr_set89) { CK(cudaFuncSetAttribute(k_v89_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set89 = true; }
             k_v89_forward<<<(n_max + V89_TB - 1) / V89_TB, V89_THREADS, smem, st>>>(net->blob, net->L89, net->CK89, count_ptr, list, boards, bstride, masks, pi, v, n_max);
         } else return fail("SantoriniNNet V89 only evaluates Santorini boards");
+    } else if (net->kind == AZG_NET_ABALONE_V21) {
+        if constexpr (G::GAME_ID == AZG_GAME_ABALONE) {
+            static bool attr_set21 = false;
+            constexpr size_t smem = v21_smem_bytes();
+            if (!attr_set21) { CK(cudaFuncSetAttribute(k_v21_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set21 = true; }
+            k_v21_forward<<<(n_max + V21_TB - 1) / V21_TB, V21_THREADS, smem, st>>>(net->blob, net->L21, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+        } else return fail("AbaloneNNet V21 only evaluates Abalone boards");
     } else return fail("net kind not built");
     net->launches++;
     CKL();
@@ -356,6 +364,15 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
 extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights) {
     if (!net) return fail("net is NULL");
     if (net->kind == AZG_NET_HASH) return 0;
+    if (net->kind == AZG_NET_ABALONE_V21) {
+        const size_t need21 = v21_src_floats();
+        if (!weights || n_weights != need21) return fail("V21 weights: expected " + std::to_string(need21) + " floats, got " + std::to_string(n_weights));
+        std::vector<float> src(n_weights), dst((size_t)net->L21.total);
+        CK(cudaMemcpy(src.data(), weights, n_weights * sizeof(float), cudaMemcpyDefault));
+        v21_prepare(src.data(), net->L21, dst.data());
+        CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return 0;
+    }
     if (net->kind == AZG_NET_SANTORINI_V89) {
         const size_t need89 = v89_src_floats();
         if (!weights || n_weights != need89) return fail("V89 weights: expected " + std::to_string(need89) + " floats, got " + std::to_string(n_weights));
@@ -378,14 +395,19 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     if (!out) return fail("out is NULL");
     azg_game_info_t gi;
     if (require_device() || azg_game_info(game_id, np, &gi)) return 1;
-    if (net_kind != AZG_NET_HASH && net_kind != AZG_NET_SPLENDOR_V80 && net_kind != AZG_NET_SANTORINI_V89)
-        return fail("unknown net kind (built: 0=hash test net, 80=Splendor V80, 89=Santorini V89)");
+    if (net_kind != AZG_NET_HASH && net_kind != AZG_NET_SPLENDOR_V80 && net_kind != AZG_NET_SANTORINI_V89 && net_kind != AZG_NET_ABALONE_V21)
+        return fail("unknown net kind (built: 0=hash test net, 80=Splendor V80, 89=Santorini V89, 21=Abalone V21)");
+    if (net_kind == AZG_NET_ABALONE_V21 && game_id != AZG_GAME_ABALONE) return fail("AbaloneNNet V21 only evaluates Abalone boards");
     if (net_kind == AZG_NET_SPLENDOR_V80 && game_id != AZG_GAME_SPLENDOR) return fail("SplendorNNet V80 only evaluates Splendor boards");
     if (net_kind == AZG_NET_SANTORINI_V89 && game_id != AZG_GAME_SANTORINI) return fail("SantoriniNNet V89 only evaluates Santorini boards");
     azg_net* net = new azg_net(); net->kind = net_kind; net->game_id = game_id; net->np = np;
     if (net_kind == AZG_NET_SPLENDOR_V80) {
         net->L = v80_layout(SP2::ROWS, np); net->CK = v80_chunks(net->L); memset(&net->DW, 0, sizeof(net->DW));
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
+        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
+    } else if (net_kind == AZG_NET_ABALONE_V21) {
+        net->L21 = v21_layout();
+        if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L21.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
         if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
     } else if (net_kind == AZG_NET_SANTORINI_V89) {
         net->L89 = v89_layout(); net->CK89 = v89_chunks(net->L89);

@@ -16,6 +16,7 @@ AZG_ABI_VERSION = 2
 AZG_NET_HASH = 0
 AZG_NET_SPLENDOR_V80 = 80
 AZG_NET_SANTORINI_V89 = 89
+AZG_NET_ABALONE_V21 = 21
 
 # every symbol include/azg.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['azg_abi_version', 'azg_last_error', 'azg_device_count', 'azg_set_device', 'azg_engine_profile', 'azg_engine_kernel_times', 'azg_game_info', 'azg_game_init', 'azg_game_valid',

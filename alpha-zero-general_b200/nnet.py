@@ -127,6 +127,61 @@ def random_v89_state_dict(seed=0):
     return sd
 
 
+def _v21_order():
+    names = ['first_layer.0.weight'] + _bn('first_layer.1')
+    for b in range(4):
+        for j in range(3):
+            names += [f'trunk.{b}.block.{j}.0.weight'] + _bn(f'trunk.{b}.block.{j}.1')
+    names += ['meta_fc.0.weight', 'meta_fc.0.bias', 'head_PI.0.weight'] + _bn('head_PI.1') + ['head_V_conv.0.weight'] + _bn('head_V_conv.1')
+    names += ['head_V_fc.0.weight', 'head_V_fc.0.bias', 'head_V_fc.2.weight', 'head_V_fc.2.bias']
+    return names
+
+
+# Order in which azg_net_create expects the AbaloneNNet V21 state_dict tensors (abalone/AbaloneNNet.py:117-156).
+V21_TENSOR_ORDER = _v21_order()
+
+
+def v21_blob(state_dict):
+    parts = []
+    for n in V21_TENSOR_ORDER:
+        t = state_dict[n]
+        if hasattr(t, 'detach'):
+            t = t.detach().cpu().numpy()
+        parts.append(np.asarray(t, dtype=np.float32).ravel())
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+def random_v21_state_dict(seed=0):
+    """Random-init V21 weights from numpy with the reference's initialisers (PyTorch-default / torchvision kaiming_normal_
+    fan_out convolutions approximated by U(+-1/sqrt(fan_in)), kaiming_uniform_ Linear weights with zero biases, default
+    BatchNorm). Used by bench.py only."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv(name, out, cin, k):
+        b = 1.0 / np.sqrt(cin * k * k)
+        sd[name] = rng.uniform(-b, b, size=(out, cin, k, k)).astype(np.float32)
+
+    def bn(prefix, ch):
+        sd[f'{prefix}.weight'] = np.ones(ch, np.float32); sd[f'{prefix}.bias'] = np.zeros(ch, np.float32)
+        sd[f'{prefix}.running_mean'] = np.zeros(ch, np.float32); sd[f'{prefix}.running_var'] = np.ones(ch, np.float32)
+
+    def lin(name, out, inn):
+        b = np.sqrt(6.0 / inn)
+        sd[f'{name}.weight'] = rng.uniform(-b, b, size=(out, inn)).astype(np.float32); sd[f'{name}.bias'] = np.zeros(out, np.float32)
+
+    conv('first_layer.0.weight', 24, 3, 3); bn('first_layer.1', 24)
+    for blk in range(4):
+        conv(f'trunk.{blk}.block.0.0.weight', 48, 24, 1); bn(f'trunk.{blk}.block.0.1', 48)
+        conv(f'trunk.{blk}.block.1.0.weight', 48, 1, 3); bn(f'trunk.{blk}.block.1.1', 48)
+        conv(f'trunk.{blk}.block.2.0.weight', 24, 48, 1); bn(f'trunk.{blk}.block.2.1', 24)
+    lin('meta_fc.0', 16, 6)
+    conv('head_PI.0.weight', 42, 24, 1); bn('head_PI.1', 42)
+    conv('head_V_conv.0.weight', 4, 24, 1); bn('head_V_conv.1', 4)
+    lin('head_V_fc.0', 64, 340); lin('head_V_fc.2', 2, 64)
+    return sd
+
+
 class CudaNet:
     """Owns an azg_net handle."""
 
@@ -218,6 +273,25 @@ class SantoriniNNetWrapper(NNetWrapper):
     def load_state_dict(self, state_dict):
         self.state_dict = state_dict
         self.net.load(v89_blob(state_dict))
+
+
+class AbaloneNNetWrapper(NNetWrapper):
+    """abalone/NNet.py:NNetWrapper (inference surface). nn_args['nn_version'] must be 21."""
+
+    def __init__(self, game, nn_args=None, state_dict=None, seed=0):
+        nn_args = dict(nn_args or {'nn_version': 21})
+        if nn_args.get('nn_version', 21) != 21:
+            raise NotImplementedError('only AbaloneNNet version 21 is built (the shipped Belgian-daisy checkpoint)')
+        self.args = nn_args
+        self.game = game
+        self.board_size = game.getBoardSize(); self.action_size = game.getActionSize(); self.num_players = game.num_players
+        self.requestKnowledgeTransfer = False
+        self.state_dict = state_dict if state_dict is not None else random_v21_state_dict(seed)
+        self.net = CudaNet(_lib.AZG_NET_ABALONE_V21, game, v21_blob(self.state_dict))
+
+    def load_state_dict(self, state_dict):
+        self.state_dict = state_dict
+        self.net.load(v21_blob(state_dict))
 
 
 class HashNetWrapper:

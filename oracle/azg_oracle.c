@@ -825,12 +825,73 @@ void azo_v89_forward(const float* blob, int batch, const i8* boards, const u8* v
     for (int b = 0; b < batch; b++) v89_forward(&N, boards + (size_t)b * SAN_S, valids + (size_t)b * SAN_A, pi + (size_t)b * SAN_A, v + (size_t)b * 2);
 }
 
+/* ---------------------------------------------------------------- AbaloneNNet V21 -------- */
+/* abalone/AbaloneNNet.py:117-156 (layers; torchvision InvertedResidual 24->48->24, kernel 3, no SE, ReLU, BatchNorm2d eps 1e-5),
+ * :173-202 (forward), eval mode. blob = state_dict tensors in the order of oracle.py:v21_order(). Planes are [c][9*r+q]. */
+typedef struct { conv_bn first, ex[4], dw[4], pr[4], pi, vc; const float *mw, *mb, *f1, *f1b, *f2, *f2b; } v21_net;
+static void v21_bind(v21_net* N, const float* blob) {
+    const float* p = blob;
+    N->first = take_conv_bn(&p, 24, 3, 3);
+    for (int i = 0; i < 4; i++) { N->ex[i] = take_conv_bn(&p, 48, 24, 1); N->dw[i] = take_conv_bn(&p, 48, 1, 3); N->pr[i] = take_conv_bn(&p, 24, 48, 1); }
+    N->mw = take(&p, 16 * 6); N->mb = take(&p, 16);
+    N->pi = take_conv_bn(&p, 42, 24, 1); N->vc = take_conv_bn(&p, 4, 24, 1);
+    N->f1 = take(&p, 64 * 340); N->f1b = take(&p, 64); N->f2 = take(&p, 2 * 64); N->f2b = take(&p, 2);
+}
+/* Conv2d(k x k, padding k/2, no bias; depthwise when dwise) + BatchNorm2d (eval) on 9x9 planes */
+static void conv9_bn(const conv_bn* c, int cout, int cin, int k, int dwise, const float* x, float* y) {
+    int r = k / 2;
+    for (int o = 0; o < cout; o++)
+        for (int py = 0; py < 9; py++)
+            for (int px = 0; px < 9; px++) {
+                float s = 0;
+                for (int ci = 0; ci < (dwise ? 1 : cin); ci++)
+                    for (int ky = 0; ky < k; ky++)
+                        for (int kx = 0; kx < k; kx++) {
+                            int yy = py + ky - r, xx = px + kx - r;
+                            if (yy < 0 || yy >= 9 || xx < 0 || xx >= 9) continue;
+                            s += c->w[((o * (dwise ? 1 : cin) + ci) * k + ky) * k + kx] * x[(dwise ? o : ci) * 81 + yy * 9 + xx];
+                        }
+                y[o * 81 + py * 9 + px] = (s - c->m[o]) / sqrtf(c->v[o] + 1e-5f) * c->g[o] + c->b[o];
+            }
+}
+static void v21_forward(const v21_net* N, const i8* board, const u8* valids, float* pi, float* v) {
+    static __thread float x[3 * 81], a[24 * 81], e[48 * 81], d[48 * 81], t[24 * 81], lg[42 * 81], vf[4 * 81], logit[ABA_A];
+    for (int c = 0; c < 3; c++) for (int pos = 0; pos < 81; pos++) x[c * 81 + pos] = (float)board[pos * 4 + c];
+    conv9_bn(&N->first, 24, 3, 3, 0, x, a);
+    for (int i = 0; i < 24 * 81; i++) a[i] = a[i] > 0 ? a[i] : 0;
+    for (int blk = 0; blk < 4; blk++) {
+        conv9_bn(&N->ex[blk], 48, 24, 1, 0, a, e); for (int i = 0; i < 48 * 81; i++) e[i] = e[i] > 0 ? e[i] : 0;
+        conv9_bn(&N->dw[blk], 48, 48, 3, 1, e, d); for (int i = 0; i < 48 * 81; i++) d[i] = d[i] > 0 ? d[i] : 0;
+        conv9_bn(&N->pr[blk], 24, 48, 1, 0, d, t); for (int i = 0; i < 24 * 81; i++) a[i] = a[i] + t[i];
+    }
+    conv9_bn(&N->pi, 42, 24, 1, 0, a, lg);
+    float mx = -INFINITY;
+    for (int pos = 0; pos < 81; pos++) for (int pl = 0; pl < 42; pl++) {         /* permute(0,2,3,1): action = 42*pos + plane */
+        int o = pos * 42 + pl; logit[o] = valids[o] ? lg[pl * 81 + pos] : -1e8f; if (logit[o] > mx) mx = logit[o];
+    }
+    float se = 0; for (int o = 0; o < ABA_A; o++) se += expf(logit[o] - mx);
+    float lse = logf(se);
+    for (int o = 0; o < ABA_A; o++) pi[o] = expf(logit[o] - mx - lse);
+    float meta[6], me[16], vc[340], h[64];
+    for (int j = 0; j < 6; j++) meta[j] = (float)board[j * 4 + 3];                /* input[:, 0, 0:6, 3] */
+    for (int o = 0; o < 16; o++) { float sacc = N->mb[o]; for (int j = 0; j < 6; j++) sacc += N->mw[o * 6 + j] * meta[j]; me[o] = sacc > 0 ? sacc : 0; }
+    conv9_bn(&N->vc, 4, 24, 1, 0, a, vf);
+    for (int i = 0; i < 324; i++) vc[i] = vf[i] > 0 ? vf[i] : 0;
+    for (int i = 0; i < 16; i++) vc[324 + i] = me[i];
+    for (int o = 0; o < 64; o++) { float sacc = N->f1b[o]; for (int k = 0; k < 340; k++) sacc += N->f1[o * 340 + k] * vc[k]; h[o] = sacc > 0 ? sacc : 0; }
+    for (int o = 0; o < 2; o++) { float sacc = N->f2b[o]; for (int k = 0; k < 64; k++) sacc += N->f2[o * 64 + k] * h[k]; v[o] = tanhf(sacc); }
+}
+void azo_v21_forward(const float* blob, int batch, const i8* boards, const u8* valids, float* pi, float* v) {
+    v21_net N; v21_bind(&N, blob);
+    for (int b = 0; b < batch; b++) v21_forward(&N, boards + (size_t)b * ABA_S, valids + (size_t)b * ABA_A, pi + (size_t)b * ABA_A, v + (size_t)b * 2);
+}
+
 /* ---------------------------------------------------------------- MCTS ------------------ */
 #define NAN_Q (-42.0)
 static const int64_t MAGIC_SEEDS[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   /* MCTS.py:14 */
 
 typedef struct {
-    int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80,2 v89*/;
+    int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80,2 v89,3 v21*/;
     double cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2;
     int game /*0 splendor, 1 santorini without gods, 2 abalone*/;
 } azo_cfg;
@@ -843,7 +904,7 @@ typedef struct node {
 } node_t;
 
 typedef struct {
-    azo_cfg cfg; int S, A; v80_net net; v89_net net89; const float* blob;
+    azo_cfg cfg; int S, A; v80_net net; v89_net net89; v21_net net21; const float* blob;
     node_t* nodes; int* table; int cap, tcap, count;
     u8* sVs; float* sPs; double* sQsa; int64_t* sNsa;        /* [cap][A] slabs */
     int dirichlet_noise, step, last_cleaning; int64_t random_seed;
@@ -891,6 +952,7 @@ azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_nois
     if (cfg->game == 1) { m->S = SAN_S; m->A = SAN_A; } else if (cfg->game == 2) { m->S = ABA_S; m->A = ABA_A; } else { m->S = azo_state_rows(cfg->num_players) * COLS; m->A = NA; }
     if (cfg->net_kind == 1) v80_bind(&m->net, blob, azo_state_rows(cfg->num_players), cfg->num_players);
     if (cfg->net_kind == 2) v89_bind(&m->net89, blob);
+    if (cfg->net_kind == 3) v21_bind(&m->net21, blob);
     m->cap = m->A > 1000 ? 512 : 4096; m->tcap = 4 * m->cap; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
     slabs_alloc(m);
     m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed);
@@ -1005,6 +1067,7 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
             g_valid(m, cur, Vs);
             if (m->cfg.net_kind == 0) azo_hashnet_a(cur, S, Vs, A, n, Ps, v);
             else if (m->cfg.net_kind == 2) v89_forward(&m->net89, cur, Vs, Ps, v);
+            else if (m->cfg.net_kind == 3) v21_forward(&m->net21, cur, Vs, Ps, v);
             else v80_forward(&m->net, cur, Vs, Ps, v);
             m->n_nn_evals++; m->n_expansions++;
             if (depth == 0 && dir_noise) { softmax_temp(Ps, A, m->cfg.temperature2); apply_dir_noise(m, Ps, Vs, noise); }

@@ -83,6 +83,7 @@ def lib():
         L.azo_aba_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_aba_symmetries.restype = C.c_int
         L.azo_v80_forward.argtypes = [pf, C.c_int, C.c_int, p8, pu8, pf, pf]
         L.azo_v89_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
+        L.azo_v21_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
         L.azo_mcts_new.argtypes = [C.POINTER(Cfg), pf, C.c_int, C.c_uint64]; L.azo_mcts_new.restype = C.c_void_p
         L.azo_mcts_free.argtypes = [C.c_void_p]
         L.azo_mcts_reset.argtypes = [C.c_void_p]
@@ -333,3 +334,26 @@ def aba_symmetries(board, pi, valids):
     ob = np.zeros((12, 9, 9, 4), np.int8); op = np.zeros((12, ABA_A), np.float32); ov = np.zeros((12, ABA_A), np.uint8)
     k = lib().azo_aba_symmetries(_p(b, C.c_int8), _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
     return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]
+
+
+def v21_order():
+    """state_dict tensor order expected by azg_oracle.c:v21_bind (names as in abalone/AbaloneNNet.py V21)."""
+    names = ['first_layer.0.weight'] + _bn('first_layer.1')
+    for b in range(4):
+        for j in range(3):
+            names += [f'trunk.{b}.block.{j}.0.weight'] + _bn(f'trunk.{b}.block.{j}.1')
+    names += ['meta_fc.0.weight', 'meta_fc.0.bias', 'head_PI.0.weight'] + _bn('head_PI.1') + ['head_V_conv.0.weight'] + _bn('head_V_conv.1')
+    names += ['head_V_fc.0.weight', 'head_V_fc.0.bias', 'head_V_fc.2.weight', 'head_V_fc.2.bias']
+    return names
+
+
+def v21_blob(state_dict):
+    return np.concatenate([np.asarray(state_dict[n], dtype=np.float32).ravel() for n in v21_order()]).astype(np.float32)
+
+
+def v21_forward(blob, boards, valids):
+    boards = np.ascontiguousarray(boards, np.int8); B = boards.shape[0]
+    v = np.ascontiguousarray(valids).astype(np.uint8); blob = np.ascontiguousarray(blob, np.float32)
+    pi = np.zeros((B, ABA_A), np.float32); val = np.zeros((B, 2), np.float32)
+    lib().azo_v21_forward(_p(blob, C.c_float), B, _p(boards, C.c_int8), _p(v, C.c_uint8), _p(pi, C.c_float), _p(val, C.c_float))
+    return pi, val

@@ -119,3 +119,13 @@ def aba_episode():
         raw[i, d['raw_idx'][i][m]] = d['raw_cnt'][i][m]
     d['raw_counts'] = raw
     return d
+
+
+@pytest.fixture(scope='session')
+def v21_golden():
+    out = {}
+    for tag in ('rand', 'shipped'):
+        z = np.load(os.path.join(GOLDEN, f'abalone_v21_{tag}.npz'))
+        sd = {k[4:]: z[k] for k in z.files if k.startswith('sd__')}
+        out[tag] = dict(sd=sd, boards=z['boards'], valids=_unpack(z['valids']), pi=z['pi'], v=z['v'])
+    return out

@@ -126,3 +126,37 @@ def test_batched_search_vs_oracle(game, hashnet, aba_kat):
         assert (raw[i] == oraw).all() and (q[i] == oq).all()
         assert (counts[i] > 0).sum() <= (raw[i] > 0).sum()           # policy-target pruning only removes mass
     eng.close()
+
+
+@pytest.mark.parametrize('tag', ['rand', 'shipped'])
+def test_v21_forward_golden(game, v21_golden, tag):
+    """AbaloneNNet V21 kernel vs the reference's torch CPU fp32 outputs; tolerance 1e-5 absolute on pi and v."""
+    from azg_b200.nnet import AbaloneNNetWrapper
+    g = v21_golden[tag]
+    net = AbaloneNNetWrapper(game, {'nn_version': 21}, state_dict=g['sd'])
+    pi, v = net.predict_batch(g['boards'], g['valids'])
+    np.testing.assert_allclose(pi, g['pi'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(v, g['v'], rtol=0, atol=1e-5)
+    assert (pi[~g['valids']] == 0).all()
+    for n in (1, 3, 5):                                        # partial tiles of the 4-leaf CTA tile
+        p2, v2 = net.predict_batch(g['boards'][:n], g['valids'][:n])
+        np.testing.assert_allclose(p2, g['pi'][:n], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(v2, g['v'][:n], rtol=0, atol=1e-5)
+
+
+def test_v21_in_the_search_loop(game, v21_golden, aba_kat):
+    from azg_b200.nnet import AbaloneNNetWrapper
+    sd = v21_golden['shipped']['sd']
+    net = AbaloneNNetWrapper(game, {'nn_version': 21}, state_dict=sd)
+    roots = aba_kat['canonical'][[0, 150, 400]]
+    args, _ = _args('default', 80)
+    eng = Engine(game, net, args, n_games=len(roots), node_cap=512)
+    counts, raw, q = eng.search(roots)
+    cfg = O.make_cfg(numMCTSSims=80, net_kind=3, game=O.GAME_ABALONE)
+    exact = 0
+    for i, r in enumerate(roots):
+        probs, oq, full, oraw = O.MCTS(cfg, blob=O.v21_blob(sd)).getActionProb(r, temp=1, force_full_search=True)
+        assert np.abs(raw[i] / raw[i].sum() - probs).max() < 0.08
+        exact += int((raw[i] == oraw).all())
+    assert exact >= len(roots) - 1
+    eng.close()

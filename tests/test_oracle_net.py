@@ -24,3 +24,14 @@ def test_v89_forward_matches_reference(v89_golden):
         np.testing.assert_allclose(pi, g['pi'], rtol=0, atol=1e-5, err_msg=tag)
         np.testing.assert_allclose(v, g['v'], rtol=0, atol=1e-5, err_msg=tag)
         assert (pi[~g['valids']] == 0).all()
+
+
+def test_v21_forward_matches_reference(v21_golden):
+    """AbaloneNNet V21 (abalone/AbaloneNNet.py:117-156,173-202): oracle vs the reference's torch CPU fp32 outputs."""
+    for tag, g in v21_golden.items():
+        blob = O.v21_blob(g['sd'])
+        assert blob.size == 35862 + sum(g['sd'][k].size for k in g['sd'] if 'running' in k)
+        pi, v = O.v21_forward(blob, g['boards'], g['valids'])
+        np.testing.assert_allclose(pi, g['pi'], rtol=0, atol=1e-5, err_msg=tag)
+        np.testing.assert_allclose(v, g['v'], rtol=0, atol=1e-5, err_msg=tag)
+        assert (pi[~g['valids']] == 0).all()
