@@ -13,6 +13,7 @@
 #include "../../include/azg.h"
 #include "common.cuh"
 #include "net_v80.cuh"
+#include "net_v80_tc.cuh"
 #include "net_v21.cuh"
 #include "net_v89.cuh"
 #include "abalone.cuh"
@@ -311,6 +312,9 @@ extern "C" int azg_game_symmetries(int game_id, int np, int n, const int8_t* boa
 struct azg_net {
     int kind, game_id, np;
     V80Layout L; V80Chunks CK; V80DW DW; float* blob = nullptr;
+    V80TCImg TI; float* img = nullptr;   // tensor-core operand images of the V80 token GEMMs (net_v80_tc.cuh)
+    long long* prof = nullptr;            // optional phase timestamps of CTA 0 (AZG_V80_PROF=1; azg_net_prof)
+    int v80_kernel = 1;                   // 1 = tcgen05 kernel (default), 0 = fp32 CUDA-core kernel (kept for A/B profiling; AZG_V80_KERNEL=fp32)
     V89Layout L89; V89Chunks CK89; V21Layout L21;
     Scratch masks;                        // packed masks for the standalone forward
     unsigned long long launches = 0;
@@ -336,11 +340,24 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
             count_ptr, list, boards, bstride, masks, pi, v, n_max);
     } else if (net->kind == AZG_NET_SPLENDOR_V80) {
         if constexpr (G::GAME_ID == AZG_GAME_SPLENDOR) {
+            if (net->v80_kernel == 1) {
+                static bool attr_tc = false; static int n_sm = 0;
+                if (!attr_tc) {
+                    CK(cudaFuncSetAttribute(k_v80_tc<G::NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+                    int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+                    attr_tc = true;
+                }
+                if ((reinterpret_cast<uintptr_t>(boards) & 3) || (bstride & 3)) return fail("V80 forward: boards must be 4-byte aligned");
+                const int tiles = (n_max + TC_TB - 1) / TC_TB;
+                k_v80_tc<G::NP><<<std::min(tiles, n_sm), TC_THREADS, TC_SMEM, st>>>(
+                    net->blob, net->img, net->L, net->TI, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max, net->prof);
+            } else {
             static bool attr_set = false;
             constexpr size_t smem = v80_smem_bytes<G::ROWS, V80_TB>();
             if (!attr_set) { CK(cudaFuncSetAttribute(k_v80_forward<G::ROWS, G::NP, V80_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
             k_v80_forward<G::ROWS, G::NP, V80_TB><<<(n_max + V80_TB - 1) / V80_TB, V80_THREADS, smem, st>>>(
                 net->blob, net->L, net->CK, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+            }
         } else return fail("SplendorNNet V80 only evaluates Splendor boards");
     } else if (net->kind == AZG_NET_SANTORINI_V89) {
         if constexpr (G::GAME_ID == AZG_GAME_SANTORINI) {
@@ -389,6 +406,9 @@ extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights
     v80_prepare(src.data(), SP2::ROWS, net->np, net->L, dst.data());
     for (int k = 0; k < 3; k++) for (int i = 0; i < 49; i++) net->DW.w[k][i] = dst[(size_t)net->L.blk[k].wd + i];
     CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> img((size_t)net->TI.total);
+    v80tc_prepare(dst.data(), net->L, net->TI, img.data());
+    CK(cudaMemcpy(net->img, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
 extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* weights, size_t n_weights, azg_net** out) {
@@ -403,8 +423,13 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     azg_net* net = new azg_net(); net->kind = net_kind; net->game_id = game_id; net->np = np;
     if (net_kind == AZG_NET_SPLENDOR_V80) {
         net->L = v80_layout(SP2::ROWS, np); net->CK = v80_chunks(net->L); memset(&net->DW, 0, sizeof(net->DW));
+        net->TI = v80tc_layout();
+        const char* kv = getenv("AZG_V80_KERNEL");
+        net->v80_kernel = (kv && !strcmp(kv, "fp32")) ? 0 : 1;
+        if (getenv("AZG_V80_PROF")) { if (cudaMalloc(&net->prof, 64 * sizeof(long long)) != cudaSuccess) net->prof = nullptr; else cudaMemset(net->prof, 0, 64 * sizeof(long long)); }
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
-        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
+        if (cudaMalloc(&net->img, sizeof(float) * (size_t)net->TI.total) != cudaSuccess) { cudaFree(net->blob); delete net; return fail("cudaMalloc weight images failed"); }
+        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); cudaFree(net->img); delete net; return 1; }
     } else if (net_kind == AZG_NET_ABALONE_V21) {
         net->L21 = v21_layout();
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L21.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
@@ -416,7 +441,11 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     }
     *out = net; return 0;
 }
-extern "C" int azg_net_destroy(azg_net* net) { if (net) { if (net->blob) cudaFree(net->blob); delete net; } return 0; }
+extern "C" int azg_net_prof(azg_net* net, long long* out64) {      // debug: phase timestamps (SM clock) of CTA 0's first tiles
+    if (!net || !net->prof) return fail("profiling not enabled (AZG_V80_PROF=1)");
+    CK(cudaDeviceSynchronize()); CK(cudaMemcpy(out64, net->prof, 64 * sizeof(long long), cudaMemcpyDeviceToHost)); return 0;
+}
+extern "C" int azg_net_destroy(azg_net* net) { if (net) { if (net->blob) cudaFree(net->blob); if (net->img) cudaFree(net->img); delete net; } return 0; }
 template <class G> static int net_forward_t(azg_net* net, int n, const int8_t* boards, const uint8_t* mask, float* pi, float* v, cudaStream_t st) {
     Arg* a = tl_arg;
     if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(mask, (size_t)n * G::A, st) || a[2].outbuf(pi, sizeof(float) * n * G::A) ||

@@ -1,0 +1,559 @@
+// net_v80_tc.cuh -- SplendorNNet V80 eval-mode forward on the 5th-generation tensor cores (tcgen05, sm_100a).
+// Same function as k_v80_forward in net_v80.cuh (splendor/SplendorNNet.py:149-204,259-280,397-404,440 behind
+// GenericNNetWrapper.predict / predict_server, GenericNNetWrapper.py:94-157); the seven token-mixing Linear layers
+// (first_layer, 3 x expand 56->168, 3 x project 168->56 = 83 % of the FLOPs) run as tcgen05.mma kind::tf32 with
+// fp32 accumulators in TMEM.  The parity bar is 1e-5 on pi and v against the reference's fp32 forward, which one
+// TF32 pass cannot meet (2e-4 .. 1e-3 measured), so every GEMM is error-compensated: x = hi + lo with hi = x rounded
+// to TF32 and lo = x - hi (exact), and  D = W_lo X_hi + W_hi X_lo + W_hi X_hi  ("3xTF32", max error 2e-6 on the golden
+// vectors incl. the measured round-toward-zero accumulation of the tensor core, profiles/r01_umma_probe.txt).
+//
+// One persistent CTA per SM, 512 threads, one tile = 16 leaves = 128 "columns" (leaf, feature f<8; f = 7 is padding):
+//   * activations live in shared memory as K-major 128-byte-swizzled MMA operands  X[column][token]  (hi and lo planes)
+//   * first_layer / project:  D[column (TMEM lane)][channel] = X . W^T     -- weights are the N-side operand; hi and lo
+//       weight rows are stacked along N (one N=128 MMA gives W_hi X_hi | W_lo X_hi, one N=64 MMA adds W_hi X_lo)
+//   * expand:                 D[channel (TMEM lane)][column] = W . X^T     -- channels on lanes so that the per-channel
+//       Linear(7->7)+BN+act over the feature axis and the SE pooling are thread-local in the epilogue (one thread = one
+//       channel, its registers = the 8 features of 4 leaves); 168 channels = two M=128 MMAs, the second one reads past
+//       the 168 weight rows (rows are independent, the extra lanes are never read)
+//   * weights arrive as pre-swizzled hi/lo images through cp.async.bulk + mbarrier; the SE / policy / value linears
+//     (fp32 on CUDA cores) read their weights from shared memory rings fed the same way
+//   * the expanded activations make one round trip through TMEM (tcgen05.st) between the depthwise pass and the SE-gated
+//     operand pass, so shared memory only ever holds two 32-channel K-chunks of them (double buffered against the MMAs)
+#pragma once
+#include "net_v80.cuh"
+#include "umma.cuh"
+
+namespace azg {
+
+constexpr int TC_THREADS = 512;           // 16 warps: TMEM lane quarter = warp & 3, sub-slice = warp >> 2
+constexpr int TC_TB = 16;                 // leaves per tile (128 columns)
+// ---- shared memory map (bytes from a 1024-aligned base) ----
+constexpr int TC_XH = 0;                  // activations hi: [2 K atoms][128 columns][128 B]
+constexpr int TC_XL = 32768;              // activations lo
+constexpr int TC_ESTG = 65536;            // 2 stages x (EH 16 KB | EL 16 KB); also raw boards, SE fc weights, head activations
+constexpr int TC_WRING = 131072;          // 64 KB: project weight slots 4 x 16 KB, first-layer image, policy/value weight ring
+constexpr int TC_SQ = 196608;             // SE pooled values, then gates: [168][16] floats
+constexpr int TC_HID = TC_SQ + 168 * 16 * 4;   // SE hidden [40][16]
+constexpr int TC_VH = TC_HID + 40 * 16 * 4;    // value-head accumulators [8][16]
+constexpr int TC_SV = TC_VH + 8 * 16 * 4;        // small vectors (biases, BN scale/shift, value-head matrix), copied once per CTA
+constexpr int SV_B0 = 0, SV_BLK = 64, SV_BLK_STRIDE = 800, SV_BE = 0, SV_SD = 168, SV_TD = 336, SV_B1 = 504, SV_B2 = 552, SV_BP = 720;
+constexpr int SV_BPI2 = 2464, SV_BPI4 = 2560, SV_BV2 = 2656, SV_BV4 = 2660, SV_V4 = 2664, SV_FLOATS = 2680;
+constexpr int TC_SMEM = TC_SV + SV_FLOATS * 4 + 1024;   // + alignment slack
+constexpr int TC_WE_BYTES = 2 * 2 * 176 * 128;       // expand image: hi (2 atoms x 176 rows x 128 B) then lo = 90112 B (spans ESTG + WRING[0,24576))
+constexpr int TC_WE_ATOM = 176 * 128;
+constexpr int TC_PIRING_SLOT = 18816;     // 56 rows of the [392][84] policy matrix
+// ---- TMEM columns ----
+constexpr int TC_DE = 0;                  // expand accumulator: [0,128) channels 0-127, [128,256) channels 128-167 on lanes 0-39
+constexpr int TC_DP = 256;                // first_layer / project accumulator: [256,320) hi-weight part, [320,384) lo-weight part
+
+struct V80TCImg { int w0; int we[3]; int wp[3]; int total; };   // float offsets into the image blob
+inline V80TCImg v80tc_layout() {
+    V80TCImg I; int o = 0;
+    I.w0 = o; o += 32768 / 4;
+    for (int b = 0; b < 3; b++) { I.we[b] = o; o += TC_WE_BYTES / 4; I.wp[b] = o; o += 6 * 16384 / 4; }
+    I.total = o; return I;
+}
+inline float tc_rn_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; }
+// Host: build the operand images from the prepared fp32 blob (BN already folded, K-major [k][out], see v80_prepare).
+inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg& I, float* img) {
+    using umma::sw128_off;
+    for (int i = 0; i < I.total; i++) img[i] = 0.f;
+    const int NV = 56, E = 168;
+    auto put = [&](int base_f, size_t byte_off, float v) { img[base_f + byte_off / 4] = v; };
+    for (int o = 0; o < NV; o++) for (int k = 0; k < NV; k++) {          // first_layer: rows o (hi) and 64 + o (lo), stacked along N
+        const float w = blob[L.w0 + k * NV + o], hi = tc_rn_tf32(w), lo = w - hi;
+        put(I.w0, (size_t)(k >> 5) * 16384 + sw128_off(o, k & 31), hi); put(I.w0, (size_t)(k >> 5) * 16384 + sw128_off(64 + o, k & 31), lo);
+    }
+    for (int b = 0; b < 3; b++) {
+        const auto& B = L.blk[b];
+        for (int c = 0; c < E; c++) for (int k = 0; k < NV; k++) {       // expand: M-side operand, rows = channels
+            const float w = blob[B.we + k * E + c], hi = tc_rn_tf32(w), lo = w - hi;
+            put(I.we[b], (size_t)(k >> 5) * TC_WE_ATOM + sw128_off(c, k & 31), hi);
+            put(I.we[b], (size_t)(2 + (k >> 5)) * TC_WE_ATOM + sw128_off(c, k & 31), lo);
+        }
+        for (int o = 0; o < NV; o++) for (int c = 0; c < E; c++) {       // project: chunk = 32 input channels, rows o (hi) / 64 + o (lo)
+            const float w = blob[B.wp + c * NV + o], hi = tc_rn_tf32(w), lo = w - hi;
+            put(I.wp[b], (size_t)(c >> 5) * 16384 + sw128_off(o, c & 31), hi); put(I.wp[b], (size_t)(c >> 5) * 16384 + sw128_off(64 + o, c & 31), lo);
+        }
+    }
+}
+
+namespace tc {
+using namespace umma;
+enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_MMA, B_PI0, B_PI1, B_PI2, B_V2, B_N };
+struct Phase {                            // per-thread parity of every barrier this thread waits on
+    uint32_t bits = 0;
+    __device__ __forceinline__ void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
+};
+__device__ __forceinline__ void load(uint64_t* bars, int id, void* dst, const void* src, uint32_t bytes) {
+    mbar_expect_tx(&bars[id], bytes); bulk_g2s(dst, src, bytes, &bars[id]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {          // hi = x rounded to TF32, hi + lo == x exactly
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = __fsub_rn(x, hi);
+}
+
+// Depthwise pass of one block for one (channel = TMEM lane, 4 leaves = 32 columns) unit: expand bias + act, Linear(7->7) over
+// the features + BN + act, SE pooling; the result replaces the accumulator in TMEM.
+template <int ACT, bool SE_MAX>
+__device__ __forceinline__ void depthwise_unit(uint32_t taddr, float be, float sd, float td, const float* __restrict__ dw, float* sq4, bool valid) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r); tmem_wait_ld();
+    float pl[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        float v[7];
+#pragma unroll
+        for (int f = 0; f < 7; f++) v[f] = act_apply(__uint_as_float(r[8 * l + f]) + be, ACT);
+        float pool = SE_MAX ? -INFINITY : 0.f;
+#pragma unroll
+        for (int g = 0; g < 7; g++) {
+            float a = 0.f;
+#pragma unroll
+            for (int f = 0; f < 7; f++) a = fmaf(dw[g * 7 + f], v[f], a);
+            a = act_apply(fmaf(a, sd, td), ACT);
+            r[8 * l + g] = __float_as_uint(a);
+            pool = SE_MAX ? fmaxf(pool, a) : pool + a;
+        }
+        r[8 * l + 7] = 0u;
+        pl[l] = SE_MAX ? pool : pool * (1.f / 7.f);
+    }
+    tmem_st32(taddr, r);
+    if (valid) *reinterpret_cast<float4*>(sq4) = make_float4(pl[0], pl[1], pl[2], pl[3]);
+}
+}  // namespace tc
+
+template <int NP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __grid_constant__ V80Layout L, const __grid_constant__ V80TCImg I,
+         const __grid_constant__ V80DW DW, const int* count_ptr, const int* list, const int8_t* boards, int bstride,
+         const uint32_t* masks, float* pi_out, float* v_out, int n_max, long long* prof) {
+    using namespace tc;
+    constexpr int NV = 56, EC = 168, Q = V80_Q, TB = TC_TB, LD = 128, A = 81, PIP = V80Layout::PIP;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[B_N];
+    __shared__ uint32_t tmem_s;
+    __shared__ int slot_of[TB];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, q = warp & 3, sub = warp >> 2;
+    const int count = count_ptr ? min(*count_ptr, n_max) : n_max;
+    const int ntiles = (count + TB - 1) / TB;
+    if ((int)blockIdx.x >= ntiles) return;
+    float* XH = reinterpret_cast<float*>(sm + TC_XH);
+    float* SQ = reinterpret_cast<float*>(sm + TC_SQ); float* HID = reinterpret_cast<float*>(sm + TC_HID); float* VH = reinterpret_cast<float*>(sm + TC_VH);
+    uint8_t* ESTG = sm + TC_ESTG; uint8_t* WRING = sm + TC_WRING;
+    float* SV = reinterpret_cast<float*>(sm + TC_SV);
+    {   // small vectors -> shared memory, once per (persistent) CTA
+        auto cp = [&](int dst, int src, int n) { for (int i = t; i < n; i += TC_THREADS) SV[dst + i] = __ldg(P + src + i); };
+        cp(SV_B0, L.b0, 56);
+        for (int b = 0; b < 3; b++) {
+            const int o = SV_BLK + b * SV_BLK_STRIDE; const V80Layout::Blk& B = L.blk[b];
+            cp(o + SV_BE, B.be, 168); cp(o + SV_SD, B.sd, 168); cp(o + SV_TD, B.td, 168); cp(o + SV_B1, B.b1, 40); cp(o + SV_B2, B.b2, 168); cp(o + SV_BP, B.bp, 56);
+        }
+        cp(SV_BPI2, L.bpi2, 84); cp(SV_BPI4, L.bpi4, 84); cp(SV_BV2, L.bv2, 4); cp(SV_BV4, L.bv4, 4); cp(SV_V4, L.v4, 16);
+    }
+    if (t == 0) { for (int i = 0; i < B_N; i++) mbar_init(&bars[i], 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc<512>(&tmem_s);
+    for (int i = t; i < 65536 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);   // token columns 56..63 stay zero for ever
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tmem_s;
+    const uint32_t tlane = tm + ((uint32_t)(32 * q) << 16);       // this warp's TMEM lane quarter
+    if (t == 0) { mbar_arrive(&bars[B_EF0]); mbar_arrive(&bars[B_EF1]); }   // both E stages start out free
+    Phase ph;
+    int prof_i = 0;
+#define TC_STAMP() do { if (prof && t == 0 && blockIdx.x == 0 && prof_i < 64) prof[prof_i++] = clock64(); } while (0)
+    const uint32_t xh_a = smem_u32(sm + TC_XH), xl_a = smem_u32(sm + TC_XL), estg_a = smem_u32(ESTG), wring_a = smem_u32(WRING);
+    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
+    const float* IMGb = IMG;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tile0 = tile * TB;
+        TC_STAMP();   /* 0: tile start */
+        if (t < TB) { const int j = tile0 + t; slot_of[t] = j < count ? (list ? list[j] : j) : -1; }
+        if (t == 0) {
+            load(bars, B_W0, WRING, IMGb + I.w0, 32768);
+            load(bars, B_WP2, WRING + 32768, IMGb + I.wp[0], 16384);                 // project chunk 0 -> slot 2
+            load(bars, B_WP3, WRING + 49152, IMGb + I.wp[0] + 4096, 16384);          // project chunk 1 -> slot 3
+        }
+        __syncthreads();
+        {   // raw boards -> ESTG (16 x 400 B), 32-bit loads (board rows are 392 B, slots are 4-byte aligned)
+            uint32_t* raw = reinterpret_cast<uint32_t*>(ESTG);
+            for (int k = t; k < TB * 98; k += TC_THREADS) {
+                const int s = k / 98, w = k - s * 98, slot = slot_of[s];
+                raw[s * 100 + w] = slot >= 0 ? reinterpret_cast<const uint32_t*>(boards + (size_t)slot * bstride)[w] : 0u;
+            }
+        }
+        __syncthreads();
+        {   // XH[column][token] = (float)board[leaf][token][f]  (small integers: exact in TF32, no lo plane needed)
+            const int8_t* raw = reinterpret_cast<const int8_t*>(ESTG);
+            for (int k = t; k < 128 * 14; k += TC_THREADS) {
+                const int row = k & 127, kq = k >> 7, s = row >> 3, f = row & 7;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (f < 7) { const int8_t* b = raw + s * 400 + (4 * kq) * 7 + f; v = make_float4((float)b[0], (float)b[7], (float)b[14], (float)b[21]); }
+                *reinterpret_cast<float4*>(sm + TC_XH + (kq >> 3) * 16384 + sw128_off(row, (4 * kq) & 31)) = v;
+            }
+        }
+        fence_async_smem(); __syncthreads();
+        TC_STAMP();   /* 1: input staged */
+        // ---------------- first_layer: D[column][channel] = X . W0^T, hi|lo weight rows stacked along N ----------------
+        if (t == 0) {
+            ph.wait(bars, B_W0); tc_fence_after();
+#pragma unroll 1
+            for (int ks = 0; ks < 7; ks++) {
+                const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+                mma_tf32(tm + TC_DP, desc_sw128(xh_a + off), desc_sw128(wring_a + off), ID128, ks > 0);
+            }
+            mma_commit(&bars[B_MMA]);
+        }
+        __syncwarp();
+        ph.wait(bars, B_MMA); tc_fence_after();
+        TC_STAMP();   /* 2: first MMA done */
+        if (t == 0) load(bars, B_WE, ESTG, IMGb + I.we[0], TC_WE_BYTES);
+        __syncwarp();
+        {   // epilogue: bias, split, write the trunk input operand in place
+            const int row = 32 * q + lane, c0 = 16 * sub;
+            uint32_t dh[16], dl[16];
+            tmem_ld16(tlane + TC_DP + c0, dh); tmem_ld16(tlane + TC_DP + 64 + c0, dl); tmem_wait_ld();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; j4++) {
+                const int c = c0 + 4 * j4;
+                if (c < NV) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) split_rn(__uint_as_float(dh[4 * j4 + j]) + __uint_as_float(dl[4 * j4 + j]) + SV[SV_B0 + c + j], hi[j], lo[j]);
+                    const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
+                    *reinterpret_cast<float4*>(sm + TC_XH + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(sm + TC_XL + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+        fence_async_smem(); tc_fence_before(); __syncthreads();
+        TC_STAMP();   /* 3: first epilogue done */
+
+#pragma unroll 1
+        for (int b = 0; b < 3; b++) {
+            const V80Layout::Blk& B = L.blk[b];
+            const float* dw = DW.w[b];
+            const float* SB = SV + SV_BLK + b * SV_BLK_STRIDE;
+            // ---------------- expand: D[channel][column] = We . X^T (3 passes x 7 k-steps x 2 channel halves) ----------------
+            if (t == 0) {
+                ph.wait(bars, B_WE); tc_fence_after();
+                TC_STAMP();   /* b0: expand weights landed */
+#pragma unroll 1
+                for (int mh = 0; mh < 2; mh++) {
+#pragma unroll 1
+                    for (int p = 0; p < 3; p++) {
+                        const uint32_t wa = estg_a + (p == 0 ? 2 * TC_WE_ATOM : 0) + mh * 16384;      // pass 0: W_lo X_hi, 1: W_hi X_lo, 2: W_hi X_hi
+                        const uint32_t xa = p == 1 ? xl_a : xh_a;
+#pragma unroll 1
+                        for (int ks = 0; ks < 7; ks++)
+                            mma_tf32(tm + TC_DE + 128 * mh, desc_sw128(wa + (ks >> 2) * TC_WE_ATOM + (ks & 3) * 32),
+                                     desc_sw128(xa + (ks >> 2) * 16384 + (ks & 3) * 32), ID128, (p | ks) != 0);
+                    }
+                }
+                mma_commit(&bars[B_MMA]);
+            }
+            __syncwarp();
+            ph.wait(bars, B_MMA); tc_fence_after();
+            TC_STAMP();   /* b1: expand MMAs done */
+            if (t == 0) {                                         // the expand image is dead: SE weights and project chunks 2, 3 take its place
+                mbar_expect_tx(&bars[B_FC], 2 * 26880);
+                bulk_g2s(ESTG, P + B.fc1, 26880, &bars[B_FC]); bulk_g2s(ESTG + 26880, P + B.fc2, 26880, &bars[B_FC]);
+                load(bars, B_WP0, WRING, IMGb + I.wp[b] + 2 * 4096, 16384);
+                load(bars, B_WP1, WRING + 16384, IMGb + I.wp[b] + 3 * 4096, 16384);
+            }
+            __syncwarp();
+            // ---------------- depthwise pass (thread = channel) ----------------
+            {
+                const int c = 32 * q + lane;
+                const float be = SB[SV_BE + c], sd = SB[SV_SD + c], td = SB[SV_TD + c];
+                const uint32_t ta = tlane + TC_DE + 32 * sub;
+                if (b == 0) depthwise_unit<1, false>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
+                else depthwise_unit<2, true>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
+                if (q < 2) {
+                    const int c2 = 128 + c; const bool ok = c2 < EC; const int cc = ok ? c2 : 0;
+                    const float be2 = SB[SV_BE + cc], sd2 = SB[SV_SD + cc], td2 = SB[SV_TD + cc];
+                    if (b == 0) depthwise_unit<1, false>(ta + 128, be2, sd2, td2, dw, SQ + cc * TB + 4 * sub, ok);
+                    else depthwise_unit<2, true>(ta + 128, be2, sd2, td2, dw, SQ + cc * TB + 4 * sub, ok);
+                }
+                tmem_wait_st();
+            }
+            __syncthreads();
+            TC_STAMP();   /* b2: depthwise done */
+            // ---------------- squeeze-excitation: fc1 (168 -> 40, ReLU), fc2 (40 -> 168, hardsigmoid) -> gates in SQ ----------------
+            ph.wait(bars, B_FC);
+            TC_STAMP();   /* b3: fc weights landed */
+            {
+                const float* W1 = reinterpret_cast<const float*>(ESTG); const float* W2 = reinterpret_cast<const float*>(ESTG + 26880);
+                float* HP = reinterpret_cast<float*>(ESTG + 53760);             // K-split partial sums [3][40][16]
+                if (t < 480) {
+                    const int part = t / 160, tt = t - part * 160, qg = tt >> 4, s = tt & 15;
+                    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+                    for (int kk = 56 * part; kk < 56 * part + 56; kk++) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(W1 + kk * Q + 4 * qg);
+                        const float x = SQ[kk * TB + s];
+                        a[0] = fmaf(w4.x, x, a[0]); a[1] = fmaf(w4.y, x, a[1]); a[2] = fmaf(w4.z, x, a[2]); a[3] = fmaf(w4.w, x, a[3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) HP[part * 640 + (4 * qg + j) * TB + s] = a[j];
+                }
+                __syncthreads();
+                for (int i = t; i < Q * TB; i += TC_THREADS) HID[i] = fmaxf(HP[i] + HP[640 + i] + HP[1280 + i] + SB[SV_B1 + (i >> 4)], 0.f);
+                __syncthreads();
+#pragma unroll 1
+                for (int task = t; task < (EC / 4) * TB; task += TC_THREADS) {
+                    const int cq = task >> 4, s = task & 15;
+                    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+                    for (int kk = 0; kk < Q; kk++) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(W2 + kk * EC + 4 * cq);
+                        const float x = HID[kk * TB + s];
+                        g[0] = fmaf(w4.x, x, g[0]); g[1] = fmaf(w4.y, x, g[1]); g[2] = fmaf(w4.z, x, g[2]); g[3] = fmaf(w4.w, x, g[3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) SQ[(4 * cq + j) * TB + s] = fminf(fmaxf(g[j] + SB[SV_B2 + 4 * cq + j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+                }
+            }
+            __syncthreads();
+            TC_STAMP();   /* b4: SE done */
+            // ---------------- SE-gated operand pass + project MMAs, three rounds of two 32-channel K chunks ----------------
+#pragma unroll 1
+            for (int r = 0; r < 3; r++) {
+                ph.wait(bars, B_EF0); ph.wait(bars, B_EF1);       // the MMAs that read the two stages (previous round) are done
+                if (t == 0 && r == 1) {                           // their weight slots are free too: chunks 4, 5
+                    load(bars, B_WP2, WRING + 32768, IMGb + I.wp[b] + 4 * 4096, 16384);
+                    load(bars, B_WP3, WRING + 49152, IMGb + I.wp[b] + 5 * 4096, 16384);
+                }
+                __syncwarp();
+                const bool active = (r == 1) ? (q >= 2) : (q < 2);
+                const int c = (r == 2 ? 128 : 0) + 32 * q + lane;
+                if (active) {                                     // warp-uniform: the TMEM load is warp-collective
+                    uint32_t d[32];
+                    tmem_ld32(tlane + TC_DE + (r == 2 ? 128 : 0) + 32 * sub, d);
+                    tmem_wait_ld();
+                    if (c < EC) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(SQ + c * TB + 4 * sub);
+                        const float gate[4] = {g4.x, g4.y, g4.z, g4.w};
+                        uint8_t* eh = ESTG + (q & 1) * 32768; uint8_t* el = eh + 16384;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            float hi, lo; split_rn(__uint_as_float(d[i]) * gate[i >> 3], hi, lo);
+                            const uint32_t o = sw128_off(32 * sub + i, lane);
+                            *reinterpret_cast<float*>(eh + o) = hi; *reinterpret_cast<float*>(el + o) = lo;
+                        }
+                    }
+                }
+                fence_async_smem(); tc_fence_before(); __syncthreads();
+                if (t == 0) {
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int jj = 0; jj < 2; jj++) {
+                        const int j = 2 * r + jj, slot = (j + 2) & 3;
+                        ph.wait(bars, B_WP0 + slot); tc_fence_after();
+                        const uint32_t ea = estg_a + jj * 32768, wa = wring_a + slot * 16384;
+                        const int nks = j == 5 ? 1 : 4;
+#pragma unroll 1
+                        for (int ks = 0; ks < nks; ks++) {
+                            mma_tf32(tm + TC_DP, desc_sw128(ea + ks * 32), desc_sw128(wa + ks * 32), ID128, (j | ks) != 0);           // E_hi . (W_hi | W_lo)
+                            mma_tf32(tm + TC_DP, desc_sw128(ea + 16384 + ks * 32), desc_sw128(wa + ks * 32), ID64, true);            // E_lo . W_hi
+                        }
+                        mma_commit(&bars[B_EF0 + jj]);
+                    }
+                    if (r == 2) mma_commit(&bars[B_MMA]);
+                }
+                __syncwarp();
+            }
+            ph.wait(bars, B_MMA); tc_fence_after();
+            TC_STAMP();   /* b5: project MMAs done */
+            if (t == 0) {                                         // everything in ESTG / WRING has been consumed
+                if (b == 0) {
+                    load(bars, B_WE, ESTG, IMGb + I.we[1], TC_WE_BYTES);
+                    load(bars, B_WP2, WRING + 32768, IMGb + I.wp[1], 16384);
+                    load(bars, B_WP3, WRING + 49152, IMGb + I.wp[1] + 4096, 16384);
+                } else if (b == 1) {
+                    load(bars, B_PI0, WRING, P + L.pi2, TC_PIRING_SLOT);
+                    load(bars, B_PI1, WRING + TC_PIRING_SLOT, P + L.pi2 + 56 * PIP, TC_PIRING_SLOT);
+                } else {
+                    load(bars, B_V2, WRING, P + L.v2, NV * 7 * 4 * 4);
+                }
+            }
+            __syncwarp();
+            {   // project epilogue: bias + residual; trunk output -> operand planes in place, head outputs -> plain [token][column] in ESTG
+                const int row = 32 * q + lane, c0 = 16 * sub;
+                uint32_t dh[16], dl[16];
+                tmem_ld16(tlane + TC_DP + c0, dh); tmem_ld16(tlane + TC_DP + 64 + c0, dl); tmem_wait_ld();
+                float* HO = reinterpret_cast<float*>(ESTG);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const int c = c0 + 4 * j4;
+                    if (c < NV) {
+                        const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
+                        const float4 rh = *reinterpret_cast<const float4*>(sm + TC_XH + o), rl = *reinterpret_cast<const float4*>(sm + TC_XL + o);
+                        const float res[4] = {rh.x + rl.x, rh.y + rl.y, rh.z + rl.z, rh.w + rl.w};
+                        float y[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) y[j] = __uint_as_float(dh[4 * j4 + j]) + __uint_as_float(dl[4 * j4 + j]) + SB[SV_BP + c + j] + res[j];
+                        if (b == 0) {
+                            float hi[4], lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) split_rn(y[j], hi[j], lo[j]);
+                            *reinterpret_cast<float4*>(sm + TC_XH + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<float4*>(sm + TC_XL + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) HO[(c + j) * LD + (row & 7) * TB + (row >> 3)] = y[j];   // [token][feature][leaf]
+                        }
+                    }
+                }
+            }
+            fence_async_smem(); tc_fence_before(); __syncthreads();
+            TC_STAMP();   /* b6: project epilogue done */
+
+            if (b == 1) {
+                // ---------------- policy head linears on CUDA cores: Linear(392 -> 81) + ReLU, Linear(81 -> 81), masked softmax ----------------
+                const float* X0 = reinterpret_cast<const float*>(ESTG);
+                float* H1 = reinterpret_cast<float*>(ESTG + 28672); float* LG = H1 + PIP * TB;
+                int ent = 0;
+                auto acquire = [&]() -> const float* {           // next ring entry (7 x pi2 chunk, 2 x pi4 part); barrier = previous entry fully consumed
+                    const int s = ent % 3;
+                    ph.wait(bars, B_PI0 + s);
+                    __syncthreads();
+                    if (t == 0 && ent + 2 < 9) {
+                        const int e = ent + 2, s2 = e % 3;
+                        const float* src = e < 7 ? P + L.pi2 + e * 56 * PIP : (e == 7 ? P + L.pi4 : P + L.pi4 + 41 * PIP);
+                        const uint32_t bytes = e < 7 ? TC_PIRING_SLOT : (e == 7 ? 41 * PIP * 4 : 40 * PIP * 4);
+                        load(bars, B_PI0 + s2, WRING + s2 * TC_PIRING_SLOT, src, bytes);
+                    }
+                    ent++;
+                    return reinterpret_cast<const float*>(WRING + s * TC_PIRING_SLOT);
+                };
+                // 504 tasks = 3 K-thirds x 21 output quads x 8 leaf pairs; partial sums meet in PP, summed in a fixed order
+                float* PP = reinterpret_cast<float*>(ESTG + 39424);   // [3][84][16]
+                const bool live = t < 504;
+                const int part = min(t / 168, 2), rem = t - part * 168, og = rem >> 3, lp = rem & 7;
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                for (int ch = 0; ch < NV / 8; ch++) {
+                    const float* W = acquire();
+                    if (live) {
+                        const int r0 = 19 * part, r1 = min(r0 + 19, 56);
+                        int il = r0 / 7, f = r0 - il * 7;
+#pragma unroll 4
+                        for (int rr = r0; rr < r1; rr++) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(W + rr * PIP + 4 * og);
+                            const float2 x = *reinterpret_cast<const float2*>(X0 + (8 * ch + il) * LD + f * TB + 2 * lp);
+                            acc[0][0] = fmaf(w4.x, x.x, acc[0][0]); acc[0][1] = fmaf(w4.y, x.x, acc[0][1]); acc[0][2] = fmaf(w4.z, x.x, acc[0][2]); acc[0][3] = fmaf(w4.w, x.x, acc[0][3]);
+                            acc[1][0] = fmaf(w4.x, x.y, acc[1][0]); acc[1][1] = fmaf(w4.y, x.y, acc[1][1]); acc[1][2] = fmaf(w4.z, x.y, acc[1][2]); acc[1][3] = fmaf(w4.w, x.y, acc[1][3]);
+                            if (++f == 7) { f = 0; il++; }
+                        }
+                    }
+                }
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) *reinterpret_cast<float2*>(PP + (part * PIP + 4 * og + j) * TB + 2 * lp) = make_float2(acc[0][j], acc[1][j]);
+                }
+                __syncthreads();
+                for (int i = t; i < PIP * TB; i += TC_THREADS) H1[i] = fmaxf(PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + SV[SV_BPI2 + (i >> 4)], 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[0][j] = acc[1][j] = 0.f;
+                for (int ch = 0; ch < 2; ch++) {
+                    const float* W = acquire();                   // first barrier: H1 complete (and PP consumed)
+                    if (live) {
+                        const int k0 = max(27 * part, 41 * ch), k1 = min(27 * part + 27, ch == 0 ? 41 : 81);
+#pragma unroll 4
+                        for (int k = k0; k < k1; k++) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(W + (k - 41 * ch) * PIP + 4 * og);
+                            const float2 x = *reinterpret_cast<const float2*>(H1 + k * TB + 2 * lp);
+                            acc[0][0] = fmaf(w4.x, x.x, acc[0][0]); acc[0][1] = fmaf(w4.y, x.x, acc[0][1]); acc[0][2] = fmaf(w4.z, x.x, acc[0][2]); acc[0][3] = fmaf(w4.w, x.x, acc[0][3]);
+                            acc[1][0] = fmaf(w4.x, x.y, acc[1][0]); acc[1][1] = fmaf(w4.y, x.y, acc[1][1]); acc[1][2] = fmaf(w4.z, x.y, acc[1][2]); acc[1][3] = fmaf(w4.w, x.y, acc[1][3]);
+                        }
+                    }
+                }
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) *reinterpret_cast<float2*>(PP + (part * PIP + 4 * og + j) * TB + 2 * lp) = make_float2(acc[0][j], acc[1][j]);
+                }
+                __syncthreads();
+                for (int i = t; i < PIP * TB; i += TC_THREADS) LG[i] = PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + SV[SV_BPI4 + (i >> 4)];
+                __syncthreads();
+                {   // masked softmax: where(valid, logits, -1e8) -> log_softmax -> exp (SplendorNNet.py:404,440; GenericNNetWrapper.py:119)
+                    const int sl = warp, slot = slot_of[sl];
+                    if (slot >= 0) {
+                        float l[3]; float mx = -INFINITY;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const int a = lane + 32 * k;
+                            const bool valid = a < A && (masks[(size_t)slot * 3 + k] >> lane & 1);
+                            l[k] = a < A ? (valid ? LG[a * TB + sl] : -1e8f) : -INFINITY;
+                            mx = fmaxf(mx, l[k]);
+                        }
+                        mx = warp_max_f32(mx);
+                        float sum = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) sum += expf(l[k] - mx);
+                        sum = warp_sum_f32(sum);
+                        const float lse = logf(sum);
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { const int a = lane + 32 * k; if (a < A) pi_out[(size_t)slot * A + a] = expf(l[k] - mx - lse); }
+                    }
+                }
+                __syncthreads();                                  // head activations and the ring are dead: value block's images
+                TC_STAMP();   /* b7 (b == 1 only): policy head done */
+                if (t == 0) {
+                    load(bars, B_WE, ESTG, IMGb + I.we[2], TC_WE_BYTES);
+                    load(bars, B_WP2, WRING + 32768, IMGb + I.wp[2], 16384);
+                    load(bars, B_WP3, WRING + 49152, IMGb + I.wp[2] + 4096, 16384);
+                }
+                __syncwarp();
+            }
+        }
+        // ---------------- value head: Linear(392 -> np) + ReLU, Linear(np -> np), tanh ----------------
+        {
+            const float* X0 = reinterpret_cast<const float*>(ESTG);
+            ph.wait(bars, B_V2);
+            __syncthreads();
+            const float* W = reinterpret_cast<const float*>(WRING);
+            if (t < 384) {
+                const int s = t & 15, kp = t >> 4;               // 24 token slices x 16 leaves
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int i = kp; i < NV; i += 24) {
+                    const float* xp = X0 + i * LD + s;
+#pragma unroll
+                    for (int f = 0; f < 7; f++) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(W + (i * 7 + f) * 4);
+                        const float x = xp[f * TB];
+                        a0 = fmaf(w4.x, x, a0); a1 = fmaf(w4.y, x, a1); a2 = fmaf(w4.z, x, a2); a3 = fmaf(w4.w, x, a3);
+                    }
+                }
+                float* VP = reinterpret_cast<float*>(ESTG + 28672);   // per-slice partial sums [24][4][16], summed in a fixed order below
+                VP[(kp * 4 + 0) * TB + s] = a0; VP[(kp * 4 + 1) * TB + s] = a1; VP[(kp * 4 + 2) * TB + s] = a2; VP[(kp * 4 + 3) * TB + s] = a3;
+            }
+            __syncthreads();
+            if (t < 4 * TB) {
+                const float* VP = reinterpret_cast<const float*>(ESTG + 28672);
+                float a = 0.f;
+                for (int kp = 0; kp < 24; kp++) a += VP[kp * 4 * TB + t];
+                VH[t] = a;
+            }
+            __syncthreads();
+            if (t < NP * TB) {
+                const int o = t / TB, sl = t - o * TB, slot = slot_of[sl];
+                float a = SV[SV_BV4 + o];
+#pragma unroll
+                for (int i = 0; i < NP; i++) a = fmaf(SV[SV_V4 + o * 4 + i], fmaxf(VH[i * TB + sl] + SV[SV_BV2 + i], 0.f), a);
+                if (slot >= 0) v_out[(size_t)slot * NP + o] = tanhf(a);
+            }
+        }
+        __syncthreads();                                          // tile done: every shared region may be reused
+        TC_STAMP();   /* tile end */
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+}  // namespace azg

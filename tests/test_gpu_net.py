@@ -51,3 +51,27 @@ def test_hashnet_bit_exact(game, kat):
     for i in range(len(b)):
         p2, v2 = hashnet_eval(b[i], va[i])
         assert (pi[i] == p2).all() and (v[i] == v2).all()
+
+
+def test_v80_tensor_core_kernel_large_batch(game, v80_golden, kat, monkeypatch):
+    """The tcgen05 (3xTF32) kernel against the fp32 CUDA-core kernel and the oracle on a batch that gives every persistent
+    CTA several tiles (5000 leaves = 313 tiles > 148 SMs) with a ragged last tile; both weight sets."""
+    reps = 9
+    b = np.concatenate([kat['canonical']] * reps)[:5000]; va = np.concatenate([kat['valids']] * reps)[:5000]
+    for tag in ('rand', 'shipped'):
+        sd = v80_golden[tag]['sd']
+        monkeypatch.delenv('AZG_V80_KERNEL', raising=False)
+        net_tc = NNetWrapper(game, {'nn_version': 80}, state_dict=sd)
+        monkeypatch.setenv('AZG_V80_KERNEL', 'fp32')
+        net_f32 = NNetWrapper(game, {'nn_version': 80}, state_dict=sd)
+        monkeypatch.delenv('AZG_V80_KERNEL', raising=False)
+        pi, v = net_tc.predict_batch(b, va)
+        pi2, v2 = net_f32.predict_batch(b, va)
+        np.testing.assert_allclose(pi, pi2, rtol=0, atol=TOL)
+        np.testing.assert_allclose(v, v2, rtol=0, atol=TOL)
+        # identical boards in different tiles / CTAs give identical results (no cross-tile state)
+        n0 = len(kat['canonical'])
+        assert (pi[:n0] == pi[n0:2 * n0]).all() and (v[:n0] == v[n0:2 * n0]).all()
+        opi, ov = O.v80_forward(O.v80_blob(sd), b[:64], va[:64])
+        np.testing.assert_allclose(pi[:64], opi, rtol=0, atol=TOL)
+        np.testing.assert_allclose(v[:64], ov, rtol=0, atol=TOL)
