@@ -518,7 +518,7 @@ struct EngineT : azg_engine {
         if (node_cap <= 0) {
             // default: room for the nodes that survive tree reuse, bounded by 60 % of free HBM
             size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-            const double per_node = 48.0 + G::SP + 8.0 + EDGE_FACTOR * (17.0 + 4.0 * U0) + 2 * 8.0;
+            const double per_node = 48.0 + G::SP + 8.0 + 4.0 * U0 + EDGE_FACTOR * (17.0 + 4.0 * U0) + 2 * 8.0;
             double fit = 0.6 * (double)free_b / (double)NG / per_node;
             node_cap = (int)std::min<double>(fit, 16.0 * c->numMCTSSims + 1024);
             node_cap = std::max(node_cap, c->numMCTSSims + 64);
@@ -536,6 +536,7 @@ struct EngineT : azg_engine {
         bad |= alloc(&d.acts, (size_t)NG * edge_cap, false); bad |= alloc(&d.ht, (size_t)NG * d.ht_cap);
         bad |= alloc(&d.n_nodes, NG); bad |= alloc(&d.n_edges, NG);
         bad |= alloc(&d.child, (size_t)NG * edge_cap * d.U, false); bad |= alloc(&d.boards, (size_t)NG * node_cap * G::SP, false);
+        bad |= alloc(&d.bestlink, (size_t)NG * node_cap * d.U, false);
         bad |= alloc(&d.remap, (size_t)NG * node_cap, false); bad |= alloc(&d.gcq, (size_t)NG * node_cap, false); bad |= alloc(&d.root_node, NG); bad |= alloc(&d.leaf_link, NG);
         bad |= alloc(&d.root, (size_t)NG * G::SP); bad |= alloc(&d.n_sims, NG); bad |= alloc(&d.full, NG); bad |= alloc(&d.move_ctr, NG);
         bad |= alloc(&d.path, (size_t)NG * G::MAX_DEPTH); bad |= alloc(&d.path_len, NG); bad |= alloc(&d.leaf_kind, NG);
@@ -632,9 +633,9 @@ struct EngineT : azg_engine {
         std::vector<unsigned long long> h((size_t)NG * ST_N);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(h.data(), d.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < 16; k++) out16[k] = 0;
+        for (int k = 0; k < AZG_N_STATS; k++) out16[k] = 0;
         for (int g = 0; g < NG; g++)
-            for (int k = 0; k < ST_N; k++) {
+            for (int k = 0; k < ST_N && k < AZG_N_STATS; k++) {
                 if (k == ST_MAXNODES) out16[k] = std::max<int64_t>(out16[k], (int64_t)h[(size_t)g * ST_N + k]);
                 else out16[k] += (int64_t)h[(size_t)g * ST_N + k];
             }

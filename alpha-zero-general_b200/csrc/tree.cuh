@@ -18,7 +18,8 @@
 // PUCT with explicit round-to-nearest intrinsics so nvcc cannot contract or reassociate them.
 //
 // HBM layout per game g (arena sizes are engine parameters):
-//   nodes [node_cap] NodeHdr 32 B : cpuct*sqrt(Ns), cpuct*sqrt(Ns+1e-8), Ns, Qs, edge_off, n_legal, round, kind
+//   nodes [node_cap] NodeHdr 32 B : cpuct*sqrt(Ns), Ns, Qs, edge_off, n_legal, round, kind, best (cached PUCT choice)
+//   bestlink[node_cap][U] u32     : child link of the node's best edge per universe (what a non-root visit follows)
 //   keys  [node_cap] NodeKey 16 B : 128-bit board hash
 //   edges [edge_cap] Edge    16 B : {Q f64, P f32, N i32} for LEGAL actions only, ascending action index
 //   acts  [edge_cap] act_t        : action id of each edge
@@ -32,18 +33,20 @@ namespace azg {
 
 struct __align__(16) Edge { double q; float p; int n; };
 struct __align__(16) NodeHdr {
-    double c1, c0;                                             // cpuct*sqrt(Ns), cpuct*sqrt(Ns+1e-8): PUCT constants, refreshed by the backup
+    double c1;                                                 // cpuct*sqrt(Ns): PUCT constant, refreshed by the backup
     int ns; float qs;
     uint32_t edge_off; uint16_t n_legal; uint8_t round; uint8_t kind;
-};
+    uint16_t best; uint16_t rsv0; uint32_t rsv1;               // best: edge (index within the node) the next non-root visit takes; refreshed
+};                                                             //       by the backup whenever the node's statistics change
 struct __align__(16) NodeKey { uint64_t lo, hi; };             // 128-bit board hash of the node (hash-table verification, GC)
 static_assert(sizeof(Edge) == 16 && sizeof(NodeHdr) == 32 && sizeof(NodeKey) == 16, "layout");
-struct PathEnt { uint32_t node; uint32_t edge_np; };          // edge index (24 bits) | next_player << 24
+struct __align__(16) PathEnt { uint32_t node; uint32_t edge_np; uint32_t edge_off; uint32_t n_legal; };   // edge_np: edge index (24 bits) | next_player << 24;
+                                                                // edge_off / n_legal of `node` ride along so that the backup can prefetch its edge block at once
 
 enum { NODE_EXPANDED = 0, NODE_TERMINAL = 1 };
 enum { LEAF_NONE = 0, LEAF_EXPAND = 1, LEAF_NEW_TERMINAL = 2, LEAF_OLD_TERMINAL = 3 };
 enum { ST_SIMS = 0, ST_VISITS, ST_EXPANSIONS, ST_NNEVALS, ST_TERMINAL, ST_OVERFLOW, ST_GC, ST_MAXNODES, ST_SUMLEGAL,
-       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_GC_SWEEP = 13, ST_SELLEGAL = 15, ST_N = 16 };
+       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_GC_SWEEP = 13, ST_SELLEGAL = 15, ST_ROOTLEGAL = 16, ST_REFLEGAL = 17, ST_N = 20 };
 
 constexpr double kNanQ = -42.0;                                // MCTS.py:11
 __constant__ long long kMagicSeeds[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   // MCTS.py:14
@@ -58,6 +61,7 @@ struct Dev {
     // trees
     NodeHdr* nodes; NodeKey* keys; Edge* edges; typename G::act_t* acts; uint64_t* ht; int* n_nodes; int* n_edges;
     uint32_t* child; int8_t* boards; int* remap; int* gcq;     // remap, gcq: [G][node_cap] scratch of the tree GC
+    uint32_t* bestlink;                                        // [G][node_cap][U] child link of every node's cached best edge
     int* root_node;                                            // [G] root node index + 1 once known for this search, else 0
     uint32_t* leaf_link;                                       // [G] child-link slot (index into child, +1) the new leaf hangs on; 0 = root
     // search control (per game)
@@ -78,6 +82,7 @@ struct Dev {
     __device__ __forceinline__ uint64_t* g_ht(int g) const { return ht + (size_t)g * ht_cap; }
     __device__ __forceinline__ uint32_t* g_child(int g) const { return child + (size_t)g * edge_cap * U; }
     __device__ __forceinline__ int8_t* g_boards(int g) const { return boards + (size_t)g * node_cap * G::SP; }
+    __device__ __forceinline__ uint32_t* g_best(int g) const { return bestlink + (size_t)g * node_cap * U; }
 };
 constexpr uint32_t LINK_IDX = 0x0FFFFFFFu;                      // child link: low 28 bits = node index + 1, high 4 = next player
 
@@ -232,6 +237,91 @@ __device__ __forceinline__ int puct_select(const Edge* e, const uint32_t* child,
     return win;
 }
 
+// Bulk L2 prefetch of [p, p + bytes): one instruction per block (a plain prefetch.global.L2 only pulls one 32 B sector)
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
+    const uint32_t n = (uint32_t)((reinterpret_cast<uintptr_t>(p) + bytes - a + 15) & ~(uintptr_t)15);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+}
+// cpuct*sqrt(Ns + 1e-8): pick_highest_UCB's constant for unvisited edges (MCTS.py:226), computed where it is needed
+__device__ __forceinline__ double puct_c0(double cpuct, int ns) { return __dmul_rn(cpuct, __dsqrt_rn(__dadd_rn((double)ns, 1e-8))); }
+__device__ __forceinline__ uint32_t f32_order_key(float x) { const uint32_t b = __float_as_uint(x); return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u); }
+
+// pick_highest_UCB (MCTS.py:210-230, no forced playouts: every non-root call, MCTS.py:175) for the NEXT visit of a node whose
+// statistics just changed. Same exact f64 arithmetic and first-index tie-break as puct_select, but behind an f32 pre-filter with a
+// rigorous bound: u32 = f32 evaluation, |u32 - u| <= tol = (|q| + |explore|) * 2^-18 (five f32 roundings + a 2-ulp division are
+// < 2^-21 relative); an edge can only be the exact argmax, or tie with it, if u32 + tol >= max_j (u32_j - tol_j). Usually one edge
+// survives and no f64 division is executed at all.
+__device__ __forceinline__ float puct_bounds(const Edge& ed, float c1f, float c0f, float fif, float& ub) {
+    const bool vis = ed.q != kNanQ;
+    const float base = vis ? (float)ed.q : fif;
+    const float tt = vis ? __fdividef(c1f * ed.p, (float)(ed.n + 1)) : c0f * ed.p;
+    const float tol = (fabsf(base) + fabsf(tt)) * 0x1p-18f + 1e-30f;
+    ub = base + tt + tol;
+    return base + tt - tol;
+}
+__device__ __forceinline__ double puct_exact(const Edge& ed, double c1, double c0, double fpu_init) {
+    const double pd = (double)ed.p;
+    return ed.q != kNanQ ? __dadd_rn(ed.q, __ddiv_rn(__dmul_rn(c1, pd), (double)(ed.n + 1))) : __fma_rn(c0, pd, fpu_init);
+}
+__device__ __forceinline__ int best_edge(const Edge* e, int L, double c1, double cpuct, int ns, float qs, double fpu, int lane) {
+    const double fpu_init = fpu > 0 ? __dsub_rn((double)qs, fpu) : fpu;
+    const float c1f = (float)c1, c0f = (float)cpuct * sqrtf((float)ns + 1e-8f), fif = (float)fpu_init;
+    // up to two edges per lane stay in registers (every Splendor node: L <= 64); longer edge lists are streamed
+    const bool h0 = lane < L, h1 = lane + 32 < L;
+    Edge e0, e1; e0.q = kNanQ; e0.p = 0.f; e0.n = 0; e1 = e0;
+    if (h0) e0 = e[lane];
+    if (h1) e1 = e[lane + 32];
+    float ub0 = -INFINITY, ub1 = -INFINITY, lb = -INFINITY;
+    if (h0) lb = puct_bounds(e0, c1f, c0f, fif, ub0);
+    if (h1) lb = fmaxf(lb, puct_bounds(e1, c1f, c0f, fif, ub1));
+    for (int i = lane + 64; i < L; i += 32) { float ub; lb = fmaxf(lb, puct_bounds(e[i], c1f, c0f, fif, ub)); }
+    const uint32_t mk = __reduce_max_sync(FULL, f32_order_key(lb));
+    const unsigned m0 = __ballot_sync(FULL, h0 && f32_order_key(ub0) >= mk), m1 = __ballot_sync(FULL, h1 && f32_order_key(ub1) >= mk);
+    if (L <= 64 && __popc(m0) + __popc(m1) == 1) return m0 ? __ffs(m0) - 1 : 31 + __ffs(m1);
+    // several candidates (exact ties among equal priors, near ties) or a long edge list: exact evaluation of the candidates only
+    const double c0 = puct_c0(cpuct, ns);
+    double best = -INFINITY; int best_i = 0x7FFFFFFF;
+    if (m0 >> lane & 1) { best = puct_exact(e0, c1, c0, fpu_init); best_i = lane; }
+    if (m1 >> lane & 1) { const double u = puct_exact(e1, c1, c0, fpu_init); if (u > best) { best = u; best_i = lane + 32; } }
+    for (int i = lane + 64; i < L; i += 32) {
+        const Edge ed = e[i]; float ub; puct_bounds(ed, c1f, c0f, fif, ub);
+        if (f32_order_key(ub) >= mk) { const double u = puct_exact(ed, c1, c0, fpu_init); if (u > best) { best = u; best_i = i; } }
+    }
+    const uint64_t key = f64_order_key(best);
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mh = __reduce_max_sync(FULL, best_i != 0x7FFFFFFF ? hi : 0u);
+    const bool ch = hi == mh && best_i != 0x7FFFFFFF;
+    const uint32_t ml = __reduce_max_sync(FULL, ch ? lo : 0u);
+    return __reduce_min_sync(FULL, (ch && lo == ml) ? best_i : 0x7FFFFFFF);
+}
+
+// The same choice computed by ONE thread over its own node (the backup refreshes every level of a path at once, one lane per
+// level: 12 independent edge streams per warp instead of one). Single pass: the edge with the largest lower bound, and the two
+// largest upper bounds; if no other edge's upper bound reaches that lower bound the choice is certain, else the candidates are
+// evaluated exactly.
+__device__ __forceinline__ int best_edge_lane(const Edge* e, int L, double c1, double cpuct, int ns, float qs, double fpu) {
+    const double fpu_init = fpu > 0 ? __dsub_rn((double)qs, fpu) : fpu;
+    const float c1f = (float)c1, c0f = (float)cpuct * sqrtf((float)ns + 1e-8f), fif = (float)fpu_init;
+    float lbm = -INFINITY, u1 = -INFINITY, u2 = -INFINITY; int im = 0, i1 = -1;
+#pragma unroll 4
+    for (int i = 0; i < L; i++) {
+        const Edge ed = e[i];
+        float ub; const float lb = puct_bounds(ed, c1f, c0f, fif, ub);
+        if (lb > lbm) { lbm = lb; im = i; }
+        if (ub > u1) { u2 = u1; u1 = ub; i1 = i; } else if (ub > u2) u2 = ub;
+    }
+    if (i1 == im && u2 < lbm) return im;
+    const double c0 = puct_c0(cpuct, ns);
+    double best = -INFINITY; int bi = im;
+    for (int i = 0; i < L; i++) {
+        const Edge ed = e[i];
+        float ub; puct_bounds(ed, c1f, c0f, fif, ub);
+        if (ub >= lbm) { const double u = puct_exact(ed, c1, c0, fpu_init); if (u > best) { best = u; bi = i; } }
+    }
+    return bi;
+}
+
 // k_select runs ONE warp (= one game) per CTA so that an SM slot is recycled as soon as its game's walk ends
 // (walk lengths differ a lot between games); 64 registers/thread -> 32 resident CTAs = 32 games per SM.
 #ifndef AZG_SELK_WARPS
@@ -341,28 +431,32 @@ __global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(
     const bool forced_root = full && d.forced_playouts;
     const bool noise_now = step == 0 && full && d.dirichlet_noise;
     const int uni = d.universes > 0 ? step % d.universes : 0;
-    const NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); uint32_t* child = d.g_child(g);
+    const NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); uint32_t* child = d.g_child(g); uint32_t* bestlink = d.g_best(g);
     PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
-    int depth = 0, kind = LEAF_NONE, sum_legal = 0;
+    int depth = 0, kind = LEAF_NONE, sum_legal = 0, root_legal = 0;
     uint32_t link_slot = 0;                                      // child-link slot (+1) a new leaf hangs on; 0 = it is the root
     bool at_new = false;                                         // ws.board holds a state that is not in the tree yet
     int idx = d.root_node[g] - 1;
     if (idx < 0) { idx = locate_root<G>(d, g, sm[w], lane); at_new = idx < 0; }
     while (!at_new) {
-        const NodeHdr h = nodes[idx];
+        const NodeHdr h = nodes[idx];                            // one round trip per level: 32 B header + the 4 B link of its cached best edge
+        uint32_t link = bestlink[(size_t)idx * d.U + uni];
         if (h.kind == NODE_TERMINAL) {                           // MCTS.py:136-138
             kind = LEAF_OLD_TERMINAL;
             if (lane == 0) { const float* es = reinterpret_cast<const float*>(edges + h.edge_off); for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p]; }
             break;
         }
-        if (depth == 0 && noise_now) renoise_root<G>(d, g, h.edge_off, (int)h.n_legal, edges, d.g_acts(g), sm[w], lane);
-        uint32_t link;
-        const int e = puct_select(edges + h.edge_off, child + (size_t)h.edge_off * d.U, d.U, uni, h.n_legal, h.c1, h.c0, h.qs, d.fpu,
-                                  depth == 0 && forced_root, step, lane, link);
+        int e = h.best;
+        if (depth == 0) {                                        // the root is scanned in full: forced playouts, fresh Dirichlet noise, tree reuse
+            if (noise_now) renoise_root<G>(d, g, h.edge_off, (int)h.n_legal, edges, d.g_acts(g), sm[w], lane);
+            e = puct_select(edges + h.edge_off, child + (size_t)h.edge_off * d.U, d.U, uni, h.n_legal, h.c1, puct_c0(d.cpuct, h.ns), h.qs, d.fpu,
+                            forced_root, step, lane, link);
+            root_legal = h.n_legal;
+        }
         sum_legal += h.n_legal;
         const uint32_t eidx = h.edge_off + (uint32_t)e;
         if (link != 0) {                                         // resolved before: pure pointer walk
-            if (lane == 0) { path[depth].node = (uint32_t)idx; path[depth].edge_np = eidx | ((link >> 28) << 24); }
+            if (lane == 0) { PathEnt pe; pe.node = (uint32_t)idx; pe.edge_np = eidx | ((link >> 28) << 24); pe.edge_off = h.edge_off; pe.n_legal = h.n_legal; path[depth] = pe; }
             idx = (int)(link & LINK_IDX) - 1;
             if (++depth >= G::MAX_DEPTH) break;
             continue;
@@ -370,24 +464,25 @@ __global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(
         const long long seed = d.universes > 0 ? kMagicSeeds[uni] : -1;
         const int found = materialise_child<G>(d, g, sm[w], idx, d.g_acts(g)[eidx], seed, lane);
         const uint32_t np = (uint32_t)sm[w].np;
-        if (lane == 0) { path[depth].node = (uint32_t)idx; path[depth].edge_np = eidx | (np << 24); }
-        depth++;
+        if (lane == 0) { PathEnt pe; pe.node = (uint32_t)idx; pe.edge_np = eidx | (np << 24); pe.edge_off = h.edge_off; pe.n_legal = h.n_legal; path[depth] = pe; }
         const size_t slot = (size_t)eidx * d.U + uni;
         if (found >= 0) {                                        // transposition, or the same child under another universe
-            if (lane == 0) child[slot] = (uint32_t)(found + 1) | (np << 28);
+            if (lane == 0) { child[slot] = (uint32_t)(found + 1) | (np << 28); if (depth > 0) bestlink[(size_t)idx * d.U + uni] = (uint32_t)(found + 1) | (np << 28); }
+            depth++;
             idx = found;
             if (depth >= G::MAX_DEPTH) break;
             continue;
         }
+        depth++;
         link_slot = (uint32_t)slot + 1u; at_new = true;
     }
     if (at_new) kind = new_leaf<G>(d, g, sm[w], link_slot, lane);
-    if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; }
+    if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; d.stats[(size_t)g * ST_N + ST_ROOTLEGAL] += (unsigned)root_legal; }
 }
 
 // ============================================================ expand + backup =========================
 template <class G>
-__global__ void __launch_bounds__(sel_warps<G>() * 32) k_backup(const __grid_constant__ Dev<G> d, int step) {
+__global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_backup(const __grid_constant__ Dev<G> d, int step) {
     __shared__ WarpSmem<G> sm[sel_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;    // leaf list consumed by the net; reset for the next step
@@ -398,6 +493,12 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_backup(const __grid_con
     const int depth = d.path_len[g];
     NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
     unsigned long long* st = d.stats + (size_t)g * ST_N;
+    if (lane >= 1 && lane < depth) {                             // levels 1..31 of the path: pull the edge blocks and links that the refresh
+        const PathEnt pp = d.path[(size_t)g * G::MAX_DEPTH + lane];   // below scans towards L2 now, while the expansion runs
+        if (pp.n_legal) {
+            l2_prefetch(edges + pp.edge_off, pp.n_legal * 16u);
+        }
+    }
     float v[NP];
     if (kind == LEAF_EXPAND) {
         float* pf = sm[w].f;
@@ -435,12 +536,15 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_backup(const __grid_con
             }
             const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
             const uint32_t ls = d.leaf_link[g];
+            __syncwarp();                                        // the new edges are visible to the whole warp
+            const int nb = best_edge(edges + eo, L, 0.0, d.cpuct, 0, v[0], d.fpu, lane);      // first visit's choice (all edges unvisited)
+            if (lane < d.U) d.g_best(g)[(size_t)ni * d.U + lane] = 0;
             if (lane == 0) {
                 if (ls) child[ls - 1] = (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28);
                 else d.root_node[g] = ni + 1;
                 NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
-                NodeHdr h; h.c1 = 0.0; h.c0 = __dmul_rn(d.cpuct, __dsqrt_rn(1e-8)); h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
-                h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_EXPANDED;
+                NodeHdr h; h.c1 = 0.0; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
+                h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_EXPANDED; h.best = (uint16_t)nb; h.rsv0 = 0; h.rsv1 = 0;
                 nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + L;
                 st[ST_EXPANSIONS]++; st[ST_NNEVALS]++; st[ST_SUMLEGAL] += (unsigned)L;
                 if ((unsigned long long)(ni + 1) > st[ST_MAXNODES]) st[ST_MAXNODES] = (unsigned long long)(ni + 1);
@@ -462,8 +566,8 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_backup(const __grid_con
                     float* es = reinterpret_cast<float*>(edges + eo);
                     for (int p = 0; p < 4; p++) es[p] = p < NP ? v[p] : 0.f;
                     NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
-                    NodeHdr h; h.c1 = 0.0; h.c0 = 0.0; h.ns = 0; h.qs = 0.f; h.edge_off = (uint32_t)eo; h.n_legal = 0;
-                    h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_TERMINAL;
+                    NodeHdr h; h.c1 = 0.0; h.ns = 0; h.qs = 0.f; h.edge_off = (uint32_t)eo; h.n_legal = 0;
+                    h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_TERMINAL; h.best = 0; h.rsv0 = 0; h.rsv1 = 0;
                     nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + 1;
                 }
                 ht_insert(d.g_ht(g), d.ht_cap, klo, khi, ni, lane);
@@ -474,7 +578,8 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_backup(const __grid_con
     // ---- backup (MCTS.py:176-181), lanes parallel over levels; a path never visits a node twice (the round
     //      counter in the key increases with every move) so the updates are independent.
     const PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
-    int carry = 0;                                               // rotation accumulated from deeper chunks
+    uint32_t* child = d.g_child(g); uint32_t* bestlink = d.g_best(g);
+    int carry = 0, ref_legal = 0;                                // rotation accumulated from deeper chunks
     for (int base = ((depth - 1) / 32) * 32; base >= 0 && depth > 0; base -= 32) {
         const int lvl = base + lane;
         PathEnt pe; pe.node = 0; pe.edge_np = 0;
@@ -484,20 +589,35 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_backup(const __grid_con
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_down_sync(FULL, suf, o); if (lane + o < 32) suf += t; }
         const int rot = (suf + carry) % NP;                      // v_lvl = roll(v_leaf, rot)
+        NodeHdr hn; hn.c1 = 0.0; hn.ns = 0; hn.qs = 0.f; hn.edge_off = 0; hn.n_legal = 0; hn.kind = NODE_TERMINAL;
         if (lvl < depth) {
             const float v0 = v[(NP - rot) % NP];
             Edge* ed = edges + (pe.edge_np & 0xFFFFFFu);
             NodeHdr* nh = nodes + pe.node;
-            Edge x = *ed; int ns = nh->ns; float qs = nh->qs;
+            Edge x = *ed; hn = *nh;
             x.q = __ddiv_rn(__dadd_rn(__dmul_rn((double)x.n, x.q), (double)v0), (double)(x.n + 1));
             x.n += 1;
-            qs = __fdiv_rn(__fadd_rn(__fmul_rn((float)(ns + 1), qs), v0), (float)(ns + 2));
-            *ed = x; nh->ns = ns + 1; nh->qs = qs;
-            nh->c1 = __dmul_rn(d.cpuct, __dsqrt_rn((double)(ns + 1)));              // pick_highest_UCB's sqrt(Ns) terms, MCTS.py:224-226
-            nh->c0 = __dmul_rn(d.cpuct, __dsqrt_rn(__dadd_rn((double)(ns + 1), 1e-8)));
+            hn.qs = __fdiv_rn(__fadd_rn(__fmul_rn((float)(hn.ns + 1), hn.qs), v0), (float)(hn.ns + 2));
+            hn.ns += 1;
+            hn.c1 = __dmul_rn(d.cpuct, __dsqrt_rn((double)hn.ns));                  // pick_highest_UCB's sqrt(Ns) term, MCTS.py:224-226
+            *ed = x; *reinterpret_cast<uint4*>(nh) = *reinterpret_cast<const uint4*>(&hn);     // {c1, ns, qs}: first 16 bytes of the header
+            if (base > 0) {                                      // deep paths: levels >= 32 were not covered by the prefetch at the top
+                if (pe.n_legal) l2_prefetch(edges + pe.edge_off, pe.n_legal * 16u);
+            }
         }
         carry = (carry + __shfl_sync(FULL, suf, 0)) % NP;
+        // ---- refresh the cached PUCT choice of every updated non-root node (what the next visit will follow), one lane per level:
+        //      each lane streams the edge list of its own node (the only edge that changed is the one it just wrote itself). The
+        //      root is always scanned in full by k_select and is skipped here.
+        if (lvl > 0 && lvl < depth && hn.kind == NODE_EXPANDED && pe.n_legal > 0) {
+            const int nb = best_edge_lane(edges + pe.edge_off, (int)pe.n_legal, hn.c1, d.cpuct, hn.ns, hn.qs, d.fpu);
+            nodes[pe.node].best = (uint16_t)nb;
+            for (int u = 0; u < d.U; u++) bestlink[(size_t)pe.node * d.U + u] = child[(size_t)(pe.edge_off + nb) * d.U + u];
+            ref_legal += (int)pe.n_legal;
+        }
     }
+    ref_legal = warp_sum_i32(ref_legal);
+    if (lane == 0) st[ST_REFLEGAL] += (unsigned)ref_legal;
     if (lane == 0) { st[ST_SIMS]++; st[ST_VISITS] += (unsigned)depth; }
 }
 
@@ -613,7 +733,7 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_n
     int wn = 0, we = 0;                                          // write cursors
     for (int base = 0; base < nn; base += 32) {
         const int i = base + lane;
-        NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.c0 = h.c1 = 0; h.ns = 0; h.qs = 0;
+        NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.c1 = 0; h.ns = 0; h.qs = 0; h.best = 0; h.rsv0 = 0; h.rsv1 = 0;
         NodeKey nk; nk.lo = nk.hi = 0;
         bool keep = false;
         if (i < nn) { h = nodes[i]; nk = keys[i]; keep = sweep ? remap[i] == -1 : ((int)h.round > r || (nk.lo == klo && nk.hi == khi)); }
@@ -668,6 +788,13 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_n
     for (size_t k = lane; k < (size_t)we * U; k += 32) {
         const uint32_t c = child[k];
         if (c) { const int m = remap[(int)(c & LINK_IDX) - 1]; child[k] = m ? ((uint32_t)m | (c & ~LINK_IDX)) : 0u; }
+    }
+    {   // cached best-edge links follow the remapped child links
+        uint32_t* bestlink = d.g_best(g);
+        for (int i = lane; i < wn; i += 32) {
+            const NodeHdr h = nodes[i];
+            for (int u = 0; u < U; u++) bestlink[(size_t)i * U + u] = h.kind == NODE_TERMINAL ? 0u : child[((size_t)h.edge_off + h.best) * U + u];
+        }
     }
     for (int s = lane; s < d.ht_cap; s += 32) ht[s] = 0;
     __threadfence_block(); __syncwarp();

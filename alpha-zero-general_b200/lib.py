@@ -12,7 +12,8 @@ SO_PATH = os.path.join(CSRC, 'libazg_b200.so')
 AZG_GAME_SPLENDOR = 1
 AZG_GAME_SANTORINI = 2
 AZG_GAME_ABALONE = 3
-AZG_ABI_VERSION = 2
+AZG_ABI_VERSION = 3
+AZG_N_STATS = 20
 AZG_NET_HASH = 0
 AZG_NET_SPLENDOR_V80 = 80
 AZG_NET_SANTORINI_V89 = 89
@@ -123,4 +124,4 @@ def game_info(game_id=AZG_GAME_SPLENDOR, num_players=2):
 
 STAT_NAMES = ['sims', 'node_visits', 'expansions', 'nn_evals', 'terminal_hits', 'arena_overflows', 'gc_runs', 'max_nodes',
               'sum_legal', 'moves_played', 'episodes_finished', 'examples_recorded', 'kernels_launched', 'gc_sweeps', 'node_cap',
-              'sum_legal_visited']
+              'sum_legal_visited', 'sum_legal_root_scans', 'sum_legal_refreshed', 'reserved18', 'reserved19']

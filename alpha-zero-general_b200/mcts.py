@@ -82,7 +82,7 @@ class Engine:
         return b[:m].reshape((m,) + self.game.getBoardSize()), pi[:m], z[:m], va[:m].astype(np.bool_), q[:m]
 
     def stats(self):
-        out = np.zeros(16, np.int64)
+        out = np.zeros(_lib.AZG_N_STATS, np.int64)
         _lib.check(self._L.azg_engine_stats(self.h, _lib.ptr(out)))
         return dict(zip(_lib.STAT_NAMES, out.tolist()))
 

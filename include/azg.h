@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define AZG_ABI_VERSION 2
+#define AZG_ABI_VERSION 3
+#define AZG_N_STATS 20                                  /* entries azg_engine_stats writes */
 
 enum { AZG_GAME_SPLENDOR = 1,                            /* GameSwitcher.py:3-13 ('splendor'), 2 players            */
        AZG_GAME_SANTORINI = 2,                           /* 'santorini' built with NB_GODS = 1 (SantoriniConstants.py:19) */
@@ -138,8 +139,10 @@ int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float
 /* Counters since creation: [0] sims [1] node_visits (select steps) [2] expansions (nodes with priors)
  * [3] nn_evals [4] terminal_hits [5] arena_overflows [6] gc_runs [7] max_nodes_in_a_tree
  * [8] sum_legal (over expansions) [9] moves_played [10] episodes_finished [11] examples_recorded
- * [12] kernels_launched [13] gc_sweeps (tier-2 reachability GCs, see tree.cuh) [14] node_cap [15] sum_legal_visited (sum of n_legal over select steps) */
-int azg_engine_stats(azg_engine* e, int64_t* out16);
+ * [12] kernels_launched [13] gc_sweeps (tier-2 reachability GCs, see tree.cuh) [14] node_cap [15] sum_legal_visited (sum of n_legal over select steps)
+ * [16] sum_legal_root_scans (edges scanned by k_select at the roots) [17] sum_legal_refreshed (edges scanned by k_backup when it
+ * refreshes the cached PUCT choice of the nodes on the path) [18..19] reserved.  out must hold AZG_N_STATS int64. */
+int azg_engine_stats(azg_engine* e, int64_t* out_stats);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch of the search loop).
  * enable=1 starts collecting (slows the loop down slightly: use a separate measuring pass), enable=0 stops.
