@@ -290,34 +290,52 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             TC_STAMP();   /* b3: fc weights landed */
             {
                 const float* W1 = reinterpret_cast<const float*>(ESTG); const float* W2 = reinterpret_cast<const float*>(ESTG + 26880);
-                float* HP = reinterpret_cast<float*>(ESTG + 53760);             // K-split partial sums [3][40][16]
-                if (t < 480) {
-                    const int part = t / 160, tt = t - part * 160, qg = tt >> 4, s = tt & 15;
-                    float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-                    for (int kk = 56 * part; kk < 56 * part + 56; kk++) {
+                // Register-tiled (shared-memory bandwidth is the limit: one LDS.128 costs four cycles of the SM's load path whatever
+                // it broadcasts): a thread owns 4 outputs x 4 leaves, 16 FMA per pair of 128-bit loads.
+                float* HP = reinterpret_cast<float*>(ESTG + 53760);             // fc1 K-split partial sums [4][40][16]
+                if (t < 160) {
+                    const int part = t / 40, rem = t - part * 40, qg = rem >> 2, lq = rem & 3;
+                    float a[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
+#pragma unroll 6
+                    for (int kk = 42 * part; kk < 42 * part + 42; kk++) {
                         const float4 w4 = *reinterpret_cast<const float4*>(W1 + kk * Q + 4 * qg);
-                        const float x = SQ[kk * TB + s];
-                        a[0] = fmaf(w4.x, x, a[0]); a[1] = fmaf(w4.y, x, a[1]); a[2] = fmaf(w4.z, x, a[2]); a[3] = fmaf(w4.w, x, a[3]);
+                        const float4 x4 = *reinterpret_cast<const float4*>(SQ + kk * TB + 4 * lq);
+                        const float w[4] = {w4.x, w4.y, w4.z, w4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) a[i][j] = fmaf(w[i], x[j], a[i][j]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) HP[part * 640 + (4 * qg + j) * TB + s] = a[j];
+                    for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(HP + part * 640 + (4 * qg + i) * TB + 4 * lq) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
                 }
                 __syncthreads();
-                for (int i = t; i < Q * TB; i += TC_THREADS) HID[i] = fmaxf(HP[i] + HP[640 + i] + HP[1280 + i] + SB[SV_B1 + (i >> 4)], 0.f);
+                for (int i = t; i < Q * TB; i += TC_THREADS) HID[i] = fmaxf(HP[i] + HP[640 + i] + HP[1280 + i] + HP[1920 + i] + SB[SV_B1 + (i >> 4)], 0.f);
                 __syncthreads();
-#pragma unroll 1
-                for (int task = t; task < (EC / 4) * TB; task += TC_THREADS) {
-                    const int cq = task >> 4, s = task & 15;
-                    float g[4] = {0.f, 0.f, 0.f, 0.f};
+                if (t < (EC / 4) * 4) {                            // 42 channel quads x 4 leaf quads
+                    const int cq = t >> 2, lq = t & 3;
+                    float g[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) g[i][0] = g[i][1] = g[i][2] = g[i][3] = 0.f;
 #pragma unroll 8
                     for (int kk = 0; kk < Q; kk++) {
                         const float4 w4 = *reinterpret_cast<const float4*>(W2 + kk * EC + 4 * cq);
-                        const float x = HID[kk * TB + s];
-                        g[0] = fmaf(w4.x, x, g[0]); g[1] = fmaf(w4.y, x, g[1]); g[2] = fmaf(w4.z, x, g[2]); g[3] = fmaf(w4.w, x, g[3]);
+                        const float4 x4 = *reinterpret_cast<const float4*>(HID + kk * TB + 4 * lq);
+                        const float w[4] = {w4.x, w4.y, w4.z, w4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) g[i][j] = fmaf(w[i], x[j], g[i][j]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) SQ[(4 * cq + j) * TB + s] = fminf(fmaxf(g[j] + SB[SV_B2 + 4 * cq + j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+                    for (int i = 0; i < 4; i++) {
+                        const float bb = SB[SV_B2 + 4 * cq + i] + 3.f;
+                        *reinterpret_cast<float4*>(SQ + (4 * cq + i) * TB + 4 * lq) =
+                            make_float4(fminf(fmaxf(g[i][0] + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g[i][1] + bb, 0.f), 6.f) * (1.f / 6.f),
+                                        fminf(fmaxf(g[i][2] + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g[i][3] + bb, 0.f), 6.f) * (1.f / 6.f));
+                    }
                 }
             }
             __syncthreads();
@@ -433,53 +451,57 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     ent++;
                     return reinterpret_cast<const float*>(WRING + s * TC_PIRING_SLOT);
                 };
-                // 504 tasks = 3 K-thirds x 21 output quads x 8 leaf pairs; partial sums meet in PP, summed in a fixed order
-                float* PP = reinterpret_cast<float*>(ESTG + 39424);   // [3][84][16]
-                const bool live = t < 504;
-                const int part = min(t / 168, 2), rem = t - part * 168, og = rem >> 3, lp = rem & 7;
-                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                // 176 tasks = 4 K-slices x 11 output octets x 4 leaf quads (register tile 8 x 4: 32 FMA per three 128-bit loads; the loads,
+                // not the FMAs, are the limit); partial sums meet in PP and are summed in a fixed order
+                float* PP = reinterpret_cast<float*>(ESTG + 39424);   // [4][84][16]
+                const bool live = t < 176;
+                const int part = min(t / 44, 3), rem = t - part * 44, o8 = rem >> 2, lq = rem & 3;
+                const bool hi_ok = o8 < 10;                       // the last octet only has outputs 80..83
+                float acc[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                auto fma_row = [&](const float* wrow, const float4 x4) {
+                    const float4 wa = *reinterpret_cast<const float4*>(wrow), wb = hi_ok ? *reinterpret_cast<const float4*>(wrow + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
+                };
+                auto flush = [&]() {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if (i < 4 || hi_ok) *reinterpret_cast<float4*>(PP + (part * PIP + 8 * o8 + i) * TB + 4 * lq) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                };
                 for (int ch = 0; ch < NV / 8; ch++) {
                     const float* W = acquire();
                     if (live) {
-                        const int r0 = 19 * part, r1 = min(r0 + 19, 56);
-                        int il = r0 / 7, f = r0 - il * 7;
-#pragma unroll 4
-                        for (int rr = r0; rr < r1; rr++) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(W + rr * PIP + 4 * og);
-                            const float2 x = *reinterpret_cast<const float2*>(X0 + (8 * ch + il) * LD + f * TB + 2 * lp);
-                            acc[0][0] = fmaf(w4.x, x.x, acc[0][0]); acc[0][1] = fmaf(w4.y, x.x, acc[0][1]); acc[0][2] = fmaf(w4.z, x.x, acc[0][2]); acc[0][3] = fmaf(w4.w, x.x, acc[0][3]);
-                            acc[1][0] = fmaf(w4.x, x.y, acc[1][0]); acc[1][1] = fmaf(w4.y, x.y, acc[1][1]); acc[1][2] = fmaf(w4.z, x.y, acc[1][2]); acc[1][3] = fmaf(w4.w, x.y, acc[1][3]);
-                            if (++f == 7) { f = 0; il++; }
+#pragma unroll 2
+                        for (int il = 0; il < 2; il++) {                 // K-slice `part` = tokens 2*part, 2*part + 1 of this 8-token chunk
+                            const float* xp = X0 + (8 * ch + 2 * part + il) * LD + 4 * lq;
+                            const float* wp = W + ((2 * part + il) * 7) * PIP + 8 * o8;
+#pragma unroll
+                            for (int f = 0; f < 7; f++) fma_row(wp + f * PIP, *reinterpret_cast<const float4*>(xp + f * TB));
                         }
                     }
                 }
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) *reinterpret_cast<float2*>(PP + (part * PIP + 4 * og + j) * TB + 2 * lp) = make_float2(acc[0][j], acc[1][j]);
-                }
+                if (live) flush();
                 __syncthreads();
-                for (int i = t; i < PIP * TB; i += TC_THREADS) H1[i] = fmaxf(PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + SV[SV_BPI2 + (i >> 4)], 0.f);
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[0][j] = acc[1][j] = 0.f;
+                for (int i = t; i < PIP * TB; i += TC_THREADS)
+                    H1[i] = fmaxf(PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI2 + (i >> 4)], 0.f);
                 for (int ch = 0; ch < 2; ch++) {
                     const float* W = acquire();                   // first barrier: H1 complete (and PP consumed)
                     if (live) {
-                        const int k0 = max(27 * part, 41 * ch), k1 = min(27 * part + 27, ch == 0 ? 41 : 81);
-#pragma unroll 4
-                        for (int k = k0; k < k1; k++) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(W + (k - 41 * ch) * PIP + 4 * og);
-                            const float2 x = *reinterpret_cast<const float2*>(H1 + k * TB + 2 * lp);
-                            acc[0][0] = fmaf(w4.x, x.x, acc[0][0]); acc[0][1] = fmaf(w4.y, x.x, acc[0][1]); acc[0][2] = fmaf(w4.z, x.x, acc[0][2]); acc[0][3] = fmaf(w4.w, x.x, acc[0][3]);
-                            acc[1][0] = fmaf(w4.x, x.y, acc[1][0]); acc[1][1] = fmaf(w4.y, x.y, acc[1][1]); acc[1][2] = fmaf(w4.z, x.y, acc[1][2]); acc[1][3] = fmaf(w4.w, x.y, acc[1][3]);
-                        }
+                        const int k0 = max(21 * part, 41 * ch), k1 = min(min(21 * part + 21, 81), ch == 0 ? 41 : 81);
+#pragma unroll 2
+                        for (int k = k0; k < k1; k++) fma_row(W + (k - 41 * ch) * PIP + 8 * o8, *reinterpret_cast<const float4*>(H1 + k * TB + 4 * lq));
                     }
                 }
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) *reinterpret_cast<float2*>(PP + (part * PIP + 4 * og + j) * TB + 2 * lp) = make_float2(acc[0][j], acc[1][j]);
-                }
+                if (live) flush();
                 __syncthreads();
-                for (int i = t; i < PIP * TB; i += TC_THREADS) LG[i] = PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + SV[SV_BPI4 + (i >> 4)];
+                for (int i = t; i < PIP * TB; i += TC_THREADS) LG[i] = PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI4 + (i >> 4)];
                 __syncthreads();
                 {   // masked softmax: where(valid, logits, -1e8) -> log_softmax -> exp (SplendorNNet.py:404,440; GenericNNetWrapper.py:119)
                     const int sl = warp, slot = slot_of[sl];

@@ -295,9 +295,20 @@ def main():
     visits, exps, evals = d['node_visits'], d['expansions'], d['nn_evals']
     Lbar_vis = d['sum_legal_visited'] / max(visits, 1); Lbar_exp = d['sum_legal'] / max(exps, 1); Dbar = visits / max(d['sims'], 1)
     n_launch = max(int(kt['select_launches']), 1)
-    sel_bytes = 16.0 * visits + 14.0 * d['sum_legal_visited']                    # B_sel = 16 + 14 L per select step
-    bak_bytes = 32.0 * visits + (2.0 * S_BYTES + 32.0) * exps + 14.0 * d['sum_legal'] + (S_BYTES + 11 + 4 * N_ACT + 4 * N_PL) * evals  # B_bak, B_exp, B_nn
+    # Algorithmic bytes. The PUCT scan of a visited node (B_sel = 16 + 14 L) is split over two kernels in this engine:
+    # k_select follows the cached choice (32 B header + 4 B link per visit, 16 B path record) and scans only the root (20 B per
+    # root edge incl. its child link); k_backup re-scans the L edges of every node whose statistics it just changed (16 B per
+    # edge) on top of the update itself (B_bak), the expansion (B_exp) and the net I/O (B_nn). 'tree_path' is the SURVEY's own
+    # figure for the whole select+expand+backup path over the time of both kernels.
+    U = max(GAMES[args.game]['universes'], 1)
+    refreshed = max(visits - d['sims'], 0)                                       # non-root visits: one cached-choice refresh each
+    sel_bytes = (36.0 + 16.0) * visits + 20.0 * d['sum_legal_root_scans']
+    bak_bytes = (32.0 * visits + (2.0 * S_BYTES + 32.0) * exps + 14.0 * d['sum_legal'] + (S_BYTES + 11 + 4 * N_ACT + 4 * N_PL) * evals
+                 + 16.0 * visits + 16.0 * d['sum_legal_refreshed'] + (2.0 + 8.0 * U) * refreshed)
+    survey_bytes = (16.0 * visits + 14.0 * d['sum_legal_visited'] + 32.0 * visits + (2.0 * S_BYTES + 32.0) * exps + 14.0 * d['sum_legal']
+                    + (S_BYTES + 11 + 4 * N_ACT + 4 * N_PL) * evals)
     net_flops = float(gm['flops']) * evals
+    tree_ms = kt['select_ms'] + kt['backup_ms']
     kern = {
         'select': {'ms': kt['select_ms'], 'bound': 'hbm', 'achieved': sel_bytes / max(kt['select_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
                    'per_launch_bytes': sel_bytes / n_launch},
@@ -306,6 +317,9 @@ def main():
         'expand_backup': {'ms': kt['backup_ms'], 'bound': 'hbm', 'achieved': bak_bytes / max(kt['backup_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
                           'per_launch_bytes': bak_bytes / n_launch},
     }
+    tree_path = {'ms': tree_ms, 'bound': 'hbm', 'achieved': survey_bytes / max(tree_ms, 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
+                 'per_step_bytes': survey_bytes / n_launch, 'frac': survey_bytes / max(tree_ms, 1e-9) / 1e6 / pk['hbm'],
+                 'note': 'SURVEY.md 8d bytes of select + expand + backup (B_sel + B_bak + B_exp + B_nn) over the time of k_select + k_backup'}
     tot_ms = kt['select_ms'] + kt['net_ms'] + kt['backup_ms'] + kt['other_ms']
     for v in kern.values():
         v['frac'] = v['achieved'] / v['peak']; v['share'] = v['ms'] / max(tot_ms, 1e-9); v['avg_launch_us'] = 1e3 * v['ms'] / n_launch
@@ -350,9 +364,9 @@ def main():
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 net / f64 PUCT / i8 boards', 'data': 'synthetic',
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 net (token GEMMs 3xTF32 on tcgen05, fp32 accumulate) / f64 PUCT / i8 boards', 'data': 'synthetic',
                 'config': workload_cfg(args), 'e2e': e2e, 'gpu_launches': int(d['kernels_launched']), 'roofline': roofline, 'cpu_baseline': cpu,
-                'clocks': clk, 'kernels': kern,
+                'clocks': clk, 'kernels': kern, 'tree_path': tree_path,
                 'counters': {'sims': d['sims'], 'node_visits': visits, 'expansions': exps, 'nn_evals': evals, 'terminal_hits': d['terminal_hits'],
                              'arena_overflows': d['arena_overflows'], 'gc_runs': d['gc_runs'], 'moves_played': d['moves_played'],
                              'episodes_finished': d['episodes_finished'], 'mean_depth': Dbar, 'mean_legal_visited': Lbar_vis, 'mean_legal_expanded': Lbar_exp,
