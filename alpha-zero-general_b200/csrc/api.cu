@@ -441,6 +441,9 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     }
     *out = net; return 0;
 }
+extern "C" int azg_debug_selprof(unsigned long long* out8) {      // debug: see g_selprof (only filled when built with -DAZG_SEL_PROF)
+    CK(cudaDeviceSynchronize()); CK(cudaMemcpyFromSymbol(out8, azg::g_selprof, 8 * sizeof(unsigned long long))); return 0;
+}
 extern "C" int azg_net_prof(azg_net* net, long long* out64) {      // debug: phase timestamps (SM clock) of CTA 0's first tiles
     if (!net || !net->prof) return fail("profiling not enabled (AZG_V80_PROF=1)");
     CK(cudaDeviceSynchronize()); CK(cudaMemcpy(out64, net->prof, 64 * sizeof(long long), cudaMemcpyDeviceToHost)); return 0;
@@ -588,7 +591,7 @@ struct EngineT : azg_engine {
     int step(int s, cudaStream_t st) {
         const int NG = d.n_games;
         prof_mark(PK_SELECT, st);
-        k_select<G><<<(unsigned)((NG + SELK_WARPS - 1) / SELK_WARPS), SELK_WARPS * 32, 0, st>>>(d, s);
+        k_select<G><<<(unsigned)((NG + selk_warps<G>() - 1) / selk_warps<G>()), selk_warps<G>() * 32, 0, st>>>(d, s);
         prof_mark(PK_NET, st);
         if (net_forward_dev<G>(net, d.nn_count, d.nn_list, d.nn_in, G::SP, d.leaf_mask, d.nn_pi, d.nn_v, NG, st)) return 1;
         prof_mark(PK_BACKUP, st);

@@ -48,7 +48,11 @@ enum { LEAF_NONE = 0, LEAF_EXPAND = 1, LEAF_NEW_TERMINAL = 2, LEAF_OLD_TERMINAL 
 enum { ST_SIMS = 0, ST_VISITS, ST_EXPANSIONS, ST_NNEVALS, ST_TERMINAL, ST_OVERFLOW, ST_GC, ST_MAXNODES, ST_SUMLEGAL,
        ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_GC_SWEEP = 13, ST_SELLEGAL = 15, ST_ROOTLEGAL = 16, ST_REFLEGAL = 17, ST_N = 20 };
 
+#ifndef AZG_SEL_PROF
+#define AZG_SEL_PROF 0
+#endif
 constexpr double kNanQ = -42.0;                                // MCTS.py:11
+__device__ unsigned long long g_selprof[8];                    // debug (AZG_SEL_PROF): cycles per phase of k_select summed over warps
 __constant__ long long kMagicSeeds[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   // MCTS.py:14
 
 template <class G>
@@ -237,11 +241,11 @@ __device__ __forceinline__ int puct_select(const Edge* e, const uint32_t* child,
     return win;
 }
 
-// Bulk L2 prefetch of [p, p + bytes): one instruction per block (a plain prefetch.global.L2 only pulls one 32 B sector)
+// L2 prefetch of [p, p + bytes), one 32-byte sector per instruction
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
-    const uint32_t n = (uint32_t)((reinterpret_cast<uintptr_t>(p) + bytes - a + 15) & ~(uintptr_t)15);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+    const char* a = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)31);
+    const char* e = reinterpret_cast<const char*>(p) + bytes;
+    for (; a < e; a += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
 }
 // cpuct*sqrt(Ns + 1e-8): pick_highest_UCB's constant for unvisited edges (MCTS.py:226), computed where it is needed
 __device__ __forceinline__ double puct_c0(double cpuct, int ns) { return __dmul_rn(cpuct, __dsqrt_rn(__dadd_rn((double)ns, 1e-8))); }
@@ -330,7 +334,7 @@ __device__ __forceinline__ int best_edge_lane(const Edge* e, int L, double c1, d
 #ifndef AZG_SEL_MIN_BLOCKS
 #define AZG_SEL_MIN_BLOCKS (32 / AZG_SELK_WARPS)
 #endif
-constexpr int SELK_WARPS = AZG_SELK_WARPS;
+
 template <class G> struct WarpSmem {
     __align__(16) int8_t board[G::SP];
     __align__(16) float f[(G::A + 31) / 32 * 32];
@@ -340,6 +344,8 @@ template <class G> struct WarpSmem {
 };
 // Warps per CTA of the one-warp-per-game kernels: 4, or 1 when the per-warp scratch is large (Abalone: 3402 actions).
 template <class G> __host__ __device__ constexpr int sel_warps() { return sizeof(WarpSmem<G>) * 4 <= 40 * 1024 ? 4 : 1; }
+// Warps per CTA of k_select (AZG_SELK_WARPS where the per-warp scratch allows it)
+template <class G> __host__ __device__ constexpr int selk_warps() { return sizeof(WarpSmem<G>) * AZG_SELK_WARPS <= 40 * 1024 ? AZG_SELK_WARPS : 1; }
 
 template <class G> __device__ __forceinline__ void warp_load_board(int8_t* sb, const int8_t* src, int lane) {
     if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(src)[lane];
@@ -422,9 +428,9 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, ui
 
 // ============================================================ select ==================================
 template <class G>
-__global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
-    __shared__ WarpSmem<G> sm[SELK_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * SELK_WARPS + w;
+__global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 32 : AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
+    __shared__ WarpSmem<G> sm[selk_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * selk_warps<G>() + w;
     if (g >= d.n_games) return;
     if (step >= d.n_sims[g]) { if (lane == 0) d.leaf_kind[g] = LEAF_NONE; return; }
     const bool full = d.full ? d.full[g] != 0 : true;
@@ -436,7 +442,15 @@ __global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(
     int depth = 0, kind = LEAF_NONE, sum_legal = 0, root_legal = 0;
     uint32_t link_slot = 0;                                      // child-link slot (+1) a new leaf hangs on; 0 = it is the root
     bool at_new = false;                                         // ws.board holds a state that is not in the tree yet
+#if AZG_SEL_PROF == 1
+    long long tp0 = clock64(), tp_root = 0, tp_mat = 0, tp_leaf = 0; int n_mat = 0;
+#endif
     int idx = d.root_node[g] - 1;
+    if (step > 0 && lane < d.path_len[g]) {                      // consecutive simulations share most of their path: pull the headers and links of
+        const uint32_t pn = path[lane].node;                     // the previous path towards L2 in parallel, ahead of the dependent walk below
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + pn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(bestlink + (size_t)pn * d.U + uni));
+    }
     if (idx < 0) { idx = locate_root<G>(d, g, sm[w], lane); at_new = idx < 0; }
     while (!at_new) {
         const NodeHdr h = nodes[idx];                            // one round trip per level: 32 B header + the 4 B link of its cached best edge
@@ -452,6 +466,9 @@ __global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(
             e = puct_select(edges + h.edge_off, child + (size_t)h.edge_off * d.U, d.U, uni, h.n_legal, h.c1, puct_c0(d.cpuct, h.ns), h.qs, d.fpu,
                             forced_root, step, lane, link);
             root_legal = h.n_legal;
+#if AZG_SEL_PROF == 1
+            tp_root = clock64() - tp0;
+#endif
         }
         sum_legal += h.n_legal;
         const uint32_t eidx = h.edge_off + (uint32_t)e;
@@ -462,7 +479,13 @@ __global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(
             continue;
         }
         const long long seed = d.universes > 0 ? kMagicSeeds[uni] : -1;
+#if AZG_SEL_PROF == 1
+        long long tm0 = clock64();
+#endif
         const int found = materialise_child<G>(d, g, sm[w], idx, d.g_acts(g)[eidx], seed, lane);
+#if AZG_SEL_PROF == 1
+        tp_mat += clock64() - tm0; n_mat++;
+#endif
         const uint32_t np = (uint32_t)sm[w].np;
         if (lane == 0) { PathEnt pe; pe.node = (uint32_t)idx; pe.edge_np = eidx | (np << 24); pe.edge_off = h.edge_off; pe.n_legal = h.n_legal; path[depth] = pe; }
         const size_t slot = (size_t)eidx * d.U + uni;
@@ -476,7 +499,15 @@ __global__ void __launch_bounds__(SELK_WARPS * 32, AZG_SEL_MIN_BLOCKS) k_select(
         depth++;
         link_slot = (uint32_t)slot + 1u; at_new = true;
     }
+#if AZG_SEL_PROF == 1
+    long long tl0 = clock64();
+#endif
     if (at_new) kind = new_leaf<G>(d, g, sm[w], link_slot, lane);
+#if AZG_SEL_PROF == 1
+    tp_leaf = clock64() - tl0;
+    if (lane == 0) { atomicAdd(&g_selprof[0], (unsigned long long)(clock64() - tp0)); atomicAdd(&g_selprof[1], (unsigned long long)tp_root); atomicAdd(&g_selprof[2], (unsigned long long)tp_mat);
+        atomicAdd(&g_selprof[3], (unsigned long long)tp_leaf); atomicAdd(&g_selprof[4], 1ULL); atomicAdd(&g_selprof[5], (unsigned long long)n_mat); atomicAdd(&g_selprof[6], (unsigned long long)depth); }
+#endif
     if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; d.stats[(size_t)g * ST_N + ST_ROOTLEGAL] += (unsigned)root_legal; }
 }
 
@@ -487,6 +518,9 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;    // leaf list consumed by the net; reset for the next step
     if (g >= d.n_games) return;
+#if AZG_SEL_PROF == 2
+    const long long bp0 = clock64(); long long bp1 = 0, bp2 = 0;
+#endif
     const int kind = d.leaf_kind[g];
     if (kind == LEAF_NONE) return;
     constexpr int NP = G::NP, A = G::A, MW = G::MASK_WORDS;
@@ -575,6 +609,9 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
         }
         if (lane == 0) st[ST_TERMINAL]++;
     }
+#if AZG_SEL_PROF == 2
+    bp1 = clock64();
+#endif
     // ---- backup (MCTS.py:176-181), lanes parallel over levels; a path never visits a node twice (the round
     //      counter in the key increases with every move) so the updates are independent.
     const PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
@@ -606,6 +643,9 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
             }
         }
         carry = (carry + __shfl_sync(FULL, suf, 0)) % NP;
+#if AZG_SEL_PROF == 2
+        __syncwarp(); bp2 += clock64() - bp1;
+#endif
         // ---- refresh the cached PUCT choice of every updated non-root node (what the next visit will follow), one lane per level:
         //      each lane streams the edge list of its own node (the only edge that changed is the one it just wrote itself). The
         //      root is always scanned in full by k_select and is skipped here.
@@ -617,6 +657,10 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
         }
     }
     ref_legal = warp_sum_i32(ref_legal);
+#if AZG_SEL_PROF == 2
+    if (lane == 0) { const long long e = clock64(); atomicAdd(&g_selprof[7], 1ULL); atomicAdd(&g_selprof[0], (unsigned long long)(e - bp0)); atomicAdd(&g_selprof[1], (unsigned long long)(bp1 - bp0));
+        atomicAdd(&g_selprof[2], (unsigned long long)bp2); atomicAdd(&g_selprof[3], (unsigned long long)(e - bp1 - bp2)); }
+#endif
     if (lane == 0) st[ST_REFLEGAL] += (unsigned)ref_legal;
     if (lane == 0) { st[ST_SIMS]++; st[ST_VISITS] += (unsigned)depth; }
 }
