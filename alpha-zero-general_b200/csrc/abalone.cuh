@@ -47,6 +47,7 @@ struct Abalone {
         return r * 378 + q * 42 + plane;
     }
 
+    static __device__ __forceinline__ bool is_chance_move(int) { return false; }     // no chance in this game
     // One action's legality (valid_moves :254-331). `player` selects the marble plane (0 on canonical boards).
     static __device__ bool action_valid(const int8_t* b, int a, int player) {
         int r, q, size, axis, d; decode(a, r, q, size, axis, d);

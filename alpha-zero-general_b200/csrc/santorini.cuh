@@ -38,6 +38,7 @@ struct Santorini {
     static __device__ __forceinline__ int gp(const int8_t* b, int i) { return b[3 * i + 2]; }
     static __device__ __forceinline__ void set_gp(int8_t* b, int i, int v) { b[3 * i + 2] = (int8_t)v; }
 
+    static __device__ __forceinline__ bool is_chance_move(int) { return false; }   // no chance in this game
     static __device__ __forceinline__ int round(const int8_t* b) { return gp(b, 2); }        // get_round :655-656
     // get_score :87-101: highest level under one of the player's workers
     static __device__ int score(const int8_t* b, int player) {

@@ -214,6 +214,9 @@ struct Splendor {
         give_nobles(b, player);
     }
 
+    // True if the move may consume the chance seed (a card is revealed from a deck): moves 0-26 buy / reserve from the table or a deck.
+    // Everything else (buy a reserved card, take / give back gems, pass) gives the same child state in every universe.
+    static __device__ __forceinline__ bool is_chance_move(int move) { return move < 27; }
     // LANE: make_move (SplendorLogicNumba.py:190-205) with _buy :370-373, _reserve :382-400,
     // _buy_reserve :414-420, _get_gems / _give_gems :436-463. Returns the next player.
     static __device__ int make_move(int8_t* b, int move, int player, long long seed, Philox* rng) {

@@ -52,7 +52,8 @@ enum { ST_SIMS = 0, ST_VISITS, ST_EXPANSIONS, ST_NNEVALS, ST_TERMINAL, ST_OVERFL
 #define AZG_SEL_PROF 0
 #endif
 constexpr double kNanQ = -42.0;                                // MCTS.py:11
-__device__ unsigned long long g_selprof[8];                    // debug (AZG_SEL_PROF): cycles per phase of k_select summed over warps
+__device__ unsigned long long g_selprof[8];
+__device__ unsigned long long g_selprof2[8];                    // debug (AZG_SEL_PROF): cycles per phase of k_select summed over warps
 __constant__ long long kMagicSeeds[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   // MCTS.py:14
 
 template <class G>
@@ -66,6 +67,8 @@ struct Dev {
     NodeHdr* nodes; NodeKey* keys; Edge* edges; typename G::act_t* acts; uint64_t* ht; int* n_nodes; int* n_edges;
     uint32_t* child; int8_t* boards; int* remap; int* gcq;     // remap, gcq: [G][node_cap] scratch of the tree GC
     uint32_t* bestlink;                                        // [G][node_cap][U] child link of every node's cached best edge
+    int* work_ctr;                                             // [2] work-item counters of the persistent k_select / k_backup warps
+    int* ord_cnt; int* ord_list;                               // longest-first work order: [2][32] bucket counts, [2][32][G] games by path depth / 4
     int* root_node;                                            // [G] root node index + 1 once known for this search, else 0
     uint32_t* leaf_link;                                       // [G] child-link slot (index into child, +1) the new leaf hangs on; 0 = root
     // search control (per game)
@@ -326,6 +329,24 @@ __device__ __forceinline__ int best_edge_lane(const Edge* e, int L, double c1, d
     return bi;
 }
 
+// Longest-first scheduling. Walk lengths differ by an order of magnitude between games and the kernels end with the slowest
+// warp, so work item b of simulation `step` is not game b but the b-th DEEPEST game of the previous simulation (k_backup files
+// every game it processed under bucket depth/4; CTAs are dispatched in index order). Simulation 0 uses the identity. Returns -1
+// if there is no b-th item (games that have finished their search are no longer listed).
+template <class G> __device__ __forceinline__ int ordered_game(const Dev<G>& d, int b, int step, int lane) {
+    if (step == 0) return b < d.n_games ? b : -1;
+    const int set = (step - 1) & 1;
+    const int c = d.ord_cnt[set * 32 + (31 - lane)];             // lane l <-> bucket 31 - l: deepest first
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    const unsigned m = __ballot_sync(FULL, b < inc);
+    if (!m) return -1;
+    const int l = __ffs(m) - 1;
+    const int exc = __shfl_sync(FULL, inc - c, l);
+    return d.ord_list[(size_t)(set * 32 + (31 - l)) * d.n_games + (b - exc)];
+}
+
 // k_select runs ONE warp (= one game) per CTA so that an SM slot is recycled as soon as its game's walk ends
 // (walk lengths differ a lot between games); 64 registers/thread -> 32 resident CTAs = 32 games per SM.
 #ifndef AZG_SELK_WARPS
@@ -428,10 +449,7 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, ui
 
 // ============================================================ select ==================================
 template <class G>
-__global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 32 : AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
-    __shared__ WarpSmem<G> sm[selk_warps<G>()];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * selk_warps<G>() + w;
-    if (g >= d.n_games) return;
+__device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const int step, WarpSmem<G>* sm, const int w, const int lane) {
     if (step >= d.n_sims[g]) { if (lane == 0) d.leaf_kind[g] = LEAF_NONE; return; }
     const bool full = d.full ? d.full[g] != 0 : true;
     const bool forced_root = full && d.forced_playouts;
@@ -482,7 +500,9 @@ __global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 3
 #if AZG_SEL_PROF == 1
         long long tm0 = clock64();
 #endif
-        const int found = materialise_child<G>(d, g, sm[w], idx, d.g_acts(g)[eidx], seed, lane);
+        const int action = d.g_acts(g)[eidx];
+        const bool all_uni = d.U > 1 && !G::is_chance_move(action);   // a deterministic move has the same child in every universe: resolve all links at once
+        const int found = materialise_child<G>(d, g, sm[w], idx, action, seed, lane);
 #if AZG_SEL_PROF == 1
         tp_mat += clock64() - tm0; n_mat++;
 #endif
@@ -490,14 +510,16 @@ __global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 3
         if (lane == 0) { PathEnt pe; pe.node = (uint32_t)idx; pe.edge_np = eidx | (np << 24); pe.edge_off = h.edge_off; pe.n_legal = h.n_legal; path[depth] = pe; }
         const size_t slot = (size_t)eidx * d.U + uni;
         if (found >= 0) {                                        // transposition, or the same child under another universe
-            if (lane == 0) { child[slot] = (uint32_t)(found + 1) | (np << 28); if (depth > 0) bestlink[(size_t)idx * d.U + uni] = (uint32_t)(found + 1) | (np << 28); }
+            const uint32_t lv = (uint32_t)(found + 1) | (np << 28);
+            if (all_uni) { if (lane < d.U) { child[(size_t)eidx * d.U + lane] = lv; if (depth > 0) bestlink[(size_t)idx * d.U + lane] = lv; } }
+            else if (lane == 0) { child[slot] = lv; if (depth > 0) bestlink[(size_t)idx * d.U + uni] = lv; }
             depth++;
             idx = found;
             if (depth >= G::MAX_DEPTH) break;
             continue;
         }
         depth++;
-        link_slot = (uint32_t)slot + 1u; at_new = true;
+        link_slot = ((uint32_t)slot + 1u) | (all_uni ? 0x80000000u : 0u); at_new = true;   // bit 31: the new node hangs on the edge in every universe
     }
 #if AZG_SEL_PROF == 1
     long long tl0 = clock64();
@@ -505,19 +527,42 @@ __global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 3
     if (at_new) kind = new_leaf<G>(d, g, sm[w], link_slot, lane);
 #if AZG_SEL_PROF == 1
     tp_leaf = clock64() - tl0;
-    if (lane == 0) { atomicAdd(&g_selprof[0], (unsigned long long)(clock64() - tp0)); atomicAdd(&g_selprof[1], (unsigned long long)tp_root); atomicAdd(&g_selprof[2], (unsigned long long)tp_mat);
+    if (lane == 0) { const unsigned long long tw = (unsigned long long)(clock64() - tp0); atomicMax(&g_selprof[7], (tw << 20) | ((unsigned long long)depth << 8) | (unsigned long long)n_mat); if (tw > 100000) atomicAdd(&g_selprof2[0], 1ULL); if (tw > 200000) atomicAdd(&g_selprof2[1], 1ULL); if (tw > 50000) atomicAdd(&g_selprof2[2], 1ULL); if (depth > 32) atomicAdd(&g_selprof2[3], 1ULL); if (depth > 64) atomicAdd(&g_selprof2[4], 1ULL);
+        atomicAdd(&g_selprof[0], (unsigned long long)(clock64() - tp0)); atomicAdd(&g_selprof[1], (unsigned long long)tp_root); atomicAdd(&g_selprof[2], (unsigned long long)tp_mat);
         atomicAdd(&g_selprof[3], (unsigned long long)tp_leaf); atomicAdd(&g_selprof[4], 1ULL); atomicAdd(&g_selprof[5], (unsigned long long)n_mat); atomicAdd(&g_selprof[6], (unsigned long long)depth); }
 #endif
     if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; d.stats[(size_t)g * ST_N + ST_ROOTLEGAL] += (unsigned)root_legal; }
 }
 
+// Persistent warps: the grid only fills the machine (resident CTA slots), every warp pulls work items from a global counter until
+// the ordered list is exhausted -- no CTA launch per game, and the deepest games (longest walks) start first.
+template <class G>
+__global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 32 : AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
+    __shared__ WarpSmem<G> sm[selk_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x < 32) d.ord_cnt[(step & 1) * 32 + threadIdx.x] = 0;     // the set this simulation's backup fills
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.work_ctr[1] = 0;                                  // k_backup's work counter
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&d.work_ctr[0], 1);
+        i = __shfl_sync(FULL, i, 0);
+        const int g = ordered_game<G>(d, i, step, lane);
+        if (g < 0) break;
+        select_game<G>(d, g, step, sm, w, lane);
+        __syncwarp();
+    }
+}
+
+// Hang a new node on the child-link slot recorded by k_select (slot + 1; bit 31 = deterministic move: all U universes of the edge).
+__device__ __forceinline__ void link_new_node(uint32_t* child, uint32_t ls, int U, uint32_t value) {
+    const uint32_t slot = (ls & 0x7FFFFFFFu) - 1u;
+    if (ls >> 31) { const uint32_t base = slot - slot % (uint32_t)U; for (int u = 0; u < U; u++) child[base + u] = value; }
+    else child[slot] = value;
+}
+
 // ============================================================ expand + backup =========================
 template <class G>
-__global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_backup(const __grid_constant__ Dev<G> d, int step) {
-    __shared__ WarpSmem<G> sm[sel_warps<G>()];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;    // leaf list consumed by the net; reset for the next step
-    if (g >= d.n_games) return;
+__device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const int step, WarpSmem<G>* sm, const int w, const int lane) {
 #if AZG_SEL_PROF == 2
     const long long bp0 = clock64(); long long bp1 = 0, bp2 = 0;
 #endif
@@ -525,6 +570,10 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
     if (kind == LEAF_NONE) return;
     constexpr int NP = G::NP, A = G::A, MW = G::MASK_WORDS;
     const int depth = d.path_len[g];
+    if (lane == 0) {                                             // file this game for the next simulation's work order
+        const int bk = (step & 1) * 32 + min(depth >> 2, 31);
+        d.ord_list[(size_t)bk * d.n_games + atomicAdd(&d.ord_cnt[bk], 1)] = g;
+    }
     NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
     unsigned long long* st = d.stats + (size_t)g * ST_N;
     if (lane >= 1 && lane < depth) {                             // levels 1..31 of the path: pull the edge blocks and links that the refresh
@@ -574,7 +623,7 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
             const int nb = best_edge(edges + eo, L, 0.0, d.cpuct, 0, v[0], d.fpu, lane);      // first visit's choice (all edges unvisited)
             if (lane < d.U) d.g_best(g)[(size_t)ni * d.U + lane] = 0;
             if (lane == 0) {
-                if (ls) child[ls - 1] = (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28);
+                if (ls) link_new_node(child, ls, d.U, (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28));
                 else d.root_node[g] = ni + 1;
                 NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
                 NodeHdr h; h.c1 = 0.0; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
@@ -595,7 +644,7 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
                 const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
                 const uint32_t ls = d.leaf_link[g];
                 if (lane == 0) {
-                    if (ls) d.g_child(g)[ls - 1] = (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28);
+                    if (ls) link_new_node(d.g_child(g), ls, d.U, (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28));
                     else d.root_node[g] = ni + 1;
                     float* es = reinterpret_cast<float*>(edges + eo);
                     for (int p = 0; p < 4; p++) es[p] = p < NP ? v[p] : 0.f;
@@ -663,6 +712,22 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_ba
 #endif
     if (lane == 0) st[ST_REFLEGAL] += (unsigned)ref_legal;
     if (lane == 0) { st[ST_SIMS]++; st[ST_VISITS] += (unsigned)depth; }
+}
+
+template <class G>
+__global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_backup(const __grid_constant__ Dev<G> d, int step) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *d.nn_count = 0; d.work_ctr[0] = 0; }            // leaf list consumed by the net; k_select's work counter
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&d.work_ctr[1], 1);
+        i = __shfl_sync(FULL, i, 0);
+        const int g = ordered_game<G>(d, i, step, lane);
+        if (g < 0) break;
+        backup_game<G>(d, g, step, sm, w, lane);
+        __syncwarp();
+    }
 }
 
 // ============================================================ finish (getActionProb tail) ==============
