@@ -534,6 +534,7 @@ struct EngineT : azg_engine {
         d.universes = c->universes; d.U = U0; d.forced_playouts = c->forced_playouts; d.dirichlet_noise = c->dirichlet_noise;
         d.cpuct = c->cpuct; d.fpu = c->fpu; d.dir_alpha = c->dirichletAlpha; d.temp2 = c->temperature[2]; d.seed = c->seed;
         d.noise = nullptr;
+        { const char* rv = getenv("AZG_TREE_REPLAY"); d.replay = (rv && rv[0] == '0') ? 0 : 1; }
         sims_full = c->numMCTSSims; sims_fast = c->ratio_fullMCTS > 0 ? c->numMCTSSims / c->ratio_fullMCTS : c->numMCTSSims;
         int bad = 0;
         bad |= alloc(&d.nodes, (size_t)NG * node_cap, false); bad |= alloc(&d.keys, (size_t)NG * node_cap, false); bad |= alloc(&d.edges, (size_t)NG * edge_cap, false);
@@ -544,7 +545,7 @@ struct EngineT : azg_engine {
         bad |= alloc(&d.ord_cnt, 64); bad |= alloc(&d.ord_list, (size_t)64 * NG, false); bad |= alloc(&d.work_ctr, 2);
         bad |= alloc(&d.remap, (size_t)NG * node_cap, false); bad |= alloc(&d.gcq, (size_t)NG * node_cap, false); bad |= alloc(&d.root_node, NG); bad |= alloc(&d.leaf_link, NG);
         bad |= alloc(&d.root, (size_t)NG * G::SP); bad |= alloc(&d.n_sims, NG); bad |= alloc(&d.full, NG); bad |= alloc(&d.move_ctr, NG);
-        bad |= alloc(&d.path, (size_t)NG * G::MAX_DEPTH); bad |= alloc(&d.path_len, NG); bad |= alloc(&d.leaf_kind, NG);
+        bad |= alloc(&d.path, (size_t)NG * d.U * G::MAX_DEPTH); bad |= alloc(&d.path_len, (size_t)NG * d.U); bad |= alloc(&d.leaf_kind, NG);
         bad |= alloc(&d.leaf_key, (size_t)2 * NG); bad |= alloc(&d.leaf_v, (size_t)NG * G::NP); bad |= alloc(&d.leaf_mask, (size_t)NG * G::MASK_WORDS);
         bad |= alloc(&d.leaf_round, NG);
         bad |= alloc(&d.nn_in, (size_t)NG * G::SP); bad |= alloc(&d.nn_pi, (size_t)NG * G::A); bad |= alloc(&d.nn_v, (size_t)NG * G::NP);

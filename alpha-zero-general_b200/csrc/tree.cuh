@@ -61,6 +61,7 @@ struct Dev {
     // configuration
     int n_games, node_cap, edge_cap, ht_cap;
     int universes, U, forced_playouts, dirichlet_noise;         // U = max(universes, 1): child links per edge
+    int replay;                                                // path replay in k_select (1; AZG_TREE_REPLAY=0 turns it off for A/B tests: results are identical)
     double cpuct, fpu, dir_alpha, temp2;
     uint64_t seed;
     // trees
@@ -90,6 +91,9 @@ struct Dev {
     __device__ __forceinline__ uint32_t* g_child(int g) const { return child + (size_t)g * edge_cap * U; }
     __device__ __forceinline__ int8_t* g_boards(int g) const { return boards + (size_t)g * node_cap * G::SP; }
     __device__ __forceinline__ uint32_t* g_best(int g) const { return bestlink + (size_t)g * node_cap * U; }
+    // the last path walked in universe `uni` of game g (kept per universe: k_select replays its still-valid prefix in parallel)
+    __device__ __forceinline__ PathEnt* g_path(int g, int uni, int max_depth) const { return path + ((size_t)g * U + uni) * max_depth; }
+    __device__ __forceinline__ int* g_path_len(int g, int uni) const { return path_len + (size_t)g * U + uni; }
 };
 constexpr uint32_t LINK_IDX = 0x0FFFFFFFu;                      // child link: low 28 bits = node index + 1, high 4 = next player
 
@@ -456,7 +460,7 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
     const bool noise_now = step == 0 && full && d.dirichlet_noise;
     const int uni = d.universes > 0 ? step % d.universes : 0;
     const NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); uint32_t* child = d.g_child(g); uint32_t* bestlink = d.g_best(g);
-    PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
+    PathEnt* path = d.g_path(g, uni, G::MAX_DEPTH);
     int depth = 0, kind = LEAF_NONE, sum_legal = 0, root_legal = 0;
     uint32_t link_slot = 0;                                      // child-link slot (+1) a new leaf hangs on; 0 = it is the root
     bool at_new = false;                                         // ws.board holds a state that is not in the tree yet
@@ -464,11 +468,16 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
     long long tp0 = clock64(), tp_root = 0, tp_mat = 0, tp_leaf = 0; int n_mat = 0;
 #endif
     int idx = d.root_node[g] - 1;
-    if (step > 0 && lane < d.path_len[g]) {                      // consecutive simulations share most of their path: pull the headers and links of
-        const uint32_t pn = path[lane].node;                     // the previous path towards L2 in parallel, ahead of the dependent walk below
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nodes + pn));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(bestlink + (size_t)pn * d.U + uni));
-    }
+    // ---- path replay, part 1: the previous walk of this universe. Fetch the header and best link of every node it recorded
+    //      (levels 1..32 here, one lane each, all loads in flight together) before the dependent walk starts.
+    const int plen = d.replay ? *d.g_path_len(g, uni) : 0;
+#if AZG_SEL_PROF == 1
+    if (lane == 0) atomicAdd(&g_selprof2[6], (unsigned long long)plen);
+#endif
+    PathEnt rp; rp.node = 0; rp.edge_np = 0; rp.edge_off = 0; rp.n_legal = 0;
+    NodeHdr rh; rh.kind = NODE_TERMINAL; rh.best = 0; rh.edge_off = 0; rh.n_legal = 0;
+    uint32_t rl = 0;
+    if (lane + 1 < plen) { rp = path[lane + 1]; rh = nodes[rp.node]; rl = bestlink[(size_t)rp.node * d.U + uni]; }
     if (idx < 0) { idx = locate_root<G>(d, g, sm[w], lane); at_new = idx < 0; }
     while (!at_new) {
         const NodeHdr h = nodes[idx];                            // one round trip per level: 32 B header + the 4 B link of its cached best edge
@@ -494,6 +503,46 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
             if (lane == 0) { PathEnt pe; pe.node = (uint32_t)idx; pe.edge_np = eidx | ((link >> 28) << 24); pe.edge_off = h.edge_off; pe.n_legal = h.n_legal; path[depth] = pe; }
             idx = (int)(link & LINK_IDX) - 1;
             if (++depth >= G::MAX_DEPTH) break;
+            if (depth == 1) {
+                // ---- path replay, part 2: level L = lane + 1 of the previous path is confirmed if the link INTO it (the root's choice for
+                //      lane 0, the fetched best link of level L - 1 otherwise) leads to the recorded node and that node is expanded. The
+                //      confirmed prefix is exactly what the dependent walk would have visited (same nodes, same cached choices), found in
+                //      two memory round trips instead of one per level. Deep chains (the slowest walks) mostly replay in full.
+                uint32_t in_link = link;
+                int base = 0;                                    // levels base+1 .. base+32 are in the lanes
+                for (;;) {
+                    const uint32_t prev = __shfl_up_sync(FULL, rl, 1);
+                    const uint32_t inl = lane == 0 ? in_link : prev;
+                    const bool ok = base + lane + 1 < plen && (int)(inl & LINK_IDX) - 1 == (int)rp.node && rh.kind == NODE_EXPANDED && base + lane + 1 < G::MAX_DEPTH - 1;
+                    const unsigned okm = __ballot_sync(FULL, ok);
+                    const int k = okm == FULL ? 32 : __ffs(~okm) - 1;           // confirmed levels base+1 .. base+k
+                    if (k == 0) break;
+                    // levels whose outgoing edge is confirmed too (all but the last confirmed one) are recorded and counted
+                    if (lane < k - 1) {
+                        PathEnt pe; pe.node = rp.node; pe.edge_np = (rh.edge_off + rh.best) | ((rl >> 28) << 24); pe.edge_off = rh.edge_off; pe.n_legal = rh.n_legal;
+                        path[base + lane + 1] = pe;
+                    }
+                    sum_legal += warp_sum_i32(lane < k - 1 ? (int)rh.n_legal : 0);
+                    idx = (int)__shfl_sync(FULL, rp.node, k - 1); depth = base + k;
+#if AZG_SEL_PROF == 1
+                    if (lane == 0) atomicAdd(&g_selprof2[5], (unsigned long long)k);
+#endif
+                    if (k < 32 || base + 33 >= plen) break;
+                    // the whole chunk was confirmed and the old path goes on: the last lane's node becomes a recorded level as well
+                    // (its outgoing link is the incoming link of the next chunk's first level)
+                    in_link = __shfl_sync(FULL, rl, 31);
+                    if (lane == 31) { PathEnt pe; pe.node = rp.node; pe.edge_np = (rh.edge_off + rh.best) | ((rl >> 28) << 24); pe.edge_off = rh.edge_off; pe.n_legal = rh.n_legal; path[base + 32] = pe; }
+                    const int n31 = (int)__shfl_sync(FULL, (uint32_t)rh.n_legal, 31);
+                    base += 32;
+                    rp.node = 0; rh.kind = NODE_TERMINAL; rl = 0;
+                    if (base + lane + 1 < plen) { rp = path[base + lane + 1]; rh = nodes[rp.node]; rl = bestlink[(size_t)rp.node * d.U + uni]; }
+                    // tentatively step onto the first level of the new chunk: if it is not confirmed the walk resumes at the old chunk's last node
+                    const uint32_t p0 = __shfl_sync(FULL, rp.node, 0);
+                    const int k0 = __shfl_sync(FULL, (int)rh.kind, 0);
+                    if (!((int)(in_link & LINK_IDX) - 1 == (int)p0 && k0 == NODE_EXPANDED && base + 1 < plen && base + 1 < G::MAX_DEPTH - 1)) { base -= 32; break; }
+                    sum_legal += n31;
+                }
+            }
             continue;
         }
         const long long seed = d.universes > 0 ? kMagicSeeds[uni] : -1;
@@ -531,7 +580,7 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
         atomicAdd(&g_selprof[0], (unsigned long long)(clock64() - tp0)); atomicAdd(&g_selprof[1], (unsigned long long)tp_root); atomicAdd(&g_selprof[2], (unsigned long long)tp_mat);
         atomicAdd(&g_selprof[3], (unsigned long long)tp_leaf); atomicAdd(&g_selprof[4], 1ULL); atomicAdd(&g_selprof[5], (unsigned long long)n_mat); atomicAdd(&g_selprof[6], (unsigned long long)depth); }
 #endif
-    if (lane == 0) { d.path_len[g] = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; d.stats[(size_t)g * ST_N + ST_ROOTLEGAL] += (unsigned)root_legal; }
+    if (lane == 0) { *d.g_path_len(g, uni) = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; d.stats[(size_t)g * ST_N + ST_ROOTLEGAL] += (unsigned)root_legal; }
 }
 
 // Persistent warps: the grid only fills the machine (resident CTA slots), every warp pulls work items from a global counter until
@@ -569,7 +618,8 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
     const int kind = d.leaf_kind[g];
     if (kind == LEAF_NONE) return;
     constexpr int NP = G::NP, A = G::A, MW = G::MASK_WORDS;
-    const int depth = d.path_len[g];
+    const int uni_b = d.universes > 0 ? step % d.universes : 0;
+    const int depth = *d.g_path_len(g, uni_b);
     if (lane == 0) {                                             // file this game for the next simulation's work order
         const int bk = (step & 1) * 32 + min(depth >> 2, 31);
         d.ord_list[(size_t)bk * d.n_games + atomicAdd(&d.ord_cnt[bk], 1)] = g;
@@ -577,7 +627,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
     NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
     unsigned long long* st = d.stats + (size_t)g * ST_N;
     if (lane >= 1 && lane < depth) {                             // levels 1..31 of the path: pull the edge blocks and links that the refresh
-        const PathEnt pp = d.path[(size_t)g * G::MAX_DEPTH + lane];   // below scans towards L2 now, while the expansion runs
+        const PathEnt pp = d.g_path(g, uni_b, G::MAX_DEPTH)[lane];    // below scans towards L2 now, while the expansion runs
         if (pp.n_legal) {
             l2_prefetch(edges + pp.edge_off, pp.n_legal * 16u);
         }
@@ -623,7 +673,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
             const int nb = best_edge(edges + eo, L, 0.0, d.cpuct, 0, v[0], d.fpu, lane);      // first visit's choice (all edges unvisited)
             if (lane < d.U) d.g_best(g)[(size_t)ni * d.U + lane] = 0;
             if (lane == 0) {
-                if (ls) link_new_node(child, ls, d.U, (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28));
+                if (ls) link_new_node(child, ls, d.U, (uint32_t)(ni + 1) | ((d.g_path(g, uni_b, G::MAX_DEPTH)[depth - 1].edge_np >> 24) << 28));
                 else d.root_node[g] = ni + 1;
                 NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
                 NodeHdr h; h.c1 = 0.0; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
@@ -644,7 +694,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
                 const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
                 const uint32_t ls = d.leaf_link[g];
                 if (lane == 0) {
-                    if (ls) link_new_node(d.g_child(g), ls, d.U, (uint32_t)(ni + 1) | ((d.path[(size_t)g * G::MAX_DEPTH + depth - 1].edge_np >> 24) << 28));
+                    if (ls) link_new_node(d.g_child(g), ls, d.U, (uint32_t)(ni + 1) | ((d.g_path(g, uni_b, G::MAX_DEPTH)[depth - 1].edge_np >> 24) << 28));
                     else d.root_node[g] = ni + 1;
                     float* es = reinterpret_cast<float*>(edges + eo);
                     for (int p = 0; p < 4; p++) es[p] = p < NP ? v[p] : 0.f;
@@ -663,7 +713,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
 #endif
     // ---- backup (MCTS.py:176-181), lanes parallel over levels; a path never visits a node twice (the round
     //      counter in the key increases with every move) so the updates are independent.
-    const PathEnt* path = d.path + (size_t)g * G::MAX_DEPTH;
+    const PathEnt* path = d.g_path(g, uni_b, G::MAX_DEPTH);
     uint32_t* child = d.g_child(g); uint32_t* bestlink = d.g_best(g);
     int carry = 0, ref_legal = 0;                                // rotation accumulated from deeper chunks
     for (int base = ((depth - 1) / 32) * 32; base >= 0 && depth > 0; base -= 32) {

@@ -110,3 +110,56 @@ def test_device_buffers_and_stats(game, hashnet, kat):
     st = eng.stats()
     assert st['sims'] == 2 * n * 64 and st['kernels_launched'] > 0
     eng.close()
+
+
+def test_deep_search_mixed_budgets_vs_oracle(game, hashnet, kat):
+    """Long searches (3000 simulations, three universes, forced playouts) from opening, mid- and late-game roots, two consecutive
+    searches per tree: deep principal variations exercise the multi-chunk path replay, the cached-choice refresh, the
+    all-universe links of deterministic moves and the longest-first work order; every other game runs the short budget
+    (numMCTSSims / ratio_fullMCTS), so games leave the work order at different simulations."""
+    n_sims, ratio = 3000, 5
+    args = dict(numMCTSSims=n_sims, cpuct=0.8, fpu=0.0593, universes=3, dirichletAlpha=0.3, temperature=[1.25, 0.8, 1.1],
+                forced_playouts=True, prob_fullMCTS=1.0, ratio_fullMCTS=ratio)
+    idx = [0, 55, 130, 210, 330, 450, 560, 610]
+    roots = np.ascontiguousarray(kat['canonical'][idx])
+    full = np.array([i % 2 == 0 for i in range(len(idx))])
+    eng = Engine(game, hashnet, args, n_games=len(idx), node_cap=8192)
+    cfg = O.make_cfg(numMCTSSims=n_sims, ratio_fullMCTS=ratio, universes=3, forced_playouts=True, net_kind=0, cpuct=0.8, fpu=0.0593,
+                     dirichletAlpha=0.3, prob_fullMCTS=0.0)
+    oracles = [O.MCTS(cfg) for _ in idx]
+    for rep in range(2):                                        # the second search reuses (and extends) the trees
+        counts, raw, q = eng.search(roots, full_search=full)
+        for i in range(len(idx)):
+            probs, oq, ofull, oraw = oracles[i].getActionProb(roots[i], temp=1, force_full_search=bool(full[i]))
+            assert ofull == bool(full[i])
+            assert (raw[i] == oraw).all(), f'game {i} search {rep}'
+            assert (q[i] == oq).all(), f'game {i} search {rep}'
+    st = eng.stats()
+    assert st['arena_overflows'] == 0 and st['sims'] == 2 * (4 * n_sims + 4 * (n_sims // ratio))
+    eng.close()
+
+
+def test_path_replay_is_exact_on_deep_trees(game, v80_golden, kat, monkeypatch):
+    """With the real net the principal variations get deep (tens of levels, beyond one 32-level replay chunk). The path replay,
+    the work order and the persistent warps only change HOW the walk is executed: an engine with the replay switched off
+    (AZG_TREE_REPLAY=0) must produce bit-identical visit counts, q values and counters over several consecutive searches."""
+    sd = v80_golden['rand']['sd']
+    net = NNetWrapper(game, {'nn_version': 80}, state_dict=sd)
+    args = dict(numMCTSSims=1200, cpuct=1.25, fpu=0.0, universes=3, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1],
+                forced_playouts=False, prob_fullMCTS=1.0, ratio_fullMCTS=5)
+    roots = np.ascontiguousarray(kat['canonical'][::10][:64])
+    res = []
+    for replay in ('1', '0'):
+        monkeypatch.setenv('AZG_TREE_REPLAY', replay)
+        eng = Engine(game, net, args, n_games=len(roots), node_cap=4096, seed=3)
+        out = [tuple(a.copy() for a in eng.search(roots)) for _ in range(2)]
+        st = eng.stats(); eng.close()
+        res.append((out, st))
+    monkeypatch.delenv('AZG_TREE_REPLAY')
+    (a, sa), (b, sb) = res
+    for x, y in zip(a, b):
+        assert (x[1] == y[1]).all() and (x[2] == y[2]).all()
+    for k in ('sims', 'node_visits', 'expansions', 'terminal_hits', 'sum_legal_visited'):
+        assert sa[k] == sb[k], k
+    assert sa['node_visits'] / sa['sims'] > 6                    # the trees really are deep
+    assert sa['arena_overflows'] == 0
