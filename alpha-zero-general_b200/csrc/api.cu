@@ -496,7 +496,6 @@ struct EngineT : azg_engine {
     std::vector<void*> allocs;
     unsigned long long launches = 0;
     int sims_full = 0, sims_fast = 0;
-    int sel_ctas = 1, bak_ctas = 1;      // resident CTA slots of the persistent k_select / k_backup grids
     bool sp_ready = false;
     bool profiling = false; std::vector<cudaEvent_t> ev; size_t ev_used = 0; std::vector<int> ev_kind; double prof_ms[4] = {0, 0, 0, 0}; long long prof_n[4] = {0, 0, 0, 0};
 
@@ -542,7 +541,7 @@ struct EngineT : azg_engine {
         bad |= alloc(&d.n_nodes, NG); bad |= alloc(&d.n_edges, NG);
         bad |= alloc(&d.child, (size_t)NG * edge_cap * d.U, false); bad |= alloc(&d.boards, (size_t)NG * node_cap * G::SP, false);
         bad |= alloc(&d.bestlink, (size_t)NG * node_cap * d.U, false);
-        bad |= alloc(&d.ord_cnt, 64); bad |= alloc(&d.ord_list, (size_t)64 * NG, false); bad |= alloc(&d.work_ctr, 2);
+        bad |= alloc(&d.ord_cnt, 64); bad |= alloc(&d.ord_list, (size_t)64 * NG, false);
         bad |= alloc(&d.remap, (size_t)NG * node_cap, false); bad |= alloc(&d.gcq, (size_t)NG * node_cap, false); bad |= alloc(&d.root_node, NG); bad |= alloc(&d.leaf_link, NG);
         bad |= alloc(&d.root, (size_t)NG * G::SP); bad |= alloc(&d.n_sims, NG); bad |= alloc(&d.full, NG); bad |= alloc(&d.move_ctr, NG);
         bad |= alloc(&d.path, (size_t)NG * d.U * G::MAX_DEPTH); bad |= alloc(&d.path_len, (size_t)NG * d.U); bad |= alloc(&d.leaf_kind, NG);
@@ -551,10 +550,6 @@ struct EngineT : azg_engine {
         bad |= alloc(&d.nn_in, (size_t)NG * G::SP); bad |= alloc(&d.nn_pi, (size_t)NG * G::A); bad |= alloc(&d.nn_v, (size_t)NG * G::NP);
         bad |= alloc(&d.nn_list, NG); bad |= alloc(&d.nn_count, 1); bad |= alloc(&d.stats, (size_t)NG * ST_N);
         if (bad) return bad;
-        int dev = 0, n_sm = 0, per_sm = 0;
-        CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select<G>, selk_warps<G>() * 32, 0)); sel_ctas = std::max(1, per_sm * n_sm);
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_backup<G>, sel_warps<G>() * 32, 0)); bak_ctas = std::max(1, per_sm * n_sm);
         return 0;
     }
     int reset(int game) override {
@@ -599,11 +594,11 @@ struct EngineT : azg_engine {
     int step(int s, cudaStream_t st) {
         const int NG = d.n_games;
         prof_mark(PK_SELECT, st);
-        k_select<G><<<(unsigned)std::min((NG + selk_warps<G>() - 1) / selk_warps<G>(), sel_ctas), selk_warps<G>() * 32, 0, st>>>(d, s);
+        k_select<G><<<(unsigned)((NG + selk_warps<G>() - 1) / selk_warps<G>()), selk_warps<G>() * 32, 0, st>>>(d, s);
         prof_mark(PK_NET, st);
         if (net_forward_dev<G>(net, d.nn_count, d.nn_list, d.nn_in, G::SP, d.leaf_mask, d.nn_pi, d.nn_v, NG, st)) return 1;
         prof_mark(PK_BACKUP, st);
-        k_backup<G><<<(unsigned)std::min((NG + sel_warps<G>() - 1) / sel_warps<G>(), bak_ctas), sel_warps<G>() * 32, 0, st>>>(d, s);
+        k_backup<G><<<grid(), sel_warps<G>() * 32, 0, st>>>(d, s);
         prof_mark(-1, st);
         launches += 3;
         return 0;

@@ -68,7 +68,6 @@ struct Dev {
     NodeHdr* nodes; NodeKey* keys; Edge* edges; typename G::act_t* acts; uint64_t* ht; int* n_nodes; int* n_edges;
     uint32_t* child; int8_t* boards; int* remap; int* gcq;     // remap, gcq: [G][node_cap] scratch of the tree GC
     uint32_t* bestlink;                                        // [G][node_cap][U] child link of every node's cached best edge
-    int* work_ctr;                                             // [2] work-item counters of the persistent k_select / k_backup warps
     int* ord_cnt; int* ord_list;                               // longest-first work order: [2][32] bucket counts, [2][32][G] games by path depth / 4
     int* root_node;                                            // [G] root node index + 1 once known for this search, else 0
     uint32_t* leaf_link;                                       // [G] child-link slot (index into child, +1) the new leaf hangs on; 0 = root
@@ -337,19 +336,25 @@ __device__ __forceinline__ int best_edge_lane(const Edge* e, int L, double c1, d
 // warp, so work item b of simulation `step` is not game b but the b-th DEEPEST game of the previous simulation (k_backup files
 // every game it processed under bucket depth/4; CTAs are dispatched in index order). Simulation 0 uses the identity. Returns -1
 // if there is no b-th item (games that have finished their search are no longer listed).
-template <class G> __device__ __forceinline__ int ordered_game(const Dev<G>& d, int b, int step, int lane) {
-    if (step == 0) return b < d.n_games ? b : -1;
-    const int set = (step - 1) & 1;
-    const int c = d.ord_cnt[set * 32 + (31 - lane)];             // lane l <-> bucket 31 - l: deepest first
-    int inc = c;
+template <class G> struct WorkOrder {                              // per-warp view of the bucket counts: loaded and scanned once per launch
+    int c, inc;
+    __device__ __forceinline__ void load(const Dev<G>& d, int step, int lane) {
+        c = inc = 0;
+        if (step == 0) return;
+        c = d.ord_cnt[((step - 1) & 1) * 32 + (31 - lane)];      // lane l <-> bucket 31 - l: deepest first
+        inc = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-    const unsigned m = __ballot_sync(FULL, b < inc);
-    if (!m) return -1;
-    const int l = __ffs(m) - 1;
-    const int exc = __shfl_sync(FULL, inc - c, l);
-    return d.ord_list[(size_t)(set * 32 + (31 - l)) * d.n_games + (b - exc)];
-}
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    }
+    __device__ __forceinline__ int game(const Dev<G>& d, int b, int step, int lane) const {
+        if (step == 0) return b < d.n_games ? b : -1;
+        const unsigned m = __ballot_sync(FULL, b < inc);
+        if (!m) return -1;
+        const int l = __ffs(m) - 1;
+        const int exc = __shfl_sync(FULL, inc - c, l);
+        return d.ord_list[(size_t)(((step - 1) & 1) * 32 + (31 - l)) * d.n_games + (b - exc)];
+    }
+};
 
 // k_select runs ONE warp (= one game) per CTA so that an SM slot is recycled as soon as its game's walk ends
 // (walk lengths differ a lot between games); 64 registers/thread -> 32 resident CTAs = 32 games per SM.
@@ -583,23 +588,15 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
     if (lane == 0) { *d.g_path_len(g, uni) = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; d.stats[(size_t)g * ST_N + ST_ROOTLEGAL] += (unsigned)root_legal; }
 }
 
-// Persistent warps: the grid only fills the machine (resident CTA slots), every warp pulls work items from a global counter until
-// the ordered list is exhausted -- no CTA launch per game, and the deepest games (longest walks) start first.
+// One CTA per work item (persistent warps pulling tickets from a global counter were measured: no gain for k_select, a loss for k_backup).
 template <class G>
 __global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 32 : AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
     __shared__ WarpSmem<G> sm[selk_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x < 32) d.ord_cnt[(step & 1) * 32 + threadIdx.x] = 0;     // the set this simulation's backup fills
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.work_ctr[1] = 0;                                  // k_backup's work counter
-    for (;;) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&d.work_ctr[0], 1);
-        i = __shfl_sync(FULL, i, 0);
-        const int g = ordered_game<G>(d, i, step, lane);
-        if (g < 0) break;
-        select_game<G>(d, g, step, sm, w, lane);
-        __syncwarp();
-    }
+    WorkOrder<G> wo; wo.load(d, step, lane);
+    const int g = wo.game(d, blockIdx.x * selk_warps<G>() + w, step, lane);   // CTAs are dispatched in index order: deepest games first
+    if (g >= 0) select_game<G>(d, g, step, sm, w, lane);
 }
 
 // Hang a new node on the child-link slot recorded by k_select (slot + 1; bit 31 = deterministic move: all U universes of the edge).
@@ -768,16 +765,10 @@ template <class G>
 __global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_backup(const __grid_constant__ Dev<G> d, int step) {
     __shared__ WarpSmem<G> sm[sel_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *d.nn_count = 0; d.work_ctr[0] = 0; }            // leaf list consumed by the net; k_select's work counter
-    for (;;) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&d.work_ctr[1], 1);
-        i = __shfl_sync(FULL, i, 0);
-        const int g = ordered_game<G>(d, i, step, lane);
-        if (g < 0) break;
-        backup_game<G>(d, g, step, sm, w, lane);
-        __syncwarp();
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;   // leaf list consumed by the net; reset for the next step
+    WorkOrder<G> wo; wo.load(d, step, lane);
+    const int g = wo.game(d, blockIdx.x * sel_warps<G>() + w, step, lane);   // CTAs are dispatched in index order: deepest games first
+    if (g >= 0) backup_game<G>(d, g, step, sm, w, lane);
 }
 
 // ============================================================ finish (getActionProb tail) ==============
