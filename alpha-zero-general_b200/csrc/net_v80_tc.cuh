@@ -80,7 +80,7 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
 
 namespace tc {
 using namespace umma;
-enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_MMA, B_PI0, B_PI1, B_PI2, B_V2, B_N };
+enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_MMA, B_PI0, B_PI1, B_PI2, B_V2, B_MM2, B_N };
 struct Phase {                            // per-thread parity of every barrier this thread waits on
     uint32_t bits = 0;
     __device__ __forceinline__ void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
@@ -241,9 +241,8 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             const float* dw = DW.w[b];
             const float* SB = SV + SV_BLK + b * SV_BLK_STRIDE;
             // ---------------- expand: D[channel][column] = We . X^T (3 passes x 7 k-steps x 2 channel halves) ----------------
-            if (t == 0) {
-                ph.wait(bars, B_WE); tc_fence_after();
-                TC_STAMP();   /* b0: expand weights landed */
+            if (t == TC_THREADS - 32) {                           // issued from the last warp (one depthwise unit), not from warp 0 (two units): the
+                ph.wait(bars, B_WE); tc_fence_after();            // issuing thread only reaches its own epilogue work once all 42 MMAs are queued
 #pragma unroll 1
                 for (int mh = 0; mh < 2; mh++) {
 #pragma unroll 1
@@ -255,19 +254,12 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                             mma_tf32(tm + TC_DE + 128 * mh, desc_sw128(wa + (ks >> 2) * TC_WE_ATOM + (ks & 3) * 32),
                                      desc_sw128(xa + (ks >> 2) * 16384 + (ks & 3) * 32), ID128, (p | ks) != 0);
                     }
+                    mma_commit(&bars[mh == 0 ? B_MMA : B_MM2]);      // channels 0-127 complete first: their depthwise pass overlaps the MMAs of 128-167
                 }
-                mma_commit(&bars[B_MMA]);
             }
             __syncwarp();
             ph.wait(bars, B_MMA); tc_fence_after();
-            TC_STAMP();   /* b1: expand MMAs done */
-            if (t == 0) {                                         // the expand image is dead: SE weights and project chunks 2, 3 take its place
-                mbar_expect_tx(&bars[B_FC], 2 * 26880);
-                bulk_g2s(ESTG, P + B.fc1, 26880, &bars[B_FC]); bulk_g2s(ESTG + 26880, P + B.fc2, 26880, &bars[B_FC]);
-                load(bars, B_WP0, WRING, IMGb + I.wp[b] + 2 * 4096, 16384);
-                load(bars, B_WP1, WRING + 16384, IMGb + I.wp[b] + 3 * 4096, 16384);
-            }
-            __syncwarp();
+            TC_STAMP();   /* b1: expand MMAs (channels 0-127) done */
             // ---------------- depthwise pass (thread = channel) ----------------
             {
                 const int c = 32 * q + lane;
@@ -275,6 +267,14 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 const uint32_t ta = tlane + TC_DE + 32 * sub;
                 if (b == 0) depthwise_unit<1, false>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
                 else depthwise_unit<2, true>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
+                ph.wait(bars, B_MM2); tc_fence_after();
+                if (t == 0) {                                     // the expand image is dead: SE weights and project chunks 2, 3 take its place
+                    mbar_expect_tx(&bars[B_FC], 2 * 26880);
+                    bulk_g2s(ESTG, P + B.fc1, 26880, &bars[B_FC]); bulk_g2s(ESTG + 26880, P + B.fc2, 26880, &bars[B_FC]);
+                    load(bars, B_WP0, WRING, IMGb + I.wp[b] + 2 * 4096, 16384);
+                    load(bars, B_WP1, WRING + 16384, IMGb + I.wp[b] + 3 * 4096, 16384);
+                }
+                __syncwarp();
                 if (q < 2) {
                     const int c2 = 128 + c; const bool ok = c2 < EC; const int cc = ok ? c2 : 0;
                     const float be2 = SB[SV_BE + cc], sd2 = SB[SV_SD + cc], td2 = SB[SV_TD + cc];

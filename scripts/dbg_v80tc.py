@@ -34,7 +34,7 @@ print('prof rc', L.azg_net_prof(net.net.h, out))
 ts = np.array(list(out), dtype=np.int64); ts = ts[ts != 0]
 names = ['tile start', 'input staged', 'first MMA done', 'first epilogue']
 for b_ in range(3):
-    names += [f'b{b_} We landed', f'b{b_} expand MMA done', f'b{b_} depthwise', f'b{b_} fc landed', f'b{b_} SE done', f'b{b_} project MMA done', f'b{b_} project epilogue']
+    names += [f'b{b_} expand MMA (ch 0-127) done', f'b{b_} depthwise', f'b{b_} fc landed', f'b{b_} SE done', f'b{b_} project MMA done', f'b{b_} project epilogue']
     if b_ == 1: names += ['policy head done']
 names += ['tile end']
 d = np.diff(ts)
