@@ -25,6 +25,11 @@
 
 namespace azg {
 
+#ifdef AZG_TC_MAXNREG
+#define TC_BOUNDS __maxnreg__(AZG_TC_MAXNREG)
+#else
+#define TC_BOUNDS __launch_bounds__(TC_THREADS, 1)
+#endif
 constexpr int TC_THREADS = 512;           // 16 warps: TMEM lane quarter = warp & 3, sub-slice = warp >> 2
 constexpr int TC_TB = 16;                 // leaves per tile (128 columns)
 // ---- shared memory map (bytes from a 1024-aligned base) ----
@@ -129,7 +134,7 @@ __device__ __forceinline__ void depthwise_unit(uint32_t taddr, float be, float s
 }  // namespace tc
 
 template <int NP>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void TC_BOUNDS
 k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __grid_constant__ V80Layout L, const __grid_constant__ V80TCImg I,
          const __grid_constant__ V80DW DW, const int* count_ptr, const int* list, const int8_t* boards, int bstride,
          const uint32_t* masks, float* pi_out, float* v_out, int n_max, long long* prof) {
@@ -139,7 +144,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bars[B_N];
     __shared__ uint32_t tmem_s;
-    __shared__ int slot_of[TB];
+    __shared__ int slot_of[TB], slot_next[TB];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31, q = warp & 3, sub = warp >> 2;
     const int count = count_ptr ? min(*count_ptr, n_max) : n_max;
     const int ntiles = (count + TB - 1) / TB;
@@ -165,6 +170,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
     const uint32_t tlane = tm + ((uint32_t)(32 * q) << 16);       // this warp's TMEM lane quarter
     if (t == 0) { mbar_arrive(&bars[B_EF0]); mbar_arrive(&bars[B_EF1]); }   // both E stages start out free
     Phase ph;
+    uint32_t rb[4] = {0u, 0u, 0u, 0u};                          // this thread's words of the next tile's raw boards (cross-tile prefetch)
     int prof_i = 0;
 #define TC_STAMP() do { if (prof && t == 0 && blockIdx.x == 0 && prof_i < 64) prof[prof_i++] = clock64(); } while (0)
     const uint32_t xh_a = smem_u32(sm + TC_XH), xl_a = smem_u32(sm + TC_XL), estg_a = smem_u32(ESTG), wring_a = smem_u32(WRING);
@@ -174,18 +180,24 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tile0 = tile * TB;
         TC_STAMP();   /* 0: tile start */
-        if (t < TB) { const int j = tile0 + t; slot_of[t] = j < count ? (list ? list[j] : j) : -1; }
+        const bool prefetched = tile != (int)blockIdx.x;          // the previous tile's value head already fetched this tile's boards (rb)
+        if (t < TB) { const int j = tile0 + t; slot_of[t] = prefetched ? slot_next[t] : (j < count ? (list ? list[j] : j) : -1); }
         if (t == 0) {
             load(bars, B_W0, WRING, IMGb + I.w0, 32768);
             load(bars, B_WP2, WRING + 32768, IMGb + I.wp[0], 16384);                 // project chunk 0 -> slot 2
             load(bars, B_WP3, WRING + 49152, IMGb + I.wp[0] + 4096, 16384);          // project chunk 1 -> slot 3
         }
-        __syncthreads();
+        if (!prefetched) __syncthreads();
         {   // raw boards -> ESTG (16 x 400 B), 32-bit loads (board rows are 392 B, slots are 4-byte aligned)
             uint32_t* raw = reinterpret_cast<uint32_t*>(ESTG);
-            for (int k = t; k < TB * 98; k += TC_THREADS) {
-                const int s = k / 98, w = k - s * 98, slot = slot_of[s];
-                raw[s * 100 + w] = slot >= 0 ? reinterpret_cast<const uint32_t*>(boards + (size_t)slot * bstride)[w] : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int k = t + i * TC_THREADS;
+                if (k < TB * 98) {
+                    const int s = k / 98, w = k - s * 98;
+                    if (!prefetched) { const int slot = slot_of[s]; rb[i] = slot >= 0 ? reinterpret_cast<const uint32_t*>(boards + (size_t)slot * bstride)[w] : 0u; }
+                    raw[s * 100 + w] = rb[i];
+                }
             }
         }
         __syncthreads();
@@ -239,6 +251,10 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         for (int b = 0; b < 3; b++) {
             const V80Layout::Blk& B = L.blk[b];
             const float* dw = DW.w[b];
+            if (b == 2 && t < TB) {                              // leaf slots of this CTA's next tile: the load has the whole value block to land
+                const int j = (tile + (int)gridDim.x) * TB + t;
+                slot_next[t] = (tile + (int)gridDim.x < ntiles && j < count) ? (list ? list[j] : j) : -1;
+            }
             const float* SB = SV + SV_BLK + b * SV_BLK_STRIDE;
             // ---------------- expand: D[channel][column] = We . X^T (3 passes x 7 k-steps x 2 channel halves) ----------------
             if (t == TC_THREADS - 32) {                           // issued from the last warp (one depthwise unit), not from warp 0 (two units): the
@@ -539,6 +555,13 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             const float* X0 = reinterpret_cast<const float*>(ESTG);
             ph.wait(bars, B_V2);
             __syncthreads();
+            if (tile + (int)gridDim.x < ntiles) {                // next tile's boards -> registers; they are stored to shared memory after this tile's last barrier
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = t + i * TC_THREADS;
+                    if (k < TB * 98) { const int s = k / 98, w = k - s * 98, slot = slot_next[s]; rb[i] = slot >= 0 ? reinterpret_cast<const uint32_t*>(boards + (size_t)slot * bstride)[w] : 0u; }
+                }
+            }
             const float* W = reinterpret_cast<const float*>(WRING);
             if (t < 384) {
                 const int s = t & 15, kp = t >> 4;               // 24 token slices x 16 leaves

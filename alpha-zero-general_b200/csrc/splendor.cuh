@@ -116,8 +116,8 @@ struct Splendor {
 
     // WARP: legal-action bitmask into `w` (MASK_WORDS words of warp-private shared memory), visible to all lanes on return.
     static __device__ __forceinline__ void valid_mask(const int8_t* b, int player, int lane, uint32_t* w) {
-#pragma unroll
-        for (int k = 0; k < MASK_WORDS; k++) {
+#pragma unroll 1
+        for (int k = 0; k < MASK_WORDS; k++) {                  // not unrolled: one copy of the (large) per-action test keeps the kernels' code small
             int a = lane + 32 * k;
             bool v = a < A && action_valid(b, a, player);
             const uint32_t m = __ballot_sync(FULL, v);
@@ -161,7 +161,9 @@ struct Splendor {
             int pc = __popc(f[c]);
             if (k >= 0 && k < pc) {
                 uint32_t rev = __brev(f[c]) >> 24;             // MSB-first position i  <->  bit i of rev
-                uint32_t t = rev; for (int j = 0; j < k; j++) t &= t - 1;
+                uint32_t t = rev;
+#pragma unroll 1
+                for (int j = 0; j < k; j++) t &= t - 1;           // drop the k lowest set bits (kept rolled: this sits in every kernel that moves)
                 colour = c; idx = __ffs(t) - 1; k = -1;
             } else if (k >= 0) k -= pc;
         }

@@ -40,3 +40,7 @@ names += ['tile end']
 d = np.diff(ts)
 for i in range(min(len(d), len(names) - 1)): print('%-26s +%7d cycles' % (names[i + 1], d[i]))
 print('tile total', ts[min(len(ts), len(names)) - 1] - ts[0], 'cycles;  stamps', len(ts))
+n1 = len(names)
+if len(ts) >= 2 * n1:
+    d2 = np.diff(ts[n1:2 * n1])
+    print('second tile of CTA 0: ' + ', '.join('%s +%d' % (names[i + 1], d2[i]) for i in range(min(3, len(d2)))) + '; total %d cycles' % (ts[2 * n1 - 1] - ts[n1]))
