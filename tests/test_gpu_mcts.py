@@ -163,3 +163,35 @@ def test_path_replay_is_exact_on_deep_trees(game, v80_golden, kat, monkeypatch):
         assert sa[k] == sb[k], k
     assert sa['node_visits'] / sa['sims'] > 6                    # the trees really are deep
     assert sa['arena_overflows'] == 0
+
+
+def test_splendor_selfplay_examples(game, hashnet):
+    """Coach.executeEpisodes on the device (Coach.py:37-148) for Splendor with chance nodes: games finish, every example is a
+    canonical board with the legal mask the rules give for it (oracle), a policy over legal moves only that sums to 1, a game
+    result from the reference's value set, and the run is reproducible from its seed; the facade augments with getSymmetries."""
+    from azg_b200.coach import Coach
+    args = dict(numMCTSSims=48, cpuct=1.25, fpu=0.0, universes=3, dirichletAlpha=-1.0, prob_fullMCTS=1.0, numEps=12)
+    runs = []
+    for rep in range(2):
+        c = Coach(game, hashnet, args, n_games=24, seed=11, node_cap=512)
+        b, pi, z, va, q = c.raw_examples(12)
+        st = c.engine.stats()
+        runs.append((b.copy(), pi.copy(), z.copy(), va.copy(), q.copy()))
+        assert st['episodes_finished'] >= 12 and st['arena_overflows'] == 0
+        if rep == 0:
+            assert len(b) >= 12 * 10 and b.shape[1:] == (56, 7)
+            assert np.allclose(pi.sum(axis=1), 1.0, atol=1e-5) and (pi[~va] == 0).all() and (pi >= 0).all()
+            for i in range(0, len(b), 7):
+                assert (O.valid_moves(b[i], 0) == va[i]).all()
+            zs = set(np.round(np.unique(z).astype(np.float64), 4).tolist())
+            assert zs <= {-1.0, 1.0, 0.01, -0.01, 0.0}, zs                 # win / loss / shared win (SplendorLogicNumba.py:221-240)
+            assert (np.abs(q) <= 1.0 + 1e-6).all()
+            ex = c.augment(b[:3], pi[:3], z[:3], va[:3], q[:3])
+            assert 3 * 10 <= len(ex) <= 3 * 14 and ex[0][0].shape == (56, 7)   # 1 + 9 card permutations + <= 4 reserve permutations
+            for e_b, e_pi, e_z, e_va, e_q in ex[:12]:
+                assert abs(float(e_pi.sum()) - 1.0) < 1e-5 and (e_pi[~e_va.astype(bool)] == 0).all()
+        c.engine.close()
+    def canon(r):                                                          # the ring is appended to with atomics: compare as a multiset
+        rows = [r[0][i].tobytes() + r[1][i].tobytes() + r[2][i].tobytes() + r[3][i].tobytes() + r[4][i].tobytes() for i in range(len(r[0]))]
+        return sorted(rows)
+    assert canon(runs[0]) == canon(runs[1])                                # same seed, same games
