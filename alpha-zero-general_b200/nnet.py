@@ -42,8 +42,11 @@ def v80_blob(state_dict):
 
 
 def random_v80_state_dict(seed=0, num_players=2):
-    """Random-init V80 weights with the reference's initialisers (kaiming_uniform_ weights, zero biases, default BN;
-    SplendorNNet.py:385-395) drawn from numpy so no torch is needed. Used by bench.py and smoke()."""
+    """Random-init V80 weights as a freshly constructed reference net really has them, drawn from numpy so no torch is needed.
+    The reference's `_init` hook (kaiming_uniform_ weights, zero biases; SplendorNNet.py:385-395) never runs: it walks
+    `self.__dict__`, which holds no sub-modules (they live in `_modules`), so every Linear keeps PyTorch's default
+    initialisation U(+-1/sqrt(fan_in)) for weights AND biases (the golden random-init state dict confirms it:
+    tests/golden/splendor_v80_rand.npz); BatchNorm is the default. Used by bench.py and smoke()."""
     rng = np.random.default_rng(seed)
     nv = 32 + 10 * num_players + num_players * num_players
     E, Q, A = 3 * nv, 40 * nv // 56, 81
@@ -67,8 +70,12 @@ def random_v80_state_dict(seed=0, num_players=2):
         if isinstance(shp[0], tuple):
             sd[name] = np.full(shp[0], shp[1], np.float32)
         else:
-            bound = np.sqrt(6.0 / shp[1])                       # kaiming_uniform_(a=0): gain sqrt(2) * sqrt(3/fan_in)
+            bound = 1.0 / np.sqrt(shp[1])                       # nn.Linear default: kaiming_uniform_(a=sqrt(5)) = U(+-1/sqrt(fan_in))
             sd[name] = rng.uniform(-bound, bound, size=shp).astype(np.float32)
+    for name in list(sd):                                       # Linear biases (SE and head linears): U(+-1/sqrt(fan_in)) as well
+        if name.endswith('.bias') and '.norm.' not in name:
+            fan_in = shapes[name[:-5] + '.weight'][1]
+            sd[name] = rng.uniform(-1.0 / np.sqrt(fan_in), 1.0 / np.sqrt(fan_in), size=sd[name].shape).astype(np.float32)
     return sd
 
 
@@ -100,9 +107,9 @@ def v89_blob(state_dict):
 
 
 def random_v89_state_dict(seed=0):
-    """Random-init V89 weights drawn from numpy with the reference's initialisers: PyTorch-default convolutions
-    (kaiming_uniform_(a=sqrt(5)) => U(+-1/sqrt(fan_in))), kaiming_uniform_ Linear weights with zero biases
-    (SantoriniNNet.py:222-232), default BatchNorm. Used by bench.py and smoke()."""
+    """Random-init V89 weights drawn from numpy as a freshly constructed reference net has them: PyTorch-default convolutions and
+    Linears (U(+-1/sqrt(fan_in)) for weights and Linear biases; the `_init` hook of SantoriniNNet.py:222-232 never touches a
+    layer, see random_v80_state_dict), default BatchNorm. Used by bench.py and smoke()."""
     rng = np.random.default_rng(seed)
     sd = {}
 
@@ -115,8 +122,8 @@ def random_v89_state_dict(seed=0):
         sd[f'{prefix}.running_mean'] = np.zeros(ch, np.float32); sd[f'{prefix}.running_var'] = np.ones(ch, np.float32)
 
     def lin(name, out, inn):
-        b = np.sqrt(6.0 / inn)
-        sd[f'{name}.weight'] = rng.uniform(-b, b, size=(out, inn)).astype(np.float32); sd[f'{name}.bias'] = np.zeros(out, np.float32)
+        b = 1.0 / np.sqrt(inn)
+        sd[f'{name}.weight'] = rng.uniform(-b, b, size=(out, inn)).astype(np.float32); sd[f'{name}.bias'] = rng.uniform(-b, b, size=out).astype(np.float32)
 
     conv('first_layer.0.weight', 64, 2, 3); bn('first_layer.1', 64)
     for blk in range(5):
@@ -152,9 +159,8 @@ def v21_blob(state_dict):
 
 
 def random_v21_state_dict(seed=0):
-    """Random-init V21 weights from numpy with the reference's initialisers (PyTorch-default / torchvision kaiming_normal_
-    fan_out convolutions approximated by U(+-1/sqrt(fan_in)), kaiming_uniform_ Linear weights with zero biases, default
-    BatchNorm). Used by bench.py only."""
+    """Random-init V21 weights from numpy as a freshly constructed reference net has them (PyTorch-default convolutions and Linears:
+    U(+-1/sqrt(fan_in)) for weights and Linear biases, see random_v80_state_dict; default BatchNorm). Used by bench.py only."""
     rng = np.random.default_rng(seed)
     sd = {}
 
@@ -167,8 +173,8 @@ def random_v21_state_dict(seed=0):
         sd[f'{prefix}.running_mean'] = np.zeros(ch, np.float32); sd[f'{prefix}.running_var'] = np.ones(ch, np.float32)
 
     def lin(name, out, inn):
-        b = np.sqrt(6.0 / inn)
-        sd[f'{name}.weight'] = rng.uniform(-b, b, size=(out, inn)).astype(np.float32); sd[f'{name}.bias'] = np.zeros(out, np.float32)
+        b = 1.0 / np.sqrt(inn)
+        sd[f'{name}.weight'] = rng.uniform(-b, b, size=(out, inn)).astype(np.float32); sd[f'{name}.bias'] = rng.uniform(-b, b, size=out).astype(np.float32)
 
     conv('first_layer.0.weight', 24, 3, 3); bn('first_layer.1', 24)
     for blk in range(4):
