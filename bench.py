@@ -327,7 +327,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')                          # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom)
+        traffic = (json.load(open(tp)).get(args.game) or {}).get(dom)               # per game: only captures of the same workload count
     roofline = {'kernel': dom, 'bound': kern[dom]['bound'], 'achieved': kern[dom]['achieved'], 'peak': kern[dom]['peak'], 'unit': kern[dom]['unit'],
                 'frac': kern[dom]['frac'], 'traffic': traffic, 'peak_source': pk['src'] + (' sustained bf16' if kern[dom]['bound'] == 'tensor' else ''),
                 'avg_launch_us': kern[dom]['avg_launch_us'], 'share_of_step': kern[dom]['share']}
