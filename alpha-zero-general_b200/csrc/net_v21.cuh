@@ -16,7 +16,7 @@
 
 namespace azg {
 
-constexpr int V21_THREADS = 256;
+constexpr int V21_THREADS = 1024;         // 32 warps per (single-CTA) SM: the layers are latency-bound weight broadcasts, more warps hide it
 constexpr int V21_TB = 4;
 constexpr int V21_N = V21_TB * 81;        // positions per tile
 constexpr int V21_A = 3402, V21_MW = 107;
@@ -173,7 +173,7 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
         for (int j = 0; j < 6; j++) LG[l * A + pos * 42 + o0 + j] = acc[j] + __ldg(P + L.bpi + o0 + j);
     }
     __syncthreads();
-    {   // value Linear(340 -> 64) + ReLU: one thread per (leaf, output)
+    if (t < TB * 64) {   // value Linear(340 -> 64) + ReLU: one thread per (leaf, output)
         const int l = t >> 6, j = t & 63;
         float a = __ldg(P + L.f1b + j);
         for (int i = 0; i < 340; i++) a = fmaf(__ldg(P + L.f1 + i * 64 + j), VC[l * 340 + i], a);
