@@ -50,6 +50,7 @@ constexpr int TC_PIRING_SLOT = 18816;     // 56 rows of the [392][84] policy mat
 // ---- TMEM columns ----
 constexpr int TC_DE = 0;                  // expand accumulator: [0,128) channels 0-127, [128,256) channels 128-167 on lanes 0-39
 constexpr int TC_DP = 256;                // first_layer / project accumulator: [256,320) hi-weight part, [320,384) lo-weight part
+constexpr int TC_T = 384;                 // the block input (fp32, [column][token]) is parked here while the E stages borrow X's shared memory
 
 struct V80TCImg { int w0; int we[3]; int wp[3]; int total; };   // float offsets into the image blob
 inline V80TCImg v80tc_layout() {
@@ -85,7 +86,7 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
 
 namespace tc {
 using namespace umma;
-enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_MMA, B_PI0, B_PI1, B_PI2, B_V2, B_MM2, B_N };
+enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_V2, B_MM2, B_N };
 struct Phase {                            // per-thread parity of every barrier this thread waits on
     uint32_t bits = 0;
     __device__ __forceinline__ void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
@@ -97,6 +98,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {          // hi = x rounded to TF32, hi + lo == x exactly
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
@@ -164,11 +170,11 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
     }
     if (t == 0) { for (int i = 0; i < B_N; i++) mbar_init(&bars[i], 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc<512>(&tmem_s);
-    for (int i = t; i < 65536 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);   // token columns 56..63 stay zero for ever
+    for (int i = t; i < 65536 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);   // token columns 56..63 only ever meet zero weights (they hold stale finite data once X's planes have served as E stages)
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tm = tmem_s;
     const uint32_t tlane = tm + ((uint32_t)(32 * q) << 16);       // this warp's TMEM lane quarter
-    if (t == 0) { mbar_arrive(&bars[B_EF0]); mbar_arrive(&bars[B_EF1]); }   // both E stages start out free
+    if (t == 0) { for (int i = 0; i < 4; i++) mbar_arrive(&bars[B_EF0 + i]); }   // the four E stages start out free
     Phase ph;
     uint32_t rb[4] = {0u, 0u, 0u, 0u};                          // this thread's words of the next tile's raw boards (cross-tile prefetch)
     int prof_i = 0;
@@ -284,6 +290,24 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 if (b == 0) depthwise_unit<1, false>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
                 else depthwise_unit<2, true>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
                 ph.wait(bars, B_MM2); tc_fence_after();
+                {   // X has been consumed by the expand MMAs. The block input (the residual of the project epilogue, and for the policy block
+                    // also the input of the value block) is parked in spare TMEM columns as fp32, which frees X's 64 KB of shared memory
+                    // as E stages 2 and 3 for the gated operand pass below.
+                    const int row = 32 * q + lane, c0 = 16 * sub;
+                    uint32_t xv[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const int c = c0 + 4 * j4;
+                        float4 rh = make_float4(0.f, 0.f, 0.f, 0.f), rl = rh;
+                        if (c < NV) {
+                            const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
+                            rh = *reinterpret_cast<const float4*>(sm + TC_XH + o); rl = *reinterpret_cast<const float4*>(sm + TC_XL + o);
+                        }
+                        xv[4 * j4 + 0] = __float_as_uint(rh.x + rl.x); xv[4 * j4 + 1] = __float_as_uint(rh.y + rl.y);
+                        xv[4 * j4 + 2] = __float_as_uint(rh.z + rl.z); xv[4 * j4 + 3] = __float_as_uint(rh.w + rl.w);
+                    }
+                    tmem_st16(tlane + TC_T + c0, xv);
+                }
                 if (t == 0) {                                     // the expand image is dead: SE weights and project chunks 2, 3 take its place
                     mbar_expect_tx(&bars[B_FC], 2 * 26880);
                     bulk_g2s(ESTG, P + B.fc1, 26880, &bars[B_FC]); bulk_g2s(ESTG + 26880, P + B.fc2, 26880, &bars[B_FC]);
@@ -356,15 +380,15 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             }
             __syncthreads();
             TC_STAMP();   /* b4: SE done */
-            // ---------------- SE-gated operand pass + project MMAs, three rounds of two 32-channel K chunks ----------------
+            // ---------------- SE-gated operand pass + project MMAs: three rounds of two 32-channel K chunks through FOUR stages (two in
+            //                  ESTG, two in X's planes), so a round's MMAs run while the next round's operands are written ----------------
 #pragma unroll 1
             for (int r = 0; r < 3; r++) {
-                ph.wait(bars, B_EF0); ph.wait(bars, B_EF1);       // the MMAs that read the two stages (previous round) are done
-                if (t == 0 && r == 1) {                           // their weight slots are free too: chunks 4, 5
-                    load(bars, B_WP2, WRING + 32768, IMGb + I.wp[b] + 4 * 4096, 16384);
-                    load(bars, B_WP3, WRING + 49152, IMGb + I.wp[b] + 5 * 4096, 16384);
-                }
-                __syncwarp();
+                const int s0 = (2 * r) & 3;                       // stages of this round: s0, s0 + 1
+                ph.wait(bars, B_EF0 + s0); ph.wait(bars, B_EF0 + s0 + 1);   // the MMAs that read them (two rounds ago) are done
+#ifdef AZG_TC_ROUND_PROF
+                if (b == 0) TC_STAMP();
+#endif
                 const bool active = (r == 1) ? (q >= 2) : (q < 2);
                 const int c = (r == 2 ? 128 : 0) + 32 * q + lane;
                 if (active) {                                     // warp-uniform: the TMEM load is warp-collective
@@ -374,36 +398,61 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     if (c < EC) {
                         const float4 g4 = *reinterpret_cast<const float4*>(SQ + c * TB + 4 * sub);
                         const float gate[4] = {g4.x, g4.y, g4.z, g4.w};
-                        uint8_t* eh = ESTG + (q & 1) * 32768; uint8_t* el = eh + 16384;
+                        const int stg = s0 + (q & 1);
+                        uint8_t* eh = (stg < 2 ? ESTG + stg * 32768 : sm + TC_XH + (stg - 2) * 32768) + sub * 4096;   // rows 32 sub .. 32 sub + 31 of the stage
+                        // element i -> row 32 sub + i, k = lane: byte offset (i >> 3) * 1024 + (i & 7) * 128 + (((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4.
+                        // The lane-dependent part only depends on i & 7: eight base pointers, everything else is an immediate.
+                        uint8_t* eb[8];
+#pragma unroll
+                        for (int v = 0; v < 8; v++) eb[v] = eh + ((((lane >> 2) ^ v) & 7) << 4) + ((lane & 3) << 2);
 #pragma unroll
                         for (int i = 0; i < 32; i++) {
                             float hi, lo; split_rn(__uint_as_float(d[i]) * gate[i >> 3], hi, lo);
-                            const uint32_t o = sw128_off(32 * sub + i, lane);
-                            *reinterpret_cast<float*>(eh + o) = hi; *reinterpret_cast<float*>(el + o) = lo;
+                            uint8_t* pdst = eb[i & 7] + (i >> 3) * 1024 + (i & 7) * 128;
+                            *reinterpret_cast<float*>(pdst) = hi; *reinterpret_cast<float*>(pdst + 16384) = lo;
                         }
                     }
                 }
+#ifdef AZG_TC_ROUND_PROF
+                if (b == 0) TC_STAMP();
+#endif
                 fence_async_smem(); tc_fence_before(); __syncthreads();
-                if (t == 0) {
+#ifdef AZG_TC_ROUND_PROF
+                if (b == 0) TC_STAMP();
+#endif
+                // The MMAs of a round are issued by a thread whose warp does NOT write operands in the next round (issuing sixteen MMAs
+                // takes one thread longer than the other warps need to write the next operands, and the next barrier waits for it):
+                // quarters 0-1 write in rounds 0 and 2, quarters 2-3 in round 1, so thread 0 issues rounds 0 and 2, the last warp round 1.
+                if (t == (r == 1 ? TC_THREADS - 32 : 0)) {
                     tc_fence_after();
 #pragma unroll 1
                     for (int jj = 0; jj < 2; jj++) {
-                        const int j = 2 * r + jj, slot = (j + 2) & 3;
+                        const int j = 2 * r + jj, slot = (j + 2) & 3, stg = s0 + jj;
                         ph.wait(bars, B_WP0 + slot); tc_fence_after();
-                        const uint32_t ea = estg_a + jj * 32768, wa = wring_a + slot * 16384;
+                        const uint32_t ea = stg < 2 ? estg_a + stg * 32768 : xh_a + (stg - 2) * 32768, wa = wring_a + slot * 16384;
+                        const uint64_t dh_ = desc_sw128(ea), dl_ = desc_sw128(ea + 16384), dw_ = desc_sw128(wa);
                         const int nks = j == 5 ? 1 : 4;
-#pragma unroll 1
-                        for (int ks = 0; ks < nks; ks++) {
-                            mma_tf32(tm + TC_DP, desc_sw128(ea + ks * 32), desc_sw128(wa + ks * 32), ID128, (j | ks) != 0);           // E_hi . (W_hi | W_lo)
-                            mma_tf32(tm + TC_DP, desc_sw128(ea + 16384 + ks * 32), desc_sw128(wa + ks * 32), ID64, true);            // E_lo . W_hi
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            if (ks < nks) {
+                                mma_tf32(tm + TC_DP, dh_ + 2 * ks, dw_ + 2 * ks, ID128, (j | ks) != 0);     // E_hi . (W_hi | W_lo); +32 B per k-step = +2 in the descriptor
+                                mma_tf32(tm + TC_DP, dl_ + 2 * ks, dw_ + 2 * ks, ID64, true);               // E_lo . W_hi
+                            }
                         }
-                        mma_commit(&bars[B_EF0 + jj]);
+                        mma_commit(&bars[B_EF0 + stg]);
                     }
                     if (r == 2) mma_commit(&bars[B_MMA]);
+                    if (r == 1) {                                 // round 0's MMAs (issued first) free the weight slots of chunks 0, 1 for chunks 4, 5;
+                        mbar_wait(&bars[B_EF0], (ph.bits >> B_EF0) & 1u); mbar_wait(&bars[B_EF1], (ph.bits >> B_EF1) & 1u);   // peek: round 2 waits again
+                        load(bars, B_WP2, WRING + 32768, IMGb + I.wp[b] + 4 * 4096, 16384);
+                        load(bars, B_WP3, WRING + 49152, IMGb + I.wp[b] + 5 * 4096, 16384);
+                    }
                 }
                 __syncwarp();
             }
-            ph.wait(bars, B_MMA); tc_fence_after();
+            ph.wait(bars, B_MMA);                                 // rounds 0 and 2 (committed by their issuing thread) ...
+            mbar_wait(&bars[B_EF2], ((ph.bits >> B_EF2) & 1u)); mbar_wait(&bars[B_EF3], ((ph.bits >> B_EF3) & 1u));   // ... and round 1 (peek: the next block's round 1 waits again)
+            tc_fence_after();
             TC_STAMP();   /* b5: project MMAs done */
             if (t == 0) {                                         // everything in ESTG / WRING has been consumed
                 if (b == 0) {
@@ -418,30 +467,29 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 }
             }
             __syncwarp();
-            {   // project epilogue: bias + residual; trunk output -> operand planes in place, head outputs -> plain [token][column] in ESTG
+            {   // project epilogue: bias + residual (the parked block input); trunk output -> X's operand planes, head outputs -> plain
+                // [token][feature][leaf] in ESTG; after the policy block the parked trunk output goes back into X's planes for the value block
                 const int row = 32 * q + lane, c0 = 16 * sub;
-                uint32_t dh[16], dl[16];
-                tmem_ld16(tlane + TC_DP + c0, dh); tmem_ld16(tlane + TC_DP + 64 + c0, dl); tmem_wait_ld();
+                uint32_t dh[16], dl[16], xr[16];
+                tmem_ld16(tlane + TC_DP + c0, dh); tmem_ld16(tlane + TC_DP + 64 + c0, dl); tmem_ld16(tlane + TC_T + c0, xr); tmem_wait_ld();
                 float* HO = reinterpret_cast<float*>(ESTG);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; j4++) {
                     const int c = c0 + 4 * j4;
                     if (c < NV) {
                         const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
-                        const float4 rh = *reinterpret_cast<const float4*>(sm + TC_XH + o), rl = *reinterpret_cast<const float4*>(sm + TC_XL + o);
-                        const float res[4] = {rh.x + rl.x, rh.y + rl.y, rh.z + rl.z, rh.w + rl.w};
-                        float y[4];
+                        float y[4], hi[4], lo[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) y[j] = __uint_as_float(dh[4 * j4 + j]) + __uint_as_float(dl[4 * j4 + j]) + SB[SV_BP + c + j] + res[j];
-                        if (b == 0) {
-                            float hi[4], lo[4];
+                        for (int j = 0; j < 4; j++) y[j] = __uint_as_float(dh[4 * j4 + j]) + __uint_as_float(dl[4 * j4 + j]) + SB[SV_BP + c + j] + __uint_as_float(xr[4 * j4 + j]);
+                        if (b != 0) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) { HO[(c + j) * LD + (row & 7) * TB + (row >> 3)] = y[j]; y[j] = __uint_as_float(xr[4 * j4 + j]); }   // [token][feature][leaf]
+                        }
+                        if (b != 2) {                             // b == 0: the trunk output; b == 1: the trunk output again (X's planes served as E stages)
 #pragma unroll
                             for (int j = 0; j < 4; j++) split_rn(y[j], hi[j], lo[j]);
                             *reinterpret_cast<float4*>(sm + TC_XH + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                             *reinterpret_cast<float4*>(sm + TC_XL + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) HO[(c + j) * LD + (row & 7) * TB + (row >> 3)] = y[j];   // [token][feature][leaf]
                         }
                     }
                 }

@@ -38,6 +38,8 @@ for b_ in range(3):
     if b_ == 1: names += ['policy head done']
 names += ['tile end']
 d = np.diff(ts)
+if os.environ.get('ROUND_PROF'):
+    print('raw stamp deltas of the first tile:', d[:45].tolist())
 for i in range(min(len(d), len(names) - 1)): print('%-26s +%7d cycles' % (names[i + 1], d[i]))
 print('tile total', ts[min(len(ts), len(names)) - 1] - ts[0], 'cycles;  stamps', len(ts))
 n1 = len(names)
