@@ -86,7 +86,7 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
 
 namespace tc {
 using namespace umma;
-enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_V2, B_MM2, B_N };
+enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_PI3, B_V2, B_MM2, B_N };
 struct Phase {                            // per-thread parity of every barrier this thread waits on
     uint32_t bits = 0;
     __device__ __forceinline__ void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
@@ -460,8 +460,9 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     load(bars, B_WP2, WRING + 32768, IMGb + I.wp[1], 16384);
                     load(bars, B_WP3, WRING + 49152, IMGb + I.wp[1] + 4096, 16384);
                 } else if (b == 1) {
-                    load(bars, B_PI0, WRING, P + L.pi2, TC_PIRING_SLOT);
-                    load(bars, B_PI1, WRING + TC_PIRING_SLOT, P + L.pi2 + 56 * PIP, TC_PIRING_SLOT);
+                    load(bars, B_PI0, WRING, P + L.pi2, TC_PIRING_SLOT);                  // policy weight ring: four slots (the last one runs over
+                    load(bars, B_PI1, WRING + TC_PIRING_SLOT, P + L.pi2 + 56 * PIP, TC_PIRING_SLOT);          // into SQ, whose gates are consumed), three
+                    load(bars, B_PI2, WRING + 2 * TC_PIRING_SLOT, P + L.pi2 + 112 * PIP, TC_PIRING_SLOT);     // loads in flight ahead of the math
                 } else {
                     load(bars, B_V2, WRING, P + L.v2, NV * 7 * 4 * 4);
                 }
@@ -503,23 +504,28 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 float* H1 = reinterpret_cast<float*>(ESTG + 28672); float* LG = H1 + PIP * TB;
                 int ent = 0;
                 auto acquire = [&]() -> const float* {           // next ring entry (7 x pi2 chunk, 2 x pi4 part); barrier = previous entry fully consumed
-                    const int s = ent % 3;
+                    const int s = ent & 3;
                     ph.wait(bars, B_PI0 + s);
                     __syncthreads();
-                    if (t == 0 && ent + 2 < 9) {
-                        const int e = ent + 2, s2 = e % 3;
+                    if (t == 0 && ent + 3 < 9) {
+                        const int e = ent + 3, s2 = e & 3;
                         const float* src = e < 7 ? P + L.pi2 + e * 56 * PIP : (e == 7 ? P + L.pi4 : P + L.pi4 + 41 * PIP);
                         const uint32_t bytes = e < 7 ? TC_PIRING_SLOT : (e == 7 ? 41 * PIP * 4 : 40 * PIP * 4);
                         load(bars, B_PI0 + s2, WRING + s2 * TC_PIRING_SLOT, src, bytes);
                     }
                     ent++;
+#ifdef AZG_TC_POLICY_PROF
+                    TC_STAMP();
+#endif
                     return reinterpret_cast<const float*>(WRING + s * TC_PIRING_SLOT);
                 };
-                // 176 tasks = 4 K-slices x 11 output octets x 4 leaf quads (register tile 8 x 4: 32 FMA per three 128-bit loads; the loads,
-                // not the FMAs, are the limit); partial sums meet in PP and are summed in a fixed order
+                // 352 tasks = 8 K-slices x 11 output octets x 4 leaf quads (register tile 8 x 4: 32 FMA per three 128-bit loads; the loads,
+                // not the FMAs, are the limit, so the work is spread over 11 warps). Slices s and s + 4 sit in lanes l and l ^ 16 of one warp
+                // and are summed by shuffle; the four remaining partial sums meet in PP and are added in a fixed order.
                 float* PP = reinterpret_cast<float*>(ESTG + 39424);   // [4][84][16]
-                const bool live = t < 176;
-                const int part = min(t / 44, 3), rem = t - part * 44, o8 = rem >> 2, lq = rem & 3;
+                const bool live = t < 352;
+                const int unit = min((t >> 5) * 16 + (t & 15), 175), half = (t >> 4) & 1;
+                const int part = unit / 44, task = unit - part * 44, o8 = task >> 2, lq = task & 3, slice = part + 4 * half;
                 const bool hi_ok = o8 < 10;                       // the last octet only has outputs 80..83
                 float acc[8][4];
 #pragma unroll
@@ -532,39 +538,51 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #pragma unroll
                         for (int j = 0; j < 4; j++) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
                 };
-                auto flush = [&]() {
+                auto flush = [&]() {                              // lanes l and l ^ 16 hold the two K-slices of one task
 #pragma unroll
                     for (int i = 0; i < 8; i++)
-                        if (i < 4 || hi_ok) *reinterpret_cast<float4*>(PP + (part * PIP + 8 * o8 + i) * TB + 4 * lq) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] += __shfl_xor_sync(FULL, acc[i][j], 16);
+                    if (live && half == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (i < 4 || hi_ok) *reinterpret_cast<float4*>(PP + (part * PIP + 8 * o8 + i) * TB + 4 * lq) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
                 };
                 for (int ch = 0; ch < NV / 8; ch++) {
                     const float* W = acquire();
-                    if (live) {
-#pragma unroll 2
-                        for (int il = 0; il < 2; il++) {                 // K-slice `part` = tokens 2*part, 2*part + 1 of this 8-token chunk
-                            const float* xp = X0 + (8 * ch + 2 * part + il) * LD + 4 * lq;
-                            const float* wp = W + ((2 * part + il) * 7) * PIP + 8 * o8;
+                    if (live) {                                   // K-slice `slice` = token `slice` of this 8-token chunk: 7 rows
+                        const float* xp = X0 + (8 * ch + slice) * LD + 4 * lq;
+                        const float* wp = W + (slice * 7) * PIP + 8 * o8;
 #pragma unroll
-                            for (int f = 0; f < 7; f++) fma_row(wp + f * PIP, *reinterpret_cast<const float4*>(xp + f * TB));
-                        }
+                        for (int f = 0; f < 7; f++) fma_row(wp + f * PIP, *reinterpret_cast<const float4*>(xp + f * TB));
                     }
+#ifdef AZG_TC_POLICY_PROF
+                    TC_STAMP();
+#endif
                 }
-                if (live) flush();
+                flush();
                 __syncthreads();
+#ifdef AZG_TC_POLICY_PROF
+                TC_STAMP();
+#endif
                 for (int i = t; i < PIP * TB; i += TC_THREADS)
                     H1[i] = fmaxf(PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI2 + (i >> 4)], 0.f);
                 for (int ch = 0; ch < 2; ch++) {
                     const float* W = acquire();                   // first barrier: H1 complete (and PP consumed)
                     if (live) {
-                        const int k0 = max(21 * part, 41 * ch), k1 = min(min(21 * part + 21, 81), ch == 0 ? 41 : 81);
+                        const int k0 = max(11 * slice, 41 * ch), k1 = min(min(11 * slice + 11, 81), ch == 0 ? 41 : 81);
 #pragma unroll 2
                         for (int k = k0; k < k1; k++) fma_row(W + (k - 41 * ch) * PIP + 8 * o8, *reinterpret_cast<const float4*>(H1 + k * TB + 4 * lq));
                     }
                 }
-                if (live) flush();
+                flush();
                 __syncthreads();
+#ifdef AZG_TC_POLICY_PROF
+                TC_STAMP();
+#endif
                 for (int i = t; i < PIP * TB; i += TC_THREADS) LG[i] = PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI4 + (i >> 4)];
                 __syncthreads();
                 {   // masked softmax: where(valid, logits, -1e8) -> log_softmax -> exp (SplendorNNet.py:404,440; GenericNNetWrapper.py:119)
