@@ -475,7 +475,8 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
     int idx = d.root_node[g] - 1;
     // ---- path replay, part 1: the previous walk of this universe. Fetch the header and best link of every node it recorded
     //      (levels 1..32 here, one lane each, all loads in flight together) before the dependent walk starts.
-    const int plen = d.replay ? *d.g_path_len(g, uni) : 0;
+    int plen = d.replay ? *d.g_path_len(g, uni) : 0;
+    if (plen <= 4) plen = 0;                                     // shallow walks: the parallel fetch costs more than the two or three round trips it saves
 #if AZG_SEL_PROF == 1
     if (lane == 0) atomicAdd(&g_selprof2[6], (unsigned long long)plen);
 #endif
