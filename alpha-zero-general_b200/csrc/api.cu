@@ -547,6 +547,7 @@ struct EngineT : azg_engine {
         bad |= alloc(&d.path, (size_t)NG * d.U * G::MAX_DEPTH); bad |= alloc(&d.path_len, (size_t)NG * d.U); bad |= alloc(&d.leaf_kind, NG);
         bad |= alloc(&d.leaf_key, (size_t)2 * NG); bad |= alloc(&d.leaf_v, (size_t)NG * G::NP); bad |= alloc(&d.leaf_mask, (size_t)NG * G::MASK_WORDS);
         bad |= alloc(&d.leaf_round, NG);
+        bad |= alloc(&d.noise_scr, (size_t)NG * G::A, false);
         bad |= alloc(&d.nn_in, (size_t)NG * G::SP); bad |= alloc(&d.nn_pi, (size_t)NG * G::A); bad |= alloc(&d.nn_v, (size_t)NG * G::NP);
         bad |= alloc(&d.nn_list, NG); bad |= alloc(&d.nn_count, 1); bad |= alloc(&d.stats, (size_t)NG * ST_N);
         if (bad) return bad;

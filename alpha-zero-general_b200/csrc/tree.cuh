@@ -76,6 +76,7 @@ struct Dev {
     int* n_sims;               // sims requested for the current search
     uint8_t* full;             // full-search flag (MCTS.py:58)
     const double* noise;       // injected Dirichlet draws [G][A] or nullptr
+    double* noise_scr;         // [G][A] f64 scratch of the root re-noising in k_select
     unsigned* move_ctr;        // searches done in this slot (RNG counter)
     // per-simulation scratch
     PathEnt* path; int* path_len; int* leaf_kind; uint64_t* leaf_key; float* leaf_v; uint32_t* leaf_mask; int* leaf_round;
@@ -372,10 +373,18 @@ template <class G> struct WarpSmem {
     uint32_t mask[G::MASK_WORDS];                                // legal-action bitmask of the state being expanded / re-noised
     uint64_t key[2]; int np;                                     // key / next player of the state in `board` (select kernel)
 };
+// k_select only needs the board being materialised, its mask and key: the A-sized prior / Dirichlet scratch of the (once per search)
+// root re-noising lives in global memory (nn_pi is idle then, plus d.noise_scr), so the kernel keeps 4 warps per CTA and full
+// occupancy even with Abalone's 3402 actions.
+template <class G> struct SelSmem {
+    __align__(16) int8_t board[G::SP];
+    uint32_t mask[G::MASK_WORDS];
+    uint64_t key[2]; int np;
+};
 // Warps per CTA of the one-warp-per-game kernels: 4, or 1 when the per-warp scratch is large (Abalone: 3402 actions).
 template <class G> __host__ __device__ constexpr int sel_warps() { return sizeof(WarpSmem<G>) * 4 <= 40 * 1024 ? 4 : 1; }
 // Warps per CTA of k_select (AZG_SELK_WARPS where the per-warp scratch allows it)
-template <class G> __host__ __device__ constexpr int selk_warps() { return sizeof(WarpSmem<G>) * AZG_SELK_WARPS <= 40 * 1024 ? AZG_SELK_WARPS : 1; }
+template <class G> __host__ __device__ constexpr int selk_warps() { return sizeof(SelSmem<G>) * AZG_SELK_WARPS <= 40 * 1024 ? AZG_SELK_WARPS : 1; }
 
 template <class G> __device__ __forceinline__ void warp_load_board(int8_t* sb, const int8_t* src, int lane) {
     if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(src)[lane];
@@ -389,15 +398,15 @@ template <class G> __device__ __forceinline__ void warp_store_board(int8_t* dst,
 // Re-noise an already expanded root (MCTS.py:156-160): the stored P of the root's edges gets a fresh Dirichlet mix.
 template <class G>
 __device__ __noinline__ void renoise_root(const Dev<G>& d, int g, uint32_t edge_off, int n_legal, Edge* edges, const typename G::act_t* acts,
-                                          WarpSmem<G>& ws, int lane) {
+                                          SelSmem<G>& ws, int lane) {
     struct { uint32_t edge_off; int n_legal; } h = {edge_off, n_legal};
-    float* pf = ws.f; uint32_t* m = ws.mask;
+    float* pf = d.nn_pi + (size_t)g * G::A; uint32_t* m = ws.mask;   // nn_pi[g] is idle until the net runs: dense prior scratch
     for (int k = lane; k < G::MASK_WORDS; k += 32) m[k] = 0;
     for (int a = lane; a < G::A; a += 32) pf[a] = 0.f;
     __syncwarp();
     for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; pf[a] = edges[h.edge_off + i].p; atomicOr(&m[a >> 5], 1u << (a & 31)); }
     __syncwarp();
-    root_noise<G>(d, g, pf, ws.d, m, lane);
+    root_noise<G>(d, g, pf, d.noise_scr + (size_t)g * G::A, m, lane);
     float s = warp_sum_avx2order(pf, G::A, lane);
     float inv = __fdiv_rn(1.0f, s);
     for (int i = lane; i < h.n_legal; i += 32) { int a = acts[h.edge_off + i]; edges[h.edge_off + i].p = __fmul_rn(pf[a], inv); }
@@ -408,7 +417,7 @@ __device__ __noinline__ void renoise_root(const Dev<G>& d, int g, uint32_t edge_
 // then the reference's dict lookup (MCTS.py:125-126) as a hash-table probe. The board stays in shared memory, its
 // key in ws.key; returns (found node index, or -1) and the next player in ws.np. Kept out of line: once per simulation.
 template <class G>
-__device__ __noinline__ int materialise_child(const Dev<G>& d, int g, WarpSmem<G>& ws, int parent, int action, long long seed, int lane) {
+__device__ __noinline__ int materialise_child(const Dev<G>& d, int g, SelSmem<G>& ws, int parent, int action, long long seed, int lane) {
     int8_t* sb = ws.board;
     warp_load_board<G>(sb, d.g_boards(g) + (size_t)parent * G::SP, lane);
     int np = 0;
@@ -425,7 +434,7 @@ __device__ __noinline__ int materialise_child(const Dev<G>& d, int g, WarpSmem<G
 
 // Root of this search (MCTS.py:125-126 for the top-level call): board from d.root, key in ws.key; returns its node or -1.
 template <class G>
-__device__ __noinline__ int locate_root(const Dev<G>& d, int g, WarpSmem<G>& ws, int lane) {
+__device__ __noinline__ int locate_root(const Dev<G>& d, int g, SelSmem<G>& ws, int lane) {
     warp_load_board<G>(ws.board, d.root + (size_t)g * G::SP, lane);
     uint64_t klo, khi;
     board_hash<G>(ws.board, lane, klo, khi);
@@ -438,7 +447,7 @@ __device__ __noinline__ int locate_root(const Dev<G>& d, int g, WarpSmem<G>& ws,
 
 // The state in ws.board has never been seen (MCTS.py:130-154): terminal test, else legal mask + hand-over to the net.
 template <class G>
-__device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, uint32_t link_slot, int lane) {
+__device__ __noinline__ int new_leaf(const Dev<G>& d, int g, SelSmem<G>& ws, uint32_t link_slot, int lane) {
     const int8_t* sb = ws.board;
     float es[G::NP];
     int kind;
@@ -458,7 +467,7 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, WarpSmem<G>& ws, ui
 
 // ============================================================ select ==================================
 template <class G>
-__device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const int step, WarpSmem<G>* sm, const int w, const int lane) {
+__device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const int step, SelSmem<G>* sm, const int w, const int lane) {
     if (step >= d.n_sims[g]) { if (lane == 0) d.leaf_kind[g] = LEAF_NONE; return; }
     const bool full = d.full ? d.full[g] != 0 : true;
     const bool forced_root = full && d.forced_playouts;
@@ -592,7 +601,7 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
 // One CTA per work item (persistent warps pulling tickets from a global counter were measured: no gain for k_select, a loss for k_backup).
 template <class G>
 __global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 32 : AZG_SEL_MIN_BLOCKS) k_select(const __grid_constant__ Dev<G> d, int step) {
-    __shared__ WarpSmem<G> sm[selk_warps<G>()];
+    __shared__ SelSmem<G> sm[selk_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x < 32) d.ord_cnt[(step & 1) * 32 + threadIdx.x] = 0;     // the set this simulation's backup fills
     WorkOrder<G> wo; wo.load(d, step, lane);
