@@ -599,7 +599,7 @@ struct EngineT : azg_engine {
         prof_mark(PK_NET, st);
         if (net_forward_dev<G>(net, d.nn_count, d.nn_list, d.nn_in, G::SP, d.leaf_mask, d.nn_pi, d.nn_v, NG, st)) return 1;
         prof_mark(PK_BACKUP, st);
-        k_backup<G><<<grid(), sel_warps<G>() * 32, 0, st>>>(d, s);
+        k_backup<G><<<(unsigned)((NG + bak_warps<G>() - 1) / bak_warps<G>()), bak_warps<G>() * 32, 0, st>>>(d, s);
         prof_mark(-1, st);
         launches += 3;
         return 0;

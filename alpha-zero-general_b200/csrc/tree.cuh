@@ -28,6 +28,7 @@
 //   ht    [ht_cap]   u64          : (tag32 << 32) | (node index + 1), 0 = empty, linear probing
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace azg {
 
@@ -384,6 +385,10 @@ template <class G> struct SelSmem {
 // Warps per CTA of the one-warp-per-game kernels: 4, or 1 when the per-warp scratch is large (Abalone: 3402 actions).
 template <class G> __host__ __device__ constexpr int sel_warps() { return sizeof(WarpSmem<G>) * 4 <= 40 * 1024 ? 4 : 1; }
 // Warps per CTA of k_select (AZG_SELK_WARPS where the per-warp scratch allows it)
+// k_backup: games with a large action space (Abalone) keep the dense priors in global memory (nn_pi is consumed by this kernel only)
+// instead of a 41 KB per-warp staging buffer, so the kernel runs 4 warps per CTA at full occupancy for every game.
+template <class G> __host__ __device__ constexpr bool big_actions() { return sizeof(WarpSmem<G>) * 4 > 40 * 1024; }
+template <class G> __host__ __device__ constexpr int bak_warps() { return 4; }
 template <class G> __host__ __device__ constexpr int selk_warps() { return sizeof(SelSmem<G>) * AZG_SELK_WARPS <= 40 * 1024 ? AZG_SELK_WARPS : 1; }
 
 template <class G> __device__ __forceinline__ void warp_load_board(int8_t* sb, const int8_t* src, int lane) {
@@ -617,8 +622,8 @@ __device__ __forceinline__ void link_new_node(uint32_t* child, uint32_t ls, int 
 }
 
 // ============================================================ expand + backup =========================
-template <class G>
-__device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const int step, WarpSmem<G>* sm, const int w, const int lane) {
+template <class G, class SM>
+__device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const int step, SM* sm, const int w, const int lane) {
 #if AZG_SEL_PROF == 2
     const long long bp0 = clock64(); long long bp1 = 0, bp2 = 0;
 #endif
@@ -641,8 +646,9 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
     }
     float v[NP];
     if (kind == LEAF_EXPAND) {
-        float* pf = sm[w].f;
-        for (int a = lane; a < A; a += 32) pf[a] = d.nn_pi[(size_t)g * A + a];
+        float* pf; double* dscr;
+        if constexpr (big_actions<G>()) { pf = d.nn_pi + (size_t)g * A; dscr = d.noise_scr + (size_t)g * A; }
+        else { pf = sm[w].f; dscr = sm[w].d; for (int a = lane; a < A; a += 32) pf[a] = d.nn_pi[(size_t)g * A + a]; }
         uint32_t* m = sm[w].mask; int L = 0;
         for (int k = lane; k < MW; k += 32) { const uint32_t x = d.leaf_mask[(size_t)g * MW + k]; m[k] = x; L += __popc(x); }
         L = warp_sum_i32(L);
@@ -650,7 +656,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
         for (int p = 0; p < NP; p++) v[p] = d.nn_v[(size_t)g * NP + p];
         __syncwarp();
         const bool full = d.full ? d.full[g] != 0 : true;
-        if (depth == 0 && step == 0 && full && d.dirichlet_noise) root_noise<G>(d, g, pf, sm[w].d, m, lane);   // MCTS.py:147-149
+        if (depth == 0 && step == 0 && full && d.dirichlet_noise) root_noise<G>(d, g, pf, dscr, m, lane);   // MCTS.py:147-149
         const float s = warp_sum_avx2order(pf, A, lane);                                                    // normalise, MCTS.py:150
         const float inv = __fdiv_rn(1.0f, s);
         const int ni = d.n_nodes[g], eo = d.n_edges[g];
@@ -772,13 +778,14 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
 }
 
 template <class G>
-__global__ void __launch_bounds__(sel_warps<G>() * 32, 32 / sel_warps<G>()) k_backup(const __grid_constant__ Dev<G> d, int step) {
-    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+__global__ void __launch_bounds__(bak_warps<G>() * 32, 32 / bak_warps<G>()) k_backup(const __grid_constant__ Dev<G> d, int step) {
+    typedef typename std::conditional<big_actions<G>(), SelSmem<G>, WarpSmem<G>>::type SM;
+    __shared__ SM sm[bak_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;   // leaf list consumed by the net; reset for the next step
     WorkOrder<G> wo; wo.load(d, step, lane);
-    const int g = wo.game(d, blockIdx.x * sel_warps<G>() + w, step, lane);   // CTAs are dispatched in index order: deepest games first
-    if (g >= 0) backup_game<G>(d, g, step, sm, w, lane);
+    const int g = wo.game(d, blockIdx.x * bak_warps<G>() + w, step, lane);   // CTAs are dispatched in index order: deepest games first
+    if (g >= 0) backup_game<G, SM>(d, g, step, sm, w, lane);
 }
 
 // ============================================================ finish (getActionProb tail) ==============
