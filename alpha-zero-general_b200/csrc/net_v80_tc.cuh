@@ -86,7 +86,7 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
 
 namespace tc {
 using namespace umma;
-enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_PI3, B_V2, B_MM2, B_N };
+enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_PI3, B_PE0, B_PE1, B_PE2, B_PE3, B_V2, B_MM2, B_N };
 struct Phase {                            // per-thread parity of every barrier this thread waits on
     uint32_t bits = 0;
     __device__ __forceinline__ void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
@@ -168,7 +168,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         }
         cp(SV_BPI2, L.bpi2, 84); cp(SV_BPI4, L.bpi4, 84); cp(SV_BV2, L.bv2, 4); cp(SV_BV4, L.bv4, 4); cp(SV_V4, L.v4, 16);
     }
-    if (t == 0) { for (int i = 0; i < B_N; i++) mbar_init(&bars[i], 1); fence_barrier_init(); }
+    if (t == 0) { for (int i = 0; i < B_N; i++) mbar_init(&bars[i], (i >= B_PE0 && i <= B_PE3) ? 11u : 1u); fence_barrier_init(); }   // B_PE*: one arrival per policy-head warp
     if (warp == 0) tmem_alloc<512>(&tmem_s);
     for (int i = t; i < 65536 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);   // token columns 56..63 only ever meet zero weights (they hold stale finite data once X's planes have served as E stages)
     tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -463,6 +463,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     load(bars, B_PI0, WRING, P + L.pi2, TC_PIRING_SLOT);                  // policy weight ring: four slots (the last one runs over
                     load(bars, B_PI1, WRING + TC_PIRING_SLOT, P + L.pi2 + 56 * PIP, TC_PIRING_SLOT);          // into SQ, whose gates are consumed), three
                     load(bars, B_PI2, WRING + 2 * TC_PIRING_SLOT, P + L.pi2 + 112 * PIP, TC_PIRING_SLOT);     // loads in flight ahead of the math
+                    load(bars, B_PI3, WRING + 3 * TC_PIRING_SLOT, P + L.pi2 + 168 * PIP, TC_PIRING_SLOT);
                 } else {
                     load(bars, B_V2, WRING, P + L.v2, NV * 7 * 4 * 4);
                 }
@@ -502,23 +503,27 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 // ---------------- policy head linears on CUDA cores: Linear(392 -> 81) + ReLU, Linear(81 -> 81), masked softmax ----------------
                 const float* X0 = reinterpret_cast<const float*>(ESTG);
                 float* H1 = reinterpret_cast<float*>(ESTG + 28672); float* LG = H1 + PIP * TB;
+                // Weight ring (7 chunks of the 392 x 84 matrix, then the 81 x 84 one in two parts) through four slots, mbarrier-only: the 11
+                // computing warps wait for a slot to be full and arrive on its "empty" barrier when done; the last thread of the CTA (its
+                // warp has no policy work) refills a slot as soon as it is empty. No CTA-wide barrier per chunk.
                 int ent = 0;
-                auto acquire = [&]() -> const float* {           // next ring entry (7 x pi2 chunk, 2 x pi4 part); barrier = previous entry fully consumed
+                auto acquire = [&]() -> const float* {
                     const int s = ent & 3;
                     ph.wait(bars, B_PI0 + s);
-                    __syncthreads();
-                    if (t == 0 && ent + 3 < 9) {
-                        const int e = ent + 3, s2 = e & 3;
+                    ent++;
+                    return reinterpret_cast<const float*>(WRING + s * TC_PIRING_SLOT);
+                };
+                auto release = [&]() { __syncwarp(); if (lane == 0) mbar_arrive(&bars[B_PE0 + ((ent - 1) & 3)]); };
+                if (t == TC_THREADS - 1) {
+#pragma unroll 1
+                    for (int e = 4; e < 9; e++) {
+                        const int s2 = e & 3;
+                        ph.wait(bars, B_PE0 + s2);                 // the previous entry of this slot has been consumed by all 11 warps
                         const float* src = e < 7 ? P + L.pi2 + e * 56 * PIP : (e == 7 ? P + L.pi4 : P + L.pi4 + 41 * PIP);
                         const uint32_t bytes = e < 7 ? TC_PIRING_SLOT : (e == 7 ? 41 * PIP * 4 : 40 * PIP * 4);
                         load(bars, B_PI0 + s2, WRING + s2 * TC_PIRING_SLOT, src, bytes);
                     }
-                    ent++;
-#ifdef AZG_TC_POLICY_PROF
-                    TC_STAMP();
-#endif
-                    return reinterpret_cast<const float*>(WRING + s * TC_PIRING_SLOT);
-                };
+                }
                 // 352 tasks = 8 K-slices x 11 output octets x 4 leaf quads (register tile 8 x 4: 32 FMA per three 128-bit loads; the loads,
                 // not the FMAs, are the limit, so the work is spread over 11 warps). Slices s and s + 4 sit in lanes l and l ^ 16 of one warp
                 // and are summed by shuffle; the four remaining partial sums meet in PP and are added in a fixed order.
@@ -539,11 +544,12 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                         for (int j = 0; j < 4; j++) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
                 };
                 auto flush = [&]() {                              // lanes l and l ^ 16 hold the two K-slices of one task
+                    if (!live) return;                            // warp-uniform (352 = 11 warps)
 #pragma unroll
                     for (int i = 0; i < 8; i++)
 #pragma unroll
                         for (int j = 0; j < 4; j++) acc[i][j] += __shfl_xor_sync(FULL, acc[i][j], 16);
-                    if (live && half == 0) {
+                    if (half == 0) {
 #pragma unroll
                         for (int i = 0; i < 8; i++)
                             if (i < 4 || hi_ok) *reinterpret_cast<float4*>(PP + (part * PIP + 8 * o8 + i) * TB + 4 * lq) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -551,17 +557,15 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #pragma unroll
                     for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
                 };
-                for (int ch = 0; ch < NV / 8; ch++) {
+                for (int ch = 0; ch < NV / 8 && live; ch++) {
                     const float* W = acquire();
-                    if (live) {                                   // K-slice `slice` = token `slice` of this 8-token chunk: 7 rows
+                    {                                             // K-slice `slice` = token `slice` of this 8-token chunk: 7 rows
                         const float* xp = X0 + (8 * ch + slice) * LD + 4 * lq;
                         const float* wp = W + (slice * 7) * PIP + 8 * o8;
 #pragma unroll
                         for (int f = 0; f < 7; f++) fma_row(wp + f * PIP, *reinterpret_cast<const float4*>(xp + f * TB));
                     }
-#ifdef AZG_TC_POLICY_PROF
-                    TC_STAMP();
-#endif
+                    release();
                 }
                 flush();
                 __syncthreads();
@@ -570,14 +574,18 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #endif
                 for (int i = t; i < PIP * TB; i += TC_THREADS)
                     H1[i] = fmaxf(PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI2 + (i >> 4)], 0.f);
-                for (int ch = 0; ch < 2; ch++) {
-                    const float* W = acquire();                   // first barrier: H1 complete (and PP consumed)
-                    if (live) {
+                __syncthreads();                                  // H1 complete (and PP consumed)
+                for (int ch = 0; ch < 2 && live; ch++) {
+                    const float* W = acquire();
+                    {
                         const int k0 = max(11 * slice, 41 * ch), k1 = min(min(11 * slice + 11, 81), ch == 0 ? 41 : 81);
 #pragma unroll 2
                         for (int k = k0; k < k1; k++) fma_row(W + (k - 41 * ch) * PIP + 8 * o8, *reinterpret_cast<const float4*>(H1 + k * TB + 4 * lq));
                     }
+                    release();
                 }
+                if (t == TC_THREADS - 1) { ph.wait(bars, B_PE0); ph.wait(bars, B_PE1); ph.wait(bars, B_PE2); ph.wait(bars, B_PE3); }   // last entry of every slot consumed (keeps the parities in step)
+                __syncwarp();
                 flush();
                 __syncthreads();
 #ifdef AZG_TC_POLICY_PROF
