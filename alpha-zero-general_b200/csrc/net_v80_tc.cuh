@@ -519,6 +519,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     for (int e = 4; e < 9; e++) {
                         const int s2 = e & 3;
                         ph.wait(bars, B_PE0 + s2);                 // the previous entry of this slot has been consumed by all 11 warps
+                        fence_async_smem();                        // (acquire above) order those generic-proxy reads before the async-proxy refill
                         const float* src = e < 7 ? P + L.pi2 + e * 56 * PIP : (e == 7 ? P + L.pi4 : P + L.pi4 + 41 * PIP);
                         const uint32_t bytes = e < 7 ? TC_PIRING_SLOT : (e == 7 ? 41 * PIP * 4 : 40 * PIP * 4);
                         load(bars, B_PI0 + s2, WRING + s2 * TC_PIRING_SLOT, src, bytes);
