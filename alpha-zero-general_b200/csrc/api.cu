@@ -369,7 +369,7 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
     } else if (net->kind == AZG_NET_ABALONE_V21) {
         if constexpr (G::GAME_ID == AZG_GAME_ABALONE) {
             static bool attr_set21 = false;
-            constexpr size_t smem = v21_smem_bytes();
+            static const size_t smem = v21_smem_bytes();
             if (!attr_set21) { CK(cudaFuncSetAttribute(k_v21_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set21 = true; }
             k_v21_forward<<<(n_max + V21_TB - 1) / V21_TB, V21_THREADS, smem, st>>>(net->blob, net->L21, count_ptr, list, boards, bstride, masks, pi, v, n_max);
         } else return fail("AbaloneNNet V21 only evaluates Abalone boards");

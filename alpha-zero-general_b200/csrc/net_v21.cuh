@@ -7,16 +7,20 @@
 //   exp | value: 1x1 24->4 +BN+ReLU, flatten 324, cat Linear(6->16)+ReLU of the misc cells, Linear(340->64)+ReLU,
 //   Linear(64->2), tanh.   2.1 MFLOP per leaf, 35 862 parameters.
 //
-// One CTA (256 threads) evaluates 4 leaves; the three activation planes [24|48|48][4 x 81] stay in shared memory
-// (156 KB), the dense 3402-wide logits of the tile overwrite the two 48-channel planes once the trunk is done.
-// Lanes run over consecutive board positions, output-channel groups of 6 are warp-uniform (broadcast weight loads
-// from L1/L2; the whole net is 144 KB). BatchNorm folded on the host. fp32 on CUDA cores (parity bar 1e-5).
+// One CTA (512 threads) evaluates 4 leaves; the three activation planes [24|48|48][4 x 81] stay in shared memory
+// (156 KB) next to ALL convolution weights (53 KB, copied once per CTA; only the 340 x 64 value matrix stays in L1/L2); the
+// dense 3402-wide logits of the tile overwrite the two 48-channel planes once the trunk is done. The layers are
+// register-tiled so that shared-memory wavefronts, not FMAs, stop being the limit: a 1x1 task is one board position
+// in all four leaves x 4..14 output channels (lanes = consecutive positions, weights = warp-uniform 128-bit broadcasts),
+// a 3x3 task is one board row (9 outputs from 27 inputs held in registers, lane stride 9 words = conflict-free).
+// The summation order of every convolution output is the reference's (k ascending). BatchNorm folded on the host.
+// fp32 on CUDA cores (parity bar 1e-5).
 #pragma once
 #include "common.cuh"
 
 namespace azg {
 
-constexpr int V21_THREADS = 1024;         // 32 warps per (single-CTA) SM: the layers are latency-bound weight broadcasts, more warps hide it
+constexpr int V21_THREADS = 512;          // one CTA per SM, up to 128 registers per thread for the register tiles
 constexpr int V21_TB = 4;
 constexpr int V21_N = V21_TB * 81;        // positions per tile
 constexpr int V21_A = 3402, V21_MW = 107;
@@ -61,32 +65,49 @@ inline void v21_prepare(const float* src, const V21Layout& L, float* dst) {
     { const float *W = take(2 * 64), *b = take(2); for (int o = 0; o < 2; o++) { dst[L.f2b + o] = b[o]; for (int k = 0; k < 64; k++) dst[L.f2 + o * 64 + k] = W[o * 64 + k]; } }
 }
 
-// out[o][n] = act(bias[o] + sum_k W[k][o] * in[k][n]) (+ out[o][n] if RES); tasks = (group of 6 outputs) x (position n).
-template <int CIN, int COUT, int ACT, bool RES>
-__device__ __forceinline__ void conv1x1(const float* __restrict__ W, const float* __restrict__ bias, const float* in, float* out) {
-    static_assert(COUT % 6 == 0, "output channels in groups of 6");
-    for (int t = threadIdx.x; t < (COUT / 6) * V21_N; t += V21_THREADS) {
-        const int og = t / V21_N, n = t - og * V21_N, o0 = 6 * og;
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
+// out[o][l][pos] = act(bias[o] + sum_k W[k][o] * in[k][l][pos]) (+ out if RES); task = (group of OG outputs) x (position, all 4 leaves)
+template <int CIN, int COUT, int OG, int ACT, bool RES>
+__device__ __forceinline__ void conv1x1(const float* W, const float* bias, const float* in, float* out) {
+    static_assert(COUT % OG == 0 && OG % 4 == 0 && COUT % 4 == 0, "128-bit weight broadcasts");
+    constexpr int N = V21_N, TASKS = (COUT / OG) * 81;
+    for (int t = threadIdx.x; t < TASKS; t += V21_THREADS) {
+        const int og = t / 81, pos = t - og * 81, o0 = OG * og;
+        float acc[OG][4];
+#pragma unroll
+        for (int j = 0; j < OG; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        const float* xin = in + pos; const float* wk = W + o0;
+#pragma unroll 4
         for (int k = 0; k < CIN; k++) {
-            const float x = in[k * V21_N + n];
-            const float2 w0 = __ldg(reinterpret_cast<const float2*>(W + k * COUT + o0)), w1 = __ldg(reinterpret_cast<const float2*>(W + k * COUT + o0 + 2)),
-                         w2 = __ldg(reinterpret_cast<const float2*>(W + k * COUT + o0 + 4));
-            acc[0] = fmaf(w0.x, x, acc[0]); acc[1] = fmaf(w0.y, x, acc[1]); acc[2] = fmaf(w1.x, x, acc[2]);
-            acc[3] = fmaf(w1.y, x, acc[3]); acc[4] = fmaf(w2.x, x, acc[4]); acc[5] = fmaf(w2.y, x, acc[5]);
+            const float x[4] = {xin[k * N], xin[k * N + 81], xin[k * N + 162], xin[k * N + 243]};
+            float w[OG];
+#pragma unroll
+            for (int j4 = 0; j4 < OG / 4; j4++) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wk + k * COUT + 4 * j4);
+                w[4 * j4] = w4.x; w[4 * j4 + 1] = w4.y; w[4 * j4 + 2] = w4.z; w[4 * j4 + 3] = w4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < OG; j++)
+#pragma unroll
+                for (int l = 0; l < 4; l++) acc[j][l] = fmaf(w[j], x[l], acc[j][l]);
         }
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
-            float v = acc[j] + __ldg(bias + o0 + j);
-            if (ACT) v = fmaxf(v, 0.f);
-            if (RES) v += out[(o0 + j) * V21_N + n];
-            out[(o0 + j) * V21_N + n] = v;
+        for (int j = 0; j < OG; j++) {
+            const float b = bias[o0 + j];
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                float v = acc[j][l] + b;
+                if (ACT) v = fmaxf(v, 0.f);
+                float* o = out + (o0 + j) * N + l * 81 + pos;
+                if (RES) v += *o;
+                *o = v;
+            }
         }
     }
 }
 
-constexpr size_t v21_smem_bytes() { return sizeof(float) * (size_t)(120 * V21_N + V21_TB * (340 + 64 + 8)); }
+// WS mirrors the parameter blob up to (not including) the value matrix f1.
+constexpr size_t v21_smem_bytes(int ws_floats) { return sizeof(float) * (size_t)(120 * V21_N + V21_TB * (340 + 64) + 8 * V21_TB * 64 + ws_floats); }
+inline size_t v21_smem_bytes() { return v21_smem_bytes(v21_layout().f1); }
 
 // boards: int8[.][324] HWC with `bstride` bytes between boards; masks: 107 words per slot; list/count as in k_v80_forward.
 __global__ void __launch_bounds__(V21_THREADS, 1)
@@ -94,14 +115,18 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
               const int8_t* boards, int bstride, const uint32_t* masks, float* pi_out, float* v_out, int n_max) {
     extern __shared__ __align__(16) float smem[];
     constexpr int TB = V21_TB, N = V21_N, A = V21_A, MW = V21_MW;
+    static_assert(TB == 4, "tasks span the four leaves of a tile");
     float* X = smem; float* E = X + 24 * N; float* D = E + 48 * N; float* VC = D + 48 * N;     // VC [TB][340]: value features + meta
-    float* VH = VC + TB * 340; float* LG = E;                                                  // LG [TB][3402] over E and D
+    float* VH = VC + TB * 340; float* VP = VH + TB * 64; float* WS = VP + 8 * TB * 64;         // VP [8][TB][64]: K-slice partials of the value Linear
+    float* LG = E;                                                                             // LG [TB][3402] over E and D
     __shared__ int slot_of[TB];
+    __shared__ float red[2][TB][4];
     const int count = count_ptr ? min(*count_ptr, n_max) : n_max;
     const int tile0 = blockIdx.x * TB;
     if (tile0 >= count) return;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (t < TB) { const int j = tile0 + t; slot_of[t] = j < count ? (list ? list[j] : j) : -1; }
+    for (int i = t; i < L.f1 / 4; i += V21_THREADS) reinterpret_cast<float4*>(WS)[i] = __ldg(reinterpret_cast<const float4*>(P) + i);
     __syncthreads();
     // input planes (channels 0..2) into D, misc cells -> meta embedding Linear(6->16)+ReLU into VC[.][324..339]
     for (int k = t; k < 3 * N; k += V21_THREADS) {
@@ -110,96 +135,176 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
     }
     if (t < TB * 16) {
         const int l = t >> 4, o = t & 15, slot = slot_of[l];
-        float a = __ldg(P + L.bm + o);
-        if (slot >= 0) for (int j = 0; j < 6; j++) a = fmaf(__ldg(P + L.wm + j * 16 + o), (float)boards[(size_t)slot * bstride + j * 4 + 3], a);
+        float a = WS[L.bm + o];
+        if (slot >= 0) for (int j = 0; j < 6; j++) a = fmaf(WS[L.wm + j * 16 + o], (float)boards[(size_t)slot * bstride + j * 4 + 3], a);
         VC[l * 340 + 324 + o] = fmaxf(a, 0.f);
     }
     __syncthreads();
-    // first_layer: Conv3x3(3->24) + BN + ReLU; tasks = (group of 6 outputs) x position
-    for (int k = t; k < 4 * N; k += V21_THREADS) {
-        const int og = k / N, n = k - og * N, l = n / 81, pos = n - l * 81, r = pos / 9, q = pos - 9 * r, o0 = 6 * og;
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < 3; c++)
+    // first_layer: Conv3x3(3->24) + BN + ReLU; task = (group of 4 outputs) x (leaf, board row): 9 x 4 outputs from 3 x 27 inputs
+    for (int k = t; k < 6 * 36; k += V21_THREADS) {
+        const int og = k / 36, m = k - 36 * og, r = m % 9, o0 = 4 * og;
+        float acc[9][4];
 #pragma unroll
-            for (int tp = 0; tp < 9; tp++) {
-                const int rr = r + tp / 3 - 1, qq = q + tp % 3 - 1;
-                if (rr < 0 || rr >= 9 || qq < 0 || qq >= 9) continue;
-                const float x = D[c * N + l * 81 + rr * 9 + qq];
-                const float* w = P + L.wf + (c * 9 + tp) * 24 + o0;
+        for (int q = 0; q < 9; q++) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 3; c++) {
 #pragma unroll
-                for (int j = 0; j < 6; j++) acc[j] = fmaf(__ldg(w + j), x, acc[j]);
+            for (int dr = 0; dr < 3; dr++) {
+                const int rr = r + dr - 1; const bool ok = rr >= 0 && rr < 9;
+                float row[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) row[q] = ok ? D[c * N + 9 * m + (dr - 1) * 9 + q] : 0.f;
+#pragma unroll
+                for (int dq = 0; dq < 3; dq++) {
+                    const float4 w = *reinterpret_cast<const float4*>(WS + L.wf + (c * 9 + dr * 3 + dq) * 24 + o0);
+#pragma unroll
+                    for (int q = 0; q < 9; q++) {
+                        const int qq = q + dq - 1;
+                        if (qq < 0 || qq >= 9) continue;
+                        acc[q][0] = fmaf(w.x, row[qq], acc[q][0]); acc[q][1] = fmaf(w.y, row[qq], acc[q][1]);
+                        acc[q][2] = fmaf(w.z, row[qq], acc[q][2]); acc[q][3] = fmaf(w.w, row[qq], acc[q][3]);
+                    }
+                }
             }
+        }
 #pragma unroll
-        for (int j = 0; j < 6; j++) X[(o0 + j) * N + n] = fmaxf(acc[j] + __ldg(P + L.bf + o0 + j), 0.f);
+        for (int j = 0; j < 4; j++) {
+            const float b = WS[L.bf + o0 + j];
+#pragma unroll
+            for (int q = 0; q < 9; q++) X[(o0 + j) * N + 9 * m + q] = fmaxf(acc[q][j] + b, 0.f);
+        }
     }
     __syncthreads();
     for (int b = 0; b < 4; b++) {                                                    // trunk: InvertedResidual x 4
         const V21Layout::Blk B = L.blk[b];
-        conv1x1<24, 48, 1, false>(P + B.we, P + B.be, X, E);
+        conv1x1<24, 48, 8, 1, false>(WS + B.we, WS + B.be, X, E);
         __syncthreads();
-        for (int k = t; k < 48 * N; k += V21_THREADS) {                               // depthwise 3x3 + BN + ReLU
-            const int c = k / N, n = k - c * N, l = n / 81, pos = n - l * 81, r = pos / 9, q = pos - 9 * r;
-            float a = __ldg(P + B.bd + c);
+        for (int k = t; k < 48 * 36; k += V21_THREADS) {                              // depthwise 3x3 + BN + ReLU; task = (channel, leaf, board row)
+            const int c = k / 36, r = (k - 36 * c) % 9;
+            const float* e = E + 9 * k;                                               // = E + c*N + leaf*81 + r*9
+            float w[9], a[9];
 #pragma unroll
-            for (int tp = 0; tp < 9; tp++) {
-                const int rr = r + tp / 3 - 1, qq = q + tp % 3 - 1;
-                if (rr < 0 || rr >= 9 || qq < 0 || qq >= 9) continue;
-                a = fmaf(__ldg(P + B.wd + tp * 48 + c), E[c * N + l * 81 + rr * 9 + qq], a);
+            for (int tp = 0; tp < 9; tp++) w[tp] = WS[B.wd + tp * 48 + c];
+            const float bd = WS[B.bd + c];
+#pragma unroll
+            for (int q = 0; q < 9; q++) a[q] = bd;
+#pragma unroll
+            for (int dr = 0; dr < 3; dr++) {
+                const int rr = r + dr - 1; const bool ok = rr >= 0 && rr < 9;
+                float row[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) row[q] = ok ? e[(dr - 1) * 9 + q] : 0.f;
+#pragma unroll
+                for (int dq = 0; dq < 3; dq++)
+#pragma unroll
+                    for (int q = 0; q < 9; q++) {
+                        const int qq = q + dq - 1;
+                        if (qq < 0 || qq >= 9) continue;
+                        a[q] = fmaf(w[dr * 3 + dq], row[qq], a[q]);
+                    }
             }
-            D[k] = fmaxf(a, 0.f);
+#pragma unroll
+            for (int q = 0; q < 9; q++) D[9 * k + q] = fmaxf(a[q], 0.f);
         }
         __syncthreads();
-        conv1x1<48, 24, 0, true>(P + B.wp, P + B.bp, D, X);                           // project + residual (X holds the block input)
+        conv1x1<48, 24, 4, 0, true>(WS + B.wp, WS + B.bp, D, X);                      // project + residual (X holds the block input)
         __syncthreads();
     }
-    // value features first (they read X only; E and D are free), then the policy logits overwrite E/D
-    for (int k = t; k < 4 * N; k += V21_THREADS) {                                    // 1x1 24->4 + BN + ReLU, flattened channel-major
-        const int c = k / N, n = k - c * N, l = n / 81, pos = n - l * 81;
-        float a = __ldg(P + L.bvc + c);
-#pragma unroll 8
-        for (int i = 0; i < 24; i++) a = fmaf(__ldg(P + L.wvc + i * 4 + c), X[i * N + n], a);
-        VC[l * 340 + c * 81 + pos] = fmaxf(a, 0.f);
-    }
-    for (int k = t; k < 7 * N; k += V21_THREADS) {                                    // 1x1 24->42 + BN -> logits[r][q][plane]
-        const int og = k / N, n = k - og * N, l = n / 81, pos = n - l * 81, o0 = 6 * og;
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
+    // heads (both read X only; E and D are free): policy logits on warps 0..7 overwrite E/D, value features on warps 8..10
+    if (t < 3 * 81) {                                                                 // 1x1 24->42 + BN -> logits[r][q][plane]; task = 14 planes x position
+        const int og = t / 81, pos = t - og * 81, o0 = 14 * og;
+        float acc[14][4];
+#pragma unroll
+        for (int j = 0; j < 14; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 2
         for (int i = 0; i < 24; i++) {
-            const float x = X[i * N + n]; const float* w = P + L.wpi + i * 42 + o0;
+            const float x[4] = {X[i * N + pos], X[i * N + 81 + pos], X[i * N + 162 + pos], X[i * N + 243 + pos]};
+            const float2* w2 = reinterpret_cast<const float2*>(WS + L.wpi + i * 42 + o0);
 #pragma unroll
-            for (int j = 0; j < 6; j++) acc[j] = fmaf(__ldg(w + j), x, acc[j]);
+            for (int j2 = 0; j2 < 7; j2++) {
+                const float2 w = w2[j2];
+#pragma unroll
+                for (int l = 0; l < 4; l++) { acc[2 * j2][l] = fmaf(w.x, x[l], acc[2 * j2][l]); acc[2 * j2 + 1][l] = fmaf(w.y, x[l], acc[2 * j2 + 1][l]); }
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 6; j++) LG[l * A + pos * 42 + o0 + j] = acc[j] + __ldg(P + L.bpi + o0 + j);
+        for (int j2 = 0; j2 < 7; j2++) {
+            const float b0 = WS[L.bpi + o0 + 2 * j2], b1 = WS[L.bpi + o0 + 2 * j2 + 1];
+#pragma unroll
+            for (int l = 0; l < 4; l++) *reinterpret_cast<float2*>(LG + l * A + pos * 42 + o0 + 2 * j2) = make_float2(acc[2 * j2][l] + b0, acc[2 * j2 + 1][l] + b1);
+        }
+    } else if (t >= 256 && t < 256 + 81) {                                            // 1x1 24->4 + BN + ReLU, flattened channel-major
+        const int pos = t - 256;
+        float acc[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = WS[L.bvc + c];
+#pragma unroll 4
+        for (int i = 0; i < 24; i++) {
+            const float x[4] = {X[i * N + pos], X[i * N + 81 + pos], X[i * N + 162 + pos], X[i * N + 243 + pos]};
+            const float4 w = *reinterpret_cast<const float4*>(WS + L.wvc + i * 4);
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                acc[0][l] = fmaf(w.x, x[l], acc[0][l]); acc[1][l] = fmaf(w.y, x[l], acc[1][l]);
+                acc[2][l] = fmaf(w.z, x[l], acc[2][l]); acc[3][l] = fmaf(w.w, x[l], acc[3][l]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int l = 0; l < 4; l++) VC[l * 340 + c * 81 + pos] = fmaxf(acc[c][l], 0.f);
     }
     __syncthreads();
-    if (t < TB * 64) {   // value Linear(340 -> 64) + ReLU: one thread per (leaf, output)
+    {   // value Linear(340 -> 64): K split in 8 slices of 43, one thread per (slice, output), all four leaves
+        const int ks = t >> 6, j = t & 63, i0 = 43 * ks, i1 = min(i0 + 43, 340);
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int i = i0; i < i1; i++) {
+            const float w = __ldg(P + L.f1 + i * 64 + j);
+#pragma unroll
+            for (int l = 0; l < 4; l++) a[l] = fmaf(w, VC[l * 340 + i], a[l]);
+        }
+#pragma unroll
+        for (int l = 0; l < 4; l++) VP[(ks * TB + l) * 64 + j] = a[l];
+    }
+    // masked softmax over 3402 actions: where(valid, logits, -1e8) -> log_softmax -> exp; four warps per leaf, mask words interleaved
+    const int sl = warp >> 2, wv = warp & 3, slot = slot_of[sl];
+    const uint32_t* mk = masks + (size_t)max(slot, 0) * MW; const float* lg = LG + sl * A;
+    auto logit = [&](int k) -> float {                                                // action lane + 32k of leaf sl (-inf past the end)
+        const int a = lane + 32 * k;
+        if (a >= A) return -INFINITY;
+        return (slot >= 0 && (__ldg(mk + k) >> lane & 1)) ? lg[a] : -1e8f;
+    };
+    {
+        float mx = -INFINITY;
+        for (int k = wv; k < MW; k += 4) mx = fmaxf(mx, logit(k));
+        mx = warp_max_f32(mx);
+        if (lane == 0) red[0][sl][wv] = mx;
+    }
+    __syncthreads();
+    if (t < TB * 64) {                                                                // value Linear: bias + the 8 partials in a fixed order, ReLU
         const int l = t >> 6, j = t & 63;
         float a = __ldg(P + L.f1b + j);
-        for (int i = 0; i < 340; i++) a = fmaf(__ldg(P + L.f1 + i * 64 + j), VC[l * 340 + i], a);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) a += VP[(ks * TB + l) * 64 + j];
         VH[l * 64 + j] = fmaxf(a, 0.f);
     }
-    // masked softmax over 3402 actions: where(valid, logits, -1e8) -> log_softmax -> exp; one warp per leaf
-    if (warp < TB) {
-        const int l = warp, slot = slot_of[l];
-        if (slot >= 0) {
-            const uint32_t* mk = masks + (size_t)slot * MW; const float* lg = LG + l * A;
-            float mx = -INFINITY;
-            for (int k = 0; k < MW; k++) { const int a = lane + 32 * k; if (a < A) mx = fmaxf(mx, (mk[k] >> lane & 1) ? lg[a] : -1e8f); }
-            mx = warp_max_f32(mx);
-            float sum = 0.f;
-            for (int k = 0; k < MW; k++) { const int a = lane + 32 * k; if (a < A) sum += expf(((mk[k] >> lane & 1) ? lg[a] : -1e8f) - mx); }
-            sum = warp_sum_f32(sum);
-            const float lse = logf(sum);
-            for (int k = 0; k < MW; k++) { const int a = lane + 32 * k; if (a < A) pi_out[(size_t)slot * A + a] = expf(((mk[k] >> lane & 1) ? lg[a] : -1e8f) - mx - lse); }
-        }
+    const float mx = fmaxf(fmaxf(red[0][sl][0], red[0][sl][1]), fmaxf(red[0][sl][2], red[0][sl][3]));
+    {
+        float sum = 0.f;
+        for (int k = wv; k < MW; k += 4) sum += expf(logit(k) - mx);
+        sum = warp_sum_f32(sum);
+        if (lane == 0) red[1][sl][wv] = sum;
     }
     __syncthreads();
-    if (t < TB * 2) {                                                                 // value Linear(64 -> 2), tanh
-        const int l = t >> 1, o = t & 1, slot = slot_of[l];
-        float a = __ldg(P + L.f2b + o);
-        for (int j = 0; j < 64; j++) a = fmaf(__ldg(P + L.f2 + o * 64 + j), VH[l * 64 + j], a);
-        if (slot >= 0) v_out[(size_t)slot * 2 + o] = tanhf(a);
+    if (slot >= 0) {
+        const float lse = logf((red[1][sl][0] + red[1][sl][1]) + (red[1][sl][2] + red[1][sl][3]));
+        for (int k = wv; k < MW; k += 4) { const int a = lane + 32 * k; if (a < A) pi_out[(size_t)slot * A + a] = expf(logit(k) - mx - lse); }
+    }
+    if (warp < TB * 2) {                                                              // value Linear(64 -> 2), tanh: one warp per (leaf, output)
+        const int l = warp >> 1, o = warp & 1, vslot = slot_of[l];
+        float a = fmaf(__ldg(P + L.f2 + o * 64 + lane), VH[l * 64 + lane], __ldg(P + L.f2 + o * 64 + 32 + lane) * VH[l * 64 + 32 + lane]);
+        a = warp_sum_f32(a);
+        if (lane == 0 && vslot >= 0) v_out[(size_t)vslot * 2 + o] = tanhf(a + __ldg(P + L.f2b + o));
     }
 }
 
