@@ -254,12 +254,14 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
             for (int l = 0; l < 4; l++) VC[l * 340 + c * 81 + pos] = fmaxf(acc[c][l], 0.f);
     }
     __syncthreads();
-    {   // value Linear(340 -> 64): K split in 8 slices of 43, one thread per (slice, output), all four leaves
-        const int ks = t >> 6, j = t & 63, i0 = 43 * ks, i1 = min(i0 + 43, 340);
+    {   // value Linear(340 -> 64): K split in 8 slices of 43 (the last one padded with zero weights), one thread per (slice, output), all
+        // four leaves; fully unrolled so the 43 weight loads (L2: the 87 KB matrix does not fit the 28 KB left to L1) are in flight together
+        const int ks = t >> 6, j = t & 63, i0 = 43 * ks;
         float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int i = i0; i < i1; i++) {
-            const float w = __ldg(P + L.f1 + i * 64 + j);
+#pragma unroll
+        for (int ii = 0; ii < 43; ii++) {
+            const int i = min(i0 + ii, 339);
+            const float w = i0 + ii < 340 ? __ldg(P + L.f1 + i * 64 + j) : 0.f;
 #pragma unroll
             for (int l = 0; l < 4; l++) a[l] = fmaf(w, VC[l * 340 + i], a[l]);
         }
@@ -267,16 +269,21 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
         for (int l = 0; l < 4; l++) VP[(ks * TB + l) * 64 + j] = a[l];
     }
     // masked softmax over 3402 actions: where(valid, logits, -1e8) -> log_softmax -> exp; four warps per leaf, mask words interleaved
+    // (warp wv owns words wv, wv+4, ...: 27 at most). Mask words are loaded once (lane i holds word wv+4i) and the masked logits stay in registers.
     const int sl = warp >> 2, wv = warp & 3, slot = slot_of[sl];
-    const uint32_t* mk = masks + (size_t)max(slot, 0) * MW; const float* lg = LG + sl * A;
-    auto logit = [&](int k) -> float {                                                // action lane + 32k of leaf sl (-inf past the end)
-        const int a = lane + 32 * k;
-        if (a >= A) return -INFINITY;
-        return (slot >= 0 && (__ldg(mk + k) >> lane & 1)) ? lg[a] : -1e8f;
-    };
+    constexpr int SW = (MW + 3) / 4;                                                  // 27 words per warp
+    float val[SW];
     {
+        const uint32_t mword = (slot >= 0 && wv + 4 * lane < MW) ? __ldg(masks + (size_t)slot * MW + wv + 4 * lane) : 0u;
+        const float* lg = LG + sl * A;
         float mx = -INFINITY;
-        for (int k = wv; k < MW; k += 4) mx = fmaxf(mx, logit(k));
+#pragma unroll
+        for (int i = 0; i < SW; i++) {
+            const int k = wv + 4 * i, a = lane + 32 * k;
+            const uint32_t m = __shfl_sync(FULL, mword, i);
+            val[i] = (k < MW && a < A) ? ((m >> lane & 1) ? lg[a] : -1e8f) : -INFINITY;   // -inf past the end of the action space
+            mx = fmaxf(mx, val[i]);
+        }
         mx = warp_max_f32(mx);
         if (lane == 0) red[0][sl][wv] = mx;
     }
@@ -291,14 +298,17 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
     const float mx = fmaxf(fmaxf(red[0][sl][0], red[0][sl][1]), fmaxf(red[0][sl][2], red[0][sl][3]));
     {
         float sum = 0.f;
-        for (int k = wv; k < MW; k += 4) sum += expf(logit(k) - mx);
+#pragma unroll
+        for (int i = 0; i < SW; i++) sum += expf(val[i] - mx);
         sum = warp_sum_f32(sum);
         if (lane == 0) red[1][sl][wv] = sum;
     }
     __syncthreads();
     if (slot >= 0) {
         const float lse = logf((red[1][sl][0] + red[1][sl][1]) + (red[1][sl][2] + red[1][sl][3]));
-        for (int k = wv; k < MW; k += 4) { const int a = lane + 32 * k; if (a < A) pi_out[(size_t)slot * A + a] = expf(logit(k) - mx - lse); }
+        float* po = pi_out + (size_t)slot * A + lane;
+#pragma unroll
+        for (int i = 0; i < SW; i++) { const int k = wv + 4 * i; if (k < MW && lane + 32 * k < A) po[32 * k] = expf(val[i] - mx - lse); }
     }
     if (warp < TB * 2) {                                                              // value Linear(64 -> 2), tanh: one warp per (leaf, output)
         const int l = warp >> 1, o = warp & 1, vslot = slot_of[l];
