@@ -368,10 +368,15 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
         } else return fail("SantoriniNNet V89 only evaluates Santorini boards");
     } else if (net->kind == AZG_NET_ABALONE_V21) {
         if constexpr (G::GAME_ID == AZG_GAME_ABALONE) {
-            static bool attr_set21 = false;
+            static bool attr_set21 = false; static int n_sm21 = 0;
             static const size_t smem = v21_smem_bytes();
-            if (!attr_set21) { CK(cudaFuncSetAttribute(k_v21_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set21 = true; }
-            k_v21_forward<<<(n_max + V21_TB - 1) / V21_TB, V21_THREADS, smem, st>>>(net->blob, net->L21, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+            if (!attr_set21) {
+                CK(cudaFuncSetAttribute(k_v21_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&n_sm21, cudaDevAttrMultiProcessorCount, dev));
+                attr_set21 = true;
+            }
+            const V21Plan plan = v21_plan(n_max, n_sm21);
+            k_v21_forward<<<plan.n_big + plan.n_small, V21_THREADS, smem, st>>>(net->blob, net->L21, count_ptr, list, boards, bstride, masks, pi, v, n_max, plan.n_big);
         } else return fail("AbaloneNNet V21 only evaluates Abalone boards");
     } else return fail("net kind not built");
     net->launches++;

@@ -7,7 +7,8 @@
 //   exp | value: 1x1 24->4 +BN+ReLU, flatten 324, cat Linear(6->16)+ReLU of the misc cells, Linear(340->64)+ReLU,
 //   Linear(64->2), tanh.   2.1 MFLOP per leaf, 35 862 parameters.
 //
-// One CTA (512 threads) evaluates 4 leaves; the three activation planes [24|48|48][4 x 81] stay in shared memory
+// One CTA (512 threads) evaluates 4 leaves (or 2: the tail of a batch is cut into half-size tiles when that fills the last wave of
+// CTAs better, see v21_plan); the three activation planes [24|48|48][4 x 81] stay in shared memory
 // (156 KB) next to ALL convolution weights (53 KB, copied once per CTA; only the 340 x 64 value matrix stays in L1/L2); the
 // dense 3402-wide logits of the tile overwrite the two 48-channel planes once the trunk is done. The layers are
 // register-tiled so that shared-memory wavefronts, not FMAs, stop being the limit: a 1x1 task is one board position
@@ -65,20 +66,24 @@ inline void v21_prepare(const float* src, const V21Layout& L, float* dst) {
     { const float *W = take(2 * 64), *b = take(2); for (int o = 0; o < 2; o++) { dst[L.f2b + o] = b[o]; for (int k = 0; k < 64; k++) dst[L.f2 + o * 64 + k] = W[o * 64 + k]; } }
 }
 
-// out[o][l][pos] = act(bias[o] + sum_k W[k][o] * in[k][l][pos]) (+ out if RES); task = (group of OG outputs) x (position, all 4 leaves)
-template <int CIN, int COUT, int OG, int ACT, bool RES>
+// out[o][l][pos] = act(bias[o] + sum_k W[k][o] * in[k][l][pos]) (+ out if RES); task = (group of OG outputs) x (position, all TB leaves)
+template <int TB, int CIN, int COUT, int OG, int ACT, bool RES>
 __device__ __forceinline__ void conv1x1(const float* W, const float* bias, const float* in, float* out) {
     static_assert(COUT % OG == 0 && OG % 4 == 0 && COUT % 4 == 0, "128-bit weight broadcasts");
-    constexpr int N = V21_N, TASKS = (COUT / OG) * 81;
+    constexpr int N = TB * 81, TASKS = (COUT / OG) * 81;
     for (int t = threadIdx.x; t < TASKS; t += V21_THREADS) {
         const int og = t / 81, pos = t - og * 81, o0 = OG * og;
-        float acc[OG][4];
+        float acc[OG][TB];
 #pragma unroll
-        for (int j = 0; j < OG; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int j = 0; j < OG; j++)
+#pragma unroll
+            for (int l = 0; l < TB; l++) acc[j][l] = 0.f;
         const float* xin = in + pos; const float* wk = W + o0;
 #pragma unroll 4
         for (int k = 0; k < CIN; k++) {
-            const float x[4] = {xin[k * N], xin[k * N + 81], xin[k * N + 162], xin[k * N + 243]};
+            float x[TB];
+#pragma unroll
+            for (int l = 0; l < TB; l++) x[l] = xin[k * N + l * 81];
             float w[OG];
 #pragma unroll
             for (int j4 = 0; j4 < OG / 4; j4++) {
@@ -88,13 +93,13 @@ __device__ __forceinline__ void conv1x1(const float* W, const float* bias, const
 #pragma unroll
             for (int j = 0; j < OG; j++)
 #pragma unroll
-                for (int l = 0; l < 4; l++) acc[j][l] = fmaf(w[j], x[l], acc[j][l]);
+                for (int l = 0; l < TB; l++) acc[j][l] = fmaf(w[j], x[l], acc[j][l]);
         }
 #pragma unroll
         for (int j = 0; j < OG; j++) {
             const float b = bias[o0 + j];
 #pragma unroll
-            for (int l = 0; l < 4; l++) {
+            for (int l = 0; l < TB; l++) {
                 float v = acc[j][l] + b;
                 if (ACT) v = fmaxf(v, 0.f);
                 float* o = out + (o0 + j) * N + l * 81 + pos;
@@ -105,29 +110,32 @@ __device__ __forceinline__ void conv1x1(const float* W, const float* bias, const
     }
 }
 
-// WS mirrors the parameter blob up to (not including) the value matrix f1.
-constexpr size_t v21_smem_bytes(int ws_floats) { return sizeof(float) * (size_t)(120 * V21_N + V21_TB * (340 + 64) + 8 * V21_TB * 64 + ws_floats); }
-inline size_t v21_smem_bytes() { return v21_smem_bytes(v21_layout().f1); }
+// Shared memory of a CTA (sized for the 4-leaf tile): activations | VC | VH | VP | WS. WS mirrors the parameter blob up to (not including) f1.
+constexpr int V21_WS_OFF = 120 * V21_N + V21_TB * (340 + 64) + 8 * V21_TB * 64;       // floats
+inline size_t v21_smem_bytes() { return sizeof(float) * (size_t)(V21_WS_OFF + v21_layout().f1); }
 
-// boards: int8[.][324] HWC with `bstride` bytes between boards; masks: 107 words per slot; list/count as in k_v80_forward.
-__global__ void __launch_bounds__(V21_THREADS, 1)
-k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, const int* count_ptr, const int* list,
-              const int8_t* boards, int bstride, const uint32_t* masks, float* pi_out, float* v_out, int n_max) {
-    extern __shared__ __align__(16) float smem[];
-    constexpr int TB = V21_TB, N = V21_N, A = V21_A, MW = V21_MW;
-    static_assert(TB == 4, "tasks span the four leaves of a tile");
+// Tiling of a batch of n leaves on n_sm SMs (one CTA per SM at a time, dispatched in blockIdx order): 4-leaf tiles, except that the
+// leaves left over after the last full round of 4-leaf tiles go into 2-leaf tiles when those fit in ONE round (a 2-leaf tile takes
+// ~0.6 of a 4-leaf one: 2048 leaves on 148 SMs = 3 rounds + 0.6 instead of 4 rounds).
+struct V21Plan { int n_big, n_small; };
+inline V21Plan v21_plan(int n, int n_sm) {
+    V21Plan p; const int full = n / (4 * n_sm) * n_sm, rest = n - 4 * full;
+    if ((rest + 1) / 2 <= n_sm) { p.n_big = full; p.n_small = (rest + 1) / 2; }
+    else { p.n_big = full + (rest + 3) / 4; p.n_small = 0; }
+    return p;
+}
+
+// One tile of TB leaves (TB = 4 or 2). slot_of[TB], red[32] in static shared memory; WS already holds the weights.
+template <int TB>
+__device__ __forceinline__ void v21_tile(const float* __restrict__ P, const V21Layout& L, float* smem, const int* slot_of, float* red,
+                                         const int8_t* boards, int bstride, const uint32_t* masks, float* pi_out, float* v_out) {
+    constexpr int N = TB * 81, A = V21_A, MW = V21_MW, ROWS = TB * 9;
+    constexpr int WPL = (V21_THREADS / 32) / TB, SW = (MW + WPL - 1) / WPL;           // softmax: warps per leaf, mask words per warp
+    static_assert(SW <= 32 && TB * 64 <= V21_THREADS && 3 * 81 <= 256, "task maps");
     float* X = smem; float* E = X + 24 * N; float* D = E + 48 * N; float* VC = D + 48 * N;     // VC [TB][340]: value features + meta
-    float* VH = VC + TB * 340; float* VP = VH + TB * 64; float* WS = VP + 8 * TB * 64;         // VP [8][TB][64]: K-slice partials of the value Linear
+    float* VH = VC + TB * 340; float* VP = VH + TB * 64; const float* WS = smem + V21_WS_OFF;  // VP [8][TB][64]: K-slice partials of the value Linear
     float* LG = E;                                                                             // LG [TB][3402] over E and D
-    __shared__ int slot_of[TB];
-    __shared__ float red[2][TB][4];
-    const int count = count_ptr ? min(*count_ptr, n_max) : n_max;
-    const int tile0 = blockIdx.x * TB;
-    if (tile0 >= count) return;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    if (t < TB) { const int j = tile0 + t; slot_of[t] = j < count ? (list ? list[j] : j) : -1; }
-    for (int i = t; i < L.f1 / 4; i += V21_THREADS) reinterpret_cast<float4*>(WS)[i] = __ldg(reinterpret_cast<const float4*>(P) + i);
-    __syncthreads();
     // input planes (channels 0..2) into D, misc cells -> meta embedding Linear(6->16)+ReLU into VC[.][324..339]
     for (int k = t; k < 3 * N; k += V21_THREADS) {
         const int c = k / N, n = k - c * N, l = n / 81, pos = n - l * 81, slot = slot_of[l];
@@ -141,8 +149,8 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
     }
     __syncthreads();
     // first_layer: Conv3x3(3->24) + BN + ReLU; task = (group of 4 outputs) x (leaf, board row): 9 x 4 outputs from 3 x 27 inputs
-    for (int k = t; k < 6 * 36; k += V21_THREADS) {
-        const int og = k / 36, m = k - 36 * og, r = m % 9, o0 = 4 * og;
+    for (int k = t; k < 6 * ROWS; k += V21_THREADS) {
+        const int og = k / ROWS, m = k - ROWS * og, r = m % 9, o0 = 4 * og;
         float acc[9][4];
 #pragma unroll
         for (int q = 0; q < 9; q++) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
@@ -175,12 +183,13 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
         }
     }
     __syncthreads();
+#pragma unroll 1
     for (int b = 0; b < 4; b++) {                                                    // trunk: InvertedResidual x 4
         const V21Layout::Blk B = L.blk[b];
-        conv1x1<24, 48, 8, 1, false>(WS + B.we, WS + B.be, X, E);
+        conv1x1<TB, 24, 48, 8, 1, false>(WS + B.we, WS + B.be, X, E);
         __syncthreads();
-        for (int k = t; k < 48 * 36; k += V21_THREADS) {                              // depthwise 3x3 + BN + ReLU; task = (channel, leaf, board row)
-            const int c = k / 36, r = (k - 36 * c) % 9;
+        for (int k = t; k < 48 * ROWS; k += V21_THREADS) {                            // depthwise 3x3 + BN + ReLU; task = (channel, leaf, board row)
+            const int c = k / ROWS, r = (k - ROWS * c) % 9;
             const float* e = E + 9 * k;                                               // = E + c*N + leaf*81 + r*9
             float w[9], a[9];
 #pragma unroll
@@ -207,85 +216,92 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
             for (int q = 0; q < 9; q++) D[9 * k + q] = fmaxf(a[q], 0.f);
         }
         __syncthreads();
-        conv1x1<48, 24, 4, 0, true>(WS + B.wp, WS + B.bp, D, X);                      // project + residual (X holds the block input)
+        conv1x1<TB, 48, 24, 4, 0, true>(WS + B.wp, WS + B.bp, D, X);                  // project + residual (X holds the block input)
         __syncthreads();
     }
     // heads (both read X only; E and D are free): policy logits on warps 0..7 overwrite E/D, value features on warps 8..10
     if (t < 3 * 81) {                                                                 // 1x1 24->42 + BN -> logits[r][q][plane]; task = 14 planes x position
         const int og = t / 81, pos = t - og * 81, o0 = 14 * og;
-        float acc[14][4];
+        float acc[14][TB];
 #pragma unroll
-        for (int j = 0; j < 14; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int j = 0; j < 14; j++)
+#pragma unroll
+            for (int l = 0; l < TB; l++) acc[j][l] = 0.f;
 #pragma unroll 2
         for (int i = 0; i < 24; i++) {
-            const float x[4] = {X[i * N + pos], X[i * N + 81 + pos], X[i * N + 162 + pos], X[i * N + 243 + pos]};
+            float x[TB];
+#pragma unroll
+            for (int l = 0; l < TB; l++) x[l] = X[i * N + l * 81 + pos];
             const float2* w2 = reinterpret_cast<const float2*>(WS + L.wpi + i * 42 + o0);
 #pragma unroll
             for (int j2 = 0; j2 < 7; j2++) {
                 const float2 w = w2[j2];
 #pragma unroll
-                for (int l = 0; l < 4; l++) { acc[2 * j2][l] = fmaf(w.x, x[l], acc[2 * j2][l]); acc[2 * j2 + 1][l] = fmaf(w.y, x[l], acc[2 * j2 + 1][l]); }
+                for (int l = 0; l < TB; l++) { acc[2 * j2][l] = fmaf(w.x, x[l], acc[2 * j2][l]); acc[2 * j2 + 1][l] = fmaf(w.y, x[l], acc[2 * j2 + 1][l]); }
             }
         }
 #pragma unroll
         for (int j2 = 0; j2 < 7; j2++) {
             const float b0 = WS[L.bpi + o0 + 2 * j2], b1 = WS[L.bpi + o0 + 2 * j2 + 1];
 #pragma unroll
-            for (int l = 0; l < 4; l++) *reinterpret_cast<float2*>(LG + l * A + pos * 42 + o0 + 2 * j2) = make_float2(acc[2 * j2][l] + b0, acc[2 * j2 + 1][l] + b1);
+            for (int l = 0; l < TB; l++) *reinterpret_cast<float2*>(LG + l * A + pos * 42 + o0 + 2 * j2) = make_float2(acc[2 * j2][l] + b0, acc[2 * j2 + 1][l] + b1);
         }
     } else if (t >= 256 && t < 256 + 81) {                                            // 1x1 24->4 + BN + ReLU, flattened channel-major
         const int pos = t - 256;
-        float acc[4][4];
+        float acc[4][TB];
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = WS[L.bvc + c];
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int l = 0; l < TB; l++) acc[c][l] = WS[L.bvc + c];
 #pragma unroll 4
         for (int i = 0; i < 24; i++) {
-            const float x[4] = {X[i * N + pos], X[i * N + 81 + pos], X[i * N + 162 + pos], X[i * N + 243 + pos]};
             const float4 w = *reinterpret_cast<const float4*>(WS + L.wvc + i * 4);
 #pragma unroll
-            for (int l = 0; l < 4; l++) {
-                acc[0][l] = fmaf(w.x, x[l], acc[0][l]); acc[1][l] = fmaf(w.y, x[l], acc[1][l]);
-                acc[2][l] = fmaf(w.z, x[l], acc[2][l]); acc[3][l] = fmaf(w.w, x[l], acc[3][l]);
+            for (int l = 0; l < TB; l++) {
+                const float x = X[i * N + l * 81 + pos];
+                acc[0][l] = fmaf(w.x, x, acc[0][l]); acc[1][l] = fmaf(w.y, x, acc[1][l]);
+                acc[2][l] = fmaf(w.z, x, acc[2][l]); acc[3][l] = fmaf(w.w, x, acc[3][l]);
             }
         }
 #pragma unroll
         for (int c = 0; c < 4; c++)
 #pragma unroll
-            for (int l = 0; l < 4; l++) VC[l * 340 + c * 81 + pos] = fmaxf(acc[c][l], 0.f);
+            for (int l = 0; l < TB; l++) VC[l * 340 + c * 81 + pos] = fmaxf(acc[c][l], 0.f);
     }
     __syncthreads();
     {   // value Linear(340 -> 64): K split in 8 slices of 43 (the last one padded with zero weights), one thread per (slice, output), all
-        // four leaves; fully unrolled so the 43 weight loads (L2: the 87 KB matrix does not fit the 28 KB left to L1) are in flight together
+        // leaves; fully unrolled so the 43 weight loads (L2: the 87 KB matrix does not fit the 28 KB left to L1) are in flight together
         const int ks = t >> 6, j = t & 63, i0 = 43 * ks;
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        float a[TB];
+#pragma unroll
+        for (int l = 0; l < TB; l++) a[l] = 0.f;
 #pragma unroll
         for (int ii = 0; ii < 43; ii++) {
             const int i = min(i0 + ii, 339);
             const float w = i0 + ii < 340 ? __ldg(P + L.f1 + i * 64 + j) : 0.f;
 #pragma unroll
-            for (int l = 0; l < 4; l++) a[l] = fmaf(w, VC[l * 340 + i], a[l]);
+            for (int l = 0; l < TB; l++) a[l] = fmaf(w, VC[l * 340 + i], a[l]);
         }
 #pragma unroll
-        for (int l = 0; l < 4; l++) VP[(ks * TB + l) * 64 + j] = a[l];
+        for (int l = 0; l < TB; l++) VP[(ks * TB + l) * 64 + j] = a[l];
     }
-    // masked softmax over 3402 actions: where(valid, logits, -1e8) -> log_softmax -> exp; four warps per leaf, mask words interleaved
-    // (warp wv owns words wv, wv+4, ...: 27 at most). Mask words are loaded once (lane i holds word wv+4i) and the masked logits stay in registers.
-    const int sl = warp >> 2, wv = warp & 3, slot = slot_of[sl];
-    constexpr int SW = (MW + 3) / 4;                                                  // 27 words per warp
+    // masked softmax over 3402 actions: where(valid, logits, -1e8) -> log_softmax -> exp; WPL warps per leaf, mask words interleaved
+    // (warp wv owns words wv, wv+WPL, ...). Mask words are loaded once (lane i holds word wv+WPL*i) and the masked logits stay in registers.
+    const int sl = warp / WPL, wv = warp % WPL, slot = slot_of[sl];
     float val[SW];
     {
-        const uint32_t mword = (slot >= 0 && wv + 4 * lane < MW) ? __ldg(masks + (size_t)slot * MW + wv + 4 * lane) : 0u;
+        const uint32_t mword = (slot >= 0 && wv + WPL * lane < MW) ? __ldg(masks + (size_t)slot * MW + wv + WPL * lane) : 0u;
         const float* lg = LG + sl * A;
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < SW; i++) {
-            const int k = wv + 4 * i, a = lane + 32 * k;
+            const int k = wv + WPL * i, a = lane + 32 * k;
             const uint32_t m = __shfl_sync(FULL, mword, i);
             val[i] = (k < MW && a < A) ? ((m >> lane & 1) ? lg[a] : -1e8f) : -INFINITY;   // -inf past the end of the action space
             mx = fmaxf(mx, val[i]);
         }
         mx = warp_max_f32(mx);
-        if (lane == 0) red[0][sl][wv] = mx;
+        if (lane == 0) red[warp] = mx;
     }
     __syncthreads();
     if (t < TB * 64) {                                                                // value Linear: bias + the 8 partials in a fixed order, ReLU
@@ -295,20 +311,25 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
         for (int ks = 0; ks < 8; ks++) a += VP[(ks * TB + l) * 64 + j];
         VH[l * 64 + j] = fmaxf(a, 0.f);
     }
-    const float mx = fmaxf(fmaxf(red[0][sl][0], red[0][sl][1]), fmaxf(red[0][sl][2], red[0][sl][3]));
+    float mx = red[sl * WPL];
+#pragma unroll
+    for (int i = 1; i < WPL; i++) mx = fmaxf(mx, red[sl * WPL + i]);
     {
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < SW; i++) sum += expf(val[i] - mx);
         sum = warp_sum_f32(sum);
-        if (lane == 0) red[1][sl][wv] = sum;
+        if (lane == 0) red[16 + warp] = sum;
     }
     __syncthreads();
     if (slot >= 0) {
-        const float lse = logf((red[1][sl][0] + red[1][sl][1]) + (red[1][sl][2] + red[1][sl][3]));
+        float tot = red[16 + sl * WPL];
+#pragma unroll
+        for (int i = 1; i < WPL; i++) tot += red[16 + sl * WPL + i];
+        const float lse = logf(tot);
         float* po = pi_out + (size_t)slot * A + lane;
 #pragma unroll
-        for (int i = 0; i < SW; i++) { const int k = wv + 4 * i; if (k < MW && lane + 32 * k < A) po[32 * k] = expf(val[i] - mx - lse); }
+        for (int i = 0; i < SW; i++) { const int k = wv + WPL * i; if (k < MW && lane + 32 * k < A) po[32 * k] = expf(val[i] - mx - lse); }
     }
     if (warp < TB * 2) {                                                              // value Linear(64 -> 2), tanh: one warp per (leaf, output)
         const int l = warp >> 1, o = warp & 1, vslot = slot_of[l];
@@ -316,6 +337,26 @@ k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, 
         a = warp_sum_f32(a);
         if (lane == 0 && vslot >= 0) v_out[(size_t)vslot * 2 + o] = tanhf(a + __ldg(P + L.f2b + o));
     }
+}
+
+// boards: int8[.][324] HWC with `bstride` bytes between boards; masks: 107 words per slot; list/count as in k_v80_forward.
+// CTAs [0, n_big) take 4 leaves each, CTAs [n_big, gridDim.x) 2 leaves each (v21_plan).
+__global__ void __launch_bounds__(V21_THREADS, 1)
+k_v21_forward(const float* __restrict__ P, const __grid_constant__ V21Layout L, const int* count_ptr, const int* list,
+              const int8_t* boards, int bstride, const uint32_t* masks, float* pi_out, float* v_out, int n_max, int n_big) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int slot_of[4];
+    __shared__ float red[32];
+    const int count = count_ptr ? min(*count_ptr, n_max) : n_max;
+    const bool big = (int)blockIdx.x < n_big;
+    const int tile0 = big ? 4 * blockIdx.x : 4 * n_big + 2 * ((int)blockIdx.x - n_big), tb = big ? 4 : 2;
+    if (tile0 >= count) return;
+    const int t = threadIdx.x;
+    if (t < 4) { const int j = tile0 + t; slot_of[t] = (t < tb && j < count) ? (list ? list[j] : j) : -1; }
+    for (int i = t; i < L.f1 / 4; i += V21_THREADS) reinterpret_cast<float4*>(smem + V21_WS_OFF)[i] = __ldg(reinterpret_cast<const float4*>(P) + i);
+    __syncthreads();
+    if (big) v21_tile<4>(P, L, smem, slot_of, red, boards, bstride, masks, pi_out, v_out);
+    else     v21_tile<2>(P, L, smem, slot_of, red, boards, bstride, masks, pi_out, v_out);
 }
 
 }  // namespace azg

@@ -144,6 +144,20 @@ def test_v21_forward_golden(game, v21_golden, tag):
         np.testing.assert_allclose(v2, g['v'][:n], rtol=0, atol=1e-5)
 
 
+def test_v21_forward_large_batch_mixed_tiles(game, v21_golden):
+    """720 leaves = full rounds of 4-leaf CTA tiles plus a tail of 2-leaf tiles (net_v21.cuh v21_plan): every replica of the 48 golden
+    boards must match the reference's outputs at 1e-5, whichever tile shape evaluated it."""
+    from azg_b200.nnet import AbaloneNNetWrapper
+    g = v21_golden['shipped']
+    net = AbaloneNNetWrapper(game, {'nn_version': 21}, state_dict=g['sd'])
+    reps = 15
+    pi, v = net.predict_batch(np.concatenate([g['boards']] * reps), np.concatenate([g['valids']] * reps))
+    assert pi.shape[0] == 48 * reps
+    np.testing.assert_allclose(pi, np.concatenate([g['pi']] * reps), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(v, np.concatenate([g['v']] * reps), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(pi.sum(1), 1.0, rtol=0, atol=1e-5)
+
+
 def test_v21_in_the_search_loop(game, v21_golden, aba_kat):
     from azg_b200.nnet import AbaloneNNetWrapper
     sd = v21_golden['shipped']['sd']
