@@ -79,12 +79,23 @@ struct Abalone {
             else return true;
         }
     }
-    // WARP: legal-action bitmask into `w` (MASK_WORDS words of warp-private shared memory), visible to all lanes on return.
+    // WARP: legal-action bitmask into `w` (MASK_WORDS words of warp-private SHARED memory), visible to all lanes on return.
+    // Only cells holding one of the mover's marbles can start an action (valid_moves :262: the first test of every action), so the
+    // lanes enumerate (own marble, plane) pairs -- at most 14 x 42 = 588 instead of 3402 actions -- and set bits with shared atomics.
     static __device__ void valid_mask(const int8_t* b, int player, int lane, uint32_t* w) {
-        for (int k = 0; k < MASK_WORDS; k++) {
-            const int a = lane + 32 * k;
-            const uint32_t m = __ballot_sync(FULL, a < A && action_valid(b, a, player));
-            if (lane == 0) w[k] = m;
+        for (int k = lane; k < MASK_WORDS; k += 32) w[k] = 0u;
+        uint32_t own[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const int c = lane + 32 * i; own[i] = __ballot_sync(FULL, c < 81 && b[4 * c + player] != 0); }
+        const int n0 = __popc(own[0]), n1 = __popc(own[1]), n = n0 + n1 + __popc(own[2]);
+        __syncwarp();
+        for (int idx = lane; idx < n * 42; idx += 32) {
+            int mi = idx / 42; const int plane = idx - 42 * mi;
+            uint32_t m; int base;
+            if (mi < n0) { m = own[0]; base = 0; } else if (mi < n0 + n1) { m = own[1]; base = 32; mi -= n0; } else { m = own[2]; base = 64; mi -= n0 + n1; }
+            for (int j = 0; j < mi; j++) m &= m - 1;                       // drop the mi lowest marbles of this word
+            const int a = (base + __ffs(m) - 1) * 42 + plane;              // r*378 + q*42 + plane with cell = 9r + q
+            if (action_valid(b, a, player)) atomicOr(&w[a >> 5], 1u << (a & 31));
         }
         __syncwarp();
     }
