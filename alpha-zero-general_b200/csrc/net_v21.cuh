@@ -66,24 +66,29 @@ inline void v21_prepare(const float* src, const V21Layout& L, float* dst) {
     { const float *W = take(2 * 64), *b = take(2); for (int o = 0; o < 2; o++) { dst[L.f2b + o] = b[o]; for (int k = 0; k < 64; k++) dst[L.f2 + o * 64 + k] = W[o * 64 + k]; } }
 }
 
-// out[o][l][pos] = act(bias[o] + sum_k W[k][o] * in[k][l][pos]) (+ out if RES); task = (group of OG outputs) x (position, all TB leaves)
+// out[o][n] = act(bias[o] + sum_k W[k][o] * in[k][n]) (+ out if RES) over the N = 81*TB positions of the tile; task = (group of OG
+// outputs) x (TB consecutive positions: one 128-bit (TB = 4) or 64-bit (TB = 2) activation load per input channel)
+template <int TB> struct V21Vec;
+template <> struct V21Vec<4> { typedef float4 T; };
+template <> struct V21Vec<2> { typedef float2 T; };
 template <int TB, int CIN, int COUT, int OG, int ACT, bool RES>
 __device__ __forceinline__ void conv1x1(const float* W, const float* bias, const float* in, float* out) {
     static_assert(COUT % OG == 0 && OG % 4 == 0 && COUT % 4 == 0, "128-bit weight broadcasts");
+    typedef typename V21Vec<TB>::T VT;
     constexpr int N = TB * 81, TASKS = (COUT / OG) * 81;
     for (int t = threadIdx.x; t < TASKS; t += V21_THREADS) {
-        const int og = t / 81, pos = t - og * 81, o0 = OG * og;
+        const int og = t / 81, nq = t - og * 81, o0 = OG * og;
         float acc[OG][TB];
 #pragma unroll
         for (int j = 0; j < OG; j++)
 #pragma unroll
             for (int l = 0; l < TB; l++) acc[j][l] = 0.f;
-        const float* xin = in + pos; const float* wk = W + o0;
+        const float* xin = in + TB * nq; const float* wk = W + o0;
 #pragma unroll 4
         for (int k = 0; k < CIN; k++) {
+            const VT xv = *reinterpret_cast<const VT*>(xin + k * N);
             float x[TB];
-#pragma unroll
-            for (int l = 0; l < TB; l++) x[l] = xin[k * N + l * 81];
+            memcpy(x, &xv, sizeof(xv));
             float w[OG];
 #pragma unroll
             for (int j4 = 0; j4 < OG / 4; j4++) {
@@ -98,14 +103,17 @@ __device__ __forceinline__ void conv1x1(const float* W, const float* bias, const
 #pragma unroll
         for (int j = 0; j < OG; j++) {
             const float b = bias[o0 + j];
+            VT* o = reinterpret_cast<VT*>(out + (o0 + j) * N + TB * nq);
+            float r[TB], v[TB];
+            if (RES) { const VT rv = *o; memcpy(r, &rv, sizeof(rv)); }
 #pragma unroll
             for (int l = 0; l < TB; l++) {
-                float v = acc[j][l] + b;
-                if (ACT) v = fmaxf(v, 0.f);
-                float* o = out + (o0 + j) * N + l * 81 + pos;
-                if (RES) v += *o;
-                *o = v;
+                v[l] = acc[j][l] + b;
+                if (ACT) v[l] = fmaxf(v[l], 0.f);
+                if (RES) v[l] += r[l];
             }
+            VT ov; memcpy(&ov, v, sizeof(ov));
+            *o = ov;
         }
     }
 }
