@@ -227,7 +227,7 @@ __device__ __forceinline__ void v21_tile(const float* __restrict__ P, const V21L
         conv1x1<TB, 48, 24, 4, 0, true>(WS + B.wp, WS + B.bp, D, X);                  // project + residual (X holds the block input)
         __syncthreads();
     }
-    // heads (both read X only; E and D are free): policy logits on warps 0..7 overwrite E/D, value features on warps 8..10
+    // heads (both read X only; E and D are free): policy logits on warps 0..7 overwrite E/D; value features and value Linear on warps 8..15
     if (t < 3 * 81) {                                                                 // 1x1 24->42 + BN -> logits[r][q][plane]; task = 14 planes x position
         const int og = t / 81, pos = t - og * 81, o0 = 14 * og;
         float acc[14][TB];
@@ -254,45 +254,46 @@ __device__ __forceinline__ void v21_tile(const float* __restrict__ P, const V21L
 #pragma unroll
             for (int l = 0; l < TB; l++) *reinterpret_cast<float2*>(LG + l * A + pos * 42 + o0 + 2 * j2) = make_float2(acc[2 * j2][l] + b0, acc[2 * j2 + 1][l] + b1);
         }
-    } else if (t >= 256 && t < 256 + 81) {                                            // 1x1 24->4 + BN + ReLU, flattened channel-major
-        const int pos = t - 256;
-        float acc[4][TB];
+    } else if (t >= 256) {                                                            // warps 8..15: the value path, under the policy conv
+        if (t < 256 + 81) {                                                           // 1x1 24->4 + BN + ReLU, flattened channel-major
+            const int pos = t - 256;
+            float acc[4][TB];
 #pragma unroll
-        for (int c = 0; c < 4; c++)
+            for (int c = 0; c < 4; c++)
 #pragma unroll
-            for (int l = 0; l < TB; l++) acc[c][l] = WS[L.bvc + c];
+                for (int l = 0; l < TB; l++) acc[c][l] = WS[L.bvc + c];
 #pragma unroll 4
-        for (int i = 0; i < 24; i++) {
-            const float4 w = *reinterpret_cast<const float4*>(WS + L.wvc + i * 4);
+            for (int i = 0; i < 24; i++) {
+                const float4 w = *reinterpret_cast<const float4*>(WS + L.wvc + i * 4);
 #pragma unroll
-            for (int l = 0; l < TB; l++) {
-                const float x = X[i * N + l * 81 + pos];
-                acc[0][l] = fmaf(w.x, x, acc[0][l]); acc[1][l] = fmaf(w.y, x, acc[1][l]);
-                acc[2][l] = fmaf(w.z, x, acc[2][l]); acc[3][l] = fmaf(w.w, x, acc[3][l]);
+                for (int l = 0; l < TB; l++) {
+                    const float x = X[i * N + l * 81 + pos];
+                    acc[0][l] = fmaf(w.x, x, acc[0][l]); acc[1][l] = fmaf(w.y, x, acc[1][l]);
+                    acc[2][l] = fmaf(w.z, x, acc[2][l]); acc[3][l] = fmaf(w.w, x, acc[3][l]);
+                }
             }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int l = 0; l < TB; l++) VC[l * 340 + c * 81 + pos] = fmaxf(acc[c][l], 0.f);
         }
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int l = 0; l < TB; l++) VC[l * 340 + c * 81 + pos] = fmaxf(acc[c][l], 0.f);
-    }
-    __syncthreads();
-    {   // value Linear(340 -> 64): K split in 8 slices of 43 (the last one padded with zero weights), one thread per (slice, output), all
-        // leaves; fully unrolled so the 43 weight loads (L2: the 87 KB matrix does not fit the 28 KB left to L1) are in flight together
-        const int ks = t >> 6, j = t & 63, i0 = 43 * ks;
+        asm volatile("bar.sync 1, 256;" ::: "memory");                                // VC complete (warps 8..15 only; warps 0..7 are in the policy conv)
+        // value Linear(340 -> 64): K split in 4 slices of 85, one thread per (slice, output), all leaves; unrolled so that the weight
+        // loads (L2: the 87 KB matrix does not fit the 28 KB left to L1) are in flight together
+        const int ks = (t - 256) >> 6, j = t & 63, i0 = 85 * ks;
         float a[TB];
 #pragma unroll
         for (int l = 0; l < TB; l++) a[l] = 0.f;
 #pragma unroll
-        for (int ii = 0; ii < 43; ii++) {
-            const int i = min(i0 + ii, 339);
-            const float w = i0 + ii < 340 ? __ldg(P + L.f1 + i * 64 + j) : 0.f;
+        for (int ii = 0; ii < 85; ii++) {
+            const float w = __ldg(P + L.f1 + (i0 + ii) * 64 + j);
 #pragma unroll
-            for (int l = 0; l < TB; l++) a[l] = fmaf(w, VC[l * 340 + i], a[l]);
+            for (int l = 0; l < TB; l++) a[l] = fmaf(w, VC[l * 340 + i0 + ii], a[l]);
         }
 #pragma unroll
         for (int l = 0; l < TB; l++) VP[(ks * TB + l) * 64 + j] = a[l];
     }
+    __syncthreads();
     // masked softmax over 3402 actions: where(valid, logits, -1e8) -> log_softmax -> exp; WPL warps per leaf, mask words interleaved
     // (warp wv owns words wv, wv+WPL, ...). Mask words are loaded once (lane i holds word wv+WPL*i) and the masked logits stay in registers.
     const int sl = warp / WPL, wv = warp % WPL, slot = slot_of[sl];
@@ -312,11 +313,11 @@ __device__ __forceinline__ void v21_tile(const float* __restrict__ P, const V21L
         if (lane == 0) red[warp] = mx;
     }
     __syncthreads();
-    if (t < TB * 64) {                                                                // value Linear: bias + the 8 partials in a fixed order, ReLU
+    if (t < TB * 64) {                                                                // value Linear: bias + the 4 partials in a fixed order, ReLU
         const int l = t >> 6, j = t & 63;
         float a = __ldg(P + L.f1b + j);
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) a += VP[(ks * TB + l) * 64 + j];
+        for (int ks = 0; ks < 4; ks++) a += VP[(ks * TB + l) * 64 + j];
         VH[l * 64 + j] = fmaxf(a, 0.f);
     }
     float mx = red[sl * WPL];
