@@ -56,3 +56,17 @@ def test_no_cpu_fallback():
         g.getInitBoard()
     with pytest.raises(lib.AzgError):
         g.getValidMoves(np.zeros((56, 7), np.int8), 0)
+
+
+def test_v21_tile_plan_host_check(tmp_path):
+    """net_v21.cuh: v21_plan (4-leaf tiles + a tail of 2-leaf tiles) covers every batch size; host-only program, no kernel launch."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    exe = str(tmp_path / 'v21_plan_check')
+    src = os.path.join(ROOT, 'tests', 'host', 'v21_plan_check.cu')
+    subprocess.run([nvcc, '-std=c++17', '-O1', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', exe, src], check=True, timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == 'ok', out.stdout + out.stderr
