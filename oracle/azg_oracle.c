@@ -654,6 +654,187 @@ int azo_sant_symmetries(const i8* b, const float* pi, const u8* valids, i8* ob, 
     return 8;
 }
 
+/* ---------------------------------------------------------------- Azul (2 players) ------- */
+/* azul/AzulLogicNumba.py (rules) and azul/AzulLogic.py:4-126 (the 120 factory permutations). ROUND-2 GROUNDWORK: rules only, pinned by
+ * tests/golden/azul_kat.npz; no CUDA plugin, MCTS dispatch or net for this game yet.
+ * State int8[23][6] (:6-24): row 0 scores (P0, P1, round), 1 bag, 2 discards, 3 centre (+ first-player token in column 5), 4-8 the five
+ * factories, 9-10 pattern-line colours of P0/P1 (-1 = empty; column 5 = holds the token), 11-12 tiles per pattern line (column 5 = floor),
+ * 13-17 / 18-22 the walls. Action = 30 source + 6 colour + line, source 0 = centre, line 5 = floor (:27-48). */
+#define AZU_S 138
+#define AZU_A 180
+#define AZ(b, r, c) (b)[6 * (r) + (c)]
+int azo_azul_get_round(const i8* b) { return AZ(b, 0, 2); }                                      /* get_round :333-334 */
+int azo_azul_get_score(const i8* b, int player) { return AZ(b, 0, player); }                     /* get_score :83-84 */
+
+void azo_azul_valid_moves(const i8* b, int player, u8* out) {                                    /* valid_moves :97-124 */
+    const i8* pc = &AZ(b, 9 + player, 0); const i8* pn = &AZ(b, 11 + player, 0);
+    for (int src = 0; src < 6; src++)
+        for (int colour = 0; colour < 5; colour++) {
+            const int avail = src == 0 ? AZ(b, 3, colour) != 0 : AZ(b, 3 + src, colour) > 0;     /* centre: astype(bool); factory: > 0 */
+            for (int line = 0; line < 6; line++) {
+                const int line_free = line == 5 ? 1 : pc[line] == -1;
+                const int wall_free = line == 5 ? 1 : AZ(b, 13 + 5 * player + line, (colour + line) % 5) == 0;
+                const int partial = pc[line] == colour && pn[line] < line + 1;
+                out[src * 30 + colour * 6 + line] = (u8)(avail && ((line_free && wall_free) || partial));
+            }
+        }
+}
+
+/* select_tiles_from_bag :258-269. seed != 0: the reference's deterministic draw; seed == 0 (true random there): the oracle's own RNG. */
+static void azul_draw(i8* b, int num, int64_t seed, azo_rng* rng, i8* result) {
+    for (int t = 0; t < num; t++) {
+        int total = 0; for (int c = 0; c < 6; c++) total += AZ(b, 1, c);
+        if (total <= 0) return;                                                                   /* the reference would divide by zero here */
+        int64_t tile;
+        if (seed == 0) tile = (int64_t)(rng_uniform(rng) * total);
+        else {
+            int64_t h = 0; for (int c = 0; c < 5; c++) h += (int64_t)AZ(b, 1, c) << c;
+            tile = (4594591 * (seed + h)) % total; if (tile < 0) tile += total;                   /* Python modulo */
+        }
+        int idx = 0, cum = 0;
+        for (; idx < 5; idx++) { cum += AZ(b, 1, idx); if (cum > tile) break; }                   /* searchsorted(cumsum, tile, side='right') */
+        if (idx > 4) idx = 4;
+        result[idx]++; AZ(b, 1, idx)--;
+    }
+}
+static int azul_setup_new_round(i8* b, int64_t seed, azo_rng* rng) {                             /* setup_new_round :238-256 */
+    for (int i = 0; i < 5; i++) {
+        int total = 0; for (int c = 0; c < 6; c++) total += AZ(b, 1, c);
+        i8 res[6] = {0, 0, 0, 0, 0, 0};
+        if (total < 4) {
+            for (int c = 0; c < 6; c++) { AZ(b, 4 + i, c) = AZ(b, 1, c); AZ(b, 1, c) = AZ(b, 2, c); AZ(b, 2, c) = 0; }
+            azul_draw(b, 4 - total, seed, rng, res);
+            for (int c = 0; c < 6; c++) AZ(b, 4 + i, c) = (i8)(AZ(b, 4 + i, c) + res[c]);
+        } else {
+            azul_draw(b, 4, seed, rng, res);
+            for (int c = 0; c < 6; c++) AZ(b, 4 + i, c) = res[c];
+        }
+    }
+    int next_player;
+    if (AZ(b, 10, 5) == 1) { next_player = 1; AZ(b, 10, 5) = 0; } else { next_player = 0; AZ(b, 9, 5) = 0; }
+    AZ(b, 0, 2) = (i8)(AZ(b, 0, 2) + 1);
+    AZ(b, 3, 5) = 1;
+    return next_player;
+}
+static int azul_run(const i8* w, int r, int c, int along_row) {                                   /* count_consecutive_ones :199-210 */
+    int count = 1;
+    if (along_row) { for (int k = c - 1; k >= 0 && w[6 * r + k] == 1; k--) count++; for (int k = c + 1; k < 5 && w[6 * r + k] == 1; k++) count++; }
+    else { for (int k = r - 1; k >= 0 && w[6 * k + c] == 1; k--) count++; for (int k = r + 1; k < 5 && w[6 * k + c] == 1; k++) count++; }
+    return count;
+}
+static int azul_score_change(i8* w, int r, int c) {                                              /* score_change :212-220; w = the player's 5 wall rows */
+    w[6 * r + c] = 1;
+    const int row_adj = (c > 0 && w[6 * r + c - 1] == 1) || (c < 4 && w[6 * r + c + 1] == 1);
+    const int col_adj = (r > 0 && w[6 * (r - 1) + c] == 1) || (r < 4 && w[6 * (r + 1) + c] == 1);
+    if (!row_adj && !col_adj) return 1;
+    return (row_adj ? azul_run(w, r, c, 1) : 0) + (col_adj ? azul_run(w, r, c, 0) : 0);
+}
+static void azul_score_round(i8* b) {                                                            /* score_round :161-181 */
+    static const int FLOOR_PENALTY[8] = {0, 1, 2, 4, 6, 8, 11, 14};
+    int pl[10], rw[10], col[10], n = 0;
+    for (int p = 0; p < 2; p++) for (int r = 0; r < 5; r++) if (AZ(b, 11 + p, r) == r + 1) { pl[n] = p; rw[n] = r; col[n] = AZ(b, 9 + p, r); n++; }   /* np.where order */
+    for (int i = 0; i < n; i++) {
+        const int c = ((col[i] + rw[i]) % 5 + 5) % 5;
+        AZ(b, 0, pl[i]) = (i8)(AZ(b, 0, pl[i]) + azul_score_change(&AZ(b, 13 + 5 * pl[i], 0), rw[i], c));
+        AZ(b, 13 + 5 * pl[i] + rw[i], c) = 1;
+    }
+    for (int i = 0; i < n; i++) AZ(b, 2, (col[i] % 6 + 6) % 6) = (i8)(AZ(b, 2, (col[i] % 6 + 6) % 6) + rw[i]);
+    for (int i = 0; i < n; i++) { AZ(b, 11 + pl[i], rw[i]) = 0; AZ(b, 9 + pl[i], rw[i]) = -1; }
+    for (int p = 0; p < 2; p++) {
+        int fl = AZ(b, 11 + p, 5); if (fl > 7) fl = 7; if (fl < 0) fl = 0;
+        const int sc = AZ(b, 0, p) - FLOOR_PENALTY[fl];
+        AZ(b, 0, p) = (i8)(sc > 0 ? sc : 0);
+        AZ(b, 11 + p, 5) = 0;
+    }
+}
+static int azul_game_over(const i8* b) {                                                         /* check_game_over :153-159 */
+    for (int r = 0; r < 10; r++) { int all = 1; for (int c = 0; c < 5; c++) all &= AZ(b, 13 + r, c) == 1; if (all) return 1; }
+    return 0;
+}
+static void azul_score_bonuses(i8* b) {                                                          /* score_bonuses :183-197 */
+    for (int p = 0; p < 2; p++) {
+        const i8* w = &AZ(b, 13 + 5 * p, 0); int add = 0;
+        for (int r = 0; r < 5; r++) { int all = 1; for (int c = 0; c < 5; c++) all &= w[6 * r + c] == 1; if (all) add += 2; }
+        for (int c = 0; c < 5; c++) { int all = 1; for (int r = 0; r < 5; r++) all &= w[6 * r + c] == 1; if (all) add += 7; }
+        for (int i = 0; i < 5; i++) { int all = 1; for (int j = 0; j < 5; j++) all &= w[6 * j + (j + i) % 5] == 1; if (all) add += 10; }
+        AZ(b, 0, p) = (i8)(AZ(b, 0, p) + add);
+    }
+}
+int azo_azul_make_move(i8* b, int move, int player, int64_t seed, uint64_t rng_seed_) {         /* make_move :126-151 */
+    azo_rng rng; rng_seed(&rng, rng_seed_);
+    i8* src = move < 30 ? &AZ(b, 3, 0) : &AZ(b, 4 + (move - 30) / 30, 0);
+    const int colour = (move % 30) / 6, line = move % 6, num = src[colour];
+    int to_floor;
+    if (line == 5) to_floor = num;
+    else {
+        const int on_line = AZ(b, 11 + player, line);
+        const int to_line = line + 1 - on_line < num ? line + 1 - on_line : num;
+        to_floor = num - to_line;
+        AZ(b, 11 + player, line) = (i8)(on_line + to_line);
+        AZ(b, 9 + player, line) = (i8)colour;
+    }
+    AZ(b, 11 + player, 5) = (i8)(AZ(b, 11 + player, 5) + to_floor);
+    AZ(b, 2, colour) = (i8)(AZ(b, 2, colour) + to_floor);
+    src[colour] = 0;
+    if (move < 30) {
+        if (src[5] == 1) { AZ(b, 11 + player, 5) = (i8)(AZ(b, 11 + player, 5) + 1); AZ(b, 9 + player, 5) = 1; src[5] = 0; }
+    } else {
+        for (int c = 0; c < 6; c++) { AZ(b, 3, c) = (i8)(AZ(b, 3, c) + src[c]); src[c] = 0; }
+    }
+    int empty = 1;
+    for (int f = 0; f < 5; f++) for (int c = 0; c < 6; c++) empty &= AZ(b, 4 + f, c) == 0;
+    for (int c = 0; c < 5; c++) empty &= AZ(b, 3, c) == 0;
+    if (!empty) return (player + 1) % 2;
+    azul_score_round(b);
+    const int next_player = azul_setup_new_round(b, seed, &rng);
+    if (azul_game_over(b)) azul_score_bonuses(b);
+    return next_player;
+}
+void azo_azul_check_end_game(const i8* b, float* out) {                                          /* check_end_game :283-302 */
+    out[0] = out[1] = 0.f;
+    if (!azul_game_over(b)) return;
+    int rows[2] = {0, 0};
+    for (int p = 0; p < 2; p++) for (int r = 0; r < 5; r++) { int all = 1; for (int c = 0; c < 5; c++) all &= AZ(b, 13 + 5 * p + r, c) == 1; rows[p] += all; }
+    const int s0 = AZ(b, 0, 0), s1 = AZ(b, 0, 1);
+    if (s0 > s1 || (s0 == s1 && rows[0] > rows[1])) { out[0] = 1.f; out[1] = -1.f; }
+    else if (s1 > s0 || (s0 == s1 && rows[1] > rows[0])) { out[0] = -1.f; out[1] = 1.f; }
+    else { out[0] = 0.01f; out[1] = 0.01f; }
+}
+void azo_azul_swap_players(i8* b) {                                                              /* swap_players :304-309 (unconditional) */
+    i8 t = AZ(b, 0, 0); AZ(b, 0, 0) = AZ(b, 0, 1); AZ(b, 0, 1) = t;
+    for (int c = 0; c < 6; c++) {
+        t = AZ(b, 9, c); AZ(b, 9, c) = AZ(b, 10, c); AZ(b, 10, c) = t;
+        t = AZ(b, 11, c); AZ(b, 11, c) = AZ(b, 12, c); AZ(b, 12, c) = t;
+        for (int r = 0; r < 5; r++) { t = AZ(b, 13 + r, c); AZ(b, 13 + r, c) = AZ(b, 18 + r, c); AZ(b, 18 + r, c) = t; }
+    }
+}
+void azo_azul_init_game(i8* b, uint64_t seed) {                                                  /* init_game :86-92 (draws from the oracle's RNG) */
+    azo_rng rng; rng_seed(&rng, seed);
+    memset(b, 0, AZU_S);
+    for (int c = 0; c < 5; c++) { AZ(b, 1, c) = 20; AZ(b, 9, c) = -1; AZ(b, 10, c) = -1; }
+    (void)azul_setup_new_round(b, 0, &rng);
+}
+/* get_symmetries :311-331: all 120 orders of the five factories (AzulLogic.py:4-126 lists them in lexicographic order). */
+int azo_azul_symmetries(const i8* b, const float* pi, const u8* valids, i8* ob, float* opi, u8* ov) {
+    int perm[5] = {0, 1, 2, 3, 4}, k = 0;
+    for (;;) {
+        i8* o = ob + (size_t)k * AZU_S; float* op = opi + (size_t)k * AZU_A; u8* om = ov + (size_t)k * AZU_A;
+        memcpy(o, b, AZU_S); memcpy(op, pi, sizeof(float) * AZU_A); memcpy(om, valids, AZU_A);
+        for (int i = 0; i < 5; i++) {
+            memcpy(&AZ(o, 4 + i, 0), &AZ(b, 4 + perm[i], 0), 6);
+            memcpy(op + 30 * (i + 1), pi + 30 * (perm[i] + 1), sizeof(float) * 30);
+            memcpy(om + 30 * (i + 1), valids + 30 * (perm[i] + 1), 30);
+        }
+        k++;
+        int i = 3; while (i >= 0 && perm[i] > perm[i + 1]) i--;                                   /* next lexicographic permutation */
+        if (i < 0) break;
+        int j = 4; while (perm[j] < perm[i]) j--;
+        int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+        for (int a = i + 1, z = 4; a < z; a++, z--) { t = perm[a]; perm[a] = perm[z]; perm[z] = t; }
+    }
+    return k;
+}
+
 /* ---------------------------------------------------------------- nets ------------------ */
 /* (1) hash-net: see oracle/hashnet.py (test-only deterministic prior/value). */
 static uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }

@@ -81,6 +81,14 @@ def lib():
         L.azo_aba_swap_players.argtypes = [p8, C.c_int]
         L.azo_aba_init_game.argtypes = [p8]
         L.azo_aba_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_aba_symmetries.restype = C.c_int
+        L.azo_azul_get_round.argtypes = [p8]; L.azo_azul_get_round.restype = C.c_int
+        L.azo_azul_get_score.argtypes = [p8, C.c_int]; L.azo_azul_get_score.restype = C.c_int
+        L.azo_azul_valid_moves.argtypes = [p8, C.c_int, pu8]
+        L.azo_azul_make_move.argtypes = [p8, C.c_int, C.c_int, C.c_int64, C.c_uint64]; L.azo_azul_make_move.restype = C.c_int
+        L.azo_azul_check_end_game.argtypes = [p8, pf]
+        L.azo_azul_swap_players.argtypes = [p8]
+        L.azo_azul_init_game.argtypes = [p8, C.c_uint64]
+        L.azo_azul_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_azul_symmetries.restype = C.c_int
         L.azo_v80_forward.argtypes = [pf, C.c_int, C.c_int, p8, pu8, pf, pf]
         L.azo_v89_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
         L.azo_v21_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
@@ -333,6 +341,53 @@ def aba_symmetries(board, pi, valids):
     b = _board(board); pi = np.ascontiguousarray(pi, np.float32); v = np.ascontiguousarray(valids).astype(np.uint8)
     ob = np.zeros((12, 9, 9, 4), np.int8); op = np.zeros((12, ABA_A), np.float32); ov = np.zeros((12, ABA_A), np.uint8)
     k = lib().azo_aba_symmetries(_p(b, C.c_int8), _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
+    return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]
+
+
+# ---- Azul, 2 players (azul/AzulLogicNumba.py) -- rules only, round-2 groundwork ----
+AZUL_A = 180
+
+
+def azul_init_game(seed=0):
+    b = np.zeros((23, 6), np.int8); lib().azo_azul_init_game(_p(b, C.c_int8), int(seed)); return b
+
+
+def azul_valid_moves(board, player=0):
+    b = _board(board); out = np.zeros(AZUL_A, np.uint8)
+    lib().azo_azul_valid_moves(_p(b, C.c_int8), int(player), _p(out, C.c_uint8))
+    return out.astype(np.bool_)
+
+
+def azul_next_state(board, player, action, random_seed, rng_seed=0):
+    b = _board(board)
+    return b, lib().azo_azul_make_move(_p(b, C.c_int8), int(action), int(player), int(random_seed), int(rng_seed))
+
+
+def azul_game_ended(board):
+    b = _board(board); out = np.zeros(2, np.float32)
+    lib().azo_azul_check_end_game(_p(b, C.c_int8), _p(out, C.c_float))
+    return out
+
+
+def azul_canonical(board, player):
+    b = _board(board)
+    if player:
+        lib().azo_azul_swap_players(_p(b, C.c_int8))
+    return b
+
+
+def azul_get_round(board):
+    b = _board(board); return lib().azo_azul_get_round(_p(b, C.c_int8))
+
+
+def azul_get_score(board, player):
+    b = _board(board); return lib().azo_azul_get_score(_p(b, C.c_int8), int(player))
+
+
+def azul_symmetries(board, pi, valids):
+    b = _board(board); pi = np.ascontiguousarray(pi, np.float32); v = np.ascontiguousarray(valids).astype(np.uint8)
+    ob = np.zeros((120, 23, 6), np.int8); op = np.zeros((120, AZUL_A), np.float32); ov = np.zeros((120, AZUL_A), np.uint8)
+    k = lib().azo_azul_symmetries(_p(b, C.c_int8), _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
     return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]
 
 

@@ -96,6 +96,12 @@ def aba_kat():
 
 
 @pytest.fixture(scope='session')
+def azul_kat():
+    z = np.load(os.path.join(GOLDEN, 'azul_kat.npz'))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope='session')
 def aba_mcts_cases():
     z = np.load(os.path.join(GOLDEN, 'abalone_mcts.npz'))
     n = int(z['n_cases'])

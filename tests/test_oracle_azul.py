@@ -1,0 +1,47 @@
+"""Pins the CPU oracle's Azul (2 players) rules to vectors produced by the UNMODIFIED reference (tests/golden/azul_kat.npz, made by
+oracle/gen_golden_azul.py: 12 random games played to the end with `random_seed != 0`, i.e. the reference's deterministic tile draws).
+Bit-exact. Round-2 groundwork: rules only -- there is no CUDA plugin for this game yet."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+def test_valid_moves_bit_exact(azul_kat):
+    k = azul_kat
+    for i in range(len(k['action'])):
+        assert (O.azul_valid_moves(k['canonical'][i], 0) == k['valids'][i]).all(), i
+        assert (O.azul_valid_moves(k['board'][i], int(k['player'][i])) == k['valids'][i]).all(), i
+
+
+def test_next_state_ended_round_score_canonical(azul_kat):
+    k = azul_kat
+    new_rounds = 0
+    for i in range(len(k['action'])):
+        nb, npl = O.azul_next_state(k['board'][i], k['player'][i], k['action'][i], k['seed'][i])
+        assert npl == k['next_player'][i] and (nb == k['next_board'][i]).all(), f'ply {i} action {k["action"][i]}'
+        assert (O.azul_game_ended(nb) == k['ended'][i]).all()
+        assert O.azul_get_round(nb) == k['round'][i] and [O.azul_get_score(nb, 0), O.azul_get_score(nb, 1)] == list(k['score'][i])
+        assert (O.azul_canonical(k['board'][i], k['player'][i]) == k['canonical'][i]).all()
+        assert (O.azul_canonical(nb, npl) == k['next_canonical'][i]).all()
+        new_rounds += int(O.azul_get_round(nb) != O.azul_get_round(k['board'][i]))
+    # the fixture covers round scoring + refills (incl. bag refills from the discards), end-of-game bonuses and every game result
+    assert new_rounds >= 60 and (np.abs(k['ended']).sum(1) > 0).sum() == 12
+    assert (k['next_board'][:, 1, :5].sum(1) < 20).any()
+
+
+def test_symmetries_all_120_factory_orders(azul_kat):
+    k = azul_kat
+    for i in range(len(k['sym_pi'])):
+        s = O.azul_symmetries(k['sym_board'][i], k['sym_pi'][i], k['sym_valids'][i])
+        assert len(s) == 120
+        for j, (b, p, v) in enumerate(s):
+            assert (b == k['sym_out_boards'][i][j]).all(), (i, j)
+            assert (p == k['sym_out_pi'][i][j]).all(), (i, j)
+            assert (v == k['sym_out_valids'][i][j]).all(), (i, j)
+
+
+def test_init_game_invariants():
+    for seed in range(20):
+        b = O.azul_init_game(seed)
+        assert b[1, :5].sum() == 80 and (b[4:9, :5].sum(1) == 4).all() and b[3, 5] == 1 and b[0, 2] == 1
+        assert (b[9:11, :5] == -1).all() and (b[11:23] == 0).all() and O.azul_valid_moves(b, 0).sum() > 0
