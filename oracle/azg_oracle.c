@@ -655,8 +655,8 @@ int azo_sant_symmetries(const i8* b, const float* pi, const u8* valids, i8* ob, 
 }
 
 /* ---------------------------------------------------------------- Azul (2 players) ------- */
-/* azul/AzulLogicNumba.py (rules) and azul/AzulLogic.py:4-126 (the 120 factory permutations). ROUND-2 GROUNDWORK: rules only, pinned by
- * tests/golden/azul_kat.npz; no CUDA plugin, MCTS dispatch or net for this game yet.
+/* azul/AzulLogicNumba.py (rules) and azul/AzulLogic.py:4-126 (the 120 factory permutations). ROUND-2 GROUNDWORK: rules + the game-generic MCTS (game id 3), pinned by
+ * tests/golden/azul_kat.npz and azul_mcts.npz; no CUDA plugin or net for this game yet.
  * State int8[23][6] (:6-24): row 0 scores (P0, P1, round), 1 bag, 2 discards, 3 centre (+ first-player token in column 5), 4-8 the five
  * factories, 9-10 pattern-line colours of P0/P1 (-1 = empty; column 5 = holds the token), 11-12 tiles per pattern line (column 5 = floor),
  * 13-17 / 18-22 the walls. Action = 30 source + 6 colour + line, source 0 = centre, line 5 = floor (:27-48). */
@@ -1130,7 +1130,7 @@ static node_t* insert(azo_mcts* m, const i8* key) {
 azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_noise, uint64_t seed) {
     azo_mcts* m = (azo_mcts*)calloc(1, sizeof(azo_mcts));
     m->cfg = *cfg; m->blob = blob;
-    if (cfg->game == 1) { m->S = SAN_S; m->A = SAN_A; } else if (cfg->game == 2) { m->S = ABA_S; m->A = ABA_A; } else { m->S = azo_state_rows(cfg->num_players) * COLS; m->A = NA; }
+    if (cfg->game == 1) { m->S = SAN_S; m->A = SAN_A; } else if (cfg->game == 2) { m->S = ABA_S; m->A = ABA_A; } else if (cfg->game == 3) { m->S = AZU_S; m->A = AZU_A; } else { m->S = azo_state_rows(cfg->num_players) * COLS; m->A = NA; }
     if (cfg->net_kind == 1) v80_bind(&m->net, blob, azo_state_rows(cfg->num_players), cfg->num_players);
     if (cfg->net_kind == 2) v89_bind(&m->net89, blob);
     if (cfg->net_kind == 3) v21_bind(&m->net21, blob);
@@ -1178,18 +1178,18 @@ static void softmax_temp(float* P, int n, double T) {
 }
 /* ---- game dispatch of the Game.py methods the search calls (MCTS.py:125-173) ---- */
 static void g_ended(const azo_mcts* m, const i8* b, int next_player, float* out) {
-    if (m->cfg.game == 1) azo_sant_check_end_game(b, next_player, out); else if (m->cfg.game == 2) azo_aba_check_end_game(b, out); else azo_check_end_game(b, m->cfg.num_players, out);
+    if (m->cfg.game == 1) azo_sant_check_end_game(b, next_player, out); else if (m->cfg.game == 2) azo_aba_check_end_game(b, out); else if (m->cfg.game == 3) azo_azul_check_end_game(b, out); else azo_check_end_game(b, m->cfg.num_players, out);
 }
 static void g_valid(const azo_mcts* m, const i8* b, u8* out) {
-    if (m->cfg.game == 1) azo_sant_valid_moves(b, 0, out); else if (m->cfg.game == 2) azo_aba_valid_moves(b, 0, out); else azo_valid_moves(b, m->cfg.num_players, 0, out);
+    if (m->cfg.game == 1) azo_sant_valid_moves(b, 0, out); else if (m->cfg.game == 2) azo_aba_valid_moves(b, 0, out); else if (m->cfg.game == 3) azo_azul_valid_moves(b, 0, out); else azo_valid_moves(b, m->cfg.num_players, 0, out);
 }
 static int g_move(const azo_mcts* m, i8* b, int a, int player, int64_t seed, azo_rng* rng) {
-    return m->cfg.game == 1 ? azo_sant_make_move(b, a, player) : m->cfg.game == 2 ? azo_aba_make_move(b, a, player) : azo_make_move(b, m->cfg.num_players, a, player, seed, rng);
+    return m->cfg.game == 1 ? azo_sant_make_move(b, a, player) : m->cfg.game == 2 ? azo_aba_make_move(b, a, player) : m->cfg.game == 3 ? azo_azul_make_move(b, a, player, seed, 1) : azo_make_move(b, m->cfg.num_players, a, player, seed, rng);
 }
 static void g_swap(const azo_mcts* m, i8* b, int nb) {
-    if (m->cfg.game == 1) azo_sant_swap_players(b, nb); else if (m->cfg.game == 2) azo_aba_swap_players(b, nb); else azo_swap_players(b, m->cfg.num_players, nb);
+    if (m->cfg.game == 1) azo_sant_swap_players(b, nb); else if (m->cfg.game == 2) azo_aba_swap_players(b, nb); else if (m->cfg.game == 3) { if (nb & 1) azo_azul_swap_players(b); } else azo_swap_players(b, m->cfg.num_players, nb);
 }
-static int g_round(const azo_mcts* m, const i8* b) { return m->cfg.game == 1 ? azo_sant_get_round(b) : m->cfg.game == 2 ? azo_aba_get_round(b) : azo_get_round(b); }
+static int g_round(const azo_mcts* m, const i8* b) { return m->cfg.game == 1 ? azo_sant_get_round(b) : m->cfg.game == 2 ? azo_aba_get_round(b) : m->cfg.game == 3 ? azo_azul_get_round(b) : azo_get_round(b); }
 
 /* MCTS.py:187-197; `noise` (length = number of legal actions) is either injected by the caller
  * (parity tests replay the reference's draws) or sampled here. */
@@ -1341,7 +1341,7 @@ static double temp_for_selfplay(double t_begin, double t_end, double half_life, 
 static void execute_episode(azo_mcts* m, uint64_t seed, double t0, double t1, double half, int max_plies, azo_run_stats* st) {
     int n = m->cfg.num_players, S = m->S; const int A = m->A; azo_rng rng; rng_seed(&rng, seed ^ 0xA5A5A5A5ULL);
     i8 board[MAXS], cb[MAXS];
-    if (m->cfg.game == 1) azo_sant_init_game(board, seed); else if (m->cfg.game == 2) azo_aba_init_game(board); else azo_init_game(board, n, seed);
+    if (m->cfg.game == 1) azo_sant_init_game(board, seed); else if (m->cfg.game == 2) azo_aba_init_game(board); else if (m->cfg.game == 3) azo_azul_init_game(board, seed); else azo_init_game(board, n, seed);
     int player = 0, step = 0; azo_mcts_reset(m);
     double probs[MAXA]; float q[MAXP], r[MAXP];
     for (;;) {

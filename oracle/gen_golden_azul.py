@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Golden step vectors for Azul (2 players) by RUNNING THE UNMODIFIED REFERENCE (test infrastructure; round-2 groundwork).
 
-    python oracle/gen_golden_azul.py [--out tests/golden]
+    python oracle/gen_golden_azul.py [--out tests/golden] [--only kat,mcts,episode]
 
 Imports azul/AzulGame.py (-> AzulLogicNumba.Board jitclass) from /root/reference. Random games are played with
 `random_seed != 0`, so every tile draw is the reference's deterministic one and the recorded next states are exact.
@@ -17,6 +17,9 @@ os.environ.setdefault('OMP_NUM_THREADS', '1')
 sys.path[:0] = [os.path.join(HERE, 'ref_shim'), '/root/reference', HERE]
 
 import numpy as np  # noqa: E402
+
+from hashnet import HashNet  # noqa: E402
+from gen_golden import MCTS_CONFIGS, RecordingRng, dotdict, tree_summary  # noqa: E402
 
 A = 180
 
@@ -71,8 +74,79 @@ def gen_kat(out, n_games=12):
           f'results {e[np.abs(e).sum(1) > 0].tolist()}, sym={len(sym["pi"])}')
 
 
+def gen_mcts(out):
+    """Root visit counts of the reference MCTS (MCTS.py:49-184) on Azul positions, driven by the hash-net (chance draws at round ends
+    follow the universes' seeds, MCTS.py:63)."""
+    from azul.AzulGame import AzulGame
+    from MCTS import MCTS
+    kat = np.load(os.path.join(out, 'azul_kat.npz'))
+    g = AzulGame()
+    net = HashNet(g)
+    idx0 = np.flatnonzero(kat['game'] == 0); idx1 = np.flatnonzero(kat['game'] == 6)
+    picks = [int(idx0[0]), int(idx0[len(idx0) // 3]), int(idx0[2 * len(idx0) // 3]), int(idx0[-4]), int(idx1[len(idx1) // 2]), int(idx1[-6])]
+    cases = []
+    for ci, (name, cfg) in enumerate(MCTS_CONFIGS.items()):
+        for pi_, p in enumerate(picks):
+            if name != 'default' and pi_ % 2 == 1:
+                continue
+            n_sims = 800 if (name == 'default' and pi_ in (0, 3)) else 200
+            args = dotdict(cfg, numMCTSSims=n_sims)
+            m = MCTS(g, net, args, dirichlet_noise=cfg['noise'])
+            rr = RecordingRng(1300 + 100 * ci + pi_)
+            m.rng = rr
+            root = np.array(kat['canonical'][p], copy=True)
+            probs, q, full = m.getActionProb(root, temp=1, force_full_search=True)
+            s = g.stringRepresentation(root)
+            raw = np.array([m.nodes_data[s][5][a] for a in range(A)], dtype=np.int64)
+            cases.append(dict(cfg=name, root=root, n_sims=n_sims, probs=np.array(probs, dtype=np.float64), q=np.array(q, dtype=np.float32), raw_counts=raw,
+                              noise=(rr.dirichlets[0] if rr.dirichlets else np.zeros(0)), summary=tree_summary(m)))
+            print(f'azul mcts {name} root#{p} n={n_sims} nodes={cases[-1]["summary"]} top={int(np.argmax(raw))}:{int(raw.max())}')
+    save = {'n_cases': np.array(len(cases))}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            save[f'c{i}_{k}'] = np.array(v)
+    np.savez_compressed(os.path.join(out, 'azul_mcts.npz'), **save)
+
+
+def gen_episode(out):
+    """Tree reuse across the plies of one game (MCTS.py:86-91 cleaning included): same MCTS object for 40 plies."""
+    from azul.AzulGame import AzulGame
+    from MCTS import MCTS
+    kat = np.load(os.path.join(out, 'azul_kat.npz'))
+    g = AzulGame()
+    net = HashNet(g)
+    cfg = MCTS_CONFIGS['default']; nsims = 120
+    args = dotdict(cfg, numMCTSSims=nsims)
+    np.random.seed(9)
+    m = MCTS(g, net, args, dirichlet_noise=False)
+    m.rng = RecordingRng(12)
+    board = np.array(kat['board'][0], copy=True); player = int(kat['player'][0])
+    roots, cnts, qs, actions, seeds, summaries = [], [], [], [], [], []
+    for ply in range(40):
+        cb = np.array(g.getCanonicalForm(board, player), copy=True)
+        probs, q, full = m.getActionProb(cb, temp=1, force_full_search=True)
+        raw = np.array([m.nodes_data[g.stringRepresentation(cb)][5][a] for a in range(A)], dtype=np.int64)
+        action = int(np.random.choice(A, p=np.array(probs) / np.sum(probs)))
+        seed = int(np.random.randint(1, 2 ** 31 - 1))
+        nb, nplayer = g.getNextState(board, player, action, random_seed=seed)
+        roots.append(cb); cnts.append(raw); qs.append(np.array(q, dtype=np.float32)); actions.append(action); seeds.append(seed); summaries.append(tree_summary(m))
+        board, player = np.array(nb, copy=True), nplayer
+        if np.array(g.getGameEnded(board, player)).any():
+            break
+    np.savez_compressed(os.path.join(out, 'azul_episode.npz'), n_sims=np.array(nsims), roots=np.array(roots), raw_counts=np.array(cnts), q=np.array(qs),
+                        actions=np.array(actions), seeds=np.array(seeds, dtype=np.int64), summaries=np.array(summaries))
+    print(f'azul episode: {len(roots)} plies, rounds seen {sorted(set(int(r[0, 2]) for r in roots))}, last summary={summaries[-1]}')
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(os.path.dirname(HERE), 'tests', 'golden'))
+    ap.add_argument('--only', default='kat,mcts,episode')
     a = ap.parse_args()
-    gen_kat(a.out)
+    only = a.only.split(',')
+    if 'kat' in only:
+        gen_kat(a.out)
+    if 'mcts' in only:
+        gen_mcts(a.out)
+    if 'episode' in only:
+        gen_episode(a.out)

@@ -175,8 +175,8 @@ def v80_forward(blob, boards, valids, n=2):
     return pi, val
 
 
-GAME_SPLENDOR, GAME_SANTORINI, GAME_ABALONE = 0, 1, 2
-GAME_ACTIONS = {GAME_SPLENDOR: 81, GAME_SANTORINI: 162, GAME_ABALONE: 3402}
+GAME_SPLENDOR, GAME_SANTORINI, GAME_ABALONE, GAME_AZUL = 0, 1, 2, 3
+GAME_ACTIONS = {GAME_SPLENDOR: 81, GAME_SANTORINI: 162, GAME_ABALONE: 3402, GAME_AZUL: 180}
 
 
 def make_cfg(num_players=2, numMCTSSims=800, ratio_fullMCTS=5, universes=1, forced_playouts=False, no_mem_optim=False,
@@ -344,7 +344,7 @@ def aba_symmetries(board, pi, valids):
     return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]
 
 
-# ---- Azul, 2 players (azul/AzulLogicNumba.py) -- rules only, round-2 groundwork ----
+# ---- Azul, 2 players (azul/AzulLogicNumba.py) -- rules + MCTS (GAME_AZUL), round-2 groundwork ----
 AZUL_A = 180
 
 

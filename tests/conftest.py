@@ -102,6 +102,19 @@ def azul_kat():
 
 
 @pytest.fixture(scope='session')
+def azul_mcts_cases():
+    z = np.load(os.path.join(GOLDEN, 'azul_mcts.npz'))
+    keys = ('cfg', 'root', 'n_sims', 'probs', 'q', 'raw_counts', 'noise', 'summary')
+    return [{k: z[f'c{i}_{k}'] for k in keys} for i in range(int(z['n_cases']))]
+
+
+@pytest.fixture(scope='session')
+def azul_episode():
+    z = np.load(os.path.join(GOLDEN, 'azul_episode.npz'))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope='session')
 def aba_mcts_cases():
     z = np.load(os.path.join(GOLDEN, 'abalone_mcts.npz'))
     n = int(z['n_cases'])

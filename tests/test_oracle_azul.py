@@ -1,8 +1,10 @@
 """Pins the CPU oracle's Azul (2 players) rules to vectors produced by the UNMODIFIED reference (tests/golden/azul_kat.npz, made by
 oracle/gen_golden_azul.py: 12 random games played to the end with `random_seed != 0`, i.e. the reference's deterministic tile draws).
-Bit-exact. Round-2 groundwork: rules only -- there is no CUDA plugin for this game yet."""
+azul_mcts.npz / azul_episode.npz: the reference's MCTS on Azul positions with the hash-net). Bit-exact.
+Round-2 groundwork: oracle only -- there is no CUDA plugin for this game yet."""
 import numpy as np
 
+from conftest import MCTS_CONFIGS
 from oracle import oracle as O
 
 
@@ -45,3 +47,33 @@ def test_init_game_invariants():
         b = O.azul_init_game(seed)
         assert b[1, :5].sum() == 80 and (b[4:9, :5].sum(1) == 4).all() and b[3, 5] == 1 and b[0, 2] == 1
         assert (b[9:11, :5] == -1).all() and (b[11:23] == 0).all() and O.azul_valid_moves(b, 0).sum() > 0
+
+
+def _cfg(name, n_sims):
+    c = MCTS_CONFIGS[name]
+    return O.make_cfg(numMCTSSims=int(n_sims), universes=c['universes'], forced_playouts=c['forced_playouts'], cpuct=c['cpuct'], fpu=c['fpu'],
+                      dirichletAlpha=c['dirichletAlpha'], temperature2=c['temperature'][2], net_kind=0, game=O.GAME_AZUL), c['noise']
+
+
+def test_mcts_counts_exact(azul_mcts_cases):
+    """Visit counts, policy, q and tree size of the reference's search (universes 0/1/3/8, forced playouts, injected Dirichlet noise)."""
+    assert len(azul_mcts_cases) == 15
+    for case in azul_mcts_cases:
+        cfg, noise = _cfg(str(case['cfg']), case['n_sims'])
+        m = O.MCTS(cfg, dirichlet_noise=noise)
+        probs, q, full, raw = m.getActionProb(case['root'], temp=1, force_full_search=True, noise=case['noise'])
+        assert (raw == case['raw_counts']).all(), str(case['cfg'])
+        np.testing.assert_allclose(probs, case['probs'], rtol=0, atol=1e-12)
+        assert (q == case['q']).all()
+        assert list(m.stats()[:3]) == list(case['summary'])
+
+
+def test_episode_tree_reuse_exact(azul_episode):
+    ep = azul_episode
+    cfg, _ = _cfg('default', ep['n_sims'])
+    m = O.MCTS(cfg, dirichlet_noise=False)
+    for i in range(len(ep['roots'])):
+        probs, q, full, raw = m.getActionProb(ep['roots'][i], temp=1, force_full_search=True)
+        assert (raw == ep['raw_counts'][i]).all(), f'ply {i}'
+        assert (q == ep['q'][i]).all(), f'ply {i}'
+        assert list(m.stats()[:3]) == list(ep['summaries'][i]), f'ply {i}'
