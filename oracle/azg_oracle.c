@@ -942,6 +942,79 @@ void azo_v80_forward(const float* blob, int n_players, int batch, const i8* boar
     for (int b = 0; b < batch; b++) v80_forward(&N, boards + (size_t)b * nv * 7, valids + (size_t)b * NA, pi + (size_t)b * NA, v + (size_t)b * n_players);
 }
 
+/* ---------------------------------------------------------------- AzulNNet V84 ------------ */
+/* azul/AzulNNet.py:84-111 (layers), :127-137 (forward), eval mode; same building blocks as SplendorNNet V80 on 23 tokens x 6 features:
+ * first_layer Linear(23->23)+BN, trunk InvertedResidual1d(23->115->23, ReLU, SE avg), policy head InvertedResidual1d(23->115->46,
+ * Hardswish, SE avg, no residual) -> Linear(276->180)+ReLU -> Linear(180->180), value head InvertedResidual1d(23->46->23, Hardswish,
+ * SE avg) -> Linear(138->2)+ReLU -> Linear(2->2). blob = state_dict tensors in the order of oracle.py:v80_order() (same module names).
+ * ROUND-2 GROUNDWORK (no CUDA kernel yet); pinned by tests/golden/azul_v84_*.npz at 1e-5. */
+#define V84_NV 23
+#define V84_F 6
+typedef struct { lin_bn expand, dw, project; const float *fc1w, *fc1b, *fc2w, *fc2b; int in, E, out, Q, hs; } ir84;
+typedef struct { lin_bn first; ir84 blk[3]; const float *pi2w, *pi2b, *pi4w, *pi4b, *v2w, *v2b, *v4w, *v4b; } v84_net;
+static void v84_bind(v84_net* N, const float* blob) {
+    static const int E_[3] = {115, 115, 46}, OUT_[3] = {23, 46, 23}, Q_[3] = {32, 32, 16}, HS_[3] = {0, 1, 1};   /* Q = _make_divisible(E // 4, 8) */
+    const float* p = blob;
+    N->first = take_lin_bn(&p, V84_NV, V84_NV, V84_NV);
+    for (int k = 0; k < 3; k++) {
+        ir84* B = &N->blk[k]; B->in = V84_NV; B->E = E_[k]; B->out = OUT_[k]; B->Q = Q_[k]; B->hs = HS_[k];
+        B->expand = take_lin_bn(&p, B->E, B->in, B->E);
+        B->dw = take_lin_bn(&p, V84_F, V84_F, B->E);
+        B->fc1w = take(&p, (size_t)B->Q * B->E); B->fc1b = take(&p, B->Q); B->fc2w = take(&p, (size_t)B->E * B->Q); B->fc2b = take(&p, B->E);
+        B->project = take_lin_bn(&p, B->out, B->E, B->out);
+    }
+    N->pi2w = take(&p, (size_t)AZU_A * 46 * V84_F); N->pi2b = take(&p, AZU_A); N->pi4w = take(&p, (size_t)AZU_A * AZU_A); N->pi4b = take(&p, AZU_A);
+    N->v2w = take(&p, 2 * V84_NV * V84_F); N->v2b = take(&p, 2); N->v4w = take(&p, 4); N->v4b = take(&p, 2);
+}
+static void token_linear6(const lin_bn* l, int out, int in, const float* x, float* y, int activation /*0 none,1 relu,2 hs*/) {
+    for (int o = 0; o < out; o++)
+        for (int f = 0; f < V84_F; f++) {
+            float s = 0; for (int i = 0; i < in; i++) s += l->w[o * in + i] * x[i * V84_F + f];
+            s = bn_apply(l, o, s);
+            y[o * V84_F + f] = activation == 0 ? s : act(s, activation == 2);
+        }
+}
+static void ir84_block(const ir84* B, const float* x, float* y) {
+    const int E = B->E, Q = B->Q;
+    float e[115 * V84_F], d[115 * V84_F], sq[115], hid[32], sc[115];
+    token_linear6(&B->expand, E, B->in, x, e, B->hs ? 2 : 1);
+    for (int c = 0; c < E; c++)                                  /* "depthwise": shared Linear(6->6) on the feature axis, BN per channel */
+        for (int g = 0; g < V84_F; g++) {
+            float s = 0; for (int f = 0; f < V84_F; f++) s += B->dw.w[g * V84_F + f] * e[c * V84_F + f];
+            d[c * V84_F + g] = act(bn_apply(&B->dw, c, s), B->hs);
+        }
+    for (int c = 0; c < E; c++) { float s = 0.f; for (int f = 0; f < V84_F; f++) s += d[c * V84_F + f]; sq[c] = s / (float)V84_F; }   /* AdaptiveAvgPool1d(1) */
+    for (int q = 0; q < Q; q++) { float s = B->fc1b[q]; for (int c = 0; c < E; c++) s += B->fc1w[q * E + c] * sq[c]; hid[q] = s > 0 ? s : 0; }
+    for (int c = 0; c < E; c++) { float s = B->fc2b[c]; for (int q = 0; q < Q; q++) s += B->fc2w[c * Q + q] * hid[q]; sc[c] = relu6f(s + 3.f) / 6.f; }
+    for (int c = 0; c < E; c++) for (int f = 0; f < V84_F; f++) d[c * V84_F + f] *= sc[c];
+    token_linear6(&B->project, B->out, E, d, y, 0);
+    if (B->in == B->out) for (int i = 0; i < B->out * V84_F; i++) y[i] += x[i];           /* use_res_connect */
+}
+static void v84_forward(const v84_net* N, const i8* board, const u8* valids, float* pi, float* v) {
+    float x[V84_NV * V84_F], x0[V84_NV * V84_F], t[V84_NV * V84_F], hp[46 * V84_F], hv[V84_NV * V84_F], h1[AZU_A], logit[AZU_A], hv1[2];
+    for (int i = 0; i < V84_NV * V84_F; i++) x[i] = (float)board[i];
+    token_linear6(&N->first, V84_NV, V84_NV, x, x0, 0);
+    ir84_block(&N->blk[0], x0, t);
+    ir84_block(&N->blk[1], t, hp);
+    ir84_block(&N->blk[2], t, hv);
+    const int FP = 46 * V84_F, FV = V84_NV * V84_F;
+    for (int o = 0; o < AZU_A; o++) { float s = N->pi2b[o]; for (int i = 0; i < FP; i++) s += N->pi2w[o * FP + i] * hp[i]; h1[o] = s > 0 ? s : 0; }
+    float mx = -INFINITY;
+    for (int o = 0; o < AZU_A; o++) {
+        float s = N->pi4b[o]; for (int i = 0; i < AZU_A; i++) s += N->pi4w[o * AZU_A + i] * h1[i];
+        logit[o] = valids[o] ? s : -1e8f; if (logit[o] > mx) mx = logit[o];
+    }
+    float se = 0; for (int o = 0; o < AZU_A; o++) se += expf(logit[o] - mx);
+    const float lse = logf(se);
+    for (int o = 0; o < AZU_A; o++) pi[o] = expf(logit[o] - mx - lse);   /* exp(log_softmax), GenericNNetWrapper.py:119 */
+    for (int p = 0; p < 2; p++) { float s = N->v2b[p]; for (int i = 0; i < FV; i++) s += N->v2w[p * FV + i] * hv[i]; hv1[p] = s > 0 ? s : 0; }
+    for (int p = 0; p < 2; p++) { float s = N->v4b[p]; for (int q = 0; q < 2; q++) s += N->v4w[p * 2 + q] * hv1[q]; v[p] = tanhf(s); }
+}
+void azo_v84_forward(const float* blob, int batch, const i8* boards, const u8* valids, float* pi, float* v) {
+    v84_net N; v84_bind(&N, blob);
+    for (int b = 0; b < batch; b++) v84_forward(&N, boards + (size_t)b * AZU_S, valids + (size_t)b * AZU_A, pi + (size_t)b * AZU_A, v + (size_t)b * 2);
+}
+
 /* ---------------------------------------------------------------- SantoriniNNet V89 ------ */
 /* santorini/SantoriniNNet.py:70-84 (SimpleResBlock), :16-40 (SimpleHead), :194-217 (layers), :273-279 (forward), eval mode.
  * blob = state_dict tensors in the order of oracle.py:v89_order() (conv weight, then BN weight/bias/mean/var; heads). */

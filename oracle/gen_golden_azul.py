@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Golden step vectors for Azul (2 players) by RUNNING THE UNMODIFIED REFERENCE (test infrastructure; round-2 groundwork).
 
-    python oracle/gen_golden_azul.py [--out tests/golden] [--only kat,mcts,episode]
+    python oracle/gen_golden_azul.py [--out tests/golden] [--only kat,mcts,episode,net]
 
 Imports azul/AzulGame.py (-> AzulLogicNumba.Board jitclass) from /root/reference. Random games are played with
 `random_seed != 0`, so every tile draw is the reference's deterministic one and the recorded next states are exact.
@@ -138,10 +138,51 @@ def gen_episode(out):
     print(f'azul episode: {len(roots)} plies, rounds seen {sorted(set(int(r[0, 2]) for r in roots))}, last summary={summaries[-1]}')
 
 
+def gen_net(out):
+    """AzulNNet V84 forward (azul/AzulNNet.py:84-137) through the reference's torch branch of GenericNNetWrapper.predict
+    (GenericNNetWrapper.py:111-120): random-init with perturbed BatchNorm statistics / biases, and the shipped azul/pretrained.pt."""
+    import torch
+    torch.set_num_threads(1)
+    from azul.AzulGame import AzulGame
+    from azul.NNet import NNetWrapper
+    kat = np.load(os.path.join(out, 'azul_kat.npz'))
+    g = AzulGame()
+    nn_args = dict(nn_version=84, dropout=0., lr=3e-4, learn_rate=3e-4, epochs=2, batch_size=32, no_compression=True, q_weight=0.5)
+    sel = np.linspace(0, len(kat['canonical']) - 1, 64).astype(int)
+    boards = kat['canonical'][sel]; valids = kat['valids'][sel]
+    for tag in ('rand', 'shipped'):
+        torch.manual_seed(0)
+        w = NNetWrapper(g, nn_args)
+        w.device['inference'] = 'cpu'
+        if tag == 'rand':
+            gen = torch.Generator().manual_seed(4)
+            with torch.no_grad():
+                for mod in w.nnet.modules():
+                    if isinstance(mod, torch.nn.BatchNorm1d):
+                        mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=gen) * 0.3)
+                        mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=gen) * 1.5 + 0.25)
+                        mod.weight.data.copy_(torch.rand(mod.weight.shape, generator=gen) + 0.5)
+                        mod.bias.data.copy_(torch.randn(mod.bias.shape, generator=gen) * 0.2)
+        else:
+            ck = torch.load('/root/reference/azul/pretrained.pt', map_location='cpu', weights_only=False)
+            print('azul pretrained args:', {k: ck['args'][k] for k in ck.get('args', {}) if k in ('nn_version', 'cpuct', 'fpu', 'universes', 'numMCTSSims')} if isinstance(ck.get('args'), dict) else type(ck.get('args')))
+            w.nnet.load_state_dict(ck['state_dict'])
+        w.nnet.eval()
+        pis, vs = [], []
+        for b, v in zip(boards, valids):
+            pi, val = w.predict(b, v)
+            pis.append(pi); vs.append(val)
+        sd = {k: t.detach().cpu().numpy() for k, t in w.nnet.state_dict().items()}
+        save = {'sd__' + k: v for k, v in sd.items()}
+        save.update(boards=boards, valids=valids, pi=np.array(pis, dtype=np.float32), v=np.array(vs, dtype=np.float32))
+        np.savez_compressed(os.path.join(out, f'azul_v84_{tag}.npz'), **save)
+        print(f'azul net {tag}: {len(sd)} tensors, {sum(v.size for v in sd.values())} values, pi[0] max={pis[0].max():.4f} v[0]={vs[0]}')
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(os.path.dirname(HERE), 'tests', 'golden'))
-    ap.add_argument('--only', default='kat,mcts,episode')
+    ap.add_argument('--only', default='kat,mcts,episode,net')
     a = ap.parse_args()
     only = a.only.split(',')
     if 'kat' in only:
@@ -150,3 +191,5 @@ if __name__ == '__main__':
         gen_mcts(a.out)
     if 'episode' in only:
         gen_episode(a.out)
+    if 'net' in only:
+        gen_net(a.out)

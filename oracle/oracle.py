@@ -89,6 +89,7 @@ def lib():
         L.azo_azul_swap_players.argtypes = [p8]
         L.azo_azul_init_game.argtypes = [p8, C.c_uint64]
         L.azo_azul_symmetries.argtypes = [p8, pf, pu8, p8, pf, pu8]; L.azo_azul_symmetries.restype = C.c_int
+        L.azo_v84_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
         L.azo_v80_forward.argtypes = [pf, C.c_int, C.c_int, p8, pu8, pf, pf]
         L.azo_v89_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
         L.azo_v21_forward.argtypes = [pf, C.c_int, p8, pu8, pf, pf]
@@ -389,6 +390,24 @@ def azul_symmetries(board, pi, valids):
     ob = np.zeros((120, 23, 6), np.int8); op = np.zeros((120, AZUL_A), np.float32); ov = np.zeros((120, AZUL_A), np.uint8)
     k = lib().azo_azul_symmetries(_p(b, C.c_int8), _p(pi, C.c_float), _p(v, C.c_uint8), _p(ob, C.c_int8), _p(op, C.c_float), _p(ov, C.c_uint8))
     return [(ob[i], op[i], ov[i].astype(np.bool_)) for i in range(k)]
+
+
+def v84_blob(state_dict):
+    """AzulNNet V84 (azul/AzulNNet.py:84-111) uses SplendorNNet V80's module names: same tensor order, different shapes."""
+    sizes = {'first_layer.linear.weight': (23, 23), 'trunk.0.expand.linear.weight': (115, 23), 'trunk.0.se.fc1.weight': (32, 115),
+             'output_layers_PI.0.project.linear.weight': (46, 115), 'output_layers_V.0.se.fc1.weight': (16, 46),
+             'output_layers_PI.2.weight': (180, 276), 'output_layers_V.2.weight': (2, 138)}
+    for k, shp in sizes.items():
+        assert tuple(np.asarray(state_dict[k]).shape) == shp, (k, np.asarray(state_dict[k]).shape)
+    return v80_blob(state_dict)
+
+
+def v84_forward(blob, boards, valids):
+    boards = np.ascontiguousarray(boards, np.int8); B = boards.shape[0]
+    v = np.ascontiguousarray(valids).astype(np.uint8); blob = np.ascontiguousarray(blob, np.float32)
+    pi = np.zeros((B, AZUL_A), np.float32); val = np.zeros((B, 2), np.float32)
+    lib().azo_v84_forward(_p(blob, C.c_float), B, _p(boards, C.c_int8), _p(v, C.c_uint8), _p(pi, C.c_float), _p(val, C.c_float))
+    return pi, val
 
 
 def v21_order():

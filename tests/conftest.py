@@ -148,3 +148,13 @@ def v21_golden():
         sd = {k[4:]: z[k] for k in z.files if k.startswith('sd__')}
         out[tag] = dict(sd=sd, boards=z['boards'], valids=_unpack(z['valids']), pi=z['pi'], v=z['v'])
     return out
+
+
+@pytest.fixture(scope='session')
+def v84_golden():
+    out = {}
+    for tag in ('rand', 'shipped'):
+        z = np.load(os.path.join(GOLDEN, f'azul_v84_{tag}.npz'))
+        sd = {k[4:]: z[k] for k in z.files if k.startswith('sd__')}
+        out[tag] = dict(sd=sd, boards=z['boards'], valids=z['valids'], pi=z['pi'], v=z['v'])
+    return out

@@ -77,3 +77,17 @@ def test_episode_tree_reuse_exact(azul_episode):
         assert (raw == ep['raw_counts'][i]).all(), f'ply {i}'
         assert (q == ep['q'][i]).all(), f'ply {i}'
         assert list(m.stats()[:3]) == list(ep['summaries'][i]), f'ply {i}'
+
+
+import pytest
+
+
+@pytest.mark.parametrize('tag', ['rand', 'shipped'])
+def test_v84_forward_vs_reference_torch(v84_golden, tag):
+    """AzulNNet V84 restatement vs the reference's torch CPU fp32 outputs (random-init with perturbed BN, and azul/pretrained.pt);
+    tolerance 1e-5 absolute on pi and v, the same bar as the three built nets."""
+    g = v84_golden[tag]
+    pi, v = O.v84_forward(O.v84_blob(g['sd']), g['boards'], g['valids'])
+    np.testing.assert_allclose(pi, g['pi'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(v, g['v'], rtol=0, atol=1e-5)
+    assert (pi[~g['valids']] == 0).all() and np.abs(pi.sum(1) - 1).max() < 1e-5
