@@ -91,3 +91,83 @@ def test_v84_forward_vs_reference_torch(v84_golden, tag):
     np.testing.assert_allclose(pi, g['pi'], rtol=0, atol=1e-5)
     np.testing.assert_allclose(v, g['v'], rtol=0, atol=1e-5)
     assert (pi[~g['valids']] == 0).all() and np.abs(pi.sum(1) - 1).max() < 1e-5
+
+
+# ---- round-2 draft of the device plugin (csrc/next/azul.cuh), run on the HOST: tests/host/azul_plugin_emul.cpp defines the CUDA
+# ---- qualifiers away and runs the lanes of a warp function one after the other. Not the product path, not a GPU result.
+@pytest.fixture(scope='module')
+def azul_emul(tmp_path_factory):
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which('g++')
+    if gxx is None:
+        pytest.skip('g++ not available')
+    so = str(tmp_path_factory.mktemp('azul_emul') / 'libazul_emul.so')
+    subprocess.run([gxx, '-std=c++17', '-O1', '-fPIC', '-shared', '-Wno-unknown-pragmas', '-o', so, os.path.join(root, 'tests', 'host', 'azul_plugin_emul.cpp')],
+                   check=True, timeout=300)
+    L = C.CDLL(so)
+    L.emul_make_move.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong]
+    L.emul_valid.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.emul_ended.argtypes = [C.c_void_p, C.c_void_p]
+    L.emul_swap.argtypes = [C.c_void_p, C.c_int]
+    L.emul_round.argtypes = [C.c_void_p]; L.emul_score.argtypes = [C.c_void_p, C.c_int]
+    L.emul_symmetries.argtypes = [C.c_void_p] * 6
+    L.emul_init.argtypes = [C.c_void_p, C.c_uint64]
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data
+
+
+def test_draft_device_plugin_rules_on_host(azul_kat, azul_emul):
+    L, k = azul_emul, azul_kat
+    sizes = np.zeros(5, np.int32); L.emul_sizes(_ptr(sizes))
+    assert sizes.tolist() == [138, 144, 180, 120, 2]
+    for i in range(len(k['action'])):
+        board = np.ascontiguousarray(k['board'][i], np.int8); player = int(k['player'][i])
+        v = np.zeros(180, np.uint8); L.emul_valid(_ptr(board), player, _ptr(v))
+        assert (v.astype(bool) == k['valids'][i]).all(), i
+        cb = board.copy(); L.emul_swap(_ptr(cb), player)
+        assert (cb == k['canonical'][i]).all(), i
+        v0 = np.zeros(180, np.uint8); L.emul_valid(_ptr(cb), 0, _ptr(v0))
+        assert (v0 == v).all(), i
+        nb = board.copy(); npl = L.emul_make_move(_ptr(nb), int(k['action'][i]), player, int(k['seed'][i]))
+        assert npl == k['next_player'][i] and (nb == k['next_board'][i]).all(), f'ply {i} action {k["action"][i]}'
+        es = np.zeros(2, np.float32); over = L.emul_ended(_ptr(nb), _ptr(es))
+        assert (es == k['ended'][i]).all() and bool(over) == bool(np.abs(k['ended'][i]).sum() > 0)
+        assert L.emul_round(_ptr(nb)) == k['round'][i] and [L.emul_score(_ptr(nb), 0), L.emul_score(_ptr(nb), 1)] == list(k['score'][i])
+        ncb = nb.copy(); L.emul_swap(_ptr(ncb), int(npl))
+        assert (ncb == k['next_canonical'][i]).all(), i
+
+
+def test_draft_device_plugin_symmetries_on_host(azul_kat, azul_emul):
+    L, k = azul_emul, azul_kat
+    for i in range(len(k['sym_pi'])):
+        b = np.ascontiguousarray(k['sym_board'][i], np.int8); pi = np.ascontiguousarray(k['sym_pi'][i], np.float32)
+        m = np.ascontiguousarray(k['sym_valids'][i]).astype(np.uint8)
+        ob = np.zeros((120, 23, 6), np.int8); op = np.zeros((120, 180), np.float32); om = np.zeros((120, 180), np.uint8)
+        assert L.emul_symmetries(_ptr(b), _ptr(pi), _ptr(m), _ptr(ob), _ptr(op), _ptr(om)) == 120
+        assert (ob == k['sym_out_boards'][i]).all() and (op == k['sym_out_pi'][i]).all() and (om.astype(bool) == k['sym_out_valids'][i]).all(), i
+    for seed in range(8):
+        b = np.zeros((23, 6), np.int8); L.emul_init(_ptr(b), seed)
+        assert b[1, :5].sum() == 80 and (b[4:9, :5].sum(1) == 4).all() and b[3, 5] == 1 and b[0, 2] == 1 and (b[9:11, :5] == -1).all()
+
+
+def test_draft_device_plugin_compiles_for_sm100a(tmp_path):
+    """nvcc generates sm_100a code for every member of the draft plugin (compile-only program, nothing is launched)."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    exe = str(tmp_path / 'azul_plugin_check')
+    subprocess.run([nvcc, '-std=c++17', '-O2', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', exe, os.path.join(root, 'tests', 'host', 'azul_plugin_check.cu')],
+                   check=True, timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and 'S=138 SP=144 A=180 MASK_WORDS=6 MAX_SYM=120' in out.stdout
