@@ -21,10 +21,27 @@ class Coach:
         self.trainExamplesHistory = []
 
     def raw_examples(self, min_episodes, max_moves=0):
-        """Plays until `min_episodes` games finished; returns un-augmented example arrays (one per full-search ply)."""
-        self.engine.selfplay(min_episodes=min_episodes, max_moves=max_moves)
+        """Plays until `min_episodes` games finished; returns un-augmented example arrays (one per full-search ply).
+        azg_engine_selfplay returns early whenever the device example ring is more than half full; the ring is drained here between
+        calls, so no example is lost however many episodes are asked for (the ring holds n_games * max_game_len examples)."""
         cap = self.n_games * self.game.info.max_game_len
-        return self.engine.examples(cap)
+        done0 = self.engine.stats()['episodes_finished']
+        parts = []; moves = 0
+        while True:
+            left = min_episodes - (self.engine.stats()['episodes_finished'] - done0)
+            if min_episodes > 0 and left <= 0:
+                break
+            m0 = self.engine.stats()['moves_played']
+            self.engine.selfplay(min_episodes=max(left, 0), max_moves=max(max_moves - moves, 0) if max_moves else 0)
+            parts.append(self.engine.examples(cap))
+            moves += (self.engine.stats()['moves_played'] - m0 + self.n_games - 1) // self.n_games
+            if min_episodes <= 0 or (max_moves and moves >= max_moves):
+                break
+        st = self.engine.stats()
+        if st['examples_dropped'] or st['arena_overflows']:
+            raise RuntimeError(f"self-play lost data: examples_dropped={st['examples_dropped']} (example ring full), "
+                               f"arena_overflows={st['arena_overflows']} (tree arena full: raise node_cap / edge_cap)")
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(5)) if parts else self.engine.examples(cap)
 
     def augment(self, boards, pis, zs, valids, qs):
         """getSymmetries for every example (Coach.py:67-69) through the batched symmetry kernel."""

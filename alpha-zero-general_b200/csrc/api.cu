@@ -488,6 +488,10 @@ struct azg_engine {                      // game-independent face of the engine 
     virtual int search(int n, const int8_t* roots, const uint8_t* full_search, const double* noise, int32_t* out_counts, int32_t* out_raw,
                        float* out_q, cudaStream_t st) = 0;
     virtual int selfplay(int min_episodes, int max_moves, cudaStream_t st) = 0;
+    virtual int selfplay_inject(const azg_selfplay_inject* inj) = 0;
+    virtual int selfplay_state(int8_t* boards, int32_t* players, int32_t* plies, int32_t* active) = 0;
+    virtual int node(int n, const int32_t* slots, const int8_t* boards, int32_t* found, float* es, uint8_t* vs, float* ps, int32_t* ns, double* qsa,
+                     int32_t* nsa, int32_t* round, float* qs, cudaStream_t st) = 0;
     virtual int examples(int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) = 0;
     virtual int stats(int64_t* out16) = 0;
     virtual int profile(int enable) = 0;
@@ -537,7 +541,7 @@ struct EngineT : azg_engine {
         d.n_games = NG; d.node_cap = node_cap; d.edge_cap = edge_cap; d.ht_cap = next_pow2(2 * node_cap);
         d.universes = c->universes; d.U = U0; d.forced_playouts = c->forced_playouts; d.dirichlet_noise = c->dirichlet_noise;
         d.cpuct = c->cpuct; d.fpu = c->fpu; d.dir_alpha = c->dirichletAlpha; d.temp2 = c->temperature[2]; d.seed = c->seed;
-        d.noise = nullptr;
+        d.noise = nullptr; d.noise_gstride = G::A; d.noise_ply = nullptr; d.game_base = c->first_game;
         { const char* rv = getenv("AZG_TREE_REPLAY"); d.replay = (rv && rv[0] == '0') ? 0 : 1; }
         sims_full = c->numMCTSSims; sims_fast = c->ratio_fullMCTS > 0 ? c->numMCTSSims / c->ratio_fullMCTS : c->numMCTSSims;
         int bad = 0;
@@ -640,6 +644,29 @@ struct EngineT : azg_engine {
         FINISH(6);
     }
 
+    int node(int n, const int32_t* slots, const int8_t* boards, int32_t* found, float* es, uint8_t* vs, float* ps, int32_t* ns, double* qsa,
+             int32_t* nsa, int32_t* round, float* qs, cudaStream_t st) override {
+        if (n <= 0) return 0;
+        if (!boards || !found) return fail("boards / found is NULL");
+        Arg* a = tl_arg; const size_t N = (size_t)n;
+        if (a[0].in(slots, sizeof(int) * N, st) || a[1].in(boards, N * G::S, st) || a[2].outbuf(found, sizeof(int) * N) || a[3].outbuf(es, sizeof(float) * N * G::NP) ||
+            a[4].outbuf(vs, N * G::A) || a[5].outbuf(ps, sizeof(float) * N * G::A) || a[6].outbuf(ns, sizeof(int) * N) || a[7].outbuf(qsa, sizeof(double) * N * G::A) ||
+            a[8].outbuf(nsa, sizeof(int) * N * G::A) || a[9].outbuf(round, sizeof(int) * N) || a[10].outbuf(qs, sizeof(float) * N)) return 1;
+        k_node_query<G><<<(n + sel_warps<G>() - 1) / sel_warps<G>(), sel_warps<G>() * 32, 0, st>>>(d, n, a[0].as<int>(), a[1].as<int8_t>(), a[2].as<int>(), a[3].as<float>(),
+            a[4].as<uint8_t>(), a[5].as<float>(), a[6].as<int>(), a[7].as<double>(), a[8].as<int>(), a[9].as<int>(), a[10].as<float>());
+        launches++;
+        FINISH(11);
+    }
+    int selfplay_state(int8_t* boards, int32_t* players, int32_t* plies, int32_t* active) override {
+        if (selfplay_setup()) return 1;
+        const int NG = d.n_games;
+        CK(cudaDeviceSynchronize());
+        if (boards) CK(cudaMemcpy2D(boards, G::S, sp.board, G::SP, G::S, NG, cudaMemcpyDefault));
+        if (players) CK(cudaMemcpy(players, sp.player, sizeof(int) * NG, cudaMemcpyDefault));
+        if (plies) CK(cudaMemcpy(plies, sp.ply, sizeof(int) * NG, cudaMemcpyDefault));
+        if (active) CK(cudaMemcpy(active, sp.active, sizeof(int) * NG, cudaMemcpyDefault));
+        return 0;
+    }
     int stats(int64_t* out16) override {
         const int NG = d.n_games;
         std::vector<unsigned long long> h((size_t)NG * ST_N);
@@ -653,6 +680,7 @@ struct EngineT : azg_engine {
             }
         out16[12] = (int64_t)(launches + (net ? net->launches : 0));
         out16[14] = d.node_cap;
+        if (sp_ready) { unsigned long long c[8]; CK(cudaMemcpy(c, sp.counters, sizeof(c), cudaMemcpyDeviceToHost)); out16[18] = (int64_t)c[2]; }
         return 0;
     }
 
@@ -673,8 +701,34 @@ struct EngineT : azg_engine {
         if (bad) return 1;
         sp_ready = true; return 0;
     }
+    // ---- injected randomness (parity tests): see azg_selfplay_inject in azg.h ----
+    Scratch inj_buf[5];
+    int selfplay_inject(const azg_selfplay_inject* inj) override {
+        if (selfplay_setup()) return 1;
+        const int NG = d.n_games;
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemset(sp.active, 0, sizeof(int) * NG)); CK(cudaMemset(sp.games_started, 0, sizeof(unsigned) * NG)); CK(cudaMemset(sp.ply, 0, sizeof(int) * NG));
+        CK(cudaMemset(sp.st_count, 0, sizeof(int) * NG)); CK(cudaMemset(sp.player, 0, sizeof(int) * NG));
+        sp.inj_P = 0; sp.inj_init = nullptr; sp.inj_u_full = sp.inj_u_move = nullptr; sp.inj_seed = nullptr; sp_noise = nullptr;
+        if (!inj) return 0;
+        if (inj->n_plies <= 0 || !inj->init_boards || !inj->u_full || !inj->u_move || !inj->chance_seed) return fail("azg_selfplay_inject: n_plies must be positive and init_boards / u_full / u_move / chance_seed non-NULL");
+        const size_t P = (size_t)inj->n_plies;
+        const void* src[5] = {inj->init_boards, inj->u_full, inj->u_move, inj->chance_seed, inj->noise};
+        const size_t bytes[5] = {(size_t)NG * G::S, sizeof(double) * NG * P, sizeof(double) * NG * P, sizeof(long long) * NG * P, sizeof(double) * NG * P * G::A};
+        for (int i = 0; i < 5; i++) {
+            if (!src[i]) continue;
+            if (inj_buf[i].ensure(bytes[i])) return 1;
+            CK(cudaMemcpy(inj_buf[i].p, src[i], bytes[i], cudaMemcpyDefault));
+        }
+        sp.inj_P = (int)P; sp.inj_init = (const int8_t*)inj_buf[0].p; sp.inj_u_full = (const double*)inj_buf[1].p; sp.inj_u_move = (const double*)inj_buf[2].p;
+        sp.inj_seed = (const long long*)inj_buf[3].p; sp_noise = inj->noise ? (const double*)inj_buf[4].p : nullptr;
+        return 0;
+    }
+    const double* sp_noise = nullptr;          // injected per-(slot, ply) Dirichlet draws of self-play
     int selfplay(int min_episodes, int max_moves, cudaStream_t st) override {
         if (selfplay_setup()) return 1;
+        d.noise = sp_noise; d.noise_gstride = sp_noise ? (size_t)sp.inj_P * G::A : (size_t)G::A; d.noise_ply = sp_noise ? sp.ply : nullptr;
+        struct Restore { Dev<G>& d; ~Restore() { d.noise = nullptr; d.noise_gstride = G::A; d.noise_ply = nullptr; } } restore{d};
         unsigned long long start[8], now[8];
         CK(cudaMemcpyAsync(start, sp.counters, sizeof(start), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
         for (int mv = 0; max_moves <= 0 || mv < max_moves; mv++) {
@@ -692,8 +746,11 @@ struct EngineT : azg_engine {
             CKL();
             if (profiling && prof_drain()) return 1;
             if (min_episodes > 0) {
-                CK(cudaMemcpyAsync(now, sp.counters, sizeof(now), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+                int ring = 0;
+                CK(cudaMemcpyAsync(now, sp.counters, sizeof(now), cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(&ring, sp.ex_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
                 if ((long long)(now[0] - start[0]) >= min_episodes) break;
+                if (ring > sp.ex_cap / 2) break;                  // the caller drains the ring (azg_engine_examples) and calls again
             }
             if (max_moves <= 0 && min_episodes <= 0) break;
         }
@@ -757,6 +814,19 @@ extern "C" int azg_engine_stats(azg_engine* e, int64_t* out16) { if (!e || !out1
 extern "C" int azg_engine_selfplay(azg_engine* e, int min_episodes, int max_moves, void* stream) {
     if (!e) return fail("engine is NULL");
     return e->selfplay(min_episodes, max_moves, (cudaStream_t)stream);
+}
+extern "C" int azg_engine_node(azg_engine* e, int n, const int32_t* slots, const int8_t* boards, int32_t* found, float* es, uint8_t* vs, float* ps,
+                               int32_t* ns, double* qsa, int32_t* nsa, int32_t* round, float* qs, void* stream) {
+    if (!e) return fail("engine is NULL");
+    return e->node(n, slots, boards, found, es, vs, ps, ns, qsa, nsa, round, qs, (cudaStream_t)stream);
+}
+extern "C" int azg_engine_selfplay_state(azg_engine* e, int8_t* boards, int32_t* players, int32_t* plies, int32_t* active) {
+    if (!e) return fail("engine is NULL");
+    return e->selfplay_state(boards, players, plies, active);
+}
+extern "C" int azg_engine_selfplay_inject(azg_engine* e, const azg_selfplay_inject* inj) {
+    if (!e) return fail("engine is NULL");
+    return e->selfplay_inject(inj);
 }
 extern "C" int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) {
     if (!e || !out_n) return fail("NULL argument");

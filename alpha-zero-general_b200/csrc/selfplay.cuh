@@ -31,6 +31,13 @@ struct SelfPlay {
     // schedule
     double prob_full = 1.0, t_begin = 1.0, t_end = 0.1, half_life = 10.0;
     int max_ply = 0;
+    // injected randomness (azg_engine_selfplay_inject; parity tests replay an episode recorded from the reference): per slot and ply
+    // p = episodeStep - 1 < inj_P. With injection every slot plays exactly ONE game from inj_init and then idles.
+    const int8_t* inj_init = nullptr;       // [n][S] initial boards
+    const double* inj_u_full = nullptr;     // [n][P] playout-cap coin (MCTS.py:58)
+    const double* inj_u_move = nullptr;     // [n][P] uniform of random_pick's np.random.choice (Coach.py:289-292)
+    const long long* inj_seed = nullptr;    // [n][P] random_seed of the real move (non-zero: deterministic chance draw)
+    int inj_P = 0;
 };
 
 // visit-count policy at the root of slot g (shared by k_finish-style read-out and self-play)
@@ -74,8 +81,12 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_begin(Dev<G> d, Self
     if (g >= d.n_games) return;
     int8_t* sb = sm[w].board;
     int8_t* board = sp.board + (size_t)g * G::SP;
+    const uint64_t gid = d.game_base + (uint64_t)g;                // global slot id: keys every RNG stream
     if (!sp.active[g]) {                                          // new game in this slot: fresh board, fresh tree
-        if (lane == 0) { Philox rng(d.seed, ((uint64_t)g << 8) | 2u, (uint64_t)sp.games_started[g]); G::init_game(sb, &rng); }
+        if (sp.inj_P) {                                           // injected episode: one game per slot, then the slot idles
+            if (sp.games_started[g] != 0) { if (lane == 0) { d.n_sims[g] = 0; d.full[g] = 0; } return; }
+            for (int i = lane; i < G::SP; i += 32) sb[i] = i < G::S ? sp.inj_init[(size_t)g * G::S + i] : (int8_t)0;
+        } else if (lane == 0) { Philox rng(d.seed, (gid << 8) | 2u, (uint64_t)sp.games_started[g]); G::init_game(sb, &rng); }
         __syncwarp();
         for (int i = lane; i < G::SP; i += 32) board[i] = sb[i];
         uint64_t* ht = d.g_ht(g);
@@ -91,9 +102,11 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_begin(Dev<G> d, Self
     for (int i = lane; i < G::SP; i += 32) d.root[(size_t)g * G::SP + i] = sb[i];
     if (lane == 0) {
         const int ply = sp.ply[g] + 1; sp.ply[g] = ply;
-        Philox rng(d.seed, ((uint64_t)g << 8) | 3u, ((uint64_t)sp.games_started[g] << 16) | (unsigned)ply);
-        const bool full = rng.uniform() < sp.prob_full;           // MCTS.py:58
+        Philox rng(d.seed, (gid << 8) | 3u, ((uint64_t)sp.games_started[g] << 16) | (unsigned)ply);
+        const double coin = sp.inj_P ? sp.inj_u_full[(size_t)g * sp.inj_P + min(ply, sp.inj_P) - 1] : rng.uniform();
+        const bool full = coin < sp.prob_full;                    // MCTS.py:58
         d.full[g] = full; d.n_sims[g] = full ? sims_full : sims_fast; d.root_node[g] = 0;
+        d.move_ctr[g] = (sp.games_started[g] << 8) | (unsigned)ply;   // a fresh Dirichlet draw for every search (MCTS.py:187-197): counter of root_noise's stream
     }
 }
 
@@ -102,7 +115,9 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPl
     __shared__ WarpSmem<G> sm[sel_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
     if (g >= d.n_games) return;
+    if (!sp.active[g]) return;                                    // idle slot (injected episodes: its one game is over)
     constexpr int A = G::A, NP = G::NP, MW = G::MASK_WORDS;
+    const uint64_t gid = d.game_base + (uint64_t)g;
     int8_t* sb = sm[w].board;
     for (int i = lane; i < G::SP; i += 32) sb[i] = d.root[(size_t)g * G::SP + i];
     __syncwarp();
@@ -114,7 +129,8 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPl
     for (int a = lane; a < A; a += 32) total += cnt[a];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
-    Philox rng(d.seed, ((uint64_t)g << 8) | 4u, ((uint64_t)sp.games_started[g] << 16) | (unsigned)ply);
+    Philox rng(d.seed, (gid << 8) | 4u, ((uint64_t)sp.games_started[g] << 16) | (unsigned)ply);
+    const size_t inj_i = sp.inj_P ? (size_t)g * sp.inj_P + min(ply, sp.inj_P) - 1 : 0;
     int action = -1;
     if (found && total > 0) {
         const bool full = d.full[g] != 0;
@@ -141,11 +157,12 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPl
             for (int a = lane; a < A; a += 32) pw[a] = cnt[a] > 0 ? pow((double)cnt[a] / (double)total, 1.0 / T) : 0.0;
         }
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0) {                                          // np.random.choice(p) (Coach.py:289-292): cdf = cumsum(p / sum p) / cdf[-1], searchsorted right
             double s = 0; for (int a = 0; a < A; a++) s += pw[a];
-            const double u = rng.uniform() * s; double acc = 0; int last = -1;
-            for (int a = 0; a < A; a++) if (pw[a] > 0) { acc += pw[a]; last = a; if (acc > u) break; }
-            action = last;
+            double acc = 0; for (int a = 0; a < A; a++) { acc += pw[a] / s; pw[a] = acc; }
+            const double u = sp.inj_P ? sp.inj_u_move[inj_i] : rng.uniform(), last = pw[A - 1];
+            int pick = 0; for (int a = 0; a < A; a++) if (pw[a] / last <= u) pick = a + 1;
+            action = min(pick, A - 1);
         }
     } else if (lane == 0) {                                       // arena overflow kept the root out of the tree: uniform legal move
         int nlegal = 0; for (int a = 0; a < A; a++) nlegal += G::action_valid(sb, a, 0);
@@ -159,7 +176,7 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPl
     for (int i = lane; i < G::SP; i += 32) sb[i] = board[i];
     __syncwarp();
     int np = 0;
-    if (lane == 0) np = G::make_move(sb, action, player, 0, &rng);
+    if (lane == 0) np = G::make_move(sb, action, player, sp.inj_P ? sp.inj_seed[inj_i] : 0, &rng);
     __syncwarp();
     np = __shfl_sync(FULL, np, 0);
     for (int i = lane; i < G::SP; i += 32) board[i] = sb[i];

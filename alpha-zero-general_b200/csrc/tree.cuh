@@ -76,7 +76,11 @@ struct Dev {
     int8_t* root;              // [G][SP] canonical root boards
     int* n_sims;               // sims requested for the current search
     uint8_t* full;             // full-search flag (MCTS.py:58)
-    const double* noise;       // injected Dirichlet draws [G][A] or nullptr
+    const double* noise;       // injected Dirichlet draws or nullptr: game g reads noise[g * noise_gstride + (noise_ply ? (noise_ply[g] - 1) * A : 0) + k]
+    size_t noise_gstride;      // elements per game (A for azg_engine_search; P * A for injected self-play)
+    const int* noise_ply;      // self-play: current ply of every slot (1-based), selects the ply's row; nullptr for azg_engine_search
+    uint64_t game_base;        // global id of slot 0 (azg_engine_cfg.first_game): every RNG stream is keyed by game_base + g, so the games a
+                               // slot plays do not depend on how the slots are sharded over ranks
     double* noise_scr;         // [G][A] f64 scratch of the root re-noising in k_select
     unsigned* move_ctr;        // searches done in this slot (RNG counter)
     // per-simulation scratch
@@ -185,11 +189,12 @@ __device__ void root_noise(const Dev<G>& d, int g, float* p, double* dscr, const
     for (int k = 0; k < G::MASK_WORDS; k++) L += __popc(mask[k]);
     // dscr[k] <- k-th Dirichlet component
     if (d.noise) {
-        for (int k = lane; k < L; k += 32) dscr[k] = d.noise[(size_t)g * A + k];
+        const double* nz = d.noise + (size_t)g * d.noise_gstride + (d.noise_ply ? (size_t)(d.noise_ply[g] - 1) * A : 0);
+        for (int k = lane; k < L; k += 32) dscr[k] = nz[k];
     } else {
         double alpha = d.dir_alpha > 0 ? d.dir_alpha : 10.0 / (double)L, part = 0;
         for (int k = lane; k < L; k += 32) {
-            Philox r(d.seed, ((uint64_t)g << 8) | 1u, ((uint64_t)d.move_ctr[g] << 16) | (unsigned)k);
+            Philox r(d.seed, ((d.game_base + (uint64_t)g) << 8) | 1u, ((uint64_t)d.move_ctr[g] << 16) | (unsigned)k);
             double x = r.gamma(alpha); dscr[k] = x; part += x;
         }
 #pragma unroll
@@ -833,6 +838,43 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_finish(Dev<G> d, int n,
     for (int a = lane; a < A; a += 32) out_counts[(size_t)g * A + a] = cnt[a];
     if (out_q && lane < NP) out_q[(size_t)g * NP + lane] = lane == 0 ? h.qs : -h.qs / (float)(NP - 1);
     if (lane == 0) d.move_ctr[g]++;
+}
+
+// ============================================================ node read-out (MCTS.nodes_data) ==========
+// nodes_data[stringRepresentation(board)] of the reference (MCTS.py:37-39: (Es, Vs, Ps, Ns, Qsa, Nsa, r, Qs)) for query i in the tree
+// of slot slots[i] (or i): dense A-wide rows rebuilt from the compact legal-edge arrays. found: 0 = not in the tree, 1 = expanded
+// node, 2 = terminal node (only Es / round are meaningful).
+template <class G>
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_node_query(Dev<G> d, int n, const int* slots, const int8_t* boards, int* found, float* es,
+                                                                     uint8_t* vs, float* ps, int* ns, double* qsa, int* nsa, int* rnd, float* qs) {
+    __shared__ __align__(16) int8_t sm[sel_warps<G>()][G::SP];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * sel_warps<G>() + w;
+    if (i >= n) return;
+    const int g = slots ? slots[i] : i;
+    constexpr int A = G::A, NP = G::NP;
+    int8_t* sb = sm[w];
+    for (int k = lane; k < G::SP; k += 32) sb[k] = k < G::S ? boards[(size_t)i * G::S + k] : (int8_t)0;
+    __syncwarp();
+    for (int a = lane; a < A; a += 32) { const size_t o = (size_t)i * A + a; if (vs) vs[o] = 0; if (ps) ps[o] = 0.f; if (qsa) qsa[o] = kNanQ; if (nsa) nsa[o] = 0; }
+    if (lane < NP && es) es[(size_t)i * NP + lane] = 0.f;
+    if (lane == 0) { found[i] = 0; if (ns) ns[i] = 0; if (rnd) rnd[i] = 0; if (qs) qs[i] = 0.f; }
+    if (g < 0 || g >= d.n_games) return;
+    uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
+    const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_keys(g), klo, khi, lane);
+    if (idx < 0) return;
+    __syncwarp();
+    const NodeHdr h = d.g_nodes(g)[idx]; const Edge* edges = d.g_edges(g); const typename G::act_t* acts = d.g_acts(g);
+    if (lane == 0) { found[i] = h.kind == NODE_TERMINAL ? 2 : 1; if (rnd) rnd[i] = h.round; }
+    if (h.kind == NODE_TERMINAL) {
+        const float* t = reinterpret_cast<const float*>(edges + h.edge_off);
+        if (lane < NP && es) es[(size_t)i * NP + lane] = t[lane];
+        return;
+    }
+    if (lane == 0) { if (ns) ns[i] = h.ns; if (qs) qs[i] = h.qs; }
+    for (int k = lane; k < h.n_legal; k += 32) {
+        const Edge ed = edges[h.edge_off + k]; const size_t o = (size_t)i * A + acts[h.edge_off + k];
+        if (vs) vs[o] = 1; if (ps) ps[o] = ed.p; if (qsa) qsa[o] = ed.q; if (nsa) nsa[o] = ed.n;
+    }
 }
 
 // ============================================================ tree GC ==================================

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(CSRC, 'libazg_b200.so')
 AZG_GAME_SPLENDOR = 1
 AZG_GAME_SANTORINI = 2
 AZG_GAME_ABALONE = 3
-AZG_ABI_VERSION = 3
+AZG_ABI_VERSION = 4
 AZG_N_STATS = 20
 AZG_NET_HASH = 0
 AZG_NET_SPLENDOR_V80 = 80
@@ -23,7 +23,7 @@ AZG_NET_ABALONE_V21 = 21
 SYMBOLS = ['azg_abi_version', 'azg_last_error', 'azg_device_count', 'azg_set_device', 'azg_engine_profile', 'azg_engine_kernel_times', 'azg_game_info', 'azg_game_init', 'azg_game_valid',
            'azg_game_next', 'azg_game_ended', 'azg_game_canonical', 'azg_game_round_score', 'azg_game_symmetries',
            'azg_net_create', 'azg_net_load', 'azg_net_forward', 'azg_net_destroy', 'azg_engine_create', 'azg_engine_destroy',
-           'azg_engine_reset', 'azg_engine_search', 'azg_engine_selfplay', 'azg_engine_examples', 'azg_engine_stats', 'azg_net_prof', 'azg_debug_selprof']
+           'azg_engine_reset', 'azg_engine_search', 'azg_engine_selfplay', 'azg_engine_selfplay_inject', 'azg_engine_selfplay_state', 'azg_engine_node', 'azg_engine_examples', 'azg_engine_stats', 'azg_net_prof', 'azg_debug_selprof']
 
 
 class GameInfo(C.Structure):
@@ -35,7 +35,12 @@ class EngineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('game_id', 'num_players', 'n_games', 'numMCTSSims', 'ratio_fullMCTS', 'universes',
                                          'forced_playouts', 'no_mem_optim', 'dirichlet_noise', 'node_cap', 'edge_cap')] + \
                [(n, C.c_double) for n in ('cpuct', 'fpu', 'dirichletAlpha', 'prob_fullMCTS')] + \
-               [('temperature', C.c_double * 3), ('tempThreshold', C.c_double), ('seed', C.c_uint64)]
+               [('temperature', C.c_double * 3), ('tempThreshold', C.c_double), ('seed', C.c_uint64), ('first_game', C.c_uint64)]
+
+
+class SelfplayInject(C.Structure):
+    _fields_ = [('n_plies', C.c_int32), ('init_boards', C.c_void_p), ('u_full', C.c_void_p), ('u_move', C.c_void_p), ('chance_seed', C.c_void_p),
+                ('noise', C.c_void_p)]
 
 
 class AzgError(RuntimeError):
@@ -80,6 +85,9 @@ def load():
     L.azg_engine_reset.argtypes = [vp, i32]
     L.azg_engine_search.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.azg_engine_selfplay.argtypes = [vp, i32, i32, vp]
+    L.azg_engine_selfplay_inject.argtypes = [vp, C.POINTER(SelfplayInject)]
+    L.azg_engine_selfplay_state.argtypes = [vp, vp, vp, vp, vp]
+    L.azg_engine_node.argtypes = [vp, i32] + [vp] * 12
     L.azg_engine_examples.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(i32)]
     L.azg_engine_stats.argtypes = [vp, vp]
     L.azg_set_device.argtypes = [i32]
@@ -124,4 +132,4 @@ def game_info(game_id=AZG_GAME_SPLENDOR, num_players=2):
 
 STAT_NAMES = ['sims', 'node_visits', 'expansions', 'nn_evals', 'terminal_hits', 'arena_overflows', 'gc_runs', 'max_nodes',
               'sum_legal', 'moves_played', 'episodes_finished', 'examples_recorded', 'kernels_launched', 'gc_sweeps', 'node_cap',
-              'sum_legal_visited', 'sum_legal_root_scans', 'sum_legal_refreshed', 'reserved18', 'reserved19']
+              'sum_legal_visited', 'sum_legal_root_scans', 'sum_legal_refreshed', 'examples_dropped', 'reserved19']

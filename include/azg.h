@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AZG_ABI_VERSION 3
+#define AZG_ABI_VERSION 4
 #define AZG_N_STATS 20                                  /* entries azg_engine_stats writes */
 
 enum { AZG_GAME_SPLENDOR = 1,                            /* GameSwitcher.py:3-13 ('splendor'), 2 players            */
@@ -106,6 +106,9 @@ typedef struct {
     double temperature[3];           /* main.py:135 ; [2] is the root-prior softmax temperature */
     double tempThreshold;            /* main.py:136 */
     uint64_t seed;                   /* device RNG seed (Dirichlet, PCR coin flips, move sampling, chance) */
+    uint64_t first_game;             /* global id of slot 0. Every RNG stream is keyed by (seed, first_game + slot, games started in the
+                                        slot, ply), so what a slot plays does not depend on how slots are sharded over ranks: rank r of a
+                                        world that shards n_total slots passes first_game = dist.shard_games(n_total, r, world)[0]. */
 } azg_engine_cfg;
 
 typedef struct azg_engine azg_engine;
@@ -128,20 +131,48 @@ int azg_engine_search(azg_engine* e, int n, const int8_t* roots, const uint8_t* 
                       int32_t* out_counts, int32_t* out_raw, float* out_q, void* stream);
 
 /* Coach.executeEpisodes (Coach.py:86-148): keeps all n_games slots playing (refilling finished games)
- * until at least `min_episodes` games have finished or `max_moves` lock-step plies were played.
+ * until at least `min_episodes` games have finished or `max_moves` lock-step plies were played, or (when min_episodes > 0) the
+ * example ring is more than half full -- drain it with azg_engine_examples and call again (stats[10] counts finished episodes).
  * Training examples (un-augmented: one per full-search ply) are appended to the engine's example ring
  * and fetched with azg_engine_examples. Returns counters in out_stats (see azg_engine_stats). */
 int azg_engine_selfplay(azg_engine* e, int min_episodes, int max_moves, void* stream);
+/* Injected randomness for azg_engine_selfplay (parity tests: replay of an episode recorded from the reference's Coach.executeEpisode,
+ * oracle/gen_golden_selfplay.py). Per slot g and ply p = episodeStep - 1 < n_plies the engine takes
+ *   u_full[g][p]      instead of MCTS.rng.random()  -- the playout-cap coin, MCTS.py:58
+ *   noise[g][p][0..L) instead of MCTS.rng.dirichlet -- the root Dirichlet draw of a full search, MCTS.py:187-197 (NULL: drawn on device)
+ *   u_move[g][p]      instead of the uniform np.random.choice consumes in random_pick, Coach.py:289-292
+ *   chance_seed[g][p] as random_seed of the real move (Coach.py:71 passes 0 = true random; non-zero = make_move's deterministic draw)
+ * and starts slot g from init_boards[g] instead of Game.getInitBoard. Every slot then plays exactly ONE game and idles (no refill).
+ * Buffers (host or device) are copied; inj == NULL returns the engine to its own device RNG. Resets all self-play slots. */
+typedef struct {
+    int32_t n_plies;
+    const int8_t* init_boards;       /* [n_games][state_bytes] */
+    const double* u_full;            /* [n_games][n_plies] */
+    const double* u_move;            /* [n_games][n_plies] */
+    const int64_t* chance_seed;      /* [n_games][n_plies] */
+    const double* noise;             /* [n_games][n_plies][action_size] or NULL */
+} azg_selfplay_inject;
+int azg_engine_selfplay_inject(azg_engine* e, const azg_selfplay_inject* inj);
 /* Drains up to `cap` finished-game examples: boards int8[cap][S], pi f32[cap][A], z f32[cap][np],
  * valids u8[cap][A], q f32[cap][np]; *out_n = number written. (tuple layout of Coach.py:76-82) */
 int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n);
+
+/* MCTS.nodes_data[stringRepresentation(board)] (MCTS.py:37-39: the tuple (Es, Vs, Ps, Ns, Qsa, Nsa, r, Qs)) for n boards, query i looked
+ * up in the tree of slot slots[i] (NULL = slot i). found int32[n]: 0 = not in the tree, 1 = expanded node, 2 = terminal node (es / round
+ * only). Dense A-wide rows like the reference's arrays: vs u8[n][A], ps f32[n][A], qsa f64[n][A] (-42 = never visited), nsa i32[n][A];
+ * es f32[n][np], ns i32[n], round i32[n], qs f32[n]. Any output but `found` may be NULL. */
+int azg_engine_node(azg_engine* e, int n, const int32_t* slots, const int8_t* boards, int32_t* found, float* es, uint8_t* vs, float* ps,
+                    int32_t* ns, double* qsa, int32_t* nsa, int32_t* round, float* qs, void* stream);
+/* The self-play slots as Coach.executeEpisode's locals (Coach.py:55-60): absolute-frame boards int8[n_games][S], curPlayer, episodeStep,
+ * and whether the slot holds a running game. Any output may be NULL. */
+int azg_engine_selfplay_state(azg_engine* e, int8_t* boards, int32_t* players, int32_t* plies, int32_t* active);
 
 /* Counters since creation: [0] sims [1] node_visits (select steps) [2] expansions (nodes with priors)
  * [3] nn_evals [4] terminal_hits [5] arena_overflows [6] gc_runs [7] max_nodes_in_a_tree
  * [8] sum_legal (over expansions) [9] moves_played [10] episodes_finished [11] examples_recorded
  * [12] kernels_launched [13] gc_sweeps (tier-2 reachability GCs, see tree.cuh) [14] node_cap [15] sum_legal_visited (sum of n_legal over select steps)
  * [16] sum_legal_root_scans (edges scanned by k_select at the roots) [17] sum_legal_refreshed (edges scanned by k_backup when it
- * refreshes the cached PUCT choice of the nodes on the path) [18..19] reserved.  out must hold AZG_N_STATS int64. */
+ * refreshes the cached PUCT choice of the nodes on the path) [18] examples_dropped (example ring full: must stay 0) [19] reserved.  out must hold AZG_N_STATS int64. */
 int azg_engine_stats(azg_engine* e, int64_t* out_stats);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch of the search loop).

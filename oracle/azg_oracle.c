@@ -1163,6 +1163,7 @@ typedef struct {
     u8* sVs; float* sPs; double* sQsa; int64_t* sNsa;        /* [cap][A] slabs */
     int dirichlet_noise, step, last_cleaning; int64_t random_seed;
     azo_rng rng;
+    double inj_u_full;               /* >= 0: injected playout-cap coin for the next getActionProb (replay of a recorded episode) */
     /* counters */
     int64_t n_sims, n_expansions, n_node_visits, n_nn_evals;
 } azo_mcts;
@@ -1209,7 +1210,7 @@ azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_nois
     if (cfg->net_kind == 3) v21_bind(&m->net21, blob);
     m->cap = m->A > 1000 ? 512 : 4096; m->tcap = 4 * m->cap; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
     slabs_alloc(m);
-    m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed);
+    m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed); m->inj_u_full = -1.0;
     return m;
 }
 void azo_mcts_free(azo_mcts* m) { if (m) { free(m->nodes); free(m->table); free(m->sVs); free(m->sPs); free(m->sQsa); free(m->sNsa); free(m); } }
@@ -1353,7 +1354,7 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
 int azo_mcts_get_action_prob(azo_mcts* m, const i8* cb, double temp, int force_full, const double* noise,
                              double* probs, float* q, int64_t* raw_counts) {
     const azo_cfg* c = &m->cfg; int n = c->num_players; const int A = m->A;
-    int full = force_full || (rng_uniform(&m->rng) < c->prob_fullMCTS);
+    int full = force_full || ((m->inj_u_full >= 0 ? m->inj_u_full : rng_uniform(&m->rng)) < c->prob_fullMCTS);
     int nsims = full ? c->numMCTSSims : c->numMCTSSims / c->ratio_fullMCTS;
     int forced = full && c->forced_playouts;
     for (m->step = 0; m->step < nsims; m->step++) {
@@ -1439,6 +1440,58 @@ static void execute_episode(azo_mcts* m, uint64_t seed, double t0, double t1, do
         if (any || (max_plies > 0 && step >= max_plies)) break;
     }
     st->games++;
+}
+
+/* Coach.executeEpisode (Coach.py:37-84) replayed with INJECTED randomness (tests): every random input the reference consumes is
+ * supplied by the caller, per ply p = episodeStep - 1 < P:
+ *   u_full[p]      the playout-cap coin (MCTS.py:58)                 noise[p*noise_stride ..]  the root Dirichlet draw (MCTS.py:187-197), or NULL
+ *   u_move[p]      the uniform of random_pick's np.random.choice (Coach.py:289-292: cdf = cumsum(p) / cdf[-1], searchsorted right)
+ *   chance_seed[p] random_seed of the real move (non-zero => the deterministic draw of make_move; games without chance ignore it)
+ * Records the UN-augmented examples (canonical board, pi = probs of getActionProb(temp=1), z = roll(r, -player), valids, q) of the
+ * full-search plies (Coach.py:65-69,76-82). Returns the number of examples, or -1 if P plies did not finish the game. */
+int azo_execute_episode_inj(azo_mcts* m, const i8* init_board, int P, const double* u_full, const double* u_move, const int64_t* chance_seed,
+                            const double* noise, int noise_stride, double t0, double t1, double half, int max_examples,
+                            i8* ex_board, float* ex_pi, float* ex_z, u8* ex_valid, float* ex_q, int* out_plies, int* out_actions, u8* out_full) {
+    const int n = m->cfg.num_players, S = m->S, A = m->A;
+    i8 board[MAXS], cb[MAXS]; memcpy(board, init_board, (size_t)S);
+    int player = 0, step = 0, n_ex = 0; azo_mcts_reset(m);
+    static __thread double probs[MAXA], w[MAXA]; float q[MAXP], r[MAXP];
+    int* ex_player = (int*)malloc(sizeof(int) * (size_t)(max_examples > 0 ? max_examples : 1));
+    azo_rng dummy; rng_seed(&dummy, 1);
+    for (;;) {
+        if (step >= P) { free(ex_player); *out_plies = step; return -1; }
+        step++;
+        memcpy(cb, board, (size_t)S); if (player) g_swap(m, cb, player);
+        m->inj_u_full = u_full[step - 1];
+        const int full = azo_mcts_get_action_prob(m, cb, 1.0, 0, noise ? noise + (size_t)(step - 1) * (size_t)noise_stride : NULL, probs, q, NULL);
+        m->inj_u_full = -1.0;
+        const double T = temp_for_selfplay(t0, t1, half, step);
+        int action = -1;
+        if (T == 0) { double b = -1; for (int a = 0; a < A; a++) if (probs[a] > b) { b = probs[a]; action = a; } }
+        else {                                                    /* applyTemperatureAndNormalize + np.random.choice, Coach.py:278-292 */
+            double s = 0; for (int a = 0; a < A; a++) { w[a] = pow(probs[a], 1.0 / T); s += w[a]; }
+            double acc = 0; for (int a = 0; a < A; a++) { w[a] = w[a] / s; acc += w[a]; w[a] = acc; }
+            const double last = w[A - 1], u = u_move[step - 1];
+            action = 0; for (int a = 0; a < A; a++) if (w[a] / last <= u) action = a + 1;
+            if (action >= A) action = A - 1;
+        }
+        if (full && n_ex < max_examples) {
+            u8* V = ex_valid + (size_t)n_ex * (size_t)A; g_valid(m, cb, V);
+            memcpy(ex_board + (size_t)n_ex * (size_t)S, cb, (size_t)S);
+            for (int a = 0; a < A; a++) ex_pi[(size_t)n_ex * (size_t)A + a] = (float)probs[a];
+            for (int p = 0; p < n; p++) ex_q[(size_t)n_ex * n + p] = q[p];
+            ex_player[n_ex] = player; n_ex++;
+        }
+        if (out_actions) out_actions[step - 1] = action;
+        if (out_full) out_full[step - 1] = (u8)full;
+        player = g_move(m, board, action, player, chance_seed ? chance_seed[step - 1] : 1, &dummy);
+        g_ended(m, board, player, r);
+        int any = 0; for (int p = 0; p < n; p++) any |= r[p] != 0.f;
+        if (any) break;
+    }
+    for (int e = 0; e < n_ex; e++) for (int p = 0; p < n; p++) ex_z[(size_t)e * n + p] = r[(p + ex_player[e]) % n];   /* np.roll(r, -player) */
+    free(ex_player); *out_plies = step;
+    return n_ex;
 }
 
 typedef struct { azo_cfg cfg; const float* blob; int games, max_plies; uint64_t seed; double t0, t1, half; azo_run_stats st; } worker_t;

@@ -217,6 +217,56 @@ class MCTS:
         return probs, q, bool(full), raw
 
 
+GAME_SHAPES = {GAME_SPLENDOR: (56, 7), GAME_SANTORINI: (5, 5, 3), GAME_ABALONE: (9, 9, 4), GAME_AZUL: (23, 6)}
+
+
+def execute_episode_inj(cfg, init_board, u_full, u_move, chance_seed, noise=None, temperature=(1.0, 0.1), tempThreshold=10, blob=None,
+                        dirichlet_noise=None):
+    """Coach.executeEpisode (Coach.py:37-84) on the oracle with injected randomness (see azo_execute_episode_inj).
+    noise: list of per-ply Dirichlet vectors (may be ragged / empty for non-full plies) or None.
+    Returns dict(boards, pi, z, valids, q: un-augmented examples; plies; actions; full)."""
+    A = GAME_ACTIONS[cfg.game]; shape = GAME_SHAPES[cfg.game]; npl = cfg.num_players
+    P = len(u_full)
+    dn = (cfg.dirichletAlpha != 0) if dirichlet_noise is None else dirichlet_noise
+    m = MCTS(cfg, blob, dirichlet_noise=dn, seed=1)
+    b0 = _board(init_board)
+    uf = np.ascontiguousarray(u_full, np.float64); um = np.ascontiguousarray(u_move, np.float64)
+    cs = np.ascontiguousarray(chance_seed if chance_seed is not None else np.ones(P), np.int64)
+    nz = None; stride = 0
+    if noise is not None:
+        stride = max(max((len(x) for x in noise), default=0), 1)
+        nz = np.zeros((P, stride), np.float64)
+        for i, x in enumerate(noise):
+            nz[i, :len(x)] = x
+    eb = np.zeros((P,) + shape, np.int8); ep = np.zeros((P, A), np.float32); ez = np.zeros((P, npl), np.float32)
+    ev = np.zeros((P, A), np.uint8); eq = np.zeros((P, npl), np.float32)
+    plies = C.c_int(0); acts = np.zeros(P, np.int32); full = np.zeros(P, np.uint8)
+    L = lib()
+    L.azo_execute_episode_inj.restype = C.c_int
+    n = L.azo_execute_episode_inj(C.c_void_p(m.h), _p(b0, C.c_int8), C.c_int(P), _p(uf, C.c_double), _p(um, C.c_double), _p(cs, C.c_int64),
+                                  _p(nz, C.c_double) if nz is not None else None, C.c_int(stride), C.c_double(temperature[0]),
+                                  C.c_double(temperature[1]), C.c_double(tempThreshold), C.c_int(P), _p(eb, C.c_int8), _p(ep, C.c_float),
+                                  _p(ez, C.c_float), _p(ev, C.c_uint8), _p(eq, C.c_float), C.byref(plies), _p(acts, C.c_int32), _p(full, C.c_uint8))
+    if n < 0:
+        raise RuntimeError(f'episode did not finish within the {P} injected plies')
+    k = plies.value
+    return dict(boards=eb[:n], pi=ep[:n], z=ez[:n], valids=ev[:n].astype(np.bool_), q=eq[:n], plies=k, actions=acts[:k], full=full[:k].astype(np.bool_))
+
+
+def symmetries_for(game):
+    """getSymmetries of oracle game id `game` as f(board, pi, valids) -> [(board, pi, valids)]."""
+    return {GAME_SPLENDOR: symmetries, GAME_SANTORINI: sant_symmetries, GAME_ABALONE: aba_symmetries, GAME_AZUL: azul_symmetries}[game]
+
+
+def augment(game, ex):
+    """Coach.py:66-69 applied to un-augmented examples: list of (board, pi, z, valids, q) in the reference's order."""
+    sym = symmetries_for(game); out = []
+    for i in range(len(ex['boards'])):
+        for b, p, v in sym(ex['boards'][i], ex['pi'][i], ex['valids'][i]):
+            out.append((b, p, ex['z'][i], v, ex['q'][i]))
+    return out
+
+
 def selfplay_bench(cfg, blob, threads, games_per_thread, max_plies=0, temperature=(1.0, 0.1), tempThreshold=10, seed=1):
     blob = np.ascontiguousarray(blob, np.float32); out = np.zeros(8, np.float64)
     lib().azo_selfplay_bench(C.byref(cfg), _p(blob, C.c_float), threads, games_per_thread, max_plies,

@@ -158,3 +158,39 @@ def v84_golden():
         sd = {k[4:]: z[k] for k in z.files if k.startswith('sd__')}
         out[tag] = dict(sd=sd, boards=z['boards'], valids=z['valids'], pi=z['pi'], v=z['v'])
     return out
+
+
+def load_selfplay_golden(game):
+    """tests/golden/<game>_selfplay.npz (oracle/gen_golden_selfplay.py): the reference's Coach.executeEpisode with every random
+    input recorded. Returns (cfg dict, [game dicts with init, u_full, u_move, chance_seed, noise (ragged list), is_full, action,
+    ex_board, ex_pi, ex_z, ex_valids, ex_q])."""
+    z = np.load(os.path.join(GOLDEN, f'{game}_selfplay.npz'))
+    cfg = {k[4:]: z[k].tolist() for k in z.files if k.startswith('cfg_')}
+    games = []
+    for gi in range(int(z['n_games'])):
+        p = f'g{gi}_'
+        d = {k: z[p + k] for k in ('init', 'u_full', 'u_move', 'chance_seed', 'is_full', 'action', 'root', 'ex_board', 'ex_z', 'ex_q')}
+        d['noise'] = [z[p + 'noise'][i, :int(n)] for i, n in enumerate(z[p + 'noise_len'])]
+        n_ex = len(d['ex_board'])
+        if p + 'ex_pi' in z.files:
+            d['ex_pi'] = z[p + 'ex_pi']; d['ex_valids'] = z[p + 'ex_valids']
+        else:
+            A = 3402
+            pi = np.zeros((n_ex, A), np.float32); idx = z[p + 'ex_pi_idx']; pi[idx[0], idx[1]] = z[p + 'ex_pi_val']
+            d['ex_pi'] = pi; d['ex_valids'] = np.unpackbits(z[p + 'ex_valids_bits'], axis=1)[:, :A].astype(np.bool_)
+        games.append(d)
+    return cfg, games
+
+
+def assert_examples_equal(got, gold, pi_tol=0.0):
+    """got: list of (board, pi, z, valids, q) tuples; gold: one game dict of load_selfplay_golden. Example for example."""
+    assert len(got) == len(gold['ex_board']), (len(got), len(gold['ex_board']))
+    for i, (b, pi, zz, v, q) in enumerate(got):
+        assert (np.asarray(b).reshape(-1) == gold['ex_board'][i].reshape(-1)).all(), f'example {i}: board'
+        if pi_tol == 0.0:
+            assert (np.asarray(pi, np.float32) == gold['ex_pi'][i]).all(), f'example {i}: pi'
+        else:
+            assert np.abs(np.asarray(pi, np.float32) - gold['ex_pi'][i]).max() <= pi_tol, f'example {i}: pi'
+        assert (np.asarray(zz, np.float32) == gold['ex_z'][i]).all(), f'example {i}: z {zz} vs {gold["ex_z"][i]}'
+        assert (np.asarray(v).astype(bool) == gold['ex_valids'][i]).all(), f'example {i}: valids'
+        assert (np.asarray(q, np.float32) == gold['ex_q'][i]).all(), f'example {i}: q'
