@@ -493,6 +493,7 @@ struct azg_engine {                      // game-independent face of the engine 
     virtual int node(int n, const int32_t* slots, const int8_t* boards, int32_t* found, float* es, uint8_t* vs, float* ps, int32_t* ns, double* qsa,
                      int32_t* nsa, int32_t* round, float* qs, cudaStream_t st) = 0;
     virtual int examples(int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) = 0;
+    virtual int examples_pending(int32_t* out_n) = 0;
     virtual int stats(int64_t* out16) = 0;
     virtual int profile(int enable) = 0;
     virtual int kernel_times(double* out8) = 0;
@@ -757,6 +758,13 @@ struct EngineT : azg_engine {
         CK(cudaStreamSynchronize(st));
         return 0;
     }
+    int examples_pending(int32_t* out_n) override {
+        *out_n = 0;
+        if (!sp_ready) return 0;
+        CK(cudaDeviceSynchronize());
+        int count = 0; CK(cudaMemcpy(&count, sp.ex_count, sizeof(int), cudaMemcpyDeviceToHost));
+        *out_n = std::min(count, sp.ex_cap); return 0;
+    }
     int examples(int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) override {
         *out_n = 0;
         if (!sp_ready) return 0;
@@ -827,6 +835,10 @@ extern "C" int azg_engine_selfplay_state(azg_engine* e, int8_t* boards, int32_t*
 extern "C" int azg_engine_selfplay_inject(azg_engine* e, const azg_selfplay_inject* inj) {
     if (!e) return fail("engine is NULL");
     return e->selfplay_inject(inj);
+}
+extern "C" int azg_engine_examples_pending(azg_engine* e, int32_t* out_n) {
+    if (!e || !out_n) return fail("NULL argument");
+    return e->examples_pending(out_n);
 }
 extern "C" int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n) {
     if (!e || !out_n) return fail("NULL argument");

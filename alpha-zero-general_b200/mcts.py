@@ -116,6 +116,26 @@ class Engine:
         m = n.value
         return b[:m].reshape((m,) + self.game.getBoardSize()), pi[:m], z[:m], va[:m].astype(np.bool_), q[:m]
 
+    def examples_pending(self):
+        n = C.c_int32(0)
+        _lib.check(self._L.azg_engine_examples_pending(self.h, C.byref(n)))
+        return n.value
+
+    def examples_device(self, device=None):
+        """Drains the example ring into torch CUDA tensors (device-to-device: the examples never touch host memory).
+        Returns (boards int8[m, *board_shape], pi f32[m,A], z f32[m,np], valids uint8[m,A], q f32[m,np])."""
+        import torch
+        A, S, NPL = self.info.action_size, self.info.state_bytes, self.game.num_players
+        m = self.examples_pending()
+        dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        b = torch.empty((m, S), dtype=torch.int8, device=dev); pi = torch.empty((m, A), dtype=torch.float32, device=dev)
+        z = torch.empty((m, NPL), dtype=torch.float32, device=dev); va = torch.empty((m, A), dtype=torch.uint8, device=dev)
+        q = torch.empty((m, NPL), dtype=torch.float32, device=dev); n = C.c_int32(0)
+        if m:
+            _lib.check(self._L.azg_engine_examples(self.h, m, _lib.ptr(b), _lib.ptr(pi), _lib.ptr(z), _lib.ptr(va), _lib.ptr(q), C.byref(n)))
+            assert n.value == m
+        return b.view((m,) + self.game.getBoardSize()), pi, z, va, q
+
     def stats(self):
         out = np.zeros(_lib.AZG_N_STATS, np.int64)
         _lib.check(self._L.azg_engine_stats(self.h, _lib.ptr(out)))

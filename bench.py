@@ -61,6 +61,9 @@ def parse():
     ap.add_argument('--sims', type=int, default=0, help='numMCTSSims (0 = the config default: 800, abalone 1600)')
     ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 6 x sims + 320)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-iteration', action='store_true', help='skip the secondary whole-iteration leg (complete games -> example drain -> NCCL gather -> symmetries)')
+    ap.add_argument('--iter-sims', type=int, default=0, help='numMCTSSims of the whole-iteration leg (0 = 40: complete games within seconds)')
+    ap.add_argument('--iter-games', type=int, default=0, help='concurrent games per GPU of the whole-iteration leg (0 = --games)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-plies', type=int, default=0, help='plies per thread of the cpu_baseline sample (0 = 12 splendor / 1 santorini: ~10-30 s)')
     a = ap.parse_args()
@@ -138,6 +141,20 @@ def cpu_sample(sims, plies, threads, seed=1, game='splendor'):
     return O.selfplay_bench(cfg, blob, threads, 1, max_plies=plies, temperature=a['temperature'][:2], tempThreshold=a['tempThreshold'], seed=seed)
 
 
+def port_vs_reference(port_value):
+    """The C port is faster than the reference's own Numba + torch-CPU path. profiles/r02_reference_cpu.json holds both timed on the
+    same cores of the build container (scripts/time_reference_cpu.py runs the UNMODIFIED Coach.executeEpisode); the measured
+    port/reference factor converts a port figure into what the reference itself would do on these cores."""
+    p = os.path.join(ROOT, 'profiles', 'r02_reference_cpu.json')
+    if not os.path.exists(p):
+        return {}
+    d = json.load(open(p)); f = float(d['port_over_reference']['all_cores'])
+    return {'port_over_reference': f, 'reference_equivalent_value': port_value / f,
+            'reference_measured': {'where': d['where'], 'cpu_model': d['cpu_model'], 'one_process_sims_per_s': d['ref_1proc']['sims_per_s_sum'],
+                                   'P_processes': d['ref_Pproc']['procs'], 'P_processes_sims_per_s': d['ref_Pproc']['sims_per_s_sum'],
+                                   'stub_net_one_process_sims_per_s': d['ref_stub_1proc']['sims_per_s_sum'], 'source': 'profiles/r02_reference_cpu.json'}}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -153,9 +170,10 @@ def run_reference(args, rank):
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32/f64',
             'data': 'synthetic', 'config': workload_cfg(args, threads),
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'cpu_baseline': dict({'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                              'sample': f'{threads} host threads x 1 {args.game} self-play game x {plies} plies x {args.sims} sims per step, {args.steps} steps; '
                                        'oracle/azg_oracle.c (C port of the reference path; the Python/numba reference cannot travel to the GPU box)'},
+                                 **port_vs_reference(val)),
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
@@ -165,7 +183,7 @@ def workload_cfg(args, cpu_threads=None):
     c = {'workload': f'{gm["tag"]}_{args.games}games_per_gpu_{args.sims}sims_randinit', 'game': args.game, 'num_players': 2,
          'games_per_gpu': args.games, 'numMCTSSims': args.sims, 'net': gm['net'],
          'universes': gm['universes'], 'prob_fullMCTS': 1.0, 'dirichlet_noise': True, 'step': 'one self-play ply of every game (numMCTSSims lock-step simulations per tree)',
-         'parallelism': f'games sharded over {args.gpus} GPU(s), no data-path collective', 'l2': 'working set >> L2 (tree arenas of tens of GB); no flush needed'}
+         'parallelism': f'games sharded over {args.gpus} GPU(s) by global slot id; no collective inside the search loop; the iteration leg gathers the examples over NCCL', 'l2': 'working set >> L2 (tree arenas of tens of GB); no flush needed'}
     if cpu_threads:
         c['cpu_threads'] = cpu_threads
     return c
@@ -219,6 +237,70 @@ class HostLoop:
         self.h2d += self.board.nbytes + self.player.nbytes; self.d2h += self.roots.nbytes
 
 
+# --------------------------------------------------------------------------- whole-iteration leg -------
+def run_iteration(torch, dist, args, game, net, rank, world, dev, barrier, max_over_ranks, sum_over_ranks, gather_examples, shard_games):
+    """One self-play ITERATION as the reference runs it (Coach.py:105-148 executeEpisodes, then learn() consumes the examples in one
+    process): every slot plays complete games until n_games episodes have finished on this rank (refill of finished slots, terminal
+    nodes, example hand-over to the ring, ring drained device-to-device whenever it is half full), then the un-augmented examples
+    of all ranks are gathered to rank 0 over NCCL (point-to-point, exact byte ranges) and getSymmetries runs on rank 0's GPU.
+    Smaller numMCTSSims than the headline so that complete games fit in seconds; everything is inside the timed region."""
+    from azg_b200 import lib
+    from azg_b200.mcts import Engine
+    sims = args.iter_sims or 40
+    n_games = args.iter_games or args.games
+    a = mcts_args(sims, args.game)
+    first_game, _ = shard_games(n_games * world, rank, world)
+    eng = Engine(game, net, a, n_games=n_games, dirichlet_noise=True, seed=2000, node_cap=8 * sims + 256, first_game=first_game)
+    eng.selfplay(max_moves=2)                                                     # warm-up plies
+    s0 = eng.stats()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    stream = torch.cuda.current_stream()
+    barrier()
+    ev[0].record(stream)
+    parts = []
+    while True:
+        left = n_games - (eng.stats()['episodes_finished'] - s0['episodes_finished'])
+        if left <= 0:
+            break
+        eng.selfplay(min_episodes=left)
+        parts.append(eng.examples_device(dev))                                    # ring -> torch CUDA tensors (device-to-device)
+    local = tuple(torch.cat([p[i] for p in parts]) for i in range(5))
+    ev[1].record(stream)
+    (gb, gpi, gz, gva, gq), gst = gather_examples(local, dst=0, return_stats=True)
+    ev[2].record(stream)
+    n_aug = 0
+    if rank == 0 and len(gb):                                                     # getSymmetries after the gather, on device pointers, in chunks
+        L = lib.load(); K = game.info.max_symmetries; S = game.info.state_bytes; A = game.info.action_size; CH = 32768
+        ob = torch.empty((CH, K, S), dtype=torch.int8, device=dev); opi = torch.empty((CH, K, A), dtype=torch.float32, device=dev)
+        om = torch.empty((CH, K, A), dtype=torch.uint8, device=dev); ok = torch.empty((CH,), dtype=torch.int32, device=dev)
+        tot = torch.zeros((), dtype=torch.int64, device=dev)
+        gbf = gb.reshape(len(gb), S)
+        for i in range(0, len(gb), CH):
+            m = min(CH, len(gb) - i)
+            lib.check(L.azg_game_symmetries(game.game_id, N_PL, m, lib.ptr(gbf[i:i + m]), lib.ptr(gpi[i:i + m]), lib.ptr(gva[i:i + m]), lib.ptr(ob), lib.ptr(opi),
+                                            lib.ptr(om), lib.ptr(ok), None))
+            tot += ok[:m].sum()
+        n_aug = int(tot.item())
+    ev[3].record(stream)
+    barrier()
+    s1 = eng.stats()
+    ms_play = max_over_ranks(ev[0].elapsed_time(ev[1])); ms_gather = max_over_ranks(ev[1].elapsed_time(ev[2])); ms_sym = max_over_ranks(ev[2].elapsed_time(ev[3]))
+    ms_total = max_over_ranks(ev[0].elapsed_time(ev[3]))
+    d = {k: s1[k] - s0[k] for k in ('sims', 'moves_played', 'episodes_finished', 'examples_recorded', 'terminal_hits', 'gc_runs', 'gc_sweeps', 'arena_overflows', 'node_visits')}
+    sims_total = sum_over_ranks(d['sims']); ex_total = sum_over_ranks(int(len(local[0]))); ep_total = sum_over_ranks(d['episodes_finished'])
+    rec = game.info.state_bytes + 4 * game.info.action_size + game.info.action_size + 8 * N_PL
+    out = {'numMCTSSims': sims, 'games_per_gpu': n_games, 'episodes_finished': ep_total, 'examples_unaugmented': ex_total, 'examples_after_symmetries_rank0': n_aug,
+           'bytes_per_example': rec, 'sims': sims_total, 'sims_per_sec_incl_gather': sims_total / (ms_total * 1e-3), 'sims_per_sec_selfplay_only': sims_total / (ms_play * 1e-3),
+           'selfplay_ms': ms_play, 'gather_ms': ms_gather, 'symmetries_ms': ms_sym, 'total_ms': ms_total, 'gather_share': ms_gather / ms_total,
+           'collective': ('none (1 rank)' if world == 1 else f'NCCL point-to-point gather to rank 0 (batch_isend_irecv = one ncclGroup; {world - 1} senders, exact byte ranges, '
+                          'no padding, device memory on both sides), after one all_gather of the counts'),
+           'gather_bytes_received_rank0': gst['bytes_received'] if rank == 0 else None,
+           'gather_GBps_into_rank0': (gst['bytes_received'] / (ms_gather * 1e-3) / 1e9) if (rank == 0 and world > 1 and ms_gather > 0) else None,
+           'rank0_counters': dict(d, examples_dropped=s1['examples_dropped'], mean_depth=d['node_visits'] / max(d['sims'], 1))}
+    eng.close()
+    return out
+
+
 # --------------------------------------------------------------------------- main (B200 arm) -----------
 def main():
     args = parse()
@@ -266,7 +348,9 @@ def main():
     S_BYTES, N_ACT = gm['S'], gm['A']
     a = mcts_args(args.sims, args.game)
     node_cap = args.node_cap or (6 * args.sims + 320)
-    eng = Engine(game, net, a, n_games=args.games, dirichlet_noise=True, seed=1000 + rank, node_cap=node_cap)
+    from azg_b200.dist import gather_examples, shard_games
+    first_game, _ = shard_games(args.games * world, rank, world)               # global slot ids: the games do not depend on the world size
+    eng = Engine(game, net, a, n_games=args.games, dirichlet_noise=True, seed=1000, node_cap=node_cap, first_game=first_game)
     K, W = args.steps, args.warmup
     stream = torch.cuda.current_stream()
 
@@ -361,19 +445,26 @@ def main():
         r = cpu_sample(args.sims, args.cpu_plies, threads, game=args.game)
         cpu = {'value': r['sims'] / r['seconds'], 'unit': UNIT, 'cores': threads, 'kind': 'port', 'seconds': r['seconds'],
                'sample': f'{threads} host threads x 1 {args.game} self-play game x {args.cpu_plies} plies x {args.sims} sims (oracle/azg_oracle.c, same MCTS args and net weights)'}
+        cpu.update(port_vs_reference(cpu['value']))
+
+    # ---- whole-iteration leg: complete games -> drain -> gather (NCCL) -> symmetries --------------------------------------
+    iteration = None
+    eng.close()
+    if not args.no_iteration:
+        iteration = run_iteration(torch, dist, args, game, net, rank, world, dev, barrier, max_over_ranks, sum_over_ranks, gather_examples, shard_games)
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 net (token GEMMs 3xTF32 on tcgen05, fp32 accumulate) / f64 PUCT / i8 boards', 'data': 'synthetic',
                 'config': workload_cfg(args), 'e2e': e2e, 'gpu_launches': int(d['kernels_launched']), 'roofline': roofline, 'cpu_baseline': cpu,
-                'clocks': clk, 'kernels': kern, 'tree_path': tree_path,
+                'clocks': clk, 'kernels': kern, 'tree_path': tree_path, 'iteration': iteration,
                 'counters': {'sims': d['sims'], 'node_visits': visits, 'expansions': exps, 'nn_evals': evals, 'terminal_hits': d['terminal_hits'],
-                             'arena_overflows': d['arena_overflows'], 'gc_runs': d['gc_runs'], 'moves_played': d['moves_played'],
+                             'arena_overflows': d['arena_overflows'], 'gc_runs': d['gc_runs'], 'gc_sweeps': d['gc_sweeps'], 'examples_dropped': s1['examples_dropped'],
+                             'moves_played': d['moves_played'],
                              'episodes_finished': d['episodes_finished'], 'mean_depth': Dbar, 'mean_legal_visited': Lbar_vis, 'mean_legal_expanded': Lbar_exp,
                              'expansions_per_sec': sum_over_ranks(exps) / (ms * 1e-3) if world == 1 else None, 'node_visits_per_sec': visits / (ms * 1e-3) if world == 1 else None,
                              'node_cap': s1['node_cap'], 'max_nodes': s1['max_nodes']}}
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -154,7 +154,10 @@ typedef struct {
 } azg_selfplay_inject;
 int azg_engine_selfplay_inject(azg_engine* e, const azg_selfplay_inject* inj);
 /* Drains up to `cap` finished-game examples: boards int8[cap][S], pi f32[cap][A], z f32[cap][np],
- * valids u8[cap][A], q f32[cap][np]; *out_n = number written. (tuple layout of Coach.py:76-82) */
+ * valids u8[cap][A], q f32[cap][np]; *out_n = number written. (tuple layout of Coach.py:76-82). The buffers may be DEVICE memory
+ * (torch tensors): the examples then never leave HBM (device-to-device copies), which is what the multi-GPU gather and a training
+ * step on the same GPU use. */
+int azg_engine_examples_pending(azg_engine* e, int32_t* out_n);     /* examples waiting in the ring (size the buffers of azg_engine_examples) */
 int azg_engine_examples(azg_engine* e, int cap, int8_t* boards, float* pi, float* z, uint8_t* valids, float* q, int32_t* out_n);
 
 /* MCTS.nodes_data[stringRepresentation(board)] (MCTS.py:37-39: the tuple (Es, Vs, Ps, Ns, Qsa, Nsa, r, Qs)) for n boards, query i looked

@@ -34,9 +34,15 @@ def _worker(rank, world, port, counts, q):
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        got = gather_examples(_examples(rank, counts[rank]))
         want = [np.concatenate([_examples(r, counts[r])[k] for r in range(world)], axis=0) for k in range(5)]
-        ok = all(g.dtype == w.dtype and g.shape == w.shape and (g == w).all() for g, w in zip(got, want))
+        same = lambda got: all(g.dtype == w.dtype and g.shape == w.shape and (g == w).all() for g, w in zip(got, want))
+        got, st = gather_examples(_examples(rank, counts[rank]), return_stats=True)               # every rank gets everything
+        ok = same(got) and st['counts'] == list(counts)
+        got0 = gather_examples(_examples(rank, counts[rank]), dst=1)                              # point-to-point gather to rank 1 only
+        ok = ok and (same(got0) if rank == 1 else all(len(g) == 0 for g in got0))
+        tens = tuple(torch.from_numpy(a.view(np.uint8) if a.dtype == np.bool_ else a) for a in _examples(rank, counts[rank]))
+        gott = gather_examples(tens)                                                               # tensors in -> tensors out (the device path on GPUs)
+        ok = ok and all(isinstance(g, torch.Tensor) for g in gott) and all((g.numpy() == (w.view(np.uint8) if w.dtype == np.bool_ else w)).all() for g, w in zip(gott, want))
         q.put((rank, ok, [g.shape for g in got]))
     finally:
         dist.destroy_process_group()

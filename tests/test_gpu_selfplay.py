@@ -54,14 +54,16 @@ def play_injected(game, cfg, inits, u_full, u_move, seeds, noises):
     return ex, st
 
 
-def split_by_game(ex, first_boards, counts):
-    """The ring holds finished games back to back in finishing order: cut it into games by their first recorded board."""
+def split_by_game(ex, want_boards):
+    """The ring holds finished games back to back in finishing order: cut it into games by the boards each game must have recorded
+    (want_boards[g]: the canonical boards of game g's full-search plies; games may share a prefix, e.g. Abalone's fixed start)."""
     b, pi, z, va, q = ex
     out = {}; cur = 0
     while cur < len(b):
-        hit = [g for g in range(len(counts)) if g not in out and counts[g] > 0 and (b[cur].reshape(-1) == first_boards[g].reshape(-1)).all()]
-        assert hit, f'example {cur} starts no expected game'
-        g = hit[0]; k = counts[g]
+        hit = [g for g in range(len(want_boards)) if g not in out and len(want_boards[g]) > 0 and cur + len(want_boards[g]) <= len(b) and
+               (b[cur:cur + len(want_boards[g])].reshape(len(want_boards[g]), -1) == np.asarray(want_boards[g]).reshape(len(want_boards[g]), -1)).all()]
+        assert hit, f'the examples from {cur} on are no expected game'
+        g = hit[0]; k = len(want_boards[g])
         out[g] = dict(boards=b[cur:cur + k], pi=pi[cur:cur + k], z=z[cur:cur + k], valids=va[cur:cur + k], q=q[cur:cur + k])
         cur += k
     return out
@@ -74,8 +76,7 @@ def test_device_episode_matches_reference_examples(name):
     ex, st = play_injected(game, cfg, [g['init'] for g in games], [g['u_full'] for g in games], [g['u_move'] for g in games],
                            [g['chance_seed'] for g in games], [g['noise'] for g in games])
     assert st['episodes_finished'] == len(games) and st['arena_overflows'] == 0 and st['examples_dropped'] == 0 and st['gc_sweeps'] == 0
-    firsts = [g['root'][np.flatnonzero(g['is_full'])[0]] for g in games]
-    per_game = split_by_game(ex, firsts, [int(g['is_full'].sum()) for g in games])
+    per_game = split_by_game(ex, [g['root'][g['is_full']] for g in games])
     assert len(per_game) == len(games)
     for gi, gd in enumerate(games):
         assert_examples_equal(O.augment(gid, per_game[gi]), gd)                # oracle symmetries (pinned by test_oracle_*) on device examples
@@ -104,7 +105,7 @@ def test_device_episode_matches_oracle_on_seeded_inputs(name, n_slots, sims):
     ex, st = play_injected(game, cfg, list(inits), list(u_full), list(u_move), list(seeds), noises)
     assert st['episodes_finished'] == n_slots and st['arena_overflows'] == 0 and st['examples_dropped'] == 0 and st['gc_sweeps'] == 0
     assert len(ex[0]) == sum(len(w['boards']) for w in want)
-    per_game = split_by_game(ex, [w['boards'][0] if len(w['boards']) else None for w in want], [len(w['boards']) for w in want])
+    per_game = split_by_game(ex, [w['boards'] for w in want])
     for g, w in enumerate(want):
         if len(w['boards']) == 0:
             continue
