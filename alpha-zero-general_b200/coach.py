@@ -54,6 +54,30 @@ class Coach:
                 out.append((ob[i, k], op[i, k], zs[i], ov[i, k], [qs[i, p] for p in range(qs.shape[1])]))
         return out
 
+    # ---- on-disk history (Coach.py:220-262) ----
+    def saveTrainExamples(self):
+        from .formats import save_train_examples
+        return save_train_examples(self.trainExamplesHistory, self.args.checkpoint)
+
+    def loadTrainExamples(self, examples_file=None):
+        import os
+        from .formats import load_train_examples
+        path = examples_file or (os.path.dirname(self.args.load_folder_file) + '/checkpoint.examples')
+        self.trainExamplesHistory = load_train_examples(path, self.args.no_compression, self.args.get('numItersHistory'), self.args.maxlenOfQueue)
+        return self.trainExamplesHistory
+
+    # ---- accept gate (Coach.py:194-215) ----
+    def pit(self, new_nnet, prev_nnet, n_parallel=None):
+        """Arena of arenaCompare games between MCTS over the new net and MCTS over the previous one, every game in flight at once.
+        Returns (nwins, pwins, draws, accepted)."""
+        from .arena import EngineArena, accept_new_net
+        ar = EngineArena(self.game, new_nnet, prev_nnet, self.args, n_parallel=n_parallel or self.args.get('arenaCompare', 30))
+        try:
+            nwins, pwins, draws = ar.playGames(self.args.get('arenaCompare', 30))
+        finally:
+            ar.close()
+        return nwins, pwins, draws, accept_new_net(nwins, pwins, self.args.get('updateThreshold', 0.55))
+
     def executeEpisode(self):
         """One finished game's examples (Coach.py:37-84); uses slot-parallel play and returns the first game that ends."""
         return self.executeEpisodes(num_eps=1)

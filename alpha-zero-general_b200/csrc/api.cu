@@ -476,7 +476,10 @@ __global__ void k_load_roots(Dev<G> d, int n, const int8_t* roots, const uint8_t
     if (g >= d.n_games) return;
     if (g < n) {
         for (int i = lane; i < G::SP; i += 32) d.root[(size_t)g * G::SP + i] = i < G::S ? roots[(size_t)g * G::S + i] : (int8_t)0;
-        if (lane == 0) { const bool f = full ? full[g] != 0 : true; d.full[g] = f; d.n_sims[g] = f ? sims_full : sims_fast; d.root_node[g] = 0; }
+        if (lane == 0) {                                          // full[g]: 1 = full search, 0 = fast search (MCTS.py:58-59), 2 = no search for this slot
+            const uint8_t fv = full ? full[g] : (uint8_t)1; const bool f = fv == 1;
+            d.full[g] = f; d.n_sims[g] = fv >= 2 ? 0 : (f ? sims_full : sims_fast); d.root_node[g] = 0;
+        }
     } else if (lane == 0) d.n_sims[g] = 0;
 }
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -635,7 +638,11 @@ struct EngineT : azg_engine {
         d.noise = a[2].as<double>();
         // without host knowledge of the flags run the longer budget; finished games idle (k_select early-out)
         int steps = sims_full;
-        if (full_search && !is_device_ptr(full_search)) { bool any = false; for (int i = 0; i < n; i++) any |= full_search[i] != 0; if (!any) steps = sims_fast; }
+        if (full_search && !is_device_ptr(full_search)) {
+            bool any_full = false, any_fast = false;
+            for (int i = 0; i < n; i++) { any_full |= full_search[i] == 1; any_fast |= full_search[i] == 0; }
+            steps = any_full ? sims_full : (any_fast ? sims_fast : 0);
+        }
         gc(steps, st);
         for (int s = 0; s < steps; s++) if (step(s, st)) return 1;
         k_finish<G><<<(n + sel_warps<G>() - 1) / sel_warps<G>(), sel_warps<G>() * 32, 0, st>>>(d, n, a[3].as<int>(), a[4].as<int>(), a[5].as<float>());

@@ -223,8 +223,35 @@ class CudaNet:
             pass
 
 
-class NNetWrapper:
+class BatchedPredictMixin:
+    """predict_client / predict_server (GenericNNetWrapper.py:122-157): the reference's lock-chain protocol between N self-play
+    threads and one inference server, unchanged (same shared_memory slots, same lock hand-over), with the batch evaluated by
+    `self.predict_batch` (one azg_net_forward over the N boards) instead of an onnxruntime session. `Coach.executeEpisodes_batch`
+    threads of the reference can therefore run against this wrapper as they are."""
+
+    def predict_client(self, board, valid_actions, batch_info):
+        i_thread, i_result, shared_memory, locks = batch_info
+        shared_memory[i_thread] = (np.expand_dims(np.asarray(board), 0), np.expand_dims(np.array(valid_actions).astype(np.bool_), 0))
+        locks[i_thread + 1].release()                              # unblock the next thread (= next MCTS or the server) ...
+        locks[i_thread].acquire()                                  # ... and wait for our turn
+        pi, v = shared_memory[i_result]
+        return pi, v
+
+    def predict_server(self, nb_threads, shared_memory, locks):
+        locks[0].release()
+        while shared_memory[-1] <= 1:
+            locks[-1].acquire()                                    # all inputs are in
+            boards = np.concatenate([x[0] for x in shared_memory[:nb_threads]])
+            valids = np.concatenate([x[1] for x in shared_memory[:nb_threads]])
+            pi, v = self.predict_batch(boards, valids)
+            for i in range(nb_threads):
+                shared_memory[i + nb_threads] = (pi[i], v[i])
+            locks[0].release()                                     # unblock the first thread
+
+
+class NNetWrapper(BatchedPredictMixin):
     """splendor/NNet.py:NNetWrapper (inference surface). nn_args['nn_version'] must be 80."""
+    NN_VERSION = 80
 
     def __init__(self, game, nn_args=None, state_dict=None, seed=0):
         nn_args = dict(nn_args or {'nn_version': 80})
@@ -250,13 +277,28 @@ class NNetWrapper:
         self.state_dict = state_dict
         self.net.load(v80_blob(state_dict))
 
-    def load_checkpoint(self, folder, filename):
-        """Reads a reference checkpoint (torch.save dict with 'state_dict', GenericNNetWrapper.py:192-205)."""
+    def load_checkpoint(self, folder='checkpoint', filename='checkpoint.pth.tar'):
+        """GenericNNetWrapper.load_checkpoint (GenericNNetWrapper.py:207-221): reads a reference checkpoint (or one written by
+        save_checkpoint) and loads its state_dict into the device net. A missing file prints and returns None like the reference.
+        The reference's model classes are NOT imported (formats.load_checkpoint_file stubs them), only 'state_dict' is used."""
         import os
-        import torch
-        ck = torch.load(os.path.join(folder, filename), map_location='cpu', weights_only=False)
+        from .formats import load_checkpoint_file
+        path = os.path.join(folder, filename)
+        if not os.path.exists(path):
+            print('No model in path {}'.format(path))
+            return None
+        ck = load_checkpoint_file(path)
+        if ck.get('nn_version') is not None and self.args.get('nn_version', 0) > 0 and ck['nn_version'] != self.args['nn_version']:
+            print('Checkpoint includes NN version', ck['nn_version'], ', but you ask version', self.args['nn_version'], ' so not loading it and initiate knowledge transfer')
+            self.requestKnowledgeTransfer = True                   # GenericNNetWrapper.py:254-257
+            return None
         self.load_state_dict(ck['state_dict'])
         return ck
+
+    def save_checkpoint(self, folder='checkpoint', filename='checkpoint.pth.tar', additional_keys={}):
+        """GenericNNetWrapper.save_checkpoint (GenericNNetWrapper.py:192-205); readable by the reference's load_checkpoint."""
+        from .formats import save_checkpoint_file
+        return save_checkpoint_file(self.state_dict, self.args.get('nn_version', self.NN_VERSION), folder, filename, additional_keys)
 
     def train(self, examples):
         raise NotImplementedError('training is outside the self-play hot path (SURVEY.md section 8f-1)')
@@ -264,6 +306,7 @@ class NNetWrapper:
 
 class SantoriniNNetWrapper(NNetWrapper):
     """santorini/NNet.py:NNetWrapper (inference surface) for the no-god game. nn_args['nn_version'] must be 89."""
+    NN_VERSION = 89
 
     def __init__(self, game, nn_args=None, state_dict=None, seed=0):
         nn_args = dict(nn_args or {'nn_version': 89})
@@ -283,6 +326,7 @@ class SantoriniNNetWrapper(NNetWrapper):
 
 class AbaloneNNetWrapper(NNetWrapper):
     """abalone/NNet.py:NNetWrapper (inference surface). nn_args['nn_version'] must be 21."""
+    NN_VERSION = 21
 
     def __init__(self, game, nn_args=None, state_dict=None, seed=0):
         nn_args = dict(nn_args or {'nn_version': 21})

@@ -12,7 +12,8 @@ class dotdict(dict):
 # main.py:118-156 defaults of the reference for the knobs MCTS / Coach read
 DEFAULT_ARGS = dict(numMCTSSims=800, cpuct=1.25, fpu=0.0, universes=1, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1],
                     tempThreshold=10, prob_fullMCTS=0.25, ratio_fullMCTS=5, forced_playouts=False, no_mem_optim=False,
-                    no_compression=True, parallel_inferences=8, numEps=500, maxlenOfQueue=10 ** 9)
+                    no_compression=True, parallel_inferences=8, numEps=500, maxlenOfQueue=10 ** 9, arenaCompare=30, updateThreshold=0.55,
+                    numItersHistory=5, checkpoint='./temp/')
 
 
 def with_defaults(args):

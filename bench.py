@@ -252,6 +252,9 @@ def run_iteration(torch, dist, args, game, net, rank, world, dev, barrier, max_o
     first_game, _ = shard_games(n_games * world, rank, world)
     eng = Engine(game, net, a, n_games=n_games, dirichlet_noise=True, seed=2000, node_cap=8 * sims + 256, first_game=first_game)
     eng.selfplay(max_moves=2)                                                     # warm-up plies
+    warm = tuple(torch.zeros((4, 8), dtype=torch.uint8, device=dev) for _ in range(5))
+    for _ in range(2):
+        gather_examples(warm, dst=0)                                              # warm-up of the collective (NCCL opens its p2p channels lazily)
     s0 = eng.stats()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     stream = torch.cuda.current_stream()

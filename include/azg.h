@@ -119,8 +119,10 @@ int azg_engine_reset(azg_engine* e, int game);
 
 /* MCTS.getActionProb (MCTS.py:49-103) for games [0,n): n_sims simulations each from roots[i] (canonical
  * boards). Trees persist across calls (tree reuse) until azg_engine_reset.
- *   full_search  uint8[n] or NULL (=all full): selects numMCTSSims vs numMCTSSims/ratio, Dirichlet at sim 0,
- *                forced playouts and policy-target pruning exactly as MCTS.py:58-65,75-80.
+ *   full_search  uint8[n] or NULL (=all full): 1 selects numMCTSSims, 0 numMCTSSims/ratio; Dirichlet at sim 0,
+ *                forced playouts and policy-target pruning exactly as MCTS.py:58-65,75-80. 2 = no search for that slot this call
+ *                (its tree is kept, its outputs are whatever the tree already holds for the root, normally all zero): lets a
+ *                caller that owns several engines search each position with the engine whose turn it is (Arena.py:75-76).
  *   noise        float64[n][action_size] or NULL: injected Dirichlet draws (first L entries used, L = number
  *                of legal actions); NULL => drawn on device.
  *   out_counts   int32[n][action_size]  root Nsa after policy-target pruning (MCTS.py:75-80)

@@ -178,3 +178,26 @@ def test_nodes_data_view_matches_reference_root_arrays(mcts_cases):
         if done >= 6:
             break
     assert done >= 4
+
+
+def test_games_do_not_depend_on_the_sharding():
+    """per-game RNG keyed by the global slot id. One engine with 8 slots and two engines with 4 slots each
+    (first_game 0 and 4: what ranks 0 and 1 of a 2-GPU run would create) play the same games: same multiset of examples."""
+    game = azg_b200.SantoriniGame()
+    args = dict(numMCTSSims=16, cpuct=1.25, fpu=0.0, universes=1, dirichletAlpha=-1.0, prob_fullMCTS=0.5, ratio_fullMCTS=4)
+
+    def run(n, first):
+        eng = Engine(game, HashNetWrapper(game), args, n_games=n, dirichlet_noise=True, seed=77, node_cap=1024, first_game=first)
+        eng.selfplay(max_moves=90)
+        ex = eng.examples(n * game.info.max_game_len); st = eng.stats(); eng.close()
+        assert st['examples_dropped'] == 0 and st['arena_overflows'] == 0
+        return ex, st
+
+    def rows(ex):
+        return [ex[0][i].tobytes() + ex[1][i].tobytes() + ex[2][i].tobytes() + ex[3][i].tobytes() + ex[4][i].tobytes() for i in range(len(ex[0]))]
+
+    whole, st = run(8, 0)
+    a, sa = run(4, 0); b, sb = run(4, 4)
+    assert st['episodes_finished'] >= 8 and st['episodes_finished'] == sa['episodes_finished'] + sb['episodes_finished']
+    assert sorted(rows(whole)) == sorted(rows(a) + rows(b))
+    assert sorted(rows(a)) != sorted(rows(b))                    # and the two shards really play different games
