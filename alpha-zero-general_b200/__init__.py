@@ -9,10 +9,10 @@ All compute goes through the C ABI in include/azg.h (csrc/libazg_b200.so, hand-w
 There is no CPU fallback: importing works anywhere, computing needs the built library and a GPU.
 """
 from . import lib  # noqa: F401
-from .game import SplendorGame, SantoriniGame, AbaloneGame, CudaGame  # noqa: F401
-from .nnet import NNetWrapper, SantoriniNNetWrapper, AbaloneNNetWrapper, V80_TENSOR_ORDER, V89_TENSOR_ORDER, V21_TENSOR_ORDER  # noqa: F401
+from .game import SplendorGame, SantoriniGame, AbaloneGame, AzulGame, CudaGame  # noqa: F401
+from .nnet import NNetWrapper, SantoriniNNetWrapper, AbaloneNNetWrapper, AzulNNetWrapper, V84_TENSOR_ORDER, V80_TENSOR_ORDER, V89_TENSOR_ORDER, V21_TENSOR_ORDER  # noqa: F401
 from .mcts import MCTS  # noqa: F401
 from .coach import Coach  # noqa: F401
 from .utils import dotdict  # noqa: F401
 
-__all__ = ['lib', 'SplendorGame', 'SantoriniGame', 'AbaloneGame', 'CudaGame', 'NNetWrapper', 'SantoriniNNetWrapper', 'AbaloneNNetWrapper', 'MCTS', 'Coach', 'dotdict', 'V80_TENSOR_ORDER', 'V89_TENSOR_ORDER', 'V21_TENSOR_ORDER']
+__all__ = ['lib', 'SplendorGame', 'SantoriniGame', 'AbaloneGame', 'AzulGame', 'CudaGame', 'NNetWrapper', 'SantoriniNNetWrapper', 'AbaloneNNetWrapper', 'AzulNNetWrapper', 'V84_TENSOR_ORDER', 'MCTS', 'Coach', 'dotdict', 'V80_TENSOR_ORDER', 'V89_TENSOR_ORDER', 'V21_TENSOR_ORDER']

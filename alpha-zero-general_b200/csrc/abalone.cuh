@@ -37,6 +37,7 @@ struct Abalone {
         return r >= 0 && r < 9 && q >= 0 && q < 9 && at(b, r, q, 2) == 1;
     }
     static __device__ __forceinline__ int round(const int8_t* b) { return b[11]; }              // misc[0,2]
+    static __device__ __forceinline__ int progress(const int8_t* b) { return round(b); }           // grows with every move (tree GC, tree.cuh)
     static __device__ __forceinline__ int score(const int8_t* b, int player) { return player == 0 ? b[3] : b[7]; }
     static __device__ __forceinline__ void decode(int a, int& r, int& q, int& size, int& axis, int& d) {    // _decode_action :72-84
         const int plane = a % 42; q = (a / 42) % 9; r = a / 378; d = plane % 6;

@@ -16,6 +16,8 @@
 #include "net_v80_tc.cuh"
 #include "net_v21.cuh"
 #include "net_v89.cuh"
+#include "net_v84.cuh"
+#include "azul.cuh"
 #include "abalone.cuh"
 #include "santorini.cuh"
 #include "selfplay.cuh"
@@ -99,7 +101,8 @@ typedef Splendor<2> SP2;
         if ((game_id) == AZG_GAME_SPLENDOR && (np) == 2) { typedef Splendor<2> G; return CALL; }           \
         if ((game_id) == AZG_GAME_SANTORINI && (np) == 2) { typedef Santorini G; return CALL; }            \
         if ((game_id) == AZG_GAME_ABALONE && (np) == 2) { typedef Abalone G; return CALL; }                \
-        return fail("unknown game (built: 1 = splendor with 2 players, 2 = santorini without gods, 3 = abalone)"); \
+        if ((game_id) == AZG_GAME_AZUL && (np) == 2) { typedef Azul G; return CALL; }                      \
+        return fail("unknown game (built: 1 = splendor with 2 players, 2 = santorini without gods, 3 = abalone, 4 = azul with 2 players)"); \
     } while (0)
 
 template <class G> static int game_info_t(azg_game_info_t* out) {
@@ -315,9 +318,10 @@ struct azg_net {
     V80TCImg TI; float* img = nullptr;   // tensor-core operand images of the V80 token GEMMs (net_v80_tc.cuh)
     long long* prof = nullptr;            // optional phase timestamps of CTA 0 (AZG_V80_PROF=1; azg_net_prof)
     int v80_kernel = 1;                   // 1 = tcgen05 kernel (default), 0 = fp32 CUDA-core kernel (kept for A/B profiling; AZG_V80_KERNEL=fp32)
-    V89Layout L89; V89Chunks CK89; V21Layout L21;
+    V89Layout L89; V89Chunks CK89; V21Layout L21; V84Layout L84;
     Scratch masks;                        // packed masks for the standalone forward
     unsigned long long launches = 0;
+    bool attr_done = false; int n_sm = 0;  // launch attributes of this net's kernel on this net's device (set at the first launch)
 };
 __global__ void k_pack_masks(int n, int A, int MW, const uint8_t* mask, uint32_t* words) {
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -341,43 +345,46 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
     } else if (net->kind == AZG_NET_SPLENDOR_V80) {
         if constexpr (G::GAME_ID == AZG_GAME_SPLENDOR) {
             if (net->v80_kernel == 1) {
-                static bool attr_tc = false; static int n_sm = 0;
-                if (!attr_tc) {
+                if (!net->attr_done) {                             // function attributes and the SM count belong to the net's device: kept in the handle
                     CK(cudaFuncSetAttribute(k_v80_tc<G::NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-                    int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-                    attr_tc = true;
+                    int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&net->n_sm, cudaDevAttrMultiProcessorCount, dev));
+                    net->attr_done = true;
                 }
+                const int n_sm = net->n_sm;
                 if ((reinterpret_cast<uintptr_t>(boards) & 3) || (bstride & 3)) return fail("V80 forward: boards must be 4-byte aligned");
                 const int tiles = (n_max + TC_TB - 1) / TC_TB;
                 k_v80_tc<G::NP><<<std::min(tiles, n_sm), TC_THREADS, TC_SMEM, st>>>(
                     net->blob, net->img, net->L, net->TI, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max, net->prof);
             } else {
-            static bool attr_set = false;
             constexpr size_t smem = v80_smem_bytes<G::ROWS, V80_TB>();
-            if (!attr_set) { CK(cudaFuncSetAttribute(k_v80_forward<G::ROWS, G::NP, V80_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            if (!net->attr_done) { CK(cudaFuncSetAttribute(k_v80_forward<G::ROWS, G::NP, V80_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); net->attr_done = true; }
             k_v80_forward<G::ROWS, G::NP, V80_TB><<<(n_max + V80_TB - 1) / V80_TB, V80_THREADS, smem, st>>>(
                 net->blob, net->L, net->CK, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max);
             }
         } else return fail("SplendorNNet V80 only evaluates Splendor boards");
     } else if (net->kind == AZG_NET_SANTORINI_V89) {
         if constexpr (G::GAME_ID == AZG_GAME_SANTORINI) {
-            static bool attr_set89 = false;
             constexpr size_t smem = v89_smem_bytes();
-            if (!attr_set89) { CK(cudaFuncSetAttribute(k_v89_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set89 = true; }
+            if (!net->attr_done) { CK(cudaFuncSetAttribute(k_v89_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); net->attr_done = true; }
             k_v89_forward<<<(n_max + V89_TB - 1) / V89_TB, V89_THREADS, smem, st>>>(net->blob, net->L89, net->CK89, count_ptr, list, boards, bstride, masks, pi, v, n_max);
         } else return fail("SantoriniNNet V89 only evaluates Santorini boards");
     } else if (net->kind == AZG_NET_ABALONE_V21) {
         if constexpr (G::GAME_ID == AZG_GAME_ABALONE) {
-            static bool attr_set21 = false; static int n_sm21 = 0;
             static const size_t smem = v21_smem_bytes();
-            if (!attr_set21) {
+            if (!net->attr_done) {
                 CK(cudaFuncSetAttribute(k_v21_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&n_sm21, cudaDevAttrMultiProcessorCount, dev));
-                attr_set21 = true;
+                int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&net->n_sm, cudaDevAttrMultiProcessorCount, dev));
+                net->attr_done = true;
             }
-            const V21Plan plan = v21_plan(n_max, n_sm21);
+            const V21Plan plan = v21_plan(n_max, net->n_sm);
             k_v21_forward<<<plan.n_big + plan.n_small, V21_THREADS, smem, st>>>(net->blob, net->L21, count_ptr, list, boards, bstride, masks, pi, v, n_max, plan.n_big);
         } else return fail("AbaloneNNet V21 only evaluates Abalone boards");
+    } else if (net->kind == AZG_NET_AZUL_V84) {
+        if constexpr (G::GAME_ID == AZG_GAME_AZUL) {
+            constexpr size_t smem = v84_smem_bytes();
+            if (!net->attr_done) { CK(cudaFuncSetAttribute(k_v84_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); net->attr_done = true; }
+            k_v84_forward<<<(n_max + V84_TB - 1) / V84_TB, V84_THREADS, smem, st>>>(net->blob, net->L84, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+        } else return fail("AzulNNet V84 only evaluates Azul boards");
     } else return fail("net kind not built");
     net->launches++;
     CKL();
@@ -392,6 +399,15 @@ extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights
         std::vector<float> src(n_weights), dst((size_t)net->L21.total);
         CK(cudaMemcpy(src.data(), weights, n_weights * sizeof(float), cudaMemcpyDefault));
         v21_prepare(src.data(), net->L21, dst.data());
+        CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    if (net->kind == AZG_NET_AZUL_V84) {
+        const size_t need84 = v84_src_floats();
+        if (!weights || n_weights != need84) return fail("V84 weights: expected " + std::to_string(need84) + " floats, got " + std::to_string(n_weights));
+        std::vector<float> src(n_weights), dst((size_t)net->L84.total);
+        CK(cudaMemcpy(src.data(), weights, n_weights * sizeof(float), cudaMemcpyDefault));
+        v84_prepare(src.data(), net->L84, dst.data());
         CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
         return 0;
     }
@@ -420,8 +436,9 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     if (!out) return fail("out is NULL");
     azg_game_info_t gi;
     if (require_device() || azg_game_info(game_id, np, &gi)) return 1;
-    if (net_kind != AZG_NET_HASH && net_kind != AZG_NET_SPLENDOR_V80 && net_kind != AZG_NET_SANTORINI_V89 && net_kind != AZG_NET_ABALONE_V21)
-        return fail("unknown net kind (built: 0=hash test net, 80=Splendor V80, 89=Santorini V89, 21=Abalone V21)");
+    if (net_kind != AZG_NET_HASH && net_kind != AZG_NET_SPLENDOR_V80 && net_kind != AZG_NET_SANTORINI_V89 && net_kind != AZG_NET_ABALONE_V21 && net_kind != AZG_NET_AZUL_V84)
+        return fail("unknown net kind (built: 0=hash test net, 80=Splendor V80, 89=Santorini V89, 21=Abalone V21, 84=Azul V84)");
+    if (net_kind == AZG_NET_AZUL_V84 && game_id != AZG_GAME_AZUL) return fail("AzulNNet V84 only evaluates Azul boards");
     if (net_kind == AZG_NET_ABALONE_V21 && game_id != AZG_GAME_ABALONE) return fail("AbaloneNNet V21 only evaluates Abalone boards");
     if (net_kind == AZG_NET_SPLENDOR_V80 && game_id != AZG_GAME_SPLENDOR) return fail("SplendorNNet V80 only evaluates Splendor boards");
     if (net_kind == AZG_NET_SANTORINI_V89 && game_id != AZG_GAME_SANTORINI) return fail("SantoriniNNet V89 only evaluates Santorini boards");
@@ -438,6 +455,10 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     } else if (net_kind == AZG_NET_ABALONE_V21) {
         net->L21 = v21_layout();
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L21.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
+        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
+    } else if (net_kind == AZG_NET_AZUL_V84) {
+        net->L84 = v84_layout();
+        if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L84.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
         if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
     } else if (net_kind == AZG_NET_SANTORINI_V89) {
         net->L89 = v89_layout(); net->CK89 = v89_chunks(net->L89);

@@ -1,11 +1,9 @@
 // azul.cuh -- Azul for 2 players (azul/AzulLogicNumba.py) as __device__ code against the game-plugin interface of
 // splendor.cuh / santorini.cuh / abalone.cuh.
 //
-// STATUS: ROUND-2 DRAFT. NOT included by api.cu, not part of the library or of the C ABI, and it has never run on a GPU. It is
-// compiled for sm_100a by tests/host/azul_plugin_check.cu, and its rules are run ON THE HOST (lanes emulated one after the other,
-// tests/host/azul_plugin_emul.cpp) against the reference goldens by tests/test_oracle_azul.py; the warp glue (ballots) is unverified. The CPU oracle's Azul restatement (oracle/azg_oracle.c: azo_azul_*) is pinned
-// bit-exactly against the reference (tests/test_oracle_azul.py); this file follows that restatement function by function and has to
-// pass the same goldens through the C ABI before it is wired in.
+// The CPU oracle's Azul restatement (oracle/azg_oracle.c: azo_azul_*) is pinned bit-exactly against the reference
+// (tests/test_oracle_azul.py); this file follows it function by function and passes the same goldens through the C ABI
+// (tests/test_gpu_azul.py). The LANE functions also compile for the host (tests/host/azul_plugin_emul.cpp, AZG_HOST_EMUL).
 //
 // Board = the reference's int8[23][6] state, byte-compatible: row 0 scores (P0, P1, round), 1 bag, 2 discards, 3 centre (+ first-player
 // token in column 5), 4-8 factories, 9-10 pattern-line colours (-1 empty; column 5 = holds the token), 11-12 tiles per pattern line
@@ -13,7 +11,7 @@
 // WARP functions are called by all 32 lanes, LANE functions by one lane (caller brackets with __syncwarp()).
 #pragma once
 #ifndef AZG_HOST_EMUL                       // tests/host/azul_plugin_emul.cpp compiles the LANE functions for the host
-#include "../common.cuh"
+#include "common.cuh"
 #endif
 
 namespace azg {
@@ -43,6 +41,13 @@ struct Azul {
     static __device__ __forceinline__ bool is_chance_move(int) { return true; }
     static __device__ __forceinline__ int round(const int8_t* b) { return at(b, 0, 2); }                   // get_round :333-334
     static __device__ __forceinline__ int score(const int8_t* b, int player) { return at(b, 0, player); } // get_score :83-84
+    // A counter that grows with EVERY move (tree GC, tree.cuh): the round counter only moves once per round, but every move takes at
+    // least one tile off the table (factories + centre), and a new round (<= 20 tiles dealt) outweighs a full round of takes.
+    static __device__ __forceinline__ int progress(const int8_t* b) {
+        int on_table = 0;
+        for (int r = 3; r < 9; r++) for (int c = 0; c < 5; c++) on_table += at(b, r, c);
+        return round(b) * 21 + (20 - min(on_table, 20));
+    }
 
     // One action's legality (valid_moves :97-124).
     static __device__ bool action_valid(const int8_t* b, int a, int player) {

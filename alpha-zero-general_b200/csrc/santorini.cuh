@@ -40,6 +40,7 @@ struct Santorini {
 
     static __device__ __forceinline__ bool is_chance_move(int) { return false; }   // no chance in this game
     static __device__ __forceinline__ int round(const int8_t* b) { return gp(b, 2); }        // get_round :655-656
+    static __device__ __forceinline__ int progress(const int8_t* b) { return round(b); }           // grows with every move (tree GC, tree.cuh)
     // get_score :87-101: highest level under one of the player's workers
     static __device__ int score(const int8_t* b, int player) {
         int best = 0;

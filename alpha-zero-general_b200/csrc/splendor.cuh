@@ -68,6 +68,7 @@ struct Splendor {
 
     // get_round (SplendorLogicNumba.py:303-304)
     static __device__ __forceinline__ int round(const int8_t* b) { return (uint8_t)b[6]; }
+    static __device__ __forceinline__ int progress(const int8_t* b) { return round(b); }           // grows with every move (tree GC, tree.cuh)
     // get_score (SplendorLogicNumba.py:151-154)
     static __device__ int score(const int8_t* b, int player) {
         int s = row(b, R_PCARDS + player)[6];

@@ -37,7 +37,7 @@ struct __align__(16) NodeHdr {
     double c1;                                                 // cpuct*sqrt(Ns): PUCT constant, refreshed by the backup
     int ns; float qs;
     uint32_t edge_off; uint16_t n_legal; uint8_t round; uint8_t kind;
-    uint16_t best; uint16_t rsv0; uint32_t rsv1;               // best: edge (index within the node) the next non-root visit takes; refreshed
+    uint16_t best; uint16_t prog; uint32_t rsv1;               // prog: G::progress of the node's state (tree GC); best: edge (index within the node) the next non-root visit takes; refreshed
 };                                                             //       by the backup whenever the node's statistics change
 struct __align__(16) NodeKey { uint64_t lo, hi; };             // 128-bit board hash of the node (hash-table verification, GC)
 static_assert(sizeof(Edge) == 16 && sizeof(NodeHdr) == 32 && sizeof(NodeKey) == 16, "layout");
@@ -471,7 +471,7 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, SelSmem<G>& ws, uin
         warp_store_board<G>(d.nn_in + (size_t)g * G::SP, sb, lane);
         if (lane == 0) { int pos = atomicAdd(d.nn_count, 1); d.nn_list[pos] = g; }
     }
-    if (lane == 0) { d.leaf_key[2 * (size_t)g] = ws.key[0]; d.leaf_key[2 * (size_t)g + 1] = ws.key[1]; d.leaf_round[g] = G::round(sb); d.leaf_link[g] = link_slot; }
+    if (lane == 0) { d.leaf_key[2 * (size_t)g] = ws.key[0]; d.leaf_key[2 * (size_t)g + 1] = ws.key[1]; d.leaf_round[g] = (G::round(sb) & 0xFF) | (G::progress(sb) << 8); d.leaf_link[g] = link_slot; }
     return kind;
 }
 
@@ -695,7 +695,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
                 else d.root_node[g] = ni + 1;
                 NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
                 NodeHdr h; h.c1 = 0.0; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
-                h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_EXPANDED; h.best = (uint16_t)nb; h.rsv0 = 0; h.rsv1 = 0;
+                h.round = (uint8_t)d.leaf_round[g]; h.prog = (uint16_t)(d.leaf_round[g] >> 8); h.kind = NODE_EXPANDED; h.best = (uint16_t)nb; h.rsv1 = 0;
                 nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + L;
                 st[ST_EXPANSIONS]++; st[ST_NNEVALS]++; st[ST_SUMLEGAL] += (unsigned)L;
                 if ((unsigned long long)(ni + 1) > st[ST_MAXNODES]) st[ST_MAXNODES] = (unsigned long long)(ni + 1);
@@ -718,7 +718,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
                     for (int p = 0; p < 4; p++) es[p] = p < NP ? v[p] : 0.f;
                     NodeKey nk; nk.lo = klo; nk.hi = khi; d.g_keys(g)[ni] = nk;
                     NodeHdr h; h.c1 = 0.0; h.ns = 0; h.qs = 0.f; h.edge_off = (uint32_t)eo; h.n_legal = 0;
-                    h.round = (uint8_t)d.leaf_round[g]; h.kind = NODE_TERMINAL; h.best = 0; h.rsv0 = 0; h.rsv1 = 0;
+                    h.round = (uint8_t)d.leaf_round[g]; h.prog = (uint16_t)(d.leaf_round[g] >> 8); h.kind = NODE_TERMINAL; h.best = 0; h.rsv1 = 0;
                     nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + 1;
                 }
                 ht_insert(d.g_ht(g), d.ht_cap, klo, khi, ni, lane);
@@ -879,9 +879,10 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_node_query(Dev<G> d, in
 
 // ============================================================ tree GC ==================================
 // Runs only when the arena could not hold another `need_nodes` / `need_edges`. Two tiers:
-//   tier 1 (exact): drop every node whose round is <= the new root's round and that is not the root itself (the
-//          round counter is part of the key and grows with every move, so such a node can never be looked up
-//          again). This is the reference's cleaning (MCTS.py:86-91, nodes with round < r-5) made tight; both are
+//   tier 1 (exact): drop every node whose progress is <= the new root's progress and that is not the root itself.
+//          G::progress(board) is part of the key and grows with EVERY move (the round counter for Splendor /
+//          Santorini / Abalone; round * 21 + tiles taken off the table this round for Azul, whose round counter
+//          only moves once per round), so such a node can never be looked up again. This is the reference's cleaning (MCTS.py:86-91, nodes with round < r-5) made tight; both are
 //          semantic no-ops.
 //   tier 2 (memory pressure only, counted in ST_GC_SWEEP): if tier 1 would not free enough, keep only what is
 //          reachable from the new root through resolved child links (breadth-first mark). The reference has
@@ -900,7 +901,7 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_n
     int8_t* sb = sm[w].board;
     warp_load_board<G>(sb, d.root + (size_t)g * G::SP, lane);
     uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
-    const int r = G::round(sb), U = d.U;
+    const int r = G::progress(sb), U = d.U;
     NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g); uint64_t* ht = d.g_ht(g);
     uint32_t* child = d.g_child(g); int8_t* boards = d.g_boards(g); int* remap = d.remap + (size_t)g * d.node_cap;
     // ---- would tier 1 free enough?
@@ -908,7 +909,7 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_n
     NodeKey* keys = d.g_keys(g);
     for (int i = lane; i < nn; i += 32) {
         const NodeHdr h = nodes[i]; const NodeKey k = keys[i];
-        if ((int)h.round > r || (k.lo == klo && k.hi == khi)) { kn1++; ke1 += h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal; }
+        if ((int)h.prog > r || (k.lo == klo && k.hi == khi)) { kn1++; ke1 += h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal; }
     }
     kn1 = warp_sum_i32(kn1); ke1 = warp_sum_i32(ke1);
     const bool sweep = force != 1 && (force == 2 || kn1 + need_nodes > d.node_cap || ke1 + need_edges > d.edge_cap);
@@ -942,10 +943,10 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_n
     int wn = 0, we = 0;                                          // write cursors
     for (int base = 0; base < nn; base += 32) {
         const int i = base + lane;
-        NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.c1 = 0; h.ns = 0; h.qs = 0; h.best = 0; h.rsv0 = 0; h.rsv1 = 0;
+        NodeHdr h; h.kind = 0; h.n_legal = 0; h.edge_off = 0; h.round = 0; h.c1 = 0; h.ns = 0; h.qs = 0; h.best = 0; h.prog = 0; h.rsv1 = 0;
         NodeKey nk; nk.lo = nk.hi = 0;
         bool keep = false;
-        if (i < nn) { h = nodes[i]; nk = keys[i]; keep = sweep ? remap[i] == -1 : ((int)h.round > r || (nk.lo == klo && nk.hi == khi)); }
+        if (i < nn) { h = nodes[i]; nk = keys[i]; keep = sweep ? remap[i] == -1 : ((int)h.prog > r || (nk.lo == klo && nk.hi == khi)); }
         const int len = keep ? (h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal) : 0;
         const unsigned km = __ballot_sync(FULL, keep);
         int pre = len;                                           // inclusive prefix sum of edge counts

@@ -200,3 +200,18 @@ class AbaloneGame(CudaGame):
             return f'marble ({r},{q}) moves {dirs[plane]}'
         size, axis = (2, (plane - 6) // 6) if plane < 24 else (3, (plane - 24) // 6)
         return f'{size} marbles from ({r},{q}) along {dirs[axis]} move {dirs[plane % 6]}'
+
+
+class AzulGame(CudaGame):
+    """Drop-in for azul/AzulGame.py:AzulGame (2 players): int8[23,6] boards, 180 actions = 30 source + 6 colour + line
+    (source 0 = centre, 1-5 = factories; line 5 = floor), azul/AzulLogicNumba.py:27-48."""
+
+    game_id = _lib.AZG_GAME_AZUL
+    max_score_diff = 50
+
+    def __init__(self):
+        super().__init__(2)
+
+    def moveToString(self, move, current_player):
+        src, colour, line = move // 30, (move % 30) // 6, move % 6
+        return f'take colour {colour} from {"the centre" if src == 0 else f"factory {src}"} to {"the floor" if line == 5 else f"line {line + 1}"}'

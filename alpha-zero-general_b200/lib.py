@@ -12,12 +12,14 @@ SO_PATH = os.path.join(CSRC, 'libazg_b200.so')
 AZG_GAME_SPLENDOR = 1
 AZG_GAME_SANTORINI = 2
 AZG_GAME_ABALONE = 3
+AZG_GAME_AZUL = 4
 AZG_ABI_VERSION = 4
 AZG_N_STATS = 20
 AZG_NET_HASH = 0
 AZG_NET_SPLENDOR_V80 = 80
 AZG_NET_SANTORINI_V89 = 89
 AZG_NET_ABALONE_V21 = 21
+AZG_NET_AZUL_V84 = 84
 
 # every symbol include/azg.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['azg_abi_version', 'azg_last_error', 'azg_device_count', 'azg_set_device', 'azg_engine_profile', 'azg_engine_kernel_times', 'azg_game_info', 'azg_game_init', 'azg_game_valid',

@@ -188,6 +188,48 @@ def random_v21_state_dict(seed=0):
     return sd
 
 
+# AzulNNet V84 (azul/AzulNNet.py:84-111) uses SplendorNNet V80's module names: same tensor order, different shapes.
+V84_TENSOR_ORDER = _v80_order()
+V84_BLOCKS = (('trunk.0', 23, 115, 23, 32), ('output_layers_PI.0', 23, 115, 46, 32), ('output_layers_V.0', 23, 46, 23, 16))   # name, in, E, out, Q
+
+
+def v84_blob(state_dict):
+    parts = []
+    for n in V84_TENSOR_ORDER:
+        t = state_dict[n]
+        if hasattr(t, 'detach'):
+            t = t.detach().cpu().numpy()
+        parts.append(np.asarray(t, dtype=np.float32).ravel())
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+def random_v84_state_dict(seed=0):
+    """Random-init V84 weights from numpy as a freshly constructed reference net has them (PyTorch-default Linears, default
+    BatchNorm; see random_v80_state_dict)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def lin(name, out, inn, bias):
+        b = 1.0 / np.sqrt(inn)
+        sd[f'{name}.weight'] = rng.uniform(-b, b, size=(out, inn)).astype(np.float32)
+        if bias:
+            sd[f'{name}.bias'] = rng.uniform(-b, b, size=out).astype(np.float32)
+
+    def bn(prefix, ch):
+        sd[f'{prefix}.weight'] = np.ones(ch, np.float32); sd[f'{prefix}.bias'] = np.zeros(ch, np.float32)
+        sd[f'{prefix}.running_mean'] = np.zeros(ch, np.float32); sd[f'{prefix}.running_var'] = np.ones(ch, np.float32)
+
+    lin('first_layer.linear', 23, 23, False); bn('first_layer.norm', 23)
+    for name, inn, E, out, Q in V84_BLOCKS:
+        lin(f'{name}.expand.linear', E, inn, False); bn(f'{name}.expand.norm', E)
+        lin(f'{name}.depthwise.linear', 6, 6, False); bn(f'{name}.depthwise.norm', E)
+        lin(f'{name}.se.fc1', Q, E, True); lin(f'{name}.se.fc2', E, Q, True)
+        lin(f'{name}.project.linear', out, E, False); bn(f'{name}.project.norm', out)
+    lin('output_layers_PI.2', 180, 276, True); lin('output_layers_PI.4', 180, 180, True)
+    lin('output_layers_V.2', 2, 138, True); lin('output_layers_V.4', 2, 2, True)
+    return sd
+
+
 class CudaNet:
     """Owns an azg_net handle."""
 
@@ -342,6 +384,26 @@ class AbaloneNNetWrapper(NNetWrapper):
     def load_state_dict(self, state_dict):
         self.state_dict = state_dict
         self.net.load(v21_blob(state_dict))
+
+
+class AzulNNetWrapper(NNetWrapper):
+    """azul/NNet.py:NNetWrapper (inference surface). nn_args['nn_version'] must be 84 (the shipped 2-player net)."""
+    NN_VERSION = 84
+
+    def __init__(self, game, nn_args=None, state_dict=None, seed=0):
+        nn_args = dict(nn_args or {'nn_version': 84})
+        if nn_args.get('nn_version', 84) != 84:
+            raise NotImplementedError('only AzulNNet version 84 is built (the shipped 2-player checkpoint)')
+        self.args = nn_args
+        self.game = game
+        self.board_size = game.getBoardSize(); self.action_size = game.getActionSize(); self.num_players = game.num_players
+        self.requestKnowledgeTransfer = False
+        self.state_dict = state_dict if state_dict is not None else random_v84_state_dict(seed)
+        self.net = CudaNet(_lib.AZG_NET_AZUL_V84, game, v84_blob(self.state_dict))
+
+    def load_state_dict(self, state_dict):
+        self.state_dict = state_dict
+        self.net.load(v84_blob(state_dict))
 
 
 class HashNetWrapper:

@@ -47,6 +47,7 @@ GAMES = {
                       tag='santorini_nogods'),
     'abalone': dict(S=324, A=3402, flops=2 * 1050360, games=2048, universes=1, net='AbaloneNNet V21 (35862 params, random init seed 0)',
                     tag='abalone_belgian_daisy', sims=1600),
+    'azul': dict(S=138, A=180, flops=2 * 203708, games=16384, universes=2, net='AzulNNet V84 (118 k params, random init seed 0)', tag='azul2p_universes2'),
 }
 
 
@@ -56,7 +57,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--game', default='splendor', choices=sorted(GAMES), help='splendor = BASELINE.json configs[2] (headline metric), santorini = configs[1], abalone = configs[4] (2048 games per GPU)')
+    ap.add_argument('--game', default='splendor', choices=sorted(GAMES), help='splendor = BASELINE.json configs[2] (headline metric), santorini = configs[1], abalone = configs[4] (2048 games per GPU), azul = the first SURVEY 8f game')
     ap.add_argument('--games', type=int, default=0, help='concurrent games per GPU (0 = the config default: 16384 splendor / 4096 santorini / 2048 abalone)')
     ap.add_argument('--sims', type=int, default=0, help='numMCTSSims (0 = the config default: 800, abalone 1600)')
     ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 6 x sims + 320)')
@@ -69,7 +70,7 @@ def parse():
     a = ap.parse_args()
     a.games = a.games or GAMES[a.game]['games']
     a.sims = a.sims or GAMES[a.game].get('sims', 800)
-    a.cpu_plies = a.cpu_plies or {'splendor': 12, 'santorini': 1, 'abalone': 2}[a.game]
+    a.cpu_plies = a.cpu_plies or {'splendor': 12, 'santorini': 1, 'abalone': 2, 'azul': 12}[a.game]
     return a
 
 
@@ -131,13 +132,13 @@ def cpu_sample(sims, plies, threads, seed=1, game='splendor'):
     """Oracle port of Coach.executeEpisode / MCTS.search / the game's Board / the net forward on `threads` host threads,
     each playing one self-play game truncated after `plies` plies. Returns the oracle's counters."""
     from oracle import oracle as O
-    from azg_b200.nnet import random_v80_state_dict, random_v89_state_dict, random_v21_state_dict
-    kind = {'splendor': 1, 'santorini': 2, 'abalone': 3}[game]; gid = {'splendor': O.GAME_SPLENDOR, 'santorini': O.GAME_SANTORINI, 'abalone': O.GAME_ABALONE}[game]
+    from azg_b200.nnet import random_v80_state_dict, random_v89_state_dict, random_v21_state_dict, random_v84_state_dict
+    kind = {'splendor': 1, 'santorini': 2, 'abalone': 3, 'azul': 4}[game]; gid = {'splendor': O.GAME_SPLENDOR, 'santorini': O.GAME_SANTORINI, 'abalone': O.GAME_ABALONE, 'azul': O.GAME_AZUL}[game]
     a = mcts_args(sims, game)
     cfg = O.make_cfg(numMCTSSims=sims, net_kind=kind, universes=a['universes'], prob_fullMCTS=1.0, cpuct=a['cpuct'], fpu=a['fpu'],
                      dirichletAlpha=a['dirichletAlpha'], temperature2=a['temperature'][2], game=gid)
     blob = {'splendor': lambda: O.v80_blob(random_v80_state_dict(0)), 'santorini': lambda: O.v89_blob(random_v89_state_dict(0)),
-            'abalone': lambda: O.v21_blob(random_v21_state_dict(0))}[game]()
+            'abalone': lambda: O.v21_blob(random_v21_state_dict(0)), 'azul': lambda: O.v84_blob(random_v84_state_dict(0))}[game]()
     return O.selfplay_bench(cfg, blob, threads, 1, max_plies=plies, temperature=a['temperature'][:2], tempThreshold=a['tempThreshold'], seed=seed)
 
 
@@ -346,6 +347,8 @@ def main():
         game = azg_b200.SplendorGame(); net = azg_b200.NNetWrapper(game, {'nn_version': 80}, seed=0)      # identical weights on every rank
     elif args.game == 'santorini':
         game = azg_b200.SantoriniGame(); net = azg_b200.SantoriniNNetWrapper(game, {'nn_version': 89}, seed=0)
+    elif args.game == 'azul':
+        game = azg_b200.AzulGame(); net = azg_b200.AzulNNetWrapper(game, {'nn_version': 84}, seed=0)
     else:
         game = azg_b200.AbaloneGame(); net = azg_b200.AbaloneNNetWrapper(game, {'nn_version': 21}, seed=0)
     S_BYTES, N_ACT = gm['S'], gm['A']

@@ -32,11 +32,13 @@ extern "C" {
 
 enum { AZG_GAME_SPLENDOR = 1,                            /* GameSwitcher.py:3-13 ('splendor'), 2 players            */
        AZG_GAME_SANTORINI = 2,                           /* 'santorini' built with NB_GODS = 1 (SantoriniConstants.py:19) */
-       AZG_GAME_ABALONE = 3 };                           /* 'abalone', Belgian daisy start (AbaloneLogicNumba.py:5-6)      */
+       AZG_GAME_ABALONE = 3,                             /* 'abalone', Belgian daisy start (AbaloneLogicNumba.py:5-6)      */
+       AZG_GAME_AZUL = 4 };                              /* 'azul', 2 players (azul/AzulLogicNumba.py)                     */
 enum { AZG_NET_HASH = 0,                                 /* deterministic test net (tests only)                       */
        AZG_NET_SPLENDOR_V80 = 80,                        /* splendor/SplendorNNet.py version 80 (shipped 2-player net) */
        AZG_NET_SANTORINI_V89 = 89,                       /* santorini/SantoriniNNet.py version 89 (shipped no-god net) */
-       AZG_NET_ABALONE_V21 = 21 };                       /* abalone/AbaloneNNet.py version 21 (shipped Belgian-daisy net) */
+       AZG_NET_ABALONE_V21 = 21,                         /* abalone/AbaloneNNet.py version 21 (shipped Belgian-daisy net) */
+       AZG_NET_AZUL_V84 = 84 };                          /* azul/AzulNNet.py version 84 (shipped 2-player net)            */
 
 typedef struct {
     int32_t game_id, num_players;
@@ -84,7 +86,7 @@ int azg_game_symmetries(int game_id, int num_players, int n, const int8_t* board
 /* ---- policy/value net: GenericNNetWrapper.predict / predict_server (GenericNNetWrapper.py:94-157) ---- */
 typedef struct azg_net azg_net;
 /* weights: float32 blob = the net's state_dict tensors concatenated in the order documented in
- * alpha-zero-general_b200/nnet.py (V80_TENSOR_ORDER / V89_TENSOR_ORDER / V21_TENSOR_ORDER); host or device pointer. NULL for AZG_NET_HASH. */
+ * alpha-zero-general_b200/nnet.py (V80_TENSOR_ORDER / V89_TENSOR_ORDER / V21_TENSOR_ORDER / V84_TENSOR_ORDER); host or device pointer. NULL for AZG_NET_HASH. */
 int azg_net_create(int net_kind, int game_id, int num_players, const float* weights, size_t n_weights, azg_net** out);
 int azg_net_load(azg_net* net, const float* weights, size_t n_weights);      /* new weights, same architecture */
 /* pi = softmax over legal actions (what predict returns after np.exp), v = tanh value vector. */

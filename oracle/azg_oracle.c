@@ -1145,7 +1145,7 @@ void azo_v21_forward(const float* blob, int batch, const i8* boards, const u8* v
 static const int64_t MAGIC_SEEDS[8] = {31416, 1, 14142, 42, 27183, 2, 16180, 7};   /* MCTS.py:14 */
 
 typedef struct {
-    int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80,2 v89,3 v21*/;
+    int num_players, numMCTSSims, ratio_fullMCTS, universes, forced_playouts, no_mem_optim, net_kind /*0 hash,1 v80,2 v89,3 v21,4 v84*/;
     double cpuct, fpu, dirichletAlpha, prob_fullMCTS, temperature2;
     int game /*0 splendor, 1 santorini without gods, 2 abalone*/;
 } azo_cfg;
@@ -1158,7 +1158,7 @@ typedef struct node {
 } node_t;
 
 typedef struct {
-    azo_cfg cfg; int S, A; v80_net net; v89_net net89; v21_net net21; const float* blob;
+    azo_cfg cfg; int S, A; v80_net net; v89_net net89; v21_net net21; v84_net net84; const float* blob;
     node_t* nodes; int* table; int cap, tcap, count;
     u8* sVs; float* sPs; double* sQsa; int64_t* sNsa;        /* [cap][A] slabs */
     int dirichlet_noise, step, last_cleaning; int64_t random_seed;
@@ -1208,6 +1208,7 @@ azo_mcts* azo_mcts_new(const azo_cfg* cfg, const float* blob, int dirichlet_nois
     if (cfg->net_kind == 1) v80_bind(&m->net, blob, azo_state_rows(cfg->num_players), cfg->num_players);
     if (cfg->net_kind == 2) v89_bind(&m->net89, blob);
     if (cfg->net_kind == 3) v21_bind(&m->net21, blob);
+    if (cfg->net_kind == 4) v84_bind(&m->net84, blob);
     m->cap = m->A > 1000 ? 512 : 4096; m->tcap = 4 * m->cap; m->nodes = (node_t*)malloc(sizeof(node_t) * (size_t)m->cap); m->table = (int*)malloc(sizeof(int) * (size_t)m->tcap);
     slabs_alloc(m);
     m->count = 0; table_rebuild(m); m->dirichlet_noise = dirichlet_noise; m->random_seed = -1; rng_seed(&m->rng, seed); m->inj_u_full = -1.0;
@@ -1323,6 +1324,7 @@ static void search(azo_mcts* m, const i8* root, int dir_noise, int forced, const
             if (m->cfg.net_kind == 0) azo_hashnet_a(cur, S, Vs, A, n, Ps, v);
             else if (m->cfg.net_kind == 2) v89_forward(&m->net89, cur, Vs, Ps, v);
             else if (m->cfg.net_kind == 3) v21_forward(&m->net21, cur, Vs, Ps, v);
+            else if (m->cfg.net_kind == 4) v84_forward(&m->net84, cur, Vs, Ps, v);
             else v80_forward(&m->net, cur, Vs, Ps, v);
             m->n_nn_evals++; m->n_expansions++;
             if (depth == 0 && dir_noise) { softmax_temp(Ps, A, m->cfg.temperature2); apply_dir_noise(m, Ps, Vs, noise); }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Golden fixtures for Coach.executeEpisode (Coach.py:37-84) by RUNNING THE REFERENCE'S OWN executeEpisode (test infrastructure).
 
-    python oracle/gen_golden_selfplay.py [--out tests/golden] [--only splendor,santorini,abalone]
+    python oracle/gen_golden_selfplay.py [--out tests/golden] [--only splendor,santorini,abalone,azul]
 
 The reference's `Coach.executeEpisode(my_mcts, my_game)` runs UNMODIFIED. Every random input it consumes is recorded so that the
 oracle and the CUDA engine can replay the same episode and must return the same training examples, example for example:
@@ -31,7 +31,9 @@ CONFIGS = {
     'abalone': dict(numMCTSSims=40, cpuct=1.25, fpu=0.2, universes=1, dirichletAlpha=-1.0, temperature=[1.0, 0.3, 1.0], tempThreshold=-20,
                     forced_playouts=False, prob_fullMCTS=0.3, ratio_fullMCTS=4, no_mem_optim=False, no_compression=True),
 }
-N_GAMES = {'splendor': 3, 'santorini': 4, 'abalone': 2}
+CONFIGS['azul'] = dict(numMCTSSims=50, cpuct=1.0, fpu=0.1, universes=2, dirichletAlpha=0.5, temperature=[1.0, 0.4, 1.2], tempThreshold=6,
+                       forced_playouts=True, prob_fullMCTS=0.5, ratio_fullMCTS=5, no_mem_optim=False, no_compression=True)
+N_GAMES = {'splendor': 3, 'santorini': 4, 'abalone': 2, 'azul': 3}
 
 
 def setup_paths(game):
@@ -56,6 +58,8 @@ def run(game, out):
         from splendor.SplendorGame import SplendorGame as Game
     elif game == 'santorini':
         from santorini.SantoriniGame import SantoriniGame as Game
+    elif game == 'azul':
+        from azul.AzulGame import AzulGame as Game
     else:
         from abalone.AbaloneGame import AbaloneGame as Game
 
@@ -138,7 +142,7 @@ def run(game, out):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(os.path.dirname(HERE), 'tests', 'golden'))
-    ap.add_argument('--only', default='splendor,santorini,abalone')
+    ap.add_argument('--only', default='splendor,santorini,abalone,azul')
     a = ap.parse_args()
     games = a.only.split(',')
     if len(games) > 1:                                                           # one process per game: the patched santorini import must not leak

@@ -1,4 +1,4 @@
-// Host emulation of the round-2 draft plugin csrc/next/azul.cuh: the CUDA qualifiers are defined away and the 32 lanes of a warp
+// Host emulation of the Azul plugin csrc/azul.cuh: the CUDA qualifiers are defined away and the 32 lanes of a warp
 // function are run one after the other (none of the emulated functions exchanges data between lanes), so the device rules can be
 // checked against the reference goldens without a GPU. Test infrastructure; built by tests/test_oracle_azul.py with g++.
 #include <algorithm>
@@ -15,7 +15,7 @@ struct Philox { uint64_t s; float uniformf() { s = s * 6364136223846793005ULL + 
 static inline unsigned __ballot_sync(unsigned, bool) { return 0u; }     // valid_mask is not emulated (action_valid is called per action instead)
 static inline void __syncwarp() {}
 }  // namespace azg
-#include "../../alpha-zero-general_b200/csrc/next/azul.cuh"
+#include "../../alpha-zero-general_b200/csrc/azul.cuh"
 using azg::Azul;
 
 extern "C" {

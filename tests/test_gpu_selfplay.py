@@ -17,7 +17,7 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 GAMES = {'splendor': (azg_b200.SplendorGame, O.GAME_SPLENDOR), 'santorini': (azg_b200.SantoriniGame, O.GAME_SANTORINI),
-         'abalone': (azg_b200.AbaloneGame, O.GAME_ABALONE)}
+         'abalone': (azg_b200.AbaloneGame, O.GAME_ABALONE), 'azul': (azg_b200.AzulGame, O.GAME_AZUL)}
 
 
 def engine_args(cfg):
@@ -69,7 +69,7 @@ def split_by_game(ex, want_boards):
     return out
 
 
-@pytest.mark.parametrize('name', ['splendor', 'santorini', 'abalone'])
+@pytest.mark.parametrize('name', ['splendor', 'santorini', 'abalone', 'azul'])
 def test_device_episode_matches_reference_examples(name):
     cls, gid = GAMES[name]; game = cls()
     cfg, games = load_selfplay_golden(name)
@@ -86,11 +86,11 @@ def test_device_episode_matches_reference_examples(name):
     assert_examples_equal(c.augment(e0['boards'], e0['pi'], e0['z'], e0['valids'], e0['q']), games[0])
 
 
-@pytest.mark.parametrize('name,n_slots,sims', [('splendor', 12, 40), ('santorini', 16, 64), ('abalone', 5, 32)])
+@pytest.mark.parametrize('name,n_slots,sims', [('splendor', 12, 40), ('santorini', 16, 64), ('abalone', 5, 32), ('azul', 10, 40)])
 def test_device_episode_matches_oracle_on_seeded_inputs(name, n_slots, sims):
     cls, gid = GAMES[name]; game = cls()
     rng = np.random.default_rng(20260 + n_slots)
-    cfg = dict(numMCTSSims=sims, cpuct=1.1, fpu=0.1, universes=2 if name == 'splendor' else 1, dirichletAlpha=0.4, temperature=[1.0, 0.2, 1.05],
+    cfg = dict(numMCTSSims=sims, cpuct=1.1, fpu=0.1, universes=2 if name in ('splendor', 'azul') else 1, dirichletAlpha=0.4, temperature=[1.0, 0.2, 1.05],
                tempThreshold=8, forced_playouts=(name != 'abalone'), prob_fullMCTS=0.5, ratio_fullMCTS=4)
     P = game.info.max_game_len
     inits = game.init_batch(np.arange(1, n_slots + 1, dtype=np.uint64) * 7919)

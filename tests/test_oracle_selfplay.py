@@ -7,7 +7,7 @@ import pytest
 from conftest import assert_examples_equal, load_selfplay_golden
 from oracle import oracle as O
 
-GAME_IDS = {'splendor': O.GAME_SPLENDOR, 'santorini': O.GAME_SANTORINI, 'abalone': O.GAME_ABALONE}
+GAME_IDS = {'splendor': O.GAME_SPLENDOR, 'santorini': O.GAME_SANTORINI, 'abalone': O.GAME_ABALONE, 'azul': O.GAME_AZUL}
 
 
 def oracle_cfg(game, cfg):
@@ -16,7 +16,7 @@ def oracle_cfg(game, cfg):
                       prob_fullMCTS=cfg['prob_fullMCTS'], temperature2=cfg['temperature'][2], game=GAME_IDS[game])
 
 
-@pytest.mark.parametrize('game', ['splendor', 'santorini', 'abalone'])
+@pytest.mark.parametrize('game', ['splendor', 'santorini', 'abalone', 'azul'])
 def test_oracle_episode_matches_reference_examples(game):
     cfg, games = load_selfplay_golden(game)
     for gd in games:
