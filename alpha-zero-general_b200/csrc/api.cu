@@ -531,6 +531,7 @@ struct EngineT : azg_engine {
     unsigned long long launches = 0;
     int sims_full = 0, sims_fast = 0;
     bool sp_ready = false;
+    bool ragged_env = true, rag_started = false;   // ragged self-play (per-slot move boundaries), see selfplay_ragged
     bool profiling = false; std::vector<cudaEvent_t> ev; size_t ev_used = 0; std::vector<int> ev_kind; double prof_ms[4] = {0, 0, 0, 0}; long long prof_n[4] = {0, 0, 0, 0};
 
     template <class T> int alloc(T** p, size_t n, bool zero = true) {
@@ -584,6 +585,8 @@ struct EngineT : azg_engine {
         bad |= alloc(&d.noise_scr, (size_t)NG * G::A, false);
         bad |= alloc(&d.nn_in, (size_t)NG * G::SP); bad |= alloc(&d.nn_pi, (size_t)NG * G::A); bad |= alloc(&d.nn_v, (size_t)NG * G::NP);
         bad |= alloc(&d.nn_list, NG); bad |= alloc(&d.nn_count, 1); bad |= alloc(&d.stats, (size_t)NG * ST_N);
+        bad |= alloc(&d.sim_idx, NG); bad |= alloc(&d.turn_list, NG); bad |= alloc(&d.turn_count, 1); d.ragged = 0;
+        { const char* rv = getenv("AZG_RAGGED"); ragged_env = !(rv && rv[0] == '0'); }
         if (bad) return bad;
         return 0;
     }
@@ -739,6 +742,7 @@ struct EngineT : azg_engine {
         CK(cudaMemset(sp.active, 0, sizeof(int) * NG)); CK(cudaMemset(sp.games_started, 0, sizeof(unsigned) * NG)); CK(cudaMemset(sp.ply, 0, sizeof(int) * NG));
         CK(cudaMemset(sp.st_count, 0, sizeof(int) * NG)); CK(cudaMemset(sp.player, 0, sizeof(int) * NG));
         sp.inj_P = 0; sp.inj_init = nullptr; sp.inj_u_full = sp.inj_u_move = nullptr; sp.inj_seed = nullptr; sp_noise = nullptr;
+        rag_started = false;
         if (!inj) return 0;
         if (inj->n_plies <= 0 || !inj->init_boards || !inj->u_full || !inj->u_move || !inj->chance_seed) return fail("azg_selfplay_inject: n_plies must be positive and init_boards / u_full / u_move / chance_seed non-NULL");
         const size_t P = (size_t)inj->n_plies;
@@ -754,8 +758,51 @@ struct EngineT : azg_engine {
         return 0;
     }
     const double* sp_noise = nullptr;          // injected per-(slot, ply) Dirichlet draws of self-play
+    // Ragged self-play: with playout-cap randomisation (MCTS.py:58-59: numMCTSSims simulations with probability prob_fullMCTS, else
+    // numMCTSSims / ratio_fullMCTS) a lock-step ply leaves the fast-search slots idle for most of its launches. Here every slot
+    // carries its own simulation index; a slot whose budget is spent makes its move and starts the next search at the next launch
+    // (k_sp_turn), so every launch works on all n_games trees. Same games as the lock-step schedule (every RNG stream is keyed by
+    // slot, game and ply), only the order in which slots reach their plies differs. max_moves counts plies per slot on average.
+    bool use_ragged() const { return ragged_env && !sp.inj_P && cfg.prob_fullMCTS > 0.0 && cfg.prob_fullMCTS < 1.0 && sims_fast < sims_full; }
+    int selfplay_ragged(int min_episodes, int max_moves, cudaStream_t st) {
+        const int NG = d.n_games;
+        unsigned long long start[8], now[8];
+        CK(cudaMemcpyAsync(start, sp.counters, sizeof(start), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        d.ragged = 1;
+        struct Restore { Dev<G>& d; ~Restore() { d.ragged = 0; } } restore{d};
+        if (!rag_started) {                                       // every slot starts its first search together
+            prof_mark(PK_OTHER, st);
+            k_sp_begin<G><<<grid(), sel_warps<G>() * 32, 0, st>>>(d, sp, sims_full, sims_fast);
+            prof_mark(-1, st);
+            launches++;
+            gc(sims_full, st);
+            rag_started = true;
+        }
+        const int chunk = std::max(16, std::min(sims_fast, 128));
+        const unsigned turn_grid = (unsigned)std::min((NG + sel_warps<G>() - 1) / sel_warps<G>(), 296);
+        for (int ln = 0;;) {
+            for (int k = 0; k < chunk; k++, ln++) {
+                if (step(ln, st)) return 1;
+                prof_mark(PK_OTHER, st);
+                k_sp_turn<G><<<turn_grid, sel_warps<G>() * 32, 0, st>>>(d, sp, sims_full, sims_fast);
+                prof_mark(-1, st);
+                launches++;
+            }
+            CKL();
+            if (profiling && prof_drain()) return 1;
+            int ring = 0;
+            CK(cudaMemcpyAsync(now, sp.counters, sizeof(now), cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(&ring, sp.ex_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (min_episodes > 0 && (long long)(now[0] - start[0]) >= min_episodes) break;
+            if (max_moves > 0 && (long long)(now[3] - start[3]) >= (long long)max_moves * NG) break;
+            if (ring > sp.ex_cap / 2) break;
+            if (max_moves <= 0 && min_episodes <= 0) break;
+        }
+        return 0;
+    }
     int selfplay(int min_episodes, int max_moves, cudaStream_t st) override {
         if (selfplay_setup()) return 1;
+        if (use_ragged()) return selfplay_ragged(min_episodes, max_moves, st);
         d.noise = sp_noise; d.noise_gstride = sp_noise ? (size_t)sp.inj_P * G::A : (size_t)G::A; d.noise_ply = sp_noise ? sp.ply : nullptr;
         struct Restore { Dev<G>& d; ~Restore() { d.noise = nullptr; d.noise_gstride = G::A; d.noise_ply = nullptr; } } restore{d};
         unsigned long long start[8], now[8];

@@ -73,13 +73,10 @@ __device__ bool root_policy(const Dev<G>& d, int g, const int8_t* sb, int lane, 
     return true;
 }
 
+// Start of a move for slot g (WARP): new game if the slot is free (Coach.py:94-96), canonical root (Coach.py:61), playout-cap coin
+// (MCTS.py:58-59). `sb` = warp-private board scratch.
 template <class G>
-__global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_begin(Dev<G> d, SelfPlay<G> sp, int sims_full, int sims_fast) {
-    __shared__ WarpSmem<G> sm[sel_warps<G>()];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;
-    if (g >= d.n_games) return;
-    int8_t* sb = sm[w].board;
+__device__ void sp_begin_game(const Dev<G>& d, const SelfPlay<G>& sp, const int g, int8_t* sb, const int lane, int sims_full, int sims_fast) {
     int8_t* board = sp.board + (size_t)g * G::SP;
     const uint64_t gid = d.game_base + (uint64_t)g;                // global slot id: keys every RNG stream
     if (!sp.active[g]) {                                          // new game in this slot: fresh board, fresh tree
@@ -109,20 +106,27 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_begin(Dev<G> d, Self
         d.move_ctr[g] = (sp.games_started[g] << 8) | (unsigned)ply;   // a fresh Dirichlet draw for every search (MCTS.py:187-197): counter of root_noise's stream
     }
 }
-
 template <class G>
-__global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPlay<G> sp) {
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_begin(Dev<G> d, SelfPlay<G> sp, int sims_full, int sims_fast) {
     __shared__ WarpSmem<G> sm[sel_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;
     if (g >= d.n_games) return;
+    sp_begin_game<G>(d, sp, g, sm[w].board, lane, sims_full, sims_fast);
+    if (d.ragged && lane == 0) d.sim_idx[g] = 0;
+}
+
+// End of a move for slot g (WARP): visit-count policy, example record, sampled move, real move, end-of-game hand-over (see the header).
+template <class G>
+__device__ void sp_end_game(const Dev<G>& d, const SelfPlay<G>& sp, const int g, WarpSmem<G>& ws, const int lane) {
     if (!sp.active[g]) return;                                    // idle slot (injected episodes: its one game is over)
     constexpr int A = G::A, NP = G::NP, MW = G::MASK_WORDS;
     const uint64_t gid = d.game_base + (uint64_t)g;
-    int8_t* sb = sm[w].board;
+    int8_t* sb = ws.board;
     for (int i = lane; i < G::SP; i += 32) sb[i] = d.root[(size_t)g * G::SP + i];
     __syncwarp();
-    int* cnt = reinterpret_cast<int*>(sm[w].f); double* pw = sm[w].d;
-    uint32_t* mask = sm[w].mask; float qs = 0.f;
+    int* cnt = reinterpret_cast<int*>(ws.f); double* pw = ws.d;
+    uint32_t* mask = ws.mask; float qs = 0.f;
     const bool found = root_policy<G>(d, g, sb, lane, cnt, mask, qs);
     const int ply = sp.ply[g], player = sp.player[g];
     long long total = 0;
@@ -206,6 +210,34 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPl
             sp.active[g] = 0; atomicAdd(&sp.counters[0], 1ULL); atomicAdd(&sp.counters[1], (unsigned long long)n_ex);
             d.stats[(size_t)g * ST_N + ST_EPISODES]++; d.stats[(size_t)g * ST_N + ST_EXAMPLES] += (unsigned)n_ex;
         }
+    }
+}
+template <class G>
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_end(Dev<G> d, SelfPlay<G> sp) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
+    if (g >= d.n_games) return;
+    sp_end_game<G>(d, sp, g, sm[w], lane);
+}
+
+// Ragged self-play: the slots whose search budget was spent in the launch that just ended (k_backup listed them) make their move
+// and start the next one -- end of move, begin of move (new game if the old one is over), tree GC check -- while every other slot
+// simply goes on with its next simulation. One launch per lock-step simulation, a few warps of work on average.
+template <class G>
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_sp_turn(Dev<G> d, SelfPlay<G> sp, int sims_full, int sims_fast) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = *d.turn_count;
+    for (int i = blockIdx.x * sel_warps<G>() + w; i < n; i += gridDim.x * sel_warps<G>()) {
+        const int g = d.turn_list[i];
+        sp_end_game<G>(d, sp, g, sm[w], lane);
+        __syncwarp();
+        sp_begin_game<G>(d, sp, g, sm[w].board, lane, sims_full, sims_fast);
+        __syncwarp();
+        const int ns = d.n_sims[g];
+        gc_game<G>(d, g, sm[w].board, ns + 2, (ns + 2) * G::MAX_LEGAL, 0, lane);
+        __syncwarp();
+        if (lane == 0) d.sim_idx[g] = 0;
     }
 }
 

@@ -83,6 +83,11 @@ struct Dev {
                                // slot plays do not depend on how the slots are sharded over ranks
     double* noise_scr;         // [G][A] f64 scratch of the root re-noising in k_select
     unsigned* move_ctr;        // searches done in this slot (RNG counter)
+    // ragged self-play (selfplay.cuh k_sp_turn): every slot carries its own simulation index, so a slot whose budget is spent starts
+    // its next move at the next launch instead of idling until the slowest budget of the lock-step is done (MCTS.py:58-59 budgets)
+    int ragged;                // 1: k_select / k_backup take the simulation index of slot g from sim_idx[g] instead of the launch number
+    int* sim_idx;              // [G] simulations done in the current search
+    int* turn_list; int* turn_count;   // slots whose search finished in this launch (appended by k_backup, consumed by k_sp_turn)
     // per-simulation scratch
     PathEnt* path; int* path_len; int* leaf_kind; uint64_t* leaf_key; float* leaf_v; uint32_t* leaf_mask; int* leaf_round;
     int8_t* nn_in; float* nn_pi; float* nn_v; int* nn_list; int* nn_count;
@@ -614,9 +619,10 @@ __global__ void __launch_bounds__(selk_warps<G>() * 32, selk_warps<G>() == 1 ? 3
     __shared__ SelSmem<G> sm[selk_warps<G>()];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x < 32) d.ord_cnt[(step & 1) * 32 + threadIdx.x] = 0;     // the set this simulation's backup fills
+    if (d.ragged && blockIdx.x == 0 && threadIdx.x == 0) *d.turn_count = 0;                       // consumed by k_sp_turn before this launch
     WorkOrder<G> wo; wo.load(d, step, lane);
     const int g = wo.game(d, blockIdx.x * selk_warps<G>() + w, step, lane);   // CTAs are dispatched in index order: deepest games first
-    if (g >= 0) select_game<G>(d, g, step, sm, w, lane);
+    if (g >= 0) select_game<G>(d, g, d.ragged ? d.sim_idx[g] : step, sm, w, lane);
 }
 
 // Hang a new node on the child-link slot recorded by k_select (slot + 1; bit 31 = deterministic move: all U universes of the edge).
@@ -628,7 +634,7 @@ __device__ __forceinline__ void link_new_node(uint32_t* child, uint32_t ls, int 
 
 // ============================================================ expand + backup =========================
 template <class G, class SM>
-__device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const int step, SM* sm, const int w, const int lane) {
+__device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const int step, const int launch, SM* sm, const int w, const int lane) {
 #if AZG_SEL_PROF == 2
     const long long bp0 = clock64(); long long bp1 = 0, bp2 = 0;
 #endif
@@ -638,7 +644,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
     const int uni_b = d.universes > 0 ? step % d.universes : 0;
     const int depth = *d.g_path_len(g, uni_b);
     if (lane == 0) {                                             // file this game for the next simulation's work order
-        const int bk = (step & 1) * 32 + min(depth >> 2, 31);
+        const int bk = (launch & 1) * 32 + min(depth >> 2, 31);
         d.ord_list[(size_t)bk * d.n_games + atomicAdd(&d.ord_cnt[bk], 1)] = g;
     }
     NodeHdr* nodes = d.g_nodes(g); Edge* edges = d.g_edges(g); typename G::act_t* acts = d.g_acts(g);
@@ -779,7 +785,13 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
         atomicAdd(&g_selprof[2], (unsigned long long)bp2); atomicAdd(&g_selprof[3], (unsigned long long)(e - bp1 - bp2)); }
 #endif
     if (lane == 0) st[ST_REFLEGAL] += (unsigned)ref_legal;
-    if (lane == 0) { st[ST_SIMS]++; st[ST_VISITS] += (unsigned)depth; }
+    if (lane == 0) {
+        st[ST_SIMS]++; st[ST_VISITS] += (unsigned)depth;
+        if (d.ragged) {                                          // this slot's next simulation; budget spent => its move is made by k_sp_turn
+            d.sim_idx[g] = step + 1;
+            if (step + 1 >= d.n_sims[g]) d.turn_list[atomicAdd(d.turn_count, 1)] = g;
+        }
+    }
 }
 
 template <class G>
@@ -790,7 +802,7 @@ __global__ void __launch_bounds__(bak_warps<G>() * 32, 32 / bak_warps<G>()) k_ba
     if (blockIdx.x == 0 && threadIdx.x == 0) *d.nn_count = 0;   // leaf list consumed by the net; reset for the next step
     WorkOrder<G> wo; wo.load(d, step, lane);
     const int g = wo.game(d, blockIdx.x * bak_warps<G>() + w, step, lane);   // CTAs are dispatched in index order: deepest games first
-    if (g >= 0) backup_game<G, SM>(d, g, step, sm, w, lane);
+    if (g >= 0) backup_game<G, SM>(d, g, d.ragged ? d.sim_idx[g] : step, step, sm, w, lane);
 }
 
 // ============================================================ finish (getActionProb tail) ==============
@@ -892,13 +904,9 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_node_query(Dev<G> d, in
 // Compacts nodes + boards + edges + actions + child links in place (ascending, destination <= source), rewrites
 // the links through an old->new index map and rebuilds the hash table.
 template <class G>
-__global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_nodes, int need_edges, int force) {
-    __shared__ WarpSmem<G> sm[sel_warps<G>()];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
-    if (g >= d.n_games) return;
+__device__ void gc_game(const Dev<G>& d, const int g, int8_t* sb /* warp-private board scratch, SP bytes */, int need_nodes, int need_edges, int force, const int lane) {
     const int nn = d.n_nodes[g], ne = d.n_edges[g];
     if (!force && nn + need_nodes <= d.node_cap && ne + need_edges <= d.edge_cap) return;
-    int8_t* sb = sm[w].board;
     warp_load_board<G>(sb, d.root + (size_t)g * G::SP, lane);
     uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
     const int r = G::progress(sb), U = d.U;
@@ -1016,6 +1024,13 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_n
             slot = (slot + 1) & (uint32_t)(d.ht_cap - 1);
     }
     if (lane == 0) { d.n_nodes[g] = wn; d.n_edges[g] = we; d.root_node[g] = 0; d.stats[(size_t)g * ST_N + ST_GC]++; if (sweep) d.stats[(size_t)g * ST_N + ST_GC_SWEEP]++; }
+}
+template <class G>
+__global__ void __launch_bounds__(sel_warps<G>() * 32) k_gc(Dev<G> d, int need_nodes, int need_edges, int force) {
+    __shared__ WarpSmem<G> sm[sel_warps<G>()];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = blockIdx.x * sel_warps<G>() + w;
+    if (g >= d.n_games) return;
+    gc_game<G>(d, g, sm[w].board, need_nodes, need_edges, force, lane);
 }
 
 // Reset trees (MCTS.reset_all_search_trees, MCTS.py:199-203): one slot (game >= 0) or all.

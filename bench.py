@@ -62,6 +62,7 @@ def parse():
     ap.add_argument('--sims', type=int, default=0, help='numMCTSSims (0 = the config default: 800, abalone 1600)')
     ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 6 x sims + 320)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-pcr', action='store_true', help='skip the secondary line with the reference-default playout-cap randomisation (prob_fullMCTS 0.25, ratio 5)')
     ap.add_argument('--no-iteration', action='store_true', help='skip the secondary whole-iteration leg (complete games -> example drain -> NCCL gather -> symmetries)')
     ap.add_argument('--iter-sims', type=int, default=0, help='numMCTSSims of the whole-iteration leg (0 = 40: complete games within seconds)')
     ap.add_argument('--iter-games', type=int, default=0, help='concurrent games per GPU of the whole-iteration leg (0 = --games)')
@@ -453,9 +454,23 @@ def main():
                'sample': f'{threads} host threads x 1 {args.game} self-play game x {args.cpu_plies} plies x {args.sims} sims (oracle/azg_oracle.c, same MCTS args and net weights)'}
         cpu.update(port_vs_reference(cpu['value']))
 
+    eng.close()
+    # ---- secondary line: the reference's default playout-cap randomisation (main.py:130-131: prob_fullMCTS 0.25, ratio_fullMCTS 5) ------
+    pcr = None
+    if not args.no_pcr:
+        a2 = dict(a, prob_fullMCTS=0.25, ratio_fullMCTS=5)
+        eng2 = Engine(game, net, a2, n_games=args.games, dirichlet_noise=True, seed=1000, node_cap=node_cap, first_game=first_game)
+        eng2.selfplay(max_moves=2)
+        t0 = eng2.stats(); barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record(stream); eng2.selfplay(max_moves=2 * K); g1.record(stream); barrier()
+        t1 = eng2.stats(); ms3 = max_over_ranks(g0.elapsed_time(g1)); sims3 = sum_over_ranks(t1['sims'] - t0['sims'])
+        pcr = {'prob_fullMCTS': 0.25, 'ratio_fullMCTS': 5, 'sims_per_sec': sims3 / (ms3 * 1e-3), 'vs_full_search_value': sims3 / (ms3 * 1e-3) / value,
+               'moves_played': t1['moves_played'] - t0['moves_played'], 'mean_sims_per_move': (t1['sims'] - t0['sims']) / max(t1['moves_played'] - t0['moves_played'], 1),
+               'schedule': 'ragged: per-slot move boundaries (k_sp_turn), every launch works on all trees', 'ms': ms3}
+        eng2.close()
     # ---- whole-iteration leg: complete games -> drain -> gather (NCCL) -> symmetries --------------------------------------
     iteration = None
-    eng.close()
     if not args.no_iteration:
         iteration = run_iteration(torch, dist, args, game, net, rank, world, dev, barrier, max_over_ranks, sum_over_ranks, gather_examples, shard_games)
 
@@ -463,7 +478,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 net (token GEMMs 3xTF32 on tcgen05, fp32 accumulate) / f64 PUCT / i8 boards', 'data': 'synthetic',
                 'config': workload_cfg(args), 'e2e': e2e, 'gpu_launches': int(d['kernels_launched']), 'roofline': roofline, 'cpu_baseline': cpu,
-                'clocks': clk, 'kernels': kern, 'tree_path': tree_path, 'iteration': iteration,
+                'clocks': clk, 'kernels': kern, 'tree_path': tree_path, 'pcr_default': pcr, 'iteration': iteration,
                 'counters': {'sims': d['sims'], 'node_visits': visits, 'expansions': exps, 'nn_evals': evals, 'terminal_hits': d['terminal_hits'],
                              'arena_overflows': d['arena_overflows'], 'gc_runs': d['gc_runs'], 'gc_sweeps': d['gc_sweeps'], 'examples_dropped': s1['examples_dropped'],
                              'moves_played': d['moves_played'],

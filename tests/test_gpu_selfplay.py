@@ -201,3 +201,41 @@ def test_games_do_not_depend_on_the_sharding():
     assert st['episodes_finished'] >= 8 and st['episodes_finished'] == sa['episodes_finished'] + sb['episodes_finished']
     assert sorted(rows(whole)) == sorted(rows(a) + rows(b))
     assert sorted(rows(a)) != sorted(rows(b))                    # and the two shards really play different games
+
+
+def test_ragged_schedule_plays_the_same_games_as_lock_step(monkeypatch):
+    """Playout-cap randomisation (MCTS.py:58-59) gives every search its own budget. The ragged scheduler (k_sp_turn: a slot whose
+    budget is spent makes its move at the next launch instead of idling until the longest budget of the ply is done) must play
+    exactly the games the lock-step scheduler plays: every example of the lock-step run appears in a longer ragged run, bit for bit,
+    and the ragged run really is denser (fewer launches per move)."""
+    game = azg_b200.SantoriniGame()
+    args = dict(numMCTSSims=20, cpuct=1.25, fpu=0.0, universes=1, dirichletAlpha=-1.0, prob_fullMCTS=0.4, ratio_fullMCTS=4, forced_playouts=True)
+    n = 8
+
+    def run(ragged, plies):
+        monkeypatch.setenv('AZG_RAGGED', '1' if ragged else '0')
+        eng = Engine(game, HashNetWrapper(game), args, n_games=n, dirichlet_noise=True, seed=91, node_cap=1024)
+        parts = []
+        s0 = eng.stats()
+        while eng.stats()['moves_played'] < plies * n:
+            left = plies - eng.stats()['moves_played'] // n
+            eng.selfplay(max_moves=max(left, 1))
+            parts.append(eng.examples(n * game.info.max_game_len))
+        st = eng.stats(); eng.close()
+        assert st['examples_dropped'] == 0 and st['arena_overflows'] == 0
+        ex = tuple(np.concatenate([p[i] for p in parts]) for i in range(5))
+        rows = [ex[0][i].tobytes() + ex[1][i].tobytes() + ex[2][i].tobytes() + ex[3][i].tobytes() + ex[4][i].tobytes() for i in range(len(ex[0]))]
+        return rows, st
+
+    lock, sl = run(False, 60)
+    rag, sr = run(True, 150)
+    monkeypatch.delenv('AZG_RAGGED')
+    assert sl['episodes_finished'] >= 8 and len(lock) > 50
+    from collections import Counter
+    missing = Counter(lock) - Counter(rag)
+    assert not missing, f'{sum(missing.values())} of {len(lock)} lock-step examples are not in the ragged run'
+    # lock-step: 20 launches per ply whatever the budgets; ragged: the mean budget (0.4 * 20 + 0.6 * 5 = 11) per ply
+    assert sl['sims'] / sl['moves_played'] < 12.5 and sr['sims'] / sr['moves_played'] < 12.5
+    # lock-step: 20 lock-step simulations (select + net + backup launches) per ply of the slowest slot; ragged: ~11 (+ the turn kernel)
+    rag_steps_per_move = (sr['kernels_launched'] / 4.0) / (sr['moves_played'] / n)
+    assert rag_steps_per_move < 15.0, rag_steps_per_move
