@@ -16,6 +16,7 @@
 #include "net_v80_tc.cuh"
 #include "net_v21.cuh"
 #include "net_v89.cuh"
+#include "net_v89_tc.cuh"
 #include "net_v84.cuh"
 #include "azul.cuh"
 #include "abalone.cuh"
@@ -319,6 +320,7 @@ struct azg_net {
     long long* prof = nullptr;            // optional phase timestamps of CTA 0 (AZG_V80_PROF=1; azg_net_prof)
     int v80_kernel = 1;                   // 1 = tcgen05 kernel (default), 0 = fp32 CUDA-core kernel (kept for A/B profiling; AZG_V80_KERNEL=fp32)
     V89Layout L89; V89Chunks CK89; V21Layout L21; V84Layout L84;
+    V89TCImg TI89; float* img89 = nullptr; float* res89 = nullptr; int v89_kernel = 1;   // tcgen05 trunk (default) or the fp32 CUDA-core kernel (AZG_V89_KERNEL=fp32, A/B runs)
     Scratch masks;                        // packed masks for the standalone forward
     unsigned long long launches = 0;
     bool attr_done = false; int n_sm = 0;  // launch attributes of this net's kernel on this net's device (set at the first launch)
@@ -364,9 +366,21 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
         } else return fail("SplendorNNet V80 only evaluates Splendor boards");
     } else if (net->kind == AZG_NET_SANTORINI_V89) {
         if constexpr (G::GAME_ID == AZG_GAME_SANTORINI) {
+            if (net->v89_kernel == 1) {
+                if (!net->attr_done) {
+                    CK(cudaFuncSetAttribute(k_v89_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, T89_SMEM));
+                    int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&net->n_sm, cudaDevAttrMultiProcessorCount, dev));
+                    net->attr_done = true;
+                }
+                if (!net->res89) CK(cudaMalloc(&net->res89, sizeof(float) * (size_t)net->n_sm * T89_RES_FLOATS));   // per-CTA residual scratch (stays in L2)
+                const int tiles = (n_max + T89_TB - 1) / T89_TB;
+                static const int grid_cap = getenv("AZG_V89_GRID") ? atoi(getenv("AZG_V89_GRID")) : 1 << 30;   // debug: fewer CTAs (is the kernel bound by L2 bandwidth?)
+                k_v89_tc<<<std::min(std::min(tiles, net->n_sm), grid_cap), T89_THREADS, T89_SMEM, st>>>(net->blob, net->img89, net->res89, net->L89, net->TI89, count_ptr, list, boards, bstride, masks, pi, v, n_max, net->prof);
+            } else {
             constexpr size_t smem = v89_smem_bytes();
             if (!net->attr_done) { CK(cudaFuncSetAttribute(k_v89_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); net->attr_done = true; }
             k_v89_forward<<<(n_max + V89_TB - 1) / V89_TB, V89_THREADS, smem, st>>>(net->blob, net->L89, net->CK89, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+            }
         } else return fail("SantoriniNNet V89 only evaluates Santorini boards");
     } else if (net->kind == AZG_NET_ABALONE_V21) {
         if constexpr (G::GAME_ID == AZG_GAME_ABALONE) {
@@ -418,6 +432,9 @@ extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights
         CK(cudaMemcpy(src.data(), weights, n_weights * sizeof(float), cudaMemcpyDefault));
         v89_prepare(src.data(), net->L89, dst.data());
         CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<float> img((size_t)net->TI89.total);
+        v89tc_prepare(dst.data(), net->L89, net->TI89, img.data());
+        CK(cudaMemcpy(net->img89, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
         return 0;
     }
     const size_t need = v80_src_floats(SP2::ROWS, net->np);
@@ -461,9 +478,12 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L84.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
         if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
     } else if (net_kind == AZG_NET_SANTORINI_V89) {
-        net->L89 = v89_layout(); net->CK89 = v89_chunks(net->L89);
+        net->L89 = v89_layout(); net->CK89 = v89_chunks(net->L89); net->TI89 = v89tc_layout();
+        { const char* kv = getenv("AZG_V89_KERNEL"); net->v89_kernel = (kv && !strcmp(kv, "fp32")) ? 0 : 1; }
+        if (getenv("AZG_V89_PROF")) { if (cudaMalloc(&net->prof, 64 * sizeof(long long)) != cudaSuccess) net->prof = nullptr; else cudaMemset(net->prof, 0, 64 * sizeof(long long)); }
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L89.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
-        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
+        if (cudaMalloc(&net->img89, sizeof(float) * (size_t)net->TI89.total) != cudaSuccess) { cudaFree(net->blob); delete net; return fail("cudaMalloc weight images failed"); }
+        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); cudaFree(net->img89); delete net; return 1; }
     }
     *out = net; return 0;
 }
@@ -471,10 +491,10 @@ extern "C" int azg_debug_selprof(unsigned long long* out8) {      // debug: see 
     CK(cudaDeviceSynchronize()); CK(cudaMemcpyFromSymbol(out8, azg::g_selprof, 8 * sizeof(unsigned long long))); CK(cudaMemcpyFromSymbol(out8 + 8, azg::g_selprof2, 8 * sizeof(unsigned long long))); return 0;
 }
 extern "C" int azg_net_prof(azg_net* net, long long* out64) {      // debug: phase timestamps (SM clock) of CTA 0's first tiles
-    if (!net || !net->prof) return fail("profiling not enabled (AZG_V80_PROF=1)");
+    if (!net || !net->prof) return fail("profiling not enabled (AZG_V80_PROF=1 / AZG_V89_PROF=1)");
     CK(cudaDeviceSynchronize()); CK(cudaMemcpy(out64, net->prof, 64 * sizeof(long long), cudaMemcpyDeviceToHost)); return 0;
 }
-extern "C" int azg_net_destroy(azg_net* net) { if (net) { if (net->blob) cudaFree(net->blob); if (net->img) cudaFree(net->img); delete net; } return 0; }
+extern "C" int azg_net_destroy(azg_net* net) { if (net) { if (net->blob) cudaFree(net->blob); if (net->img) cudaFree(net->img); if (net->img89) cudaFree(net->img89); if (net->res89) cudaFree(net->res89); delete net; } return 0; }
 template <class G> static int net_forward_t(azg_net* net, int n, const int8_t* boards, const uint8_t* mask, float* pi, float* v, cudaStream_t st) {
     Arg* a = tl_arg;
     if (a[0].in(boards, (size_t)n * G::S, st) || a[1].in(mask, (size_t)n * G::A, st) || a[2].outbuf(pi, sizeof(float) * n * G::A) ||

@@ -342,8 +342,12 @@ class NNetWrapper(BatchedPredictMixin):
         from .formats import save_checkpoint_file
         return save_checkpoint_file(self.state_dict, self.args.get('nn_version', self.NN_VERSION), folder, filename, additional_keys)
 
-    def train(self, examples):
-        raise NotImplementedError('training is outside the self-play hot path (SURVEY.md section 8f-1)')
+    def train(self, examples, validation_set=None, save_folder=None, every=0):
+        """GenericNNetWrapper.train (GenericNNetWrapper.py:44-92): examples = list / deque of the reference's example tuples, or the
+        five arrays / CUDA tensors of Engine.examples_device(). Trains with train.Trainer (torch autograd) and loads the new weights
+        into the CUDA inference kernels. Versions 80 / 84 / 89."""
+        from .train import Trainer
+        return Trainer(self).train(examples)
 
 
 class SantoriniNNetWrapper(NNetWrapper):
