@@ -17,7 +17,7 @@
 #include "net_v21.cuh"
 #include "net_v89.cuh"
 #include "net_v89_tc.cuh"
-#include "net_v84.cuh"
+#include "net_tokmix.cuh"
 #include "azul.cuh"
 #include "abalone.cuh"
 #include "santorini.cuh"
@@ -100,10 +100,12 @@ typedef Splendor<2> SP2;
 #define DISPATCH(game_id, np, CALL)                                                                       \
     do {                                                                                                  \
         if ((game_id) == AZG_GAME_SPLENDOR && (np) == 2) { typedef Splendor<2> G; return CALL; }           \
+        if ((game_id) == AZG_GAME_SPLENDOR && (np) == 3) { typedef Splendor<3> G; return CALL; }           \
+        if ((game_id) == AZG_GAME_SPLENDOR && (np) == 4) { typedef Splendor<4> G; return CALL; }           \
         if ((game_id) == AZG_GAME_SANTORINI && (np) == 2) { typedef Santorini G; return CALL; }            \
         if ((game_id) == AZG_GAME_ABALONE && (np) == 2) { typedef Abalone G; return CALL; }                \
         if ((game_id) == AZG_GAME_AZUL && (np) == 2) { typedef Azul G; return CALL; }                      \
-        return fail("unknown game (built: 1 = splendor with 2 players, 2 = santorini without gods, 3 = abalone, 4 = azul with 2 players)"); \
+        return fail("unknown game (built: 1 = splendor with 2, 3 or 4 players, 2 = santorini without gods, 3 = abalone, 4 = azul with 2 players)"); \
     } while (0)
 
 template <class G> static int game_info_t(azg_game_info_t* out) {
@@ -319,7 +321,7 @@ struct azg_net {
     V80TCImg TI; float* img = nullptr;   // tensor-core operand images of the V80 token GEMMs (net_v80_tc.cuh)
     long long* prof = nullptr;            // optional phase timestamps of CTA 0 (AZG_V80_PROF=1; azg_net_prof)
     int v80_kernel = 1;                   // 1 = tcgen05 kernel (default), 0 = fp32 CUDA-core kernel (kept for A/B profiling; AZG_V80_KERNEL=fp32)
-    V89Layout L89; V89Chunks CK89; V21Layout L21; V84Layout L84;
+    V89Layout L89; V89Chunks CK89; V21Layout L21; TokMixLayout LTM; bool tokmix = false;   // tokmix: AzulNNet V84, SplendorNNet V80 for 3 / 4 players
     V89TCImg TI89; float* img89 = nullptr; float* res89 = nullptr; int v89_kernel = 1;   // tcgen05 trunk (default) or the fp32 CUDA-core kernel (AZG_V89_KERNEL=fp32, A/B runs)
     Scratch masks;                        // packed masks for the standalone forward
     unsigned long long launches = 0;
@@ -345,7 +347,7 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
         k_hashnet_forward<G::S, G::A, G::NP, G::MASK_WORDS><<<(n_max + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
             count_ptr, list, boards, bstride, masks, pi, v, n_max);
     } else if (net->kind == AZG_NET_SPLENDOR_V80) {
-        if constexpr (G::GAME_ID == AZG_GAME_SPLENDOR) {
+        if constexpr (G::GAME_ID == AZG_GAME_SPLENDOR && G::NP == 2) {
             if (net->v80_kernel == 1) {
                 if (!net->attr_done) {                             // function attributes and the SM count belong to the net's device: kept in the handle
                     CK(cudaFuncSetAttribute(k_v80_tc<G::NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -363,6 +365,11 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
             k_v80_forward<G::ROWS, G::NP, V80_TB><<<(n_max + V80_TB - 1) / V80_TB, V80_THREADS, smem, st>>>(
                 net->blob, net->L, net->CK, net->DW, count_ptr, list, boards, bstride, masks, pi, v, n_max);
             }
+        } else if constexpr (G::GAME_ID == AZG_GAME_SPLENDOR) {      // 3 / 4 players: 71 / 88 tokens, generic fp32 token-mixer kernel
+            typedef typename std::conditional<G::NP == 3, TMS_V80_3P, TMS_V80_4P>::type SMX;
+            auto kern = k_tokmix_forward<G::ROWS, 7, 81, G::NP, 3 * G::ROWS, G::ROWS, G::NP == 3 ? 56 : 64>;
+            if (!net->attr_done) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMX::bytes())); net->attr_done = true; }
+            kern<<<(n_max + TM_TB - 1) / TM_TB, TM_THREADS, SMX::bytes(), st>>>(net->blob, net->LTM, count_ptr, list, boards, bstride, masks, pi, v, n_max);
         } else return fail("SplendorNNet V80 only evaluates Splendor boards");
     } else if (net->kind == AZG_NET_SANTORINI_V89) {
         if constexpr (G::GAME_ID == AZG_GAME_SANTORINI) {
@@ -395,9 +402,9 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
         } else return fail("AbaloneNNet V21 only evaluates Abalone boards");
     } else if (net->kind == AZG_NET_AZUL_V84) {
         if constexpr (G::GAME_ID == AZG_GAME_AZUL) {
-            constexpr size_t smem = v84_smem_bytes();
-            if (!net->attr_done) { CK(cudaFuncSetAttribute(k_v84_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); net->attr_done = true; }
-            k_v84_forward<<<(n_max + V84_TB - 1) / V84_TB, V84_THREADS, smem, st>>>(net->blob, net->L84, count_ptr, list, boards, bstride, masks, pi, v, n_max);
+            auto kern = k_tokmix_forward<23, 6, 180, 2, 115, 46, 32>;
+            if (!net->attr_done) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMS_V84::bytes())); net->attr_done = true; }
+            kern<<<(n_max + TM_TB - 1) / TM_TB, TM_THREADS, TMS_V84::bytes(), st>>>(net->blob, net->LTM, count_ptr, list, boards, bstride, masks, pi, v, n_max);
         } else return fail("AzulNNet V84 only evaluates Azul boards");
     } else return fail("net kind not built");
     net->launches++;
@@ -416,12 +423,12 @@ extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights
         CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
         return 0;
     }
-    if (net->kind == AZG_NET_AZUL_V84) {
-        const size_t need84 = v84_src_floats();
-        if (!weights || n_weights != need84) return fail("V84 weights: expected " + std::to_string(need84) + " floats, got " + std::to_string(n_weights));
-        std::vector<float> src(n_weights), dst((size_t)net->L84.total);
+    if (net->tokmix) {
+        const size_t need84 = tokmix_src_floats(net->LTM);
+        if (!weights || n_weights != need84) return fail("token-mixer net weights: expected " + std::to_string(need84) + " floats, got " + std::to_string(n_weights));
+        std::vector<float> src(n_weights), dst((size_t)net->LTM.total);
         CK(cudaMemcpy(src.data(), weights, n_weights * sizeof(float), cudaMemcpyDefault));
-        v84_prepare(src.data(), net->L84, dst.data());
+        tokmix_prepare(src.data(), net->LTM, dst.data());
         CK(cudaMemcpy(net->blob, dst.data(), dst.size() * sizeof(float), cudaMemcpyHostToDevice));
         return 0;
     }
@@ -460,7 +467,11 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
     if (net_kind == AZG_NET_SPLENDOR_V80 && game_id != AZG_GAME_SPLENDOR) return fail("SplendorNNet V80 only evaluates Splendor boards");
     if (net_kind == AZG_NET_SANTORINI_V89 && game_id != AZG_GAME_SANTORINI) return fail("SantoriniNNet V89 only evaluates Santorini boards");
     azg_net* net = new azg_net(); net->kind = net_kind; net->game_id = game_id; net->np = np;
-    if (net_kind == AZG_NET_SPLENDOR_V80) {
+    if (net_kind == AZG_NET_SPLENDOR_V80 && np != 2) {
+        net->tokmix = true; net->LTM = tokmix_layout(80, gi.state_rows, 7, 81, np);
+        if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->LTM.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
+        if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
+    } else if (net_kind == AZG_NET_SPLENDOR_V80) {
         net->L = v80_layout(SP2::ROWS, np); net->CK = v80_chunks(net->L); memset(&net->DW, 0, sizeof(net->DW));
         net->TI = v80tc_layout();
         const char* kv = getenv("AZG_V80_KERNEL");
@@ -474,8 +485,8 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L21.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
         if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
     } else if (net_kind == AZG_NET_AZUL_V84) {
-        net->L84 = v84_layout();
-        if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L84.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
+        net->tokmix = true; net->LTM = tokmix_layout(84, 23, 6, 180, 2);
+        if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->LTM.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
         if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); delete net; return 1; }
     } else if (net_kind == AZG_NET_SANTORINI_V89) {
         net->L89 = v89_layout(); net->CK89 = v89_chunks(net->L89); net->TI89 = v89tc_layout();

@@ -814,8 +814,7 @@ __global__ void __launch_bounds__(sel_warps<G>() * 32) k_finish(Dev<G> d, int n,
     if (g >= n) return;
     constexpr int A = G::A, NP = G::NP;
     int8_t* sb = sm[w].board;
-    if (lane < G::SP / 16) reinterpret_cast<uint4*>(sb)[lane] = reinterpret_cast<const uint4*>(d.root + (size_t)g * G::SP)[lane];
-    __syncwarp();
+    warp_load_board<G>(sb, d.root + (size_t)g * G::SP, lane);     // (boards may be longer than 32 x 16 bytes: Splendor with 4 players)
     uint64_t klo, khi; board_hash<G>(sb, lane, klo, khi);
     const NodeHdr* nodes = d.g_nodes(g); const Edge* edges = d.g_edges(g); const typename G::act_t* acts = d.g_acts(g);
     const int idx = ht_find(d.g_ht(g), d.ht_cap, d.g_keys(g), klo, khi, lane);

@@ -159,10 +159,11 @@ def splendor_move_to_str(move):
 
 
 class SplendorGame(CudaGame):
-    """Drop-in for splendor/SplendorGame.py:SplendorGame (2 players)."""
+    """Drop-in for splendor/SplendorGame.py:SplendorGame. The reference fixes the player count with the module constant
+    NUMBER_PLAYERS (SplendorGame.py:9); here it is a constructor argument: 2 (default), 3 or 4."""
 
-    def __init__(self):
-        super().__init__(NUMBER_PLAYERS)
+    def __init__(self, num_players=NUMBER_PLAYERS):
+        super().__init__(num_players)
 
     def moveToString(self, move, current_player):
         return splendor_move_to_str(move)

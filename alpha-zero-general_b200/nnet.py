@@ -49,7 +49,8 @@ def random_v80_state_dict(seed=0, num_players=2):
     tests/golden/splendor_v80_rand.npz); BatchNorm is the default. Used by bench.py and smoke()."""
     rng = np.random.default_rng(seed)
     nv = 32 + 10 * num_players + num_players * num_players
-    E, Q, A = 3 * nv, 40 * nv // 56, 81
+    E, A = 3 * nv, 81
+    Q = max(8, (E // 4 + 4) // 8 * 8); Q += 8 if Q < 0.9 * (E // 4) else 0          # _make_divisible(E // 4, 8): 40 / 56 / 64 for 2 / 3 / 4 players
     shapes = {}
     def lin_bn(prefix, out, inn, ch):
         shapes[f'{prefix}.linear.weight'] = (out, inn)
@@ -298,7 +299,7 @@ class NNetWrapper(BatchedPredictMixin):
     def __init__(self, game, nn_args=None, state_dict=None, seed=0):
         nn_args = dict(nn_args or {'nn_version': 80})
         if nn_args.get('nn_version', 80) != 80:
-            raise NotImplementedError('only SplendorNNet version 80 is built (the shipped 2-player checkpoint)')
+            raise NotImplementedError('only SplendorNNet version 80 is built (the shipped 2-, 3- and 4-player checkpoints)')
         self.args = nn_args
         self.game = game
         self.board_size = game.getBoardSize(); self.action_size = game.getActionSize(); self.num_players = game.num_players

@@ -386,23 +386,34 @@ def main():
     visits, exps, evals = d['node_visits'], d['expansions'], d['nn_evals']
     Lbar_vis = d['sum_legal_visited'] / max(visits, 1); Lbar_exp = d['sum_legal'] / max(exps, 1); Dbar = visits / max(d['sims'], 1)
     n_launch = max(int(kt['select_launches']), 1)
-    # Algorithmic bytes. The PUCT scan of a visited node (B_sel = 16 + 14 L) is split over two kernels in this engine:
-    # k_select follows the cached choice (32 B header + 4 B link per visit, 16 B path record) and scans only the root (20 B per
-    # root edge incl. its child link); k_backup re-scans the L edges of every node whose statistics it just changed (16 B per
-    # edge) on top of the update itself (B_bak), the expansion (B_exp) and the net I/O (B_nn). 'tree_path' is the SURVEY's own
-    # figure for the whole select+expand+backup path over the time of both kernels.
+    # Algorithmic bytes PER KERNEL: what each kernel itself has to touch in this engine's data layout, counted from
+    # the engine's own counters of the same run. SP = board slot padded to 16 B, MW = mask words, U = child links per edge.
+    #   k_select : per visit the 32 B node header + 4 B cached link + 16 B path record; the root is scanned in full (16 B edge + 4 B link
+    #              per legal action); the ONE new child of a simulation is materialised here: parent board read (SP), action id, hash-table
+    #              probe (32 slots x 8 B) + key check (16 B), child link write, and the new leaf's hand-over to the net: board (SP),
+    #              legal mask, key / round / link (32 B).
+    #   k_backup : per expansion the net's outputs (4 A + 4 np), the mask, L new edges (16 B + action id + 4 U link bytes each), the
+    #              board slot (read SP + write SP), key (16 B), header (32 B), hash-table insert (256 B probe + 8 B); per visited level
+    #              the path record (16 B), edge read-modify-write (32 B), header read + partial write (48 B); the cached-choice
+    #              refresh re-reads 16 B per edge of every non-root node on the path and rewrites its U links + best (2 B).
+    # 'tree_path' below is the SURVEY's own figure (B_sel + B_bak + B_exp + B_nn of a dense re-scan design) over the time of both kernels.
     U = max(GAMES[args.game]['universes'], 1)
+    SPAD = (S_BYTES + 15) // 16 * 16; MWB = 4 * ((N_ACT + 31) // 32); ACTB = 1 if N_ACT <= 256 else 2
     refreshed = max(visits - d['sims'], 0)                                       # non-root visits: one cached-choice refresh each
-    sel_bytes = (36.0 + 16.0) * visits + 20.0 * d['sum_legal_root_scans']
-    bak_bytes = (32.0 * visits + (2.0 * S_BYTES + 32.0) * exps + 14.0 * d['sum_legal'] + (S_BYTES + 11 + 4 * N_ACT + 4 * N_PL) * evals
-                 + 16.0 * visits + 16.0 * d['sum_legal_refreshed'] + (2.0 + 8.0 * U) * refreshed)
+    new_leaves = exps + d['terminal_hits']
+    sel_bytes = (52.0 * visits + 20.0 * d['sum_legal_root_scans'] + (SPAD + ACTB + 256 + 16 + 4 * U) * new_leaves + (SPAD + MWB + 32) * exps)
+    bak_bytes = ((4.0 * N_ACT + 4 * N_PL + MWB + 2 * SPAD + 16 + 32 + 264) * exps + (16.0 + ACTB + 4 * U) * d['sum_legal']
+                 + (16.0 + 32 + 48) * visits + 16.0 * d['sum_legal_refreshed'] + (2.0 + 4.0 * U) * refreshed)
     survey_bytes = (16.0 * visits + 14.0 * d['sum_legal_visited'] + 32.0 * visits + (2.0 * S_BYTES + 32.0) * exps + 14.0 * d['sum_legal']
                     + (S_BYTES + 11 + 4 * N_ACT + 4 * N_PL) * evals)
+    survey_sel_bytes = 16.0 * visits + 14.0 * d['sum_legal_visited']             # SURVEY 8d B_sel = 16 + 14 L per select step (dense re-scan of every visited node)
     net_flops = float(gm['flops']) * evals
     tree_ms = kt['select_ms'] + kt['backup_ms']
     kern = {
         'select': {'ms': kt['select_ms'], 'bound': 'hbm', 'achieved': sel_bytes / max(kt['select_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
-                   'per_launch_bytes': sel_bytes / n_launch},
+                   'per_launch_bytes': sel_bytes / n_launch,
+                   'survey_B_sel_frac': survey_sel_bytes / max(kt['select_ms'], 1e-9) / 1e6 / pk['hbm'],
+                   'survey_B_sel_note': 'SURVEY 8d books 16 + 14 L bytes per select step (a design that re-scans every visited node); this engine follows a cached choice (52 B per non-root visit), so it moves fewer bytes than that model'},
         'net': {'ms': kt['net_ms'], 'bound': 'tensor', 'achieved': net_flops / max(kt['net_ms'], 1e-9) / 1e9, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
                     'per_launch_flops': net_flops / n_launch},
         'expand_backup': {'ms': kt['backup_ms'], 'bound': 'hbm', 'achieved': bak_bytes / max(kt['backup_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
@@ -412,13 +423,15 @@ def main():
                  'per_step_bytes': survey_bytes / n_launch, 'frac': survey_bytes / max(tree_ms, 1e-9) / 1e6 / pk['hbm'],
                  'note': 'SURVEY.md 8d bytes of select + expand + backup (B_sel + B_bak + B_exp + B_nn) over the time of k_select + k_backup'}
     tot_ms = kt['select_ms'] + kt['net_ms'] + kt['backup_ms'] + kt['other_ms']
-    for v in kern.values():
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')                          # dram bytes per launch from the committed ncu --set full captures
+    tj = (json.load(open(tp)).get(args.game) or {}) if os.path.exists(tp) else {}  # per game: only captures of the same workload count
+    for name, v in kern.items():
         v['frac'] = v['achieved'] / v['peak']; v['share'] = v['ms'] / max(tot_ms, 1e-9); v['avg_launch_us'] = 1e3 * v['ms'] / n_launch
+        v['dram_bytes_per_launch_ncu'] = tj.get(name)
+        if tj.get(name) and 'per_launch_bytes' in v:
+            v['dram_over_algorithmic'] = tj[name] / v['per_launch_bytes']
     dom = max(kern, key=lambda k: kern[k]['ms'])
-    traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'traffic.json')                          # dram bytes per launch from the committed ncu --set full capture
-    if os.path.exists(tp):
-        traffic = (json.load(open(tp)).get(args.game) or {}).get(dom)               # per game: only captures of the same workload count
+    traffic = tj.get(dom)
     roofline = {'kernel': dom, 'bound': kern[dom]['bound'], 'achieved': kern[dom]['achieved'], 'peak': kern[dom]['peak'], 'unit': kern[dom]['unit'],
                 'frac': kern[dom]['frac'], 'traffic': traffic, 'peak_source': pk['src'] + (' sustained bf16' if kern[dom]['bound'] == 'tensor' else ''),
                 'avg_launch_us': kern[dom]['avg_launch_us'], 'share_of_step': kern[dom]['share']}

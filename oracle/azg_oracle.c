@@ -870,8 +870,9 @@ static const float* take(const float** p, size_t n) { const float* r = *p; *p +=
 static lin_bn take_lin_bn(const float** p, int out, int in, int ch) {
     lin_bn l; l.w = take(p, (size_t)out * in); l.g = take(p, ch); l.b = take(p, ch); l.m = take(p, ch); l.v = take(p, ch); return l;
 }
+static int make_divisible8(int v) { int n = (v + 4) / 8 * 8; if (n < 8) n = 8; if (n < 0.9 * v) n += 8; return n; }   /* torchvision _make_divisible(v, 8) */
 static void v80_bind(v80_net* N, const float* blob, int nv, int np) {
-    const float* p = blob; int E = 3 * nv, Q = 40 * nv / 56; /* _make_divisible(168//4, 8) = 40 for nv=56 */
+    const float* p = blob; int E = 3 * nv, Q = make_divisible8(E / 4); /* _make_divisible(E // 4, 8): 40 / 56 / 64 for nv = 56 / 71 / 88 */
     N->nv = nv; N->np = np;
     N->first = take_lin_bn(&p, nv, nv, nv);
     for (int k = 0; k < 3; k++) {
@@ -898,7 +899,7 @@ static void token_linear(const lin_bn* l, int out, int in, const float* x, float
         }
 }
 static void ir_block(const irblock* B, int nv, const float* x, float* y, int hs, int se_max) {
-    int E = 3 * nv, Q = 40 * nv / 56;
+    int E = 3 * nv, Q = make_divisible8(E / 4);
     float e[3 * MAXROWS * 7], d[3 * MAXROWS * 7], sq[3 * MAXROWS], hid[64], sc[3 * MAXROWS], pr[MAXROWS * 7];
     token_linear(&B->expand, E, nv, x, e, hs ? 2 : 1);
     for (int c = 0; c < E; c++)                                  /* "depthwise": shared Linear(7->7) on the feature axis, BN per channel */

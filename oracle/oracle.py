@@ -225,7 +225,8 @@ def execute_episode_inj(cfg, init_board, u_full, u_move, chance_seed, noise=None
     """Coach.executeEpisode (Coach.py:37-84) on the oracle with injected randomness (see azo_execute_episode_inj).
     noise: list of per-ply Dirichlet vectors (may be ragged / empty for non-full plies) or None.
     Returns dict(boards, pi, z, valids, q: un-augmented examples; plies; actions; full)."""
-    A = GAME_ACTIONS[cfg.game]; shape = GAME_SHAPES[cfg.game]; npl = cfg.num_players
+    A = GAME_ACTIONS[cfg.game]; npl = cfg.num_players
+    shape = GAME_SHAPES[cfg.game] if cfg.game != GAME_SPLENDOR else (32 + 10 * npl + npl * npl, 7)
     P = len(u_full)
     dn = (cfg.dirichletAlpha != 0) if dirichlet_noise is None else dirichlet_noise
     m = MCTS(cfg, blob, dirichlet_noise=dn, seed=1)

@@ -194,3 +194,14 @@ def assert_examples_equal(got, gold, pi_tol=0.0):
         assert (np.asarray(zz, np.float32) == gold['ex_z'][i]).all(), f'example {i}: z {zz} vs {gold["ex_z"][i]}'
         assert (np.asarray(v).astype(bool) == gold['ex_valids'][i]).all(), f'example {i}: valids'
         assert (np.asarray(q, np.float32) == gold['ex_q'][i]).all(), f'example {i}: q'
+
+
+def load_splendor_np(n):
+    """Goldens of Splendor with n = 3 / 4 players (oracle/gen_golden_splendor_np.py): kat dict, MCTS cases, shipped-net vectors."""
+    kat = dict(np.load(os.path.join(GOLDEN, f'splendor{n}p_kat.npz')))
+    z = np.load(os.path.join(GOLDEN, f'splendor{n}p_mcts.npz'))
+    keys = ('cfg', 'root', 'n_sims', 'probs', 'q', 'raw_counts', 'noise', 'summary')
+    cases = [{k: z[f'c{i}_{k}'] for k in keys} for i in range(int(z['n_cases']))]
+    zn = np.load(os.path.join(GOLDEN, f'splendor{n}p_v80_shipped.npz'))
+    net = dict(sd={k[4:]: zn[k] for k in zn.files if k.startswith('sd__')}, boards=zn['boards'], valids=zn['valids'], pi=zn['pi'], v=zn['v'])
+    return kat, cases, net
