@@ -471,10 +471,12 @@ __device__ __noinline__ int new_leaf(const Dev<G>& d, int g, SelSmem<G>& ws, uin
         if (lane == 0) for (int p = 0; p < G::NP; p++) d.leaf_v[(size_t)g * G::NP + p] = es[p];
     } else {
         kind = LEAF_EXPAND;
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(d.nn_count, 1);            // one counter for all games: issued first, its round trip hides behind the legal-move test
         G::valid_mask(sb, 0, lane, ws.mask);
         for (int k = lane; k < G::MASK_WORDS; k += 32) d.leaf_mask[(size_t)g * G::MASK_WORDS + k] = ws.mask[k];
         warp_store_board<G>(d.nn_in + (size_t)g * G::SP, sb, lane);
-        if (lane == 0) { int pos = atomicAdd(d.nn_count, 1); d.nn_list[pos] = g; }
+        if (lane == 0) d.nn_list[pos] = g;
     }
     if (lane == 0) { d.leaf_key[2 * (size_t)g] = ws.key[0]; d.leaf_key[2 * (size_t)g + 1] = ws.key[1]; d.leaf_round[g] = (G::round(sb) & 0xFF) | (G::progress(sb) << 8); d.leaf_link[g] = link_slot; }
     return kind;
@@ -610,7 +612,10 @@ __device__ __forceinline__ void select_game(const Dev<G>& d, const int g, const 
         atomicAdd(&g_selprof[0], (unsigned long long)(clock64() - tp0)); atomicAdd(&g_selprof[1], (unsigned long long)tp_root); atomicAdd(&g_selprof[2], (unsigned long long)tp_mat);
         atomicAdd(&g_selprof[3], (unsigned long long)tp_leaf); atomicAdd(&g_selprof[4], 1ULL); atomicAdd(&g_selprof[5], (unsigned long long)n_mat); atomicAdd(&g_selprof[6], (unsigned long long)depth); }
 #endif
-    if (lane == 0) { *d.g_path_len(g, uni) = depth; d.leaf_kind[g] = kind; d.stats[(size_t)g * ST_N + ST_SELLEGAL] += (unsigned)sum_legal; d.stats[(size_t)g * ST_N + ST_ROOTLEGAL] += (unsigned)root_legal; }
+    if (lane == 0) {                                              // counters: reductions without a return value (no load to wait for before the warp can retire)
+        *d.g_path_len(g, uni) = depth; d.leaf_kind[g] = kind;
+        atomicAdd(&d.stats[(size_t)g * ST_N + ST_SELLEGAL], (unsigned long long)sum_legal); atomicAdd(&d.stats[(size_t)g * ST_N + ST_ROOTLEGAL], (unsigned long long)root_legal);
+    }
 }
 
 // One CTA per work item (persistent warps pulling tickets from a global counter were measured: no gain for k_select, a loss for k_backup).
@@ -672,7 +677,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
         const float inv = __fdiv_rn(1.0f, s);
         const int ni = d.n_nodes[g], eo = d.n_edges[g];
         if (ni >= d.node_cap || eo + L > d.edge_cap) {
-            if (lane == 0) st[ST_OVERFLOW]++;                    // arena full: value is still backed up, node not stored
+            if (lane == 0) atomicAdd(&st[ST_OVERFLOW], 1ULL);    // arena full: value is still backed up, node not stored
         } else {
             int before = 0;
             for (int k = 0; k < MW; k++) {
@@ -703,8 +708,8 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
                 NodeHdr h; h.c1 = 0.0; h.ns = 0; h.qs = v[0]; h.edge_off = (uint32_t)eo; h.n_legal = (uint16_t)L;
                 h.round = (uint8_t)d.leaf_round[g]; h.prog = (uint16_t)(d.leaf_round[g] >> 8); h.kind = NODE_EXPANDED; h.best = (uint16_t)nb; h.rsv1 = 0;
                 nodes[ni] = h; d.n_nodes[g] = ni + 1; d.n_edges[g] = eo + L;
-                st[ST_EXPANSIONS]++; st[ST_NNEVALS]++; st[ST_SUMLEGAL] += (unsigned)L;
-                if ((unsigned long long)(ni + 1) > st[ST_MAXNODES]) st[ST_MAXNODES] = (unsigned long long)(ni + 1);
+                atomicAdd(&st[ST_EXPANSIONS], 1ULL); atomicAdd(&st[ST_NNEVALS], 1ULL); atomicAdd(&st[ST_SUMLEGAL], (unsigned long long)L);
+                atomicMax(&st[ST_MAXNODES], (unsigned long long)(ni + 1));
             }
             ht_insert(d.g_ht(g), d.ht_cap, klo, khi, ni, lane);
         }
@@ -713,7 +718,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
         for (int p = 0; p < NP; p++) v[p] = d.leaf_v[(size_t)g * NP + p];
         if (kind == LEAF_NEW_TERMINAL) {                         // MCTS.py:130-135: terminal states are stored too
             const int ni = d.n_nodes[g], eo = d.n_edges[g];
-            if (ni >= d.node_cap || eo + 1 > d.edge_cap) { if (lane == 0) st[ST_OVERFLOW]++; }
+            if (ni >= d.node_cap || eo + 1 > d.edge_cap) { if (lane == 0) atomicAdd(&st[ST_OVERFLOW], 1ULL); }
             else {
                 const uint64_t klo = d.leaf_key[2 * (size_t)g], khi = d.leaf_key[2 * (size_t)g + 1];
                 const uint32_t ls = d.leaf_link[g];
@@ -730,7 +735,7 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
                 ht_insert(d.g_ht(g), d.ht_cap, klo, khi, ni, lane);
             }
         }
-        if (lane == 0) st[ST_TERMINAL]++;
+        if (lane == 0) atomicAdd(&st[ST_TERMINAL], 1ULL);
     }
 #if AZG_SEL_PROF == 2
     bp1 = clock64();
@@ -769,10 +774,25 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
 #if AZG_SEL_PROF == 2
         __syncwarp(); bp2 += clock64() - bp1;
 #endif
-        // ---- refresh the cached PUCT choice of every updated non-root node (what the next visit will follow), one lane per level:
-        //      each lane streams the edge list of its own node (the only edge that changed is the one it just wrote itself). The
-        //      root is always scanned in full by k_select and is skipped here.
-        if (lvl > 0 && lvl < depth && hn.kind == NODE_EXPANDED && pe.n_legal > 0) {
+        // ---- refresh the cached PUCT choice of every updated non-root node (what the next visit will follow). The root is always
+        //      scanned in full by k_select and is skipped here. Two forms with the same (exact) result:
+        //      * short paths (the common case in the opening: a handful of levels): the WARP takes the nodes one after the other, all
+        //        lanes stream one node's edges coalesced (best_edge), one memory round trip per node;
+        //      * long paths: one LANE per level, each lane streams the edge list of its own node (best_edge_lane): up to 32 independent
+        //        edge streams per warp instead of one per round trip.
+        if (depth <= 7 && base == 0) {
+            __syncwarp();                                        // the updated edges / headers of all levels are visible to the whole warp
+            for (int l = 1; l < depth; l++) {
+                const uint32_t nd = __shfl_sync(FULL, pe.node, l), eoff = __shfl_sync(FULL, pe.edge_off, l), nl = __shfl_sync(FULL, pe.n_legal, l);
+                const double c1 = __shfl_sync(FULL, hn.c1, l); const int ns = __shfl_sync(FULL, hn.ns, l); const float qs = __shfl_sync(FULL, hn.qs, l);
+                const int knd = __shfl_sync(FULL, (int)hn.kind, l);
+                if (knd != NODE_EXPANDED || nl == 0) continue;
+                const int nb = best_edge(edges + eoff, (int)nl, c1, d.cpuct, ns, qs, d.fpu, lane);
+                if (lane == 0) nodes[nd].best = (uint16_t)nb;
+                if (lane < d.U) bestlink[(size_t)nd * d.U + lane] = child[(size_t)(eoff + nb) * d.U + lane];
+                if (lane == 0) ref_legal += (int)nl;
+            }
+        } else if (lvl > 0 && lvl < depth && hn.kind == NODE_EXPANDED && pe.n_legal > 0) {
             const int nb = best_edge_lane(edges + pe.edge_off, (int)pe.n_legal, hn.c1, d.cpuct, hn.ns, hn.qs, d.fpu);
             nodes[pe.node].best = (uint16_t)nb;
             for (int u = 0; u < d.U; u++) bestlink[(size_t)pe.node * d.U + u] = child[(size_t)(pe.edge_off + nb) * d.U + u];
@@ -784,9 +804,8 @@ __device__ __forceinline__ void backup_game(const Dev<G>& d, const int g, const 
     if (lane == 0) { const long long e = clock64(); atomicAdd(&g_selprof[7], 1ULL); atomicAdd(&g_selprof[0], (unsigned long long)(e - bp0)); atomicAdd(&g_selprof[1], (unsigned long long)(bp1 - bp0));
         atomicAdd(&g_selprof[2], (unsigned long long)bp2); atomicAdd(&g_selprof[3], (unsigned long long)(e - bp1 - bp2)); }
 #endif
-    if (lane == 0) st[ST_REFLEGAL] += (unsigned)ref_legal;
     if (lane == 0) {
-        st[ST_SIMS]++; st[ST_VISITS] += (unsigned)depth;
+        atomicAdd(&st[ST_REFLEGAL], (unsigned long long)ref_legal); atomicAdd(&st[ST_SIMS], 1ULL); atomicAdd(&st[ST_VISITS], (unsigned long long)depth);
         if (d.ragged) {                                          // this slot's next simulation; budget spent => its move is made by k_sp_turn
             d.sim_idx[g] = step + 1;
             if (step + 1 >= d.n_sims[g]) d.turn_list[atomicAdd(d.turn_count, 1)] = g;

@@ -119,6 +119,32 @@ def gen_mcts(out):
     np.savez_compressed(os.path.join(out, 'abalone_mcts.npz'), **save)
 
 
+def gen_mcts1600(out):
+    """BASELINE.json configs[4] runs numMCTSSims = 1600: two reference searches of that length (opening position with the main.py
+    defaults; a mid-game position with the shipped-style arguments incl. injected root noise), same format as abalone_mcts.npz."""
+    from abalone.AbaloneGame import AbaloneGame
+    from MCTS import MCTS
+    kat = np.load(os.path.join(out, 'abalone_kat.npz'))
+    g = AbaloneGame(); net = HashNet(g)
+    idx0 = np.flatnonzero(kat['game'] == 0)
+    cases = []
+    for ci, (name, p) in enumerate((('default', int(idx0[0])), ('shipped', int(idx0[len(idx0) // 2])))):
+        cfg = MCTS_CONFIGS[name]; args = dotdict(cfg, numMCTSSims=1600)
+        m = MCTS(g, net, args, dirichlet_noise=cfg['noise']); rr = RecordingRng(1600 + ci); m.rng = rr
+        root = np.array(kat['canonical'][p], copy=True)
+        probs, q, full = m.getActionProb(root, temp=1, force_full_search=True)
+        raw = np.array(m.nodes_data[g.stringRepresentation(root)][5], dtype=np.int64); nz = np.flatnonzero(raw)
+        cases.append(dict(cfg=name, root=root, n_sims=1600, q=np.array(q, dtype=np.float32), raw_idx=nz.astype(np.int32), raw_cnt=raw[nz],
+                          probs_nz=np.array(probs, dtype=np.float64)[np.flatnonzero(np.array(probs))], probs_idx=np.flatnonzero(np.array(probs)).astype(np.int32),
+                          noise=(rr.dirichlets[0] if rr.dirichlets else np.zeros(0)), summary=tree_summary(m)))
+        print(f'abalone mcts1600 {name} root#{p} nodes={cases[-1]["summary"]} top={int(np.argmax(raw))}:{int(raw.max())}')
+    save = {'n_cases': np.array(len(cases))}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            save[f'c{i}_{k}'] = np.array(v)
+    np.savez_compressed(os.path.join(out, 'abalone_mcts1600.npz'), **save)
+
+
 def gen_episode(out):
     from abalone.AbaloneGame import AbaloneGame
     from MCTS import MCTS
@@ -198,6 +224,8 @@ def main():
         gen_kat(a.out)
     if 'mcts' in only:
         gen_mcts(a.out)
+    if 'mcts1600' in only:
+        gen_mcts1600(a.out)
     if 'episode' in only:
         gen_episode(a.out)
     if 'net' in only:

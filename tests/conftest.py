@@ -116,7 +116,17 @@ def azul_episode():
 
 @pytest.fixture(scope='session')
 def aba_mcts_cases():
-    z = np.load(os.path.join(GOLDEN, 'abalone_mcts.npz'))
+    return _aba_cases('abalone_mcts.npz')
+
+
+@pytest.fixture(scope='session')
+def aba_mcts1600_cases():
+    """numMCTSSims = 1600, the length BASELINE.json configs[4] runs (oracle/gen_golden_abalone.py --only mcts1600)."""
+    return _aba_cases('abalone_mcts1600.npz')
+
+
+def _aba_cases(fname):
+    z = np.load(os.path.join(GOLDEN, fname))
     n = int(z['n_cases'])
     keys = ('cfg', 'root', 'n_sims', 'q', 'raw_idx', 'raw_cnt', 'probs_nz', 'probs_idx', 'noise', 'summary')
     out = []

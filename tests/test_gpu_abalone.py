@@ -76,6 +76,20 @@ def test_search_matches_reference(game, hashnet, aba_mcts_cases):
         m.engine.close()
 
 
+def test_search_1600_sims_matches_reference(game, hashnet, aba_mcts1600_cases):
+    """numMCTSSims = 1600 (BASELINE.json configs[4]): root visit counts of the reference, exact."""
+    for case in aba_mcts1600_cases:
+        args, noise = _args(str(case['cfg']), case['n_sims'])
+        m = MCTS(game, hashnet, args, dirichlet_noise=noise, node_cap=4096)
+        probs, q, full = m.getActionProb(case['root'], temp=1, force_full_search=True, noise=case['noise'])
+        assert (m.last_raw_counts == case['raw_counts']).all(), str(case['cfg'])
+        np.testing.assert_allclose(np.array(probs), case['probs'], rtol=0, atol=1e-5)
+        assert (np.array(q, np.float32) == case['q']).all()
+        st = m.engine.stats()
+        assert st['sims'] == 1600 and st['arena_overflows'] == 0 and st['gc_sweeps'] == 0
+        m.engine.close()
+
+
 def test_tree_reuse_episode_matches_reference(game, hashnet, aba_episode):
     ep = aba_episode
     args, _ = _args('default', ep['n_sims'])

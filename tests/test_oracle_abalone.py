@@ -57,6 +57,12 @@ def test_mcts_counts_exact(aba_mcts_cases):
         assert list(m.stats()[:3]) == list(case['summary'])
 
 
+def test_mcts_1600_sims_exact(aba_mcts1600_cases):
+    """The search length of BASELINE.json configs[4]."""
+    assert len(aba_mcts1600_cases) == 2
+    test_mcts_counts_exact(aba_mcts1600_cases)
+
+
 def test_episode_tree_reuse_exact(aba_episode):
     ep = aba_episode
     cfg, _ = _cfg('default', ep['n_sims'])
