@@ -108,7 +108,8 @@ __device__ __forceinline__ void token_linear(const float* __restrict__ Wt, const
         float acc[8]; const float bb = __ldg(b + o);
 #pragma unroll
         for (int l = 0; l < 8; l++) acc[l] = bb;
-        for (int i = 0; i < in; i++) fma8(acc, __ldg(Wt + i * out + o), ld8(X + (i * F + f) * TM_TB));
+#pragma unroll 4
+        for (int i = 0; i < in; i++) fma8(acc, __ldg(Wt + i * out + o), ld8(X + (i * F + f) * TM_TB));   // 4 weight + 8 activation loads in flight per thread
         if (R) { const F8 r = ld8(R + (o * F + f) * TM_TB); const float rr[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
 #pragma unroll
             for (int l = 0; l < 8; l++) acc[l] += rr[l]; }
@@ -126,6 +127,7 @@ __device__ __forceinline__ void dense_partial(const float* __restrict__ Wt, int 
 #pragma unroll
         for (int l = 0; l < 8; l++) acc[l] = 0.f;
         const int k1 = min(K, (ks + 1) * per);
+#pragma unroll 4
         for (int k = ks * per; k < k1; k++) fma8(acc, __ldg(Wt + k * out + o), ld8(X + k * TM_TB));
         st8(PART + (ks * out + o) * TM_TB, acc);
     }
@@ -145,9 +147,10 @@ __device__ __forceinline__ void dense_reduce(const float* PART, const float* __r
 template <int NV, int F, int A, int NP, int EMAX, int OMAX, int QMAX> struct TokMixSmem {
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int VKS = 32;                                // K split of the value head
+    static constexpr int PKS = A <= 96 ? 6 : 4;                   // K split of the two policy Linears (A x PKS work items for 256 threads)
     static constexpr int X = 0, T = X + NV * F * 8, E = T + NV * F * 8, D = E + EMAX * F * 8, H = D + EMAX * F * 8, SQ = H + OMAX * F * 8,
                          HID = SQ + EMAX * 8, PART = HID + cmax(QMAX, NP) * 8,
-                         PART_N = cmax(cmax(8 * QMAX, 2 * EMAX), cmax(2 * A, VKS * NP)) * 8, H1 = PART + PART_N, TOTAL = H1 + A * 8;
+                         PART_N = cmax(cmax(8 * QMAX, 2 * EMAX), cmax(PKS * A, VKS * NP)) * 8, H1 = PART + PART_N, TOTAL = H1 + A * 8;
     static constexpr size_t bytes() { return (size_t)TOTAL * 4; }
 };
 
@@ -216,13 +219,13 @@ k_tokmix_forward(const float* __restrict__ P, const __grid_constant__ TokMixLayo
         token_linear<F>(P + B.wp, P + B.bp, B.out, B.E, D, OUT, 0, B.res ? IN : nullptr, t);
         __syncthreads();
         if (k == 1) {   // ---- policy head: Linear(out*F -> A) + ReLU, Linear(A -> A), masked log_softmax -> exp
-            dense_partial(P + L.pi2, A, B.out * F, 2, H, PART, t);
+            dense_partial(P + L.pi2, A, B.out * F, SM::PKS, H, PART, t);
             __syncthreads();
-            dense_reduce(PART, P + L.bpi2, A, 2, H1, 1, t);
+            dense_reduce(PART, P + L.bpi2, A, SM::PKS, H1, 1, t);
             __syncthreads();
-            dense_partial(P + L.pi4, A, A, 2, H1, PART, t);
+            dense_partial(P + L.pi4, A, A, SM::PKS, H1, PART, t);
             __syncthreads();
-            dense_reduce(PART, P + L.bpi4, A, 2, H1, 0, t);
+            dense_reduce(PART, P + L.bpi4, A, SM::PKS, H1, 0, t);
             __syncthreads();
             {
                 const int sl = warp, slot = slot_of[sl];          // 8 warps = 8 leaves

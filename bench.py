@@ -43,11 +43,11 @@ N_PL = 2
 GAMES = {
     'splendor': dict(S=392, A=81, flops=2 * 521205, games=16384, universes=3, net='SplendorNNet V80 (142406 params, random init seed 0)',
                      tag='splendor2p_chance_universes3'),
-    'santorini': dict(S=75, A=162, flops=2 * 9259428, games=4096, universes=1, net='SantoriniNNet V89 (381454 params, random init seed 0)',
+    'santorini': dict(S=75, A=162, flops=2 * 9259428, games=4096, universes=1, node_cap_per_sim=16, net='SantoriniNNet V89 (381454 params, random init seed 0)',
                       tag='santorini_nogods'),
     'abalone': dict(S=324, A=3402, flops=2 * 1050360, games=2048, universes=1, net='AbaloneNNet V21 (35862 params, random init seed 0)',
                     tag='abalone_belgian_daisy', sims=1600),
-    'azul': dict(S=138, A=180, flops=2 * 203708, games=16384, universes=2, net='AzulNNet V84 (118 k params, random init seed 0)', tag='azul2p_universes2'),
+    'azul': dict(S=138, A=180, flops=2 * 203708, games=8192, universes=2, node_cap_per_sim=12, net='AzulNNet V84 (118 k params, random init seed 0)', tag='azul2p_universes2'),
 }
 
 
@@ -58,9 +58,9 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--game', default='splendor', choices=sorted(GAMES), help='splendor = BASELINE.json configs[2] (headline metric), santorini = configs[1], abalone = configs[4] (2048 games per GPU), azul = the first SURVEY 8f game')
-    ap.add_argument('--games', type=int, default=0, help='concurrent games per GPU (0 = the config default: 16384 splendor / 4096 santorini / 2048 abalone)')
+    ap.add_argument('--games', type=int, default=0, help='concurrent games per GPU (0 = the config default: 16384 splendor / 4096 santorini / 2048 abalone / 8192 azul)')
     ap.add_argument('--sims', type=int, default=0, help='numMCTSSims (0 = the config default: 800, abalone 1600)')
-    ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 6 x sims + 320)')
+    ap.add_argument('--node-cap', type=int, default=0, help='nodes per tree arena (0 = 6 x sims + 320; santorini 16 x, azul 12 x)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-pcr', action='store_true', help='skip the secondary line with the reference-default playout-cap randomisation (prob_fullMCTS 0.25, ratio 5)')
     ap.add_argument('--no-iteration', action='store_true', help='skip the secondary whole-iteration leg (complete games -> example drain -> NCCL gather -> symmetries)')
@@ -354,7 +354,7 @@ def main():
         game = azg_b200.AbaloneGame(); net = azg_b200.AbaloneNNetWrapper(game, {'nn_version': 21}, seed=0)
     S_BYTES, N_ACT = gm['S'], gm['A']
     a = mcts_args(args.sims, args.game)
-    node_cap = args.node_cap or (6 * args.sims + 320)
+    node_cap = args.node_cap or (gm.get('node_cap_per_sim', 6) * args.sims + 320)      # sized so that the tier-2 GC (gc_sweeps) never runs in the timed region
     from azg_b200.dist import gather_examples, shard_games
     first_game, _ = shard_games(args.games * world, rank, world)               # global slot ids: the games do not depend on the world size
     eng = Engine(game, net, a, n_games=args.games, dirichlet_noise=True, seed=1000, node_cap=node_cap, first_game=first_game)
