@@ -563,7 +563,7 @@ struct EngineT : azg_engine {
     int sims_full = 0, sims_fast = 0;
     bool sp_ready = false;
     bool ragged_env = true, rag_started = false;   // ragged self-play (per-slot move boundaries), see selfplay_ragged
-    bool profiling = false; std::vector<cudaEvent_t> ev; size_t ev_used = 0; std::vector<int> ev_kind; double prof_ms[4] = {0, 0, 0, 0}; long long prof_n[4] = {0, 0, 0, 0};
+    bool profiling = false; int prof_every = 1; bool prof_now = true; std::vector<cudaEvent_t> ev; size_t ev_used = 0; std::vector<int> ev_kind; double prof_ms[4] = {0, 0, 0, 0}; long long prof_n[4] = {0, 0, 0, 0};
 
     template <class T> int alloc(T** p, size_t n, bool zero = true) {
         void* q = nullptr;
@@ -630,7 +630,7 @@ struct EngineT : azg_engine {
 
     // ---- optional per-kernel timing: an event before and after each launch, drained by prof_drain() ----
     void prof_mark(int kind, cudaStream_t st) {              // kind >= 0: start of a launch of that kind; -1: end
-        if (!profiling) return;
+        if (!profiling || !prof_now) return;
         if (ev_used == ev.size()) { cudaEvent_t x; cudaEventCreate(&x); ev.push_back(x); ev_kind.push_back(0); }
         ev_kind[ev_used] = kind;
         cudaEventRecord(ev[ev_used++], st);
@@ -646,9 +646,9 @@ struct EngineT : azg_engine {
         }
         ev_used = 0; return 0;
     }
-    int profile(int enable) override {
-        if (prof_drain()) return 1;
-        profiling = enable != 0;
+    int profile(int enable) override {                        // enable = N > 1: only every N-th lock-step simulation is timed (the events of the
+        if (prof_drain()) return 1;                           // others are not recorded: 6 event records per simulation cost ~4 % of the loop)
+        profiling = enable != 0; prof_every = enable > 1 ? enable : 1; prof_now = true;
         if (enable) for (int k = 0; k < 4; k++) { prof_ms[k] = 0; prof_n[k] = 0; }
         return 0;
     }
@@ -662,6 +662,8 @@ struct EngineT : azg_engine {
     // One lock-step simulation for every game: select -> batched leaf evaluation -> expand + backup.
     int step(int s, cudaStream_t st) {
         const int NG = d.n_games;
+        prof_now = (s % prof_every) == 0;                     // sampled timing; the per-move kernels (begin / end / gc) are always timed
+        struct Unsample { bool& f; ~Unsample() { f = true; } } unsample{prof_now};
         prof_mark(PK_SELECT, st);
         k_select<G><<<(unsigned)((NG + selk_warps<G>() - 1) / selk_warps<G>()), selk_warps<G>() * 32, 0, st>>>(d, s);
         prof_mark(PK_NET, st);

@@ -100,7 +100,8 @@ class Engine:
         return o
 
     def profile(self, enable):
-        _lib.check(self._L.azg_engine_profile(self.h, int(bool(enable))))
+        """True / 1: time every launch; N > 1: time every N-th lock-step simulation (sampled); False / 0: off."""
+        _lib.check(self._L.azg_engine_profile(self.h, int(enable)))
 
     def kernel_times(self):
         out = np.zeros(8, np.float64)

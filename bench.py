@@ -364,7 +364,8 @@ def main():
     # ---- device-resident arm ------------------------------------------------------------------------
     eng.selfplay(max_moves=W)                                                  # warm-up plies (untimed)
     s0 = eng.stats()
-    eng.profile(True)
+    PROF_EVERY = 8                                                             # CUDA events around every 8th lock-step simulation of the timed region
+    eng.profile(PROF_EVERY)                                                    # (around EVERY launch they cost ~4 % of the loop: 6 event records per simulation)
     clocks = ClockSampler(local)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -384,8 +385,9 @@ def main():
     # ---- roofline of the dominant kernel (rank 0's launches; all ranks run the same kernels) --------------
     pk = peaks()
     visits, exps, evals = d['node_visits'], d['expansions'], d['nn_evals']
+    samp = max(int(kt['select_launches']), 1) / max(d['sims'] / args.games, 1)   # fraction of the simulations whose launches were timed
     Lbar_vis = d['sum_legal_visited'] / max(visits, 1); Lbar_exp = d['sum_legal'] / max(exps, 1); Dbar = visits / max(d['sims'], 1)
-    n_launch = max(int(kt['select_launches']), 1)
+    n_launch = max(int(kt['select_launches']), 1) / samp                       # launches in the timed region (bytes / flops below are totals of the region)
     # Algorithmic bytes PER KERNEL: what each kernel itself has to touch in this engine's data layout, counted from
     # the engine's own counters of the same run. SP = board slot padded to 16 B, MW = mask words, U = child links per edge.
     #   k_select : per visit the 32 B node header + 4 B cached link + 16 B path record; the root is scanned in full (16 B edge + 4 B link
@@ -410,23 +412,24 @@ def main():
     net_flops = float(gm['flops']) * evals
     tree_ms = kt['select_ms'] + kt['backup_ms']
     kern = {
-        'select': {'ms': kt['select_ms'], 'bound': 'hbm', 'achieved': sel_bytes / max(kt['select_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
+        'select': {'ms': kt['select_ms'], 'bound': 'hbm', 'achieved': sel_bytes * samp / max(kt['select_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
                    'per_launch_bytes': sel_bytes / n_launch,
-                   'survey_B_sel_frac': survey_sel_bytes / max(kt['select_ms'], 1e-9) / 1e6 / pk['hbm'],
+                   'survey_B_sel_frac': survey_sel_bytes * samp / max(kt['select_ms'], 1e-9) / 1e6 / pk['hbm'],
                    'survey_B_sel_note': 'SURVEY 8d books 16 + 14 L bytes per select step (a design that re-scans every visited node); this engine follows a cached choice (52 B per non-root visit), so it moves fewer bytes than that model'},
-        'net': {'ms': kt['net_ms'], 'bound': 'tensor', 'achieved': net_flops / max(kt['net_ms'], 1e-9) / 1e9, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+        'net': {'ms': kt['net_ms'], 'bound': 'tensor', 'achieved': net_flops * samp / max(kt['net_ms'], 1e-9) / 1e9, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
                     'per_launch_flops': net_flops / n_launch},
-        'expand_backup': {'ms': kt['backup_ms'], 'bound': 'hbm', 'achieved': bak_bytes / max(kt['backup_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
+        'expand_backup': {'ms': kt['backup_ms'], 'bound': 'hbm', 'achieved': bak_bytes * samp / max(kt['backup_ms'], 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
                           'per_launch_bytes': bak_bytes / n_launch},
     }
-    tree_path = {'ms': tree_ms, 'bound': 'hbm', 'achieved': survey_bytes / max(tree_ms, 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
-                 'per_step_bytes': survey_bytes / n_launch, 'frac': survey_bytes / max(tree_ms, 1e-9) / 1e6 / pk['hbm'],
+    tree_path = {'ms': tree_ms, 'bound': 'hbm', 'achieved': survey_bytes * samp / max(tree_ms, 1e-9) / 1e6, 'peak': pk['hbm'], 'unit': 'GB/s',
+                 'per_step_bytes': survey_bytes / n_launch, 'frac': survey_bytes * samp / max(tree_ms, 1e-9) / 1e6 / pk['hbm'],
                  'note': 'SURVEY.md 8d bytes of select + expand + backup (B_sel + B_bak + B_exp + B_nn) over the time of k_select + k_backup'}
-    tot_ms = kt['select_ms'] + kt['net_ms'] + kt['backup_ms'] + kt['other_ms']
+    tot_ms = kt['select_ms'] + kt['net_ms'] + kt['backup_ms'] + kt['other_ms'] / PROF_EVERY      # the per-move kernels are timed at every move, the simulations sampled
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')                          # dram bytes per launch from the committed ncu --set full captures
     tj = (json.load(open(tp)).get(args.game) or {}) if os.path.exists(tp) else {}  # per game: only captures of the same workload count
     for name, v in kern.items():
-        v['frac'] = v['achieved'] / v['peak']; v['share'] = v['ms'] / max(tot_ms, 1e-9); v['avg_launch_us'] = 1e3 * v['ms'] / n_launch
+        v['frac'] = v['achieved'] / v['peak']; v['share'] = v['ms'] / max(tot_ms, 1e-9); v['avg_launch_us'] = 1e3 * v['ms'] / max(int(kt['select_launches']), 1)
+        v['timed_launches'] = int(kt['select_launches'])
         v['dram_bytes_per_launch_ncu'] = tj.get(name)
         if tj.get(name) and 'per_launch_bytes' in v:
             v['dram_over_algorithmic'] = tj[name] / v['per_launch_bytes']

@@ -183,7 +183,8 @@ int azg_engine_selfplay_state(azg_engine* e, int8_t* boards, int32_t* players, i
 int azg_engine_stats(azg_engine* e, int64_t* out_stats);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch of the search loop).
- * enable=1 starts collecting (slows the loop down slightly: use a separate measuring pass), enable=0 stops.
+ * enable=1 starts collecting for every launch (6 event records per simulation: ~4 % slower loop), enable=N>1 times only every N-th
+ * lock-step simulation (sampled: negligible overhead; the per-move kernels are always timed), enable=0 stops.
  * azg_engine_kernel_times drains the events: out8 = [0] select ms [1] leaf-eval (net) ms [2] expand+backup ms
  * [3] other (gc, move begin/end, finish) ms [4] profiled lock-step simulations [5] select launches
  * [6] net launches [7] backup launches. */
