@@ -8,7 +8,7 @@
 //                            kernel, net_v80_tc.cuh)
 // fp32 on the CUDA cores: these are the "next" games of SURVEY 8f, not the headline configuration.
 //
-// One CTA = 8 leaves, 256 threads. Activations live in shared memory as [feature index][leaf] (the 8 leaves of a feature are two
+// One CTA = 8 leaves, 512 threads. Activations live in shared memory as [feature index][leaf] (the 8 leaves of a feature are two
 // 128-bit words), so one thread owns one output feature for all 8 leaves: per input it needs ONE weight (K-major images, coalesced
 // across the threads' outputs, L1/L2 resident) and two 128-bit shared loads for 8 FMAs. Layers with few outputs (SE fc1, the value
 // head) split K over thread groups and add the partial sums in a fixed order (bit-reproducible results). BatchNorm (eval mode) is
@@ -19,7 +19,7 @@
 
 namespace azg {
 
-constexpr int TM_TB = 8, TM_THREADS = 256;
+constexpr int TM_TB = 8, TM_THREADS = 512;   // 16 warps per CTA: the phases are latency-bound (L2 weight loads, barriers), more warps hide more of it
 struct TokMixBlk { int in, E, out, Q, act, res, se_max; int we, be, dw, sd, td, w1, b1, w2, b2, wp, bp; };
 struct TokMixLayout { int nv, f, a, np; int w0, b0; TokMixBlk blk[3]; int pi2, bpi2, pi4, bpi4, v2, bv2, v4, bv4; int total; };
 
@@ -147,7 +147,7 @@ __device__ __forceinline__ void dense_reduce(const float* PART, const float* __r
 template <int NV, int F, int A, int NP, int EMAX, int OMAX, int QMAX> struct TokMixSmem {
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int VKS = 32;                                // K split of the value head
-    static constexpr int PKS = A <= 96 ? 6 : 4;                   // K split of the two policy Linears (A x PKS work items for 256 threads)
+    static constexpr int PKS = A <= 96 ? 6 : 4;                   // K split of the two policy Linears (A x PKS work items for the CTA's threads)
     static constexpr int X = 0, T = X + NV * F * 8, E = T + NV * F * 8, D = E + EMAX * F * 8, H = D + EMAX * F * 8, SQ = H + OMAX * F * 8,
                          HID = SQ + EMAX * 8, PART = HID + cmax(QMAX, NP) * 8,
                          PART_N = cmax(cmax(8 * QMAX, 2 * EMAX), cmax(PKS * A, VKS * NP)) * 8, H1 = PART + PART_N, TOTAL = H1 + A * 8;
@@ -228,7 +228,7 @@ k_tokmix_forward(const float* __restrict__ P, const __grid_constant__ TokMixLayo
             dense_reduce(PART, P + L.bpi4, A, SM::PKS, H1, 0, t);
             __syncthreads();
             {
-                const int sl = warp, slot = slot_of[sl];          // 8 warps = 8 leaves
+                const int sl = warp & 7, slot = warp < TM_TB ? slot_of[sl] : -1;   // warps 0-7 = the 8 leaves
                 if (slot >= 0) {
                     float lg[MW]; float mx = -INFINITY;
 #pragma unroll
