@@ -476,7 +476,7 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
         net->TI = v80tc_layout();
         const char* kv = getenv("AZG_V80_KERNEL");
         net->v80_kernel = (kv && !strcmp(kv, "fp32")) ? 0 : 1;
-        if (getenv("AZG_V80_PROF")) { if (cudaMalloc(&net->prof, 64 * sizeof(long long)) != cudaSuccess) net->prof = nullptr; else cudaMemset(net->prof, 0, 64 * sizeof(long long)); }
+        if (getenv("AZG_V80_PROF")) { if (cudaMalloc(&net->prof, 704 * sizeof(long long)) != cudaSuccess) net->prof = nullptr; else cudaMemset(net->prof, 0, 704 * sizeof(long long)); }
         if (cudaMalloc(&net->blob, sizeof(float) * (size_t)net->L.total) != cudaSuccess) { delete net; return fail("cudaMalloc weights failed"); }
         if (cudaMalloc(&net->img, sizeof(float) * (size_t)net->TI.total) != cudaSuccess) { cudaFree(net->blob); delete net; return fail("cudaMalloc weight images failed"); }
         if (azg_net_load(net, weights, n_weights)) { cudaFree(net->blob); cudaFree(net->img); delete net; return 1; }
@@ -500,6 +500,10 @@ extern "C" int azg_net_create(int net_kind, int game_id, int np, const float* we
 }
 extern "C" int azg_debug_selprof(unsigned long long* out8) {      // debug: see g_selprof (only filled when built with -DAZG_SEL_PROF)
     CK(cudaDeviceSynchronize()); CK(cudaMemcpyFromSymbol(out8, azg::g_selprof, 8 * sizeof(unsigned long long))); CK(cudaMemcpyFromSymbol(out8 + 8, azg::g_selprof2, 8 * sizeof(unsigned long long))); return 0;
+}
+extern "C" int azg_net_prof_ctas(azg_net* net, long long* out640) {   // debug (V80 only): per CTA {entry, prologue done, exit} in globaltimer ns + SM id
+    if (!net || !net->prof || net->kind != AZG_NET_SPLENDOR_V80) return fail("profiling not enabled (AZG_V80_PROF=1)");
+    CK(cudaDeviceSynchronize()); CK(cudaMemcpy(out640, net->prof + 64, 640 * sizeof(long long), cudaMemcpyDeviceToHost)); return 0;
 }
 extern "C" int azg_net_prof(azg_net* net, long long* out64) {      // debug: phase timestamps (SM clock) of CTA 0's first tiles
     if (!net || !net->prof) return fail("profiling not enabled (AZG_V80_PROF=1 / AZG_V89_PROF=1)");

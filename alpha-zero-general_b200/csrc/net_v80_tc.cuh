@@ -147,7 +147,9 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
     using namespace tc;
     constexpr int NV = 56, EC = 168, Q = V80_Q, TB = TC_TB, LD = 128, A = 81, PIP = V80Layout::PIP;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-aligned base as symbol + offset: the pointer stays in the shared state space (LDS / STS). Rounding the generic address instead
+    // turns every access below into a generic LD.E / ST.E.
+    uint8_t* sm = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t bars[B_N];
     __shared__ uint32_t tmem_s;
     __shared__ int slot_of[TB], slot_next[TB];
@@ -155,6 +157,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
     const int count = count_ptr ? min(*count_ptr, n_max) : n_max;
     const int ntiles = (count + TB - 1) / TB;
     if ((int)blockIdx.x >= ntiles) return;
+    if (prof && t == 0 && blockIdx.x < 160) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); prof[64 + 4 * blockIdx.x] = g; }   // debug: CTA timeline (ns)
     float* XH = reinterpret_cast<float*>(sm + TC_XH);
     float* SQ = reinterpret_cast<float*>(sm + TC_SQ); float* HID = reinterpret_cast<float*>(sm + TC_HID); float* VH = reinterpret_cast<float*>(sm + TC_VH);
     uint8_t* ESTG = sm + TC_ESTG; uint8_t* WRING = sm + TC_WRING;
@@ -175,10 +178,16 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
     const uint32_t tm = tmem_s;
     const uint32_t tlane = tm + ((uint32_t)(32 * q) << 16);       // this warp's TMEM lane quarter
     if (t == 0) { for (int i = 0; i < 4; i++) mbar_arrive(&bars[B_EF0 + i]); }   // the four E stages start out free
+    if (prof && t == 0 && blockIdx.x < 160) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); prof[64 + 4 * blockIdx.x + 1] = g; }
     Phase ph;
     uint32_t rb[4] = {0u, 0u, 0u, 0u};                          // this thread's words of the next tile's raw boards (cross-tile prefetch)
     int prof_i = 0;
 #define TC_STAMP() do { if (prof && t == 0 && blockIdx.x == 0 && prof_i < 64) prof[prof_i++] = clock64(); } while (0)
+#ifdef AZG_TC_FINE_PROF
+#define TC_FSTAMP() do { if (b == 0) TC_STAMP(); } while (0)      /* debug build: extra stamps inside the phases of block 0 */
+#else
+#define TC_FSTAMP() do { } while (0)
+#endif
     const uint32_t xh_a = smem_u32(sm + TC_XH), xl_a = smem_u32(sm + TC_XL), estg_a = smem_u32(ESTG), wring_a = smem_u32(WRING);
     constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
     const float* IMGb = IMG;
@@ -289,7 +298,9 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 const uint32_t ta = tlane + TC_DE + 32 * sub;
                 if (b == 0) depthwise_unit<1, false>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
                 else depthwise_unit<2, true>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
+                TC_FSTAMP();   /* f: unit 1 done */
                 ph.wait(bars, B_MM2); tc_fence_after();
+                TC_FSTAMP();   /* f: MM2 wait done */
                 {   // X has been consumed by the expand MMAs. The block input (the residual of the project epilogue, and for the policy block
                     // also the input of the value block) is parked in spare TMEM columns as fp32, which frees X's 64 KB of shared memory
                     // as E stages 2 and 3 for the gated operand pass below.
@@ -315,6 +326,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     load(bars, B_WP1, WRING + 16384, IMGb + I.wp[b] + 3 * 4096, 16384);
                 }
                 __syncwarp();
+                TC_FSTAMP();   /* f: parked */
                 if (q < 2) {
                     const int c2 = 128 + c; const bool ok = c2 < EC; const int cc = ok ? c2 : 0;
                     const float be2 = SB[SV_BE + cc], sd2 = SB[SV_SD + cc], td2 = SB[SV_TD + cc];
@@ -322,6 +334,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     else depthwise_unit<2, true>(ta + 128, be2, sd2, td2, dw, SQ + cc * TB + 4 * sub, ok);
                 }
                 tmem_wait_st();
+                TC_FSTAMP();   /* f: unit 2 done */
             }
             __syncthreads();
             TC_STAMP();   /* b2: depthwise done */
@@ -351,9 +364,12 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #pragma unroll
                     for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(HP + part * 640 + (4 * qg + i) * TB + 4 * lq) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
                 }
+                TC_FSTAMP();   /* f: fc1 partials */
                 __syncthreads();
+                TC_FSTAMP();   /* f: barrier */
                 for (int i = t; i < Q * TB; i += TC_THREADS) HID[i] = fmaxf(HP[i] + HP[640 + i] + HP[1280 + i] + HP[1920 + i] + SB[SV_B1 + (i >> 4)], 0.f);
                 __syncthreads();
+                TC_FSTAMP();   /* f: hidden done + barrier */
                 if (t < (EC / 4) * 4) {                            // 42 channel quads x 4 leaf quads
                     const int cq = t >> 2, lq = t & 3;
                     float g[4][4];
@@ -377,6 +393,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                                         fminf(fmaxf(g[i][2] + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g[i][3] + bb, 0.f), 6.f) * (1.f / 6.f));
                     }
                 }
+                TC_FSTAMP();   /* f: fc2 done */
             }
             __syncthreads();
             TC_STAMP();   /* b4: SE done */
@@ -673,6 +690,10 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         TC_STAMP();   /* tile end */
     }
     tc_fence_before(); __syncthreads();
+    if (prof && t == 0 && blockIdx.x < 160) {
+        long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); prof[64 + 4 * blockIdx.x + 2] = g;
+        uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); prof[64 + 4 * blockIdx.x + 3] = smid;
+    }
     if (warp == 0) tmem_dealloc<512>(tm);
 }
 

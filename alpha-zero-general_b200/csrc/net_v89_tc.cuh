@@ -103,7 +103,9 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
     using namespace t89;
     constexpr int TB = T89_TB, A = V89_A, MW = 6;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-aligned base as symbol + offset: the pointer stays in the shared state space (LDS / STS). Rounding the generic address instead
+    // turns every access below into a generic LD.E / ST.E.
+    uint8_t* sm = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t bar_full[T89_NSLOT], bar_empty[T89_NSLOT], bar_acc;
     __shared__ uint32_t tmem_s;
     __shared__ int slot_of[TB];

@@ -25,7 +25,7 @@ AZG_NET_AZUL_V84 = 84
 SYMBOLS = ['azg_abi_version', 'azg_last_error', 'azg_device_count', 'azg_set_device', 'azg_engine_profile', 'azg_engine_kernel_times', 'azg_game_info', 'azg_game_init', 'azg_game_valid',
            'azg_game_next', 'azg_game_ended', 'azg_game_canonical', 'azg_game_round_score', 'azg_game_symmetries',
            'azg_net_create', 'azg_net_load', 'azg_net_forward', 'azg_net_destroy', 'azg_engine_create', 'azg_engine_destroy',
-           'azg_engine_reset', 'azg_engine_search', 'azg_engine_selfplay', 'azg_engine_selfplay_inject', 'azg_engine_selfplay_state', 'azg_engine_node', 'azg_engine_examples', 'azg_engine_examples_pending', 'azg_engine_stats', 'azg_net_prof', 'azg_debug_selprof']
+           'azg_engine_reset', 'azg_engine_search', 'azg_engine_selfplay', 'azg_engine_selfplay_inject', 'azg_engine_selfplay_state', 'azg_engine_node', 'azg_engine_examples', 'azg_engine_examples_pending', 'azg_engine_stats', 'azg_net_prof', 'azg_net_prof_ctas', 'azg_debug_selprof']
 
 
 class GameInfo(C.Structure):

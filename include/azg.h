@@ -193,12 +193,14 @@ int azg_engine_kernel_times(azg_engine* e, double* out8);
 
 /* ---- debug / profiling hooks (no reference counterpart; used by scripts/dbg_*.py) ----
  * azg_net_prof: SM-clock timestamps of the phases of the first tiles CTA 0 of the V80 tensor-core kernel processed (nets created with
- *   AZG_V80_PROF=1 in the environment); out64 receives 64 int64.
+ *   AZG_V80_PROF=1 in the environment); out64 receives 64 int64. azg_net_prof_ctas: the same nets, last launch: per CTA (160 x 4 int64)
+ *   {kernel entry, prologue done, exit} in globaltimer ns and the SM id.
  * azg_debug_selprof: per-phase cycle sums of k_select / k_backup, only filled by a library built with -DAZG_SEL_PROF=1|2; out16
  *   receives 16 uint64.
  * Environment switches read at handle creation: AZG_V80_KERNEL=fp32 (CUDA-core V80 forward instead of the tcgen05 kernel, for A/B
  * runs), AZG_TREE_REPLAY=0 (k_select without path replay; results are identical). */
 int azg_net_prof(azg_net* net, long long* out64);
+int azg_net_prof_ctas(azg_net* net, long long* out640);
 int azg_debug_selprof(unsigned long long* out16);
 
 #ifdef __cplusplus

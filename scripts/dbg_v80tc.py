@@ -46,3 +46,20 @@ n1 = len(names)
 if len(ts) >= 2 * n1:
     d2 = np.diff(ts[n1:2 * n1])
     print('second tile of CTA 0: ' + ', '.join('%s +%d' % (names[i + 1], d2[i]) for i in range(min(3, len(d2)))) + '; total %d cycles' % (ts[2 * n1 - 1] - ts[n1]))
+
+# ---- per-CTA timeline of the last launch (globaltimer ns): entry, prologue done, exit, SM id ----
+out2 = (C.c_longlong * 640)()
+L.azg_net_prof_ctas.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+if L.azg_net_prof_ctas(net.net.h, out2) == 0:
+    a = np.array(list(out2), dtype=np.int64).reshape(160, 4); a = a[a[:, 0] != 0]
+    t0 = a[:, 0].min()
+    ent, pro, ex = (a[:, 0] - t0) / 1e3, (a[:, 1] - a[:, 0]) / 1e3, (a[:, 2] - t0) / 1e3
+    ntile = np.array([len(range(i, 1024, len(a))) for i in range(len(a))])
+    body = (a[:, 2] - a[:, 1]) / 1e3
+    print('CTAs %d | entry us: min %.1f max %.1f | prologue us: min %.1f med %.1f max %.1f | exit us: min %.1f med %.1f max %.1f' % (
+        len(a), ent.min(), ent.max(), pro.min(), np.median(pro), pro.max(), ex.min(), np.median(ex), ex.max()))
+    for k in (6, 7):
+        m = ntile == k
+        if m.any(): print('  CTAs with %d tiles: %d, us per tile: min %.2f med %.2f max %.2f' % (k, m.sum(), (body[m] / k).min(), np.median(body[m] / k), (body[m] / k).max()))
+    slow = np.argsort(-ex)[:8]
+    print('  slowest CTAs (cta, sm, tiles, exit us, us/tile):', [(int(i), int(a[i, 3]), int(ntile[i]), round(float(ex[i]), 1), round(float(body[i] / ntile[i]), 2)) for i in slow])
