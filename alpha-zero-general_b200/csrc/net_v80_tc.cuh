@@ -319,9 +319,13 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     }
                     tmem_st16(tlane + TC_T + c0, xv);
                 }
-                if (t == 0) {                                     // the expand image is dead: SE weights and project chunks 2, 3 take its place
+                // The expand image is dead: SE weights and project chunks 2, 3 take its place. Issued from quarters 2 and 3, which have no
+                // second depthwise unit (a bulk-copy issue costs its thread a few hundred cycles).
+                if (t == TC_THREADS - 32) {
                     mbar_expect_tx(&bars[B_FC], 2 * 26880);
                     bulk_g2s(ESTG, P + B.fc1, 26880, &bars[B_FC]); bulk_g2s(ESTG + 26880, P + B.fc2, 26880, &bars[B_FC]);
+                }
+                if (t == TC_THREADS - 64) {
                     load(bars, B_WP0, WRING, IMGb + I.wp[b] + 2 * 4096, 16384);
                     load(bars, B_WP1, WRING + 16384, IMGb + I.wp[b] + 3 * 4096, 16384);
                 }
@@ -338,21 +342,23 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             }
             __syncthreads();
             TC_STAMP();   /* b2: depthwise done */
-            // ---------------- squeeze-excitation: fc1 (168 -> 40, ReLU), fc2 (40 -> 168, hardsigmoid) -> gates in SQ ----------------
+            // ---------------- squeeze-excitation: fc1 (168 -> 40, ReLU), fc2 (40 -> 168, hardsigmoid) ----------------
             ph.wait(bars, B_FC);
             TC_STAMP();   /* b3: fc weights landed */
+            float* GP = reinterpret_cast<float*>(sm + TC_XH);                    // fc2 K-split partial sums [3][168][16] (32 256 B)
             {
                 const float* W1 = reinterpret_cast<const float*>(ESTG); const float* W2 = reinterpret_cast<const float*>(ESTG + 26880);
-                // Register-tiled (shared-memory bandwidth is the limit: one LDS.128 costs four cycles of the SM's load path whatever
-                // it broadcasts): a thread owns 4 outputs x 4 leaves, 16 FMA per pair of 128-bit loads.
-                float* HP = reinterpret_cast<float*>(ESTG + 53760);             // fc1 K-split partial sums [4][40][16]
-                if (t < 160) {
+                // Register-tiled: a thread owns 4 outputs x 4 leaves, 16 FMA per pair of 128-bit loads; the K range is split 12 / 3 ways so
+                // that all 16 warps issue (these loops are FMA-issue bound). The partial sums meet in X's planes, which are free: the
+                // block input is parked in TMEM. Fixed summation order: results do not depend on the launch.
+                float* HP = reinterpret_cast<float*>(sm + TC_XH);                // fc1 partial sums [12][40][16] (30 720 B)
+                if (t < 480) {
                     const int part = t / 40, rem = t - part * 40, qg = rem >> 2, lq = rem & 3;
                     float a[4][4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
-#pragma unroll 6
-                    for (int kk = 42 * part; kk < 42 * part + 42; kk++) {
+#pragma unroll 7
+                    for (int kk = 14 * part; kk < 14 * part + 14; kk++) {
                         const float4 w4 = *reinterpret_cast<const float4*>(W1 + kk * Q + 4 * qg);
                         const float4 x4 = *reinterpret_cast<const float4*>(SQ + kk * TB + 4 * lq);
                         const float w[4] = {w4.x, w4.y, w4.z, w4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
@@ -366,17 +372,22 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 }
                 TC_FSTAMP();   /* f: fc1 partials */
                 __syncthreads();
-                TC_FSTAMP();   /* f: barrier */
-                for (int i = t; i < Q * TB; i += TC_THREADS) HID[i] = fmaxf(HP[i] + HP[640 + i] + HP[1280 + i] + HP[1920 + i] + SB[SV_B1 + (i >> 4)], 0.f);
+                for (int i = t; i < Q * TB; i += TC_THREADS) {
+                    float h = HP[i];
+#pragma unroll
+                    for (int pt = 1; pt < 12; pt++) h += HP[pt * 640 + i];
+                    HID[i] = fmaxf(h + SB[SV_B1 + (i >> 4)], 0.f);
+                }
                 __syncthreads();
                 TC_FSTAMP();   /* f: hidden done + barrier */
-                if (t < (EC / 4) * 4) {                            // 42 channel quads x 4 leaf quads
-                    const int cq = t >> 2, lq = t & 3;
+                if (t < 504) {                                     // 3 K slices x 42 channel quads x 4 leaf quads
+                    const int part = t / 168, rem = t - part * 168, cq = rem >> 2, lq = rem & 3;
+                    const int k0 = part == 0 ? 0 : (part == 1 ? 14 : 27), k1 = part == 0 ? 14 : (part == 1 ? 27 : 40);
                     float g[4][4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) g[i][0] = g[i][1] = g[i][2] = g[i][3] = 0.f;
-#pragma unroll 8
-                    for (int kk = 0; kk < Q; kk++) {
+#pragma unroll 7
+                    for (int kk = k0; kk < k1; kk++) {
                         const float4 w4 = *reinterpret_cast<const float4*>(W2 + kk * EC + 4 * cq);
                         const float4 x4 = *reinterpret_cast<const float4*>(HID + kk * TB + 4 * lq);
                         const float w[4] = {w4.x, w4.y, w4.z, w4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
@@ -386,103 +397,113 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                             for (int j = 0; j < 4; j++) g[i][j] = fmaf(w[i], x[j], g[i][j]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float bb = SB[SV_B2 + 4 * cq + i] + 3.f;
-                        *reinterpret_cast<float4*>(SQ + (4 * cq + i) * TB + 4 * lq) =
-                            make_float4(fminf(fmaxf(g[i][0] + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g[i][1] + bb, 0.f), 6.f) * (1.f / 6.f),
-                                        fminf(fmaxf(g[i][2] + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g[i][3] + bb, 0.f), 6.f) * (1.f / 6.f));
-                    }
+                    for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(GP + (part * EC + 4 * cq + i) * TB + 4 * lq) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
                 }
                 TC_FSTAMP();   /* f: fc2 done */
             }
             __syncthreads();
             TC_STAMP();   /* b4: SE done */
-            // ---------------- SE-gated operand pass + project MMAs: three rounds of two 32-channel K chunks through FOUR stages (two in
-            //                  ESTG, two in X's planes), so a round's MMAs run while the next round's operands are written ----------------
-#pragma unroll 1
-            for (int r = 0; r < 3; r++) {
-                const int s0 = (2 * r) & 3;                       // stages of this round: s0, s0 + 1
-                ph.wait(bars, B_EF0 + s0); ph.wait(bars, B_EF0 + s0 + 1);   // the MMAs that read them (two rounds ago) are done
+            // ---------------- SE-gated operand pass + project MMAs. Six 32-channel K chunks through FOUR stages (two in ESTG, two in X's
+            //                  planes). Round A: warp quarter q writes chunk q into stage q (all 16 warps); round B: quarters 0 / 1 write
+            //                  chunks 4 / 5 into stages 0 / 1 as soon as the MMAs of chunks 0 / 1 are done, while those of chunks 2, 3 run.
+            //                  All MMAs are issued by one thread of the last warp (quarter 3: no round-B work). ----------------
+            {
+                auto gate_of = [&](int c) -> float4 {             // hardsigmoid(fc2 + b2) of channel c for this thread's 4 leaves
+                    const float4 g0 = *reinterpret_cast<const float4*>(GP + c * TB + 4 * sub), g1 = *reinterpret_cast<const float4*>(GP + (EC + c) * TB + 4 * sub),
+                                 g2 = *reinterpret_cast<const float4*>(GP + (2 * EC + c) * TB + 4 * sub);
+                    const float bb = SB[SV_B2 + c] + 3.f;
+                    return make_float4(fminf(fmaxf(g0.x + g1.x + g2.x + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g0.y + g1.y + g2.y + bb, 0.f), 6.f) * (1.f / 6.f),
+                                       fminf(fmaxf(g0.z + g1.z + g2.z + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g0.w + g1.w + g2.w + bb, 0.f), 6.f) * (1.f / 6.f));
+                };
+                const int cA = 32 * q + lane, cB = 128 + 32 * q + lane;
+                const bool okB = q < 2 && cB < EC;
+                const float4 gA = gate_of(cA), gB = gate_of(okB ? cB : 0);
+                __syncthreads();                                  // every gate is in registers: the partial sums (stage 2) may be overwritten
+                // element i of a thread -> row 32 sub + i, k = lane of the stage: byte offset (i >> 3) * 1024 + (i & 7) * 128 +
+                // (((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4. The lane-dependent part only depends on i & 7: eight base pointers.
+                auto gated_write = [&](uint32_t tcol, const float4 g4, int stg, bool ok) {
+                    uint32_t d[32];
+                    tmem_ld32(tlane + tcol, d);                   // warp-collective
+                    tmem_wait_ld();
+                    if (!ok) return;
+                    const float gate[4] = {g4.x, g4.y, g4.z, g4.w};
+                    uint8_t* eh = (stg < 2 ? ESTG + stg * 32768 : sm + TC_XH + (stg - 2) * 32768) + sub * 4096;   // rows 32 sub .. 32 sub + 31 of the stage
+                    uint8_t* eb[8];
+#pragma unroll
+                    for (int v = 0; v < 8; v++) eb[v] = eh + ((((lane >> 2) ^ v) & 7) << 4) + ((lane & 3) << 2);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        float hi, lo; split_rn(__uint_as_float(d[i]) * gate[i >> 3], hi, lo);
+                        uint8_t* pdst = eb[i & 7] + (i >> 3) * 1024 + (i & 7) * 128;
+                        *reinterpret_cast<float*>(pdst) = hi; *reinterpret_cast<float*>(pdst + 16384) = lo;
+                    }
+                };
+                auto issue_chunk = [&](int j) {                   // chunk j: stage j & 3, weight slot (j + 2) & 3
+                    const int slot = (j + 2) & 3, stg = j & 3;
+                    ph.wait(bars, B_WP0 + slot); tc_fence_after();
+                    const uint32_t ea = stg < 2 ? estg_a + stg * 32768 : xh_a + (stg - 2) * 32768, wa = wring_a + slot * 16384;
+                    const uint64_t dh_ = desc_sw128(ea), dl_ = desc_sw128(ea + 16384), dw_ = desc_sw128(wa);
+                    const int nks = j == 5 ? 1 : 4;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        if (ks < nks) {
+                            mma_tf32(tm + TC_DP, dh_ + 2 * ks, dw_ + 2 * ks, ID128, (j | ks) != 0);     // E_hi . (W_hi | W_lo); +32 B per k-step = +2 in the descriptor
+                            mma_tf32(tm + TC_DP, dl_ + 2 * ks, dw_ + 2 * ks, ID64, true);               // E_lo . W_hi
+                        }
+                    }
+                    mma_commit(&bars[B_EF0 + stg]);
+                };
+                // ---- round A
+                ph.wait(bars, B_EF0 + q);                         // the MMAs that last read stage q are done
 #ifdef AZG_TC_ROUND_PROF
                 if (b == 0) TC_STAMP();
 #endif
-                const bool active = (r == 1) ? (q >= 2) : (q < 2);
-                const int c = (r == 2 ? 128 : 0) + 32 * q + lane;
-                if (active) {                                     // warp-uniform: the TMEM load is warp-collective
-                    uint32_t d[32];
-                    tmem_ld32(tlane + TC_DE + (r == 2 ? 128 : 0) + 32 * sub, d);
-                    tmem_wait_ld();
-                    if (c < EC) {
-                        const float4 g4 = *reinterpret_cast<const float4*>(SQ + c * TB + 4 * sub);
-                        const float gate[4] = {g4.x, g4.y, g4.z, g4.w};
-                        const int stg = s0 + (q & 1);
-                        uint8_t* eh = (stg < 2 ? ESTG + stg * 32768 : sm + TC_XH + (stg - 2) * 32768) + sub * 4096;   // rows 32 sub .. 32 sub + 31 of the stage
-                        // element i -> row 32 sub + i, k = lane: byte offset (i >> 3) * 1024 + (i & 7) * 128 + (((lane >> 2) ^ (i & 7)) << 4) + (lane & 3) * 4.
-                        // The lane-dependent part only depends on i & 7: eight base pointers, everything else is an immediate.
-                        uint8_t* eb[8];
-#pragma unroll
-                        for (int v = 0; v < 8; v++) eb[v] = eh + ((((lane >> 2) ^ v) & 7) << 4) + ((lane & 3) << 2);
-#pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            float hi, lo; split_rn(__uint_as_float(d[i]) * gate[i >> 3], hi, lo);
-                            uint8_t* pdst = eb[i & 7] + (i >> 3) * 1024 + (i & 7) * 128;
-                            *reinterpret_cast<float*>(pdst) = hi; *reinterpret_cast<float*>(pdst + 16384) = lo;
-                        }
-                    }
-                }
+                gated_write(TC_DE + 32 * sub, gA, q, true);
 #ifdef AZG_TC_ROUND_PROF
                 if (b == 0) TC_STAMP();
 #endif
                 fence_async_smem(); tc_fence_before(); __syncthreads();
-#ifdef AZG_TC_ROUND_PROF
-                if (b == 0) TC_STAMP();
-#endif
-                // The MMAs of a round are issued by a thread whose warp does NOT write operands in the next round (issuing sixteen MMAs
-                // takes one thread longer than the other warps need to write the next operands, and the next barrier waits for it):
-                // quarters 0-1 write in rounds 0 and 2, quarters 2-3 in round 1, so thread 0 issues rounds 0 and 2, the last warp round 1.
-                if (t == (r == 1 ? TC_THREADS - 32 : 0)) {
+                if (t == TC_THREADS - 32) {
                     tc_fence_after();
 #pragma unroll 1
-                    for (int jj = 0; jj < 2; jj++) {
-                        const int j = 2 * r + jj, slot = (j + 2) & 3, stg = s0 + jj;
-                        ph.wait(bars, B_WP0 + slot); tc_fence_after();
-                        const uint32_t ea = stg < 2 ? estg_a + stg * 32768 : xh_a + (stg - 2) * 32768, wa = wring_a + slot * 16384;
-                        const uint64_t dh_ = desc_sw128(ea), dl_ = desc_sw128(ea + 16384), dw_ = desc_sw128(wa);
-                        const int nks = j == 5 ? 1 : 4;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            if (ks < nks) {
-                                mma_tf32(tm + TC_DP, dh_ + 2 * ks, dw_ + 2 * ks, ID128, (j | ks) != 0);     // E_hi . (W_hi | W_lo); +32 B per k-step = +2 in the descriptor
-                                mma_tf32(tm + TC_DP, dl_ + 2 * ks, dw_ + 2 * ks, ID64, true);               // E_lo . W_hi
-                            }
-                        }
-                        mma_commit(&bars[B_EF0 + stg]);
-                    }
-                    if (r == 2) mma_commit(&bars[B_MMA]);
-                    if (r == 1) {                                 // round 0's MMAs (issued first) free the weight slots of chunks 0, 1 for chunks 4, 5;
-                        mbar_wait(&bars[B_EF0], (ph.bits >> B_EF0) & 1u); mbar_wait(&bars[B_EF1], (ph.bits >> B_EF1) & 1u);   // peek: round 2 waits again
-                        load(bars, B_WP2, WRING + 32768, IMGb + I.wp[b] + 4 * 4096, 16384);
-                        load(bars, B_WP3, WRING + 49152, IMGb + I.wp[b] + 5 * 4096, 16384);
-                    }
+                    for (int j = 0; j < 4; j++) issue_chunk(j);
+                }
+                __syncwarp();
+                // ---- round B
+                if (q < 2) {                                      // warp-uniform
+                    ph.wait(bars, B_EF0 + q);                     // chunk q's MMAs are done: stage q and weight slot q + 2 are free
+                    if (sub == 0 && lane == 0) load(bars, B_WP2 + q, WRING + (2 + q) * 16384, IMGb + I.wp[b] + (4 + q) * 4096, 16384);
+                    __syncwarp();
+#ifdef AZG_TC_ROUND_PROF
+                    if (b == 0) TC_STAMP();
+#endif
+                    gated_write(TC_DE + 128 + 32 * sub, gB, q, okB);
+#ifdef AZG_TC_ROUND_PROF
+                    if (b == 0) TC_STAMP();
+#endif
+                }
+                fence_async_smem(); tc_fence_before(); __syncthreads();
+                if (t == TC_THREADS - 32) {
+                    tc_fence_after();
+                    issue_chunk(4); issue_chunk(5);
+                    mma_commit(&bars[B_MMA]);
                 }
                 __syncwarp();
             }
-            ph.wait(bars, B_MMA);                                 // rounds 0 and 2 (committed by their issuing thread) ...
-            mbar_wait(&bars[B_EF2], ((ph.bits >> B_EF2) & 1u)); mbar_wait(&bars[B_EF3], ((ph.bits >> B_EF3) & 1u));   // ... and round 1 (peek: the next block's round 1 waits again)
+            ph.wait(bars, B_MMA);                                 // committed after the last chunk by the thread that issued every MMA: all of them are done
             tc_fence_after();
             TC_STAMP();   /* b5: project MMAs done */
-            if (t == 0) {                                         // everything in ESTG / WRING has been consumed
+            if (lane == 0 && warp >= 12) {                        // everything in ESTG / WRING has been consumed; one bulk copy per warp (12 .. 15)
+                const int w = warp - 12;
                 if (b == 0) {
-                    load(bars, B_WE, ESTG, IMGb + I.we[1], TC_WE_BYTES);
-                    load(bars, B_WP2, WRING + 32768, IMGb + I.wp[1], 16384);
-                    load(bars, B_WP3, WRING + 49152, IMGb + I.wp[1] + 4096, 16384);
+                    if (w == 0) load(bars, B_WE, ESTG, IMGb + I.we[1], TC_WE_BYTES);
+                    if (w == 1) load(bars, B_WP2, WRING + 32768, IMGb + I.wp[1], 16384);
+                    if (w == 2) load(bars, B_WP3, WRING + 49152, IMGb + I.wp[1] + 4096, 16384);
                 } else if (b == 1) {
-                    load(bars, B_PI0, WRING, P + L.pi2, TC_PIRING_SLOT);                  // policy weight ring: four slots (the last one runs over
-                    load(bars, B_PI1, WRING + TC_PIRING_SLOT, P + L.pi2 + 56 * PIP, TC_PIRING_SLOT);          // into SQ, whose gates are consumed), three
-                    load(bars, B_PI2, WRING + 2 * TC_PIRING_SLOT, P + L.pi2 + 112 * PIP, TC_PIRING_SLOT);     // loads in flight ahead of the math
-                    load(bars, B_PI3, WRING + 3 * TC_PIRING_SLOT, P + L.pi2 + 168 * PIP, TC_PIRING_SLOT);
+                    // policy weight ring: four slots (the last one runs over into SQ, whose gates are consumed), loads in flight ahead of the math
+                    load(bars, B_PI0 + w, WRING + w * TC_PIRING_SLOT, P + L.pi2 + w * 56 * PIP, TC_PIRING_SLOT);
                 } else {
-                    load(bars, B_V2, WRING, P + L.v2, NV * 7 * 4 * 4);
+                    if (w == 0) load(bars, B_V2, WRING, P + L.v2, NV * 7 * 4 * 4);
                 }
             }
             __syncwarp();
