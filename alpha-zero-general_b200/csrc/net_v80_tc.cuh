@@ -37,8 +37,9 @@ constexpr int TC_XH = 0;                  // activations hi: [2 K atoms][128 col
 constexpr int TC_XL = 32768;              // activations lo
 constexpr int TC_ESTG = 65536;            // 2 stages x (EH 16 KB | EL 16 KB); also raw boards, SE fc weights, head activations
 constexpr int TC_WRING = 131072;          // 64 KB: project weight slots 4 x 16 KB, first-layer image, policy/value weight ring
-constexpr int TC_SQ = 196608;             // SE pooled values, then gates: [168][16] floats
-constexpr int TC_HID = TC_SQ + 168 * 16 * 4;   // SE hidden [40][16]
+constexpr int TC_SQ = 196608;             // SE pooled values [leaf quad][169 (padded)][4] floats: consecutive channels 16 B apart (the depthwise threads store without
+                                          // bank conflicts), odd pitch (a quarter-warp of fc1 reads the four leaf quads of one channel from different banks)
+constexpr int TC_HID = TC_SQ + 4 * 169 * 16;   // SE hidden [40][16]
 constexpr int TC_VH = TC_HID + 40 * 16 * 4;    // value-head accumulators [8][16]
 constexpr int TC_SV = TC_VH + 8 * 16 * 4;        // small vectors (biases, BN scale/shift, value-head matrix), copied once per CTA
 constexpr int SV_B0 = 0, SV_BLK = 64, SV_BLK_STRIDE = 800, SV_BE = 0, SV_SD = 168, SV_TD = 336, SV_B1 = 504, SV_B2 = 552, SV_BP = 720;
@@ -145,7 +146,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
          const __grid_constant__ V80DW DW, const int* count_ptr, const int* list, const int8_t* boards, int bstride,
          const uint32_t* masks, float* pi_out, float* v_out, int n_max, long long* prof) {
     using namespace tc;
-    constexpr int NV = 56, EC = 168, Q = V80_Q, TB = TC_TB, LD = 128, A = 81, PIP = V80Layout::PIP;
+    constexpr int NV = 56, EC = 168, Q = V80_Q, TB = TC_TB, LD = 128, A = 81, PIP = V80Layout::PIP, SQP = EC + 1;
     extern __shared__ uint8_t smem_raw[];
     // 1024-aligned base as symbol + offset: the pointer stays in the shared state space (LDS / STS). Rounding the generic address instead
     // turns every access below into a generic LD.E / ST.E.
@@ -296,8 +297,8 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 const int c = 32 * q + lane;
                 const float be = SB[SV_BE + c], sd = SB[SV_SD + c], td = SB[SV_TD + c];
                 const uint32_t ta = tlane + TC_DE + 32 * sub;
-                if (b == 0) depthwise_unit<1, false>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
-                else depthwise_unit<2, true>(ta, be, sd, td, dw, SQ + c * TB + 4 * sub, true);
+                if (b == 0) depthwise_unit<1, false>(ta, be, sd, td, dw, SQ + (sub * SQP + c) * 4, true);
+                else depthwise_unit<2, true>(ta, be, sd, td, dw, SQ + (sub * SQP + c) * 4, true);
                 TC_FSTAMP();   /* f: unit 1 done */
                 ph.wait(bars, B_MM2); tc_fence_after();
                 TC_FSTAMP();   /* f: MM2 wait done */
@@ -334,8 +335,8 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 if (q < 2) {
                     const int c2 = 128 + c; const bool ok = c2 < EC; const int cc = ok ? c2 : 0;
                     const float be2 = SB[SV_BE + cc], sd2 = SB[SV_SD + cc], td2 = SB[SV_TD + cc];
-                    if (b == 0) depthwise_unit<1, false>(ta + 128, be2, sd2, td2, dw, SQ + cc * TB + 4 * sub, ok);
-                    else depthwise_unit<2, true>(ta + 128, be2, sd2, td2, dw, SQ + cc * TB + 4 * sub, ok);
+                    if (b == 0) depthwise_unit<1, false>(ta + 128, be2, sd2, td2, dw, SQ + (sub * SQP + cc) * 4, ok);
+                    else depthwise_unit<2, true>(ta + 128, be2, sd2, td2, dw, SQ + (sub * SQP + cc) * 4, ok);
                 }
                 tmem_wait_st();
                 TC_FSTAMP();   /* f: unit 2 done */
@@ -345,13 +346,15 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             // ---------------- squeeze-excitation: fc1 (168 -> 40, ReLU), fc2 (40 -> 168, hardsigmoid) ----------------
             ph.wait(bars, B_FC);
             TC_STAMP();   /* b3: fc weights landed */
-            float* GP = reinterpret_cast<float*>(sm + TC_XH);                    // fc2 K-split partial sums [3][168][16] (32 256 B)
+            // fc2 K-split partial sums [3][leaf quad][169][4] (32 448 B): consecutive channels 16 B apart for the gated pass (one thread per
+            // channel), the odd pitch spreads the four leaf quads of the producers' stores over the banks
+            float* GP = reinterpret_cast<float*>(sm + TC_XH); constexpr int GPP = EC + 1;
             {
                 const float* W1 = reinterpret_cast<const float*>(ESTG); const float* W2 = reinterpret_cast<const float*>(ESTG + 26880);
                 // Register-tiled: a thread owns 4 outputs x 4 leaves, 16 FMA per pair of 128-bit loads; the K range is split 12 / 3 ways so
                 // that all 16 warps issue (these loops are FMA-issue bound). The partial sums meet in X's planes, which are free: the
                 // block input is parked in TMEM. Fixed summation order: results do not depend on the launch.
-                float* HP = reinterpret_cast<float*>(sm + TC_XH);                // fc1 partial sums [12][40][16] (30 720 B)
+                float* HP = reinterpret_cast<float*>(sm + TC_XH);                // fc1 partial sums [12][leaf quad][41 (padded)][4] (31 488 B)
                 if (t < 480) {
                     const int part = t / 40, rem = t - part * 40, qg = rem >> 2, lq = rem & 3;
                     float a[4][4];
@@ -360,7 +363,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #pragma unroll 7
                     for (int kk = 14 * part; kk < 14 * part + 14; kk++) {
                         const float4 w4 = *reinterpret_cast<const float4*>(W1 + kk * Q + 4 * qg);
-                        const float4 x4 = *reinterpret_cast<const float4*>(SQ + kk * TB + 4 * lq);
+                        const float4 x4 = *reinterpret_cast<const float4*>(SQ + (lq * SQP + kk) * 4);
                         const float w[4] = {w4.x, w4.y, w4.z, w4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                         for (int i = 0; i < 4; i++)
@@ -368,15 +371,16 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                             for (int j = 0; j < 4; j++) a[i][j] = fmaf(w[i], x[j], a[i][j]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(HP + part * 640 + (4 * qg + i) * TB + 4 * lq) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
+                    for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(HP + ((part * 4 + lq) * 41 + 4 * qg + i) * 4) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
                 }
                 TC_FSTAMP();   /* f: fc1 partials */
                 __syncthreads();
                 for (int i = t; i < Q * TB; i += TC_THREADS) {
-                    float h = HP[i];
+                    const int lq = i / 160, rem = i - lq * 160;      // rem = 4 * hidden unit + leaf of the quad
+                    float h = HP[lq * 164 + rem];
 #pragma unroll
-                    for (int pt = 1; pt < 12; pt++) h += HP[pt * 640 + i];
-                    HID[i] = fmaxf(h + SB[SV_B1 + (i >> 4)], 0.f);
+                    for (int pt = 1; pt < 12; pt++) h += HP[(pt * 4 + lq) * 164 + rem];
+                    HID[(rem >> 2) * TB + 4 * lq + (rem & 3)] = fmaxf(h + SB[SV_B1 + (rem >> 2)], 0.f);
                 }
                 __syncthreads();
                 TC_FSTAMP();   /* f: hidden done + barrier */
@@ -397,7 +401,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                             for (int j = 0; j < 4; j++) g[i][j] = fmaf(w[i], x[j], g[i][j]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(GP + (part * EC + 4 * cq + i) * TB + 4 * lq) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
+                    for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(GP + ((part * 4 + lq) * GPP + 4 * cq + i) * 4) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
                 }
                 TC_FSTAMP();   /* f: fc2 done */
             }
@@ -409,8 +413,8 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             //                  All MMAs are issued by one thread of the last warp (quarter 3: no round-B work). ----------------
             {
                 auto gate_of = [&](int c) -> float4 {             // hardsigmoid(fc2 + b2) of channel c for this thread's 4 leaves
-                    const float4 g0 = *reinterpret_cast<const float4*>(GP + c * TB + 4 * sub), g1 = *reinterpret_cast<const float4*>(GP + (EC + c) * TB + 4 * sub),
-                                 g2 = *reinterpret_cast<const float4*>(GP + (2 * EC + c) * TB + 4 * sub);
+                    const float4 g0 = *reinterpret_cast<const float4*>(GP + (sub * GPP + c) * 4), g1 = *reinterpret_cast<const float4*>(GP + ((4 + sub) * GPP + c) * 4),
+                                 g2 = *reinterpret_cast<const float4*>(GP + ((8 + sub) * GPP + c) * 4);
                     const float bb = SB[SV_B2 + c] + 3.f;
                     return make_float4(fminf(fmaxf(g0.x + g1.x + g2.x + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g0.y + g1.y + g2.y + bb, 0.f), 6.f) * (1.f / 6.f),
                                        fminf(fmaxf(g0.z + g1.z + g2.z + bb, 0.f), 6.f) * (1.f / 6.f), fminf(fmaxf(g0.w + g1.w + g2.w + bb, 0.f), 6.f) * (1.f / 6.f));
