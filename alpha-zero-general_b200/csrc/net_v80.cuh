@@ -88,7 +88,7 @@ inline size_t v80_src_floats(int nv, int np) {
 
 __device__ __forceinline__ float act_apply(float x, int act) {
     if (act == 1) return fmaxf(x, 0.f);
-    if (act == 2) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);           // hardswish
+    if (act == 2) return x * __saturatef(fmaf(x, 1.f / 6.f, 0.5f));                    // hardswish = x relu6(x + 3) / 6 as one saturating FMA and one multiply
     return x;
 }
 

@@ -548,6 +548,11 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 // Weight ring (7 chunks of the 392 x 84 matrix, then the 81 x 84 one in two parts) through four slots, mbarrier-only: the 11
                 // computing warps wait for a slot to be full and arrive on its "empty" barrier when done; the last thread of the CTA (its
                 // warp has no policy work) refills a slot as soon as it is empty. No CTA-wide barrier per chunk.
+                uint32_t mw[3] = {0u, 0u, 0u};                     // this warp's leaf: legal-move words for the softmax below (the global load lands during the linears)
+                {
+                    const int slot = slot_of[warp];
+                    if (slot >= 0) { mw[0] = masks[(size_t)slot * 3]; mw[1] = masks[(size_t)slot * 3 + 1]; mw[2] = masks[(size_t)slot * 3 + 2]; }
+                }
                 int ent = 0;
                 auto acquire = [&]() -> const float* {
                     const int s = ent & 3;
@@ -643,7 +648,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
                             const int a = lane + 32 * k;
-                            const bool valid = a < A && (masks[(size_t)slot * 3 + k] >> lane & 1);
+                            const bool valid = a < A && (mw[k] >> lane & 1);
                             l[k] = a < A ? (valid ? LG[a * TB + sl] : -1e8f) : -INFINITY;
                             mx = fmaxf(mx, l[k]);
                         }
