@@ -146,7 +146,10 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
          const __grid_constant__ V80DW DW, const int* count_ptr, const int* list, const int8_t* boards, int bstride,
          const uint32_t* masks, float* pi_out, float* v_out, int n_max, long long* prof) {
     using namespace tc;
-    constexpr int NV = 56, EC = 168, Q = V80_Q, TB = TC_TB, LD = 128, A = 81, PIP = V80Layout::PIP, SQP = EC + 1;
+    constexpr int NV = 56, EC = 168, Q = V80_Q, TB = TC_TB, A = 81, PIP = V80Layout::PIP, SQP = EC + 1;
+    // head inputs [token][feature][leaf] with a feature pitch of 20 floats: the 32 (leaf, feature) rows a warp stores in the project epilogue
+    // fall into 32 different banks; rows stay 16-byte aligned for the policy head's 128-bit loads
+    constexpr int HFP = 20, HLD = 7 * HFP, HEAD_X0 = NV * HLD * 4, LGP = 85;
     extern __shared__ uint8_t smem_raw[];
     // 1024-aligned base as symbol + offset: the pointer stays in the shared state space (LDS / STS). Rounding the generic address instead
     // turns every access below into a generic LD.E / ST.E.
@@ -527,7 +530,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                         for (int j = 0; j < 4; j++) y[j] = __uint_as_float(dh[4 * j4 + j]) + __uint_as_float(dl[4 * j4 + j]) + SB[SV_BP + c + j] + __uint_as_float(xr[4 * j4 + j]);
                         if (b != 0) {
 #pragma unroll
-                            for (int j = 0; j < 4; j++) { HO[(c + j) * LD + (row & 7) * TB + (row >> 3)] = y[j]; y[j] = __uint_as_float(xr[4 * j4 + j]); }   // [token][feature][leaf]
+                            for (int j = 0; j < 4; j++) { if ((row & 7) < 7) HO[(c + j) * HLD + (row & 7) * HFP + (row >> 3)] = y[j]; y[j] = __uint_as_float(xr[4 * j4 + j]); }   // [token][feature][leaf]
                         }
                         if (b != 2) {                             // b == 0: the trunk output; b == 1: the trunk output again (X's planes served as E stages)
 #pragma unroll
@@ -544,7 +547,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
             if (b == 1) {
                 // ---------------- policy head linears on CUDA cores: Linear(392 -> 81) + ReLU, Linear(81 -> 81), masked softmax ----------------
                 const float* X0 = reinterpret_cast<const float*>(ESTG);
-                float* H1 = reinterpret_cast<float*>(ESTG + 28672); float* LG = H1 + PIP * TB;
+                float* H1 = reinterpret_cast<float*>(ESTG + HEAD_X0); float* LG = H1 + PIP * TB;     // LG: logits [leaf][85] (a warp reads one leaf's row)
                 // Weight ring (7 chunks of the 392 x 84 matrix, then the 81 x 84 one in two parts) through four slots, mbarrier-only: the 11
                 // computing warps wait for a slot to be full and arrive on its "empty" barrier when done; the last thread of the CTA (its
                 // warp has no policy work) refills a slot as soon as it is empty. No CTA-wide barrier per chunk.
@@ -575,7 +578,8 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 // 352 tasks = 8 K-slices x 11 output octets x 4 leaf quads (register tile 8 x 4: 32 FMA per three 128-bit loads; the loads,
                 // not the FMAs, are the limit, so the work is spread over 11 warps). Slices s and s + 4 sit in lanes l and l ^ 16 of one warp
                 // and are summed by shuffle; the four remaining partial sums meet in PP and are added in a fixed order.
-                float* PP = reinterpret_cast<float*>(ESTG + 39424);   // [4][84][16]
+                float* PP = reinterpret_cast<float*>(ESTG + HEAD_X0 + (PIP + LGP) * TB * 4);   // [4][84][16]
+                static_assert(HEAD_X0 + (PIP + LGP) * TC_TB * 4 + 4 * PIP * TC_TB * 4 <= 65536, "policy head scratch must fit the E stages");
                 const bool live = t < 352;
                 const int unit = min((t >> 5) * 16 + (t & 15), 175), half = (t >> 4) & 1;
                 const int part = unit / 44, task = unit - part * 44, o8 = task >> 2, lq = task & 3, slice = part + 4 * half;
@@ -608,10 +612,10 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 for (int ch = 0; ch < NV / 8 && live; ch++) {
                     const float* W = acquire();
                     {                                             // K-slice `slice` = token `slice` of this 8-token chunk: 7 rows
-                        const float* xp = X0 + (8 * ch + slice) * LD + 4 * lq;
+                        const float* xp = X0 + (8 * ch + slice) * HLD + 4 * lq;
                         const float* wp = W + (slice * 7) * PIP + 8 * o8;
 #pragma unroll
-                        for (int f = 0; f < 7; f++) fma_row(wp + f * PIP, *reinterpret_cast<const float4*>(xp + f * TB));
+                        for (int f = 0; f < 7; f++) fma_row(wp + f * PIP, *reinterpret_cast<const float4*>(xp + f * HFP));
                     }
                     release();
                 }
@@ -623,24 +627,39 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 for (int i = t; i < PIP * TB; i += TC_THREADS)
                     H1[i] = fmaxf(PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI2 + (i >> 4)], 0.f);
                 __syncthreads();                                  // H1 complete (and PP consumed)
+#ifdef AZG_TC_POLICY_PROF
+                TC_STAMP();
+#endif
                 for (int ch = 0; ch < 2 && live; ch++) {
                     const float* W = acquire();
+#ifdef AZG_TC_POLICY_PROF
+                    TC_STAMP();
+#endif
                     {
-                        const int k0 = max(11 * slice, 41 * ch), k1 = min(min(11 * slice + 11, 81), ch == 0 ? 41 : 81);
+                        const int k0 = 41 * ch + 6 * slice, k1 = min(k0 + 6, ch == 0 ? 41 : 81);   // every K slice has rows in both chunks: no half-idle warps
 #pragma unroll 2
                         for (int k = k0; k < k1; k++) fma_row(W + (k - 41 * ch) * PIP + 8 * o8, *reinterpret_cast<const float4*>(H1 + k * TB + 4 * lq));
                     }
                     release();
                 }
+#ifdef AZG_TC_POLICY_PROF
+                TC_STAMP();
+#endif
                 if (t == TC_THREADS - 1) { ph.wait(bars, B_PE0); ph.wait(bars, B_PE1); ph.wait(bars, B_PE2); ph.wait(bars, B_PE3); }   // last entry of every slot consumed (keeps the parities in step)
                 __syncwarp();
                 flush();
+#ifdef AZG_TC_POLICY_PROF
+                TC_STAMP();
+#endif
                 __syncthreads();
 #ifdef AZG_TC_POLICY_PROF
                 TC_STAMP();
 #endif
-                for (int i = t; i < PIP * TB; i += TC_THREADS) LG[i] = PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI4 + (i >> 4)];
+                for (int i = t; i < PIP * TB; i += TC_THREADS) LG[(i & 15) * LGP + (i >> 4)] = PP[i] + PP[PIP * TB + i] + PP[2 * PIP * TB + i] + PP[3 * PIP * TB + i] + SV[SV_BPI4 + (i >> 4)];
                 __syncthreads();
+#ifdef AZG_TC_POLICY_PROF
+                TC_STAMP();
+#endif
                 {   // masked softmax: where(valid, logits, -1e8) -> log_softmax -> exp (SplendorNNet.py:404,440; GenericNNetWrapper.py:119)
                     const int sl = warp, slot = slot_of[sl];
                     if (slot >= 0) {
@@ -649,7 +668,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                         for (int k = 0; k < 3; k++) {
                             const int a = lane + 32 * k;
                             const bool valid = a < A && (mw[k] >> lane & 1);
-                            l[k] = a < A ? (valid ? LG[a * TB + sl] : -1e8f) : -INFINITY;
+                            l[k] = a < A ? (valid ? LG[sl * LGP + a] : -1e8f) : -INFINITY;
                             mx = fmaxf(mx, l[k]);
                         }
                         mx = warp_max_f32(mx);
@@ -689,20 +708,20 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 const int s = t & 15, kp = t >> 4;               // 24 token slices x 16 leaves
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 for (int i = kp; i < NV; i += 24) {
-                    const float* xp = X0 + i * LD + s;
+                    const float* xp = X0 + i * HLD + s;
 #pragma unroll
                     for (int f = 0; f < 7; f++) {
                         const float4 w4 = *reinterpret_cast<const float4*>(W + (i * 7 + f) * 4);
-                        const float x = xp[f * TB];
+                        const float x = xp[f * HFP];
                         a0 = fmaf(w4.x, x, a0); a1 = fmaf(w4.y, x, a1); a2 = fmaf(w4.z, x, a2); a3 = fmaf(w4.w, x, a3);
                     }
                 }
-                float* VP = reinterpret_cast<float*>(ESTG + 28672);   // per-slice partial sums [24][4][16], summed in a fixed order below
+                float* VP = reinterpret_cast<float*>(ESTG + HEAD_X0);   // per-slice partial sums [24][4][16], summed in a fixed order below
                 VP[(kp * 4 + 0) * TB + s] = a0; VP[(kp * 4 + 1) * TB + s] = a1; VP[(kp * 4 + 2) * TB + s] = a2; VP[(kp * 4 + 3) * TB + s] = a3;
             }
             __syncthreads();
             if (t < 4 * TB) {
-                const float* VP = reinterpret_cast<const float*>(ESTG + 28672);
+                const float* VP = reinterpret_cast<const float*>(ESTG + HEAD_X0);
                 float a = 0.f;
                 for (int kp = 0; kp < 24; kp++) a += VP[kp * 4 * TB + t];
                 VH[t] = a;
