@@ -105,6 +105,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+// Packed fp32 FMA (FFMA2): two IEEE fp32 FMAs per instruction, bit-identical to two fmaf. Same FMA-lane throughput as FFMA
+// (csrc/probe/ffma2_probe.cu) but half the issue slots, which is what the register-tiled linears below are bound by.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void fma2(uint64_t& acc, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+// acc[ip][j] (+)= (w[2 ip], w[2 ip + 1]) * x[j] for a 4 x 4 register tile: 8 FFMA2
+__device__ __forceinline__ void tile44_fma2(uint64_t (&acc)[2][4], const float4 w4, const float4 x4) {
+    const uint64_t w01 = pk2(w4.x, w4.y), w23 = pk2(w4.z, w4.w);
+    const uint64_t xd[4] = {pk2(x4.x, x4.x), pk2(x4.y, x4.y), pk2(x4.z, x4.z), pk2(x4.w, x4.w)};
+#pragma unroll
+    for (int j = 0; j < 4; j++) { fma2(acc[0][j], w01, xd[j]); fma2(acc[1][j], w23, xd[j]); }
+}
 __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {          // hi = x rounded to TF32, hi + lo == x exactly
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
     lo = __fsub_rn(x, hi);
@@ -360,19 +372,15 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 float* HP = reinterpret_cast<float*>(sm + TC_XH);                // fc1 partial sums [12][leaf quad][41 (padded)][4] (31 488 B)
                 if (t < 480) {
                     const int part = t / 40, rem = t - part * 40, qg = rem >> 2, lq = rem & 3;
+                    uint64_t a2[2][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) a2[0][j] = a2[1][j] = 0ull;
+#pragma unroll 7
+                    for (int kk = 14 * part; kk < 14 * part + 14; kk++)
+                        tile44_fma2(a2, *reinterpret_cast<const float4*>(W1 + kk * Q + 4 * qg), *reinterpret_cast<const float4*>(SQ + (lq * SQP + kk) * 4));
                     float a[4][4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
-#pragma unroll 7
-                    for (int kk = 14 * part; kk < 14 * part + 14; kk++) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(W1 + kk * Q + 4 * qg);
-                        const float4 x4 = *reinterpret_cast<const float4*>(SQ + (lq * SQP + kk) * 4);
-                        const float w[4] = {w4.x, w4.y, w4.z, w4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) a[i][j] = fmaf(w[i], x[j], a[i][j]);
-                    }
+                    for (int j = 0; j < 4; j++) { upk2(a2[0][j], a[0][j], a[1][j]); upk2(a2[1][j], a[2][j], a[3][j]); }
 #pragma unroll
                     for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(HP + ((part * 4 + lq) * 41 + 4 * qg + i) * 4) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
                 }
@@ -390,19 +398,15 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 if (t < 504) {                                     // 3 K slices x 42 channel quads x 4 leaf quads
                     const int part = t / 168, rem = t - part * 168, cq = rem >> 2, lq = rem & 3;
                     const int k0 = part == 0 ? 0 : (part == 1 ? 14 : 27), k1 = part == 0 ? 14 : (part == 1 ? 27 : 40);
+                    uint64_t g2[2][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) g2[0][j] = g2[1][j] = 0ull;
+#pragma unroll 7
+                    for (int kk = k0; kk < k1; kk++)
+                        tile44_fma2(g2, *reinterpret_cast<const float4*>(W2 + kk * EC + 4 * cq), *reinterpret_cast<const float4*>(HID + kk * TB + 4 * lq));
                     float g[4][4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) g[i][0] = g[i][1] = g[i][2] = g[i][3] = 0.f;
-#pragma unroll 7
-                    for (int kk = k0; kk < k1; kk++) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(W2 + kk * EC + 4 * cq);
-                        const float4 x4 = *reinterpret_cast<const float4*>(HID + kk * TB + 4 * lq);
-                        const float w[4] = {w4.x, w4.y, w4.z, w4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) g[i][j] = fmaf(w[i], x[j], g[i][j]);
-                    }
+                    for (int j = 0; j < 4; j++) { upk2(g2[0][j], g[0][j], g[1][j]); upk2(g2[1][j], g[2][j], g[3][j]); }
 #pragma unroll
                     for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(GP + ((part * 4 + lq) * GPP + 4 * cq + i) * 4) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
                 }
@@ -584,19 +588,21 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 const int unit = min((t >> 5) * 16 + (t & 15), 175), half = (t >> 4) & 1;
                 const int part = unit / 44, task = unit - part * 44, o8 = task >> 2, lq = task & 3, slice = part + 4 * half;
                 const bool hi_ok = o8 < 10;                       // the last octet only has outputs 80..83
-                float acc[8][4];
+                uint64_t acc2a[2][4], acc2b[2][4];                // outputs 0-3 / 4-7 of the octet x 4 leaves, as FFMA2 pairs (2 outputs x 1 leaf)
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                for (int j = 0; j < 4; j++) acc2a[0][j] = acc2a[1][j] = acc2b[0][j] = acc2b[1][j] = 0ull;
                 auto fma_row = [&](const float* wrow, const float4 x4) {
                     const float4 wa = *reinterpret_cast<const float4*>(wrow), wb = hi_ok ? *reinterpret_cast<const float4*>(wrow + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
+                    tile44_fma2(acc2a, wa, x4); tile44_fma2(acc2b, wb, x4);
                 };
                 auto flush = [&]() {                              // lanes l and l ^ 16 hold the two K-slices of one task
                     if (!live) return;                            // warp-uniform (352 = 11 warps)
+                    float acc[8][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        upk2(acc2a[0][j], acc[0][j], acc[1][j]); upk2(acc2a[1][j], acc[2][j], acc[3][j]);
+                        upk2(acc2b[0][j], acc[4][j], acc[5][j]); upk2(acc2b[1][j], acc[6][j], acc[7][j]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -607,7 +613,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                             if (i < 4 || hi_ok) *reinterpret_cast<float4*>(PP + (part * PIP + 8 * o8 + i) * TB + 4 * lq) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                    for (int j = 0; j < 4; j++) acc2a[0][j] = acc2a[1][j] = acc2b[0][j] = acc2b[1][j] = 0ull;
                 };
                 for (int ch = 0; ch < NV / 8 && live; ch++) {
                     const float* W = acquire();
