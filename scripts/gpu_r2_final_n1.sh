@@ -7,7 +7,7 @@ timeout 900 python bench.py > gpurun_out/r02_bench_splendor_16384x800.json 2> gp
 timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r02_bench_splendor_reference_arm.json 2>> gpurun_out/bench_splendor.err
 timeout 900 python bench.py --game santorini > gpurun_out/r02_bench_santorini_4096x800.json 2> gpurun_out/bench_santorini.err
 timeout 900 python bench.py --game abalone > gpurun_out/r02_bench_abalone_2048x1600.json 2> gpurun_out/bench_abalone.err
-timeout 900 python bench.py --game azul > gpurun_out/r02_bench_azul_16384x800.json 2> gpurun_out/bench_azul.err
+timeout 900 python bench.py --game azul > gpurun_out/r02_bench_azul_8192x800.json 2> gpurun_out/bench_azul.err
 B="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-pcr --no-iteration"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2400 -c 300 --csv --log-file gpurun_out/r02_launches.csv $B > gpurun_out/ncu_launch_run.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log gpurun_out/smoke.log; wc -c gpurun_out/r02_bench_*.json
