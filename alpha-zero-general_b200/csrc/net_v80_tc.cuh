@@ -87,7 +87,7 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
 
 namespace tc {
 using namespace umma;
-enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_PI3, B_PE0, B_PE1, B_PE2, B_PE3, B_V2, B_MM2, B_N };
+enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_PI3, B_V2, B_MM2, B_N };
 struct Phase {                            // per-thread parity of every barrier this thread waits on
     uint32_t bits = 0;
     __device__ __forceinline__ void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
@@ -187,7 +187,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         }
         cp(SV_BPI2, L.bpi2, 84); cp(SV_BPI4, L.bpi4, 84); cp(SV_BV2, L.bv2, 4); cp(SV_BV4, L.bv4, 4); cp(SV_V4, L.v4, 16);
     }
-    if (t == 0) { for (int i = 0; i < B_N; i++) mbar_init(&bars[i], (i >= B_PE0 && i <= B_PE3) ? 11u : 1u); fence_barrier_init(); }   // B_PE*: one arrival per policy-head warp
+    if (t == 0) { for (int i = 0; i < B_N; i++) mbar_init(&bars[i], 1u); fence_barrier_init(); }
     if (warp == 0) tmem_alloc<512>(&tmem_s);
     for (int i = t; i < 65536 / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);   // token columns 56..63 only ever meet zero weights (they hold stale finite data once X's planes have served as E stages)
     tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -552,9 +552,10 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 // ---------------- policy head linears on CUDA cores: Linear(392 -> 81) + ReLU, Linear(81 -> 81), masked softmax ----------------
                 const float* X0 = reinterpret_cast<const float*>(ESTG);
                 float* H1 = reinterpret_cast<float*>(ESTG + HEAD_X0); float* LG = H1 + PIP * TB;     // LG: logits [leaf][85] (a warp reads one leaf's row)
-                // Weight ring (7 chunks of the 392 x 84 matrix, then the 81 x 84 one in two parts) through four slots, mbarrier-only: the 11
-                // computing warps wait for a slot to be full and arrive on its "empty" barrier when done; the last thread of the CTA (its
-                // warp has no policy work) refills a slot as soon as it is empty. No CTA-wide barrier per chunk.
+                // Weight ring (7 chunks of the 392 x 84 matrix, then the 81 x 84 one in two parts) through four slots. "Full" is the slot's
+                // mbarrier (bulk-copy transaction bytes). "Empty" is a NAMED barrier per slot (ids 1-4, 384 threads): the 11 computing warps
+                // bar.arrive when they are done with a slot, the last warp (no policy work) bar.syncs on it and its last lane refills the
+                // slot. No CTA-wide barrier per chunk, and the write-after-read edge is one compute-sanitizer's racecheck models.
                 uint32_t mw[3] = {0u, 0u, 0u};                     // this warp's leaf: legal-move words for the softmax below (the global load lands during the linears)
                 {
                     const int slot = slot_of[warp];
@@ -567,16 +568,19 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                     ent++;
                     return reinterpret_cast<const float*>(WRING + s * TC_PIRING_SLOT);
                 };
-                auto release = [&]() { __syncwarp(); if (lane == 0) mbar_arrive(&bars[B_PE0 + ((ent - 1) & 3)]); };
-                if (t == TC_THREADS - 1) {
+                auto release = [&]() { asm volatile("bar.arrive %0, 384;" ::"r"(1 + ((ent - 1) & 3)) : "memory"); };
+                if (warp == TC_THREADS / 32 - 1) {
 #pragma unroll 1
                     for (int e = 4; e < 9; e++) {
                         const int s2 = e & 3;
-                        ph.wait(bars, B_PE0 + s2);                 // the previous entry of this slot has been consumed by all 11 warps
-                        fence_async_smem();                        // (acquire above) order those generic-proxy reads before the async-proxy refill
-                        const float* src = e < 7 ? P + L.pi2 + e * 56 * PIP : (e == 7 ? P + L.pi4 : P + L.pi4 + 41 * PIP);
-                        const uint32_t bytes = e < 7 ? TC_PIRING_SLOT : (e == 7 ? 41 * PIP * 4 : 40 * PIP * 4);
-                        load(bars, B_PI0 + s2, WRING + s2 * TC_PIRING_SLOT, src, bytes);
+                        asm volatile("bar.sync %0, 384;" ::"r"(1 + s2) : "memory");   // the previous entry of this slot has been consumed by all 11 warps
+                        if (lane == 31) {
+                            fence_async_smem();                    // order those generic-proxy reads before the async-proxy refill
+                            const float* src = e < 7 ? P + L.pi2 + e * 56 * PIP : (e == 7 ? P + L.pi4 : P + L.pi4 + 41 * PIP);
+                            const uint32_t bytes = e < 7 ? TC_PIRING_SLOT : (e == 7 ? 41 * PIP * 4 : 40 * PIP * 4);
+                            load(bars, B_PI0 + s2, WRING + s2 * TC_PIRING_SLOT, src, bytes);
+                        }
+                        __syncwarp();
                     }
                 }
                 // 352 tasks = 8 K-slices x 11 output octets x 4 leaf quads (register tile 8 x 4: 32 FMA per three 128-bit loads; the loads,
@@ -651,7 +655,10 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #ifdef AZG_TC_POLICY_PROF
                 TC_STAMP();
 #endif
-                if (t == TC_THREADS - 1) { ph.wait(bars, B_PE0); ph.wait(bars, B_PE1); ph.wait(bars, B_PE2); ph.wait(bars, B_PE3); }   // last entry of every slot consumed (keeps the parities in step)
+                if (warp == TC_THREADS / 32 - 1) {                   // the last entry of every slot has been released too: every named barrier is back at a fresh generation
+                    asm volatile("bar.sync 1, 384;" ::: "memory"); asm volatile("bar.sync 2, 384;" ::: "memory");
+                    asm volatile("bar.sync 3, 384;" ::: "memory"); asm volatile("bar.sync 4, 384;" ::: "memory");
+                }
                 __syncwarp();
                 flush();
 #ifdef AZG_TC_POLICY_PROF
