@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SO_PATH = os.path.join(CSRC, 'libazg_b200.so')
+SO_PATH = os.environ.get('AZG_LIB_PATH') or os.path.join(CSRC, 'libazg_b200.so')   # AZG_LIB_PATH: another build of the same ABI (A/B timing runs)
 
 AZG_GAME_SPLENDOR = 1
 AZG_GAME_SANTORINI = 2
