@@ -9,8 +9,8 @@
 // fp32 on the CUDA cores: these are the "next" games of SURVEY 8f, not the headline configuration.
 //
 // One CTA = 8 leaves, 512 threads. Activations live in shared memory as [feature index][leaf] (the 8 leaves of a feature are two
-// 128-bit words), so one thread owns one output feature for all 8 leaves: per input it needs ONE weight (K-major images, coalesced
-// across the threads' outputs, L1/L2 resident) and two 128-bit shared loads for 8 FMAs. Layers with few outputs (SE fc1, the value
+// 128-bit words); one thread owns TWO output features for all 8 leaves: per input it needs two weights (K-major images, coalesced
+// across the threads' outputs, L1/L2 resident) and two 128-bit shared loads for 16 FMAs. Layers with few outputs (SE fc1, the value
 // head) split K over thread groups and add the partial sums in a fixed order (bit-reproducible results). BatchNorm (eval mode) is
 // folded into the preceding linear on the host (tokmix_prepare).
 #pragma once
@@ -100,36 +100,59 @@ __device__ __forceinline__ void fma8(float (&acc)[8], float w, const F8& x) {
     acc[4] = fmaf(w, x.b.x, acc[4]); acc[5] = fmaf(w, x.b.y, acc[5]); acc[6] = fmaf(w, x.b.z, acc[6]); acc[7] = fmaf(w, x.b.w, acc[7]);
 }
 // token-axis Linear (+ folded BN, + activation, + optional residual): Y[(o*F+f)][l] = act(b[o] + sum_i Wt[i*out+o] X[(i*F+f)][l]) (+ R)
+// A thread owns TWO outputs (o, o + 1) of one feature row for all 8 leaves: the two 128-bit activation loads of an input feed 16 FMAs.
+// With one output per thread the phase is bound by shared-memory wavefronts (a broadcast 128-bit load still costs one wavefront per
+// quarter-warp): 1 wavefront-cycle per FMA instruction. The summation order per output is unchanged.
 template <int F>
 __device__ __forceinline__ void token_linear(const float* __restrict__ Wt, const float* __restrict__ b, int out, int in, const float* X, float* Y,
                                              int act, const float* R, int t) {
-    for (int idx = t; idx < out * F; idx += TM_THREADS) {
-        const int f = idx / out, o = idx - f * out;              // consecutive threads = consecutive outputs: coalesced weight reads
-        float acc[8]; const float bb = __ldg(b + o);
+    const int op = (out + 1) >> 1;
+    for (int idx = t; idx < op * F; idx += TM_THREADS) {
+        const int f = idx / op, o = 2 * (idx - f * op);          // consecutive threads = consecutive output pairs: coalesced weight reads
+        const bool two = o + 1 < out;
+        float a0[8], a1[8]; const float b0 = __ldg(b + o), b1 = two ? __ldg(b + o + 1) : 0.f;
 #pragma unroll
-        for (int l = 0; l < 8; l++) acc[l] = bb;
+        for (int l = 0; l < 8; l++) { a0[l] = b0; a1[l] = b1; }
+        const float* w = Wt + o; const float* x = X + f * TM_TB;
 #pragma unroll 4
-        for (int i = 0; i < in; i++) fma8(acc, __ldg(Wt + i * out + o), ld8(X + (i * F + f) * TM_TB));   // 4 weight + 8 activation loads in flight per thread
-        if (R) { const F8 r = ld8(R + (o * F + f) * TM_TB); const float rr[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+        for (int i = 0; i < in; i++) {
+            const float w0 = __ldg(w + i * out), w1 = two ? __ldg(w + i * out + 1) : 0.f;
+            const F8 xv = ld8(x + i * F * TM_TB);
+            fma8(a0, w0, xv); fma8(a1, w1, xv);
+        }
 #pragma unroll
-            for (int l = 0; l < 8; l++) acc[l] += rr[l]; }
+        for (int h = 0; h < 2; h++) {
+            if (h == 1 && !two) break;
+            float (&acc)[8] = h ? a1 : a0;
+            const int oo = o + h;
+            if (R) { const F8 r = ld8(R + (oo * F + f) * TM_TB); const float rr[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
 #pragma unroll
-        for (int l = 0; l < 8; l++) acc[l] = act_apply(acc[l], act);
-        st8(Y + (o * F + f) * TM_TB, acc);
+                for (int l = 0; l < 8; l++) acc[l] += rr[l]; }
+#pragma unroll
+            for (int l = 0; l < 8; l++) acc[l] = act_apply(acc[l], act);
+            st8(Y + (oo * F + f) * TM_TB, acc);
+        }
     }
 }
-// dense layer over flat features with a K split: PART[(ks*out+o)][l] = sum_{k in slice ks} Wt[k*out+o] X[k][l]
+// dense layer over flat features with a K split: PART[(ks*out+o)][l] = sum_{k in slice ks} Wt[k*out+o] X[k][l]; two outputs per thread
 __device__ __forceinline__ void dense_partial(const float* __restrict__ Wt, int out, int K, int KS, const float* X, float* PART, int t) {
-    const int per = (K + KS - 1) / KS;
-    for (int idx = t; idx < out * KS; idx += TM_THREADS) {
-        const int ks = idx / out, o = idx - ks * out;
-        float acc[8];
+    const int per = (K + KS - 1) / KS, op = (out + 1) >> 1;
+    for (int idx = t; idx < op * KS; idx += TM_THREADS) {
+        const int ks = idx / op, o = 2 * (idx - ks * op);
+        const bool two = o + 1 < out;
+        float a0[8], a1[8];
 #pragma unroll
-        for (int l = 0; l < 8; l++) acc[l] = 0.f;
+        for (int l = 0; l < 8; l++) a0[l] = a1[l] = 0.f;
         const int k1 = min(K, (ks + 1) * per);
+        const float* w = Wt + o;
 #pragma unroll 4
-        for (int k = ks * per; k < k1; k++) fma8(acc, __ldg(Wt + k * out + o), ld8(X + k * TM_TB));
-        st8(PART + (ks * out + o) * TM_TB, acc);
+        for (int k = ks * per; k < k1; k++) {
+            const float w0 = __ldg(w + k * out), w1 = two ? __ldg(w + k * out + 1) : 0.f;
+            const F8 xv = ld8(X + k * TM_TB);
+            fma8(a0, w0, xv); fma8(a1, w1, xv);
+        }
+        st8(PART + (ks * out + o) * TM_TB, a0);
+        if (two) st8(PART + (ks * out + o + 1) * TM_TB, a1);
     }
 }
 // Y[o][l] = epi(b[o] + sum_ks PART[ks][o][l]) in a fixed order; epi: 0 none, 1 relu, 3 hardsigmoid
@@ -185,17 +208,23 @@ k_tokmix_forward(const float* __restrict__ P, const __grid_constant__ TokMixLayo
         float* OUT = k == 0 ? X : H;
         token_linear<F>(P + B.we, P + B.be, B.E, B.in, IN, E, B.act, nullptr, t);
         __syncthreads();
-        for (int idx = t; idx < B.E * F; idx += TM_THREADS) {        // "depthwise": shared Linear(F->F) over the features, BN per channel, act
-            const int c = idx / F, g = idx - c * F;
-            float acc[8];
+        constexpr int GP = (F + 1) / 2;
+        for (int idx = t; idx < B.E * GP; idx += TM_THREADS) {       // "depthwise": shared Linear(F->F) over the features, BN per channel, act;
+            const int c = idx / GP, g = 2 * (idx - c * GP);          // two output features per thread share the activation loads
+            const bool two = g + 1 < F;
+            float a0[8], a1[8];
 #pragma unroll
-            for (int l = 0; l < 8; l++) acc[l] = 0.f;
+            for (int l = 0; l < 8; l++) a0[l] = a1[l] = 0.f;
 #pragma unroll
-            for (int f = 0; f < F; f++) fma8(acc, __ldg(P + B.dw + g * F + f), ld8(E + (c * F + f) * TM_TB));
+            for (int f = 0; f < F; f++) {
+                const F8 xv = ld8(E + (c * F + f) * TM_TB);
+                fma8(a0, __ldg(P + B.dw + g * F + f), xv); fma8(a1, two ? __ldg(P + B.dw + (g + 1) * F + f) : 0.f, xv);
+            }
             const float sd = __ldg(P + B.sd + c), td = __ldg(P + B.td + c);
 #pragma unroll
-            for (int l = 0; l < 8; l++) acc[l] = act_apply(fmaf(acc[l], sd, td), B.act);
-            st8(D + idx * TM_TB, acc);
+            for (int l = 0; l < 8; l++) { a0[l] = act_apply(fmaf(a0[l], sd, td), B.act); a1[l] = act_apply(fmaf(a1[l], sd, td), B.act); }
+            st8(D + (c * F + g) * TM_TB, a0);
+            if (two) st8(D + (c * F + g + 1) * TM_TB, a1);
         }
         __syncthreads();
         for (int idx = t; idx < B.E * TM_TB; idx += TM_THREADS) {     // squeeze over the F features: AdaptiveAvgPool1d(1) or AdaptiveMaxPool1d(1)
