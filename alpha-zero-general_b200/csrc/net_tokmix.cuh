@@ -116,7 +116,7 @@ __device__ __forceinline__ void token_linear(const float* __restrict__ Wt, const
         const float* w = Wt + o; const float* x = X + f * TM_TB;
 #pragma unroll 4
         for (int i = 0; i < in; i++) {
-            const float w0 = __ldg(w + i * out), w1 = two ? __ldg(w + i * out + 1) : 0.f;
+            const float w0 = __ldg(w + i * out), w1 = __ldg(w + i * out + 1);   // an odd tail reads the next row's first weight (inside the blob); its sums are dropped
             const F8 xv = ld8(x + i * F * TM_TB);
             fma8(a0, w0, xv); fma8(a1, w1, xv);
         }
@@ -147,7 +147,7 @@ __device__ __forceinline__ void dense_partial(const float* __restrict__ Wt, int 
         const float* w = Wt + o;
 #pragma unroll 4
         for (int k = ks * per; k < k1; k++) {
-            const float w0 = __ldg(w + k * out), w1 = two ? __ldg(w + k * out + 1) : 0.f;
+            const float w0 = __ldg(w + k * out), w1 = __ldg(w + k * out + 1);
             const F8 xv = ld8(X + k * TM_TB);
             fma8(a0, w0, xv); fma8(a1, w1, xv);
         }
