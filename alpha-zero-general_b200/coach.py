@@ -19,6 +19,8 @@ class Coach:
         self.engine = Engine(game, nnet, a, self.n_games, dirichlet_noise=(a.dirichletAlpha != 0), seed=seed,
                              node_cap=node_cap, edge_cap=edge_cap)
         self.trainExamplesHistory = []
+        self.skipFirstSelfPlay = False                                  # Coach.py:33: set when examples were loaded from a checkpoint
+        self.consecutive_failures = 0
 
     def raw_examples(self, min_episodes, max_moves=0):
         """Plays until `min_episodes` games finished; returns un-augmented example arrays (one per full-search ply).
@@ -64,6 +66,7 @@ class Coach:
         from .formats import load_train_examples
         path = examples_file or (os.path.dirname(self.args.load_folder_file) + '/checkpoint.examples')
         self.trainExamplesHistory = load_train_examples(path, self.args.no_compression, self.args.get('numItersHistory'), self.args.maxlenOfQueue)
+        self.skipFirstSelfPlay = True                                   # Coach.py:262: the loaded history already holds this iteration's examples
         return self.trainExamplesHistory
 
     # ---- accept gate (Coach.py:194-215) ----
@@ -85,6 +88,65 @@ class Coach:
     def executeEpisodes(self, num_eps=None):
         num_eps = int(self.args.numEps if num_eps is None else num_eps)
         ex = self.augment(*self.raw_examples(num_eps))
+        if not self.args.no_compression:                                # Coach.py:69: examples are kept as zlib(pickle(tuple)) unless --no-compression
+            from .formats import compress_example
+            ex = [compress_example(e) for e in ex]
         q = deque([], maxlen=self.args.maxlenOfQueue)
         q += ex
         return q
+
+    # ---- the outer loop (Coach.py:150-215) ----
+    @staticmethod
+    def getCheckpointFile(iteration):
+        return 'checkpoint_' + str(iteration) + '.pt'
+
+    def learn(self, log=print):
+        """numIters iterations of: self-play on the device engine (numEps finished games) -> history of the last numItersHistory
+        iterations saved as checkpoint.examples -> the net is trained on the shuffled history (a copy of the old weights is kept as
+        temp.pt) -> arena of arenaCompare games new vs previous on the engine, every game in flight at once -> the new net is kept
+        (checkpoint_<i>.pt and best.pt) when it wins >= updateThreshold of the decisive games, else temp.pt is restored. After
+        stop_after_N_fail consecutive rejections the loop stops (the reference exits the process). Returns one record per iteration."""
+        import random
+        a = self.args
+        pnet = type(self.nnet)(self.game, dict(self.nnet.args))         # Coach.py:27: the competitor network
+        records = []
+        for i in range(1, int(a.get('numIters', 50)) + 1):
+            if not self.skipFirstSelfPlay or i > 1:
+                it = self.executeEpisodes()
+                if len(it) == a.maxlenOfQueue:
+                    log('saturation of elements in iterationTrainExamples, think about decreasing numEps or increasing maxlenOfQueue')
+                self.trainExamplesHistory.append(it)
+                if len(it) and a.dirichletAlpha > 0:                    # Coach.py:168-175: advice on the Dirichlet alpha
+                    from .formats import decompress_example
+                    avg_valid = float(np.mean([np.sum((x if a.no_compression else decompress_example(x))[3]) for x in it]))
+                    if not (1 / 1.5 < a.dirichletAlpha / (10 / avg_valid) < 1.5):
+                        log(f'There are about {avg_valid:.1f} valid moves per state, so I advise to set dirichlet to {10 / avg_valid:.1f} instead')
+            if a.get('profile'):
+                return records
+            if len(self.trainExamplesHistory) > a.numItersHistory:
+                self.trainExamplesHistory.pop(0)
+            self.saveTrainExamples()
+            train_examples = []
+            for e in self.trainExamplesHistory:
+                train_examples.extend(e)
+            random.shuffle(train_examples)
+            extra = {k: v for k, v in dict(a).items() if isinstance(v, (int, float, str, bool, list, tuple, type(None)))}
+            self.nnet.save_checkpoint(folder=a.checkpoint, filename='temp.pt', additional_keys=extra)
+            pnet.load_checkpoint(folder=a.checkpoint, filename='temp.pt')
+            self.nnet.train(train_examples)
+            nwins, pwins, draws, accepted = self.pit(self.nnet, pnet)
+            if not accepted:
+                self.consecutive_failures += 1
+                log(f'Iter #{i} - new vs previous: {nwins}-{pwins}  ({draws} draws) --> REJECTED ({self.consecutive_failures})')
+                self.nnet.load_checkpoint(folder=a.checkpoint, filename='temp.pt')
+            else:
+                log(f'Iter #{i} - new vs previous: {nwins}-{pwins}  ({draws} draws) --> ACCEPTED')
+                self.nnet.save_checkpoint(folder=a.checkpoint, filename=self.getCheckpointFile(i), additional_keys=extra)
+                self.nnet.save_checkpoint(folder=a.checkpoint, filename='best.pt', additional_keys=extra)
+                self.consecutive_failures = 0
+            records.append(dict(iteration=i, examples=len(train_examples), nwins=nwins, pwins=pwins, draws=draws, accepted=accepted))
+            stop = a.get('stop_after_N_fail', -1)
+            if not accepted and stop is not None and stop > 0 and self.consecutive_failures >= stop and i < a.get('numIters', 50):
+                log('Exceeded threshold number of consecutive fails, stopping process')
+                break
+        return records
