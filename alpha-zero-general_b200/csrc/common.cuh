@@ -89,4 +89,10 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
     return v;
 }
 
+
+// Packed fp32 FMA (FFMA2): two IEEE fp32 FMAs per instruction, bit-identical to two fmaf. Same FMA-lane throughput as FFMA
+// (csrc/probe/ffma2_probe.cu) but half the issue slots, which is what the register-tiled linears / 1x1 convolutions are bound by.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void fma2(uint64_t& acc, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 }  // namespace azg

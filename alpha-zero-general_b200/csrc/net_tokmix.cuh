@@ -170,10 +170,14 @@ __device__ __forceinline__ void dense_reduce(const float* PART, const float* __r
 template <int NV, int F, int A, int NP, int EMAX, int OMAX, int QMAX> struct TokMixSmem {
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int VKS = 32;                                // K split of the value head
-    static constexpr int PKS = A <= 96 ? 6 : 4;                   // K split of the two policy Linears (A x PKS work items for the CTA's threads)
+    static constexpr int PKS = A <= 96 ? 6 : 4;                   // K split of the two policy Linears (A / 2 output pairs x PKS work items; 5 instead of 4 for Azul measured 45 % SLOWER)
     static constexpr int X = 0, T = X + NV * F * 8, E = T + NV * F * 8, D = E + EMAX * F * 8, H = D + EMAX * F * 8, SQ = H + OMAX * F * 8,
                          HID = SQ + EMAX * 8, PART = HID + cmax(QMAX, NP) * 8,
-                         PART_N = cmax(cmax(8 * QMAX, 2 * EMAX), cmax(PKS * A, VKS * NP)) * 8, H1 = PART + PART_N, TOTAL = H1 + A * 8;
+                         PART_N = cmax(cmax(8 * QMAX, 2 * EMAX), VKS * NP) * 8, TOTAL = PART + PART_N,
+                         // the policy head runs between the policy block and the value block, when E and D are dead: its K-split partial sums and
+                         // its hidden layer live there (a smaller CTA leaves more of the SM's 256 KB to the L1 that holds the weights)
+                         PPART = E, H1 = E + PKS * A * 8;
+    static_assert(PKS * A * 8 + A * 8 <= 2 * EMAX * F * 8, "policy head scratch must fit the expanded-activation buffers");
     static constexpr size_t bytes() { return (size_t)TOTAL * 4; }
 };
 
@@ -191,7 +195,7 @@ k_tokmix_forward(const float* __restrict__ P, const __grid_constant__ TokMixLayo
     const int tile0 = blockIdx.x * TM_TB;
     if (tile0 >= count) return;
     float* X = smf + SM::X; float* T = smf + SM::T; float* E = smf + SM::E; float* D = smf + SM::D; float* H = smf + SM::H;
-    float* SQ = smf + SM::SQ; float* HID = smf + SM::HID; float* PART = smf + SM::PART; float* H1 = smf + SM::H1;
+    float* SQ = smf + SM::SQ; float* HID = smf + SM::HID; float* PART = smf + SM::PART; float* H1 = smf + SM::H1; float* PPART = smf + SM::PPART;
     if (t < TM_TB) { const int j = tile0 + t; slot_of[t] = j < count ? (list ? list[j] : j) : -1; }
     __syncthreads();
     for (int idx = t; idx < S * TM_TB; idx += TM_THREADS) {       // X[i][l] = (float)board[l][i]
@@ -248,13 +252,13 @@ k_tokmix_forward(const float* __restrict__ P, const __grid_constant__ TokMixLayo
         token_linear<F>(P + B.wp, P + B.bp, B.out, B.E, D, OUT, 0, B.res ? IN : nullptr, t);
         __syncthreads();
         if (k == 1) {   // ---- policy head: Linear(out*F -> A) + ReLU, Linear(A -> A), masked log_softmax -> exp
-            dense_partial(P + L.pi2, A, B.out * F, SM::PKS, H, PART, t);
+            dense_partial(P + L.pi2, A, B.out * F, SM::PKS, H, PPART, t);
             __syncthreads();
-            dense_reduce(PART, P + L.bpi2, A, SM::PKS, H1, 1, t);
+            dense_reduce(PPART, P + L.bpi2, A, SM::PKS, H1, 1, t);
             __syncthreads();
-            dense_partial(P + L.pi4, A, A, SM::PKS, H1, PART, t);
+            dense_partial(P + L.pi4, A, A, SM::PKS, H1, PPART, t);
             __syncthreads();
-            dense_reduce(PART, P + L.bpi4, A, SM::PKS, H1, 0, t);
+            dense_reduce(PPART, P + L.bpi4, A, SM::PKS, H1, 0, t);
             __syncthreads();
             {
                 const int sl = warp & 7, slot = warp < TM_TB ? slot_of[sl] : -1;   // warps 0-7 = the 8 leaves

@@ -78,28 +78,33 @@ __device__ __forceinline__ void conv1x1(const float* W, const float* bias, const
     constexpr int N = TB * 81, TASKS = (COUT / OG) * 81;
     for (int t = threadIdx.x; t < TASKS; t += V21_THREADS) {
         const int og = t / 81, nq = t - og * 81, o0 = OG * og;
-        float acc[OG][TB];
+        uint64_t acc2[OG / 2][TB];                                 // FFMA2 pairs: outputs (2 jp, 2 jp + 1) x one position
 #pragma unroll
-        for (int j = 0; j < OG; j++)
+        for (int j = 0; j < OG / 2; j++)
 #pragma unroll
-            for (int l = 0; l < TB; l++) acc[j][l] = 0.f;
+            for (int l = 0; l < TB; l++) acc2[j][l] = 0ull;
         const float* xin = in + TB * nq; const float* wk = W + o0;
 #pragma unroll 4
         for (int k = 0; k < CIN; k++) {
             const VT xv = *reinterpret_cast<const VT*>(xin + k * N);
             float x[TB];
             memcpy(x, &xv, sizeof(xv));
-            float w[OG];
+            uint64_t xd[TB];
+#pragma unroll
+            for (int l = 0; l < TB; l++) xd[l] = pk2(x[l], x[l]);
 #pragma unroll
             for (int j4 = 0; j4 < OG / 4; j4++) {
                 const float4 w4 = *reinterpret_cast<const float4*>(wk + k * COUT + 4 * j4);
-                w[4 * j4] = w4.x; w[4 * j4 + 1] = w4.y; w[4 * j4 + 2] = w4.z; w[4 * j4 + 3] = w4.w;
+                const uint64_t w01 = pk2(w4.x, w4.y), w23 = pk2(w4.z, w4.w);
+#pragma unroll
+                for (int l = 0; l < TB; l++) { fma2(acc2[2 * j4][l], w01, xd[l]); fma2(acc2[2 * j4 + 1][l], w23, xd[l]); }
             }
-#pragma unroll
-            for (int j = 0; j < OG; j++)
-#pragma unroll
-                for (int l = 0; l < TB; l++) acc[j][l] = fmaf(w[j], x[l], acc[j][l]);
         }
+        float acc[OG][TB];
+#pragma unroll
+        for (int j = 0; j < OG / 2; j++)
+#pragma unroll
+            for (int l = 0; l < TB; l++) upk2(acc2[j][l], acc[2 * j][l], acc[2 * j + 1][l]);
 #pragma unroll
         for (int j = 0; j < OG; j++) {
             const float b = bias[o0 + j];
@@ -230,24 +235,29 @@ __device__ __forceinline__ void v21_tile(const float* __restrict__ P, const V21L
     // heads (both read X only; E and D are free): policy logits on warps 0..7 overwrite E/D; value features and value Linear on warps 8..15
     if (t < 3 * 81) {                                                                 // 1x1 24->42 + BN -> logits[r][q][plane]; task = 14 planes x position
         const int og = t / 81, pos = t - og * 81, o0 = 14 * og;
-        float acc[14][TB];
+        uint64_t acc2[7][TB];                                                          // FFMA2 pairs: planes (2 j2, 2 j2 + 1) x one leaf
 #pragma unroll
-        for (int j = 0; j < 14; j++)
+        for (int j = 0; j < 7; j++)
 #pragma unroll
-            for (int l = 0; l < TB; l++) acc[j][l] = 0.f;
+            for (int l = 0; l < TB; l++) acc2[j][l] = 0ull;
 #pragma unroll 2
         for (int i = 0; i < 24; i++) {
-            float x[TB];
+            uint64_t xd[TB];
 #pragma unroll
-            for (int l = 0; l < TB; l++) x[l] = X[i * N + l * 81 + pos];
+            for (int l = 0; l < TB; l++) { const float x = X[i * N + l * 81 + pos]; xd[l] = pk2(x, x); }
             const float2* w2 = reinterpret_cast<const float2*>(WS + L.wpi + i * 42 + o0);
 #pragma unroll
             for (int j2 = 0; j2 < 7; j2++) {
-                const float2 w = w2[j2];
+                const float2 w = w2[j2]; const uint64_t wp = pk2(w.x, w.y);
 #pragma unroll
-                for (int l = 0; l < TB; l++) { acc[2 * j2][l] = fmaf(w.x, x[l], acc[2 * j2][l]); acc[2 * j2 + 1][l] = fmaf(w.y, x[l], acc[2 * j2 + 1][l]); }
+                for (int l = 0; l < TB; l++) fma2(acc2[j2][l], wp, xd[l]);
             }
         }
+        float acc[14][TB];
+#pragma unroll
+        for (int j = 0; j < 7; j++)
+#pragma unroll
+            for (int l = 0; l < TB; l++) upk2(acc2[j][l], acc[2 * j][l], acc[2 * j + 1][l]);
 #pragma unroll
         for (int j2 = 0; j2 < 7; j2++) {
             const float b0 = WS[L.bpi + o0 + 2 * j2], b1 = WS[L.bpi + o0 + 2 * j2 + 1];

@@ -105,11 +105,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
-// Packed fp32 FMA (FFMA2): two IEEE fp32 FMAs per instruction, bit-identical to two fmaf. Same FMA-lane throughput as FFMA
-// (csrc/probe/ffma2_probe.cu) but half the issue slots, which is what the register-tiled linears below are bound by.
-__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ void fma2(uint64_t& acc, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 // acc[ip][j] (+)= (w[2 ip], w[2 ip + 1]) * x[j] for a 4 x 4 register tile: 8 FFMA2
 __device__ __forceinline__ void tile44_fma2(uint64_t (&acc)[2][4], const float4 w4, const float4 x4) {
     const uint64_t w01 = pk2(w4.x, w4.y), w23 = pk2(w4.z, w4.w);

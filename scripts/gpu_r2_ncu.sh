@@ -18,3 +18,11 @@ echo "==== k_v89_tc (Santorini bench) ====" >> gpurun_out/r02_ncu_summary.txt
 python scripts/ncu_summary.py /tmp/r02_k_v89_tc.ncu-rep >> gpurun_out/r02_ncu_summary.txt 2>&1
 python scripts/ncu_source_hot.py /tmp/r02_k_v89_tc.ncu-rep >> gpurun_out/r02_ncu_summary.txt 2>&1
 tail -5 gpurun_out/r02_ncu_summary.txt
+for GK in "abalone k_v21_forward" "azul k_tokmix_forward"; do
+  set -- $GK
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s 200 -c 1 -f -o /tmp/r02_$2 python bench.py --game $1 --steps 1 --warmup 1 --no-e2e --no-cpu --no-pcr --no-iteration > gpurun_out/ncu_$2.log 2>&1
+  echo "==== $2 ($1 bench) ====" >> gpurun_out/r02_ncu_summary.txt
+  python scripts/ncu_summary.py /tmp/r02_$2.ncu-rep >> gpurun_out/r02_ncu_summary.txt 2>&1
+  python scripts/ncu_source_hot.py /tmp/r02_$2.ncu-rep >> gpurun_out/r02_ncu_summary.txt 2>&1
+done
+tail -5 gpurun_out/r02_ncu_summary.txt
