@@ -137,6 +137,7 @@ def test_reference_execute_episode_runs_over_the_facades(fake):
     from azg_b200.nnet import HashNetWrapper
     from azg_b200.utils import dotdict
     game = azg_b200.SplendorGame()
+    game._seed_ctr = 20261017                                           # the facade seeds its real-move RNG keys from OS entropy: fixed here, the test plays one known game
     net = HashNetWrapper(game)
     args = dotdict(numMCTSSims=12, cpuct=1.25, fpu=0.0, universes=1, dirichletAlpha=0.3, temperature=[1.0, 0.1, 1.1], tempThreshold=10,
                    prob_fullMCTS=0.5, ratio_fullMCTS=3, forced_playouts=False, no_mem_optim=False, no_compression=True)
@@ -149,7 +150,7 @@ def test_reference_execute_episode_runs_over_the_facades(fake):
     for b, pi, z, valids, q in examples[:40]:
         assert isinstance(b, np.ndarray) and b.dtype == np.int8 and b.shape == (56, 7)
         assert pi.dtype == np.float32 and pi.shape == (81,) and abs(float(pi.sum()) - 1.0) < 1e-5
-        assert z.dtype == np.float32 and z.shape == (2,) and set(np.abs(z).round(2).tolist()) <= {1.0, 0.01}
+        assert z.dtype == np.float32 and z.shape == (2,) and all(min(abs(abs(float(x)) - 1.0), abs(abs(float(x)) - 0.01)) < 1e-6 for x in z)   # win / loss, or the 0.01 of a tie (a game that ran into the round limit)
         assert valids.shape == (81,) and valids.dtype == np.bool_ and (pi[~valids] == 0).all()
         assert len(q) == 2 and abs(float(q[0]) + float(q[1])) < 1e-6
     # the reference's example pipeline accepts them: Coach.py:172-176 (valid-move statistics) and the on-disk format
