@@ -322,7 +322,7 @@ struct azg_net {
     long long* prof = nullptr;            // optional phase timestamps of CTA 0 (AZG_V80_PROF=1; azg_net_prof)
     int v80_kernel = 1;                   // 1 = tcgen05 kernel (default), 0 = fp32 CUDA-core kernel (kept for A/B profiling; AZG_V80_KERNEL=fp32)
     V89Layout L89; V89Chunks CK89; V21Layout L21; TokMixLayout LTM; bool tokmix = false;   // tokmix: AzulNNet V84, SplendorNNet V80 for 3 / 4 players
-    V89TCImg TI89; float* img89 = nullptr; float* res89 = nullptr; int v89_kernel = 1;   // tcgen05 trunk (default) or the fp32 CUDA-core kernel (AZG_V89_KERNEL=fp32, A/B runs)
+    V89TCImg TI89; V89First F89; float* img89 = nullptr; float* res89 = nullptr; int v89_kernel = 1;   // tcgen05 trunk (default) or the fp32 CUDA-core kernel (AZG_V89_KERNEL=fp32, A/B runs)
     Scratch masks;                        // packed masks for the standalone forward
     unsigned long long launches = 0;
     bool attr_done = false; int n_sm = 0;  // launch attributes of this net's kernel on this net's device (set at the first launch)
@@ -382,7 +382,7 @@ static int net_forward_dev(azg_net* net, const int* count_ptr, const int* list, 
                 if (!net->res89) CK(cudaMalloc(&net->res89, sizeof(float) * (size_t)net->n_sm * T89_RES_FLOATS));   // per-CTA residual scratch (stays in L2)
                 const int tiles = (n_max + T89_TB - 1) / T89_TB;
                 static const int grid_cap = getenv("AZG_V89_GRID") ? atoi(getenv("AZG_V89_GRID")) : 1 << 30;   // debug: fewer CTAs (is the kernel bound by L2 bandwidth?)
-                k_v89_tc<<<std::min(std::min(tiles, net->n_sm), grid_cap), T89_THREADS, T89_SMEM, st>>>(net->blob, net->img89, net->res89, net->L89, net->TI89, count_ptr, list, boards, bstride, masks, pi, v, n_max, net->prof);
+                k_v89_tc<<<std::min(std::min(tiles, net->n_sm), grid_cap), T89_THREADS, T89_SMEM, st>>>(net->blob, net->img89, net->res89, net->L89, net->TI89, net->F89, count_ptr, list, boards, bstride, masks, pi, v, n_max, net->prof);
             } else {
             constexpr size_t smem = v89_smem_bytes();
             if (!net->attr_done) { CK(cudaFuncSetAttribute(k_v89_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); net->attr_done = true; }
@@ -442,6 +442,9 @@ extern "C" int azg_net_load(azg_net* net, const float* weights, size_t n_weights
         std::vector<float> img((size_t)net->TI89.total);
         v89tc_prepare(dst.data(), net->L89, net->TI89, img.data());
         CK(cudaMemcpy(net->img89, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+        for (int i = 0; i < 2 * 9 * 64; i++) net->F89.w[i] = dst[net->L89.conv[0] + i];          // first layer: kernel-parameter copy (constant bank)
+        for (int i = 0; i < 64; i++) net->F89.b[i] = dst[net->L89.cbias[0] + i];
+        for (int i = 0; i < 64; i++) { net->F89.wh[3 * i] = dst[net->L89.pi_w + 2 * i]; net->F89.wh[3 * i + 1] = dst[net->L89.pi_w + 2 * i + 1]; net->F89.wh[3 * i + 2] = dst[net->L89.v_w + i]; }
         return 0;
     }
     const size_t need = v80_src_floats(SP2::ROWS, net->np);

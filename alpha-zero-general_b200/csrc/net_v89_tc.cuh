@@ -97,9 +97,14 @@ __device__ __forceinline__ void store_row16(uint8_t* act, int row, int c0, const
 }
 }  // namespace t89
 
+// First-layer weights [cin 2][tap 9][cout 64] and bias as a kernel parameter: with the loops unrolled every weight is a constant-bank
+// operand of its FFMA. (Read from shared memory, the same weight for all lanes is a broadcast 128-bit load = one wavefront per
+// quarter-warp, 17 wavefronts per 16 FMAs: the layer was bound by that.)
+struct V89First { float w[2 * 9 * 64]; float b[64]; float wh[64 * 3]; };   // wh: the 1x1 head convolutions [cin][policy 0, policy 1, value]
+
 __global__ void __launch_bounds__(T89_THREADS, 1)
 k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __restrict__ RES, const __grid_constant__ V89Layout L, const __grid_constant__ V89TCImg I,
-         const int* count_ptr, const int* list, const int8_t* boards, int bstride, const uint32_t* masks, float* pi_out, float* v_out, int n_max, long long* prof) {
+         const __grid_constant__ V89First F0, const int* count_ptr, const int* list, const int8_t* boards, int bstride, const uint32_t* masks, float* pi_out, float* v_out, int n_max, long long* prof) {
     using namespace t89;
     constexpr int TB = T89_TB, A = V89_A, MW = 6;
     extern __shared__ uint8_t smem_raw[];
@@ -117,8 +122,6 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
     float* BIAS = reinterpret_cast<float*>(sm + T89_MISC); float* W0 = BIAS + 11 * 64; float* WH = W0 + 2 * 9 * 64; float* IN = WH + 64 * 4;     // IN [2][TB][49]
     float* PF = IN + 2 * TB * 49; float* VF = PF + TB * 50; float* VH = VF + TB * 28; float* LG = VH + TB * 64;
     for (int i = t; i < 11 * 64; i += T89_THREADS) BIAS[i] = __ldg(P + L.cbias[i >> 6] + (i & 63));
-    for (int i = t; i < 2 * 9 * 64; i += T89_THREADS) W0[i] = __ldg(P + L.conv[0] + i);
-    for (int i = t; i < 64; i += T89_THREADS) { WH[4 * i] = __ldg(P + L.pi_w + 2 * i); WH[4 * i + 1] = __ldg(P + L.pi_w + 2 * i + 1); WH[4 * i + 2] = __ldg(P + L.v_w + i); WH[4 * i + 3] = 0.f; }
     for (int i = t; i < 4 * T89_PLANE / 16; i += T89_THREADS) reinterpret_cast<uint4*>(ACT)[i] = make_uint4(0, 0, 0, 0);   // pad rows stay zero for good
     if (t == 0) { for (int i = 0; i < T89_NSLOT; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); } mbar_init(&bar_acc, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc<512>(&tmem_s);
@@ -161,26 +164,23 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
         }
         csync();
         {   // ---- first layer: Conv3x3(2 -> 64) + BN + ReLU on the CUDA cores; thread = row, 64 outputs in four 16-channel passes
-#pragma unroll 1
+            float vin[18];                                       // the 2 x 9 inputs of this row's cell (zero-padded planes)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int tp = 0; tp < 9; tp++) vin[c * 9 + tp] = cell ? IN[(c * TB + rl) * 49 + (ry + tp / 3) * 7 + rx + tp % 3] : 0.f;
+#pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 float y[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) y[j] = 0.f;
                 if (cell) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) y[j] = BIAS[c0 + j];
+                    for (int j = 0; j < 16; j++) y[j] = F0.b[c0 + j];
 #pragma unroll
-                    for (int c = 0; c < 2; c++)
+                    for (int k = 0; k < 18; k++)
 #pragma unroll
-                        for (int tp = 0; tp < 9; tp++) {
-                            const float v = IN[(c * TB + rl) * 49 + (ry + tp / 3) * 7 + rx + tp % 3];
-                            const float4* w4 = reinterpret_cast<const float4*>(W0 + (c * 9 + tp) * 64 + c0);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const float4 w = w4[j];
-                                y[4 * j] = fmaf(w.x, v, y[4 * j]); y[4 * j + 1] = fmaf(w.y, v, y[4 * j + 1]); y[4 * j + 2] = fmaf(w.z, v, y[4 * j + 2]); y[4 * j + 3] = fmaf(w.w, v, y[4 * j + 3]);
-                            }
-                        }
+                        for (int j = 0; j < 16; j++) y[j] = fmaf(F0.w[k * 64 + c0 + j], vin[k], y[j]);
 #pragma unroll
                     for (int j = 0; j < 16; j++) y[j] = fmaxf(y[j], 0.f);
                 }
@@ -257,15 +257,15 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
         // ---- heads: 1x1 convolutions (+BN, ReLU) to 2 + 1 planes from the trunk output (this thread's own residual row), flattened channel-major
         {
             float a0 = __ldg(P + L.pi_b), a1 = __ldg(P + L.pi_b + 1), a2 = __ldg(P + L.v_b);
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 float xr[16];
 #pragma unroll
                 for (int j = 0; j < 4; j++) { const float4 r4 = __ldcg(res + ((c0 >> 2) + j) * 256); xr[4 * j] = r4.x; xr[4 * j + 1] = r4.y; xr[4 * j + 2] = r4.z; xr[4 * j + 3] = r4.w; }
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    const float x = xr[j]; const float4 w = *reinterpret_cast<const float4*>(WH + 4 * (c0 + j));
-                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2);
+                    const float x = xr[j];
+                    a0 = fmaf(F0.wh[3 * (c0 + j)], x, a0); a1 = fmaf(F0.wh[3 * (c0 + j) + 1], x, a1); a2 = fmaf(F0.wh[3 * (c0 + j) + 2], x, a2);
                 }
             }
             if (cell) { const int pos = ry * 5 + rx; PF[rl * 50 + pos] = fmaxf(a0, 0.f); PF[rl * 50 + 25 + pos] = fmaxf(a1, 0.f); VF[rl * 28 + pos] = fmaxf(a2, 0.f); }
