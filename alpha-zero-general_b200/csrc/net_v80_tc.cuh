@@ -300,6 +300,24 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 }
             }
             __syncwarp();
+            {   // While the expand MMAs run (they only READ X, and every warp would just wait for them): the block input (the residual of the
+                // project epilogue, and for the policy block also the input of the value block) is parked in spare TMEM columns as fp32.
+                // Once the MMAs are done that frees X's 64 KB of shared memory for the SE partial sums and as E stages 2 and 3.
+                const int row = 32 * q + lane, c0 = 16 * sub;
+                uint32_t xv[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const int c = c0 + 4 * j4;
+                    float4 rh = make_float4(0.f, 0.f, 0.f, 0.f), rl = rh;
+                    if (c < NV) {
+                        const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
+                        rh = *reinterpret_cast<const float4*>(sm + TC_XH + o); rl = *reinterpret_cast<const float4*>(sm + TC_XL + o);
+                    }
+                    xv[4 * j4 + 0] = __float_as_uint(rh.x + rl.x); xv[4 * j4 + 1] = __float_as_uint(rh.y + rl.y);
+                    xv[4 * j4 + 2] = __float_as_uint(rh.z + rl.z); xv[4 * j4 + 3] = __float_as_uint(rh.w + rl.w);
+                }
+                tmem_st16(tlane + TC_T + c0, xv);
+            }
             ph.wait(bars, B_MMA); tc_fence_after();
             TC_STAMP();   /* b1: expand MMAs (channels 0-127) done */
             // ---------------- depthwise pass (thread = channel) ----------------
@@ -312,24 +330,6 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 TC_FSTAMP();   /* f: unit 1 done */
                 ph.wait(bars, B_MM2); tc_fence_after();
                 TC_FSTAMP();   /* f: MM2 wait done */
-                {   // X has been consumed by the expand MMAs. The block input (the residual of the project epilogue, and for the policy block
-                    // also the input of the value block) is parked in spare TMEM columns as fp32, which frees X's 64 KB of shared memory
-                    // as E stages 2 and 3 for the gated operand pass below.
-                    const int row = 32 * q + lane, c0 = 16 * sub;
-                    uint32_t xv[16];
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; j4++) {
-                        const int c = c0 + 4 * j4;
-                        float4 rh = make_float4(0.f, 0.f, 0.f, 0.f), rl = rh;
-                        if (c < NV) {
-                            const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
-                            rh = *reinterpret_cast<const float4*>(sm + TC_XH + o); rl = *reinterpret_cast<const float4*>(sm + TC_XL + o);
-                        }
-                        xv[4 * j4 + 0] = __float_as_uint(rh.x + rl.x); xv[4 * j4 + 1] = __float_as_uint(rh.y + rl.y);
-                        xv[4 * j4 + 2] = __float_as_uint(rh.z + rl.z); xv[4 * j4 + 3] = __float_as_uint(rh.w + rl.w);
-                    }
-                    tmem_st16(tlane + TC_T + c0, xv);
-                }
                 // The expand image is dead: SE weights and project chunks 2, 3 take its place. Issued from quarters 2 and 3, which have no
                 // second depthwise unit (a bulk-copy issue costs its thread a few hundred cycles).
                 if (t == TC_THREADS - 32) {

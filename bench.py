@@ -488,7 +488,10 @@ def main():
     # ---- whole-iteration leg: complete games -> drain -> gather (NCCL) -> symmetries --------------------------------------
     iteration = None
     if not args.no_iteration:
+        clocks2 = ClockSampler(local) if rank == 0 else None                     # this leg runs last, after ~1 minute of load: its own clocks line
         iteration = run_iteration(torch, dist, args, game, net, rank, world, dev, barrier, max_over_ranks, sum_over_ranks, gather_examples, shard_games)
+        if clocks2 is not None:
+            iteration['clocks'] = clocks2.stop()
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
