@@ -47,7 +47,7 @@ struct __align__(16) PathEnt { uint32_t node; uint32_t edge_np; uint32_t edge_of
 enum { NODE_EXPANDED = 0, NODE_TERMINAL = 1 };
 enum { LEAF_NONE = 0, LEAF_EXPAND = 1, LEAF_NEW_TERMINAL = 2, LEAF_OLD_TERMINAL = 3 };
 enum { ST_SIMS = 0, ST_VISITS, ST_EXPANSIONS, ST_NNEVALS, ST_TERMINAL, ST_OVERFLOW, ST_GC, ST_MAXNODES, ST_SUMLEGAL,
-       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_GC_SWEEP = 13, ST_SELLEGAL = 15, ST_ROOTLEGAL = 16, ST_REFLEGAL = 17, ST_N = 20 };
+       ST_MOVES, ST_EPISODES, ST_EXAMPLES, ST_GC_SWEEP = 13, ST_SELLEGAL = 15, ST_ROOTLEGAL = 16, ST_REFLEGAL = 17, ST_GC_TRIM = 19, ST_N = 20 };
 
 #ifndef AZG_SEL_PROF
 #define AZG_SEL_PROF 0
@@ -964,6 +964,31 @@ __device__ void gc_game(const Dev<G>& d, const int g, int8_t* sb /* warp-private
             }
             head += cnt;
             __syncwarp();
+        }
+        // ---- tier 3: even the tree the new root reaches leaves no room for this search (long principal variations accumulate
+        // thousands of reused nodes). Keep its first nodes in breadth-first order -- q[] is in that order: the nodes closest to the
+        // root -- up to what fits beside the coming search, drop the deeper ones. Their parents' links are cleared below, so a later
+        // visit re-expands them like any new state (the edge statistics of the kept nodes stay). Counted in ST_GC_TRIM.
+        {
+            const int budget_n = max(1, d.node_cap - need_nodes), budget_e = d.edge_cap - need_edges;
+            int keep_n = 0, acc_e = 0;
+            for (int base = 0; base < tail; base += 32) {
+                const int i = base + lane; int len = 0;
+                if (i < tail) { const NodeHdr h = nodes[q[i]]; len = h.kind == NODE_TERMINAL ? 1 : (int)h.n_legal; }
+                int pre = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
+                const bool ok = i < tail && i < budget_n && acc_e + pre <= budget_e;      // both conditions are prefix-monotone
+                const int cnt = __popc(__ballot_sync(FULL, ok));
+                keep_n = base + cnt; acc_e += __shfl_sync(FULL, pre, 31);
+                if (cnt < 32) break;
+            }
+            keep_n = max(keep_n, min(tail, 1));                  // the root itself always stays
+            if (keep_n < tail) {
+                for (int i = keep_n + lane; i < tail; i += 32) remap[q[i]] = 0;
+                if (lane == 0) d.stats[(size_t)g * ST_N + ST_GC_TRIM]++;
+                __syncwarp();
+            }
         }
     }
     int wn = 0, we = 0;                                          // write cursors

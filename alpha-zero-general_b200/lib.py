@@ -135,4 +135,4 @@ def game_info(game_id=AZG_GAME_SPLENDOR, num_players=2):
 
 STAT_NAMES = ['sims', 'node_visits', 'expansions', 'nn_evals', 'terminal_hits', 'arena_overflows', 'gc_runs', 'max_nodes',
               'sum_legal', 'moves_played', 'episodes_finished', 'examples_recorded', 'kernels_launched', 'gc_sweeps', 'node_cap',
-              'sum_legal_visited', 'sum_legal_root_scans', 'sum_legal_refreshed', 'examples_dropped', 'reserved19']
+              'sum_legal_visited', 'sum_legal_root_scans', 'sum_legal_refreshed', 'examples_dropped', 'gc_trims']

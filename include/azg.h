@@ -179,7 +179,8 @@ int azg_engine_selfplay_state(azg_engine* e, int8_t* boards, int32_t* players, i
  * [8] sum_legal (over expansions) [9] moves_played [10] episodes_finished [11] examples_recorded
  * [12] kernels_launched [13] gc_sweeps (tier-2 reachability GCs, see tree.cuh) [14] node_cap [15] sum_legal_visited (sum of n_legal over select steps)
  * [16] sum_legal_root_scans (edges scanned by k_select at the roots) [17] sum_legal_refreshed (edges scanned by k_backup when it
- * refreshes the cached PUCT choice of the nodes on the path) [18] examples_dropped (example ring full: must stay 0) [19] reserved.  out must hold AZG_N_STATS int64. */
+ * refreshes the cached PUCT choice of the nodes on the path) [18] examples_dropped (example ring full: must stay 0)
+ * [19] gc_trims (tier-3 GCs: the reused tree itself was too large for the arena and lost its deepest nodes; raise node_cap to avoid).  out must hold AZG_N_STATS int64. */
 int azg_engine_stats(azg_engine* e, int64_t* out_stats);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch of the search loop).
