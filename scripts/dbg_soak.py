@@ -11,6 +11,12 @@ n = int(os.environ.get('N', 16384)); sims = int(os.environ.get('SIMS', 800)); ep
 from azg_b200.game_switcher import import_game, DEFAULT_NN_VERSION
 gname = os.environ.get('GAME', 'splendor')
 Game, NNet, _ = import_game(gname); game = Game(); net = NNet(game, {'nn_version': DEFAULT_NN_VERSION[gname]})
+if os.environ.get('WEIGHTS') == 'shipped':                       # the reference's shipped checkpoint as recorded in the golden vectors
+    import numpy as np
+    tag = {'splendor': 'splendor_v80_shipped', 'santorini': 'santorini_v89_shipped', 'abalone': 'abalone_v21_shipped', 'azul': 'azul_v84_shipped'}[gname]
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', tag + '.npz'))
+    net.load_state_dict({k[4:]: z[k] for k in z.files if k.startswith('sd__')})
+    gname += ' (shipped weights)'
 a = dotdict(numMCTSSims=sims, cpuct=1.25, fpu=0.0, universes={'splendor': 3, 'azul': 2}.get(gname, 1), dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1], tempThreshold=10, prob_fullMCTS=1.0,
             ratio_fullMCTS=5, forced_playouts=False, no_mem_optim=False)
 dev = torch.device('cuda', 0)
