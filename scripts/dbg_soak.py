@@ -17,7 +17,7 @@ if os.environ.get('WEIGHTS') == 'shipped':                       # the reference
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', tag + '.npz'))
     net.load_state_dict({k[4:]: z[k] for k in z.files if k.startswith('sd__')})
     gname += ' (shipped weights)'
-a = dotdict(numMCTSSims=sims, cpuct=1.25, fpu=0.0, universes={'splendor': 3, 'azul': 2}.get(gname, 1), dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1], tempThreshold=10, prob_fullMCTS=1.0,
+a = dotdict(numMCTSSims=sims, cpuct=1.25, fpu=0.0, universes={'splendor': 3, 'azul': 2}.get(gname, 1), dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1], tempThreshold=10, prob_fullMCTS=float(os.environ.get('PROB', 1.0)),
             ratio_fullMCTS=5, forced_playouts=False, no_mem_optim=False)
 dev = torch.device('cuda', 0)
 eng = Engine(game, net, a, n_games=n, dirichlet_noise=True, seed=7, node_cap=int(os.environ.get('NODE_CAP', 0)))
@@ -29,6 +29,6 @@ while True:
     n_ex += len(eng.examples_device(dev)[0])
 torch.cuda.synchronize(); wall = time.perf_counter() - t0
 s1 = eng.stats(); d = {k: s1[k] - s0[k] for k in ('sims', 'moves_played', 'episodes_finished', 'examples_recorded', 'terminal_hits', 'gc_runs', 'gc_sweeps', 'arena_overflows', 'node_visits')}
-print(gname, 'whole games at %d sims: %.1f s, %.2f M sims/s, %d episodes, %d examples (%d drained), mean depth %.2f, moves per game %.1f' % (
+print(gname, 'prob_fullMCTS', a.prob_fullMCTS, 'whole games at %d sims: %.1f s, %.2f M sims/s, %d episodes, %d examples (%d drained), mean depth %.2f, moves per game %.1f' % (
     sims, wall, d['sims'] / wall / 1e6, d['episodes_finished'], d['examples_recorded'], n_ex, d['node_visits'] / max(d['sims'], 1), d['moves_played'] / max(d['episodes_finished'], 1)))
 print({k: d[k] for k in ('terminal_hits', 'gc_runs', 'gc_sweeps', 'arena_overflows')}, 'gc_trims', s1['gc_trims'] - s0['gc_trims'], 'examples_dropped', s1['examples_dropped'], 'max_nodes', s1.get('max_nodes'), 'node_cap', s1.get('node_cap'))
