@@ -4,7 +4,7 @@ tcgen05.commit, REDUX = warp reductions, RED = fire-and-forget atomics). Usage: 
 import collections, os, re, subprocess, sys
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'alpha-zero-general_b200', 'csrc', 'libazg_b200.so')
 out = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
-KEYS = ['UTCHMMA', 'UTCQMMA', 'UTCBAR', 'LDTM', 'STTM', 'UBLKCP', 'UTMALDG', 'SYNCS', 'REDUX', 'HMMA', 'DFMA', 'DADD', 'DMUL', 'FFMA', 'LDG', 'STG', 'LDS', 'STS', 'ATOMG', 'RED', 'BAR', 'SHFL', 'VOTE', 'MUFU']
+KEYS = ['UTCHMMA', 'UTCQMMA', 'UTCBAR', 'LDTM', 'STTM', 'UBLKCP', 'UTMALDG', 'SYNCS', 'REDUX', 'HMMA', 'DFMA', 'DADD', 'DMUL', 'FFMA', 'FFMA2', 'LDG', 'STG', 'LDS', 'STS', 'ATOMG', 'RED', 'BAR', 'SHFL', 'VOTE', 'MUFU']
 cur = None; hist = collections.OrderedDict()
 for line in out.splitlines():
     m = re.match(r'\s*Function : (\S+)', line)
