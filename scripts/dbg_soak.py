@@ -10,10 +10,11 @@ from azg_b200.utils import dotdict
 n = int(os.environ.get('N', 16384)); sims = int(os.environ.get('SIMS', 800)); eps = int(os.environ.get('EPISODES', n))
 from azg_b200.game_switcher import import_game, DEFAULT_NN_VERSION
 gname = os.environ.get('GAME', 'splendor')
-Game, NNet, _ = import_game(gname); game = Game(); net = NNet(game, {'nn_version': DEFAULT_NN_VERSION[gname]})
+npl = int(os.environ.get('NUM_PLAYERS', 0)) or None
+Game, NNet, _ = import_game(gname, npl); game = Game(); net = NNet(game, {'nn_version': DEFAULT_NN_VERSION[gname]})
 if os.environ.get('WEIGHTS') == 'shipped':                       # the reference's shipped checkpoint as recorded in the golden vectors
     import numpy as np
-    tag = {'splendor': 'splendor_v80_shipped', 'santorini': 'santorini_v89_shipped', 'abalone': 'abalone_v21_shipped', 'azul': 'azul_v84_shipped'}[gname]
+    tag = {'splendor': {None: 'splendor_v80_shipped', 2: 'splendor_v80_shipped', 3: 'splendor3p_v80_shipped', 4: 'splendor4p_v80_shipped'}[npl], 'santorini': 'santorini_v89_shipped', 'abalone': 'abalone_v21_shipped', 'azul': 'azul_v84_shipped'}[gname]
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', tag + '.npz'))
     net.load_state_dict({k[4:]: z[k] for k in z.files if k.startswith('sd__')})
     gname += ' (shipped weights)'
@@ -29,6 +30,6 @@ while True:
     n_ex += len(eng.examples_device(dev)[0])
 torch.cuda.synchronize(); wall = time.perf_counter() - t0
 s1 = eng.stats(); d = {k: s1[k] - s0[k] for k in ('sims', 'moves_played', 'episodes_finished', 'examples_recorded', 'terminal_hits', 'gc_runs', 'gc_sweeps', 'arena_overflows', 'node_visits')}
-print(gname, 'prob_fullMCTS', a.prob_fullMCTS, 'whole games at %d sims: %.1f s, %.2f M sims/s, %d episodes, %d examples (%d drained), mean depth %.2f, moves per game %.1f' % (
+print(gname, ('%d players' % npl) if npl else '', 'prob_fullMCTS', a.prob_fullMCTS, 'whole games at %d sims: %.1f s, %.2f M sims/s, %d episodes, %d examples (%d drained), mean depth %.2f, moves per game %.1f' % (
     sims, wall, d['sims'] / wall / 1e6, d['episodes_finished'], d['examples_recorded'], n_ex, d['node_visits'] / max(d['sims'], 1), d['moves_played'] / max(d['episodes_finished'], 1)))
 print({k: d[k] for k in ('terminal_hits', 'gc_runs', 'gc_sweeps', 'arena_overflows')}, 'gc_trims', s1['gc_trims'] - s0['gc_trims'], 'examples_dropped', s1['examples_dropped'], 'max_nodes', s1.get('max_nodes'), 'node_cap', s1.get('node_cap'))
