@@ -239,3 +239,24 @@ def test_ragged_schedule_plays_the_same_games_as_lock_step(monkeypatch):
     # lock-step: 20 lock-step simulations (select + net + backup launches) per ply of the slowest slot; ragged: ~11 (+ the turn kernel)
     rag_steps_per_move = (sr['kernels_launched'] / 4.0) / (sr['moves_played'] / n)
     assert rag_steps_per_move < 15.0, rag_steps_per_move
+
+
+@pytest.mark.parametrize('ragged', [False, True])
+def test_small_arena_is_trimmed_not_overflowed(ragged, monkeypatch):
+    """Tree GC under memory pressure (tree.cuh gc_game): an arena barely larger than one search forces the tier-2 sweep and the tier-3
+    trim (the reused tree keeps its breadth-first prefix) on almost every move. No expansion may be lost (arena_overflows = 0: every
+    search still stores its numMCTSSims new nodes), every recorded policy is a distribution over legal moves, and the games go on."""
+    if not ragged:
+        monkeypatch.setenv('AZG_RAGGED', '0')
+    game = azg_b200.SplendorGame(); net = HashNetWrapper(game)
+    sims = 120
+    args = dict(numMCTSSims=sims, cpuct=1.25, fpu=0.0, universes=2, dirichletAlpha=-1.0, temperature=[1.0, 0.1, 1.1], tempThreshold=10,
+                forced_playouts=False, prob_fullMCTS=0.5 if ragged else 1.0, ratio_fullMCTS=4, no_mem_optim=False)
+    eng = Engine(game, net, args, n_games=24, dirichlet_noise=True, seed=5, node_cap=sims + 40)
+    eng.selfplay(min_episodes=24)
+    st = eng.stats()
+    b, pi, z, va, q = eng.examples(24 * game.info.max_game_len)
+    eng.close()
+    assert st['arena_overflows'] == 0 and st['examples_dropped'] == 0 and st['episodes_finished'] >= 24
+    assert st['gc_sweeps'] > 0 and st['gc_trims'] > 0 and st['max_nodes'] <= st['node_cap'] == sims + 40
+    assert len(b) > 100 and np.allclose(pi.sum(axis=1), 1.0, atol=1e-5) and (pi[~va] == 0).all()
