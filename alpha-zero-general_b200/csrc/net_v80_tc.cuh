@@ -53,11 +53,12 @@ constexpr int TC_DE = 0;                  // expand accumulator: [0,128) channel
 constexpr int TC_DP = 256;                // first_layer / project accumulator: [256,320) hi-weight part, [320,384) lo-weight part
 constexpr int TC_T = 384;                 // the block input (fp32, [column][token]) is parked here while the E stages borrow X's shared memory
 
-struct V80TCImg { int w0; int we[3]; int wp[3]; int total; };   // float offsets into the image blob
+struct V80TCImg { int w0; int we[3]; int wp[3]; int be0; int total; };   // float offsets into the image blob (be0: expand bias of block 0 with first_layer folded in)
 inline V80TCImg v80tc_layout() {
     V80TCImg I; int o = 0;
     I.w0 = o; o += 32768 / 4;
     for (int b = 0; b < 3; b++) { I.we[b] = o; o += TC_WE_BYTES / 4; I.wp[b] = o; o += 6 * 16384 / 4; }
+    I.be0 = o; o += 176;
     I.total = o; return I;
 }
 inline float tc_rn_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; }
@@ -74,9 +75,20 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
     for (int b = 0; b < 3; b++) {
         const auto& B = L.blk[b];
         for (int c = 0; c < E; c++) for (int k = 0; k < NV; k++) {       // expand: M-side operand, rows = channels
-            const float w = blob[B.we + k * E + c], hi = tc_rn_tf32(w), lo = w - hi;
+            float w = blob[B.we + k * E + c];
+            if (b == 0) {   // first_layer (Linear + BN, no activation) is folded into the trunk block's expand: W' = We . W0 (accumulated in double);
+                double a = 0;   // the expand of block 0 then reads the raw board planes, which are exact in TF32 (no lo plane, two passes)
+                for (int j = 0; j < NV; j++) a += (double)blob[L.w0 + k * NV + j] * (double)blob[B.we + j * E + c];
+                w = (float)a;
+            }
+            const float hi = tc_rn_tf32(w), lo = w - hi;
             put(I.we[b], (size_t)(k >> 5) * TC_WE_ATOM + sw128_off(c, k & 31), hi);
             put(I.we[b], (size_t)(2 + (k >> 5)) * TC_WE_ATOM + sw128_off(c, k & 31), lo);
+        }
+        if (b == 0) for (int c = 0; c < E; c++) {                        // be' = be + We . b0
+            double a = blob[B.be + c];
+            for (int j = 0; j < NV; j++) a += (double)blob[L.b0 + j] * (double)blob[B.we + j * E + c];
+            img[I.be0 + c] = (float)a;
         }
         for (int o = 0; o < NV; o++) for (int c = 0; c < E; c++) {       // project: chunk = 32 input channels, rows o (hi) / 64 + o (lo)
             const float w = blob[B.wp + c * NV + o], hi = tc_rn_tf32(w), lo = w - hi;
@@ -87,7 +99,7 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
 
 namespace tc {
 using namespace umma;
-enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_PI3, B_V2, B_MM2, B_N };
+enum { B_W0 = 0, B_WE, B_FC, B_WP0, B_WP1, B_WP2, B_WP3, B_EF0, B_EF1, B_EF2, B_EF3, B_MMA, B_PI0, B_PI1, B_PI2, B_PI3, B_V2, B_MM2, B_FL, B_N };
 struct Phase {                            // per-thread parity of every barrier this thread waits on
     uint32_t bits = 0;
     __device__ __forceinline__ void wait(uint64_t* bars, int id) { mbar_wait(&bars[id], (bits >> id) & 1u); bits ^= 1u << id; }
@@ -178,7 +190,8 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         cp(SV_B0, L.b0, 56);
         for (int b = 0; b < 3; b++) {
             const int o = SV_BLK + b * SV_BLK_STRIDE; const V80Layout::Blk& B = L.blk[b];
-            cp(o + SV_BE, B.be, 168); cp(o + SV_SD, B.sd, 168); cp(o + SV_TD, B.td, 168); cp(o + SV_B1, B.b1, 40); cp(o + SV_B2, B.b2, 168); cp(o + SV_BP, B.bp, 56);
+            if (b == 0) { for (int i = t; i < 168; i += TC_THREADS) SV[o + SV_BE + i] = __ldg(IMG + I.be0 + i); } else cp(o + SV_BE, B.be, 168);
+            cp(o + SV_SD, B.sd, 168); cp(o + SV_TD, B.td, 168); cp(o + SV_B1, B.b1, 40); cp(o + SV_B2, B.b2, 168); cp(o + SV_BP, B.bp, 56);
         }
         cp(SV_BPI2, L.bpi2, 84); cp(SV_BPI4, L.bpi4, 84); cp(SV_BV2, L.bv2, 4); cp(SV_BV4, L.bv4, 4); cp(SV_V4, L.v4, 16);
     }
@@ -208,14 +221,13 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         TC_STAMP();   /* 0: tile start */
         const bool prefetched = tile != (int)blockIdx.x;          // the previous tile's value head already fetched this tile's boards (rb)
         if (t < TB) { const int j = tile0 + t; slot_of[t] = prefetched ? slot_next[t] : (j < count ? (list ? list[j] : j) : -1); }
-        if (t == 0) {
-            load(bars, B_W0, WRING, IMGb + I.w0, 32768);
-            load(bars, B_WP2, WRING + 32768, IMGb + I.wp[0], 16384);                 // project chunk 0 -> slot 2
-            load(bars, B_WP3, WRING + 49152, IMGb + I.wp[0] + 4096, 16384);          // project chunk 1 -> slot 3
+        if (t == 0) {                                             // first-layer image -> weight slots 2, 3; the trunk block's expand image -> ESTG .. WRING[0, 24 KB)
+            load(bars, B_W0, WRING + 32768, IMGb + I.w0, 32768);
+            load(bars, B_WE, ESTG, IMGb + I.we[0], TC_WE_BYTES);
         }
         if (!prefetched) __syncthreads();
-        {   // raw boards -> ESTG (16 x 400 B), 32-bit loads (board rows are 392 B, slots are 4-byte aligned)
-            uint32_t* raw = reinterpret_cast<uint32_t*>(ESTG);
+        {   // raw boards -> the SE scratch (16 x 400 B; ESTG is receiving the expand image), 32-bit loads (board rows are 392 B, slots are 4-byte aligned)
+            uint32_t* raw = reinterpret_cast<uint32_t*>(sm + TC_SQ);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int k = t + i * TC_THREADS;
@@ -228,7 +240,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         }
         __syncthreads();
         {   // XH[column][token] = (float)board[leaf][token][f]  (small integers: exact in TF32, no lo plane needed)
-            const int8_t* raw = reinterpret_cast<const int8_t*>(ESTG);
+            const int8_t* raw = reinterpret_cast<const int8_t*>(sm + TC_SQ);
             for (int k = t; k < 128 * 14; k += TC_THREADS) {
                 const int row = k & 127, kq = k >> 7, s = row >> 3, f = row & 7;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -238,40 +250,20 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
         }
         fence_async_smem(); __syncthreads();
         TC_STAMP();   /* 1: input staged */
-        // ---------------- first_layer: D[column][channel] = X . W0^T, hi|lo weight rows stacked along N ----------------
-        if (t == 0) {
+        // ---------------- first_layer: D[column][channel] = X . W0^T, hi|lo weight rows stacked along N. Its output T is only needed as the
+        // residual of the trunk block (first_layer has no activation, so the block's expand reads the raw planes through the folded
+        // weights We . W0): the MMAs are queued here, the expand MMAs of block 0 right behind them, and T goes from the accumulator
+        // straight to its parking columns in TMEM while the expand MMAs run. ----------------
+        if (t == TC_THREADS - 32) {
             ph.wait(bars, B_W0); tc_fence_after();
 #pragma unroll 1
             for (int ks = 0; ks < 7; ks++) {
                 const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-                mma_tf32(tm + TC_DP, desc_sw128(xh_a + off), desc_sw128(wring_a + off), ID128, ks > 0);
+                mma_tf32(tm + TC_DP, desc_sw128(xh_a + off), desc_sw128(wring_a + 32768 + off), ID128, ks > 0);
             }
-            mma_commit(&bars[B_MMA]);
+            mma_commit(&bars[B_FL]);
         }
         __syncwarp();
-        ph.wait(bars, B_MMA); tc_fence_after();
-        TC_STAMP();   /* 2: first MMA done */
-        if (t == 0) load(bars, B_WE, ESTG, IMGb + I.we[0], TC_WE_BYTES);
-        __syncwarp();
-        {   // epilogue: bias, split, write the trunk input operand in place
-            const int row = 32 * q + lane, c0 = 16 * sub;
-            uint32_t dh[16], dl[16];
-            tmem_ld16(tlane + TC_DP + c0, dh); tmem_ld16(tlane + TC_DP + 64 + c0, dl); tmem_wait_ld();
-#pragma unroll
-            for (int j4 = 0; j4 < 4; j4++) {
-                const int c = c0 + 4 * j4;
-                if (c < NV) {
-                    float hi[4], lo[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) split_rn(__uint_as_float(dh[4 * j4 + j]) + __uint_as_float(dl[4 * j4 + j]) + SV[SV_B0 + c + j], hi[j], lo[j]);
-                    const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
-                    *reinterpret_cast<float4*>(sm + TC_XH + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(sm + TC_XL + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                }
-            }
-        }
-        fence_async_smem(); tc_fence_before(); __syncthreads();
-        TC_STAMP();   /* 3: first epilogue done */
 
 #pragma unroll 1
         for (int b = 0; b < 3; b++) {
@@ -289,6 +281,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 for (int mh = 0; mh < 2; mh++) {
 #pragma unroll 1
                     for (int p = 0; p < 3; p++) {
+                        if (b == 0 && p == 1) continue;               // the raw planes have no lo part
                         const uint32_t wa = estg_a + (p == 0 ? 2 * TC_WE_ATOM : 0) + mh * 16384;      // pass 0: W_lo X_hi, 1: W_hi X_lo, 2: W_hi X_hi
                         const uint32_t xa = p == 1 ? xl_a : xh_a;
 #pragma unroll 1
@@ -300,7 +293,20 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 }
             }
             __syncwarp();
-            {   // While the expand MMAs run (they only READ X, and every warp would just wait for them): the block input (the residual of the
+            if (b == 0) {   // trunk block: its residual T = first_layer(x) comes out of the first-layer accumulator (bias added) into the parking columns
+                const int c0 = 16 * sub;
+                ph.wait(bars, B_FL); tc_fence_after();
+                if (t == 0) {                                     // the first-layer image is consumed: project chunks 0, 1 -> slots 2, 3
+                    load(bars, B_WP2, WRING + 32768, IMGb + I.wp[0], 16384);
+                    load(bars, B_WP3, WRING + 49152, IMGb + I.wp[0] + 4096, 16384);
+                }
+                __syncwarp();
+                uint32_t dh[16], dl[16], xv[16];
+                tmem_ld16(tlane + TC_DP + c0, dh); tmem_ld16(tlane + TC_DP + 64 + c0, dl); tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; j++) xv[j] = __float_as_uint(__uint_as_float(dh[j]) + __uint_as_float(dl[j]) + (c0 + j < NV ? SV[SV_B0 + c0 + j] : 0.f));
+                tmem_st16(tlane + TC_T + c0, xv);
+            } else {   // While the expand MMAs run (they only READ X, and every warp would just wait for them): the block input (the residual of the
                 // project epilogue, and for the policy block also the input of the value block) is parked in spare TMEM columns as fp32.
                 // Once the MMAs are done that frees X's 64 KB of shared memory for the SE partial sums and as E stages 2 and 3.
                 const int row = 32 * q + lane, c0 = 16 * sub;

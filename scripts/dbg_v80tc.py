@@ -32,7 +32,7 @@ out = (C.c_longlong * 64)()
 L = net.net._L; L.azg_net_prof.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
 print('prof rc', L.azg_net_prof(net.net.h, out))
 ts = np.array(list(out), dtype=np.int64); ts = ts[ts != 0]
-names = ['tile start', 'input staged', 'first MMA done', 'first epilogue']
+names = ['tile start', 'input staged']                           # first_layer is folded into the trunk block (no phase of its own)
 for b_ in range(3):
     names += [f'b{b_} expand MMA (ch 0-127) done', f'b{b_} depthwise', f'b{b_} fc landed', f'b{b_} SE done', f'b{b_} project MMA done', f'b{b_} project epilogue']
     if b_ == 1: names += ['policy head done']
@@ -45,7 +45,7 @@ print('tile total', ts[min(len(ts), len(names)) - 1] - ts[0], 'cycles;  stamps',
 n1 = len(names)
 if len(ts) >= 2 * n1:
     d2 = np.diff(ts[n1:2 * n1])
-    print('second tile of CTA 0: ' + ', '.join('%s +%d' % (names[i + 1], d2[i]) for i in range(min(3, len(d2)))) + '; total %d cycles' % (ts[2 * n1 - 1] - ts[n1]))
+    print('second tile of CTA 0: ' + ', '.join('%s +%d' % (names[i + 1], d2[i]) for i in range(min(2, len(d2)))) + '; total %d cycles' % (ts[2 * n1 - 1] - ts[n1]))
 
 # ---- per-CTA timeline of the last launch (globaltimer ns): entry, prologue done, exit, SM id ----
 out2 = (C.c_longlong * 640)()
