@@ -70,6 +70,21 @@ inline void tokmix_prepare(const float* src, const TokMixLayout& L, float* dst) 
     for (int k = 0; k < 3; k++) {
         const TokMixBlk& B = L.blk[k];
         { const float* W = take((size_t)B.E * B.in); fold(W, B.E, B.in, B.we, B.be); }
+        if (k == 0) {   // first_layer (Linear + BN, no activation) folded into this expand: W'[i][c] = sum_j W0[i][j] We[j][c], b' = be + sum_j b0[j] We[j][c]
+            std::vector<double> w2((size_t)L.nv * B.E), b2(B.E);
+            for (int c = 0; c < B.E; c++) {
+                double a = dst[B.be + c];
+                for (int j = 0; j < L.nv; j++) a += (double)dst[L.b0 + j] * (double)dst[B.we + j * B.E + c];
+                b2[c] = a;
+                for (int i = 0; i < L.nv; i++) {
+                    double m = 0;
+                    for (int j = 0; j < L.nv; j++) m += (double)dst[L.w0 + i * L.nv + j] * (double)dst[B.we + j * B.E + c];
+                    w2[(size_t)i * B.E + c] = m;
+                }
+            }
+            for (int c = 0; c < B.E; c++) dst[B.be + c] = (float)b2[c];
+            for (size_t i = 0; i < w2.size(); i++) dst[B.we + i] = (float)w2[i];
+        }
         { const float* W = take(F * F); for (int i = 0; i < F * F; i++) dst[B.dw + i] = W[i];
           const float* g = take(B.E); const float* b = take(B.E); const float* m = take(B.E); const float* v = take(B.E);
           for (int c = 0; c < B.E; c++) { const float s = g[c] / sqrtf(v[c] + 1e-5f); dst[B.sd + c] = s; dst[B.td + c] = b[c] - m[c] * s; } }
@@ -203,12 +218,14 @@ k_tokmix_forward(const float* __restrict__ P, const __grid_constant__ TokMixLayo
         X[i * TM_TB + l] = slot >= 0 ? (float)boards[(size_t)slot * bstride + i] : 0.f;
     }
     __syncthreads();
-    token_linear<F>(P + L.w0, P + L.b0, NV, NV, X, T, 0, nullptr, t);
-    __syncthreads();
+    token_linear<F>(P + L.w0, P + L.b0, NV, NV, X, T, 0, nullptr, t);   // T = first_layer(x): only the residual of the trunk block needs it.
+    // No barrier: first_layer has no activation and is folded into the trunk block's expand weights on the host (tokmix_prepare), so
+    // that expand reads the raw planes X as well and runs in the same phase.
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
         const TokMixBlk& B = L.blk[k];
-        const float* IN = k == 0 ? T : X;                         // heads read the trunk output (kept in X after block 0)
+        const float* IN = X;                                      // trunk block: the raw planes (folded first_layer); heads: the trunk output (kept in X after block 0)
+        const float* RES = k == 0 ? T : X;
         float* OUT = k == 0 ? X : H;
         token_linear<F>(P + B.we, P + B.be, B.E, B.in, IN, E, B.act, nullptr, t);
         __syncthreads();
@@ -249,7 +266,7 @@ k_tokmix_forward(const float* __restrict__ P, const __grid_constant__ TokMixLayo
         __syncthreads();
         for (int idx = t; idx < B.E * F * TM_TB; idx += TM_THREADS) D[idx] *= SQ[((idx >> 3) / F) * TM_TB + (idx & 7)];   // gate
         __syncthreads();
-        token_linear<F>(P + B.wp, P + B.bp, B.out, B.E, D, OUT, 0, B.res ? IN : nullptr, t);
+        token_linear<F>(P + B.wp, P + B.bp, B.out, B.E, D, OUT, 0, B.res ? RES : nullptr, t);
         __syncthreads();
         if (k == 1) {   // ---- policy head: Linear(out*F -> A) + ReLU, Linear(A -> A), masked log_softmax -> exp
             dense_partial(P + L.pi2, A, B.out * F, SM::PKS, H, PPART, t);
