@@ -204,7 +204,7 @@ class HostLoop:
         self.board = pin((n, S_BYTES), torch.int8); self.board2 = pin((n, S_BYTES), torch.int8); self.roots = pin((n, S_BYTES), torch.int8)
         self.player = pin((n,), torch.int32); self.player2 = pin((n,), torch.int32); self.action = pin((n,), torch.int32)
         self.seeds = pin((n,), torch.int64); self.keys = pin((n,), torch.int64).view(np.uint64); self.ended = pin((n, N_PL), torch.float32)
-        self.counts = pin((n, N_ACT), torch.int32); self.raw = pin((n, N_ACT), torch.int32); self.q = pin((n, N_PL), torch.float32)
+        self.counts = pin((n, N_ACT), torch.int32); self.q = pin((n, N_PL), torch.float32)
         self.rng = np.random.default_rng(seed); self.key_ctr = 1 << 20
         self.board[:] = game.init_batch(np.arange(1, n + 1, dtype=np.uint64) + (seed << 32)).reshape(n, S_BYTES)
         self.player[:] = 0; self.seeds[:] = 0
@@ -215,8 +215,8 @@ class HostLoop:
         lib, L, g, n = self.lib, self.L, self.game, self.n
         p = lib.ptr; N_ACT = self.N_ACT
         # MCTS.getActionProb for every game (host roots in, host counts out)
-        lib.check(L.azg_engine_search(self.eng.h, n, p(self.roots), None, None, p(self.counts), p(self.raw), p(self.q), None))
-        self.h2d += self.roots.nbytes; self.d2h += self.counts.nbytes + self.raw.nbytes + self.q.nbytes
+        lib.check(L.azg_engine_search(self.eng.h, n, p(self.roots), None, None, p(self.counts), None, p(self.q), None))   # getActionProb returns probs and q; the un-pruned counts are not asked for
+        self.h2d += self.roots.nbytes; self.d2h += self.counts.nbytes + self.q.nbytes
         # Coach.py:63 random_pick with temp_for_selfplay ~ 1 (early plies): sample from the visit counts
         if N_ACT <= 512:
             c = self.counts.astype(np.float64); cs = np.cumsum(c, axis=1); u = self.rng.random(n) * cs[:, -1]
