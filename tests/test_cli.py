@@ -116,3 +116,15 @@ def test_main_runs_one_iteration_on_the_engine(tmp_path):
     assert load_checkpoint_file(os.path.join(tmp_path, 'temp.pt'))['numMCTSSims'] == 12
     one, two, draws = P.main(['splendor', os.path.join(tmp_path, 'temp.pt'), 'random', '-n', '8', '-m', '12'])
     assert one + two + draws == 8
+
+
+def test_learn_resumes_from_loaded_examples(tmp_path):
+    """Coach.py:160 with skipFirstSelfPlay (set by loadTrainExamples, Coach.py:262): the first iteration after a resume trains on the
+    loaded history without playing; self-play starts again with the second iteration."""
+    c = _stub_coach(tmp_path, [(20, 0, 0), (20, 0, 0)])
+    played = []
+    ex = c.executeEpisodes()
+    c.executeEpisodes = lambda: (played.append(1), ex)[1]
+    c.trainExamplesHistory = [list(ex), list(ex)]; c.skipFirstSelfPlay = True
+    rec = c.learn(log=lambda *a: None)
+    assert len(played) == 1 and [r['examples'] for r in rec] == [4, 4]          # iteration 1: the two loaded iterations; iteration 2: history capped at 2
