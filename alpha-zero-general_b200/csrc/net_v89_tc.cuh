@@ -31,6 +31,7 @@
 #include "net_v89.cuh"
 #include "net_v80_tc.cuh"   // tc_rn_tf32
 #include "umma.cuh"
+#include <cuda_fp16.h>
 
 namespace azg {
 
@@ -40,9 +41,11 @@ constexpr int T89_TB = 7;                 // leaves per tile
 constexpr int T89_ROW0 = 14;              // first output row (leaf 0, cell (0, 0)); taps reach 7 rows either side
 constexpr int T89_ROWS = 280;             // rows of an activation plane (35 groups of 8)
 constexpr int T89_PLANE = T89_ROWS * 128; // bytes of one (plane, K atom)
-constexpr int T89_ACT = 0;                // [H atom0 | H atom1 | L atom0 | L atom1]
-constexpr int T89_WRING = 4 * T89_PLANE;  // 143360: two slots x 32 KB; one unit = one tap: [K atom][128 rows: W_hi 0-63, W_lo 64-127][128 B]
-constexpr int T89_UNIT_BYTES = 32768;     // (four 16 KB slots, one per (tap, K atom), were measured too: 25.1 k cycles per convolution instead of 21.8 k)
+constexpr int T89_ACT = 0;                // [H atom0 | H atom1 | L (fp16: 64 channels = one 128-byte atom)]
+constexpr int T89_WRING = 3 * T89_PLANE;  // 107520: two slots x 40 KB; one unit = one tap: [K atom][128 rows: W_hi 0-63, W_lo 64-127][128 B] tf32, then [64 rows][128 B] W as fp16
+constexpr int T89_UNIT_TF32 = 32768;      // (four 16 KB slots, one per (tap, K atom), were measured too: 25.1 k cycles per convolution instead of 21.8 k)
+constexpr int T89_UNIT_BYTES = T89_UNIT_TF32 + 8192;
+constexpr int T89_UNIT_FLOATS = T89_UNIT_BYTES / 4;
 constexpr int T89_NSLOT = 2;
 constexpr int T89_MISC = T89_WRING + T89_NSLOT * T89_UNIT_BYTES;   // biases [11][64], conv0 weights [2][9][64], head 1x1 weights [64][4], input planes, head scratch
 constexpr int T89_MISC_FLOATS = 11 * 64 + 2 * 9 * 64 + 64 * 4 + 2 * T89_TB * 49 + T89_TB * (50 + 28 + 64 + V89_AP);
@@ -50,8 +53,22 @@ constexpr int T89_SMEM = T89_MISC + T89_MISC_FLOATS * 4 + 1024;
 constexpr int T89_ACC = 0;                // TMEM columns: M tile m, tap group a (taps 0-4 / 5-8): [(2m + a) * 128, +128) = [H W_hi | H W_lo + L W_hi]
 constexpr int T89_RES_FLOATS = 256 * 64;  // per-CTA residual scratch in global memory: [channel quad 0..15][row - 14][4] (a warp's 32 rows of one quad = 512 contiguous bytes)
 
-struct V89TCImg { int conv[10]; int total; };                     // float offsets of the per-conv images (9 taps x 8192 floats)
-inline V89TCImg v89tc_layout() { V89TCImg I; int o = 0; for (int i = 0; i < 10; i++) { I.conv[i] = o; o += 9 * 8192; } I.total = o; return I; }
+struct V89TCImg { int conv[10]; int total; };                     // float offsets of the per-conv images (9 taps x T89_UNIT_FLOATS)
+inline V89TCImg v89tc_layout() { V89TCImg I; int o = 0; for (int i = 0; i < 10; i++) { I.conv[i] = o; o += 9 * T89_UNIT_FLOATS; } I.total = o; return I; }
+inline uint16_t v89_f32_to_f16(float x) {                          // round to nearest even, host side (weights are far inside the fp16 range)
+    uint32_t u; memcpy(&u, &x, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u; const int e = (int)((u >> 23) & 0xFF) - 127 + 15; uint32_t m = u & 0x7FFFFFu;
+    if (e >= 31) return (uint16_t)(sign | 0x7BFFu);                // clamp (not reached)
+    if (e <= 0) {                                                  // subnormal or zero
+        if (e < -10) return (uint16_t)sign;
+        m |= 0x800000u; const int sh = 14 - e; uint32_t r = m >> sh; const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+        if (rem > half || (rem == half && (r & 1u))) r++;
+        return (uint16_t)(sign | r);
+    }
+    uint32_t r = ((uint32_t)e << 10) | (m >> 13); const uint32_t rem = m & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) r++;
+    return (uint16_t)(sign | r);
+}
 // Host: operand images of trunk conv i (1..10 of the prepared blob: [cin][tap][cout], BN folded) -> [tap][atom][row][k] swizzled
 inline void v89tc_prepare(const float* blob, const V89Layout& L, const V89TCImg& I, float* img) {
     using umma::sw128_off;
@@ -59,8 +76,11 @@ inline void v89tc_prepare(const float* blob, const V89Layout& L, const V89TCImg&
     for (int ci = 1; ci < V89_NCONV; ci++)
         for (int c = 0; c < 64; c++) for (int t = 0; t < 9; t++) for (int o = 0; o < 64; o++) {
             const float w = blob[L.conv[ci] + (c * 9 + t) * 64 + o], hi = tc_rn_tf32(w), lo = w - hi;
-            const size_t base = (size_t)I.conv[ci - 1] + (size_t)t * 8192 + (size_t)(c >> 5) * 4096;
+            const size_t unit = (size_t)I.conv[ci - 1] + (size_t)t * T89_UNIT_FLOATS, base = unit + (size_t)(c >> 5) * 4096;
             img[base + sw128_off(o, c & 31) / 4] = hi; img[base + sw128_off(64 + o, c & 31) / 4] = lo;
+            // fp16 copy of w for the L . W term: B operand [cout row][cin], one 128-byte atom, same 16-byte-chunk swizzle
+            uint16_t* h16 = reinterpret_cast<uint16_t*>(img + unit + T89_UNIT_TF32 / 4);
+            h16[((o >> 3) * 1024 + (o & 7) * 128 + ((((c >> 3) ^ (o & 7)) & 7) << 4) + (c & 7) * 2) / 2] = v89_f32_to_f16(w);
         }
 }
 
@@ -82,9 +102,11 @@ __device__ __forceinline__ bool row_cell(int row, int& l, int& y, int& x) {
     const int r = row - T89_ROW0; l = r / 36; const int rem = r - 36 * l; y = rem / 6; x = rem - 6 * y;
     return r >= 0 && l < T89_TB && y < 5 && x < 5;
 }
-// y[16] (channels c0..c0+15 of one row) -> the two operand planes: H = y, L = y - trunc_tf32(y)
+// y[16] (channels c0..c0+15 of one row) -> the operand planes: H = y (fp32; the tensor core truncates it to TF32) and
+// L = y - trunc_tf32(y) as FP16 (|L| < 2^-10 |y|: its 11-bit mantissa keeps the product L . W to 2^-21 of y . w)
 __device__ __forceinline__ void store_row16(uint8_t* act, int row, int c0, const float (&y)[16]) {
     uint8_t* base = act + (c0 >> 5) * T89_PLANE;
+    uint32_t lp[8];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const uint32_t o = sw128_off(row, (c0 & 31) + 4 * j);
@@ -92,8 +114,13 @@ __device__ __forceinline__ void store_row16(uint8_t* act, int row, int c0, const
 #pragma unroll
         for (int i = 0; i < 4; i++) lo[i] = __fsub_rn(y[4 * j + i], __uint_as_float(__float_as_uint(y[4 * j + i]) & 0xFFFFE000u));
         *reinterpret_cast<float4*>(base + o) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        *reinterpret_cast<float4*>(base + 2 * T89_PLANE + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        const __half2 a = __floats2half2_rn(lo[0], lo[1]), b = __floats2half2_rn(lo[2], lo[3]);
+        lp[2 * j] = *reinterpret_cast<const uint32_t*>(&a); lp[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&b);
     }
+    uint8_t* lrow = act + 2 * T89_PLANE + (row >> 3) * 1024 + (row & 7) * 128;        // 16 channels = two 16-byte chunks of the row's 128 bytes
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        *reinterpret_cast<uint4*>(lrow + ((((c0 >> 3) + h) ^ (row & 7)) << 4)) = make_uint4(lp[4 * h], lp[4 * h + 1], lp[4 * h + 2], lp[4 * h + 3]);
 }
 }  // namespace t89
 
@@ -122,7 +149,7 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
     float* BIAS = reinterpret_cast<float*>(sm + T89_MISC); float* W0 = BIAS + 11 * 64; float* WH = W0 + 2 * 9 * 64; float* IN = WH + 64 * 4;     // IN [2][TB][49]
     float* PF = IN + 2 * TB * 49; float* VF = PF + TB * 50; float* VH = VF + TB * 28; float* LG = VH + TB * 64;
     for (int i = t; i < 11 * 64; i += T89_THREADS) BIAS[i] = __ldg(P + L.cbias[i >> 6] + (i & 63));
-    for (int i = t; i < 4 * T89_PLANE / 16; i += T89_THREADS) reinterpret_cast<uint4*>(ACT)[i] = make_uint4(0, 0, 0, 0);   // pad rows stay zero for good
+    for (int i = t; i < 3 * T89_PLANE / 16; i += T89_THREADS) reinterpret_cast<uint4*>(ACT)[i] = make_uint4(0, 0, 0, 0);   // pad rows stay zero for good
     if (t == 0) { for (int i = 0; i < T89_NSLOT; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); } mbar_init(&bar_acc, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc<512>(&tmem_s);
     fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -133,7 +160,7 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
     float4* res = reinterpret_cast<float4*>(RES + (size_t)blockIdx.x * T89_RES_FLOATS) + (128 * mt + 32 * q + lane);   // its residual row: quad c4 at res[c4 * 256]
     int rl, ry, rx; const bool cell = row_cell(row, rl, ry, rx);
     const uint32_t act_a = smem_u32(ACT), wr_a = smem_u32(WR);
-    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
+    constexpr uint32_t ID128 = idesc_tf32(128, 128), IDH64 = idesc_f16(128, 64);
     uint32_t g_mma = 0, g_load = 0, n_acc = 0;                    // global tap counters of the issuer / the producer, accumulator phases
     int prof_i = 0; long long wait_cyc = 0;
 #define T89_STAMP() do { if (prof && t == 0 && blockIdx.x == 0 && prof_i < 60) prof[prof_i++] = clock64(); } while (0)
@@ -147,7 +174,7 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
                     const uint32_t s = g_load % T89_NSLOT, use = g_load / T89_NSLOT;
                     if (use >= 1) mbar_wait(&bar_empty[s], (use & 1u) ^ 1u);
                     mbar_expect_tx(&bar_full[s], T89_UNIT_BYTES);
-                    bulk_g2s(WR + s * T89_UNIT_BYTES, IMG + (size_t)k * 8192, T89_UNIT_BYTES, &bar_full[s]);
+                    bulk_g2s(WR + s * T89_UNIT_BYTES, IMG + (size_t)k * T89_UNIT_FLOATS, T89_UNIT_BYTES, &bar_full[s]);
                 }
         }
         __syncwarp();
@@ -211,10 +238,11 @@ k_v89_tc(const float* __restrict__ P, const float* __restrict__ IMG, float* __re
 #pragma unroll
                         for (int ks = 0; ks < 8; ks++) {
                             const uint32_t ao = (ks >> 2) * T89_PLANE + (ks & 3) * 32;
-                            const uint64_t dw = desc_sw128(wb + (ks >> 2) * 16384 + (ks & 3) * 32);
-                            mma_tf32(dcol, desc_sw128(arow + ao), dw, ID128, accum || ks != 0);                              // H . (W_hi | W_lo)
-                            mma_tf32(dcol + 64, desc_sw128(arow + 2 * T89_PLANE + ao), dw, ID64, true);                      // L . W_hi, next to H . W_lo
+                            mma_tf32(dcol, desc_sw128(arow + ao), desc_sw128(wb + (ks >> 2) * 16384 + (ks & 3) * 32), ID128, accum || ks != 0);   // H . (W_hi | W_lo)
                         }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++)                                                                       // L . W in FP16, K = 16 per MMA, next to H . W_lo
+                            mma_f16(dcol + 64, desc_sw128(arow + 2 * T89_PLANE + ks * 32), desc_sw128(wb + T89_UNIT_TF32 + ks * 32), IDH64, true);
                     }
                     mma_commit(&bar_empty[s]);                     // slot free once these MMAs have read it
                 }
