@@ -22,6 +22,7 @@
 #pragma once
 #include "net_v80.cuh"
 #include "umma.cuh"
+#include <cuda_bf16.h>
 
 namespace azg {
 
@@ -34,7 +35,7 @@ constexpr int TC_THREADS = 512;           // 16 warps: TMEM lane quarter = warp 
 constexpr int TC_TB = 16;                 // leaves per tile (128 columns)
 // ---- shared memory map (bytes from a 1024-aligned base) ----
 constexpr int TC_XH = 0;                  // activations hi: [2 K atoms][128 columns][128 B]
-constexpr int TC_XL = 32768;              // activations lo
+constexpr int TC_XL = 32768;              // the small 3xTF32 terms of the expand run in BF16: [X as bf16: 128 columns x 128 B][X_lo = x - rn_tf32(x) as bf16], 16 KB each
 constexpr int TC_ESTG = 65536;            // 2 stages x (EH 16 KB | EL 16 KB); also raw boards, SE fc weights, head activations
 constexpr int TC_WRING = 131072;          // 64 KB: project weight slots 4 x 16 KB, first-layer image, policy/value weight ring
 constexpr int TC_SQ = 196608;             // SE pooled values [leaf quad][169 (padded)][4] floats: consecutive channels 16 B apart (the depthwise threads store without
@@ -45,7 +46,7 @@ constexpr int TC_SV = TC_VH + 8 * 16 * 4;        // small vectors (biases, BN sc
 constexpr int SV_B0 = 0, SV_BLK = 64, SV_BLK_STRIDE = 800, SV_BE = 0, SV_SD = 168, SV_TD = 336, SV_B1 = 504, SV_B2 = 552, SV_BP = 720;
 constexpr int SV_BPI2 = 2464, SV_BPI4 = 2560, SV_BV2 = 2656, SV_BV4 = 2660, SV_V4 = 2664, SV_FLOATS = 2680;
 constexpr int TC_SMEM = TC_SV + SV_FLOATS * 4 + 1024;   // + alignment slack
-constexpr int TC_WE_BYTES = 2 * 2 * 176 * 128;       // expand image: hi (2 atoms x 176 rows x 128 B) then lo = 90112 B (spans ESTG + WRING[0,24576))
+constexpr int TC_WE_BYTES = 2 * 2 * 176 * 128;       // expand image: W_hi tf32 (2 atoms x 176 rows x 128 B), then W as bf16 and W_lo as bf16 (one atom each) = 90112 B (spans ESTG + WRING[0,24576))
 constexpr int TC_WE_ATOM = 176 * 128;
 constexpr int TC_PIRING_SLOT = 18816;     // 56 rows of the [392][84] policy matrix
 // ---- TMEM columns ----
@@ -83,7 +84,9 @@ inline void v80tc_prepare(const float* blob, const V80Layout& L, const V80TCImg&
             }
             const float hi = tc_rn_tf32(w), lo = w - hi;
             put(I.we[b], (size_t)(k >> 5) * TC_WE_ATOM + sw128_off(c, k & 31), hi);
-            put(I.we[b], (size_t)(2 + (k >> 5)) * TC_WE_ATOM + sw128_off(c, k & 31), lo);
+            uint16_t* h16 = reinterpret_cast<uint16_t*>(img + I.we[b]);  // atoms 2, 3: W and W_lo as bf16 (K = 64 tokens = one atom) for the small terms (bf16: W_lo ~ 2^-12 |w| would be subnormal in fp16)
+            h16[((size_t)2 * TC_WE_ATOM + umma::sw128_off_h(c, k)) / 2] = umma::f32_to_bf16_host(w);
+            h16[((size_t)3 * TC_WE_ATOM + umma::sw128_off_h(c, k)) / 2] = umma::f32_to_bf16_host(lo);
         }
         if (b == 0) for (int c = 0; c < E; c++) {                        // be' = be + We . b0
             double a = blob[B.be + c];
@@ -213,7 +216,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #define TC_FSTAMP() do { } while (0)
 #endif
     const uint32_t xh_a = smem_u32(sm + TC_XH), xl_a = smem_u32(sm + TC_XL), estg_a = smem_u32(ESTG), wring_a = smem_u32(WRING);
-    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64);
+    constexpr uint32_t ID128 = idesc_tf32(128, 128), ID64 = idesc_tf32(128, 64), IDH128 = idesc_bf16(128, 128);
     const float* IMGb = IMG;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -246,7 +249,12 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (f < 7) { const int8_t* b = raw + s * 400 + (4 * kq) * 7 + f; v = make_float4((float)b[0], (float)b[7], (float)b[14], (float)b[21]); }
                 *reinterpret_cast<float4*>(sm + TC_XH + (kq >> 3) * 16384 + sw128_off(row, (4 * kq) & 31)) = v;
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);       // the same planes as bf16 (small integers: exact)
+                *reinterpret_cast<uint2*>(sm + TC_XL + sw128_off_h(row, 4 * kq)) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
             }
+            // token columns 56..63 of the bf16 plane must be ZERO: the region served as an E stage, and stale bits read as bf16 can be
+            // Inf / NaN, which a zero weight does not cancel (stale fp32 data in XH is always finite)
+            if (t < 256) *reinterpret_cast<uint2*>(sm + TC_XL + sw128_off_h(t & 127, 56 + 4 * (t >> 7))) = make_uint2(0u, 0u);
         }
         fence_async_smem(); __syncthreads();
         TC_STAMP();   /* 1: input staged */
@@ -279,16 +287,20 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 ph.wait(bars, B_WE); tc_fence_after();            // issuing thread only reaches its own epilogue work once all 42 MMAs are queued
 #pragma unroll 1
                 for (int mh = 0; mh < 2; mh++) {
+                    const uint32_t wa = estg_a + mh * 16384, dcol = tm + TC_DE + 128 * mh;
+                    // the two small terms first, in BF16 (K = 16 per MMA, 4 k-steps for the 56 tokens): W_lo . X and, unless the input is
+                    // the raw planes (block 0: exact, no lo part), W . X_lo; then the main term W_hi . X_hi in TF32 (7 k-steps)
 #pragma unroll 1
-                    for (int p = 0; p < 3; p++) {
-                        if (b == 0 && p == 1) continue;               // the raw planes have no lo part
-                        const uint32_t wa = estg_a + (p == 0 ? 2 * TC_WE_ATOM : 0) + mh * 16384;      // pass 0: W_lo X_hi, 1: W_hi X_lo, 2: W_hi X_hi
-                        const uint32_t xa = p == 1 ? xl_a : xh_a;
+                    for (int ks = 0; ks < 4; ks++)
+                        mma_f16(dcol, desc_sw128(wa + 3 * TC_WE_ATOM + ks * 32), desc_sw128(xl_a + ks * 32), IDH128, ks != 0);
+                    if (b != 0) {
 #pragma unroll 1
-                        for (int ks = 0; ks < 7; ks++)
-                            mma_tf32(tm + TC_DE + 128 * mh, desc_sw128(wa + (ks >> 2) * TC_WE_ATOM + (ks & 3) * 32),
-                                     desc_sw128(xa + (ks >> 2) * 16384 + (ks & 3) * 32), ID128, (p | ks) != 0);
+                        for (int ks = 0; ks < 4; ks++)
+                            mma_f16(dcol, desc_sw128(wa + 2 * TC_WE_ATOM + ks * 32), desc_sw128(xl_a + 16384 + ks * 32), IDH128, true);
                     }
+#pragma unroll 1
+                    for (int ks = 0; ks < 7; ks++)
+                        mma_tf32(dcol, desc_sw128(wa + (ks >> 2) * TC_WE_ATOM + (ks & 3) * 32), desc_sw128(xh_a + (ks >> 2) * 16384 + (ks & 3) * 32), ID128, true);
                     mma_commit(&bars[mh == 0 ? B_MMA : B_MM2]);      // channels 0-127 complete first: their depthwise pass overlaps the MMAs of 128-167
                 }
             }
@@ -306,24 +318,7 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
 #pragma unroll
                 for (int j = 0; j < 16; j++) xv[j] = __float_as_uint(__uint_as_float(dh[j]) + __uint_as_float(dl[j]) + (c0 + j < NV ? SV[SV_B0 + c0 + j] : 0.f));
                 tmem_st16(tlane + TC_T + c0, xv);
-            } else {   // While the expand MMAs run (they only READ X, and every warp would just wait for them): the block input (the residual of the
-                // project epilogue, and for the policy block also the input of the value block) is parked in spare TMEM columns as fp32.
-                // Once the MMAs are done that frees X's 64 KB of shared memory for the SE partial sums and as E stages 2 and 3.
-                const int row = 32 * q + lane, c0 = 16 * sub;
-                uint32_t xv[16];
-#pragma unroll
-                for (int j4 = 0; j4 < 4; j4++) {
-                    const int c = c0 + 4 * j4;
-                    float4 rh = make_float4(0.f, 0.f, 0.f, 0.f), rl = rh;
-                    if (c < NV) {
-                        const uint32_t o = (c >> 5) * 16384 + sw128_off(row, c & 31);
-                        rh = *reinterpret_cast<const float4*>(sm + TC_XH + o); rl = *reinterpret_cast<const float4*>(sm + TC_XL + o);
-                    }
-                    xv[4 * j4 + 0] = __float_as_uint(rh.x + rl.x); xv[4 * j4 + 1] = __float_as_uint(rh.y + rl.y);
-                    xv[4 * j4 + 2] = __float_as_uint(rh.z + rl.z); xv[4 * j4 + 3] = __float_as_uint(rh.w + rl.w);
-                }
-                tmem_st16(tlane + TC_T + c0, xv);
-            }
+            }   // (blocks 1 and 2 find their input already parked: block 0's project epilogue put the trunk output there)
             ph.wait(bars, B_MMA); tc_fence_after();
             TC_STAMP();   /* b1: expand MMAs (channels 0-127) done */
             // ---------------- depthwise pass (thread = channel) ----------------
@@ -525,6 +520,9 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                 uint32_t dh[16], dl[16], xr[16];
                 tmem_ld16(tlane + TC_DP + c0, dh); tmem_ld16(tlane + TC_DP + 64 + c0, dl); tmem_ld16(tlane + TC_T + c0, xr); tmem_wait_ld();
                 float* HO = reinterpret_cast<float*>(ESTG);
+                uint32_t yv[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) yv[j] = 0u;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; j4++) {
                     const int c = c0 + 4 * j4;
@@ -539,12 +537,23 @@ k_v80_tc(const float* __restrict__ P, const float* __restrict__ IMG, const __gri
                         }
                         if (b != 2) {                             // b == 0: the trunk output; b == 1: the trunk output again (X's planes served as E stages)
 #pragma unroll
-                            for (int j = 0; j < 4; j++) split_rn(y[j], hi[j], lo[j]);
+                            for (int j = 0; j < 4; j++) { split_rn(y[j], hi[j], lo[j]); yv[4 * j4 + j] = __float_as_uint(y[j]); }
                             *reinterpret_cast<float4*>(sm + TC_XH + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<float4*>(sm + TC_XL + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                            const uint32_t oh = sw128_off_h(row, c);
+                            const __nv_bfloat162 x0 = __floats2bfloat162_rn(y[0], y[1]), x1 = __floats2bfloat162_rn(y[2], y[3]), l0 = __floats2bfloat162_rn(lo[0], lo[1]), l1 = __floats2bfloat162_rn(lo[2], lo[3]);
+                            *reinterpret_cast<uint2*>(sm + TC_XL + oh) = make_uint2(*reinterpret_cast<const uint32_t*>(&x0), *reinterpret_cast<const uint32_t*>(&x1));
+                            *reinterpret_cast<uint2*>(sm + TC_XL + 16384 + oh) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
                         }
                     }
                 }
+                if (b != 2 && sub == 3) {                         // token columns 56..63 of both bf16 planes: zero (see the staging pass)
+#pragma unroll
+                    for (int cz = 56; cz < 64; cz += 4) {
+                        *reinterpret_cast<uint2*>(sm + TC_XL + sw128_off_h(row, cz)) = make_uint2(0u, 0u);
+                        *reinterpret_cast<uint2*>(sm + TC_XL + 16384 + sw128_off_h(row, cz)) = make_uint2(0u, 0u);
+                    }
+                }
+                if (b == 0) { tmem_st16(tlane + TC_T + c0, yv); tmem_wait_st(); }   // the trunk output is the input AND the residual of both head blocks: parked once, here
             }
             fence_async_smem(); tc_fence_before(); __syncthreads();
             TC_STAMP();   /* b6: project epilogue done */

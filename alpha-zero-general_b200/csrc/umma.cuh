@@ -34,6 +34,30 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// fp32 -> fp16 bits, round to nearest even, host side (operand images)
+inline uint16_t f32_to_f16_host(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u; const int e = (int)((u >> 23) & 0xFF) - 127 + 15; uint32_t m = u & 0x7FFFFFu;
+    if (e >= 31) return (uint16_t)(sign | 0x7BFFu);                // clamp (weights never get here)
+    if (e <= 0) {                                                  // subnormal or zero
+        if (e < -10) return (uint16_t)sign;
+        m |= 0x800000u; const int sh = 14 - e; uint32_t r = m >> sh; const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+        if (rem > half || (rem == half && (r & 1u))) r++;
+        return (uint16_t)(sign | r);
+    }
+    uint32_t r = ((uint32_t)e << 10) | (m >> 13); const uint32_t rem = m & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) r++;
+    return (uint16_t)(sign | r);
+}
+// byte offset of fp16 element (row r, k < 64) in a K-major 128-byte-swizzled atom ([rows][128 B])
+__host__ __device__ inline uint32_t sw128_off_h(int r, int k) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + ((k & 7) << 1)); }
+
+// the same with BF16 operands (a/b format 1): fp32's exponent range, 8-bit mantissa
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+inline uint16_t f32_to_bf16_host(float x) { uint32_t u; memcpy(&u, &x, 4); return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16); }   // round to nearest even
+
 // ---- mbarrier -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
