@@ -5,7 +5,9 @@
 // fp32 accumulators in TMEM.  The parity bar is 1e-5 on pi and v against the reference's fp32 forward, which one
 // TF32 pass cannot meet (2e-4 .. 1e-3 measured), so every GEMM is error-compensated: x = hi + lo with hi = x rounded
 // to TF32 and lo = x - hi (exact), and  D = W_lo X_hi + W_hi X_lo + W_hi X_hi  ("3xTF32", max error 2e-6 on the golden
-// vectors incl. the measured round-toward-zero accumulation of the tensor core, profiles/r01_umma_probe.txt).
+// vectors incl. the measured round-toward-zero accumulation of the tensor core, profiles/r01_umma_probe.txt). In the expand
+// GEMMs the two small terms (2^-12 of the main one) run as BF16 MMAs with K = 16 per instruction (W_lo . X and W . X_lo on
+// bf16 copies: 2^-20 of the main term); first_layer has no activation and is folded into the trunk block's expand weights.
 //
 // One persistent CTA per SM, 512 threads, one tile = 16 leaves = 128 "columns" (leaf, feature f<8; f = 7 is padding):
 //   * activations live in shared memory as K-major 128-byte-swizzled MMA operands  X[column][token]  (hi and lo planes)

@@ -12,8 +12,9 @@
 //   * one tile = 7 leaves = rows 14..269 = two M=128 accumulators in TMEM; 175 of the 256 rows are board cells (68 %)
 //   * the parity bar is 1e-5 against the reference's fp32 forward, so every GEMM is error-compensated like the V80 kernel ("3xTF32"):
 //     X is kept as two planes, H = the fp32 value itself (the tensor core truncates its operands to TF32) and L = x - trunc_tf32(x);
-//     W as W_hi = rn_tf32(w) and W_lo = w - W_hi stacked along N:  D[:, 0:64] = H W_hi + L W_hi,  D[:, 64:128] = H W_lo
-//     (one N=128 and one N=64 tcgen05.mma per 8-wide k-step: 76 + 49 cycles measured)
+//     W as W_hi = rn_tf32(w) and W_lo = w - W_hi stacked along N:  D[:, 0:64] = H W_hi,  D[:, 64:128] = H W_lo + L W
+//     (one N=128 TF32 MMA per 8-wide k-step; the small L W term runs as kind::f16 MMAs with FP16 operands, K = 16 per instruction:
+//     |L| < 2^-10 |x| keeps it to 2^-21 of the main product, and a TF32 MMA with N = 64 costs the same ~76 cycles as N = 128)
 //   * the accumulator lives in TMEM, so a layer's output overwrites its input IN PLACE in the epilogue (bias, residual, ReLU,
 //     zero at the pad rows, split into H / L); the block input (the residual) waits in a per-CTA scratch in global memory (L2)
 //   * the tensor core adds into its fp32 accumulator with round-toward-zero (profiles/r01_umma_probe.txt: -1.9e-8 relative per
@@ -21,7 +22,7 @@
 //     output. The chain is therefore cut: taps 0-4 and taps 5-8 go to two separate accumulators (all 512 TMEM columns are used:
 //     2 M tiles x 2 x 128), and the small L W_hi products go to the W_lo half of the columns, so the large H W_hi sums see 40 and 32
 //     truncating additions instead of 144; the epilogue adds the four parts in fp32 round-to-nearest
-//   * weights stream as pre-swizzled images, one 32 KB unit per tap, through a two-slot cp.async.bulk / mbarrier ring fed by a
+//   * weights stream as pre-swizzled images, one 40 KB unit per tap (TF32 W_hi | W_lo + an FP16 copy of W), through a two-slot cp.async.bulk / mbarrier ring fed by a
 //     producer thread that runs ahead of the MMA-issuing thread, across layer and tile boundaries
 //   * measured (profiles/r02_v89tc_phases.txt): a convolution's 288 MMAs take 21.8 k cycles = 92 B/clk of operand fetch + 13 B/clk of
 //     weight writes, which is the shared-memory rate the tensor core reaches in isolation (105-122 B/clk, csrc/probe); the MMA
