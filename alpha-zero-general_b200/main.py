@@ -16,38 +16,38 @@ from .utils import dotdict
 
 def build_parser():
     p = argparse.ArgumentParser(description='AlphaZero training loop on the B200 self-play engine (flags of the reference main.py)')
-    p.add_argument('game', action='store', default='splendor', help='The name of the game to simulate')
+    p.add_argument('game', action='store', default='splendor', help='game plugin: splendor, santorini, abalone or azul')
     p.add_argument('--checkpoint', '-C', action='store', default='./temp/', help='')
     p.add_argument('--load-folder-file', '-L', action='store', default=None, help='')
-    p.add_argument('--numEps', '-e', action='store', default=500, type=int, help='Number of complete self-play games to simulate during a new iteration')
+    p.add_argument('--numEps', '-e', action='store', default=500, type=int, help='finished self-play games per iteration')
     p.add_argument('--numItersHistory', '-i', action='store', default=5, type=int, help='')
-    p.add_argument('--numMCTSSims', '-m', action='store', default=1600, type=int, help='Number of moves for MCTS to simulate in FULL exploration')
-    p.add_argument('--tempThreshold', '-T', action='store', default=10, type=int, help='Nb of moves for half-life of temperature decay')
+    p.add_argument('--numMCTSSims', '-m', action='store', default=1600, type=int, help='simulations of a full search')
+    p.add_argument('--tempThreshold', '-T', action='store', default=10, type=int, help='half-life (in moves) of the move-sampling temperature')
     p.add_argument('--temperature', '-t', action='store', default=[1.0, 0.1, 1.1], type=float, nargs=3,
-                   help='Temperatures at begin/end, and softmax temp applied on root policy before Dirichlet')
-    p.add_argument('--cpuct', '-c', action='store', default=1.25, type=float, help='cpuct value')
-    p.add_argument('--dirichletAlpha', '-d', action='store', default=-1, type=float, help='0 to disable, negative for 10 / number of valid moves')
-    p.add_argument('--fpu', '-f', action='store', default=0., type=float, help='first play urgency: negative = absolute value, positive = parent-based reduction')
-    p.add_argument('--forced-playouts', '-F', action='store_true', help='Enabled forced playouts')
+                   help='sampling temperature at the start / at the end of a game, and the exponent applied to the root priors before the noise')
+    p.add_argument('--cpuct', '-c', action='store', default=1.25, type=float, help='exploration constant of PUCT')
+    p.add_argument('--dirichletAlpha', '-d', action='store', default=-1, type=float, help='Dirichlet alpha of the root noise: 0 = none, negative = 10 / number of legal moves')
+    p.add_argument('--fpu', '-f', action='store', default=0., type=float, help='first-play urgency: > 0 subtracts from the parent value, < 0 is used as is')
+    p.add_argument('--forced-playouts', '-F', action='store_true', help='forced playouts and policy-target pruning')
     p.add_argument('--learn-rate', '-l', action='store', default=0.0003, type=float, help='')
     p.add_argument('--epochs', '-p', action='store', default=2, type=int, help='')
     p.add_argument('--batch-size', '-b', action='store', default=32, type=int, help='')
-    p.add_argument('--dropout', '-D', action='store', default=0., type=float, help='Dropout value - advised to disable')
-    p.add_argument('--nn-version', '-V', action='store', default=None, type=int, help='Which architecture to choose (default: the one built for the game)')
-    p.add_argument('--q-weight', '-q', action='store', default=0.5, type=float, help='Weight for mixing Q into value loss')
-    p.add_argument('--updateThreshold', action='store', default=0.60, type=float, help='new net accepted if this share of the decisive arena games is won')
-    p.add_argument('--ratio-fullMCTS', action='store', default=5, type=int, help='Ratio of MCTS sims between full and fast exploration')
-    p.add_argument('--prob-fullMCTS', action='store', default=0.25, type=float, help='Probability to choose full MCTS exploration')
-    p.add_argument('--universes', '-u', action='store', default=1, type=int, choices=range(9), help='Number of universes (up to 8); 0 for a deterministic game')
-    p.add_argument('--forget-examples', action='store_true', help='Do not load previous examples')
+    p.add_argument('--dropout', '-D', action='store', default=0., type=float, help='dropout of the trunk during training')
+    p.add_argument('--nn-version', '-V', action='store', default=None, type=int, help='net architecture (default: the one built for the game)')
+    p.add_argument('--q-weight', '-q', action='store', default=0.5, type=float, help='share of the search value Q in the value target')
+    p.add_argument('--updateThreshold', action='store', default=0.60, type=float, help='share of the decisive arena games the new net must win')
+    p.add_argument('--ratio-fullMCTS', action='store', default=5, type=int, help='a fast search runs numMCTSSims / this')
+    p.add_argument('--prob-fullMCTS', action='store', default=0.25, type=float, help='probability that a move gets a full search (playout-cap randomisation)')
+    p.add_argument('--universes', '-u', action='store', default=1, type=int, choices=range(9), help='chance seeds the search cycles through (0 = deterministic game)')
+    p.add_argument('--forget-examples', action='store_true', help='with -L: do not load checkpoint.examples')
     p.add_argument('--numIters', '-n', action='store', default=50, type=int, help='')
-    p.add_argument('--stop-after-N-fail', '-s', action='store', default=-1, type=float, help='consecutive failed arenas that stop the loop (-N means N*numItersHistory)')
+    p.add_argument('--stop-after-N-fail', '-s', action='store', default=-1, type=float, help='stop after this many rejected nets in a row (-N = N * numItersHistory)')
     p.add_argument('--profile', action='store_true', help='self-play of one iteration only')
     p.add_argument('--debug', action='store_true', help='one game in flight, no compression, no tree clean-up')
     p.add_argument('--useray', action='store_true', help='accepted for compatibility (quieter output)')
     p.add_argument('--parallel-inferences', '-P', action='store', default=8, type=int, help='games in flight on the GPU = size of the inference batch')
     p.add_argument('--no-compression', action='store_true', help='keep examples uncompressed in memory and on disk')
-    p.add_argument('--no-mem-optim', action='store_true', help='Prevent cleaning MCTS tree of old moves during each game')
+    p.add_argument('--no-mem-optim', action='store_true', help='keep every tree node (no garbage collection between moves)')
     p.add_argument('--num-players', action='store', default=None, type=int, help='Splendor only: 2, 3 or 4 players')
     p.add_argument('--seed', action='store', default=0, type=int, help='seed of the device RNG streams')
     return p

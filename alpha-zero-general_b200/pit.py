@@ -16,10 +16,10 @@ from .utils import dotdict
 def build_parser():
     p = argparse.ArgumentParser(description='tester of AlphaZero nets on the B200 engine (flags of the reference pit.py)')
     p.add_argument('--num-games', '-n', action='store', default=30, type=int, help='')
-    p.add_argument('--numMCTSSims', '-m', action='store', default=None, type=int, help='Number of games moves for MCTS to simulate.')
-    p.add_argument('--cpuct', '-c', action='store', default=None, type=float, help='cpuct value')
-    p.add_argument('--fpu', '-f', action='store', default=None, type=float, help='Value for FPU (first play urgency)')
-    p.add_argument('game', action='store', default='splendor', help='The name of the game to play')
+    p.add_argument('--numMCTSSims', '-m', action='store', default=None, type=int, help='simulations per move (default: the setting stored in the first checkpoint)')
+    p.add_argument('--cpuct', '-c', action='store', default=None, type=float, help='exploration constant of PUCT')
+    p.add_argument('--fpu', '-f', action='store', default=None, type=float, help='first-play urgency')
+    p.add_argument('game', action='store', default='splendor', help='game plugin: splendor, santorini, abalone or azul')
     p.add_argument('players', metavar='player', nargs='*', help='two players: checkpoint files or "random"')
     p.add_argument('--num-players', action='store', default=None, type=int, help='Splendor only: 2, 3 or 4 players')
     p.add_argument('--universes', '-u', action='store', default=None, type=int, help='universes of the search (default: the checkpoint setting, else 1)')
